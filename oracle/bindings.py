@@ -1,0 +1,245 @@
+"""ctypes bindings for the CHECKERS: oracle/liboracle.so (our C restatement) and
+oracle/_ref/libyael_ref.so (the unmodified reference compiled by oracle/Makefile).
+
+TEST INFRASTRUCTURE ONLY.  Imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs; the product package (yael_b200) never imports it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "liboracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libyael_ref.so")
+
+DOT_F32_SEQ, DOT_F64 = 0, 1
+
+KMEANS_QUIET = 0x10000
+KMEANS_INIT_BERKELEY = 0x20000
+KMEANS_NORMALIZE_CENTS = 0x40000
+KMEANS_INIT_RANDOM = 0x80000
+KMEANS_INIT_USER = 0x100000
+
+_f = C.POINTER(C.c_float)
+_i = C.POINTER(C.c_int)
+_u8 = C.POINTER(C.c_uint8)
+_u16 = C.POINTER(C.c_uint16)
+
+
+def build(quiet=True):
+    """Compile liboracle.so (and _ref when the reference tree is present)."""
+    out = subprocess.run(["make", "-C", HERE], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + out.stdout + out.stderr)
+    if not quiet:
+        print(out.stdout)
+
+
+def fp(a):
+    return a.ctypes.data_as(_f) if a is not None else None
+
+
+def ip(a):
+    return a.ctypes.data_as(_i) if a is not None else None
+
+
+def u8p(a):
+    return a.ctypes.data_as(_u8) if a is not None else None
+
+
+def u16p(a):
+    return a.ctypes.data_as(_u16) if a is not None else None
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        if not os.path.exists(ORACLE_SO):
+            build()
+        L = C.CDLL(ORACLE_SO)
+        L.orc_cross_distances.argtypes = [C.c_int] * 3 + [_f, _f, _f, C.c_int]
+        L.orc_cross_distances_nonpacked.argtypes = [C.c_int] * 3 + [_f, C.c_int, _f, C.c_int, _f, C.c_int, C.c_int]
+        L.orc_distances_1.argtypes = [C.c_int, C.c_int, _f, _f, C.c_int, _f, C.c_int]
+        L.orc_knn_full.argtypes = [C.c_int] * 4 + [_f, _f, _f, _i, _f, C.c_int, C.c_int]
+        L.orc_knn_canonical.argtypes = [C.c_int] * 4 + [_f, _f, _i, _f, C.c_int, C.c_int]
+        L.orc_knn_reorder_shortlist.argtypes = [C.c_int] * 4 + [_f, _f, _i, _f, C.c_int]
+        L.orc_fvec_k_min.argtypes = [_f, C.c_int, _i, C.c_int]
+        L.orc_fvecs_k_min.argtypes = [_f, C.c_long, C.c_long, _i, C.c_int]
+        L.orc_fvec_k_min_canonical.argtypes = [_f, C.c_int, _i, C.c_int]
+        L.orc_kmeans.argtypes = [C.c_int] * 4 + [_f, C.c_int, C.c_long, C.c_int, _f, _f, _i, _i, C.c_int]
+        L.orc_kmeans.restype = C.c_float
+        L.orc_kmeans_step.argtypes = [C.c_int] * 3 + [_f, _f, _f, _i, _f, _i, C.c_int, C.c_int]
+        L.orc_kmeans_step.restype = C.c_double
+        L.orc_kmeans_reassign_empty.argtypes = [C.c_int] * 3 + [_f, _i, _i, C.c_uint]
+        L.orc_kmeans_reassign_empty.restype = C.c_int
+        L.orc_random_perm_r.argtypes = [C.c_int, C.c_uint]
+        L.orc_random_perm_r.restype = C.POINTER(C.c_int)
+        L.orc_fvec_randn_r.argtypes = [_f, C.c_long, C.c_uint]
+        L.orc_hamming.argtypes = [_u8, _u8, C.c_int]
+        L.orc_hamming.restype = C.c_uint16
+        L.orc_compute_hamming.argtypes = [_u16, _u8, _u8, C.c_int, C.c_int, C.c_int]
+        L.orc_nn_hamming.argtypes = [C.c_int] * 4 + [_u8, _u8, _i, _u16, C.c_int]
+        L.orc_match_hamming_count.argtypes = [_u8, _u8, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+        L.orc_match_hamming_thres_prealloc.argtypes = [_u8, _u8, C.c_int, C.c_int, C.c_int, C.c_int, _i, _u16]
+        L.orc_match_hamming_thres_prealloc.restype = C.c_size_t
+        _oracle = L
+    return _oracle
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    """The compiled, unmodified reference (prototypes: yael/nn.h:41-214, kmeans.h:41-44,
+    sorting.h:19-40, hamming.h:24-50, vector.h)."""
+    global _ref
+    if _ref is None:
+        os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")  # yael threads itself (README:161-162)
+        L = C.CDLL(REF_SO)
+        L.knn_full.argtypes = [C.c_int] * 5 + [_f, _f, _f, _i, _f]
+        L.knn_full_thread.argtypes = [C.c_int] * 5 + [_f, _f, _f, _i, _f, C.c_int]
+        L.knn_reorder_shortlist.argtypes = [C.c_int] * 4 + [_f, _f, _i, _f]
+        L.compute_cross_distances.argtypes = [C.c_int] * 3 + [_f, _f, _f]
+        L.compute_cross_distances_nonpacked.argtypes = [C.c_int] * 3 + [_f, C.c_int, _f, C.c_int, _f, C.c_int]
+        L.compute_distances_1.argtypes = [C.c_int, C.c_int, _f, _f, _f]
+        L.kmeans.argtypes = [C.c_int] * 4 + [_f, C.c_int, C.c_long, C.c_int, _f, _f, _i, _i]
+        L.kmeans.restype = C.c_float
+        L.fvec_k_min.argtypes = [_f, C.c_int, _i, C.c_int]
+        L.fvecs_k_min.argtypes = [_f, C.c_long, C.c_long, _i, C.c_int]
+        L.compute_hamming.argtypes = [_u16, _u8, _u8, C.c_int, C.c_int, C.c_int]
+        L.match_hamming_count.argtypes = [_u8, _u8, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+        L.match_hamming_thres_prealloc.argtypes = [_u8, _u8, C.c_int, C.c_int, C.c_int, C.c_int, _i, _u16]
+        L.match_hamming_thres_prealloc.restype = C.c_size_t
+        L.ivec_new_random_perm_r.argtypes = [C.c_int, C.c_uint]
+        L.ivec_new_random_perm_r.restype = C.POINTER(C.c_int)
+        L.fvec_randn_r.argtypes = [_f, C.c_long, C.c_uint]
+        L.count_cpu.restype = C.c_int
+        _ref = L
+    return _ref
+
+
+# ---------------------------------------------------------------- numpy conveniences
+
+
+def orc_knn(base, query, k, dot_mode=DOT_F32_SEQ, nt=8, canonical=False, weights=None):
+    base, query = f32(base), f32(query)
+    nq, d = query.shape
+    nb = base.shape[0]
+    idx = np.empty((nq, k), np.int32)
+    dis = np.empty((nq, k), np.float32)
+    if canonical:
+        oracle().orc_knn_canonical(nq, nb, d, k, fp(base), fp(query), ip(idx), fp(dis), dot_mode, nt)
+    else:
+        w = f32(weights) if weights is not None else None
+        oracle().orc_knn_full(nq, nb, d, k, fp(base), fp(query), fp(w), ip(idx), fp(dis), dot_mode, nt)
+    return idx, dis
+
+
+def ref_knn(base, query, k, nt=8, weights=None):
+    base, query = f32(base), f32(query)
+    nq, d = query.shape
+    nb = base.shape[0]
+    idx = np.empty((nq, k), np.int32)
+    dis = np.empty((nq, k), np.float32)
+    w = f32(weights) if weights is not None else None
+    ref().knn_full_thread(2, nq, nb, d, k, fp(base), fp(query), fp(w), ip(idx), fp(dis), nt)
+    return idx, dis
+
+
+def orc_cross(a, b, dot_mode=DOT_F32_SEQ):
+    a, b = f32(a), f32(b)
+    out = np.empty((b.shape[0], a.shape[0]), np.float32)
+    oracle().orc_cross_distances(a.shape[1], a.shape[0], b.shape[0], fp(a), fp(b), fp(out), dot_mode)
+    return out
+
+
+def ref_cross(a, b):
+    a, b = f32(a), f32(b)
+    out = np.empty((b.shape[0], a.shape[0]), np.float32)
+    ref().compute_cross_distances(a.shape[1], a.shape[0], b.shape[0], fp(a), fp(b), fp(out))
+    return out
+
+
+def _kmeans_call(fn, v, k, niter, flags, seed, redo, init, extra):
+    v = f32(v)
+    n, d = v.shape
+    cent = np.zeros((k, d), np.float32)
+    if init is not None:
+        cent[:] = init
+    dis = np.empty(n, np.float32)
+    assign = np.empty(n, np.int32)
+    nassign = np.empty(k, np.int32)
+    q = fn(d, n, k, niter, fp(v), flags, seed, redo, fp(cent), fp(dis), ip(assign), ip(nassign), *extra)
+    return q, cent, dis, assign, nassign
+
+
+def orc_kmeans(v, k, niter, flags, seed, redo=1, init=None, dot_mode=DOT_F32_SEQ):
+    return _kmeans_call(oracle().orc_kmeans, v, k, niter, flags, seed, redo, init, (dot_mode,))
+
+
+def ref_kmeans(v, k, niter, flags, seed, redo=1, init=None):
+    return _kmeans_call(ref().kmeans, v, k, niter, flags, seed, redo, init, ())
+
+
+def orc_kmeans_step(v, cent, dot_mode=DOT_F32_SEQ, nt=8):
+    v, cent = f32(v), f32(cent)
+    n, d = v.shape
+    k = cent.shape[0]
+    out = np.empty_like(cent)
+    assign = np.empty(n, np.int32)
+    dis = np.empty(n, np.float32)
+    nassign = np.empty(k, np.int32)
+    q = oracle().orc_kmeans_step(d, n, k, fp(v), fp(cent), fp(out), ip(assign), fp(dis), ip(nassign), dot_mode, nt)
+    return q, out, assign, dis, nassign
+
+
+def orc_nn_hamming(base, query, k, nt=8):
+    base = np.ascontiguousarray(base, np.uint8)
+    query = np.ascontiguousarray(query, np.uint8)
+    nq, nc = query.shape
+    idx = np.empty((nq, k), np.int32)
+    dis = np.empty((nq, k), np.uint16)
+    oracle().orc_nn_hamming(nq, base.shape[0], nc, k, u8p(base), u8p(query), ip(idx), u16p(dis), nt)
+    return idx, dis
+
+
+def orc_compute_hamming(a, b):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    out = np.empty((b.shape[0], a.shape[0]), np.uint16)
+    oracle().orc_compute_hamming(u16p(out), u8p(a), u8p(b), a.shape[0], b.shape[0], a.shape[1])
+    return out
+
+
+def ref_compute_hamming(a, b):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    out = np.empty((b.shape[0], a.shape[0]), np.uint16)
+    ref().compute_hamming(u16p(out), u8p(a), u8p(b), a.shape[0], b.shape[0], a.shape[1])
+    return out
+
+
+def orc_k_min(val, k, canonical=False):
+    val = f32(val)
+    idx = np.empty(k, np.int32)
+    fn = oracle().orc_fvec_k_min_canonical if canonical else oracle().orc_fvec_k_min
+    fn(fp(val), val.shape[0], ip(idx), k)
+    return idx
+
+
+def ref_k_min(val, k):
+    val = f32(val)
+    idx = np.empty(k, np.int32)
+    ref().fvec_k_min(fp(val), val.shape[0], ip(idx), k)
+    return idx
