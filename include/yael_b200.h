@@ -1,0 +1,154 @@
+/*
+ * yael_b200.h -- device-level C ABI of libyael_b200.so.
+ *
+ * Two layers are exported by the library:
+ *
+ *  1. The DROP-IN layer: yael's own C prototypes (include/yael/*.h -- knn_full,
+ *     knn_full_thread, compute_cross_distances, fvec_k_min, kmeans, compute_hamming,
+ *     nn_hamming ...).  Host pointers in, host pointers out, exactly what a program
+ *     linked against the reference's libyael.so binds (yael/Makefile:31-39).
+ *
+ *  2. This layer (prefix yb_): the same operations on DEVICE pointers and a caller
+ *     stream, used by the drop-in layer itself (yael_b200/csrc/host/*.c), by the
+ *     multi-GPU plumbing (yael_b200/dist.py hands in torch tensors' data_ptr()) and by
+ *     bench.py's HBM-resident timing.  Plain C: pointers, sizes, an opaque stream
+ *     handle (cudaStream_t passed as void*).  No C++ or torch types.
+ *
+ * Conventions: every yb_ function returns 0 on success and a non-zero code on failure
+ * (yb_last_error() describes it); nothing here falls back to the CPU.  Vectors are
+ * row-major [n][d] float (yael/vector.h:32-42, yael/nn.h:15-23).  Indices are int.
+ */
+#ifndef YAEL_B200_H
+#define YAEL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *yb_stream_t; /* cudaStream_t; NULL = the library's own per-device stream */
+
+/* ---- runtime ------------------------------------------------------------------ */
+const char *yb_version(void);
+const char *yb_last_error(void);
+int yb_device_count(void);            /* <0 if the CUDA runtime is unusable            */
+int yb_set_device(int dev);           /* device used by subsequent calls of this thread */
+int yb_sync(yb_stream_t s);           /* cudaStreamSynchronize on s (or the own stream) */
+/* number of kernels this library launched since the last reset (bench.py: gpu_launches) */
+long yb_launch_count(int reset);
+/* which kNN engine the last yb_knn_l2 call used: 1 = tcgen05 TF32 shortlist + FP32 re-rank,
+ * 0 = exact FP32 SIMT path; and how many queries failed the shortlist certificate and were
+ * re-done by the exact path */
+int yb_last_knn_engine(void);
+long yb_last_knn_uncertified(void);
+/* force an engine for testing: -1 auto (default), 0 exact SIMT only, 1 TF32 whenever legal */
+void yb_set_knn_engine(int engine);
+
+/* device memory helpers for C callers.  yb_malloc/yb_free go through a small caching pool
+ * (freed blocks are kept for reuse; yb_release_scratch() returns them to the driver);
+ * allocation failure prints a message and aborts, as the reference's allocators do
+ * (yael/vector.c:37-40). */
+void *yb_malloc(size_t bytes);
+void yb_free(void *p);
+int yb_is_device_ptr(const void *p); /* 1: device/managed memory, 0: host memory */
+/* gather rows: dst[i][:] = src[rows[i]][:] (all device pointers) */
+int yb_gather_rows(const float *src, const int *rows, int n, int d, float *dst, yb_stream_t s);
+int yb_h2d(void *dst, const void *src, size_t bytes, yb_stream_t s);
+int yb_d2h(void *dst, const void *src, size_t bytes, yb_stream_t s);
+void yb_release_scratch(void); /* drop the cached workspace of the current device */
+
+/* ---- distances: yael/nn.c:92-162 ---------------------------------------------- */
+/* dist2[i + ldd*j] = fl32(fl64(|b_j|^2) + fl32(|a_i|^2)) - 2 <a_i,b_j>, the dot product
+ * accumulated as a sequential FP32 FMA chain over the coordinates (the order the
+ * reference's sgemm micro-kernel uses).  Replaces
+ * compute_cross_distances_nonpacked (yael/nn.c:100-129). */
+int yb_cross_distances_l2(int d, int na, int nb, const float *a, int lda, const float *b,
+                          int ldb, float *dist2, int ldd, yb_stream_t s);
+/* dist2[j] for one query a[d] against nb rows, both norms in double:
+ * compute_distances_1_nonpacked (yael/nn.c:132-154). */
+int yb_distances_1(int d, int nb, const float *a, const float *b, int ldb, float *dist2,
+                   yb_stream_t s);
+/* alternative distances, compute_cross_distances_alt_nonpacked (yael/nn.c:280-350):
+ * 1 L1, 2 L2 (double accumulation), 3 chi2, 4 chi2 |.|, 5 hist. intersection, 6 dot,
+ * 12 = yb_cross_distances_l2, 16 = dot product as FP32 FMA chain. */
+int yb_cross_distances_alt(int distance_type, int d, int na, int nb, const float *a, int lda,
+                           const float *b, int ldb, float *dist2, int ldd, yb_stream_t s);
+
+/* ---- exact k-NN: knn_full (yael/nn.c:451-525), nn_single_full (yael/nn.c:383-446) -- */
+/* base[nb][d], query[nq][d] -> assign[nq][k] (ids + id_offset), dis[nq][k] ascending by
+ * (distance, id); NaN distances are never selected; short lists are padded with id -1 and
+ * distance bits 0xffffffff (yael/nn.c:515-518).  b_weights (device, may be NULL) multiplies
+ * the squared distances per base vector (yael/nn.c:497-500).  k == 1 follows nn_single_full:
+ * strict '<' from (-1, 1e30), lowest id on ties. */
+int yb_knn_l2(int nq, int nb, int d, int k, const float *base, const float *query,
+              const float *b_weights, int *assign, float *dis, int id_offset, yb_stream_t s);
+/* merge G per-shard results laid out [G][nq][k] into [nq][k] by (distance, id); padded
+ * entries (id < 0) sort last.  The exchange step of the sharded k-NN. */
+int yb_knn_merge(int nq, int k, int G, const int *assign_in, const float *dis_in,
+                 int *assign_out, float *dis_out, yb_stream_t s);
+/* knn_reorder_shortlist (yael/nn.c:528-580): exact one-vs-many distances for the listed
+ * ids (stop at the first id < 0), re-ordered ascending by (distance, position). */
+int yb_knn_reorder_shortlist(int nq, int nb, int d, int k, const float *base,
+                             const float *query, int *idx, float *dis, yb_stream_t s);
+
+/* ---- k smallest: fvec_k_min / fvecs_k_min (yael/sorting.c:191-255) ---------------- */
+/* nrow arrays of length n (row stride ld) -> idx[nrow][k] (+ optional vals[nrow][k]),
+ * ascending by (value, index); sign = +1 for k-min, -1 for k-max (values negated as the
+ * reference does, yael/sorting.c:153). */
+int yb_k_min_rows(const float *val, long n, long ld, long nrow, int k, int sign, int *idx,
+                  float *vals, yb_stream_t s);
+
+/* ---- k-means building blocks: kmeans_core (yael/kmeans.c:213-329) ----------------- */
+/* nassign[k] histogram + centroid sums[k][d] (strict point order inside each centroid when
+ * exact_order != 0, as yael/kmeans.c:278-283) + qerr = sum of dis as double
+ * (yael/kmeans.c:310).  Outputs are UNSCALED sums so a sharded run can all-reduce them. */
+int yb_kmeans_accumulate(int d, int n, int k, const float *v, const int *assign,
+                         const float *dis, float *sums, int *nassign, double *qerr,
+                         int exact_order, yb_stream_t s);
+/* centroids[j][t] = (float)((double)sums[j][t] * (1.0 / nassign[j])) (yael/kmeans.c:286-288,
+ * yael/vector.c:1792-1797); optional L2 normalisation (yael/kmeans.c:291-293). */
+int yb_kmeans_scale(int d, int k, const float *sums, const int *nassign, float *centroids,
+                    int normalize, yb_stream_t s);
+
+/* hooks for the sharded k-means: called by the host loop after the local accumulation
+ * with DEVICE pointers; must leave the global sums in place on every rank */
+typedef struct {
+  void *ctx;
+  /* returns 0 on success */
+  int (*allreduce_sums)(void *ctx, float *sums, long n_float, int *nassign, long n_int,
+                        double *qerr, yb_stream_t s);
+  long n_total; /* global number of points (0 = n) */
+} yb_kmeans_comm_t;
+
+/* kmeans (yael/kmeans.c:332-447) on a device-resident v[n][d]; every other argument as the
+ * reference's (host pointers; centroids is also the input under KMEANS_INIT_USER).  With
+ * comm != NULL the points are this rank's shard and the init must be KMEANS_INIT_USER. */
+float yb_kmeans_dev(int d, int n, int k, int niter, const float *v_dev, int flags, long seed,
+                    int redo, float *centroids, float *dis, int *assign, int *nassign,
+                    const yb_kmeans_comm_t *comm, yb_stream_t s);
+
+/* ---- Hamming: yael/hamming.c:66-219 ------------------------------------------------ */
+/* dis[j*na + i] = popcount(a_i xor b_j), uint16 (compute_hamming, yael/hamming.c:177-219) */
+int yb_compute_hamming(uint16_t *dis, const uint8_t *a, const uint8_t *b, int na, int nb,
+                       int ncodes, yb_stream_t s);
+/* NEW (not in the reference): k smallest Hamming distances per query ordered by
+ * (distance, id); padding id -1 / distance 0xffff. */
+int yb_nn_hamming(int nq, int nb, int ncodes, int k, const uint8_t *base, const uint8_t *query,
+                  int *assign, uint16_t *dis, int id_offset, yb_stream_t s);
+int yb_nn_hamming_merge(int nq, int k, int G, const int *assign_in, const uint16_t *dis_in,
+                        int *assign_out, uint16_t *dis_out, yb_stream_t s);
+/* match_hamming_count / match_hamming_thres_prealloc (yael/hamming.c:283-300, 563-700):
+ * pairs with distance <= ht, emitted query-major / base-ascending.  count is a device
+ * size_t; idx receives (qid, bid) interleaved. */
+int yb_match_hamming_count(const uint8_t *bs1, const uint8_t *bs2, int n1, int n2, int ht,
+                           int ncodes, unsigned long long *count, yb_stream_t s);
+int yb_match_hamming_thres(const uint8_t *bs1, const uint8_t *bs2, int n1, int n2, int ht,
+                           int ncodes, int *idx, uint16_t *hams, unsigned long long *count,
+                           yb_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,199 @@
+"""GPU parity of the exact FP32 path (engine 0) against the oracle, through the C ABI.
+
+Bar: bit-exact for everything this path computes -- the distance kernels reproduce the
+reference's rounding sequence (sequential FP32 FMA dot product, float / double norms), and
+selection is defined as (value, id) order, which the oracle's canonical variants restate.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def rs(seed):
+    return np.random.RandomState(seed)
+
+
+@pytest.fixture(autouse=True)
+def _exact_engine():
+    import yael_b200
+    yael_b200.lib().yb_set_knn_engine(0)
+    yield
+    yael_b200.lib().yb_set_knn_engine(-1)
+
+
+@pytest.mark.parametrize("na,nb,d", [(300, 200, 64), (65, 129, 128), (1, 1, 1), (130, 7, 3),
+                                     (257, 255, 96), (64, 64, 37)])
+def test_cross_distances_bit_exact(yn, ob, na, nb, d):
+    r = rs(na * 1000 + nb)
+    a = r.rand(na, d).astype(np.float32)
+    b = r.rand(nb, d).astype(np.float32)
+    got = yn.cross_distances(a, b)
+    want = ob.orc_cross(a, b, ob.DOT_F32_SEQ)
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("dtype", [1, 2, 3, 4, 5, 6, 16])
+@pytest.mark.parametrize("d", [8, 13])
+def test_cross_distances_alt(yn, ob, dtype, d):
+    r = rs(dtype * 10 + d)
+    a = r.rand(40, d).astype(np.float32)
+    b = r.rand(33, d).astype(np.float32)
+    got = yn.cross_distances(a, b, dtype)
+    if ob.have_ref():
+        L = ob.ref()
+        import ctypes as C
+        want = np.empty((33, 40), np.float32)
+        L.compute_cross_distances_alt_nonpacked = L.compute_cross_distances_alt_nonpacked
+        L.compute_cross_distances_alt_nonpacked.argtypes = [C.c_int] * 4 + [
+            C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float), C.c_int]
+        L.compute_cross_distances_alt_nonpacked(dtype, d, 40, 33, ob.fp(a), d, ob.fp(b), d, ob.fp(want), 40)
+        if dtype == 16:  # sgemm: accumulation order of the BLAS edge kernels is not pinned
+            np.testing.assert_allclose(got, want, rtol=1e-6)
+        else:
+            assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("nq,nb,d,k", [(100, 5000, 128, 1), (100, 5000, 128, 10), (33, 777, 96, 100),
+                                        (5, 100, 16, 100), (257, 3000, 20, 7), (10, 70000, 32, 50)])
+def test_knn_exact_engine(yn, ob, nq, nb, d, k):
+    r = rs(nq + nb + k)
+    b = r.rand(nb, d).astype(np.float32)
+    q = r.rand(nq, d).astype(np.float32)
+    idx, dis = yn.knn(q, b, k)
+    widx, wdis = ob.orc_knn(b, q, k, ob.DOT_F32_SEQ, canonical=True)
+    assert np.array_equal(dis.view(np.uint32), wdis.view(np.uint32))
+    assert np.array_equal(idx, widx)
+
+
+def test_knn_integer_ties_and_padding(yn, ob):
+    r = rs(5)
+    b = r.randint(0, 3, (500, 8)).astype(np.float32)
+    q = r.randint(0, 3, (40, 8)).astype(np.float32)
+    for k in (1, 3, 60):
+        idx, dis = yn.knn(q, b, k)
+        widx, wdis = ob.orc_knn(b, q, k, canonical=True)
+        assert np.array_equal(idx, widx) and np.array_equal(dis, wdis)
+        # the reference (heap tie order) returns the same distance multiset
+        hidx, hdis = ob.orc_knn(b, q, k)
+        assert np.array_equal(dis, hdis)
+    # NaN rows are never selected, short lists padded with -1 / all-ones bits (nn.c:515-518)
+    b2 = b.copy()
+    b2[1::2] = np.nan
+    idx, dis = yn.knn(q, b2, 300)
+    widx, wdis = ob.orc_knn(b2, q, 300)
+    assert (idx[:, 250:] == -1).all() and (widx[:, 250:] == -1).all()
+    assert (dis[:, 250:].view(np.uint32) == 0xFFFFFFFF).all()
+    assert np.array_equal(dis[:, :250], wdis[:, :250])
+
+
+def test_knn_weights(yn, ob):
+    r = rs(6)
+    b = r.rand(2000, 24).astype(np.float32)
+    q = r.rand(50, 24).astype(np.float32)
+    w = (0.5 + r.rand(2000)).astype(np.float32)
+    idx, dis = yn.knn_weighted(q, b, w, 5)
+    widx, wdis = ob.orc_knn(b, q, 5, weights=w)
+    assert np.array_equal(idx, widx) and np.array_equal(dis, wdis)
+
+
+@pytest.mark.parametrize("n,k", [(100000, 1), (100000, 7), (100000, 100), (1000, 100), (50, 50),
+                                 (30000, 5000)])
+def test_k_min(yn, ob, n, k):
+    r = rs(n + k)
+    v = r.rand(3, n).astype(np.float32)
+    v[1] = r.randint(0, 50, n)  # heavy ties
+    got = yn.kmin(v, k)
+    for i in range(3):
+        want = ob.orc_k_min(v[i], k, canonical=True)
+        assert np.array_equal(got[i], want)
+    gotmax = yn.kmax(v, k)
+    for i in range(3):
+        want = ob.orc_k_min(-v[i], k, canonical=True)
+        assert np.array_equal(gotmax[i], want)
+
+
+def test_k_min_is_prefix_of_full_sort(yn):
+    # the reference's own check, test/matlab/test_kmin.m:20
+    r = rs(11)
+    v = r.rand(4, 20000).astype(np.float32)
+    got = yn.kmin(v, 100)
+    for i in range(4):
+        assert np.array_equal(got[i], np.argsort(v[i], kind="stable")[:100])
+
+
+@pytest.mark.parametrize("nc", [4, 8, 16, 24, 5, 64])
+def test_compute_hamming(yn, ob, nc):
+    r = rs(nc)
+    a = r.randint(0, 256, (70, nc)).astype(np.uint8)
+    b = r.randint(0, 256, (50, nc)).astype(np.uint8)
+    assert np.array_equal(yn.hamming_distances(a, b), ob.orc_compute_hamming(a, b))
+
+
+@pytest.mark.parametrize("nq,nb,nc,k", [(300, 20000, 8, 100), (10, 5000, 16, 7), (700, 3000, 4, 1),
+                                         (5, 100, 8, 100), (64, 40000, 32, 33), (3, 1000, 5, 10)])
+def test_nn_hamming_bit_exact(yn, ob, nq, nb, nc, k):
+    r = rs(nq + nb)
+    b = r.randint(0, 256, (nb, nc)).astype(np.uint8)
+    q = r.randint(0, 256, (nq, nc)).astype(np.uint8)
+    b[::17] = q[0]  # planted duplicates: distance-0 ties resolved by id
+    idx, dis = yn.knn_hamming(q, b, k)
+    widx, wdis = ob.orc_nn_hamming(b, q, k)
+    assert np.array_equal(dis, wdis)
+    assert np.array_equal(idx, widx)
+
+
+def test_match_hamming_self_consistency(yn, ob):
+    # test/matlab/test_hamming.m:5-22: thresholded output == filtered full matrix
+    r = rs(3)
+    a = r.randint(0, 256, (80, 8)).astype(np.uint8)
+    b = r.randint(0, 256, (1000, 8)).astype(np.uint8)
+    full = yn.hamming_distances(a, b)  # [nb][na]
+    for ht in (0, 20, 26, 64):
+        pairs, scores = yn.match_hamming(a, b, ht)
+        qi, bj = np.nonzero(full.T <= ht)  # query-major, base ascending
+        assert np.array_equal(pairs[:, 0], qi) and np.array_equal(pairs[:, 1], bj)
+        assert np.array_equal(scores, full.T[qi, bj])
+
+
+def test_kmeans_step_teacher_forced(yn, ob):
+    r = rs(1234)
+    v = r.rand(20000, 32).astype(np.float32)
+    c0 = v[r.permutation(20000)[:64]].copy()
+    cent, qerr, dis, assign, nassign = yn.kmeans(v, 64, niter=1, verbose=False, init=c0, output="all")
+    q, wc, wa, wd, wn = ob.orc_kmeans_step(v, c0)
+    assert np.array_equal(assign, wa) and np.array_equal(nassign, wn)
+    assert np.array_equal(dis.view(np.uint32), wd.view(np.uint32))
+    np.testing.assert_allclose(cent, wc, rtol=0, atol=1e-6)
+    assert abs(qerr - q / 20000) < 1e-5 * qerr
+
+
+def test_kmeans_full_matches_oracle_small(yn, ob):
+    r = rs(99)
+    v = r.rand(5000, 16).astype(np.float32)
+    import os
+    os.environ["YAEL_B200_EXACT_UPDATE"] = "1"
+    try:
+        got = yn.kmeans(v, 32, niter=12, seed=777, verbose=False, output="all", nt=4)
+    finally:
+        del os.environ["YAEL_B200_EXACT_UPDATE"]
+    want = ob.orc_kmeans(v, 32, 12, ob.KMEANS_QUIET | 4, 777)
+    # exact-order update + bit-exact assignment => the whole trajectory is identical
+    assert np.array_equal(got[0], want[1])
+    assert np.array_equal(got[3], want[3]) and np.array_equal(got[4], want[4])
+    assert got[1] == pytest.approx(want[0], rel=1e-6)
+
+
+def test_kmeans_empty_cluster_split(yn, ob):
+    r = rs(5)
+    v = np.repeat(r.rand(30, 8).astype(np.float32), 50, axis=0)
+    import os
+    os.environ["YAEL_B200_EXACT_UPDATE"] = "1"
+    try:
+        got = yn.kmeans(v, 40, niter=10, seed=5, verbose=False, output="all")
+    finally:
+        del os.environ["YAEL_B200_EXACT_UPDATE"]
+    want = ob.orc_kmeans(v, 40, 10, ob.KMEANS_QUIET | 1, 5)
+    assert np.array_equal(got[4], want[4])
+    assert np.array_equal(got[0], want[1])

@@ -1,0 +1,499 @@
+// yb_hamming.cu -- popcount Hamming kernels over packed codes (yael/hamming.c).
+//
+//   k_compute_hamming   full uint16 matrix, dis[j*na+i] (compute_hamming, hamming.c:177-219)
+//   k_nn_hamming_scan   NEW nn_hamming: streaming k-smallest per query, (distance, id) order.
+//                       Thread-owns-query: each thread keeps QT query codes in registers, the
+//                       CTA stages database codes through shared memory with 128-bit loads,
+//                       every (query, code) pair costs xor + popc; candidates below the
+//                       query's running threshold are appended to a lane-interleaved list
+//                       that is compacted in lock-step by a bisection on the distance value
+//                       (distances are small integers, so 7 counting passes find the pivot).
+//   k_nn_hamming_merge  merges the per-split (or per-GPU) lists: 64-bit (distance,id) sort.
+//   k_match_*           threshold matching (match_hamming_count / _thres_prealloc,
+//                       hamming.c:224-300, 563-700).
+//
+// The scan is popcount-pipe bound at the BASELINE shape (1e11 pairs), not HBM bound: the
+// algorithmic bytes are 86 MB ("Hamming roofline").
+#include "yb_common.cuh"
+#include "yb_internal.cuh"
+
+namespace yb {
+
+constexpr int HT = 128;    // threads per CTA in the scan
+constexpr int HQT = 2;     // queries per thread
+constexpr int HTILE = 1024;  // nominal tile (codes) used for split sizing
+constexpr int HTILE_WORDS = 4096;  // 64-bit words staged per tile (32 KB)
+
+// repack codes of `ncodes` bytes into W 64-bit words each (zero padded)
+__global__ void k_ham_pack(const uint8_t *__restrict__ src, long n, int ncodes, int W,
+                           unsigned long long *__restrict__ dst) {
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * W) return;
+  long row = t / W;
+  int w = (int)(t - row * W);
+  unsigned long long v = 0;
+  for (int b = 0; b < 8; b++) {
+    int byte = w * 8 + b;
+    if (byte < ncodes) v |= (unsigned long long)src[row * ncodes + byte] << (8 * b);
+  }
+  dst[t] = v;
+}
+
+template <int W>
+__global__ void __launch_bounds__(256)
+k_compute_hamming(uint16_t *__restrict__ dis, const unsigned long long *__restrict__ a,
+                  const unsigned long long *__restrict__ b, long na, long nb) {
+  // thread per a-row (fast output dimension), 8 b-rows per CTA row
+  const long i = (long)blockIdx.x * 32 + (threadIdx.x & 31);
+  const long j = (long)blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (i >= na || j >= nb) return;
+  int h = 0;
+#pragma unroll
+  for (int w = 0; w < W; w++) h += __popcll(a[i * W + w] ^ b[j * W + w]);
+  dis[j * na + i] = (uint16_t)h;
+}
+
+// ---------------------------------------------------------------------------------------
+// lists: entry e of query slot (thread t, qq) of CTA (bx, by) lives at
+//   lists[(((by * gridDim.x + bx) * HQT + qq) * cap + e) * HT + t]
+// as (distance << 32 | id); counts[...] the number of valid entries.
+// ---------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(HT)
+k_nn_hamming_scan(int nq, long nb, int k, int cap, const unsigned long long *__restrict__ base,
+                  const unsigned long long *__restrict__ query, long split_len,
+                  unsigned long long *__restrict__ lists, int *__restrict__ counts,
+                  int id_offset) {
+  constexpr int TC = HTILE_WORDS / W;  // codes per tile
+  __shared__ __align__(16) unsigned long long tile[HTILE_WORDS];
+  const int tid = threadIdx.x;
+  const long b0 = (long)blockIdx.y * split_len;
+  const long b1 = min(nb, b0 + split_len);
+
+  unsigned long long qc[HQT][W];
+  int thr[HQT], cnt[HQT];
+  unsigned long long *my[HQT];
+#pragma unroll
+  for (int qq = 0; qq < HQT; qq++) {
+    long q = ((long)blockIdx.x * HQT + qq) * HT + tid;
+#pragma unroll
+    for (int w = 0; w < W; w++) qc[qq][w] = q < nq ? query[q * W + w] : 0ull;
+    thr[qq] = q < nq ? 0x7fffffff : -1;  // inactive slots never admit anything
+    cnt[qq] = 0;
+    my[qq] = lists + ((((size_t)blockIdx.y * gridDim.x + blockIdx.x) * HQT + qq) * cap) * HT + tid;
+  }
+
+  // lock-step compaction of every lane's list down to the k smallest (distance, id)
+  auto compact = [&](int qq) {
+    const int n = cnt[qq];
+    int lo = 0, hi = 64 * W;  // smallest p with count(dist <= p) >= k
+    const bool active = n > k;
+    while (__any_sync(0xffffffffu, active && lo < hi)) {
+      int mid = (lo + hi) >> 1, c = 0;
+      const int nmax = __reduce_max_sync(0xffffffffu, active ? n : 0);
+      for (int e = 0; e < nmax; e++)
+        if (e < n && (int)(my[qq][(size_t)e * HT] >> 32) <= mid) c++;
+      if (active && lo < hi) {
+        if (c >= k) hi = mid; else lo = mid + 1;
+      }
+    }
+    if (active) {
+      // keep everything below the pivot and the first (lowest-id) ties; list order == id
+      // order because each thread streams the database in increasing id order
+      int below = 0;
+      for (int e = 0; e < n; e++) below += ((int)(my[qq][(size_t)e * HT] >> 32) < lo);
+      int ties = k - below, out = 0;
+      for (int e = 0; e < n; e++) {
+        unsigned long long v = my[qq][(size_t)e * HT];
+        int dist = (int)(v >> 32);
+        bool keep = dist < lo || (dist == lo && ties > 0);
+        if (dist == lo && ties > 0) ties--;
+        if (keep) my[qq][(size_t)(out++) * HT] = v;
+      }
+      cnt[qq] = out;
+      thr[qq] = lo;  // a later code at distance == lo has a higher id than every kept tie
+    }
+  };
+
+  for (long t0 = b0; t0 < b1; t0 += TC) {
+    const int tn = (int)min((long)TC, b1 - t0);
+    __syncthreads();
+    {  // stage: 128-bit loads, two 64-bit words per load
+      const int words = tn * W;
+      const unsigned long long *src = base + t0 * W;
+      if ((((uintptr_t)src) & 15) == 0) {
+        for (int x = tid * 2; x < words; x += HT * 2) {
+          if (x + 1 < words) {
+            uint4 v = ld_stream_u4(src + x);
+            *reinterpret_cast<uint4 *>(&tile[x]) = v;
+          } else {
+            tile[x] = src[x];
+          }
+        }
+      } else {
+        for (int x = tid; x < words; x += HT) tile[x] = src[x];
+      }
+    }
+    __syncthreads();
+    for (int c0 = 0; c0 < tn; c0 += 32) {
+      // room for 32 more appends in every list of this warp?
+#pragma unroll
+      for (int qq = 0; qq < HQT; qq++)
+        if (__any_sync(0xffffffffu, cnt[qq] > cap - 32)) compact(qq);
+      const int cn = min(32, tn - c0);
+      if (cn == 32) {
+#pragma unroll 8
+        for (int c = 0; c < 32; c++) {
+          unsigned long long code[W];
+#pragma unroll
+          for (int w = 0; w < W; w++) code[w] = tile[(c0 + c) * W + w];
+#pragma unroll
+          for (int qq = 0; qq < HQT; qq++) {
+            int dist = 0;
+#pragma unroll
+            for (int w = 0; w < W; w++) dist += __popcll(code[w] ^ qc[qq][w]);
+            if (dist < thr[qq]) {
+              my[qq][(size_t)cnt[qq] * HT] =
+                  ((unsigned long long)dist << 32) | (unsigned)(int)(t0 + c0 + c + id_offset);
+              cnt[qq]++;
+            }
+          }
+        }
+      } else {
+        for (int c = 0; c < cn; c++) {
+#pragma unroll
+          for (int qq = 0; qq < HQT; qq++) {
+            int dist = 0;
+#pragma unroll
+            for (int w = 0; w < W; w++) dist += __popcll(tile[(c0 + c) * W + w] ^ qc[qq][w]);
+            if (dist < thr[qq]) {
+              my[qq][(size_t)cnt[qq] * HT] =
+                  ((unsigned long long)dist << 32) | (unsigned)(int)(t0 + c0 + c + id_offset);
+              cnt[qq]++;
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int qq = 0; qq < HQT; qq++) {
+    if (__any_sync(0xffffffffu, cnt[qq] > k)) compact(qq);
+    counts[(((size_t)blockIdx.y * gridDim.x + blockIdx.x) * HQT + qq) * HT + tid] = cnt[qq];
+  }
+}
+
+// one CTA per query: gather the S split lists, sort, emit k
+__global__ void __launch_bounds__(128)
+k_nn_hamming_gather(int nq, int k, int cap, int S, int gx,
+                    const unsigned long long *__restrict__ lists, const int *__restrict__ counts,
+                    int *__restrict__ assign, uint16_t *__restrict__ dis, int m_pad) {
+  extern __shared__ unsigned long long sbuf[];
+  __shared__ int total;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int bx = q / (HQT * HT), rem = q % (HQT * HT), qq = rem / HT, t = rem % HT;
+  if (tid == 0) total = 0;
+  for (int j = tid; j < m_pad; j += 128) sbuf[j] = ~0ull;
+  __syncthreads();
+  for (int s = 0; s < S; s++) {
+    size_t slot = (((size_t)s * gx + bx) * HQT + qq);
+    int n = counts[slot * HT + t];
+    int base = total;
+    __syncthreads();
+    for (int e = tid; e < n; e += 128) sbuf[base + e] = lists[(slot * cap + e) * HT + t];
+    if (tid == 0) total = base + n;
+    __syncthreads();
+  }
+  bitonic_sort_u64(sbuf, m_pad, tid, 128, [] { __syncthreads(); });
+  for (int j = tid; j < k; j += 128) {
+    unsigned long long v = sbuf[j];
+    if (v != ~0ull) {
+      assign[(size_t)q * k + j] = (int)(uint32_t)v;
+      dis[(size_t)q * k + j] = (uint16_t)(v >> 32);
+    } else {
+      assign[(size_t)q * k + j] = -1;
+      dis[(size_t)q * k + j] = 0xffff;
+    }
+  }
+}
+
+// merge G result sets [G][nq][k] by (distance, id)
+__global__ void __launch_bounds__(128)
+k_nn_hamming_merge(long nq, int k, int G, const int *__restrict__ ain,
+                   const uint16_t *__restrict__ din, int *__restrict__ aout,
+                   uint16_t *__restrict__ dout, unsigned long long *gsort, int m_pad) {
+  extern __shared__ unsigned long long sbuf[];
+  const long q = blockIdx.x;
+  const int tid = threadIdx.x, m = G * k;
+  unsigned long long *buf = m_pad <= 4096 ? sbuf : gsort + q * m_pad;
+  for (int j = tid; j < m_pad; j += 128) {
+    unsigned long long key = ~0ull;
+    if (j < m) {
+      int g = j / k, r = j - g * k;
+      size_t src = ((size_t)g * nq + q) * k + r;
+      int id = ain[src];
+      if (id >= 0) key = ((unsigned long long)din[src] << 32) | (unsigned)id;
+    }
+    buf[j] = key;
+  }
+  bitonic_sort_u64(buf, m_pad, tid, 128, [] { __syncthreads(); });
+  for (int j = tid; j < k; j += 128) {
+    unsigned long long v = buf[j];
+    aout[q * k + j] = v != ~0ull ? (int)(uint32_t)v : -1;
+    dout[q * k + j] = v != ~0ull ? (uint16_t)(v >> 32) : (uint16_t)0xffff;
+  }
+}
+
+// ------------------------------------------------------------------ threshold matching
+// one CTA per query row i: count / emit base ids j (ascending) with distance <= ht
+template <int W, bool EMIT>
+__global__ void __launch_bounds__(256)
+k_match_rows(const unsigned long long *__restrict__ bs1, const unsigned long long *__restrict__ bs2,
+             long n2, int ht, unsigned long long *__restrict__ row_counts,
+             const unsigned long long *__restrict__ row_offsets, int *__restrict__ idx,
+             uint16_t *__restrict__ hams) {
+  __shared__ int wtot[8];
+  __shared__ unsigned long long running;
+  const long i = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned long long qc[W];
+#pragma unroll
+  for (int w = 0; w < W; w++) qc[w] = bs1[i * W + w];
+  if (tid == 0) running = EMIT ? row_offsets[i] : 0ull;
+  unsigned long long local = 0;
+  __syncthreads();
+  for (long j0 = 0; j0 < n2; j0 += 256) {
+    long j = j0 + tid;
+    int h = 0x7fffffff;
+    if (j < n2) {
+      h = 0;
+#pragma unroll
+      for (int w = 0; w < W; w++) h += __popcll(qc[w] ^ bs2[j * W + w]);
+    }
+    const bool hit = h <= ht;
+    if (!EMIT) {
+      local += hit;
+    } else {
+      unsigned ball = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0) wtot[warp] = __popc(ball);
+      __syncthreads();
+      unsigned long long base = running;
+      int before = 0, all = 0;
+      for (int w = 0; w < 8; w++) {
+        if (w < warp) before += wtot[w];
+        all += wtot[w];
+      }
+      if (hit) {
+        unsigned long long pos = base + before + __popc(ball & ((1u << lane) - 1u));
+        idx[2 * pos] = (int)i;
+        idx[2 * pos + 1] = (int)j;
+        hams[pos] = (uint16_t)h;
+      }
+      __syncthreads();
+      if (tid == 0) running = base + all;
+      __syncthreads();
+    }
+  }
+  if (!EMIT) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if (lane == 0) atomicAdd(&running, local);
+    __syncthreads();
+    if (tid == 0) row_counts[i] = running;
+  }
+}
+
+// exclusive scan of n counts by one CTA (n1 query rows: small)
+__global__ void __launch_bounds__(1024)
+k_scan_u64(const unsigned long long *__restrict__ in, long n, unsigned long long *__restrict__ out,
+           unsigned long long *__restrict__ total) {
+  __shared__ unsigned long long part[1024];
+  const int tid = threadIdx.x;
+  long per = (n + 1023) / 1024;
+  long b = tid * per, e = min(n, b + per);
+  unsigned long long s = 0;
+  for (long i = b; i < e; i++) s += in[i];
+  part[tid] = s;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long acc = 0;
+    for (int t = 0; t < 1024; t++) {
+      unsigned long long v = part[t];
+      part[t] = acc;
+      acc += v;
+    }
+    *total = acc;
+  }
+  __syncthreads();
+  unsigned long long acc = part[tid];
+  for (long i = b; i < e; i++) {
+    unsigned long long v = in[i];
+    out[i] = acc;
+    acc += v;
+  }
+}
+
+// ------------------------------------------------------------------ host helpers
+static int words_for(int ncodes) {
+  int w = (ncodes + 7) / 8;
+  if (w <= 1) return 1;
+  if (w <= 2) return 2;
+  if (w <= 4) return 4;
+  if (w <= 8) return 8;
+  return 0;
+}
+
+// codes as W-word rows: the caller's buffer when it already has that shape, else a repack
+static int packed_codes(const uint8_t *src, long n, int ncodes, int W, unsigned long long *tmp,
+                        const unsigned long long **out, cudaStream_t st) {
+  if (ncodes == W * 8 && (((uintptr_t)src) & 7) == 0) {
+    *out = (const unsigned long long *)src;
+    return 0;
+  }
+  long tot = n * W;
+  k_ham_pack<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, n, ncodes, W, tmp);
+  YB_LAUNCH_CHECK();
+  *out = tmp;
+  return 0;
+}
+
+#define YB_DISPATCH_W(W, CALL)                 \
+  switch (W) {                                 \
+    case 1: { constexpr int WW = 1; CALL; } break; \
+    case 2: { constexpr int WW = 2; CALL; } break; \
+    case 4: { constexpr int WW = 4; CALL; } break; \
+    default: { constexpr int WW = 8; CALL; } break; \
+  }
+
+}  // namespace yb
+
+using namespace yb;
+
+extern "C" int yb_compute_hamming(uint16_t *dis, const uint8_t *a, const uint8_t *b, int na,
+                                   int nb, int ncodes, yb_stream_t s) {
+  if (na <= 0 || nb <= 0) return 0;
+  const int W = words_for(ncodes);
+  if (!W) return fail(3, "compute_hamming: codes of %d bytes are not supported (max 64)", ncodes);
+  Guard g;
+  cudaStream_t st = stream_of(s);
+  ScratchScope ws(Carver::need(8ull * W * na) + Carver::need(8ull * W * nb), st);
+  Carver c(ws.p);
+  const unsigned long long *pa, *pb;
+  int rc;
+  if ((rc = packed_codes(a, na, ncodes, W, c.take<unsigned long long>((size_t)W * na), &pa, st))) return rc;
+  if ((rc = packed_codes(b, nb, ncodes, W, c.take<unsigned long long>((size_t)W * nb), &pb, st))) return rc;
+  const long slab = 65535L * 8;
+  for (long j0 = 0; j0 < nb; j0 += slab) {
+    long nbj = nb - j0 < slab ? nb - j0 : slab;
+    dim3 grid((unsigned)((na + 31) / 32), (unsigned)((nbj + 7) / 8));
+    YB_DISPATCH_W(W, (k_compute_hamming<WW><<<grid, 256, 0, st>>>(dis + j0 * (long)na, pa,
+                                                                   pb + j0 * W, na, nbj)));
+    YB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int yb_nn_hamming(int nq, int nb, int ncodes, int k, const uint8_t *base,
+                              const uint8_t *query, int *assign, uint16_t *dis, int id_offset,
+                              yb_stream_t s) {
+  if (nq <= 0) return 0;
+  if (k <= 0 || k > nb) return fail(3, "nn_hamming: need 0 < k <= nb (k=%d, nb=%d)", k, nb);
+  const int W = words_for(ncodes);
+  if (!W) return fail(3, "nn_hamming: codes of %d bytes are not supported (max 64)", ncodes);
+  Guard g;
+  cudaStream_t st = stream_of(s);
+  const int gx = (nq + HQT * HT - 1) / (HQT * HT);
+  // splits: fill the machine about 4 CTAs deep, keep every split at least 4 tiles long
+  int S = (4 * sm_count() + gx - 1) / gx;
+  long max_s = ((long)nb + 4 * HTILE - 1) / (4 * HTILE);
+  if (S > max_s) S = (int)max_s;
+  if (S < 1) S = 1;
+  int cap = k + 64 > 2 * k ? k + 64 : 2 * k;
+  cap = (cap + 31) & ~31;
+  while (S > 1 && pow2_ceil(S * k) > 4096) S--;  // gather kernel sorts S*k entries in smem
+  if (pow2_ceil(S * k) > 4096) return fail(3, "nn_hamming: k=%d too large (max 4096)", k);
+  long split_len = ((long)nb + S - 1) / S;
+  split_len = (split_len + HTILE - 1) / HTILE * HTILE;
+  S = (int)(((long)nb + split_len - 1) / split_len);
+  const size_t nslots = (size_t)S * gx * HQT * HT;
+  ScratchScope ws(Carver::need(8ull * W * nb) + Carver::need(8ull * W * nq) +
+                      Carver::need(8ull * nslots * cap) + Carver::need(4ull * nslots),
+                  st);
+  Carver c(ws.p);
+  const unsigned long long *pb, *pq;
+  int rc;
+  if ((rc = packed_codes(base, nb, ncodes, W, c.take<unsigned long long>((size_t)W * nb), &pb, st))) return rc;
+  if ((rc = packed_codes(query, nq, ncodes, W, c.take<unsigned long long>((size_t)W * nq), &pq, st))) return rc;
+  unsigned long long *lists = c.take<unsigned long long>(nslots * cap);
+  int *counts = c.take<int>(nslots);
+  dim3 grid(gx, S);
+  YB_DISPATCH_W(W, (k_nn_hamming_scan<WW><<<grid, HT, 0, st>>>(nq, nb, k, cap, pb, pq, split_len,
+                                                               lists, counts, id_offset)));
+  YB_LAUNCH_CHECK();
+  int m_pad = pow2_ceil(S * k < 2 ? 2 : S * k);
+  k_nn_hamming_gather<<<nq, 128, 8ull * m_pad, st>>>(nq, k, cap, S, gx, lists, counts, assign, dis,
+                                                     m_pad);
+  YB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int yb_nn_hamming_merge(int nq, int k, int G, const int *assign_in,
+                                    const uint16_t *dis_in, int *assign_out, uint16_t *dis_out,
+                                    yb_stream_t s) {
+  if (nq <= 0 || k <= 0 || G <= 0) return 0;
+  Guard g;
+  cudaStream_t st = stream_of(s);
+  int m_pad = pow2_ceil(G * k < 2 ? 2 : G * k);
+  size_t wsb = m_pad <= 4096 ? 256 : Carver::need(8ull * (size_t)nq * m_pad);
+  ScratchScope ws(wsb, st);
+  k_nn_hamming_merge<<<nq, 128, m_pad <= 4096 ? 8ull * m_pad : 0, st>>>(
+      nq, k, G, assign_in, dis_in, assign_out, dis_out, (unsigned long long *)ws.p, m_pad);
+  YB_LAUNCH_CHECK();
+  return 0;
+}
+
+static int match_impl(const uint8_t *bs1, const uint8_t *bs2, int n1, int n2, int ht, int ncodes,
+                      int *idx, uint16_t *hams, unsigned long long *count, bool emit,
+                      yb_stream_t s) {
+  const int W = words_for(ncodes);
+  if (!W) return fail(3, "match_hamming: codes of %d bytes are not supported (max 64)", ncodes);
+  Guard g;
+  cudaStream_t st = stream_of(s);
+  if (n1 <= 0 || n2 <= 0) {
+    YB_CUDA(cudaMemsetAsync(count, 0, sizeof(*count), st));
+    return 0;
+  }
+  ScratchScope ws(Carver::need(8ull * W * n1) + Carver::need(8ull * W * n2) +
+                      2 * Carver::need(8ull * n1),
+                  st);
+  Carver c(ws.p);
+  const unsigned long long *p1, *p2;
+  int rc;
+  if ((rc = packed_codes(bs1, n1, ncodes, W, c.take<unsigned long long>((size_t)W * n1), &p1, st))) return rc;
+  if ((rc = packed_codes(bs2, n2, ncodes, W, c.take<unsigned long long>((size_t)W * n2), &p2, st))) return rc;
+  unsigned long long *rc_cnt = c.take<unsigned long long>(n1);
+  unsigned long long *rc_off = c.take<unsigned long long>(n1);
+  YB_DISPATCH_W(W, (k_match_rows<WW, false><<<n1, 256, 0, st>>>(p1, p2, n2, ht, rc_cnt, nullptr,
+                                                                nullptr, nullptr)));
+  YB_LAUNCH_CHECK();
+  k_scan_u64<<<1, 1024, 0, st>>>(rc_cnt, n1, rc_off, count);
+  YB_LAUNCH_CHECK();
+  if (emit) {
+    YB_DISPATCH_W(W, (k_match_rows<WW, true><<<n1, 256, 0, st>>>(p1, p2, n2, ht, nullptr, rc_off,
+                                                                 idx, hams)));
+    YB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int yb_match_hamming_count(const uint8_t *bs1, const uint8_t *bs2, int n1, int n2,
+                                       int ht, int ncodes, unsigned long long *count,
+                                       yb_stream_t s) {
+  return match_impl(bs1, bs2, n1, n2, ht, ncodes, nullptr, nullptr, count, false, s);
+}
+
+extern "C" int yb_match_hamming_thres(const uint8_t *bs1, const uint8_t *bs2, int n1, int n2,
+                                       int ht, int ncodes, int *idx, uint16_t *hams,
+                                       unsigned long long *count, yb_stream_t s) {
+  return match_impl(bs1, bs2, n1, n2, ht, ncodes, idx, hams, count, true, s);
+}

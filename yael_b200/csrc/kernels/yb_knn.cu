@@ -1,0 +1,484 @@
+// yb_knn.cu -- exact k-NN orchestration (knn_full, yael/nn.c:451-525) on device pointers.
+//
+// Two engines produce the same values:
+//   engine 1  tcgen05 TF32 shortlist (yb_knn_tf32.cu) -> exact FP32 re-rank (k_rerank below)
+//             with a per-query certificate; queries that fail it are re-done by engine 0.
+//   engine 0  exact FP32 distance slab (k_l2_simt) -> per-row select (k_kmin_rows).
+// Both end in the reference's distance formula with the dot product as a sequential FP32
+// FMA chain, and both order results by (distance, id).
+#include <stdlib.h>
+
+#include "yb_common.cuh"
+#include "yb_internal.cuh"
+
+namespace yb {
+
+static int g_engine_force = -1;
+static int g_last_engine = 0;
+static long g_last_uncert = 0;
+
+// ------------------------------------------------------------------ exact re-rank
+// One CTA (4 warps) per query.  Candidates come as ids; each warp takes 32 candidates at a
+// time and every lane walks its candidate's row sequentially (warp_rows_seq pattern,
+// restated here because rows are gathered).
+//
+// MODE 0: knn_reorder_shortlist (yael/nn.c:528-580): ids = idx[q][0..ki) up to the first
+//         negative id; distance = compute_distances_1 (both norms double, nn.c:132-154);
+//         order (distance, position).
+// MODE 1: shortlist re-rank for knn_full: ids = lists[q][0..m) (id < 0 = empty slot);
+//         distance = nn.c:100-129 with the base row as the a-operand (float norm) and the
+//         query as the b-operand (double norm); order (distance, id); emits the k best,
+//         padding, and the certificate flag.
+struct RerankArgs {
+  int nq, nb, d, k;
+  const float *base;
+  const float *query;
+  // MODE 0
+  int *idx;
+  float *dis;
+  // MODE 1
+  const float2 *lists;     // [nq][m] (score, id as int bits)
+  const float *thresholds; // [nq][splits]
+  int m, splits;
+  float err_scale;         // certificate: E_q = err_scale * |q| * max|b|
+  const float *bmax;       // device scalar: max |b| (sqrt of max squared norm)
+  int *assign;
+  int id_offset;
+  int *uncert_flags;       // [nq] 1 = certificate failed
+  unsigned long long *gsort; // global sort slab when m_pad > 4096
+  int m_pad;
+  int k1;                  // k == 1: nn_single_full start value (-1, 1e30f), nn.c:404-407
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_rerank(RerankArgs A) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ float tile[4][32][33];
+  __shared__ double qn_sh;
+  const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int d = A.d;
+  const int m = MODE == 0 ? A.k : A.m;
+  const int m_pad = A.m_pad;
+  float *qs = reinterpret_cast<float *>(smem_raw);
+  size_t off = ((size_t)d * sizeof(float) + 15) & ~(size_t)15;
+  int *ids = reinterpret_cast<int *>(smem_raw + off);
+  off += ((size_t)m * sizeof(int) + 15) & ~(size_t)15;
+  float *dv = reinterpret_cast<float *>(smem_raw + off);
+  off += ((size_t)m * sizeof(float) + 15) & ~(size_t)15;
+  unsigned long long *sortbuf = (m_pad <= 4096)
+                                    ? reinterpret_cast<unsigned long long *>(smem_raw + off)
+                                    : A.gsort + (size_t)q * m_pad;
+
+  for (int t = tid; t < d; t += 128) qs[t] = A.query[(size_t)q * d + t];
+  int ki = m;
+  if (MODE == 0) {
+    for (int j = tid; j < m; j += 128) ids[j] = A.idx[(size_t)q * m + j];
+  } else {
+    for (int j = tid; j < m; j += 128) ids[j] = __float_as_int(A.lists[(size_t)q * m + j].y);
+  }
+  __syncthreads();
+  if (MODE == 0) {  // stop at the first negative id (nn.c:546-551)
+    ki = m;
+    for (int j = 0; j < m; j++)
+      if (ids[j] < 0) {
+        ki = j;
+        break;
+      }
+  }
+  if (tid == 0) {
+    double s = 0.0;
+    for (int t = 0; t < d; t++) s += (double)__fmul_rn(qs[t], qs[t]);
+    qn_sh = s;
+  }
+  __syncthreads();
+  const double qn = qn_sh;
+
+  for (int c0 = warp * 32; c0 < ki; c0 += 128) {
+    const int c = c0 + lane;
+    const int id = c < ki ? ids[c] : -1;
+    const float *rowp = id >= 0 ? A.base + (size_t)id * d : nullptr;
+    float nf = 0.f, dot = 0.f;
+    double nd = 0.0;
+    for (int t0 = 0; t0 < d; t0 += 32) {
+      const int w = min(32, d - t0);
+#pragma unroll 4
+      for (int r = 0; r < 32; r++) {
+        const float *p = (const float *)__shfl_sync(0xffffffffu, (unsigned long long)rowp, r);
+        tile[warp][r][lane] = (p != nullptr && lane < w) ? __ldg(p + t0 + lane) : 0.f;
+      }
+      __syncwarp();
+      if (rowp != nullptr) {
+        for (int t = 0; t < w; t++) {
+          float v = tile[warp][lane][t];
+          float sq = __fmul_rn(v, v);
+          if (MODE == 0) nd += (double)sq; else nf = __fadd_rn(nf, sq);
+          dot = fmaf(v, qs[t0 + t], dot);
+        }
+      }
+      __syncwarp();
+    }
+    if (c < ki) {
+      float base = MODE == 0 ? (float)(nd + qn) : (float)(qn + (double)nf);
+      dv[c] = id >= 0 ? __fadd_rn(base, __fmul_rn(-2.0f, dot)) : __uint_as_float(0x7fc00000u);
+    }
+  }
+  __syncthreads();
+  for (int j = tid; j < m_pad; j += 128) {
+    unsigned long long key = ~0ull;
+    if (j < ki && ids[j] >= 0) {
+      uint32_t fk = float_key(dv[j]);
+      if (MODE == 0)
+        key = ((unsigned long long)fk << 32) | (unsigned)j;
+      else if (!is_nan_key(fk))
+        key = ((unsigned long long)fk << 32) | (unsigned)j;
+    }
+    sortbuf[j] = key;
+  }
+  if (MODE == 1) {
+    // order by (distance, id): positions are not ids, so fold the id in instead
+    __syncthreads();
+    for (int j = tid; j < m_pad; j += 128) {
+      unsigned long long key = sortbuf[j];
+      if (key != ~0ull) sortbuf[j] = (key & 0xffffffff00000000ull) | (unsigned)ids[(int)(uint32_t)key];
+    }
+  }
+  bitonic_sort_u64(sortbuf, m_pad, tid, 128, [] { __syncthreads(); });
+
+  if (MODE == 0) {
+    for (int j = tid; j < ki; j += 128) {
+      int pos = (int)(uint32_t)sortbuf[j];
+      A.dis[(size_t)q * m + j] = dv[pos];
+      A.idx[(size_t)q * m + j] = ids[pos];
+    }
+  } else {
+    const int k = A.k;
+    for (int j = tid; j < k; j += 128) {
+      unsigned long long key = j < m_pad ? sortbuf[j] : ~0ull;
+      uint32_t fk = (uint32_t)(key >> 32);
+      uint32_t bits = (fk & 0x80000000u) ? (fk & 0x7fffffffu) : ~fk;
+      if (A.k1 && !(key != ~0ull && __uint_as_float(bits) < 1e30f)) {
+        A.assign[(size_t)q * k + j] = -1;
+        A.dis[(size_t)q * k + j] = 1e30f;
+      } else if (key != ~0ull) {
+        A.assign[(size_t)q * k + j] = (int)(uint32_t)key + A.id_offset;
+        A.dis[(size_t)q * k + j] = __uint_as_float(bits);
+      } else {  // yael/nn.c:515-518
+        A.assign[(size_t)q * k + j] = -1;
+        A.dis[(size_t)q * k + j] = __uint_as_float(0xffffffffu);
+      }
+    }
+    // Certificate.  Every base row that is NOT in the lists has a TF32 score >= T, the
+    // smallest final admission threshold over the splits; its exact score is >= T - E_q.
+    // The k-th exact distance D_k (score S_k = D_k - |q|^2) cannot be beaten by such a row
+    // when S_k + E_q < T.  T = +inf means no row was ever dropped: exact by construction.
+    if (tid == 0) {
+      const float inf = __uint_as_float(0x7f800000u);
+      float T = inf;
+      for (int s = 0; s < A.splits; s++) T = fminf(T, A.thresholds[(size_t)q * A.splits + s]);
+      int flag = 0;
+      if (T < inf) {
+        unsigned long long key = (k - 1) < m_pad ? sortbuf[k - 1] : ~0ull;
+        if (key == ~0ull) {
+          flag = 1;  // fewer than k candidates survived although rows were dropped
+        } else {
+          uint32_t fk = (uint32_t)(key >> 32);
+          uint32_t bits = (fk & 0x80000000u) ? (fk & 0x7fffffffu) : ~fk;
+          double Dk = (double)__uint_as_float(bits);
+          double E = (double)A.err_scale * sqrt(qn) * (double)(*A.bmax) + 4e-6 * fabs(Dk);
+          if (!((Dk - qn) + E < (double)T)) flag = 1;
+        }
+      }
+      A.uncert_flags[q] = flag;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ shard merge
+// One CTA per query: G*k (distance, id) pairs -> k best by (distance, id).
+__global__ void __launch_bounds__(128)
+k_knn_merge(int k, int G, long nq, const int *__restrict__ ain, const float *__restrict__ din,
+            int *__restrict__ aout, float *__restrict__ dout, unsigned long long *gsort,
+            int m_pad) {
+  extern __shared__ unsigned long long ssort[];
+  const long q = blockIdx.x;
+  const int tid = threadIdx.x, m = G * k;
+  unsigned long long *buf = m_pad <= 4096 ? ssort : gsort + q * m_pad;
+  for (int j = tid; j < m_pad; j += 128) {
+    unsigned long long key = ~0ull;
+    if (j < m) {
+      int g = j / k, r = j - g * k;
+      size_t src = ((size_t)g * nq + q) * k + r;
+      int id = ain[src];
+      uint32_t fk = float_key(din[src]);
+      if (id >= 0 && !is_nan_key(fk)) key = ((unsigned long long)fk << 32) | (unsigned)id;
+    }
+    buf[j] = key;
+  }
+  bitonic_sort_u64(buf, m_pad, tid, 128, [] { __syncthreads(); });
+  for (int j = tid; j < k; j += 128) {
+    unsigned long long key = buf[j];
+    if (key != ~0ull) {
+      uint32_t fk = (uint32_t)(key >> 32);
+      uint32_t bits = (fk & 0x80000000u) ? (fk & 0x7fffffffu) : ~fk;
+      aout[q * k + j] = (int)(uint32_t)key;
+      dout[q * k + j] = __uint_as_float(bits);
+    } else {
+      aout[q * k + j] = -1;
+      dout[q * k + j] = __uint_as_float(0xffffffffu);
+    }
+  }
+}
+
+static size_t rerank_smem_bytes(int d, int m, int m_pad) {
+  size_t a16 = 15;
+  size_t b = ((size_t)d * 4 + a16) & ~a16;
+  b += 2 * (((size_t)m * 4 + a16) & ~a16);
+  if (m_pad <= 4096) b += (size_t)m_pad * 8;
+  return b;
+}
+
+static void rerank_attrs() {
+  static bool done = false;
+  if (!done) {
+    cudaFuncSetAttribute(k_rerank<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_rerank<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    done = true;
+  }
+}
+
+// ------------------------------------------------------------------ engine 0
+static size_t exact_chunk_rows(int nq, int nb) {
+  size_t budget = (size_t)1 << 30;  // distance slab budget (bytes)
+  const char *e = getenv("YAEL_B200_SLAB_MB");
+  if (e && atol(e) > 0) budget = (size_t)atol(e) << 20;
+  size_t rows = budget / (sizeof(float) * (size_t)nb);
+  if (rows < 1) rows = 1;
+  if (rows > (size_t)nq) rows = nq;
+  if (rows > 64) rows &= ~(size_t)63;
+  return rows;
+}
+
+size_t knn_exact_ws_bytes(int nq, int nb, int k) {
+  size_t rows = exact_chunk_rows(nq, nb);
+  return l2_ws_bytes(nb, nq) + Carver::need(sizeof(float) * rows * (size_t)nb) +
+         kmin_ws_bytes((long)rows, k) + 1024;
+}
+
+int knn_exact(int nq, int nb, int d, int k, const float *base, const float *query,
+              const float *w, int *assign, float *dis, int id_offset, void *wsp,
+              cudaStream_t st) {
+  Carver c(wsp);
+  size_t rows = exact_chunk_rows(nq, nb);
+  float *an = c.take<float>(nb);
+  double *bn = c.take<double>(nq);
+  float *slab = c.take<float>(rows * (size_t)nb);
+  void *kws = c.take<char>(kmin_ws_bytes((long)rows, k));
+  int rc;
+  if ((rc = row_norms_seq(base, nb, d, d, an, nullptr, st))) return rc;
+  if ((rc = row_norms_seq(query, nq, d, d, nullptr, bn, st))) return rc;
+  for (long q0 = 0; q0 < nq; q0 += (long)rows) {
+    long nr = nq - q0 < (long)rows ? nq - q0 : (long)rows;
+    if ((rc = l2_matrix(d, nb, nr, base, d, query + q0 * d, d, an, bn + q0, w, slab, nb, st)))
+      return rc;
+    if ((rc = kmin_rows(slab, nb, nb, nr, k, +1, assign + q0 * k, dis + q0 * k, id_offset,
+                        k == 1 ? 1 : 0, kws, st)))
+      return rc;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ engine 1
+__global__ void k_sqrt_max(const float *__restrict__ sq, long n, float *out) {
+  float m = 0.f;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float v = sq[i];
+    if (v == v) m = fmaxf(m, v);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax((int *)out, __float_as_int(sqrtf(m)));  // m >= 0
+}
+
+__global__ void k_collect_flags(const int *__restrict__ flags, int nq, int *list, int *count) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nq && flags[q]) list[atomicAdd(count, 1)] = q;
+}
+
+__global__ void k_gather_rows(const float *__restrict__ src, const int *__restrict__ rows, int n,
+                              int d, float *__restrict__ dst) {
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < (long)n * d) dst[t] = src[(size_t)rows[t / d] * d + t % d];
+}
+
+__global__ void k_scatter_results(const int *__restrict__ rows, int n, int k,
+                                  const int *__restrict__ a_src, const float *__restrict__ d_src,
+                                  int *__restrict__ a_dst, float *__restrict__ d_dst) {
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < (long)n * k) {
+    size_t o = (size_t)rows[t / k] * k + t % k;
+    a_dst[o] = a_src[t];
+    d_dst[o] = d_src[t];
+  }
+}
+
+// TF32 operands keep 10 explicit mantissa bits; the hardware drops (or rounds) the rest, so
+// each operand carries a relative error < 2^-10 and each product < 2^-9 (+2^-20); with
+// Cauchy-Schwarz the score |b|^2 - 2<q,b> is off by at most 2 * 2^-9 * |q||b|.  2.5 % head
+// room covers the FP32 accumulation inside the tensor core and the norm rounding.
+static const float kTf32ErrScale = 1.025f / 256.0f;
+
+// returns -1000 when the tensor-core path does not apply (caller falls through to engine 0)
+int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *query,
+                  const float *w, int *assign, float *dis, int id_offset, int force,
+                  int *engine_out, long *uncert_out, cudaStream_t st) {
+  if (force == 0 || w != nullptr) return -1000;
+  Tf32Plan plan = tf32_plan(nq, nb, d, k);
+  if (!plan.ok) return -1000;
+  if (force < 0 && (double)nq * nb < 1e6) return -1000;  // tiny problems: not worth a TMA setup
+  const int m = plan.splits * plan.kprime;
+  const int m_pad = pow2_ceil(m < 2 ? 2 : m);
+  size_t smem = rerank_smem_bytes(d, m, m_pad);
+  if (smem > 200 * 1024) return -1000;
+
+  size_t need = Carver::need(sizeof(float) * (size_t)nb) + Carver::need(64) +
+                Carver::need(sizeof(float2) * (size_t)nq * m) +
+                Carver::need(sizeof(float) * (size_t)nq * plan.splits) +
+                2 * Carver::need(sizeof(int) * (size_t)nq) +
+                (m_pad > 4096 ? Carver::need(sizeof(unsigned long long) * (size_t)nq * m_pad) : 0) +
+                Carver::need(plan.ws_bytes) + 1024;
+  int n_flag = 0;
+  int *flag_list_keep = nullptr;
+  {
+    ScratchScope ws(need, st);
+    Carver c(ws.p);
+    float *an = c.take<float>(nb);
+    float *scal = c.take<float>(16);  // [0] = max |b|, [1] = flag count (int)
+    float2 *lists = c.take<float2>((size_t)nq * m);
+    float *thr = c.take<float>((size_t)nq * plan.splits);
+    int *flags = c.take<int>(nq);
+    int *flag_list = c.take<int>(nq);
+    unsigned long long *gsort = m_pad > 4096 ? c.take<unsigned long long>((size_t)nq * m_pad) : nullptr;
+    void *tfws = c.take<char>(plan.ws_bytes);
+    int rc;
+    if ((rc = row_norms_seq(base, nb, d, d, an, nullptr, st))) return rc;
+    YB_CUDA(cudaMemsetAsync(scal, 0, 64, st));
+    k_sqrt_max<<<2 * sm_count(), 256, 0, st>>>(an, nb, scal);
+    YB_LAUNCH_CHECK();
+    if ((rc = tf32_shortlist(plan, nq, nb, d, base, query, an, lists, thr, tfws, st))) return rc;
+
+    RerankArgs A = {};
+    A.nq = nq; A.nb = nb; A.d = d; A.k = k; A.base = base; A.query = query;
+    A.dis = dis; A.assign = assign; A.id_offset = id_offset;
+    A.lists = lists; A.thresholds = thr; A.m = m; A.splits = plan.splits;
+    A.err_scale = kTf32ErrScale; A.bmax = scal; A.uncert_flags = flags;
+    A.gsort = gsort; A.m_pad = m_pad; A.k1 = (k == 1);
+    rerank_attrs();
+    k_rerank<1><<<nq, 128, smem, st>>>(A);
+    YB_LAUNCH_CHECK();
+    k_collect_flags<<<(nq + 255) / 256, 256, 0, st>>>(flags, nq, flag_list, (int *)(scal + 1));
+    YB_LAUNCH_CHECK();
+    YB_CUDA(cudaMemcpyAsync(&n_flag, scal + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    YB_CUDA(cudaStreamSynchronize(st));
+    flag_list_keep = flag_list;
+    if (n_flag > 0) {
+      // uncertified queries: redo them with the exact engine (own allocations: rare path)
+      float *qsub = nullptr, *dsub = nullptr;
+      int *asub = nullptr, *rows = nullptr;
+      void *ews = nullptr;
+      YB_CUDA(cudaMalloc(&qsub, sizeof(float) * (size_t)n_flag * d));
+      YB_CUDA(cudaMalloc(&dsub, sizeof(float) * (size_t)n_flag * k));
+      YB_CUDA(cudaMalloc(&asub, sizeof(int) * (size_t)n_flag * k));
+      YB_CUDA(cudaMalloc(&rows, sizeof(int) * (size_t)n_flag));
+      YB_CUDA(cudaMalloc(&ews, knn_exact_ws_bytes(n_flag, nb, k)));
+      YB_CUDA(cudaMemcpyAsync(rows, flag_list_keep, sizeof(int) * (size_t)n_flag,
+                              cudaMemcpyDeviceToDevice, st));
+      long tot = (long)n_flag * d;
+      k_gather_rows<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(query, rows, n_flag, d, qsub);
+      YB_LAUNCH_CHECK();
+      rc = knn_exact(n_flag, nb, d, k, base, qsub, nullptr, asub, dsub, id_offset, ews, st);
+      if (!rc) {
+        tot = (long)n_flag * k;
+        k_scatter_results<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(rows, n_flag, k, asub,
+                                                                         dsub, assign, dis);
+        count_launch();
+        cudaStreamSynchronize(st);
+      }
+      cudaFree(qsub); cudaFree(dsub); cudaFree(asub); cudaFree(rows); cudaFree(ews);
+      if (rc) return rc;
+    }
+  }
+  *engine_out = 1;
+  *uncert_out = n_flag;
+  return 0;
+}
+
+}  // namespace yb
+
+using namespace yb;
+
+extern "C" void yb_set_knn_engine(int engine) { g_engine_force = engine; }
+extern "C" int yb_last_knn_engine(void) { return g_last_engine; }
+extern "C" long yb_last_knn_uncertified(void) { return g_last_uncert; }
+
+extern "C" int yb_knn_l2(int nq, int nb, int d, int k, const float *base, const float *query,
+                          const float *b_weights, int *assign, float *dis, int id_offset,
+                          yb_stream_t s) {
+  if (nq <= 0) return 0;
+  if (k <= 0 || k > nb) return fail(3, "yb_knn_l2: need 0 < k <= nb (k=%d, nb=%d)", k, nb);
+  Guard g;
+  cudaStream_t st = stream_of(s);
+  int rc = knn_tf32_path(nq, nb, d, k, base, query, b_weights, assign, dis, id_offset,
+                         g_engine_force, &g_last_engine, &g_last_uncert, st);
+  if (rc != -1000) return rc;  // -1000: tensor-core path not applicable
+  g_last_engine = 0;
+  g_last_uncert = 0;
+  ScratchScope ws(knn_exact_ws_bytes(nq, nb, k), st);
+  return knn_exact(nq, nb, d, k, base, query, b_weights, assign, dis, id_offset, ws.p, st);
+}
+
+extern "C" int yb_knn_merge(int nq, int k, int G, const int *assign_in, const float *dis_in,
+                             int *assign_out, float *dis_out, yb_stream_t s) {
+  if (nq <= 0 || k <= 0 || G <= 0) return 0;
+  Guard g;
+  cudaStream_t st = stream_of(s);
+  int m_pad = pow2_ceil(G * k < 2 ? 2 : G * k);
+  size_t wsb = m_pad <= 4096 ? 256 : Carver::need(sizeof(unsigned long long) * (size_t)nq * m_pad);
+  ScratchScope ws(wsb, st);
+  size_t smem = m_pad <= 4096 ? sizeof(unsigned long long) * (size_t)m_pad : 0;
+  k_knn_merge<<<nq, 128, smem, st>>>(k, G, nq, assign_in, dis_in, assign_out, dis_out,
+                                     (unsigned long long *)ws.p, m_pad);
+  YB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int yb_knn_reorder_shortlist(int nq, int nb, int d, int k, const float *base,
+                                         const float *query, int *idx, float *dis,
+                                         yb_stream_t s) {
+  (void)nb;
+  if (nq <= 0 || k <= 0) return 0;
+  Guard g;
+  cudaStream_t st = stream_of(s);
+  int m_pad = pow2_ceil(k < 2 ? 2 : k);
+  size_t wsb = m_pad <= 4096 ? 256 : Carver::need(sizeof(unsigned long long) * (size_t)nq * m_pad);
+  ScratchScope ws(wsb, st);
+  RerankArgs A = {};
+  A.nq = nq; A.nb = nb; A.d = d; A.k = k; A.base = base; A.query = query;
+  A.idx = idx; A.dis = dis; A.m = k; A.m_pad = m_pad; A.gsort = (unsigned long long *)ws.p;
+  size_t smem = rerank_smem_bytes(d, k, m_pad);
+  if (smem > 200 * 1024) return fail(3, "knn_reorder_shortlist: d=%d k=%d too large for one CTA", d, k);
+  rerank_attrs();
+  k_rerank<0><<<nq, 128, smem, st>>>(A);
+  YB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int yb_gather_rows(const float *src, const int *rows, int n, int d, float *dst,
+                               yb_stream_t s) {
+  if (n <= 0 || d <= 0) return 0;
+  Guard g;
+  cudaStream_t st = stream_of(s);
+  long tot = (long)n * d;
+  k_gather_rows<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, rows, n, d, dst);
+  YB_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,247 @@
+// yb_runtime.cu -- device context, workspace cache, error reporting.
+//
+// The reference has no device or global state (doc/index.rst:55-58: every function is
+// re-entrant); the library therefore keeps one lazily created context per device behind a
+// mutex and never requires an init call.
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "yb_common.cuh"
+
+namespace {
+
+constexpr int kMaxDev = 16;
+
+struct DevState {
+  cudaStream_t stream = nullptr;
+  void *scratch = nullptr;
+  size_t scratch_bytes = 0;
+  cudaEvent_t scratch_ev = nullptr;  // completion of the last op that used the scratch
+  cudaStream_t scratch_stream = nullptr;
+  bool scratch_used = false;
+  int sms = 0;
+};
+
+struct PoolBlock {
+  void *p;
+  size_t bytes;
+  int dev;
+  bool free_;
+};
+std::vector<PoolBlock> g_pool;
+
+DevState g_dev[kMaxDev];
+std::recursive_mutex g_mutex;
+thread_local char g_err[512] = "";
+long g_launches = 0;
+
+int cur_dev() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) return 0;
+  return d < kMaxDev ? d : 0;
+}
+
+
+void pool_trim(int dev) {
+  std::lock_guard<std::recursive_mutex> lk(g_mutex);
+  cudaDeviceSynchronize();
+  for (size_t i = 0; i < g_pool.size();) {
+    if (g_pool[i].free_ && (dev < 0 || g_pool[i].dev == dev)) {
+      cudaFree(g_pool[i].p);
+      g_pool[i] = g_pool.back();
+      g_pool.pop_back();
+    } else {
+      i++;
+    }
+  }
+}
+
+}  // namespace
+
+namespace yb {
+
+int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+Guard::Guard() { g_mutex.lock(); }
+Guard::~Guard() { g_mutex.unlock(); }
+
+cudaStream_t stream_of(yb_stream_t s) {
+  if (s) return (cudaStream_t)s;
+  DevState &st = g_dev[cur_dev()];
+  if (!st.stream) {
+    if (cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking) != cudaSuccess) {
+      fprintf(stderr, "yael_b200: cannot create a CUDA stream: %s\n",
+              cudaGetErrorString(cudaGetLastError()));
+      abort();
+    }
+  }
+  return st.stream;
+}
+
+void *scratch_reserve(size_t bytes, cudaStream_t on) {
+  DevState &st = g_dev[cur_dev()];
+  if (!st.scratch_ev) cudaEventCreateWithFlags(&st.scratch_ev, cudaEventDisableTiming);
+  // an earlier op on ANOTHER stream may still be using the block: order after it
+  if (st.scratch_used && st.scratch_stream != on) cudaStreamWaitEvent(on, st.scratch_ev, 0);
+  if (bytes > st.scratch_bytes) {
+    if (st.scratch) {
+      cudaDeviceSynchronize();  // earlier work may still read the old block
+      cudaFree(st.scratch);
+      st.scratch = nullptr;
+      st.scratch_bytes = 0;
+    }
+    size_t want = bytes + (bytes >> 3) + (1u << 20);
+    cudaError_t e = cudaMalloc(&st.scratch, want);
+    if (e != cudaSuccess) {
+      // same convention as the reference's allocators (yael/vector.c:37-40): message + abort
+      fprintf(stderr, "yael_b200: device workspace of %zu bytes: %s\n", want,
+              cudaGetErrorString(e));
+      abort();
+    }
+    st.scratch_bytes = want;
+  }
+  return st.scratch;
+}
+
+void scratch_done(cudaStream_t on) {
+  DevState &st = g_dev[cur_dev()];
+  if (!st.scratch_ev) cudaEventCreateWithFlags(&st.scratch_ev, cudaEventDisableTiming);
+  cudaEventRecord(st.scratch_ev, on);
+  st.scratch_stream = on;
+  st.scratch_used = true;
+}
+
+int sm_count() {
+  DevState &st = g_dev[cur_dev()];
+  if (!st.sms) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, cur_dev());
+    st.sms = v > 0 ? v : 148;
+  }
+  return st.sms;
+}
+
+void count_launch(long n) { g_launches += n; }
+
+}  // namespace yb
+
+extern "C" {
+
+const char *yb_version(void) { return "yael_b200 0.1 (sm_100a)"; }
+const char *yb_last_error(void) { return g_err; }
+
+int yb_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    yb::fail(1, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return -1;
+  }
+  return n;
+}
+
+int yb_set_device(int dev) {
+  YB_CUDA(cudaSetDevice(dev));
+  return 0;
+}
+
+int yb_sync(yb_stream_t s) {
+  YB_CUDA(cudaStreamSynchronize(yb::stream_of(s)));
+  return 0;
+}
+
+long yb_launch_count(int reset) {
+  long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+// caching pool: exact-ish reuse of freed blocks (a k-means run or a stream of knn calls asks
+// for the same sizes again and again; cudaMalloc/cudaFree would serialise the device)
+void *yb_malloc(size_t bytes) {
+  if (bytes == 0) bytes = 1;
+  bytes = (bytes + 511) & ~(size_t)511;
+  int dev = cur_dev();
+  {
+    std::lock_guard<std::recursive_mutex> lk(g_mutex);
+    PoolBlock *best = nullptr;
+    for (auto &b : g_pool)
+      if (b.free_ && b.dev == dev && b.bytes >= bytes && b.bytes <= bytes + (bytes >> 2) + 4096 &&
+          (!best || b.bytes < best->bytes))
+        best = &b;
+    if (best) {
+      best->free_ = false;
+      return best->p;
+    }
+  }
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    pool_trim(dev);  // give cached blocks back and retry once
+    e = cudaMalloc(&p, bytes);
+  }
+  if (e != cudaSuccess) {
+    fprintf(stderr, "yael_b200: cudaMalloc(%zu): %s\n", bytes, cudaGetErrorString(e));
+    abort();
+  }
+  std::lock_guard<std::recursive_mutex> lk(g_mutex);
+  g_pool.push_back({p, bytes, dev, false});
+  return p;
+}
+
+void yb_free(void *p) {
+  if (!p) return;
+  std::lock_guard<std::recursive_mutex> lk(g_mutex);
+  for (auto &b : g_pool)
+    if (b.p == p) {
+      b.free_ = true;
+      return;
+    }
+  cudaFree(p);  // not ours
+}
+
+int yb_is_device_ptr(const void *p) {
+  if (!p) return 0;
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+int yb_h2d(void *dst, const void *src, size_t bytes, yb_stream_t s) {
+  YB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, yb::stream_of(s)));
+  return 0;
+}
+
+int yb_d2h(void *dst, const void *src, size_t bytes, yb_stream_t s) {
+  YB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, yb::stream_of(s)));
+  return 0;
+}
+
+void yb_release_scratch(void) {
+  yb::Guard g;
+  DevState &st = g_dev[cur_dev()];
+  if (st.scratch) {
+    cudaDeviceSynchronize();
+    cudaFree(st.scratch);
+    st.scratch = nullptr;
+    st.scratch_bytes = 0;
+  }
+  pool_trim(cur_dev());
+}
+
+}  // extern "C"

@@ -1,0 +1,211 @@
+"""numpy front-end mirroring the reference's yael/ynumpy.py call shapes
+(knn :46-67, cross_distances :69-84, kmeans :87-130, kmin/kmax :372-390), bound to
+libyael_b200.so through the reference's own C prototypes.  Same argument names and order,
+same return values, same error behaviour (kmeans raises RuntimeError when the C call
+returns a negative qerr)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib
+
+KMEANS_QUIET = 0x10000
+KMEANS_INIT_BERKELEY = 0x20000
+KMEANS_NORMALIZE_CENTS = 0x40000
+KMEANS_INIT_RANDOM = 0x80000
+KMEANS_INIT_USER = 0x100000
+KMEANS_L1 = 0x200000
+KMEANS_CHI2 = 0x400000
+
+_f = C.POINTER(C.c_float)
+_i = C.POINTER(C.c_int)
+_u8 = C.POINTER(C.c_uint8)
+_u16 = C.POINTER(C.c_uint16)
+
+
+def _check_row_float32(a):
+    # yael/ynumpy.py:24-27
+    if a.dtype != np.float32:
+        raise TypeError("expected float32 matrix, got %s" % a.dtype)
+    if not a.flags.c_contiguous:
+        raise TypeError("expected C order matrix")
+
+
+def _check_row_uint8(a):
+    if a.dtype != np.uint8:
+        raise TypeError("expected uint8 matrix, got %s" % a.dtype)
+    if not a.flags.c_contiguous:
+        raise TypeError("expected C order matrix")
+
+
+def _fp(a):
+    return a.ctypes.data_as(_f)
+
+
+def _ip(a):
+    return a.ctypes.data_as(_i)
+
+
+def knn(queries, base, nnn=1, distance_type=2, nt=1):
+    """yael/ynumpy.py:46-67 -> knn_full_thread (yael/nn.c:679-699)."""
+    _check_row_float32(base)
+    _check_row_float32(queries)
+    n, d = base.shape
+    nq, d2 = queries.shape
+    assert d == d2, "base and queries must have same nb of rows (got %d != %d) " % (d, d2)
+    assert nnn <= n
+    _lib.require_gpu()
+    idx = np.empty((nq, nnn), dtype=np.int32)
+    dis = np.empty((nq, nnn), dtype=np.float32)
+    lib().knn_full_thread(distance_type, nq, n, d, nnn, _fp(base), _fp(queries), None,
+                          _ip(idx), _fp(dis), nt)
+    return idx, dis
+
+
+def knn_weighted(queries, base, weights, nnn=1, nt=1):
+    """knn_full_thread with the per-base-vector weights of yael/nn.c:497-500."""
+    _check_row_float32(base)
+    _check_row_float32(queries)
+    weights = np.ascontiguousarray(weights, dtype=np.float32)
+    n, d = base.shape
+    nq = queries.shape[0]
+    _lib.require_gpu()
+    idx = np.empty((nq, nnn), dtype=np.int32)
+    dis = np.empty((nq, nnn), dtype=np.float32)
+    lib().knn_full_thread(2, nq, n, d, nnn, _fp(base), _fp(queries), _fp(weights), _ip(idx),
+                          _fp(dis), nt)
+    return idx, dis
+
+
+def knn_reorder_shortlist(queries, base, idx):
+    """yael/nn.c:528-580; idx is re-ordered in place, distances returned."""
+    _check_row_float32(base)
+    _check_row_float32(queries)
+    assert idx.dtype == np.int32 and idx.flags.c_contiguous
+    nq, k = idx.shape
+    _lib.require_gpu()
+    dis = np.zeros((nq, k), dtype=np.float32)
+    lib().knn_reorder_shortlist(nq, base.shape[0], base.shape[1], k, _fp(base), _fp(queries),
+                                _ip(idx), _fp(dis))
+    return dis
+
+
+def cross_distances(a, b, distance_type=12):
+    """yael/ynumpy.py:69-84 -> compute_cross_distances_alt_nonpacked (yael/nn.c:280-350)."""
+    _check_row_float32(a)
+    na, d = a.shape
+    _check_row_float32(b)
+    nb, d2 = b.shape
+    assert d2 == d
+    _lib.require_gpu()
+    dis = np.empty((nb, na), dtype=np.float32)
+    lib().compute_cross_distances_alt_nonpacked(distance_type, d, na, nb, _fp(a), d, _fp(b), d,
+                                                _fp(dis), na)
+    return dis
+
+
+def kmeans(v, k, distance_type=2, nt=1, niter=30, seed=0, redo=1, verbose=True,
+           normalize=False, init='random', output='centroids'):
+    """yael/ynumpy.py:87-130 -> kmeans (yael/kmeans.c:332-447).  init may also be an array of
+    k initial centroids (KMEANS_INIT_USER, yael/kmeans.h:15)."""
+    _check_row_float32(v)
+    n, d = v.shape
+    _lib.require_gpu()
+    centroids = np.zeros((k, d), dtype=np.float32)
+    dis = np.empty(n, dtype=np.float32)
+    assign = np.empty(n, dtype=np.int32)
+    nassign = np.empty(k, dtype=np.int32)
+    flags = nt
+    if not verbose:
+        flags |= KMEANS_QUIET
+    if distance_type == 2:
+        pass
+    elif distance_type == 1:
+        flags |= KMEANS_L1
+    elif distance_type == 3:
+        flags |= KMEANS_CHI2
+    if isinstance(init, np.ndarray):
+        assert init.shape == (k, d)
+        centroids[:] = init
+        flags |= KMEANS_INIT_USER
+    elif init == 'random':
+        flags |= KMEANS_INIT_RANDOM
+    elif init == 'kmeans++':
+        flags |= KMEANS_INIT_BERKELEY
+    if normalize:
+        flags |= KMEANS_NORMALIZE_CENTS
+    qerr = lib().kmeans(d, n, k, niter, _fp(v), flags, seed, redo, _fp(centroids), _fp(dis),
+                        _ip(assign), _ip(nassign))
+    if qerr < 0:
+        raise RuntimeError("kmeans: clustering failed. Is dataset diverse enough?")
+    if output == 'centroids':
+        return centroids
+    return centroids, qerr, dis, assign, nassign
+
+
+def kmin(v, k):
+    """yael/ynumpy.py:372-380: indices of the k smallest values of each line."""
+    _check_row_float32(v)
+    n, d = v.shape
+    assert k <= d
+    _lib.require_gpu()
+    idx = np.empty((n, k), dtype='int32')
+    lib().fvecs_k_min(_fp(v), d, n, _ip(idx), k)
+    return idx
+
+
+def kmax(v, k):
+    """yael/ynumpy.py:382-390."""
+    _check_row_float32(v)
+    n, d = v.shape
+    assert k <= d
+    _lib.require_gpu()
+    idx = np.empty((n, k), dtype='int32')
+    lib().fvecs_k_max(_fp(v), d, n, _ip(idx), k)
+    return idx
+
+
+def hamming_distances(a, b):
+    """compute_hamming (yael/hamming.c:177-219): uint16 matrix dis[j, i] = ham(a_i, b_j)."""
+    _check_row_uint8(a)
+    _check_row_uint8(b)
+    assert a.shape[1] == b.shape[1]
+    _lib.require_gpu()
+    dis = np.empty((b.shape[0], a.shape[0]), dtype=np.uint16)
+    lib().compute_hamming(dis.ctypes.data_as(_u16), a.ctypes.data_as(_u8), b.ctypes.data_as(_u8),
+                          a.shape[0], b.shape[0], a.shape[1])
+    return dis
+
+
+def knn_hamming(queries, base, nnn=1):
+    """NEW nn_hamming: (idx, dis) of the nnn closest base codes, ordered by (distance, id)."""
+    _check_row_uint8(base)
+    _check_row_uint8(queries)
+    assert base.shape[1] == queries.shape[1]
+    assert nnn <= base.shape[0]
+    _lib.require_gpu()
+    nq = queries.shape[0]
+    idx = np.empty((nq, nnn), dtype=np.int32)
+    dis = np.empty((nq, nnn), dtype=np.uint16)
+    lib().nn_hamming(nq, base.shape[0], base.shape[1], nnn, base.ctypes.data_as(_u8),
+                     queries.ctypes.data_as(_u8), _ip(idx), dis.ctypes.data_as(_u16))
+    return idx, dis
+
+
+def match_hamming(a, b, ht):
+    """match_hamming_count + match_hamming_thres_prealloc (yael/hamming.c:283-300, 704-748):
+    returns (pairs[n, 2] as (qid, bid), scores[n])."""
+    _check_row_uint8(a)
+    _check_row_uint8(b)
+    _lib.require_gpu()
+    n = C.c_size_t(0)
+    lib().match_hamming_count(a.ctypes.data_as(_u8), b.ctypes.data_as(_u8), a.shape[0],
+                              b.shape[0], ht, a.shape[1], C.byref(n))
+    pairs = np.empty((n.value, 2), dtype=np.int32)
+    scores = np.empty(n.value, dtype=np.uint16)
+    if n.value:
+        lib().match_hamming_thres_prealloc(a.ctypes.data_as(_u8), b.ctypes.data_as(_u8),
+                                           a.shape[0], b.shape[0], ht, a.shape[1], _ip(pairs),
+                                           scores.ctypes.data_as(_u16))
+    return pairs, scores
