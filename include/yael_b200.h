@@ -93,6 +93,11 @@ int yb_knn_merge(int nq, int k, int G, const int *assign_in, const float *dis_in
 int yb_knn_reorder_shortlist(int nq, int nb, int d, int k, const float *base,
                              const float *query, int *idx, float *dis, yb_stream_t s);
 
+/* Test / bring-up entry of the tensor-core engine: scores[q][n] = |b_n|^2 - 2 <q, b_n> with TF32
+ * operands for every pair (the fused top-k switched off).  d must be a multiple of 4, <= 128. */
+int yb_debug_tf32_scores(int nq, int nb, int d, const float *base, const float *query,
+                         float *scores, yb_stream_t s);
+
 /* ---- k smallest: fvec_k_min / fvecs_k_min (yael/sorting.c:191-255) ---------------- */
 /* nrow arrays of length n (row stride ld) -> idx[nrow][k] (+ optional vals[nrow][k]),
  * ascending by (value, index); sign = +1 for k-min, -1 for k-max (values negated as the

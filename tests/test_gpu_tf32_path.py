@@ -1,0 +1,127 @@
+"""GPU parity of the tcgen05 TF32 engine: raw tensor-core scores against the error model the
+certificate relies on, and the full shortlist -> re-rank pipeline against the oracle.
+
+Tolerances (BASELINE.json north_star): L2 distances within 1e-5 relative of the reference's
+CPU implementation, ids identical except for ties inside that tolerance.  The re-rank uses the
+reference's arithmetic, so in practice the distances are bit-identical."""
+import numpy as np
+import pytest
+
+import yael_b200
+from devmem import DevArray
+
+pytestmark = pytest.mark.gpu
+
+
+def rs(seed):
+    return np.random.RandomState(seed)
+
+
+@pytest.mark.parametrize("nq,nb,d", [(128, 256, 128), (128, 256, 32), (130, 700, 128), (77, 1000, 96),
+                                     (300, 5000, 64), (5, 300, 100), (256, 2048, 8)])
+def test_tf32_scores_within_error_model(nq, nb, d):
+    L = yael_b200.lib()
+    r = rs(nq + nb + d)
+    base = r.rand(nb, d).astype(np.float32)
+    query = r.rand(nq, d).astype(np.float32)
+    db, dq = DevArray(base), DevArray(query)
+    out = DevArray(shape=(nq, nb), dtype=np.float32)
+    rc = L.yb_debug_tf32_scores(nq, nb, d, db.ptr, dq.ptr, out.ptr, None)
+    assert rc == 0, L.yb_last_error()
+    L.yb_sync(None)
+    got = out.get()
+    b64, q64 = base.astype(np.float64), query.astype(np.float64)
+    exact = (b64 * b64).sum(1)[None, :] - 2.0 * q64 @ b64.T
+    err = np.abs(got - exact)
+    bound = (1.025 / 256.0) * np.linalg.norm(q64, axis=1)[:, None] * np.linalg.norm(b64, axis=1).max()
+    assert np.isfinite(got).all()
+    assert (err <= bound + 1e-5).all(), "max err %g vs bound %g" % (err.max(), bound.min())
+    # and it really is a TF32-class result, not an FP32 one or garbage
+    assert err.max() < 0.05 * np.abs(exact).max()
+    for a in (db, dq, out):
+        a.free()
+
+
+@pytest.fixture
+def tf32_engine():
+    L = yael_b200.lib()
+    L.yb_set_knn_engine(1)
+    yield L
+    L.yb_set_knn_engine(-1)
+
+
+def check_knn(idx, dis, widx, wdis, rtol=1e-5):
+    # distances within tolerance everywhere
+    valid = widx >= 0
+    assert np.array_equal(valid, idx >= 0)
+    np.testing.assert_allclose(dis[valid], wdis[valid], rtol=rtol, atol=1e-6)
+    # ids identical except inside ties
+    diff = (idx != widx) & valid
+    if diff.any():
+        qs, js = np.nonzero(diff)
+        for q, j in zip(qs, js):
+            # the id we returned must be a legitimate member at that distance
+            assert abs(dis[q, j] - wdis[q, j]) <= rtol * max(abs(wdis[q, j]), 1e-6)
+
+
+@pytest.mark.parametrize("nq,nb,d,k", [(256, 20000, 128, 10), (100, 5000, 128, 100), (1000, 30000, 96, 1),
+                                        (130, 3000, 64, 5), (64, 100000, 32, 50), (700, 2500, 128, 100)])
+def test_knn_tf32_engine_matches_oracle(yn, ob, tf32_engine, nq, nb, d, k):
+    r = rs(nq * 7 + nb + k)
+    b = r.rand(nb, d).astype(np.float32)
+    q = r.rand(nq, d).astype(np.float32)
+    idx, dis = yn.knn(q, b, k)
+    assert tf32_engine.yb_last_knn_engine() == 1
+    widx, wdis = ob.orc_knn(b, q, k, ob.DOT_F32_SEQ, canonical=True)
+    check_knn(idx, dis, widx, wdis)
+    # uniform data never needs the exact fallback in bulk
+    assert tf32_engine.yb_last_knn_uncertified() <= nq // 20
+
+
+def test_knn_tf32_sift_like_integers(yn, ob, tf32_engine):
+    # integer coordinates 0..255 are exact in TF32: the tensor pass is exact, ties abound
+    r = rs(42)
+    b = np.minimum(255, r.gamma(1.2, 25.0, (20000, 128))).astype(np.int32).astype(np.float32)
+    q = np.minimum(255, r.gamma(1.2, 25.0, (200, 128))).astype(np.int32).astype(np.float32)
+    idx, dis = yn.knn(q, b, 100)
+    widx, wdis = ob.orc_knn(b, q, 100, canonical=True)
+    assert np.array_equal(dis, wdis)
+    assert np.array_equal(idx, widx)
+
+
+def test_knn_tf32_adversarial_near_duplicates(yn, ob, tf32_engine):
+    # clusters of near-duplicates with large norms: the certificate must route the hard
+    # queries to the exact engine instead of returning a wrong neighbour
+    r = rs(7)
+    centers = (r.rand(50, 64) * 100).astype(np.float32)
+    b = (centers[r.randint(0, 50, 20000)] + r.randn(20000, 64) * 1e-3).astype(np.float32)
+    q = (centers[r.randint(0, 50, 300)] + r.randn(300, 64) * 1e-3).astype(np.float32)
+    idx, dis = yn.knn(q, b, 10)
+    widx, wdis = ob.orc_knn(b, q, 10, canonical=True)
+    assert np.array_equal(dis, wdis)
+    assert np.array_equal(idx, widx)
+
+
+def test_knn_tf32_nan_and_padding(yn, ob, tf32_engine):
+    r = rs(8)
+    b = r.rand(3000, 32).astype(np.float32)
+    b[5::7] = np.nan
+    q = r.rand(150, 32).astype(np.float32)
+    idx, dis = yn.knn(q, b, 20)
+    widx, wdis = ob.orc_knn(b, q, 20, canonical=True)
+    check_knn(idx, dis, widx, wdis)
+    assert not np.isin(idx, np.arange(5, 3000, 7)).any()
+
+
+def test_kmeans_assignment_tf32(yn, ob, tf32_engine):
+    r = rs(1234)
+    v = r.rand(50000, 128).astype(np.float32)
+    c0 = v[r.permutation(50000)[:256]].copy()
+    cent, qerr, dis, assign, nassign = yn.kmeans(v, 256, niter=1, verbose=False, init=c0, output="all")
+    q, wc, wa, wd, wn = ob.orc_kmeans_step(v, c0)
+    mism = assign != wa
+    # any disagreement must be a tie inside 1e-5 relative
+    assert np.all(np.abs(dis[mism] - wd[mism]) <= 1e-5 * wd[mism])
+    assert mism.mean() < 1e-3
+    np.testing.assert_allclose(dis, wd, rtol=1e-5)
+    np.testing.assert_allclose(cent, wc, atol=1e-4)

@@ -140,6 +140,7 @@ DEVICE = {
     "yb_kmeans_accumulate": (C.c_int, [C.c_int] * 3 + [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "yb_kmeans_scale": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
     "yb_kmeans_dev": (C.c_float, [C.c_int] * 4 + [_vp, C.c_int, C.c_long, C.c_int, _f, _f, _i, _i, _vp, _vp]),
+    "yb_debug_tf32_scores": (C.c_int, [C.c_int] * 3 + [_vp, _vp, _vp, _vp]),
     "yb_compute_hamming": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "yb_nn_hamming": (C.c_int, [C.c_int] * 4 + [_vp, _vp, _vp, _vp, C.c_int, _vp]),
     "yb_nn_hamming_merge": (C.c_int, [C.c_int] * 3 + [_vp, _vp, _vp, _vp, _vp]),

@@ -28,11 +28,15 @@ struct Tf32Plan {
   size_t ws_bytes; // workspace for buffers + shortlists
 };
 Tf32Plan tf32_plan(int nq, int nb, int d, int k);
-// Produces, for every query, `splits` shortlists of `kprime` (score, id) pairs, score =
-// |b|^2 - 2<q,b> evaluated with TF32 operands, unused slots id = -1; plus per (query, split)
-// the final admission threshold (every base row NOT in the list has score >= threshold).
+// Produces, for every query, `splits` shortlists of `kprime` candidates: out_score[q][s][e] =
+// |b|^2 - 2<q,b> evaluated with TF32 operands, out_id[q][s][e] the row id (unused slots:
+// +inf / -1).  Every database row that is NOT listed for (q, s) has a TF32 score >= the
+// largest listed score of a full list.  bnorm_padded: |b|^2 for tf32_padded_rows(nb) rows,
+// the padding filled with +inf.
 int tf32_shortlist(const Tf32Plan &plan, int nq, int nb, int d, const float *base,
-                   const float *query, const float *bnorm, float2 *lists, float *thresholds,
+                   const float *query, const float *bnorm_padded, float *out_score, int *out_id,
                    void *ws, cudaStream_t st);
+long tf32_padded_rows(int nb);
+int fill_f32(float *p, long n, float v, cudaStream_t st);
 
 }  // namespace yb

@@ -36,10 +36,14 @@ struct RerankArgs {
   // MODE 0
   int *idx;
   float *dis;
-  // MODE 1
-  const float2 *lists;     // [nq][m] (score, id as int bits)
-  const float *thresholds; // [nq][splits]
-  int m, splits;
+  // MODE 1: candidates = cand_id[q][pos] for pos = sel[q][j] (or pos = j when sel == NULL),
+  // j < m; cand_score carries their TF32 scores
+  const int *cand_id;      // [nq][cand_stride]
+  const float *cand_score; // [nq][cand_stride]
+  const int *sel;          // [nq][m] positions (ascending TF32 score), -1 = none
+  int cand_stride;
+  int m;
+  int all_listed;          // 1: every database row is a candidate (nothing was ever dropped)
   float err_scale;         // certificate: E_q = err_scale * |q| * max|b|
   const float *bmax;       // device scalar: max |b| (sqrt of max squared norm)
   int *assign;
@@ -74,7 +78,10 @@ __global__ void __launch_bounds__(128) k_rerank(RerankArgs A) {
   if (MODE == 0) {
     for (int j = tid; j < m; j += 128) ids[j] = A.idx[(size_t)q * m + j];
   } else {
-    for (int j = tid; j < m; j += 128) ids[j] = __float_as_int(A.lists[(size_t)q * m + j].y);
+    for (int j = tid; j < m; j += 128) {
+      int pos = A.sel ? A.sel[(size_t)q * m + j] : j;
+      ids[j] = pos >= 0 ? A.cand_id[(size_t)q * A.cand_stride + pos] : -1;
+    }
   }
   __syncthreads();
   if (MODE == 0) {  // stop at the first negative id (nn.c:546-551)
@@ -167,14 +174,26 @@ __global__ void __launch_bounds__(128) k_rerank(RerankArgs A) {
         A.dis[(size_t)q * k + j] = __uint_as_float(0xffffffffu);
       }
     }
-    // Certificate.  Every base row that is NOT in the lists has a TF32 score >= T, the
-    // smallest final admission threshold over the splits; its exact score is >= T - E_q.
-    // The k-th exact distance D_k (score S_k = D_k - |q|^2) cannot be beaten by such a row
-    // when S_k + E_q < T.  T = +inf means no row was ever dropped: exact by construction.
+    // Certificate.  Every database row that is NOT a candidate has a TF32 score >= T, the
+    // largest TF32 score among the m candidates when the candidate set is full (rows are only
+    // ever dropped from a full list, in favour of smaller scores); its exact score is then
+    // >= T - E_q.  The k-th exact distance D_k (score S_k = D_k - |q|^2) cannot be beaten by
+    // such a row when S_k + E_q < T.
     if (tid == 0) {
       const float inf = __uint_as_float(0x7f800000u);
       float T = inf;
-      for (int s = 0; s < A.splits; s++) T = fminf(T, A.thresholds[(size_t)q * A.splits + s]);
+      if (!A.all_listed) {
+        int nvalid = 0;
+        float mx = -inf;
+        for (int j = 0; j < m; j++) {
+          int pos = A.sel ? A.sel[(size_t)q * m + j] : j;
+          if (pos >= 0 && A.cand_id[(size_t)q * A.cand_stride + pos] >= 0) {
+            nvalid++;
+            mx = fmaxf(mx, A.cand_score[(size_t)q * A.cand_stride + pos]);
+          }
+        }
+        if (nvalid == m) T = mx;  // a partially filled set means nothing was dropped
+      }
       int flag = 0;
       if (T < inf) {
         unsigned long long key = (k - 1) < m_pad ? sortbuf[k - 1] : ~0ull;
@@ -335,43 +354,55 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
   Tf32Plan plan = tf32_plan(nq, nb, d, k);
   if (!plan.ok) return -1000;
   if (force < 0 && (double)nq * nb < 1e6) return -1000;  // tiny problems: not worth a TMA setup
-  const int m = plan.splits * plan.kprime;
+  const int kp = plan.kprime;
+  const int stride = plan.splits * kp;  // candidates per query produced by the tensor pass
+  const int m = kp;                     // candidates per query that are re-ranked
   const int m_pad = pow2_ceil(m < 2 ? 2 : m);
   size_t smem = rerank_smem_bytes(d, m, m_pad);
   if (smem > 200 * 1024) return -1000;
+  const long padded = tf32_padded_rows(nb);
+  const bool need_sel = plan.splits > 1;
 
-  size_t need = Carver::need(sizeof(float) * (size_t)nb) + Carver::need(64) +
-                Carver::need(sizeof(float2) * (size_t)nq * m) +
-                Carver::need(sizeof(float) * (size_t)nq * plan.splits) +
-                2 * Carver::need(sizeof(int) * (size_t)nq) +
-                (m_pad > 4096 ? Carver::need(sizeof(unsigned long long) * (size_t)nq * m_pad) : 0) +
+  size_t need = Carver::need(sizeof(float) * (size_t)padded) + Carver::need(64) +
+                Carver::need(sizeof(float) * (size_t)nq * stride) +
+                Carver::need(sizeof(int) * (size_t)nq * stride) +
+                Carver::need(sizeof(int) * (size_t)nq * kp) +
+                2 * Carver::need(sizeof(int) * (size_t)nq) + kmin_ws_bytes(nq, kp) +
                 Carver::need(plan.ws_bytes) + 1024;
   int n_flag = 0;
   int *flag_list_keep = nullptr;
   {
     ScratchScope ws(need, st);
     Carver c(ws.p);
-    float *an = c.take<float>(nb);
+    float *an = c.take<float>(padded);
     float *scal = c.take<float>(16);  // [0] = max |b|, [1] = flag count (int)
-    float2 *lists = c.take<float2>((size_t)nq * m);
-    float *thr = c.take<float>((size_t)nq * plan.splits);
+    float *cscore = c.take<float>((size_t)nq * stride);
+    int *cid = c.take<int>((size_t)nq * stride);
+    int *sel = c.take<int>((size_t)nq * kp);
     int *flags = c.take<int>(nq);
     int *flag_list = c.take<int>(nq);
-    unsigned long long *gsort = m_pad > 4096 ? c.take<unsigned long long>((size_t)nq * m_pad) : nullptr;
+    void *kws = c.take<char>(kmin_ws_bytes(nq, kp));
     void *tfws = c.take<char>(plan.ws_bytes);
     int rc;
     if ((rc = row_norms_seq(base, nb, d, d, an, nullptr, st))) return rc;
+    if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
     YB_CUDA(cudaMemsetAsync(scal, 0, 64, st));
     k_sqrt_max<<<2 * sm_count(), 256, 0, st>>>(an, nb, scal);
     YB_LAUNCH_CHECK();
-    if ((rc = tf32_shortlist(plan, nq, nb, d, base, query, an, lists, thr, tfws, st))) return rc;
+    if ((rc = tf32_shortlist(plan, nq, nb, d, base, query, an, cscore, cid, tfws, st))) return rc;
+    if (need_sel) {
+      // merge the per-range shortlists: the kp smallest TF32 scores of the union
+      if ((rc = kmin_rows(cscore, stride, stride, nq, kp, +1, sel, nullptr, 0, 0, kws, st)))
+        return rc;
+    }
 
     RerankArgs A = {};
     A.nq = nq; A.nb = nb; A.d = d; A.k = k; A.base = base; A.query = query;
     A.dis = dis; A.assign = assign; A.id_offset = id_offset;
-    A.lists = lists; A.thresholds = thr; A.m = m; A.splits = plan.splits;
+    A.cand_id = cid; A.cand_score = cscore; A.sel = need_sel ? sel : nullptr;
+    A.cand_stride = stride; A.m = m; A.all_listed = (nb <= kp);
     A.err_scale = kTf32ErrScale; A.bmax = scal; A.uncert_flags = flags;
-    A.gsort = gsort; A.m_pad = m_pad; A.k1 = (k == 1);
+    A.gsort = nullptr; A.m_pad = m_pad; A.k1 = (k == 1);
     rerank_attrs();
     k_rerank<1><<<nq, 128, smem, st>>>(A);
     YB_LAUNCH_CHECK();

@@ -1,10 +1,625 @@
-// yb_knn_tf32.cu -- placeholder until the tcgen05 kernel lands (next commit).
+// yb_knn_tf32.cu -- the distance GEMM of knn_full / nn_single_full (yael/nn.c:54-67,92-129,
+// 383-525) as a tcgen05 TF32 tensor-core kernel with the per-query top-k fused into its
+// epilogue.  The nq x nb distance matrix never reaches HBM.
+//
+// What it computes: for every query q and database row b the SCORE s = |b|^2 - 2 <q,b> with
+// TF32 operands and FP32 accumulation (|q|^2 is constant per query and irrelevant for the
+// ranking), and per (query, database range) the k' smallest scores with their row ids.  The
+// caller (yb_knn.cu) re-ranks those in exact FP32 and certifies the result.
+//
+// Shape of the kernel (one persistent CTA per SM, 192 threads, warp-specialised):
+//   warp 4   TMA producer: query tile A (128 rows x d, resident in smem for a whole work item),
+//            database chunks B (256 rows x 32 floats, 4-stage ring), |b|^2 tiles (1-D bulk copy)
+//   warp 5   MMA issuer: tcgen05.mma.cta_group::1.kind::tf32, M=128 (queries) x N=256 (rows) x
+//            K=8 per instruction, SWIZZLE_128B K-major operands straight from the TMA layout,
+//            accumulators in TMEM, double buffered (2 x 256 columns) so the epilogue of tile t
+//            overlaps the MMAs of tile t+1
+//   warps 0-3 epilogue: thread t owns query t of the tile (TMEM lane t).  tcgen05.ld brings 32
+//            columns at a time; s = fma(acc, -2, |b|^2); a candidate with s < thr (the query's
+//            running k'-th best, a register) is appended to the query's list in L2-resident
+//            scratch.  When a list fills up the warp compacts it cooperatively with a 4-pass
+//            radix select and tightens thr.  This replaces the reference's binheap
+//            (yael/binheap.c:139-156) with the same strict '<' admission rule.
+// Work items are (query tile, database range) pairs walked range-major so that the CTAs that
+// run concurrently stream the same database range and share it through L2.
+#include <cuda.h>
+
 #include "yb_common.cuh"
 #include "yb_internal.cuh"
+
 namespace yb {
-Tf32Plan tf32_plan(int, int, int, int) { Tf32Plan p = {}; return p; }
-int tf32_shortlist(const Tf32Plan &, int, int, int, const float *, const float *, const float *,
-                   float2 *, float *, void *, cudaStream_t) {
-  return fail(5, "tf32 path not built");
+
+// ------------------------------------------------------------------ constants
+constexpr int TM = 128;          // queries per tile (MMA M)
+constexpr int TN = 256;          // database rows per tile (MMA N)
+constexpr int KC = 32;           // floats per K chunk = one 128-byte swizzle span
+constexpr int MAX_NKC = 4;       // d <= 128
+constexpr int STAGES = 4;        // B ring depth
+constexpr int NBN = 4;           // |b|^2 ring depth
+constexpr int A_CHUNK_BYTES = TM * KC * 4;  // 16 KB
+constexpr int B_CHUNK_BYTES = TN * KC * 4;  // 32 KB
+constexpr int EPI_THREADS = 128;
+constexpr int TF32_THREADS = 192;
+
+struct Smem {  // offsets inside the 1024-byte aligned dynamic shared memory block
+  static constexpr int a_off = 0;
+  static constexpr int b_off = MAX_NKC * A_CHUNK_BYTES;
+  static constexpr int bn_off = b_off + STAGES * B_CHUNK_BYTES;
+  static constexpr int hist_off = bn_off + NBN * TN * 4;
+  static constexpr int bar_off = hist_off + 4 * 256 * 4;
+  // barriers (8 bytes each)
+  static constexpr int a_full = 0, a_empty = 1, b_full = 2, b_empty = b_full + STAGES,
+                       n_full = b_empty + STAGES, n_empty = n_full + NBN,
+                       t_full = n_empty + NBN, t_empty = t_full + 2, nbar = t_empty + 2;
+  static constexpr int tmem_ptr_off = bar_off + nbar * 8;
+  static constexpr int total = tmem_ptr_off + 16;
+};
+constexpr int TF32_SMEM_BYTES = Smem::total + 1024;  // slack for the manual 1 KB alignment
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes,
+                                             uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {  // arrives on bar when prior MMAs retire
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, TF32 inputs, FP32 accumulate
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+        "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024
+// bytes apart (SBO), descriptor version 1 (sm_100), layout type 2.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  uint64_t desc = 0;
+  desc |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, 16-byte units
+  desc |= (uint64_t)1 << 16;                         // leading byte offset (unused with swizzle)
+  desc |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset
+  desc |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+  desc |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  return desc;
+}
+// instruction descriptor, kind::tf32: D=F32, A=B=TF32, both K-major, N=256, M=128
+constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) |
+                                ((uint32_t)(TM >> 4) << 24);
+
+// ------------------------------------------------------------------ parameters
+struct Tf32Params {
+  int nq, nb, d;
+  int nkc;            // K chunks of 32 floats
+  int last_k8;        // K=8 steps in the last chunk
+  int tiles_q;        // query tiles
+  int nbt;            // database tiles (256 rows)
+  int range_tiles;    // database tiles per range
+  int splits;         // ranges
+  int items;          // tiles_q * splits
+  int kprime, cap;
+  const float *bnorm;  // [nbt*256], padded with +inf
+  float2 *scratch;     // [gridDim.x][128][cap] append lists
+  float *out_score;    // [nq][splits][kprime]
+  int *out_id;         // [nq][splits][kprime]
+  float *dump;         // debug: [nq][nb] raw scores (lists are not produced)
+};
+
+// ------------------------------------------------------------------ warp-cooperative compaction
+// Reduce lane `owner`'s list (n entries, global memory) to its kp smallest scores in place.
+// Returns the new admission threshold (the kp-th smallest score): every dropped entry and
+// every later candidate with score >= thr is not among the kp smallest.
+__device__ __forceinline__ float warp_select_compact(float2 *list, int n, int kp, int *hist) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  uint32_t prefix = 0, mask = 0;
+  int rem = kp;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) hist[lane * 8 + u] = 0;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      uint32_t key = float_key(list[i].x);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+    }
+    __syncwarp();
+    int loc[8], s = 0;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      loc[u] = hist[lane * 8 + u];
+      s += loc[u];
+    }
+    int inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    int off = inc - s;
+    int found = -1, newrem = 0;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      if (found < 0 && off < rem && rem <= off + loc[u]) {
+        found = lane * 8 + u;
+        newrem = rem - off;
+      }
+      off += loc[u];
+    }
+    unsigned who = __ballot_sync(0xffffffffu, found >= 0);
+    int src = __ffs(who) - 1;
+    found = __shfl_sync(0xffffffffu, found, src);
+    rem = __shfl_sync(0xffffffffu, newrem, src);
+    prefix |= (uint32_t)found << shift;
+    mask |= 0xffu << shift;
+    __syncwarp();
+  }
+  const uint32_t pivot = prefix;
+  int out = 0, eq_taken = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    float2 e = make_float2(0.f, 0.f);
+    uint32_t key = 0xffffffffu;
+    if (i < n) {
+      e = list[i];
+      key = float_key(e.x);
+    }
+    const bool eq = key == pivot;
+    const unsigned eqb = __ballot_sync(0xffffffffu, eq);
+    const bool keep = (i < n) && (key < pivot || (eq && eq_taken + __popc(eqb & lt_mask) < rem));
+    const unsigned kb = __ballot_sync(0xffffffffu, keep);
+    if (keep) list[out + __popc(kb & lt_mask)] = e;
+    out += __popc(kb);
+    eq_taken += __popc(eqb);
+    __syncwarp();
+  }
+  const uint32_t bits = (pivot & 0x80000000u) ? (pivot & 0x7fffffffu) : ~pivot;
+  return __uint_as_float(bits);
+}
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(TF32_THREADS, 1)
+k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_b,
+           const Tf32Params P) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto bar = [&](int i) { return sbase + Smem::bar_off + 8 * i; };
+  volatile uint32_t *tmem_ptr_smem = (volatile uint32_t *)(smem + Smem::tmem_ptr_off);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(Smem::a_full), 1);
+    mbar_init(bar(Smem::a_empty), 1);
+    for (int i = 0; i < STAGES; i++) {
+      mbar_init(bar(Smem::b_full + i), 1);
+      mbar_init(bar(Smem::b_empty + i), 1);
+    }
+    for (int i = 0; i < NBN; i++) {
+      mbar_init(bar(Smem::n_full + i), 1);
+      mbar_init(bar(Smem::n_empty + i), EPI_THREADS);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(bar(Smem::t_full + i), 1);
+      mbar_init(bar(Smem::t_empty + i), EPI_THREADS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {  // TMEM: all 512 columns (2 accumulator buffers of 256)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     sbase + Smem::tmem_ptr_off),
+                 "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int first_item = blockIdx.x, item_step = gridDim.x;
+
+  if (warp == 4) {
+    // ======================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t icount = 0, ccount = 0, tcount = 0;
+      for (int item = first_item; item < P.items; item += item_step, icount++) {
+        const int sp = item / P.tiles_q, qt = item - sp * P.tiles_q;
+        const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
+        // query tile: wait until the MMAs of the previous item have drained A
+        mbar_wait(bar(Smem::a_empty), (icount & 1) ^ 1);
+        mbar_expect_tx(bar(Smem::a_full), (uint32_t)(P.nkc * A_CHUNK_BYTES));
+        for (int kc = 0; kc < P.nkc; kc++)
+          tma_load_2d(sbase + Smem::a_off + kc * A_CHUNK_BYTES, &map_q, bar(Smem::a_full), kc * KC,
+                      qt * TM);
+        for (int jt = jt0; jt < jt1; jt++, tcount++) {
+          const uint32_t slot = tcount % NBN;
+          mbar_wait(bar(Smem::n_empty + slot), ((tcount / NBN) & 1) ^ 1);
+          mbar_expect_tx(bar(Smem::n_full + slot), TN * 4);
+          bulk_load_1d(sbase + Smem::bn_off + slot * TN * 4, P.bnorm + (size_t)jt * TN, TN * 4,
+                       bar(Smem::n_full + slot));
+          for (int kc = 0; kc < P.nkc; kc++, ccount++) {
+            const uint32_t st = ccount % STAGES;
+            mbar_wait(bar(Smem::b_empty + st), ((ccount / STAGES) & 1) ^ 1);
+            mbar_expect_tx(bar(Smem::b_full + st), B_CHUNK_BYTES);
+            tma_load_2d(sbase + Smem::b_off + st * B_CHUNK_BYTES, &map_b, bar(Smem::b_full + st),
+                        kc * KC, jt * TN);
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ======================================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t icount = 0, ccount = 0, tcount = 0;
+      for (int item = first_item; item < P.items; item += item_step, icount++) {
+        const int sp = item / P.tiles_q;
+        const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
+        mbar_wait(bar(Smem::a_full), icount & 1);
+        for (int jt = jt0; jt < jt1; jt++, tcount++) {
+          const uint32_t buf = tcount & 1;
+          mbar_wait(bar(Smem::t_empty + buf), ((tcount >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * TN;
+          for (int kc = 0; kc < P.nkc; kc++, ccount++) {
+            const uint32_t st = ccount % STAGES;
+            mbar_wait(bar(Smem::b_full + st), (ccount / STAGES) & 1);
+            tc_fence_after();
+            const int nk8 = (kc == P.nkc - 1) ? P.last_k8 : 4;
+            const uint64_t adesc = smem_desc_sw128(sbase + Smem::a_off + kc * A_CHUNK_BYTES);
+            const uint64_t bdesc = smem_desc_sw128(sbase + Smem::b_off + st * B_CHUNK_BYTES);
+            for (int k8 = 0; k8 < nk8; k8++) {
+              // advancing K inside the 128-byte swizzle span: +32 bytes = +2 in 16-byte units
+              tc_mma_tf32(d_tmem, adesc + (uint64_t)(2 * k8), bdesc + (uint64_t)(2 * k8),
+                          IDESC_TF32, (kc | k8) != 0);
+            }
+            tc_commit(bar(Smem::b_empty + st));  // smem slot reusable once these MMAs retire
+          }
+          tc_commit(bar(Smem::t_full + buf));  // accumulator complete
+        }
+        tc_commit(bar(Smem::a_empty));  // query tile no longer needed
+      }
+    }
+  } else {
+    // ======================================================================== epilogue
+    const int t = threadIdx.x;  // query row inside the tile == TMEM lane
+    int *hist = (int *)(smem + Smem::hist_off) + warp * 256;
+    float2 *mylist = P.scratch + ((size_t)blockIdx.x * TM + t) * P.cap;
+    const float inf = __uint_as_float(0x7f800000u);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t tcount = 0;
+    for (int item = first_item; item < P.items; item += item_step) {
+      const int sp = item / P.tiles_q, qt = item - sp * P.tiles_q;
+      const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
+      const int q = qt * TM + t;
+      const bool valid = q < P.nq;
+      float thr = valid ? inf : -inf;
+      int cnt = 0;
+      for (int jt = jt0; jt < jt1; jt++, tcount++) {
+        const uint32_t buf = tcount & 1, slot = tcount % NBN;
+        mbar_wait(bar(Smem::n_full + slot), (tcount / NBN) & 1);
+        mbar_wait(bar(Smem::t_full + buf), (tcount >> 1) & 1);
+        tc_fence_after();
+        const float *bn = (const float *)(smem + Smem::bn_off + slot * TN * 4);
+        const int n0 = jt * TN;
+#pragma unroll 1
+        for (int g = 0; g < TN / 32; g++) {
+          uint32_t v[32];
+          tc_ld32(lane_addr + buf * TN + g * 32, v);
+          tc_wait_ld();
+          if (P.dump) {
+            if (valid) {
+#pragma unroll
+              for (int c = 0; c < 32; c++) {
+                int n = n0 + g * 32 + c;
+                if (n < P.nb)
+                  P.dump[(size_t)q * P.nb + n] = fmaf(__uint_as_float(v[c]), -2.0f, bn[g * 32 + c]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int c4 = 0; c4 < 8; c4++) {
+              const float4 b4 = *reinterpret_cast<const float4 *>(bn + g * 32 + c4 * 4);
+              const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                const float s = fmaf(__uint_as_float(v[c4 * 4 + u]), -2.0f, bb[u]);
+                if (s < thr) {
+                  mylist[cnt] = make_float2(s, __int_as_float(n0 + g * 32 + c4 * 4 + u));
+                  cnt++;
+                }
+              }
+            }
+          }
+        }
+        // accumulator buffer and |b|^2 slot are free again
+        tc_fence_before();
+        mbar_arrive(bar(Smem::t_empty + buf));
+        mbar_arrive(bar(Smem::n_empty + slot));
+        // keep room for a full tile of appends in every list of the warp
+        unsigned need = __ballot_sync(0xffffffffu, cnt > P.cap - TN);
+        while (need) {
+          const int owner = __ffs(need) - 1;
+          need &= need - 1;
+          float2 *l = (float2 *)__shfl_sync(0xffffffffu, (unsigned long long)mylist, owner);
+          const int n = __shfl_sync(0xffffffffu, cnt, owner);
+          __syncwarp();
+          const float nt = warp_select_compact(l, n, P.kprime, hist);
+          if (lane == owner) {
+            thr = nt;
+            cnt = P.kprime;
+          }
+        }
+      }
+      if (!P.dump) {
+        // final compaction of over-full lists, then publish the shortlist of this item
+        unsigned need = __ballot_sync(0xffffffffu, cnt > P.kprime);
+        while (need) {
+          const int owner = __ffs(need) - 1;
+          need &= need - 1;
+          float2 *l = (float2 *)__shfl_sync(0xffffffffu, (unsigned long long)mylist, owner);
+          const int n = __shfl_sync(0xffffffffu, cnt, owner);
+          __syncwarp();
+          const float nt = warp_select_compact(l, n, P.kprime, hist);
+          if (lane == owner) {
+            thr = nt;
+            cnt = P.kprime;
+          }
+        }
+        __syncwarp();
+        if (valid) {
+          float *os = P.out_score + ((size_t)q * P.splits + sp) * P.kprime;
+          int *oi = P.out_id + ((size_t)q * P.splits + sp) * P.kprime;
+          for (int e = 0; e < P.kprime; e++) {
+            if (e < cnt) {
+              float2 x = mylist[e];
+              os[e] = x.x;
+              oi[e] = __float_as_int(x.y);
+            } else {
+              os[e] = inf;
+              oi[e] = -1;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+__global__ void k_fill_f32(float *p, long n, float v) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D map over a row-major [rows][d] float matrix, box = 32 floats x box_rows, 128-byte swizzle,
+// out-of-bounds elements read as zero
+static int make_map(CUtensorMap *m, const float *ptr, long rows, int d, int box_rows) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return fail(6, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)d * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(6, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+  return 0;
+}
+
+static int kprime_for(int k) {
+  int a = 2 * k, b = k + 32 < 8 * k ? k + 32 : 8 * k;
+  return a > b ? a : b;
+}
+
+Tf32Plan tf32_plan(int nq, int nb, int d, int k) {
+  Tf32Plan p = {};
+  if (d < 1 || d > MAX_NKC * KC || (d % 4) != 0) return p;  // TMA: 16-byte row pitch; A resident
+  if (nq < 1 || nb < 1) return p;
+  const int kp = kprime_for(k);
+  if (kp > 1024) return p;
+  int cap = pow2_ceil(8 * kp);
+  if (cap < 512) cap = 512;
+  if (cap > 4096) cap = 4096;
+  if (cap < kp + 2 * TN) cap = pow2_ceil(kp + 2 * TN);
+  const int G = sm_count();
+  const int tiles_q = (nq + TM - 1) / TM;
+  const int nbt = (nb + TN - 1) / TN;
+  // database ranges: the smallest split count whose last wave is at least 90 % full; every
+  // range at least 8 tiles long
+  int best_s = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= 16; s++) {
+    if (s > 1 && nbt / s < 8) break;
+    int range = (nbt + s - 1) / s;
+    int s_eff = (nbt + range - 1) / range;
+    long items = (long)tiles_q * s_eff;
+    long waves = (items + G - 1) / G;
+    double eff = (double)items / (double)(waves * G);
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best_s = s;
+    }
+    if (eff >= 0.9) break;
+  }
+  int range = (nbt + best_s - 1) / best_s;
+  p.splits = (nbt + range - 1) / range;
+  p.kprime = kp;
+  p.cap = cap;
+  long items = (long)tiles_q * p.splits;
+  p.ctas = (int)(items < G ? items : G);
+  p.ws_bytes = Carver::need(sizeof(float2) * (size_t)p.ctas * TM * cap) + 256;
+  p.ok = 1;
+  return p;
+}
+
+static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, const float *base,
+                       const float *query, const float *bnorm_padded, float *out_score,
+                       int *out_id, float *dump, void *ws, cudaStream_t st) {
+  if ((((uintptr_t)base) & 15) || (((uintptr_t)query) & 15))
+    return fail(6, "tf32 path needs 16-byte aligned matrices");
+  CUtensorMap mq, mb;
+  int rc;
+  if ((rc = make_map(&mq, query, nq, d, TM))) return rc;
+  if ((rc = make_map(&mb, base, nb, d, TN))) return rc;
+  Tf32Params P = {};
+  P.nq = nq; P.nb = nb; P.d = d;
+  P.nkc = (d + KC - 1) / KC;
+  P.last_k8 = (d - (P.nkc - 1) * KC + 7) / 8;
+  P.tiles_q = (nq + TM - 1) / TM;
+  P.nbt = (nb + TN - 1) / TN;
+  P.range_tiles = (P.nbt + plan.splits - 1) / plan.splits;
+  P.splits = plan.splits;
+  P.items = P.tiles_q * P.splits;
+  P.kprime = plan.kprime;
+  P.cap = plan.cap;
+  P.bnorm = bnorm_padded;
+  P.scratch = (float2 *)ws;
+  P.out_score = out_score;
+  P.out_id = out_id;
+  P.dump = dump;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_knn_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TF32_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(6, "cannot reserve %d bytes of shared memory: %s",
+                                      TF32_SMEM_BYTES, cudaGetErrorString(e));
+    attr = true;
+  }
+  k_knn_tf32<<<plan.ctas, TF32_THREADS, TF32_SMEM_BYTES, st>>>(mq, mb, P);
+  YB_LAUNCH_CHECK();
+  return 0;
+}
+
+int tf32_shortlist(const Tf32Plan &plan, int nq, int nb, int d, const float *base,
+                   const float *query, const float *bnorm_padded, float *out_score, int *out_id,
+                   void *ws, cudaStream_t st) {
+  return launch_tf32(plan, nq, nb, d, base, query, bnorm_padded, out_score, out_id, nullptr, ws,
+                     st);
+}
+
+long tf32_padded_rows(int nb) { return (long)((nb + TN - 1) / TN) * TN; }
+
+int fill_f32(float *p, long n, float v, cudaStream_t st) {
+  if (n <= 0) return 0;
+  k_fill_f32<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v);
+  YB_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace yb
+
+using namespace yb;
+
+// Debug / test entry: raw TF32 scores s[q][n] = |b_n|^2 - 2 <q, b_n> for every pair (the tensor
+// path with the top-k switched off).  Used by tests to bound the TF32 error against the
+// certificate's model, and for bring-up.
+extern "C" int yb_debug_tf32_scores(int nq, int nb, int d, const float *base, const float *query,
+                                    float *scores, yb_stream_t s) {
+  Guard g;
+  cudaStream_t st = stream_of(s);
+  Tf32Plan plan = tf32_plan(nq, nb, d, 1);
+  if (!plan.ok) return fail(3, "tf32 path does not support this shape (d=%d)", d);
+  long padded = tf32_padded_rows(nb);
+  ScratchScope ws(Carver::need(4ull * padded) + Carver::need(plan.ws_bytes), st);
+  Carver c(ws.p);
+  float *bn = c.take<float>(padded);
+  void *tws = c.take<char>(plan.ws_bytes);
+  int rc;
+  if ((rc = row_norms_seq(base, nb, d, d, bn, nullptr, st))) return rc;
+  if ((rc = fill_f32(bn + nb, padded - nb, __builtin_inff(), st))) return rc;
+  return launch_tf32(plan, nq, nb, d, base, query, bn, nullptr, nullptr, scores, tws, st);
+}
