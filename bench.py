@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the yael hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path
+
+Workload (BASELINE.json configs[1]): exact k-NN, SIFT1M shape -- 1M x 128 float32 database,
+10 000 queries, k = 100, squared L2, through knn_full's semantics.  One "step" = one pass of
+the hot path over the batch of 10 000 queries.  Synthetic uniform[0,1) data, fixed seeds.
+
+  value   queries/s with the database and the queries already resident in HBM (device-level
+          C ABI yb_knn_l2 on the caller's stream), CUDA events, max over ranks.
+  e2e     the same through the drop-in call knn_full_thread() with HOST (pinned) buffers:
+          host->device copies of base + queries and device->host copies of ids + distances
+          are inside the timed region.
+  roofline  the tcgen05 TF32 shortlist kernel: algorithmic 2*nq*nb*d FLOP / its own average
+          duration (CUDA events on the launching stream, yb_prof_*).
+  cpu_baseline  the unmodified reference (oracle/_ref, OpenBLAS + OpenMP) or the oracle port on
+          the host cores, on a bounded sample of the same workload.
+
+N > 1 (torchrun, one rank per GPU): every rank holds its own 1M x 128 shard of an N-million
+row database and scans it for all queries; the per-rank top-k lists are all-gathered over NCCL
+and merged on every rank.  value = N * nq / time: query x 1M-shard scans per
+second ("weak": per-GPU work is fixed).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NB, NQ, D, K = 1_000_000, 10_000, 128, 100
+METRIC = "kNN queries/s (1M x 128 db, k=100)"
+UNIT = "queries/s"
+
+
+def gen_data(rank):
+    r = np.random.RandomState(1234 + 7919 * rank)
+    base = r.random_sample((NB, D)).astype(np.float32)
+    rq = np.random.RandomState(1235)  # same queries on every rank
+    query = rq.random_sample((NQ, D)).astype(np.float32)
+    return base, query
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU baseline
+def cpu_reference_rate(base, query, target_s=15.0, max_q=NQ):
+    """Time the reference's own CPU implementation (knn_full_thread, yael/nn.c:679-699) on a
+    bounded sample: all host threads, OPENBLAS_NUM_THREADS=1 (yael threads itself)."""
+    from oracle import bindings as ob
+    cores = len(os.sched_getaffinity(0))
+    if ob.have_ref():
+        kind = "reference"
+        fn = lambda b, q: ob.ref_knn(b, q, K, nt=cores)
+    else:
+        kind = "port"
+        fn = lambda b, q: ob.orc_knn(b, q, K, dot_mode=ob.DOT_F32_SEQ, nt=cores)
+    probe = min(4 * cores if 4 * cores >= 64 else 64, max_q)
+    t = time.perf_counter()
+    fn(base, query[:probe])
+    dt = time.perf_counter() - t
+    rate = probe / dt
+    n = int(min(max_q, max(probe, rate * target_s)))
+    n = max(cores, (n // cores) * cores)
+    t = time.perf_counter()
+    fn(base, query[:n])
+    dt = time.perf_counter() - t
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d of %d queries against the full 1M x 128 database, k=100, %.1f s" % (n, NQ, dt)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path on the host cores, same metric / config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, query = gen_data(0)
+    from oracle import bindings as ob
+    cores = len(os.sched_getaffinity(0))
+    kind = "reference" if ob.have_ref() else "port"
+    fn = (lambda b, q: ob.ref_knn(b, q, K, nt=cores)) if ob.have_ref() else \
+        (lambda b, q: ob.orc_knn(b, q, K, nt=cores))
+    # size a step so the whole run (warmup + steps) stays within a few minutes
+    probe = min(max(64, 4 * cores), NQ)
+    t = time.perf_counter()
+    fn(base, query[:probe])
+    rate = probe / (time.perf_counter() - t)
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    n = int(min(NQ, max(probe, rate * budget)))
+    n = max(cores, (n // cores) * cores)
+    for _ in range(args.warmup):
+        fn(base, query[:n])
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        fn(base, query[:n])
+    dt = (time.perf_counter() - t) / args.steps
+    val = n / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic uniform[0,1), seeds 1234/1235",
+        "config": {"workload": "exact kNN 1M x 128 db, 10k queries, k=100 (BASELINE configs[1])",
+                   "step": "%d of the 10000 queries per step (bounded CPU sample)" % n},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": "%d queries per step against the full database" % n},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def measure_tf32_peak(torch, dev):
+    """cuBLAS TF32 GEMM throughput measured the way MEASURED_PEAKS.json measures bf16
+    (8192^3, best of 10): the denominator for the kind::tf32 kernel."""
+    try:
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(3):
+            a @ b
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        torch.backends.cuda.matmul.allow_tf32 = old
+        del a, b
+        torch.cuda.empty_cache()
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import yael_b200
+    from yael_b200 import dist as ydist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    L = yael_b200.lib()
+    if L.yb_device_count() <= 0:
+        raise SystemExit("bench.py needs a GPU: " + L.yb_last_error().decode())
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    L.yb_set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    base_h, query_h = gen_data(rank)
+    base = torch.from_numpy(base_h).to(dev)
+    query = torch.from_numpy(query_h).to(dev)
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+    searcher = ydist.ShardedKnn(base, K, rank=rank, world=world)
+
+    def step():
+        return searcher.search(query)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    engine = L.yb_last_knn_engine()
+    uncert = L.yb_last_knn_uncertified()
+
+    # ---- timed region: HBM-resident inputs, CUDA events on the launching stream
+    L.yb_prof_enable(1)
+    L.yb_prof_ms(1, None, 1)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    L.yb_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    launches = L.yb_launch_count(0)
+    ms = e0.elapsed_time(e1) / args.steps
+    cnt = C.c_long(0)
+    phase_ms = {}
+    for ph, name in ((0, "norms"), (1, "tf32_shortlist"), (2, "merge_select"), (3, "rerank"),
+                     (4, "exact_fallback"), (5, "exact_slab"), (6, "row_select")):
+        t = L.yb_prof_ms(ph, C.byref(cnt), 0)
+        if cnt.value:
+            phase_ms[name] = t / cnt.value
+    L.yb_prof_ms(0, None, 1)
+    L.yb_prof_enable(0)
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    value = world * NQ / (ms * 1e-3)
+
+    # ---- end to end through the drop-in C call with pinned host buffers
+    bh = torch.from_numpy(base_h).pin_memory()
+    qh = torch.from_numpy(query_h).pin_memory()
+    idx_h = torch.empty((NQ, K), dtype=torch.int32).pin_memory()
+    dis_h = torch.empty((NQ, K), dtype=torch.float32).pin_memory()
+    e2e_steps = max(2, min(args.steps, 5))
+
+    def e2e_step():
+        searcher.search_host(bh.numpy(), qh.numpy(), idx_h.numpy(), dis_h.numpy())
+
+    e2e_step()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    t_e2e = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        tmax = torch.tensor([t_e2e], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        t_e2e = float(tmax.item())
+    e2e = {"value": world * NQ / t_e2e, "unit": UNIT,
+           "h2d_bytes_per_step": int(base_h.nbytes + query_h.nbytes),
+           "d2h_bytes_per_step": int(NQ * K * 8), "ms_per_step": t_e2e * 1e3}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf32_meas = measure_tf32_peak(torch, dev) if world == 1 else None
+    bf16_peak = peaks.get("bf16_tflops", 1590.0)
+    if tf32_meas:
+        peak, peak_src = tf32_meas, "cuBLAS TF32 8192^3 GEMM measured in this run (burst)"
+    else:
+        peak = bf16_peak / 2.0
+        peak_src = ("half of MEASURED_PEAKS.json bf16_tflops" if peaks else
+                    "half of the fallback 1590 TF/s bf16 (of fallback)")
+    roof = None
+    if "tf32_shortlist" in phase_ms:
+        kms = phase_ms["tf32_shortlist"]
+        ach = 2.0 * NQ * NB * D / (kms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "k_knn_tf32", "achieved": ach, "peak": peak,
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "kernel_ms": kms, "peak_source": peak_src,
+                "frac_of_bf16_peak": ach / bf16_peak,
+                "algorithmic_flops_per_launch": 2.0 * NQ * NB * D}
+    elif "exact_slab" in phase_ms:
+        kms = phase_ms["exact_slab"]
+        roof = {"bound": "tensor", "kernel": "k_l2_simt (exact FP32 engine, CUDA cores)",
+                "achieved": 2.0 * NQ * NB * D / (kms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                "frac": 2.0 * NQ * NB * D / (kms * 1e-3) / 1e12 / peak, "traffic": None,
+                "peak_source": peak_src}
+
+    cpu = cpu_reference_rate(base_h, query_h)
+
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "tf32 shortlist + f32 exact re-rank",
+        "data": "synthetic uniform[0,1), seeds 1234/1235",
+        "config": {
+            "workload": "exact kNN, SIFT1M shape: 1M x 128 float32 database per GPU, 10000 queries, "
+                        "k=100 (BASELINE configs[1]); knn_full semantics",
+            "parallelism": ("single GPU" if world == 1 else
+                            "database sharded x%d (1M rows per rank), NCCL all-gather of per-rank "
+                            "top-k + merge; value counts query x 1M-shard scans" % world),
+            "l2": "database (512 MB) is larger than L2 (126 MB): no flush needed between steps",
+            "engine": "tcgen05 TF32 + FP32 re-rank" if engine == 1 else "exact FP32 SIMT",
+            "uncertified_queries_redone_exactly": int(uncert),
+            "phase_ms": phase_ms,
+        },
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roof, "cpu_baseline": cpu,
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

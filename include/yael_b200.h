@@ -46,6 +46,13 @@ long yb_last_knn_uncertified(void);
 /* force an engine for testing: -1 auto (default), 0 exact SIMT only, 1 TF32 whenever legal */
 void yb_set_knn_engine(int engine);
 
+/* phase timing with CUDA events on the launching stream (off by default).  Phases:
+ * 0 row norms, 1 tcgen05 TF32 shortlist kernel, 2 shortlist merge-select, 3 exact FP32 re-rank,
+ * 4 exact-engine fallback, 5 exact distance slab (k_l2_simt), 6 per-row select (k_kmin_rows),
+ * 7 Hamming scan, 8 k-means accumulate (sort + segmented sums), 9 k-means scale */
+void yb_prof_enable(int on);
+double yb_prof_ms(int phase, long *count, int reset);
+
 /* device memory helpers for C callers.  yb_malloc/yb_free go through a small caching pool
  * (freed blocks are kept for reuse; yb_release_scratch() returns them to the driver);
  * allocation failure prints a message and aborts, as the reference's allocators do

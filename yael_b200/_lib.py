@@ -123,6 +123,8 @@ DEVICE = {
     "yb_last_knn_engine": (C.c_int, []),
     "yb_last_knn_uncertified": (C.c_long, []),
     "yb_set_knn_engine": (None, [C.c_int]),
+    "yb_prof_enable": (None, [C.c_int]),
+    "yb_prof_ms": (C.c_double, [C.c_int, C.POINTER(C.c_long), C.c_int]),
     "yb_malloc": (_vp, [C.c_size_t]),
     "yb_free": (None, [_vp]),
     "yb_is_device_ptr": (C.c_int, [_vp]),

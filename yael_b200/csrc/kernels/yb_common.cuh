@@ -22,6 +22,15 @@ void *scratch_reserve(size_t bytes, cudaStream_t on);
 void scratch_done(cudaStream_t on);
 int sm_count();
 void count_launch(long n = 1);
+// phase timing for bench.py (no-ops unless yb_prof_enable(1)); phases: see yael_b200.h
+int prof_begin(int phase, cudaStream_t st);
+void prof_end(int handle, cudaStream_t st);
+struct ProfScope {
+  int h;
+  cudaStream_t st;
+  ProfScope(int phase, cudaStream_t s) : h(prof_begin(phase, s)), st(s) {}
+  ~ProfScope() { prof_end(h, st); }
+};
 
 struct Guard {  // RAII lock of the library-wide mutex (the reference promises re-entrancy:
   Guard();      // doc/index.rst:55-58; callers may come from several host threads)

@@ -427,6 +427,7 @@ extern "C" int yb_nn_hamming(int nq, int nb, int ncodes, int k, const uint8_t *b
   unsigned long long *lists = c.take<unsigned long long>(nslots * cap);
   int *counts = c.take<int>(nslots);
   dim3 grid(gx, S);
+  ProfScope ps(7, st);
   YB_DISPATCH_W(W, (k_nn_hamming_scan<WW><<<grid, HT, 0, st>>>(nq, nb, k, cap, pb, pq, split_len,
                                                                lists, counts, id_offset)));
   YB_LAUNCH_CHECK();

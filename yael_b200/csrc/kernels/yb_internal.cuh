@@ -23,12 +23,13 @@ struct Tf32Plan {
   int ok;          // 0: shape not supported by the tensor-core path
   int kprime;      // shortlist length per (query, split)
   int cap;         // append-buffer capacity per (query, split)
-  int splits;      // database splits per query tile
+  int splits;      // database ranges per query tile
+  int lists;       // shortlists produced per query (2 per range: one per column half)
   int ctas;        // persistent grid size
   size_t ws_bytes; // workspace for buffers + shortlists
 };
 Tf32Plan tf32_plan(int nq, int nb, int d, int k);
-// Produces, for every query, `splits` shortlists of `kprime` candidates: out_score[q][s][e] =
+// Produces, for every query, `lists` shortlists of `kprime` candidates: out_score[q][s][e] =
 // |b|^2 - 2<q,b> evaluated with TF32 operands, out_id[q][s][e] the row id (unused slots:
 // +inf / -1).  Every database row that is NOT listed for (q, s) has a TF32 score >= the
 // largest listed score of a full list.  bnorm_padded: |b|^2 for tf32_padded_rows(nb) rows,

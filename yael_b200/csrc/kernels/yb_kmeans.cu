@@ -327,6 +327,7 @@ extern "C" int yb_kmeans_accumulate(int d, int n, int k, const float *v, const i
                 2 * Carver::need(4ull * (k + 1)) + Carver::need(4ull * max_pieces) +
                 Carver::need(4ull * (size_t)max_pieces * d) + Carver::need(8 * 1024 + 64);
   ScratchScope ws(need, st);
+  ProfScope ps(8, st);
   Carver c(ws.p);
   int2 *bufA = c.take<int2>(n > 0 ? n : 1);
   int2 *bufB = c.take<int2>(n > 0 ? n : 1);

@@ -297,11 +297,17 @@ int knn_exact(int nq, int nb, int d, int k, const float *base, const float *quer
   if ((rc = row_norms_seq(query, nq, d, d, nullptr, bn, st))) return rc;
   for (long q0 = 0; q0 < nq; q0 += (long)rows) {
     long nr = nq - q0 < (long)rows ? nq - q0 : (long)rows;
-    if ((rc = l2_matrix(d, nb, nr, base, d, query + q0 * d, d, an, bn + q0, w, slab, nb, st)))
-      return rc;
-    if ((rc = kmin_rows(slab, nb, nb, nr, k, +1, assign + q0 * k, dis + q0 * k, id_offset,
-                        k == 1 ? 1 : 0, kws, st)))
-      return rc;
+    {
+      ProfScope ps(5, st);
+      if ((rc = l2_matrix(d, nb, nr, base, d, query + q0 * d, d, an, bn + q0, w, slab, nb, st)))
+        return rc;
+    }
+    {
+      ProfScope ps(6, st);
+      if ((rc = kmin_rows(slab, nb, nb, nr, k, +1, assign + q0 * k, dis + q0 * k, id_offset,
+                          k == 1 ? 1 : 0, kws, st)))
+        return rc;
+    }
   }
   return 0;
 }
@@ -355,13 +361,13 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
   if (!plan.ok) return -1000;
   if (force < 0 && (double)nq * nb < 1e6) return -1000;  // tiny problems: not worth a TMA setup
   const int kp = plan.kprime;
-  const int stride = plan.splits * kp;  // candidates per query produced by the tensor pass
+  const int stride = plan.lists * kp;  // candidates per query produced by the tensor pass
   const int m = kp;                     // candidates per query that are re-ranked
   const int m_pad = pow2_ceil(m < 2 ? 2 : m);
   size_t smem = rerank_smem_bytes(d, m, m_pad);
   if (smem > 200 * 1024) return -1000;
   const long padded = tf32_padded_rows(nb);
-  const bool need_sel = plan.splits > 1;
+  const bool need_sel = plan.lists > 1;
 
   size_t need = Carver::need(sizeof(float) * (size_t)padded) + Carver::need(64) +
                 Carver::need(sizeof(float) * (size_t)nq * stride) +
@@ -384,14 +390,21 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
     void *kws = c.take<char>(kmin_ws_bytes(nq, kp));
     void *tfws = c.take<char>(plan.ws_bytes);
     int rc;
-    if ((rc = row_norms_seq(base, nb, d, d, an, nullptr, st))) return rc;
-    if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
-    YB_CUDA(cudaMemsetAsync(scal, 0, 64, st));
-    k_sqrt_max<<<2 * sm_count(), 256, 0, st>>>(an, nb, scal);
-    YB_LAUNCH_CHECK();
-    if ((rc = tf32_shortlist(plan, nq, nb, d, base, query, an, cscore, cid, tfws, st))) return rc;
+    {
+      ProfScope ps(0, st);
+      if ((rc = row_norms_seq(base, nb, d, d, an, nullptr, st))) return rc;
+      if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
+      YB_CUDA(cudaMemsetAsync(scal, 0, 64, st));
+      k_sqrt_max<<<2 * sm_count(), 256, 0, st>>>(an, nb, scal);
+      YB_LAUNCH_CHECK();
+    }
+    {
+      ProfScope ps(1, st);
+      if ((rc = tf32_shortlist(plan, nq, nb, d, base, query, an, cscore, cid, tfws, st))) return rc;
+    }
     if (need_sel) {
       // merge the per-range shortlists: the kp smallest TF32 scores of the union
+      ProfScope ps(2, st);
       if ((rc = kmin_rows(cscore, stride, stride, nq, kp, +1, sel, nullptr, 0, 0, kws, st)))
         return rc;
     }
@@ -404,8 +417,11 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
     A.err_scale = kTf32ErrScale; A.bmax = scal; A.uncert_flags = flags;
     A.gsort = nullptr; A.m_pad = m_pad; A.k1 = (k == 1);
     rerank_attrs();
-    k_rerank<1><<<nq, 128, smem, st>>>(A);
-    YB_LAUNCH_CHECK();
+    {
+      ProfScope ps(3, st);
+      k_rerank<1><<<nq, 128, smem, st>>>(A);
+      YB_LAUNCH_CHECK();
+    }
     k_collect_flags<<<(nq + 255) / 256, 256, 0, st>>>(flags, nq, flag_list, (int *)(scal + 1));
     YB_LAUNCH_CHECK();
     YB_CUDA(cudaMemcpyAsync(&n_flag, scal + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -426,7 +442,10 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
       long tot = (long)n_flag * d;
       k_gather_rows<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(query, rows, n_flag, d, qsub);
       YB_LAUNCH_CHECK();
-      rc = knn_exact(n_flag, nb, d, k, base, qsub, nullptr, asub, dsub, id_offset, ews, st);
+      {
+        ProfScope ps(4, st);
+        rc = knn_exact(n_flag, nb, d, k, base, qsub, nullptr, asub, dsub, id_offset, ews, st);
+      }
       if (!rc) {
         tot = (long)n_flag * k;
         k_scatter_results<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(rows, n_flag, k, asub,

@@ -7,18 +7,20 @@
 // ranking), and per (query, database range) the k' smallest scores with their row ids.  The
 // caller (yb_knn.cu) re-ranks those in exact FP32 and certifies the result.
 //
-// Shape of the kernel (one persistent CTA per SM, 192 threads, warp-specialised):
-//   warp 4   TMA producer: query tile A (128 rows x d, resident in smem for a whole work item),
+// Shape of the kernel (one persistent CTA per SM, 320 threads, warp-specialised):
+//   warp 8   TMA producer: query tile A (128 rows x d, resident in smem for a whole work item),
 //            database chunks B (256 rows x 32 floats, 4-stage ring), |b|^2 tiles (1-D bulk copy)
-//   warp 5   MMA issuer: tcgen05.mma.cta_group::1.kind::tf32, M=128 (queries) x N=256 (rows) x
+//   warp 9   MMA issuer: tcgen05.mma.cta_group::1.kind::tf32, M=128 (queries) x N=256 (rows) x
 //            K=8 per instruction, SWIZZLE_128B K-major operands straight from the TMA layout,
 //            accumulators in TMEM, double buffered (2 x 256 columns) so the epilogue of tile t
 //            overlaps the MMAs of tile t+1
-//   warps 0-3 epilogue: thread t owns query t of the tile (TMEM lane t).  tcgen05.ld brings 32
-//            columns at a time; s = fma(acc, -2, |b|^2); a candidate with s < thr (the query's
-//            running k'-th best, a register) is appended to the query's list in L2-resident
-//            scratch.  When a list fills up the warp compacts it cooperatively with a 4-pass
-//            radix select and tightens thr.  This replaces the reference's binheap
+//   warps 0-7 epilogue: two warps per scheduler.  Thread (w, lane) owns query 32*(w%4)+lane of
+//            the tile (its TMEM lane) for the column half w/4 of every tile.  tcgen05.ld brings
+//            32 columns at a time; s = fma(acc, -2, |b|^2); a candidate with s < thr (the running
+//            k'-th best of this thread's list, a register) is appended to the list in
+//            L2-resident scratch by PREDICATED stores (no branch per candidate).  When a list
+//            fills up the warp compacts it cooperatively (keys in registers, 4-pass radix
+//            select) and tightens thr.  This replaces the reference's binheap
 //            (yael/binheap.c:139-156) with the same strict '<' admission rule.
 // Work items are (query tile, database range) pairs walked range-major so that the CTAs that
 // run concurrently stream the same database range and share it through L2.
@@ -38,15 +40,17 @@ constexpr int STAGES = 4;        // B ring depth
 constexpr int NBN = 4;           // |b|^2 ring depth
 constexpr int A_CHUNK_BYTES = TM * KC * 4;  // 16 KB
 constexpr int B_CHUNK_BYTES = TN * KC * 4;  // 32 KB
-constexpr int EPI_THREADS = 128;
-constexpr int TF32_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int TF32_THREADS = EPI_THREADS + 64;
+constexpr int HALF_N = TN / 2;   // columns per epilogue warp and tile
 
 struct Smem {  // offsets inside the 1024-byte aligned dynamic shared memory block
   static constexpr int a_off = 0;
   static constexpr int b_off = MAX_NKC * A_CHUNK_BYTES;
   static constexpr int bn_off = b_off + STAGES * B_CHUNK_BYTES;
   static constexpr int hist_off = bn_off + NBN * TN * 4;
-  static constexpr int bar_off = hist_off + 4 * 256 * 4;
+  static constexpr int bar_off = hist_off + EPI_WARPS * 256 * 4;
   // barriers (8 bytes each)
   static constexpr int a_full = 0, a_empty = 1, b_full = 2, b_empty = b_full + STAGES,
                        n_full = b_empty + STAGES, n_empty = n_full + NBN,
@@ -54,7 +58,7 @@ struct Smem {  // offsets inside the 1024-byte aligned dynamic shared memory blo
   static constexpr int tmem_ptr_off = bar_off + nbar * 8;
   static constexpr int total = tmem_ptr_off + 16;
 };
-constexpr int TF32_SMEM_BYTES = Smem::total + 1024;  // slack for the manual 1 KB alignment
+constexpr int TF32_SMEM_BYTES = Smem::total;
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -165,46 +169,60 @@ struct Tf32Params {
   int nbt;            // database tiles (256 rows)
   int range_tiles;    // database tiles per range
   int splits;         // ranges
+  int lists;          // shortlists per query = 2 * splits (one per range and column half)
   int items;          // tiles_q * splits
   int kprime, cap;
   const float *bnorm;  // [nbt*256], padded with +inf
-  float2 *scratch;     // [gridDim.x][128][cap] append lists
-  float *out_score;    // [nq][splits][kprime]
-  int *out_id;         // [nq][splits][kprime]
+  float2 *scratch;     // [gridDim.x][256][cap] append lists (score, id bits)
+  float *out_score;    // [nq][lists][kprime]
+  int *out_id;         // [nq][lists][kprime]
   float *dump;         // debug: [nq][nb] raw scores (lists are not produced)
 };
 
 // ------------------------------------------------------------------ warp-cooperative compaction
-// Reduce lane `owner`'s list (n entries, global memory) to its kp smallest scores in place.
-// Returns the new admission threshold (the kp-th smallest score): every dropped entry and
-// every later candidate with score >= thr is not among the kp smallest.
+// Reduce one query's list (n <= MAXL entries, global memory, SoA) to its kp smallest scores in
+// place.  Returns the new admission threshold (the kp-th smallest score): every dropped entry
+// and every later candidate with score >= thr is not among the kp smallest.
+//
+// The keys are pulled into registers once (MAXL/32 per lane, coalesced, all loads in flight
+// together), a 4 x 8-bit radix select runs on the registers with a per-warp shared-memory
+// histogram, and one more sweep moves the survivors' ids.
+constexpr int MAXL = 1024;
+constexpr int KPL = MAXL / 32;  // keys per lane
+
 __device__ __forceinline__ float warp_select_compact(float2 *list, int n, int kp, int *hist) {
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
+  uint32_t keys[KPL];
+#pragma unroll
+  for (int j = 0; j < KPL; j++) {
+    const int i = j * 32 + lane;
+    keys[j] = i < n ? float_key(list[i].x) : 0xffffffffu;
+  }
   uint32_t prefix = 0, mask = 0;
   int rem = kp;
+#pragma unroll 1
   for (int shift = 24; shift >= 0; shift -= 8) {
 #pragma unroll
     for (int u = 0; u < 8; u++) hist[lane * 8 + u] = 0;
     __syncwarp();
-    for (int i = lane; i < n; i += 32) {
-      uint32_t key = float_key(list[i].x);
-      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
-    }
+#pragma unroll
+    for (int j = 0; j < KPL; j++)
+      if ((keys[j] & mask) == prefix) atomicAdd(&hist[(keys[j] >> shift) & 255], 1);
     __syncwarp();
-    int loc[8], s = 0;
+    int loc[8], sum = 0;
 #pragma unroll
     for (int u = 0; u < 8; u++) {
       loc[u] = hist[lane * 8 + u];
-      s += loc[u];
+      sum += loc[u];
     }
-    int inc = s;
+    int inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       int t = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += t;
     }
-    int off = inc - s;
+    int off = inc - sum;
     int found = -1, newrem = 0;
 #pragma unroll
     for (int u = 0; u < 8; u++) {
@@ -214,8 +232,8 @@ __device__ __forceinline__ float warp_select_compact(float2 *list, int n, int kp
       }
       off += loc[u];
     }
-    unsigned who = __ballot_sync(0xffffffffu, found >= 0);
-    int src = __ffs(who) - 1;
+    const unsigned who = __ballot_sync(0xffffffffu, found >= 0);
+    const int src = __ffs(who) - 1;
     found = __shfl_sync(0xffffffffu, found, src);
     rem = __shfl_sync(0xffffffffu, newrem, src);
     prefix |= (uint32_t)found << shift;
@@ -224,33 +242,47 @@ __device__ __forceinline__ float warp_select_compact(float2 *list, int n, int kp
   }
   const uint32_t pivot = prefix;
   int out = 0, eq_taken = 0;
-  for (int i0 = 0; i0 < n; i0 += 32) {
-    const int i = i0 + lane;
-    float2 e = make_float2(0.f, 0.f);
-    uint32_t key = 0xffffffffu;
-    if (i < n) {
-      e = list[i];
-      key = float_key(e.x);
-    }
+#pragma unroll
+  for (int j = 0; j < KPL; j++) {
+    const uint32_t key = keys[j];
     const bool eq = key == pivot;
     const unsigned eqb = __ballot_sync(0xffffffffu, eq);
-    const bool keep = (i < n) && (key < pivot || (eq && eq_taken + __popc(eqb & lt_mask) < rem));
+    const bool keep = key < pivot || (eq && eq_taken + __popc(eqb & lt_mask) < rem);
     const unsigned kb = __ballot_sync(0xffffffffu, keep);
+    eq_taken += __popc(eqb);
+    if (kb == 0) continue;
+    float2 e = make_float2(0.f, 0.f);
+    if (keep) e = list[j * 32 + lane];
+    __syncwarp();
     if (keep) list[out + __popc(kb & lt_mask)] = e;
     out += __popc(kb);
-    eq_taken += __popc(eqb);
-    __syncwarp();
   }
+  __syncwarp();
   const uint32_t bits = (pivot & 0x80000000u) ? (pivot & 0x7fffffffu) : ~pivot;
   return __uint_as_float(bits);
+}
+
+// branch-free append: if (s < thr) { list[cnt] = (s, id); cnt++; }
+__device__ __forceinline__ void append_if_below(float2 *list, int &cnt, float s, float thr, int id) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 a;\n\t"
+      "setp.lt.f32 p, %1, %2;\n\t"
+      "mad.wide.s32 a, %0, 8, %3;\n\t"
+      "@p st.global.v2.b32 [a], {%4, %5};\n\t"
+      "@p add.s32 %0, %0, 1;\n\t"
+      "}"
+      : "+r"(cnt)
+      : "f"(s), "f"(thr), "l"(list), "r"(__float_as_uint(s)), "r"(id)
+      : "memory");
 }
 
 // ------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(TF32_THREADS, 1)
 k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_b,
            const Tf32Params P) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto bar = [&](int i) { return sbase + Smem::bar_off + 8 * i; };
@@ -273,7 +305,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {  // TMEM: all 512 columns (2 accumulator buffers of 256)
+  if (warp == EPI_WARPS + 1) {  // TMEM: all 512 columns (2 accumulator buffers of 256)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      sbase + Smem::tmem_ptr_off),
                  "r"(512));
@@ -286,7 +318,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 
   const int first_item = blockIdx.x, item_step = gridDim.x;
 
-  if (warp == 4) {
+  if (warp == EPI_WARPS) {
     // ======================================================================== TMA producer
     if (lane == 0) {
       uint32_t icount = 0, ccount = 0, tcount = 0;
@@ -315,7 +347,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == EPI_WARPS + 1) {
     // ======================================================================== MMA issuer
     if (lane == 0) {
       uint32_t icount = 0, ccount = 0, tcount = 0;
@@ -349,11 +381,12 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     }
   } else {
     // ======================================================================== epilogue
-    const int t = threadIdx.x;  // query row inside the tile == TMEM lane
+    const int quarter = warp & 3, half = warp >> 2;
+    const int t = quarter * 32 + lane;  // query row inside the tile == TMEM lane
     int *hist = (int *)(smem + Smem::hist_off) + warp * 256;
-    float2 *mylist = P.scratch + ((size_t)blockIdx.x * TM + t) * P.cap;
+    float2 *mylist = P.scratch + ((size_t)blockIdx.x * (2 * TM) + half * TM + t) * P.cap;
     const float inf = __uint_as_float(0x7f800000u);
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * HALF_N;
     uint32_t tcount = 0;
     for (int item = first_item; item < P.items; item += item_step) {
       const int sp = item / P.tiles_q, qt = item - sp * P.tiles_q;
@@ -367,10 +400,10 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         mbar_wait(bar(Smem::n_full + slot), (tcount / NBN) & 1);
         mbar_wait(bar(Smem::t_full + buf), (tcount >> 1) & 1);
         tc_fence_after();
-        const float *bn = (const float *)(smem + Smem::bn_off + slot * TN * 4);
-        const int n0 = jt * TN;
+        const float *bn = (const float *)(smem + Smem::bn_off + slot * TN * 4) + half * HALF_N;
+        const int n0 = jt * TN + half * HALF_N;
 #pragma unroll 1
-        for (int g = 0; g < TN / 32; g++) {
+        for (int g = 0; g < HALF_N / 32; g++) {
           uint32_t v[32];
           tc_ld32(lane_addr + buf * TN + g * 32, v);
           tc_wait_ld();
@@ -384,27 +417,26 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
               }
             }
           } else {
+            float sv[32];
 #pragma unroll
             for (int c4 = 0; c4 < 8; c4++) {
               const float4 b4 = *reinterpret_cast<const float4 *>(bn + g * 32 + c4 * 4);
-              const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-              for (int u = 0; u < 4; u++) {
-                const float s = fmaf(__uint_as_float(v[c4 * 4 + u]), -2.0f, bb[u]);
-                if (s < thr) {
-                  mylist[cnt] = make_float2(s, __int_as_float(n0 + g * 32 + c4 * 4 + u));
-                  cnt++;
-                }
-              }
+              sv[c4 * 4 + 0] = fmaf(__uint_as_float(v[c4 * 4 + 0]), -2.0f, b4.x);
+              sv[c4 * 4 + 1] = fmaf(__uint_as_float(v[c4 * 4 + 1]), -2.0f, b4.y);
+              sv[c4 * 4 + 2] = fmaf(__uint_as_float(v[c4 * 4 + 2]), -2.0f, b4.z);
+              sv[c4 * 4 + 3] = fmaf(__uint_as_float(v[c4 * 4 + 3]), -2.0f, b4.w);
             }
+            const int idb = n0 + g * 32;
+#pragma unroll
+            for (int c = 0; c < 32; c++) append_if_below(mylist, cnt, sv[c], thr, idb + c);
           }
         }
         // accumulator buffer and |b|^2 slot are free again
         tc_fence_before();
         mbar_arrive(bar(Smem::t_empty + buf));
         mbar_arrive(bar(Smem::n_empty + slot));
-        // keep room for a full tile of appends in every list of the warp
-        unsigned need = __ballot_sync(0xffffffffu, cnt > P.cap - TN);
+        // keep room for a full half tile of appends in every list of the warp
+        unsigned need = __ballot_sync(0xffffffffu, cnt > P.cap - HALF_N);
         while (need) {
           const int owner = __ffs(need) - 1;
           need &= need - 1;
@@ -435,16 +467,15 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         }
         __syncwarp();
         if (valid) {
-          float *os = P.out_score + ((size_t)q * P.splits + sp) * P.kprime;
-          int *oi = P.out_id + ((size_t)q * P.splits + sp) * P.kprime;
+          const size_t o = ((size_t)q * P.lists + sp * 2 + half) * P.kprime;
           for (int e = 0; e < P.kprime; e++) {
             if (e < cnt) {
-              float2 x = mylist[e];
-              os[e] = x.x;
-              oi[e] = __float_as_int(x.y);
+              const float2 x = mylist[e];
+              P.out_score[o + e] = x.x;
+              P.out_id[o + e] = __float_as_int(x.y);
             } else {
-              os[e] = inf;
-              oi[e] = -1;
+              P.out_score[o + e] = inf;
+              P.out_id[o + e] = -1;
             }
           }
         }
@@ -454,7 +485,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == EPI_WARPS + 1) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
@@ -510,11 +541,10 @@ Tf32Plan tf32_plan(int nq, int nb, int d, int k) {
   if (d < 1 || d > MAX_NKC * KC || (d % 4) != 0) return p;  // TMA: 16-byte row pitch; A resident
   if (nq < 1 || nb < 1) return p;
   const int kp = kprime_for(k);
-  if (kp > 1024) return p;
+  if (kp + 2 * HALF_N > MAXL) return p;  // the in-register compaction handles MAXL entries
   int cap = pow2_ceil(8 * kp);
   if (cap < 512) cap = 512;
-  if (cap > 4096) cap = 4096;
-  if (cap < kp + 2 * TN) cap = pow2_ceil(kp + 2 * TN);
+  if (cap > MAXL) cap = MAXL;
   const int G = sm_count();
   const int tiles_q = (nq + TM - 1) / TM;
   const int nbt = (nb + TN - 1) / TN;
@@ -541,7 +571,8 @@ Tf32Plan tf32_plan(int nq, int nb, int d, int k) {
   p.cap = cap;
   long items = (long)tiles_q * p.splits;
   p.ctas = (int)(items < G ? items : G);
-  p.ws_bytes = Carver::need(sizeof(float2) * (size_t)p.ctas * TM * cap) + 256;
+  p.lists = 2 * p.splits;
+  p.ws_bytes = Carver::need(sizeof(float2) * (size_t)p.ctas * 2 * TM * cap) + 256;
   p.ok = 1;
   return p;
 }
@@ -563,6 +594,7 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, const float 
   P.nbt = (nb + TN - 1) / TN;
   P.range_tiles = (P.nbt + plan.splits - 1) / plan.splits;
   P.splits = plan.splits;
+  P.lists = plan.lists;
   P.items = P.tiles_q * P.splits;
   P.kprime = plan.kprime;
   P.cap = plan.cap;

@@ -132,6 +132,38 @@ int sm_count() {
 
 void count_launch(long n) { g_launches += n; }
 
+// ---- optional phase timing (bench.py roofline): CUDA event pairs on the launching stream
+struct ProfSpan {
+  int phase;
+  cudaEvent_t a, b;
+};
+static bool g_prof_on = false;
+static std::vector<ProfSpan> g_spans;
+static std::vector<cudaEvent_t> g_ev_pool;
+
+static cudaEvent_t prof_event() {
+  if (!g_ev_pool.empty()) {
+    cudaEvent_t e = g_ev_pool.back();
+    g_ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+int prof_begin(int phase, cudaStream_t st) {
+  if (!g_prof_on) return -1;
+  ProfSpan s = {phase, prof_event(), prof_event()};
+  cudaEventRecord(s.a, st);
+  g_spans.push_back(s);
+  return (int)g_spans.size() - 1;
+}
+
+void prof_end(int handle, cudaStream_t st) {
+  if (handle >= 0 && handle < (int)g_spans.size()) cudaEventRecord(g_spans[handle].b, st);
+}
+
 }  // namespace yb
 
 extern "C" {
@@ -230,6 +262,36 @@ int yb_h2d(void *dst, const void *src, size_t bytes, yb_stream_t s) {
 int yb_d2h(void *dst, const void *src, size_t bytes, yb_stream_t s) {
   YB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, yb::stream_of(s)));
   return 0;
+}
+
+void yb_prof_enable(int on) {
+  yb::Guard g;
+  yb::g_prof_on = on != 0;
+}
+
+// total milliseconds (and number of spans via *count) recorded for a phase; reset drops them
+double yb_prof_ms(int phase, long *count, int reset) {
+  yb::Guard g;
+  double ms = 0.0;
+  long n = 0;
+  for (auto &s : yb::g_spans) {
+    if (s.phase != phase) continue;
+    cudaEventSynchronize(s.b);
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) {
+      ms += t;
+      n++;
+    }
+  }
+  if (count) *count = n;
+  if (reset) {
+    for (auto &s : yb::g_spans) {
+      yb::g_ev_pool.push_back(s.a);
+      yb::g_ev_pool.push_back(s.b);
+    }
+    yb::g_spans.clear();
+  }
+  return ms;
 }
 
 void yb_release_scratch(void) {
