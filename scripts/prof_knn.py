@@ -32,7 +32,7 @@ for i in range(reps):
                                                    L.yb_last_knn_engine(), L.yb_last_knn_uncertified()))
 import ctypes as C
 cnt = C.c_long(0)
-for ph in range(8):
+for ph in range(12):
     ms = L.yb_prof_ms(ph, C.byref(cnt), 0)
     if cnt.value:
         print("phase %d: %.3f ms avg over %d" % (ph, ms / cnt.value, cnt.value))

@@ -29,15 +29,24 @@ struct Tf32Plan {
   size_t ws_bytes; // workspace for buffers + shortlists
 };
 Tf32Plan tf32_plan(int nq, int nb, int d, int k);
-// Produces, for every query, `lists` shortlists of `kprime` candidates: out_score[q][s][e] =
-// |b|^2 - 2<q,b> evaluated with TF32 operands, out_id[q][s][e] the row id (unused slots:
-// +inf / -1).  Every database row that is NOT listed for (q, s) has a TF32 score >= the
-// largest listed score of a full list.  bnorm_padded: |b|^2 for tf32_padded_rows(nb) rows,
+Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kprime);
+int tf32_kprime_for(int k);
+// One pass of the tensor-core kernel over the logical tiles 0..nbt_logical-1, logical tile j being
+// database tile j*tile_stride (256 rows each).  Produces, for every query, `lists` shortlists of
+// `kprime` candidates: out_score[q][l][e] = |b|^2 - 2<q,b> evaluated with TF32 operands,
+// out_id[q][l][e] the row id (unused slots: +inf / -1), and out_thr[q][l]: every visited row of
+// the list's range that is NOT listed has a TF32 score >= out_thr[q][l].  thr_init[q] (may be
+// NULL) is the initial admission threshold.  bnorm_padded: |b|^2 for tf32_padded_rows(nb) rows,
 // the padding filled with +inf.
-int tf32_shortlist(const Tf32Plan &plan, int nq, int nb, int d, const float *base,
-                   const float *query, const float *bnorm_padded, float *out_score, int *out_id,
-                   void *ws, cudaStream_t st);
+int tf32_shortlist(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical, int tile_stride,
+                   const float *base, const float *query, const float *bnorm_padded,
+                   const float *thr_init, float *out_score, int *out_id, float *out_thr, void *ws,
+                   cudaStream_t st);
+int tf32_scores(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical, int tile_stride,
+                const float *base, const float *query, const float *bnorm_padded, float *scores,
+                long ld, void *ws, cudaStream_t st);
 long tf32_padded_rows(int nb);
+int tf32_tiles(int nb);
 int fill_f32(float *p, long n, float v, cudaStream_t st);
 
 }  // namespace yb

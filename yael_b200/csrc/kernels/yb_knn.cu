@@ -44,6 +44,8 @@ struct RerankArgs {
   int cand_stride;
   int m;
   int all_listed;          // 1: every database row is a candidate (nothing was ever dropped)
+  const float *cand_thr;   // [nq][lists] final admission threshold of every shortlist
+  int lists;
   float err_scale;         // certificate: E_q = err_scale * |q| * max|b|
   const float *bmax;       // device scalar: max |b| (sqrt of max squared norm)
   int *assign;
@@ -174,15 +176,16 @@ __global__ void __launch_bounds__(128) k_rerank(RerankArgs A) {
         A.dis[(size_t)q * k + j] = __uint_as_float(0xffffffffu);
       }
     }
-    // Certificate.  Every database row that is NOT a candidate has a TF32 score >= T, the
-    // largest TF32 score among the m candidates when the candidate set is full (rows are only
-    // ever dropped from a full list, in favour of smaller scores); its exact score is then
-    // >= T - E_q.  The k-th exact distance D_k (score S_k = D_k - |q|^2) cannot be beaten by
-    // such a row when S_k + E_q < T.
+    // Certificate.  A database row that is NOT among the m candidates was either refused by
+    // a shortlist (TF32 score >= that list's final admission threshold) or dropped by the merge
+    // (TF32 score >= the largest selected score).  With T the smallest of those bounds, its
+    // exact score is >= T - E_q, so the k-th exact distance D_k (score S_k = D_k - |q|^2)
+    // cannot be beaten by such a row when S_k + E_q < T.  T = +inf: nothing was ever refused.
     if (tid == 0) {
       const float inf = __uint_as_float(0x7f800000u);
       float T = inf;
       if (!A.all_listed) {
+        for (int l = 0; l < A.lists; l++) T = fminf(T, A.cand_thr[(size_t)q * A.lists + l]);
         int nvalid = 0;
         float mx = -inf;
         for (int j = 0; j < m; j++) {
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(128) k_rerank(RerankArgs A) {
             mx = fmaxf(mx, A.cand_score[(size_t)q * A.cand_stride + pos]);
           }
         }
-        if (nvalid == m) T = mx;  // a partially filled set means nothing was dropped
+        if (nvalid == m) T = fminf(T, mx);  // the merge may have dropped rows at or above mx
       }
       int flag = 0;
       if (T < inf) {
@@ -346,6 +349,16 @@ __global__ void k_scatter_results(const int *__restrict__ rows, int n, int k,
   }
 }
 
+// thr[q] = the j-th smallest sampled score (kmin_rows output), +inf when the sample held
+// fewer than j rows
+__global__ void k_threshold_from_kmin(const int *__restrict__ idx, const float *__restrict__ vals,
+                                      int nq, int j, float *__restrict__ thr) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  thr[q] = idx[(size_t)q * j + (j - 1)] >= 0 ? vals[(size_t)q * j + (j - 1)]
+                                              : __uint_as_float(0x7f800000u);
+}
+
 // TF32 operands keep 10 explicit mantissa bits; the hardware drops (or rounds) the rest, so
 // each operand carries a relative error < 2^-10 and each product < 2^-9 (+2^-20); with
 // Cauchy-Schwarz the score |b|^2 - 2<q,b> is off by at most 2 * 2^-9 * |q||b|.  2.5 % head
@@ -367,14 +380,52 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
   size_t smem = rerank_smem_bytes(d, m, m_pad);
   if (smem > 200 * 1024) return -1000;
   const long padded = tf32_padded_rows(nb);
+  const int nbt = tf32_tiles(nb);
   const bool need_sel = plan.lists > 1;
+
+  // Sampling pre-passes (large databases).  A threshold tau_q with "about 3x the wanted number
+  // of rows below it" turns the streaming top-k into a plain filter: lists hardly ever fill up,
+  // so the epilogue never stops to compact.  Level 2 scans every 16th tile and keeps the j2
+  // smallest scores; its own threshold comes from level 1, a raw score slab over a few tiles.
+  // Any threshold is SOUND as long as enough rows pass it, which the re-rank verifies per
+  // query (too few candidates -> exact engine); the levels only affect speed.
+  const int kSampleStride = 16;
+  const bool use_sample = nbt >= 8 * kSampleStride;
+  const int nbt_s = (nbt + kSampleStride - 1) / kSampleStride;
+  int j2 = (3 * kp + kSampleStride - 1) / kSampleStride;
+  if (j2 < 32) j2 = 32;
+  Tf32Plan splan = {};
+  if (use_sample) splan = tf32_plan_tiles(nq, nbt_s, d, j2);
+  const bool sample_ok = use_sample && splan.ok;
+  const int sstride = sample_ok ? splan.lists * j2 : 1;
+  // level 1: t1 tiles spread over the database, j1-th smallest -> about 3*j2 rows of level 2
+  int t1 = nbt_s / 8;
+  if (t1 > 32) t1 = 32;
+  const int stride1 = t1 > 0 ? nbt / t1 : 1;
+  const long rows1 = (long)t1 * 256;
+  int j1 = t1 > 0 ? (int)((3L * j2 * t1 + nbt_s - 1) / nbt_s) : 0;
+  if (j1 < 12) j1 = 12;
+  Tf32Plan l1plan = {};
+  const bool level1_ok = sample_ok && t1 >= 8 && (size_t)nq * rows1 * 4 <= ((size_t)1 << 30) &&
+                         (l1plan = tf32_plan_tiles(nq, t1, d, 8)).ok;
 
   size_t need = Carver::need(sizeof(float) * (size_t)padded) + Carver::need(64) +
                 Carver::need(sizeof(float) * (size_t)nq * stride) +
                 Carver::need(sizeof(int) * (size_t)nq * stride) +
+                Carver::need(sizeof(float) * (size_t)nq * plan.lists) +
                 Carver::need(sizeof(int) * (size_t)nq * kp) +
                 2 * Carver::need(sizeof(int) * (size_t)nq) + kmin_ws_bytes(nq, kp) +
                 Carver::need(plan.ws_bytes) + 1024;
+  if (sample_ok)
+    need += Carver::need(sizeof(float) * (size_t)nq * sstride) +
+            Carver::need(sizeof(int) * (size_t)nq * sstride) +
+            Carver::need(sizeof(float) * (size_t)nq * splan.lists) +
+            2 * Carver::need(sizeof(int) * (size_t)nq * j2) + 2 * Carver::need(sizeof(float) * (size_t)nq) +
+            kmin_ws_bytes(nq, j2) + Carver::need(splan.ws_bytes);
+  if (level1_ok)
+    need += Carver::need(sizeof(float) * (size_t)nq * rows1) +
+            2 * Carver::need(sizeof(int) * (size_t)nq * j1) + kmin_ws_bytes(nq, j1) +
+            Carver::need(l1plan.ws_bytes);
   int n_flag = 0;
   int *flag_list_keep = nullptr;
   {
@@ -384,11 +435,13 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
     float *scal = c.take<float>(16);  // [0] = max |b|, [1] = flag count (int)
     float *cscore = c.take<float>((size_t)nq * stride);
     int *cid = c.take<int>((size_t)nq * stride);
+    float *cthr = c.take<float>((size_t)nq * plan.lists);
     int *sel = c.take<int>((size_t)nq * kp);
     int *flags = c.take<int>(nq);
     int *flag_list = c.take<int>(nq);
     void *kws = c.take<char>(kmin_ws_bytes(nq, kp));
     void *tfws = c.take<char>(plan.ws_bytes);
+    float *thr_init = nullptr;
     int rc;
     {
       ProfScope ps(0, st);
@@ -398,12 +451,47 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
       k_sqrt_max<<<2 * sm_count(), 256, 0, st>>>(an, nb, scal);
       YB_LAUNCH_CHECK();
     }
+    if (sample_ok) {
+      ProfScope ps(10, st);
+      float *sscore = c.take<float>((size_t)nq * sstride);
+      int *sid = c.take<int>((size_t)nq * sstride);
+      float *sthr = c.take<float>((size_t)nq * splan.lists);
+      int *ssel = c.take<int>((size_t)nq * j2);
+      float *svals = (float *)c.take<int>((size_t)nq * j2);
+      thr_init = c.take<float>(nq);
+      float *thr1 = c.take<float>(nq);
+      void *skws = c.take<char>(kmin_ws_bytes(nq, j2));
+      void *stfws = c.take<char>(splan.ws_bytes);
+      const float *thr_l1 = nullptr;
+      if (level1_ok) {
+        float *slab = c.take<float>((size_t)nq * rows1);
+        int *sel1 = c.take<int>((size_t)nq * j1);
+        float *vals1 = (float *)c.take<int>((size_t)nq * j1);
+        void *kws1 = c.take<char>(kmin_ws_bytes(nq, j1));
+        void *tfws1 = c.take<char>(l1plan.ws_bytes);
+        if ((rc = tf32_scores(l1plan, nq, nb, d, t1, stride1, base, query, an, slab, rows1, tfws1, st)))
+          return rc;
+        if ((rc = kmin_rows(slab, rows1, rows1, nq, j1, +1, sel1, vals1, 0, 0, kws1, st))) return rc;
+        k_threshold_from_kmin<<<(nq + 255) / 256, 256, 0, st>>>(sel1, vals1, nq, j1, thr1);
+        YB_LAUNCH_CHECK();
+        thr_l1 = thr1;
+      }
+      if ((rc = tf32_shortlist(splan, nq, nb, d, nbt_s, kSampleStride, base, query, an, thr_l1,
+                               sscore, sid, sthr, stfws, st)))
+        return rc;
+      if ((rc = kmin_rows(sscore, sstride, sstride, nq, j2, +1, ssel, svals, 0, 0, skws, st)))
+        return rc;
+      k_threshold_from_kmin<<<(nq + 255) / 256, 256, 0, st>>>(ssel, svals, nq, j2, thr_init);
+      YB_LAUNCH_CHECK();
+    }
     {
       ProfScope ps(1, st);
-      if ((rc = tf32_shortlist(plan, nq, nb, d, base, query, an, cscore, cid, tfws, st))) return rc;
+      if ((rc = tf32_shortlist(plan, nq, nb, d, nbt, 1, base, query, an, thr_init, cscore, cid,
+                               cthr, tfws, st)))
+        return rc;
     }
     if (need_sel) {
-      // merge the per-range shortlists: the kp smallest TF32 scores of the union
+      // merge the per-list shortlists: the kp smallest TF32 scores of the union
       ProfScope ps(2, st);
       if ((rc = kmin_rows(cscore, stride, stride, nq, kp, +1, sel, nullptr, 0, 0, kws, st)))
         return rc;
@@ -414,6 +502,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
     A.dis = dis; A.assign = assign; A.id_offset = id_offset;
     A.cand_id = cid; A.cand_score = cscore; A.sel = need_sel ? sel : nullptr;
     A.cand_stride = stride; A.m = m; A.all_listed = (nb <= kp);
+    A.cand_thr = cthr; A.lists = plan.lists;
     A.err_scale = kTf32ErrScale; A.bmax = scal; A.uncert_flags = flags;
     A.gsort = nullptr; A.m_pad = m_pad; A.k1 = (k == 1);
     rerank_attrs();

@@ -176,7 +176,13 @@ struct Tf32Params {
   float2 *scratch;     // [gridDim.x][256][cap] append lists (score, id bits)
   float *out_score;    // [nq][lists][kprime]
   int *out_id;         // [nq][lists][kprime]
-  float *dump;         // debug: [nq][nb] raw scores (lists are not produced)
+  float *dump;         // [nq][dump_ld] raw scores by LOGICAL column (lists are not produced)
+  long dump_ld;
+  const float *thr_init;  // [nq] initial admission threshold per query (NULL = +inf): rows whose
+                          // score is >= thr_init[q] are known not to matter
+  float *out_thr;      // [nq][lists] final admission threshold of every list: each row of the
+                       // list's range that is NOT in the list has a score >= this value
+  int tile_stride;     // logical tile j covers database tile j * tile_stride (sampling pass)
 };
 
 // ------------------------------------------------------------------ warp-cooperative compaction
@@ -335,14 +341,15 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
           const uint32_t slot = tcount % NBN;
           mbar_wait(bar(Smem::n_empty + slot), ((tcount / NBN) & 1) ^ 1);
           mbar_expect_tx(bar(Smem::n_full + slot), TN * 4);
-          bulk_load_1d(sbase + Smem::bn_off + slot * TN * 4, P.bnorm + (size_t)jt * TN, TN * 4,
+          const int jta = jt * P.tile_stride;  // actual database tile
+          bulk_load_1d(sbase + Smem::bn_off + slot * TN * 4, P.bnorm + (size_t)jta * TN, TN * 4,
                        bar(Smem::n_full + slot));
           for (int kc = 0; kc < P.nkc; kc++, ccount++) {
             const uint32_t st = ccount % STAGES;
             mbar_wait(bar(Smem::b_empty + st), ((ccount / STAGES) & 1) ^ 1);
             mbar_expect_tx(bar(Smem::b_full + st), B_CHUNK_BYTES);
             tma_load_2d(sbase + Smem::b_off + st * B_CHUNK_BYTES, &map_b, bar(Smem::b_full + st),
-                        kc * KC, jt * TN);
+                        kc * KC, jta * TN);
           }
         }
       }
@@ -393,7 +400,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
       const int q = qt * TM + t;
       const bool valid = q < P.nq;
-      float thr = valid ? inf : -inf;
+      float thr = valid ? (P.thr_init ? P.thr_init[q] : inf) : -inf;
       int cnt = 0;
       for (int jt = jt0; jt < jt1; jt++, tcount++) {
         const uint32_t buf = tcount & 1, slot = tcount % NBN;
@@ -401,7 +408,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         mbar_wait(bar(Smem::t_full + buf), (tcount >> 1) & 1);
         tc_fence_after();
         const float *bn = (const float *)(smem + Smem::bn_off + slot * TN * 4) + half * HALF_N;
-        const int n0 = jt * TN + half * HALF_N;
+        const int n0 = jt * P.tile_stride * TN + half * HALF_N;
 #pragma unroll 1
         for (int g = 0; g < HALF_N / 32; g++) {
           uint32_t v[32];
@@ -409,12 +416,12 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
           tc_wait_ld();
           if (P.dump) {
             if (valid) {
+              const long col0 = (long)jt * TN + half * HALF_N + g * 32;  // logical column
 #pragma unroll
-              for (int c = 0; c < 32; c++) {
-                int n = n0 + g * 32 + c;
-                if (n < P.nb)
-                  P.dump[(size_t)q * P.nb + n] = fmaf(__uint_as_float(v[c]), -2.0f, bn[g * 32 + c]);
-              }
+              for (int c = 0; c < 32; c++)
+                if (col0 + c < P.dump_ld)
+                  P.dump[(size_t)q * P.dump_ld + col0 + c] =
+                      fmaf(__uint_as_float(v[c]), -2.0f, bn[g * 32 + c]);
             }
           } else {
             float sv[32];
@@ -468,6 +475,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         __syncwarp();
         if (valid) {
           const size_t o = ((size_t)q * P.lists + sp * 2 + half) * P.kprime;
+          P.out_thr[(size_t)q * P.lists + sp * 2 + half] = thr;
           for (int e = 0; e < P.kprime; e++) {
             if (e < cnt) {
               const float2 x = mylist[e];
@@ -531,23 +539,24 @@ static int make_map(CUtensorMap *m, const float *ptr, long rows, int d, int box_
   return 0;
 }
 
-static int kprime_for(int k) {
+int tf32_kprime_for(int k) {
   int a = 2 * k, b = k + 32 < 8 * k ? k + 32 : 8 * k;
   return a > b ? a : b;
 }
 
-Tf32Plan tf32_plan(int nq, int nb, int d, int k) {
+// Plan a pass over `nbt_logical` database tiles (a sampling pass sees every tile_stride-th tile)
+// that keeps kp candidates per list.
+Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kp) {
   Tf32Plan p = {};
   if (d < 1 || d > MAX_NKC * KC || (d % 4) != 0) return p;  // TMA: 16-byte row pitch; A resident
-  if (nq < 1 || nb < 1) return p;
-  const int kp = kprime_for(k);
+  if (nq < 1 || nbt_logical < 1 || kp < 1) return p;
   if (kp + 2 * HALF_N > MAXL) return p;  // the in-register compaction handles MAXL entries
   int cap = pow2_ceil(8 * kp);
   if (cap < 512) cap = 512;
   if (cap > MAXL) cap = MAXL;
   const int G = sm_count();
   const int tiles_q = (nq + TM - 1) / TM;
-  const int nbt = (nb + TN - 1) / TN;
+  const int nbt = nbt_logical;
   // database ranges: the smallest split count whose last wave is at least 90 % full; every
   // range at least 8 tiles long
   int best_s = 1;
@@ -567,19 +576,29 @@ Tf32Plan tf32_plan(int nq, int nb, int d, int k) {
   }
   int range = (nbt + best_s - 1) / best_s;
   p.splits = (nbt + range - 1) / range;
+  p.lists = 2 * p.splits;
   p.kprime = kp;
   p.cap = cap;
   long items = (long)tiles_q * p.splits;
   p.ctas = (int)(items < G ? items : G);
-  p.lists = 2 * p.splits;
   p.ws_bytes = Carver::need(sizeof(float2) * (size_t)p.ctas * 2 * TM * cap) + 256;
   p.ok = 1;
   return p;
 }
 
-static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, const float *base,
-                       const float *query, const float *bnorm_padded, float *out_score,
-                       int *out_id, float *dump, void *ws, cudaStream_t st) {
+Tf32Plan tf32_plan(int nq, int nb, int d, int k) {
+  if (nb < 1) {
+    Tf32Plan p = {};
+    return p;
+  }
+  return tf32_plan_tiles(nq, (nb + TN - 1) / TN, d, tf32_kprime_for(k));
+}
+
+static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical,
+                       int tile_stride, const float *base, const float *query,
+                       const float *bnorm_padded, const float *thr_init, float *out_score,
+                       int *out_id, float *out_thr, float *dump, long dump_ld, void *ws,
+                       cudaStream_t st) {
   if ((((uintptr_t)base) & 15) || (((uintptr_t)query) & 15))
     return fail(6, "tf32 path needs 16-byte aligned matrices");
   CUtensorMap mq, mb;
@@ -591,7 +610,7 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, const float 
   P.nkc = (d + KC - 1) / KC;
   P.last_k8 = (d - (P.nkc - 1) * KC + 7) / 8;
   P.tiles_q = (nq + TM - 1) / TM;
-  P.nbt = (nb + TN - 1) / TN;
+  P.nbt = nbt_logical;
   P.range_tiles = (P.nbt + plan.splits - 1) / plan.splits;
   P.splits = plan.splits;
   P.lists = plan.lists;
@@ -602,7 +621,11 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, const float 
   P.scratch = (float2 *)ws;
   P.out_score = out_score;
   P.out_id = out_id;
+  P.out_thr = out_thr;
+  P.thr_init = thr_init;
+  P.tile_stride = tile_stride;
   P.dump = dump;
+  P.dump_ld = dump_ld;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(k_knn_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -616,14 +639,24 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, const float 
   return 0;
 }
 
-int tf32_shortlist(const Tf32Plan &plan, int nq, int nb, int d, const float *base,
-                   const float *query, const float *bnorm_padded, float *out_score, int *out_id,
-                   void *ws, cudaStream_t st) {
-  return launch_tf32(plan, nq, nb, d, base, query, bnorm_padded, out_score, out_id, nullptr, ws,
-                     st);
+int tf32_shortlist(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical, int tile_stride,
+                   const float *base, const float *query, const float *bnorm_padded,
+                   const float *thr_init, float *out_score, int *out_id, float *out_thr, void *ws,
+                   cudaStream_t st) {
+  return launch_tf32(plan, nq, nb, d, nbt_logical, tile_stride, base, query, bnorm_padded,
+                     thr_init, out_score, out_id, out_thr, nullptr, 0, ws, st);
+}
+
+// raw TF32 scores of the logical tiles (every tile_stride-th database tile): scores[q][ld]
+int tf32_scores(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical, int tile_stride,
+                const float *base, const float *query, const float *bnorm_padded, float *scores,
+                long ld, void *ws, cudaStream_t st) {
+  return launch_tf32(plan, nq, nb, d, nbt_logical, tile_stride, base, query, bnorm_padded, nullptr,
+                     nullptr, nullptr, nullptr, scores, ld, ws, st);
 }
 
 long tf32_padded_rows(int nb) { return (long)((nb + TN - 1) / TN) * TN; }
+int tf32_tiles(int nb) { return (nb + TN - 1) / TN; }
 
 int fill_f32(float *p, long n, float v, cudaStream_t st) {
   if (n <= 0) return 0;
@@ -653,5 +686,6 @@ extern "C" int yb_debug_tf32_scores(int nq, int nb, int d, const float *base, co
   int rc;
   if ((rc = row_norms_seq(base, nb, d, d, bn, nullptr, st))) return rc;
   if ((rc = fill_f32(bn + nb, padded - nb, __builtin_inff(), st))) return rc;
-  return launch_tf32(plan, nq, nb, d, base, query, bn, nullptr, nullptr, scores, tws, st);
+  return launch_tf32(plan, nq, nb, d, tf32_tiles(nb), 1, base, query, bn, nullptr, nullptr, nullptr,
+                     nullptr, scores, nb, tws, st);
 }
