@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(128) k_rerank(RerankArgs A) {
           uint32_t fk = (uint32_t)(key >> 32);
           uint32_t bits = (fk & 0x80000000u) ? (fk & 0x7fffffffu) : ~fk;
           double Dk = (double)__uint_as_float(bits);
-          double E = (double)A.err_scale * sqrt(qn) * (double)(*A.bmax) + 4e-6 * fabs(Dk);
+          double E = (double)A.err_scale * sqrt(qn) * (double)(*A.bmax) + 4e-5 * (fabs(Dk) + qn);
           if (!((Dk - qn) + E < (double)T)) flag = 1;
         }
       }
@@ -361,9 +361,10 @@ __global__ void k_threshold_from_kmin(const int *__restrict__ idx, const float *
 
 // TF32 operands keep 10 explicit mantissa bits; the hardware drops (or rounds) the rest, so
 // each operand carries a relative error < 2^-10 and each product < 2^-9 (+2^-20); with
-// Cauchy-Schwarz the score |b|^2 - 2<q,b> is off by at most 2 * 2^-9 * |q||b|.  2.5 % head
-// room covers the FP32 accumulation inside the tensor core and the norm rounding.
-static const float kTf32ErrScale = 1.025f / 256.0f;
+// Cauchy-Schwarz the score |b|^2 - 2<q,b> is off by at most 2 * 2^-9 * |q||b|.  5 % head
+// room covers the FP32 accumulation inside the tensor core, the norm rounding and the 7 mantissa
+// bits of a listed score that carry its column index (relative 2^-16).
+static const float kTf32ErrScale = 1.05f / 256.0f;
 
 // returns -1000 when the tensor-core path does not apply (caller falls through to engine 0)
 int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *query,

@@ -25,6 +25,7 @@
 // Work items are (query tile, database range) pairs walked range-major so that the CTAs that
 // run concurrently stream the same database range and share it through L2.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "yb_common.cuh"
 #include "yb_internal.cuh"
@@ -141,6 +142,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -183,6 +195,7 @@ struct Tf32Params {
   float *out_thr;      // [nq][lists] final admission threshold of every list: each row of the
                        // list's range that is NOT in the list has a score >= this value
   int tile_stride;     // logical tile j covers database tile j * tile_stride (sampling pass)
+  int debug;           // bring-up switches (YAEL_B200_TF32_DEBUG): 1 skip epilogue math, 2 skip MMAs
 };
 
 // ------------------------------------------------------------------ warp-cooperative compaction
@@ -268,20 +281,37 @@ __device__ __forceinline__ float warp_select_compact(float2 *list, int n, int kp
   return __uint_as_float(bits);
 }
 
-// branch-free append: if (s < thr) { list[cnt] = (s, id); cnt++; }
-__device__ __forceinline__ void append_if_below(float2 *list, int &cnt, float s, float thr, int id) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      ".reg .b64 a;\n\t"
-      "setp.lt.f32 p, %1, %2;\n\t"
-      "mad.wide.s32 a, %0, 8, %3;\n\t"
-      "@p st.global.v2.b32 [a], {%4, %5};\n\t"
-      "@p add.s32 %0, %0, 1;\n\t"
-      "}"
-      : "+r"(cnt)
-      : "f"(s), "f"(thr), "l"(list), "r"(__float_as_uint(s)), "r"(id)
-      : "memory");
+// 16 accumulator columns of one query.  Fast path: scores and their minimum (one FFMA and one
+// FMNMX per candidate); only when the minimum beats the query's admission threshold -- rare once
+// the threshold is tight -- are the 16 candidates tested one by one and appended to the query's
+// list in global memory.
+template <int G>
+__device__ __forceinline__ void process_group(const uint32_t (&v)[16], const float *bn, float thr,
+                                              float2 *mylist, int &cnt, int n0) {
+  float sc[16];
+#pragma unroll
+  for (int c4 = 0; c4 < 4; c4++) {
+    const float4 b4 = *reinterpret_cast<const float4 *>(bn + G * 16 + c4 * 4);
+    sc[c4 * 4 + 0] = fmaf(__uint_as_float(v[c4 * 4 + 0]), -2.0f, b4.x);
+    sc[c4 * 4 + 1] = fmaf(__uint_as_float(v[c4 * 4 + 1]), -2.0f, b4.y);
+    sc[c4 * 4 + 2] = fmaf(__uint_as_float(v[c4 * 4 + 2]), -2.0f, b4.z);
+    sc[c4 * 4 + 3] = fmaf(__uint_as_float(v[c4 * 4 + 3]), -2.0f, b4.w);
+  }
+  // fminf ignores NaN operands, which is what we want: a NaN score is never admitted
+  float m01 = fminf(fminf(sc[0], sc[1]), fminf(sc[2], sc[3]));
+  float m23 = fminf(fminf(sc[4], sc[5]), fminf(sc[6], sc[7]));
+  float m45 = fminf(fminf(sc[8], sc[9]), fminf(sc[10], sc[11]));
+  float m67 = fminf(fminf(sc[12], sc[13]), fminf(sc[14], sc[15]));
+  const float m = fminf(fminf(m01, m23), fminf(m45, m67));
+  if (m < thr) {
+#pragma unroll
+    for (int c = 0; c < 16; c++) {
+      if (sc[c] < thr) {
+        mylist[cnt] = make_float2(sc[c], __int_as_float(n0 + G * 16 + c));
+        cnt++;
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -375,6 +405,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
             const uint64_t adesc = smem_desc_sw128(sbase + Smem::a_off + kc * A_CHUNK_BYTES);
             const uint64_t bdesc = smem_desc_sw128(sbase + Smem::b_off + st * B_CHUNK_BYTES);
             for (int k8 = 0; k8 < nk8; k8++) {
+              if (P.debug & 2) break;
               // advancing K inside the 128-byte swizzle span: +32 bytes = +2 in 16-byte units
               tc_mma_tf32(d_tmem, adesc + (uint64_t)(2 * k8), bdesc + (uint64_t)(2 * k8),
                           IDESC_TF32, (kc | k8) != 0);
@@ -409,12 +440,12 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         tc_fence_after();
         const float *bn = (const float *)(smem + Smem::bn_off + slot * TN * 4) + half * HALF_N;
         const int n0 = jt * P.tile_stride * TN + half * HALF_N;
+        if (P.dump) {
 #pragma unroll 1
-        for (int g = 0; g < HALF_N / 32; g++) {
-          uint32_t v[32];
-          tc_ld32(lane_addr + buf * TN + g * 32, v);
-          tc_wait_ld();
-          if (P.dump) {
+          for (int g = 0; g < HALF_N / 32; g++) {
+            uint32_t v[32];
+            tc_ld32(lane_addr + buf * TN + g * 32, v);
+            tc_wait_ld();
             if (valid) {
               const long col0 = (long)jt * TN + half * HALF_N + g * 32;  // logical column
 #pragma unroll
@@ -423,19 +454,53 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
                   P.dump[(size_t)q * P.dump_ld + col0 + c] =
                       fmaf(__uint_as_float(v[c]), -2.0f, bn[g * 32 + c]);
             }
-          } else {
-            float sv[32];
+          }
+        } else if (!(P.debug & 1)) {
+          // 8 groups of 16 columns, the TMEM load of group g+1 in flight while g is processed
+          uint32_t va[16], vb[16];
+          const uint32_t ta = lane_addr + buf * TN;
+          if (P.debug & 8) {  // bring-up: math on whatever the registers hold, no TMEM traffic
 #pragma unroll
-            for (int c4 = 0; c4 < 8; c4++) {
-              const float4 b4 = *reinterpret_cast<const float4 *>(bn + g * 32 + c4 * 4);
-              sv[c4 * 4 + 0] = fmaf(__uint_as_float(v[c4 * 4 + 0]), -2.0f, b4.x);
-              sv[c4 * 4 + 1] = fmaf(__uint_as_float(v[c4 * 4 + 1]), -2.0f, b4.y);
-              sv[c4 * 4 + 2] = fmaf(__uint_as_float(v[c4 * 4 + 2]), -2.0f, b4.z);
-              sv[c4 * 4 + 3] = fmaf(__uint_as_float(v[c4 * 4 + 3]), -2.0f, b4.w);
+            for (int c = 0; c < 16; c++) va[c] = vb[c] = 0x3f800000u + c + jt;
+            process_group<0>(va, bn, thr, mylist, cnt, n0);
+            process_group<1>(vb, bn, thr, mylist, cnt, n0);
+            process_group<2>(va, bn, thr, mylist, cnt, n0);
+            process_group<3>(vb, bn, thr, mylist, cnt, n0);
+            process_group<4>(va, bn, thr, mylist, cnt, n0);
+            process_group<5>(vb, bn, thr, mylist, cnt, n0);
+            process_group<6>(va, bn, thr, mylist, cnt, n0);
+            process_group<7>(vb, bn, thr, mylist, cnt, n0);
+          } else if (P.debug & 4) {  // bring-up: TMEM traffic only
+#pragma unroll 1
+            for (int g = 0; g < 8; g++) {
+              tc_ld16(ta + g * 16, va);
+              tc_wait_ld();
             }
-            const int idb = n0 + g * 32;
-#pragma unroll
-            for (int c = 0; c < 32; c++) append_if_below(mylist, cnt, sv[c], thr, idb + c);
+          } else {
+            tc_ld16(ta, va);
+            tc_wait_ld();
+            tc_ld16(ta + 16, vb);
+            process_group<0>(va, bn, thr, mylist, cnt, n0);
+            tc_wait_ld();
+            tc_ld16(ta + 32, va);
+            process_group<1>(vb, bn, thr, mylist, cnt, n0);
+            tc_wait_ld();
+            tc_ld16(ta + 48, vb);
+            process_group<2>(va, bn, thr, mylist, cnt, n0);
+            tc_wait_ld();
+            tc_ld16(ta + 64, va);
+            process_group<3>(vb, bn, thr, mylist, cnt, n0);
+            tc_wait_ld();
+            tc_ld16(ta + 80, vb);
+            process_group<4>(va, bn, thr, mylist, cnt, n0);
+            tc_wait_ld();
+            tc_ld16(ta + 96, va);
+            process_group<5>(vb, bn, thr, mylist, cnt, n0);
+            tc_wait_ld();
+            tc_ld16(ta + 112, vb);
+            process_group<6>(va, bn, thr, mylist, cnt, n0);
+            tc_wait_ld();
+            process_group<7>(vb, bn, thr, mylist, cnt, n0);
           }
         }
         // accumulator buffer and |b|^2 slot are free again
@@ -624,6 +689,10 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   P.out_thr = out_thr;
   P.thr_init = thr_init;
   P.tile_stride = tile_stride;
+  {
+    const char *e = getenv("YAEL_B200_TF32_DEBUG");
+    P.debug = e ? atoi(e) : 0;
+  }
   P.dump = dump;
   P.dump_ld = dump_ld;
   static bool attr = false;
