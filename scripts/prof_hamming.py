@@ -1,0 +1,31 @@
+"""Time nn_hamming on device-resident codes.  Usage:
+    python scripts/prof_hamming.py [nq] [nb] [ncodes] [k]"""
+import ctypes as C
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import yael_b200
+
+nq = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
+nb = int(sys.argv[2]) if len(sys.argv) > 2 else 10000000
+nc = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+k = int(sys.argv[4]) if len(sys.argv) > 4 else 100
+L = yael_b200.lib()
+torch.manual_seed(1236)
+base = torch.randint(0, 256, (nb, nc), device="cuda", dtype=torch.uint8)
+query = torch.randint(0, 256, (nq, nc), device="cuda", dtype=torch.uint8)
+idx = torch.empty((nq, k), device="cuda", dtype=torch.int32)
+dis = torch.empty((nq, k), device="cuda", dtype=torch.int16)
+for rep in range(3):
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    rc = L.yb_nn_hamming(nq, nb, nc, k, base.data_ptr(), query.data_ptr(), idx.data_ptr(), dis.data_ptr(), 0, None)
+    assert rc == 0, L.yb_last_error()
+    L.yb_sync(None)
+    dt = time.perf_counter() - t
+    print("rep %d: %.3f ms -> %.0f q/s, %.3e pairs/s" % (rep, dt * 1e3, nq / dt, nq * nb / dt))
+print(idx[0, :5].tolist(), dis[0, :5].tolist())

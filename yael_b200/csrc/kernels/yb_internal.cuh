@@ -45,6 +45,10 @@ int tf32_shortlist(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical,
 int tf32_scores(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical, int tile_stride,
                 const float *base, const float *query, const float *bnorm_padded, float *scores,
                 long ld, void *ws, cudaStream_t st);
+Tf32Plan tf32_plan_nearest(int nq, int nb, int d);
+int tf32_nearest(const Tf32Plan &plan, int nq, int nb, int d, const float *base, const float *query,
+                 const float *bnorm_padded, const float *k1_margin, float *out_score, int *out_id,
+                 float *out_thr, void *ws, cudaStream_t st);
 long tf32_padded_rows(int nb);
 int tf32_tiles(int nb);
 int fill_f32(float *p, long n, float v, cudaStream_t st);

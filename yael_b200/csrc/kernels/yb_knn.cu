@@ -46,6 +46,8 @@ struct RerankArgs {
   int all_listed;          // 1: every database row is a candidate (nothing was ever dropped)
   const float *cand_thr;   // [nq][lists] final admission threshold of every shortlist
   int lists;
+  const float *query_c;    // centred queries the tensor pass saw (row pitch qc_ld)
+  int qc_ld;
   float err_scale;         // certificate: E_q = err_scale * |q| * max|b|
   const float *bmax;       // device scalar: max |b| (sqrt of max squared norm)
   int *assign;
@@ -205,9 +207,14 @@ __global__ void __launch_bounds__(128) k_rerank(RerankArgs A) {
         } else {
           uint32_t fk = (uint32_t)(key >> 32);
           uint32_t bits = (fk & 0x80000000u) ? (fk & 0x7fffffffu) : ~fk;
+          // the tensor pass scored CENTRED operands: S_c(b) = |q-b|^2 - |q-mu|^2
+          double qcn = 0.0;
+          const float *qc = A.query_c + (size_t)q * A.qc_ld;
+          for (int t = 0; t < d; t++) qcn += (double)qc[t] * (double)qc[t];
           double Dk = (double)__uint_as_float(bits);
-          double E = (double)A.err_scale * sqrt(qn) * (double)(*A.bmax) + 4e-5 * (fabs(Dk) + qn);
-          if (!((Dk - qn) + E < (double)T)) flag = 1;
+          double E = (double)A.err_scale * sqrt(qcn) * (double)(*A.bmax) +
+                     4e-5 * (fabs(Dk) + qcn) + 2e-6 * (fabs(Dk) + qn);
+          if (!((Dk - qcn) + E < (double)T)) flag = 1;
         }
       }
       A.uncert_flags[q] = flag;
@@ -366,14 +373,281 @@ __global__ void k_threshold_from_kmin(const int *__restrict__ idx, const float *
 // bits of a listed score that carry its column index (relative 2^-16).
 static const float kTf32ErrScale = 1.05f / 256.0f;
 
+// ------------------------------------------------------------------ centring
+// Squared L2 distances are translation invariant: |q-b|^2 = |(q-mu)-(b-mu)|^2 for ANY mu.  The
+// tensor pass therefore runs on copies shifted by the column mean of the database: operand
+// norms shrink, and with them the TF32 error bound err*|q-mu||b-mu| that sizes the shortlist
+// margin (for k-means on unstructured data this is the difference between a margin that
+// covers every centroid and one that covers one or two).  The exact re-rank always reads the
+// caller's original rows.
+constexpr int CM_ROWS = 1024;  // rows per block in the column-mean reduction
+
+__global__ void __launch_bounds__(256)
+k_col_partial(const float *__restrict__ x, long n, int d, float *__restrict__ psum,
+              int *__restrict__ pcnt) {
+  // thread t owns columns t, t+256, ...; sequential over the block's rows (deterministic)
+  const long r0 = (long)blockIdx.x * CM_ROWS, r1 = min(n, r0 + CM_ROWS);
+  for (int c = threadIdx.x; c < d; c += 256) {
+    float s = 0.f;
+    int m = 0;
+    for (long r = r0; r < r1; r++) {
+      float v = x[r * d + c];
+      if (isfinite(v)) {
+        s += v;
+        m++;
+      }
+    }
+    psum[(size_t)blockIdx.x * d + c] = s;
+    pcnt[(size_t)blockIdx.x * d + c] = m;
+  }
+}
+
+__global__ void k_col_final(const float *__restrict__ psum, const int *__restrict__ pcnt, int nblk,
+                            int d, float *__restrict__ mu) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  double s = 0.0;
+  long m = 0;
+  for (int b = 0; b < nblk; b++) {
+    s += (double)psum[(size_t)b * d + c];
+    m += pcnt[(size_t)b * d + c];
+  }
+  mu[c] = m > 0 ? (float)(s / (double)m) : 0.f;
+}
+
+// out[r][0..dpad) = x[r][c] - mu[c] (zero padded to dpad columns)
+__global__ void k_center(const float *__restrict__ x, long n, int d, int dpad,
+                         const float *__restrict__ mu, float *__restrict__ out) {
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * dpad) return;
+  long r = t / dpad;
+  int c = (int)(t - r * dpad);
+  out[t] = c < d ? __fsub_rn(x[r * d + c], mu[c]) : 0.f;
+}
+
+static size_t center_ws_bytes(long nb, int d) {
+  long nblk = (nb + CM_ROWS - 1) / CM_ROWS;
+  return 2 * Carver::need(sizeof(float) * (size_t)nblk * d) + Carver::need(sizeof(float) * d);
+}
+
+// base_c / query_c: centred copies with row pitch dpad (multiple of 4 floats)
+static int center_operands(int nq, int nb, int d, int dpad, const float *base, const float *query,
+                           float *base_c, float *query_c, void *ws, cudaStream_t st) {
+  Carver c(ws);
+  int nblk = (int)(((long)nb + CM_ROWS - 1) / CM_ROWS);
+  float *psum = c.take<float>((size_t)nblk * d);
+  int *pcnt = c.take<int>((size_t)nblk * d);
+  float *mu = c.take<float>(d);
+  k_col_partial<<<nblk, 256, 0, st>>>(base, nb, d, psum, pcnt);
+  YB_LAUNCH_CHECK();
+  k_col_final<<<(d + 127) / 128, 128, 0, st>>>(psum, pcnt, nblk, d, mu);
+  YB_LAUNCH_CHECK();
+  long tb = (long)nb * dpad, tq = (long)nq * dpad;
+  k_center<<<(unsigned)((tb + 255) / 256), 256, 0, st>>>(base, nb, d, dpad, mu, base_c);
+  YB_LAUNCH_CHECK();
+  k_center<<<(unsigned)((tq + 255) / 256), 256, 0, st>>>(query, nq, d, dpad, mu, query_c);
+  YB_LAUNCH_CHECK();
+  return 0;
+}
+
+// Queries whose certificate failed are re-done by the exact engine (own allocations: rare
+// path).  flag_list / flag_count live in the caller's scratch.
+static int redo_flagged_exact(int nq, int nb, int d, int k, const float *base, const float *query,
+                              int *assign, float *dis, int id_offset, const int *flag_list,
+                              const int *flag_count_dev, int *n_flag_out, cudaStream_t st) {
+  (void)nq;
+  int n_flag = 0;
+  YB_CUDA(cudaMemcpyAsync(&n_flag, flag_count_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+  YB_CUDA(cudaStreamSynchronize(st));
+  *n_flag_out = n_flag;
+  if (n_flag <= 0) return 0;
+  float *qsub = nullptr, *dsub = nullptr;
+  int *asub = nullptr, *rows = nullptr;
+  void *ews = nullptr;
+  YB_CUDA(cudaMalloc(&qsub, sizeof(float) * (size_t)n_flag * d));
+  YB_CUDA(cudaMalloc(&dsub, sizeof(float) * (size_t)n_flag * k));
+  YB_CUDA(cudaMalloc(&asub, sizeof(int) * (size_t)n_flag * k));
+  YB_CUDA(cudaMalloc(&rows, sizeof(int) * (size_t)n_flag));
+  YB_CUDA(cudaMalloc(&ews, knn_exact_ws_bytes(n_flag, nb, k)));
+  YB_CUDA(cudaMemcpyAsync(rows, flag_list, sizeof(int) * (size_t)n_flag, cudaMemcpyDeviceToDevice, st));
+  long tot = (long)n_flag * d;
+  k_gather_rows<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(query, rows, n_flag, d, qsub);
+  count_launch();
+  int rc;
+  {
+    ProfScope ps(4, st);
+    rc = knn_exact(n_flag, nb, d, k, base, qsub, nullptr, asub, dsub, id_offset, ews, st);
+  }
+  if (!rc) {
+    tot = (long)n_flag * k;
+    k_scatter_results<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(rows, n_flag, k, asub, dsub,
+                                                                     assign, dis);
+    count_launch();
+    cudaStreamSynchronize(st);
+  }
+  cudaFree(qsub); cudaFree(dsub); cudaFree(asub); cudaFree(rows); cudaFree(ews);
+  return rc;
+}
+
+// ------------------------------------------------------------------ engine 1, k = 1
+// margin[q] = 2.05 * E_q with E_q the TF32 score error bound of the query (see kTf32ErrScale)
+__global__ void k_k1_margin(const float *__restrict__ query, int nq, int d,
+                            const float *__restrict__ bmax, float err_scale,
+                            float *__restrict__ margin) {
+  const int q = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  float s = 0.f;
+  for (int t = lane; t < d; t += 32) {
+    float v = query[(size_t)q * d + t];
+    s = fmaf(v, v, s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) margin[q] = 2.05f * err_scale * sqrtf(s) * (*bmax) + 1e-30f;
+}
+
+// exact re-rank of the few k = 1 candidates: one warp per query, one lane per candidate slot;
+// every lane walks its candidate row with the reference's arithmetic (yael/nn.c:100-129: float
+// norm of the base row, double norm of the query, sequential FP32 FMA dot product) and the warp
+// takes the (distance, id) minimum.  nn_single_full semantics (yael/nn.c:404-440).
+__global__ void __launch_bounds__(128)
+k_rerank_k1(int nq, int d, int slots, int lists, const float *__restrict__ base,
+            const float *__restrict__ query, const int *__restrict__ cand_id,
+            const float *__restrict__ cand_thr, int *__restrict__ assign, float *__restrict__ dis,
+            int id_offset, int *__restrict__ flags) {
+  const int q = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  const float *qrow = query + (size_t)q * d;
+  unsigned long long best = ~0ull;
+  double qn = 0.0;
+  bool have_qn = false;
+  for (int s0 = 0; s0 < slots; s0 += 32) {
+    const int slot = s0 + lane;
+    const int id = slot < slots ? cand_id[(size_t)q * slots + slot] : -1;
+    if (id >= 0) {
+      if (!have_qn) {
+        for (int t = 0; t < d; t++) qn += (double)__fmul_rn(qrow[t], qrow[t]);
+        have_qn = true;
+      }
+      const float *brow = base + (size_t)id * d;
+      float nf = 0.f, dot = 0.f;
+      for (int t = 0; t < d; t++) {
+        const float v = __ldg(brow + t);
+        nf = __fadd_rn(nf, __fmul_rn(v, v));
+        dot = fmaf(v, qrow[t], dot);
+      }
+      const float dist = __fadd_rn((float)(qn + (double)nf), __fmul_rn(-2.0f, dot));
+      const uint32_t fk = float_key(dist);
+      if (!is_nan_key(fk)) {
+        unsigned long long key = ((unsigned long long)fk << 32) | (unsigned)id;
+        best = key < best ? key : best;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+    best = t < best ? t : best;
+  }
+  if (lane == 0) {
+    int flag = 0;
+    for (int l = 0; l < lists; l++) {
+      float t = cand_thr[(size_t)q * lists + l];
+      if (t != t) flag = 1;  // NaN: a list overflowed, the candidate set is incomplete
+    }
+    flags[q] = flag;
+    const uint32_t fk = (uint32_t)(best >> 32);
+    const uint32_t bits = (fk & 0x80000000u) ? (fk & 0x7fffffffu) : ~fk;
+    const float dv = __uint_as_float(bits);
+    if (best != ~0ull && dv < 1e30f) {
+      assign[q] = (int)(uint32_t)best + id_offset;
+      dis[q] = dv;
+    } else {
+      assign[q] = -1;
+      dis[q] = 1e30f;
+    }
+  }
+}
+
+static int knn_tf32_nearest(int nq, int nb, int d, const float *base, const float *query,
+                            int *assign, float *dis, int id_offset, long *uncert_out,
+                            cudaStream_t st) {
+  const int dpad = (d + 3) & ~3;
+  Tf32Plan plan = tf32_plan_nearest(nq, nb, dpad);
+  if (!plan.ok) return -1000;
+  const int kp = plan.kprime, slots = plan.lists * kp;
+  const long padded = tf32_padded_rows(nb);
+  size_t need = Carver::need(sizeof(float) * (size_t)padded) + Carver::need(64) +
+                Carver::need(sizeof(float) * (size_t)nb * dpad) +
+                Carver::need(sizeof(float) * (size_t)nq * dpad) + center_ws_bytes(nb, d) +
+                Carver::need(sizeof(float) * (size_t)nq) +
+                Carver::need(sizeof(float) * (size_t)nq * slots) +
+                Carver::need(sizeof(int) * (size_t)nq * slots) +
+                Carver::need(sizeof(float) * (size_t)nq * plan.lists) +
+                2 * Carver::need(sizeof(int) * (size_t)nq) + Carver::need(plan.ws_bytes) + 1024;
+  int n_flag = 0;
+  {
+    ScratchScope ws(need, st);
+    Carver c(ws.p);
+    float *an = c.take<float>(padded);
+    float *scal = c.take<float>(16);
+    float *margin = c.take<float>(nq);
+    float *cscore = c.take<float>((size_t)nq * slots);
+    int *cid = c.take<int>((size_t)nq * slots);
+    float *cthr = c.take<float>((size_t)nq * plan.lists);
+    int *flags = c.take<int>(nq);
+    int *flag_list = c.take<int>(nq);
+    void *tfws = c.take<char>(plan.ws_bytes);
+    float *base_c = c.take<float>((size_t)nb * dpad);
+    float *query_c = c.take<float>((size_t)nq * dpad);
+    void *cws = c.take<char>(center_ws_bytes(nb, d));
+    int rc;
+    {
+      ProfScope ps(0, st);
+      if ((rc = center_operands(nq, nb, d, dpad, base, query, base_c, query_c, cws, st))) return rc;
+      if ((rc = row_norms_seq(base_c, nb, dpad, dpad, an, nullptr, st))) return rc;
+      if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
+      YB_CUDA(cudaMemsetAsync(scal, 0, 64, st));
+      k_sqrt_max<<<2 * sm_count(), 256, 0, st>>>(an, nb, scal);
+      YB_LAUNCH_CHECK();
+      k_k1_margin<<<(nq + 3) / 4, 128, 0, st>>>(query_c, nq, dpad, scal, kTf32ErrScale, margin);
+      YB_LAUNCH_CHECK();
+    }
+    {
+      ProfScope ps(1, st);
+      if ((rc = tf32_nearest(plan, nq, nb, dpad, base_c, query_c, an, margin, cscore, cid, cthr,
+                             tfws, st)))
+        return rc;
+    }
+    {
+      ProfScope ps(3, st);
+      k_rerank_k1<<<(nq + 3) / 4, 128, 0, st>>>(nq, d, slots, plan.lists, base, query, cid, cthr,
+                                                assign, dis, id_offset, flags);
+      YB_LAUNCH_CHECK();
+    }
+    k_collect_flags<<<(nq + 255) / 256, 256, 0, st>>>(flags, nq, flag_list, (int *)(scal + 1));
+    YB_LAUNCH_CHECK();
+    if ((rc = redo_flagged_exact(nq, nb, d, 1, base, query, assign, dis, id_offset, flag_list,
+                                 (int *)(scal + 1), &n_flag, st)))
+      return rc;
+  }
+  *uncert_out = n_flag;
+  return 0;
+}
+
 // returns -1000 when the tensor-core path does not apply (caller falls through to engine 0)
 int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *query,
                   const float *w, int *assign, float *dis, int id_offset, int force,
                   int *engine_out, long *uncert_out, cudaStream_t st) {
   if (force == 0 || w != nullptr) return -1000;
-  Tf32Plan plan = tf32_plan(nq, nb, d, k);
+  const int dpad = (d + 3) & ~3;  // the tensor pass runs on centred, pitch-padded copies
+  Tf32Plan plan = tf32_plan(nq, nb, dpad, k);
   if (!plan.ok) return -1000;
   if (force < 0 && (double)nq * nb < 1e6) return -1000;  // tiny problems: not worth a TMA setup
+  if (k == 1) {
+    int rc1 = knn_tf32_nearest(nq, nb, d, base, query, assign, dis, id_offset, uncert_out, st);
+    if (rc1 == 0) *engine_out = 1;
+    return rc1;
+  }
   const int kp = plan.kprime;
   const int stride = plan.lists * kp;  // candidates per query produced by the tensor pass
   const int m = kp;                     // candidates per query that are re-ranked
@@ -396,7 +670,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
   int j2 = (3 * kp + kSampleStride - 1) / kSampleStride;
   if (j2 < 32) j2 = 32;
   Tf32Plan splan = {};
-  if (use_sample) splan = tf32_plan_tiles(nq, nbt_s, d, j2);
+  if (use_sample) splan = tf32_plan_tiles(nq, nbt_s, dpad, j2);
   const bool sample_ok = use_sample && splan.ok;
   const int sstride = sample_ok ? splan.lists * j2 : 1;
   // level 1: t1 tiles spread over the database, j1-th smallest -> about 3*j2 rows of level 2
@@ -408,7 +682,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
   if (j1 < 12) j1 = 12;
   Tf32Plan l1plan = {};
   const bool level1_ok = sample_ok && t1 >= 8 && (size_t)nq * rows1 * 4 <= ((size_t)1 << 30) &&
-                         (l1plan = tf32_plan_tiles(nq, t1, d, 8)).ok;
+                         (l1plan = tf32_plan_tiles(nq, t1, dpad, 8)).ok;
 
   size_t need = Carver::need(sizeof(float) * (size_t)padded) + Carver::need(64) +
                 Carver::need(sizeof(float) * (size_t)nq * stride) +
@@ -416,7 +690,9 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
                 Carver::need(sizeof(float) * (size_t)nq * plan.lists) +
                 Carver::need(sizeof(int) * (size_t)nq * kp) +
                 2 * Carver::need(sizeof(int) * (size_t)nq) + kmin_ws_bytes(nq, kp) +
-                Carver::need(plan.ws_bytes) + 1024;
+                Carver::need(plan.ws_bytes) + 1024 +
+                Carver::need(sizeof(float) * (size_t)nb * dpad) +
+                Carver::need(sizeof(float) * (size_t)nq * dpad) + center_ws_bytes(nb, d);
   if (sample_ok)
     need += Carver::need(sizeof(float) * (size_t)nq * sstride) +
             Carver::need(sizeof(int) * (size_t)nq * sstride) +
@@ -428,7 +704,6 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
             2 * Carver::need(sizeof(int) * (size_t)nq * j1) + kmin_ws_bytes(nq, j1) +
             Carver::need(l1plan.ws_bytes);
   int n_flag = 0;
-  int *flag_list_keep = nullptr;
   {
     ScratchScope ws(need, st);
     Carver c(ws.p);
@@ -442,11 +717,15 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
     int *flag_list = c.take<int>(nq);
     void *kws = c.take<char>(kmin_ws_bytes(nq, kp));
     void *tfws = c.take<char>(plan.ws_bytes);
+    float *base_c = c.take<float>((size_t)nb * dpad);
+    float *query_c = c.take<float>((size_t)nq * dpad);
+    void *cws = c.take<char>(center_ws_bytes(nb, d));
     float *thr_init = nullptr;
     int rc;
     {
       ProfScope ps(0, st);
-      if ((rc = row_norms_seq(base, nb, d, d, an, nullptr, st))) return rc;
+      if ((rc = center_operands(nq, nb, d, dpad, base, query, base_c, query_c, cws, st))) return rc;
+      if ((rc = row_norms_seq(base_c, nb, dpad, dpad, an, nullptr, st))) return rc;
       if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
       YB_CUDA(cudaMemsetAsync(scal, 0, 64, st));
       k_sqrt_max<<<2 * sm_count(), 256, 0, st>>>(an, nb, scal);
@@ -470,14 +749,14 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
         float *vals1 = (float *)c.take<int>((size_t)nq * j1);
         void *kws1 = c.take<char>(kmin_ws_bytes(nq, j1));
         void *tfws1 = c.take<char>(l1plan.ws_bytes);
-        if ((rc = tf32_scores(l1plan, nq, nb, d, t1, stride1, base, query, an, slab, rows1, tfws1, st)))
+        if ((rc = tf32_scores(l1plan, nq, nb, dpad, t1, stride1, base_c, query_c, an, slab, rows1, tfws1, st)))
           return rc;
         if ((rc = kmin_rows(slab, rows1, rows1, nq, j1, +1, sel1, vals1, 0, 0, kws1, st))) return rc;
         k_threshold_from_kmin<<<(nq + 255) / 256, 256, 0, st>>>(sel1, vals1, nq, j1, thr1);
         YB_LAUNCH_CHECK();
         thr_l1 = thr1;
       }
-      if ((rc = tf32_shortlist(splan, nq, nb, d, nbt_s, kSampleStride, base, query, an, thr_l1,
+      if ((rc = tf32_shortlist(splan, nq, nb, dpad, nbt_s, kSampleStride, base_c, query_c, an, thr_l1,
                                sscore, sid, sthr, stfws, st)))
         return rc;
       if ((rc = kmin_rows(sscore, sstride, sstride, nq, j2, +1, ssel, svals, 0, 0, skws, st)))
@@ -487,7 +766,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
     }
     {
       ProfScope ps(1, st);
-      if ((rc = tf32_shortlist(plan, nq, nb, d, nbt, 1, base, query, an, thr_init, cscore, cid,
+      if ((rc = tf32_shortlist(plan, nq, nb, dpad, nbt, 1, base_c, query_c, an, thr_init, cscore, cid,
                                cthr, tfws, st)))
         return rc;
     }
@@ -503,7 +782,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
     A.dis = dis; A.assign = assign; A.id_offset = id_offset;
     A.cand_id = cid; A.cand_score = cscore; A.sel = need_sel ? sel : nullptr;
     A.cand_stride = stride; A.m = m; A.all_listed = (nb <= kp);
-    A.cand_thr = cthr; A.lists = plan.lists;
+    A.cand_thr = cthr; A.lists = plan.lists; A.query_c = query_c; A.qc_ld = dpad;
     A.err_scale = kTf32ErrScale; A.bmax = scal; A.uncert_flags = flags;
     A.gsort = nullptr; A.m_pad = m_pad; A.k1 = (k == 1);
     rerank_attrs();
@@ -514,38 +793,9 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
     }
     k_collect_flags<<<(nq + 255) / 256, 256, 0, st>>>(flags, nq, flag_list, (int *)(scal + 1));
     YB_LAUNCH_CHECK();
-    YB_CUDA(cudaMemcpyAsync(&n_flag, scal + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-    YB_CUDA(cudaStreamSynchronize(st));
-    flag_list_keep = flag_list;
-    if (n_flag > 0) {
-      // uncertified queries: redo them with the exact engine (own allocations: rare path)
-      float *qsub = nullptr, *dsub = nullptr;
-      int *asub = nullptr, *rows = nullptr;
-      void *ews = nullptr;
-      YB_CUDA(cudaMalloc(&qsub, sizeof(float) * (size_t)n_flag * d));
-      YB_CUDA(cudaMalloc(&dsub, sizeof(float) * (size_t)n_flag * k));
-      YB_CUDA(cudaMalloc(&asub, sizeof(int) * (size_t)n_flag * k));
-      YB_CUDA(cudaMalloc(&rows, sizeof(int) * (size_t)n_flag));
-      YB_CUDA(cudaMalloc(&ews, knn_exact_ws_bytes(n_flag, nb, k)));
-      YB_CUDA(cudaMemcpyAsync(rows, flag_list_keep, sizeof(int) * (size_t)n_flag,
-                              cudaMemcpyDeviceToDevice, st));
-      long tot = (long)n_flag * d;
-      k_gather_rows<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(query, rows, n_flag, d, qsub);
-      YB_LAUNCH_CHECK();
-      {
-        ProfScope ps(4, st);
-        rc = knn_exact(n_flag, nb, d, k, base, qsub, nullptr, asub, dsub, id_offset, ews, st);
-      }
-      if (!rc) {
-        tot = (long)n_flag * k;
-        k_scatter_results<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(rows, n_flag, k, asub,
-                                                                         dsub, assign, dis);
-        count_launch();
-        cudaStreamSynchronize(st);
-      }
-      cudaFree(qsub); cudaFree(dsub); cudaFree(asub); cudaFree(rows); cudaFree(ews);
-      if (rc) return rc;
-    }
+    if ((rc = redo_flagged_exact(nq, nb, d, k, base, query, assign, dis, id_offset, flag_list,
+                                 (int *)(scal + 1), &n_flag, st)))
+      return rc;
   }
   *engine_out = 1;
   *uncert_out = n_flag;

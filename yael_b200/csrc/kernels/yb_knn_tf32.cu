@@ -195,6 +195,7 @@ struct Tf32Params {
   float *out_thr;      // [nq][lists] final admission threshold of every list: each row of the
                        // list's range that is NOT in the list has a score >= this value
   int tile_stride;     // logical tile j covers database tile j * tile_stride (sampling pass)
+  const float *k1_margin;  // [nq] k = 1 mode (NULL = top-k' mode): admit s < best_so_far + margin
   int debug;           // bring-up switches (YAEL_B200_TF32_DEBUG): 1 skip epilogue math, 2 skip MMAs
 };
 
@@ -285,9 +286,10 @@ __device__ __forceinline__ float warp_select_compact(float2 *list, int n, int kp
 // FMNMX per candidate); only when the minimum beats the query's admission threshold -- rare once
 // the threshold is tight -- are the 16 candidates tested one by one and appended to the query's
 // list in global memory.
-template <int G>
-__device__ __forceinline__ void process_group(const uint32_t (&v)[16], const float *bn, float thr,
-                                              float2 *mylist, int &cnt, int n0) {
+template <int G, bool K1>
+__device__ __forceinline__ void process_group(const uint32_t (&v)[16], const float *bn, float &thr,
+                                              float &best, float margin, float2 *mylist, int &cnt,
+                                              int cap, int n0) {
   float sc[16];
 #pragma unroll
   for (int c4 = 0; c4 < 4; c4++) {
@@ -309,6 +311,27 @@ __device__ __forceinline__ void process_group(const uint32_t (&v)[16], const flo
       if (sc[c] < thr) {
         mylist[cnt] = make_float2(sc[c], __int_as_float(n0 + G * 16 + c));
         cnt++;
+      }
+    }
+    if (K1) {
+      // k = 1: everything within `margin` of the best score seen so far stays a candidate.
+      // margin >= 2 * (TF32 error bound), so the exact nearest row can never be refused.
+      if (m < best) {
+        best = m;
+        thr = m + margin;
+      }
+      if (cnt > cap - 16) {  // drop what the tighter threshold no longer admits
+        int j = 0;
+        for (int e = 0; e < cnt; e++) {
+          const float2 x = mylist[e];
+          if (x.x < thr) mylist[j++] = x;
+        }
+        cnt = j;
+        if (cnt > cap - 16) {  // a dense cluster of near-ties: give up on this list
+          cnt = 0;
+          best = __uint_as_float(0x7fc00000u);  // NaN marks the overflow
+          thr = __uint_as_float(0xff800000u);
+        }
       }
     }
   }
@@ -432,6 +455,9 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       const int q = qt * TM + t;
       const bool valid = q < P.nq;
       float thr = valid ? (P.thr_init ? P.thr_init[q] : inf) : -inf;
+      float best = inf;
+      const bool k1 = P.k1_margin != nullptr;
+      const float margin = (k1 && valid) ? P.k1_margin[q] : 0.f;
       int cnt = 0;
       for (int jt = jt0; jt < jt1; jt++, tcount++) {
         const uint32_t buf = tcount & 1, slot = tcount % NBN;
@@ -462,14 +488,8 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
           if (P.debug & 8) {  // bring-up: math on whatever the registers hold, no TMEM traffic
 #pragma unroll
             for (int c = 0; c < 16; c++) va[c] = vb[c] = 0x3f800000u + c + jt;
-            process_group<0>(va, bn, thr, mylist, cnt, n0);
-            process_group<1>(vb, bn, thr, mylist, cnt, n0);
-            process_group<2>(va, bn, thr, mylist, cnt, n0);
-            process_group<3>(vb, bn, thr, mylist, cnt, n0);
-            process_group<4>(va, bn, thr, mylist, cnt, n0);
-            process_group<5>(vb, bn, thr, mylist, cnt, n0);
-            process_group<6>(va, bn, thr, mylist, cnt, n0);
-            process_group<7>(vb, bn, thr, mylist, cnt, n0);
+            process_group<0, false>(va, bn, thr, best, margin, mylist, cnt, P.cap, n0);
+            process_group<1, false>(vb, bn, thr, best, margin, mylist, cnt, P.cap, n0);
           } else if (P.debug & 4) {  // bring-up: TMEM traffic only
 #pragma unroll 1
             for (int g = 0; g < 8; g++) {
@@ -477,30 +497,37 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
               tc_wait_ld();
             }
           } else {
-            tc_ld16(ta, va);
-            tc_wait_ld();
-            tc_ld16(ta + 16, vb);
-            process_group<0>(va, bn, thr, mylist, cnt, n0);
-            tc_wait_ld();
-            tc_ld16(ta + 32, va);
-            process_group<1>(vb, bn, thr, mylist, cnt, n0);
-            tc_wait_ld();
-            tc_ld16(ta + 48, vb);
-            process_group<2>(va, bn, thr, mylist, cnt, n0);
-            tc_wait_ld();
-            tc_ld16(ta + 64, va);
-            process_group<3>(vb, bn, thr, mylist, cnt, n0);
-            tc_wait_ld();
-            tc_ld16(ta + 80, vb);
-            process_group<4>(va, bn, thr, mylist, cnt, n0);
-            tc_wait_ld();
-            tc_ld16(ta + 96, va);
-            process_group<5>(vb, bn, thr, mylist, cnt, n0);
-            tc_wait_ld();
-            tc_ld16(ta + 112, vb);
-            process_group<6>(va, bn, thr, mylist, cnt, n0);
-            tc_wait_ld();
-            process_group<7>(vb, bn, thr, mylist, cnt, n0);
+#define YB_TILE_GROUPS(K1FLAG)                                                              \
+  tc_ld16(ta, va);                                                                          \
+  tc_wait_ld();                                                                             \
+  tc_ld16(ta + 16, vb);                                                                     \
+  process_group<0, K1FLAG>(va, bn, thr, best, margin, mylist, cnt, P.cap, n0);              \
+  tc_wait_ld();                                                                             \
+  tc_ld16(ta + 32, va);                                                                     \
+  process_group<1, K1FLAG>(vb, bn, thr, best, margin, mylist, cnt, P.cap, n0);              \
+  tc_wait_ld();                                                                             \
+  tc_ld16(ta + 48, vb);                                                                     \
+  process_group<2, K1FLAG>(va, bn, thr, best, margin, mylist, cnt, P.cap, n0);              \
+  tc_wait_ld();                                                                             \
+  tc_ld16(ta + 64, va);                                                                     \
+  process_group<3, K1FLAG>(vb, bn, thr, best, margin, mylist, cnt, P.cap, n0);              \
+  tc_wait_ld();                                                                             \
+  tc_ld16(ta + 80, vb);                                                                     \
+  process_group<4, K1FLAG>(va, bn, thr, best, margin, mylist, cnt, P.cap, n0);              \
+  tc_wait_ld();                                                                             \
+  tc_ld16(ta + 96, va);                                                                     \
+  process_group<5, K1FLAG>(vb, bn, thr, best, margin, mylist, cnt, P.cap, n0);              \
+  tc_wait_ld();                                                                             \
+  tc_ld16(ta + 112, vb);                                                                    \
+  process_group<6, K1FLAG>(va, bn, thr, best, margin, mylist, cnt, P.cap, n0);              \
+  tc_wait_ld();                                                                             \
+  process_group<7, K1FLAG>(vb, bn, thr, best, margin, mylist, cnt, P.cap, n0);
+            if (k1) {
+              YB_TILE_GROUPS(true)
+            } else {
+              YB_TILE_GROUPS(false)
+            }
+#undef YB_TILE_GROUPS
           }
         }
         // accumulator buffer and |b|^2 slot are free again
@@ -508,7 +535,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         mbar_arrive(bar(Smem::t_empty + buf));
         mbar_arrive(bar(Smem::n_empty + slot));
         // keep room for a full half tile of appends in every list of the warp
-        unsigned need = __ballot_sync(0xffffffffu, cnt > P.cap - HALF_N);
+        unsigned need = __ballot_sync(0xffffffffu, !k1 && cnt > P.cap - HALF_N);
         while (need) {
           const int owner = __ffs(need) - 1;
           need &= need - 1;
@@ -522,7 +549,33 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
           }
         }
       }
-      if (!P.dump) {
+      if (!P.dump && k1) {
+        // k = 1: publish the candidates within the margin of the final best score
+        if (valid) {
+          const size_t l = (size_t)q * P.lists + sp * 2 + half;
+          const size_t o = l * P.kprime;
+          int nout = 0;
+          bool over = best != best;  // NaN: the list overflowed
+          for (int e = 0; e < cnt; e++) {
+            const float2 x = mylist[e];
+            if (x.x < thr) {
+              if (nout < P.kprime) {
+                P.out_score[o + nout] = x.x;
+                P.out_id[o + nout] = __float_as_int(x.y);
+                nout++;
+              } else {
+                over = true;
+              }
+            }
+          }
+          for (int e = nout; e < P.kprime; e++) {
+            P.out_score[o + e] = inf;
+            P.out_id[o + e] = -1;
+          }
+          // out_thr: every unlisted row of this list's range scores >= thr; NaN = overflow
+          P.out_thr[l] = over ? __uint_as_float(0x7fc00000u) : thr;
+        }
+      } else if (!P.dump) {
         // final compaction of over-full lists, then publish the shortlist of this item
         unsigned need = __ballot_sync(0xffffffffu, cnt > P.kprime);
         while (need) {
@@ -661,9 +714,9 @@ Tf32Plan tf32_plan(int nq, int nb, int d, int k) {
 
 static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical,
                        int tile_stride, const float *base, const float *query,
-                       const float *bnorm_padded, const float *thr_init, float *out_score,
-                       int *out_id, float *out_thr, float *dump, long dump_ld, void *ws,
-                       cudaStream_t st) {
+                       const float *bnorm_padded, const float *thr_init, const float *k1_margin,
+                       float *out_score, int *out_id, float *out_thr, float *dump, long dump_ld,
+                       void *ws, cudaStream_t st) {
   if ((((uintptr_t)base) & 15) || (((uintptr_t)query) & 15))
     return fail(6, "tf32 path needs 16-byte aligned matrices");
   CUtensorMap mq, mb;
@@ -688,6 +741,7 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   P.out_id = out_id;
   P.out_thr = out_thr;
   P.thr_init = thr_init;
+  P.k1_margin = k1_margin;
   P.tile_stride = tile_stride;
   {
     const char *e = getenv("YAEL_B200_TF32_DEBUG");
@@ -713,7 +767,26 @@ int tf32_shortlist(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical,
                    const float *thr_init, float *out_score, int *out_id, float *out_thr, void *ws,
                    cudaStream_t st) {
   return launch_tf32(plan, nq, nb, d, nbt_logical, tile_stride, base, query, bnorm_padded,
-                     thr_init, out_score, out_id, out_thr, nullptr, 0, ws, st);
+                     thr_init, nullptr, out_score, out_id, out_thr, nullptr, 0, ws, st);
+}
+
+// k = 1 mode: per list the (at most plan.kprime) rows whose TF32 score is within k1_margin[q]
+// of the list's best score; out_thr[q][l] = best + margin, or NaN when more rows than that
+// qualified (the caller re-does such queries exactly).
+int tf32_nearest(const Tf32Plan &plan, int nq, int nb, int d, const float *base, const float *query,
+                 const float *bnorm_padded, const float *k1_margin, float *out_score, int *out_id,
+                 float *out_thr, void *ws, cudaStream_t st) {
+  return launch_tf32(plan, nq, nb, d, tf32_tiles(nb), 1, base, query, bnorm_padded, nullptr,
+                     k1_margin, out_score, out_id, out_thr, nullptr, 0, ws, st);
+}
+
+Tf32Plan tf32_plan_nearest(int nq, int nb, int d) {
+  Tf32Plan p = tf32_plan_tiles(nq, tf32_tiles(nb), d, 8);
+  if (p.ok) {
+    p.cap = 64;
+    p.ws_bytes = Carver::need(sizeof(float2) * (size_t)p.ctas * 2 * TM * p.cap) + 256;
+  }
+  return p;
 }
 
 // raw TF32 scores of the logical tiles (every tile_stride-th database tile): scores[q][ld]
@@ -721,7 +794,7 @@ int tf32_scores(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical, in
                 const float *base, const float *query, const float *bnorm_padded, float *scores,
                 long ld, void *ws, cudaStream_t st) {
   return launch_tf32(plan, nq, nb, d, nbt_logical, tile_stride, base, query, bnorm_padded, nullptr,
-                     nullptr, nullptr, nullptr, scores, ld, ws, st);
+                     nullptr, nullptr, nullptr, nullptr, scores, ld, ws, st);
 }
 
 long tf32_padded_rows(int nb) { return (long)((nb + TN - 1) / TN) * TN; }
@@ -756,5 +829,5 @@ extern "C" int yb_debug_tf32_scores(int nq, int nb, int d, const float *base, co
   if ((rc = row_norms_seq(base, nb, d, d, bn, nullptr, st))) return rc;
   if ((rc = fill_f32(bn + nb, padded - nb, __builtin_inff(), st))) return rc;
   return launch_tf32(plan, nq, nb, d, tf32_tiles(nb), 1, base, query, bn, nullptr, nullptr, nullptr,
-                     nullptr, scores, nb, tws, st);
+                     nullptr, nullptr, scores, nb, tws, st);
 }
