@@ -40,6 +40,8 @@ sys.path.insert(0, ROOT)
 NB, NQ, D, K = 1_000_000, 10_000, 128, 100
 METRIC = "kNN queries/s (1M x 128 db, k=100)"
 UNIT = "queries/s"
+WORKLOAD = ("exact kNN, SIFT1M shape: 1M x 128 float32 database per GPU, 10000 queries, k=100 "
+            "(BASELINE configs[1]); knn_full semantics")
 
 
 def gen_data(rank):
@@ -163,8 +165,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic uniform[0,1), seeds 1234/1235",
-        "config": {"workload": "exact kNN 1M x 128 db, 10k queries, k=100 (BASELINE configs[1])",
-                   "step": "%d of the 10000 queries per step (bounded CPU sample)" % n},
+        "config": {"workload": WORKLOAD,
+                   "step": "%d of the 10000 queries per step (bounded CPU sample), all %d host threads" % (n, cores)},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": "%d queries per step against the full database" % n},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -256,8 +258,9 @@ def run_ours(args):
     ms = e0.elapsed_time(e1) / args.steps
     cnt = C.c_long(0)
     phase_ms = {}
-    for ph, name in ((0, "norms"), (1, "tf32_shortlist"), (2, "merge_select"), (3, "rerank"),
-                     (4, "exact_fallback"), (5, "exact_slab"), (6, "row_select")):
+    for ph, name in ((0, "center_and_norms"), (10, "sample_thresholds"), (1, "tf32_shortlist"),
+                     (2, "merge_select"), (3, "rerank"), (4, "exact_fallback"), (5, "exact_slab"),
+                     (6, "row_select")):
         t = L.yb_prof_ms(ph, C.byref(cnt), 0)
         if cnt.value:
             phase_ms[name] = t / cnt.value
@@ -317,8 +320,14 @@ def run_ours(args):
     if "tf32_shortlist" in phase_ms:
         kms = phase_ms["tf32_shortlist"]
         ach = 2.0 * NQ * NB * D / (kms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "k_knn_tf32", "achieved": ach, "peak": peak,
-                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+        traffic = None
+        try:  # DRAM bytes of this kernel from the committed ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_knn_tf32_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "kernel": "k_knn_tf32 (full pass; the sampling passes are in phase_ms)",
+                "achieved": ach, "peak": peak,
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "kernel_ms": kms, "peak_source": peak_src,
                 "frac_of_bf16_peak": ach / bf16_peak,
                 "algorithmic_flops_per_launch": 2.0 * NQ * NB * D}
@@ -334,11 +343,11 @@ def run_ours(args):
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "tf32 shortlist + f32 exact re-rank",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (tf32 tensor-core shortlist, exact f32 re-rank)",
         "data": "synthetic uniform[0,1), seeds 1234/1235",
         "config": {
-            "workload": "exact kNN, SIFT1M shape: 1M x 128 float32 database per GPU, 10000 queries, "
-                        "k=100 (BASELINE configs[1]); knn_full semantics",
+            "workload": WORKLOAD,
             "parallelism": ("single GPU" if world == 1 else
                             "database sharded x%d (1M rows per rank), NCCL all-gather of per-rank "
                             "top-k + merge; value counts query x 1M-shard scans" % world),
