@@ -9,7 +9,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libyael_b200.so")
+LIB_PATH = os.environ.get("YAEL_B200_LIB") or os.path.join(HERE, "libyael_b200.so")  # override: A/B runs
 CSRC = os.path.join(HERE, "csrc")
 
 _f = C.POINTER(C.c_float)
