@@ -26,11 +26,13 @@ struct Tf32Plan {
   int splits;      // database ranges per query tile
   int lists;       // shortlists produced per query (2 per range: one per column half)
   int ctas;        // persistent grid size
+  int pair;        // CTAs launched as clusters of 2 sharing the database stream
   size_t ws_bytes; // workspace for buffers + shortlists
 };
 Tf32Plan tf32_plan(int nq, int nb, int d, int k);
 Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kprime);
 int tf32_kprime_for(int k);
+int tf32_pair_mode();
 // One pass of the tensor-core kernel over the logical tiles 0..nbt_logical-1, logical tile j being
 // database tile j*tile_stride (256 rows each).  Produces, for every query, `lists` shortlists of
 // `kprime` candidates: out_score[q][l][e] = |b|^2 - 2<q,b> evaluated with TF32 operands,

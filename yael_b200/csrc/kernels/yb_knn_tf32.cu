@@ -97,6 +97,32 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same box lands at the same shared offset in every CTA of `mask`, and completes the same
+// mbarrier offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, uint32_t bar,
+                                               int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+          "r"(bar),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes,
                                              uint32_t bar) {
   asm volatile(
@@ -196,6 +222,9 @@ struct Tf32Params {
                        // list's range that is NOT in the list has a score >= this value
   int tile_stride;     // logical tile j covers database tile j * tile_stride (sampling pass)
   const float *k1_margin;  // [nq] k = 1 mode (NULL = top-k' mode): admit s < best_so_far + margin
+  int pair;            // 1: CTAs run as clusters of 2 that share every database chunk: each CTA
+                       // fetches half of it and multicasts it to both (L2->SM traffic halves)
+  int tiles_q2;        // query-tile pairs when pair != 0
   int debug;           // bring-up switches (YAEL_B200_TF32_DEBUG): 1 skip epilogue math, 2 skip MMAs
 };
 
@@ -286,14 +315,74 @@ __device__ __forceinline__ float warp_select_compact(float2 *list, int n, int kp
 // FMNMX per candidate); only when the minimum beats the query's admission threshold -- rare once
 // the threshold is tight -- are the 16 candidates tested one by one and appended to the query's
 // list in global memory.
-template <int G, bool K1>
+// Slow paths, out of line and with the 16 scores passed BY VALUE (registers, no stack traffic in
+// the caller): the hot loop has to stay small -- an earlier fully inlined version stalled mostly
+// on instruction fetch.
+#define YB_SC16_PARAMS float s0, float s1, float s2, float s3, float s4, float s5, float s6, float s7, \
+                       float s8, float s9, float s10, float s11, float s12, float s13, float s14, float s15
+#define YB_SC16_ARGS(a) a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], \
+                        a[12], a[13], a[14], a[15]
+
+__device__ __noinline__ int slow_append(YB_SC16_PARAMS, float thr, float2 *mylist, int cnt, int id0) {
+  const float sc[16] = {s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15};
+#pragma unroll
+  for (int c = 0; c < 16; c++) {
+    if (sc[c] < thr) {
+      mylist[cnt] = make_float2(sc[c], __int_as_float(id0 + c));
+      cnt++;
+    }
+  }
+  return cnt;
+}
+
+// k = 1: everything within `margin` of the best score seen so far stays a candidate.
+// margin >= 2 * (TF32 error bound), so the exact nearest row can never be refused.
+// state[0] = thr, state[1] = best (in/out through a small per-thread struct in registers)
+struct K1State {
+  float thr, best;
+  int cnt;
+};
+__device__ __noinline__ K1State slow_append_k1(YB_SC16_PARAMS, float m, K1State st, float margin,
+                                               float2 *mylist, int cap, int id0) {
+  const float sc[16] = {s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15};
+#pragma unroll
+  for (int c = 0; c < 16; c++) {
+    if (sc[c] < st.thr) {
+      mylist[st.cnt] = make_float2(sc[c], __int_as_float(id0 + c));
+      st.cnt++;
+    }
+  }
+  if (m < st.best) {
+    st.best = m;
+    st.thr = m + margin;
+  }
+  if (st.cnt > cap - 16) {  // drop what the tighter threshold no longer admits
+    int j = 0;
+    for (int e = 0; e < st.cnt; e++) {
+      const float2 x = mylist[e];
+      if (x.x < st.thr) mylist[j++] = x;
+    }
+    st.cnt = j;
+    if (st.cnt > cap - 16) {  // a dense cluster of near-ties: give up on this list
+      st.cnt = 0;
+      st.best = __uint_as_float(0x7fc00000u);  // NaN marks the overflow
+      st.thr = __uint_as_float(0xff800000u);
+    }
+  }
+  return st;
+}
+
+// 16 accumulator columns of one query.  Fast path: scores and their minimum (one FFMA and one
+// FMNMX3 lane per candidate); only when the minimum beats the query's admission threshold --
+// rare once the threshold is tight -- are the 16 candidates tested one by one.
+template <bool K1>
 __device__ __forceinline__ void process_group(const uint32_t (&v)[16], const float *bn, float &thr,
                                               float &best, float margin, float2 *mylist, int &cnt,
-                                              int cap, int n0) {
+                                              int cap, int id0) {
   float sc[16];
 #pragma unroll
   for (int c4 = 0; c4 < 4; c4++) {
-    const float4 b4 = *reinterpret_cast<const float4 *>(bn + G * 16 + c4 * 4);
+    const float4 b4 = *reinterpret_cast<const float4 *>(bn + c4 * 4);
     sc[c4 * 4 + 0] = fmaf(__uint_as_float(v[c4 * 4 + 0]), -2.0f, b4.x);
     sc[c4 * 4 + 1] = fmaf(__uint_as_float(v[c4 * 4 + 1]), -2.0f, b4.y);
     sc[c4 * 4 + 2] = fmaf(__uint_as_float(v[c4 * 4 + 2]), -2.0f, b4.z);
@@ -306,33 +395,14 @@ __device__ __forceinline__ void process_group(const uint32_t (&v)[16], const flo
   float m67 = fminf(fminf(sc[12], sc[13]), fminf(sc[14], sc[15]));
   const float m = fminf(fminf(m01, m23), fminf(m45, m67));
   if (m < thr) {
-#pragma unroll
-    for (int c = 0; c < 16; c++) {
-      if (sc[c] < thr) {
-        mylist[cnt] = make_float2(sc[c], __int_as_float(n0 + G * 16 + c));
-        cnt++;
-      }
-    }
     if (K1) {
-      // k = 1: everything within `margin` of the best score seen so far stays a candidate.
-      // margin >= 2 * (TF32 error bound), so the exact nearest row can never be refused.
-      if (m < best) {
-        best = m;
-        thr = m + margin;
-      }
-      if (cnt > cap - 16) {  // drop what the tighter threshold no longer admits
-        int j = 0;
-        for (int e = 0; e < cnt; e++) {
-          const float2 x = mylist[e];
-          if (x.x < thr) mylist[j++] = x;
-        }
-        cnt = j;
-        if (cnt > cap - 16) {  // a dense cluster of near-ties: give up on this list
-          cnt = 0;
-          best = __uint_as_float(0x7fc00000u);  // NaN marks the overflow
-          thr = __uint_as_float(0xff800000u);
-        }
-      }
+      K1State st = {thr, best, cnt};
+      st = slow_append_k1(YB_SC16_ARGS(sc), m, st, margin, mylist, cap, id0);
+      thr = st.thr;
+      best = st.best;
+      cnt = st.cnt;
+    } else {
+      cnt = slow_append(YB_SC16_ARGS(sc), thr, mylist, cnt, id0);
     }
   }
 }
@@ -340,7 +410,7 @@ __device__ __forceinline__ void process_group(const uint32_t (&v)[16], const flo
 // ------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(TF32_THREADS, 1)
 k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_b,
-           const Tf32Params P) {
+           const __grid_constant__ CUtensorMap map_bh, const Tf32Params P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -352,7 +422,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     mbar_init(bar(Smem::a_empty), 1);
     for (int i = 0; i < STAGES; i++) {
       mbar_init(bar(Smem::b_full + i), 1);
-      mbar_init(bar(Smem::b_empty + i), 1);
+      mbar_init(bar(Smem::b_empty + i), P.pair ? 2 : 1);  // paired: both CTAs' MMAs must be done
     }
     for (int i = 0; i < NBN; i++) {
       mbar_init(bar(Smem::n_full + i), 1);
@@ -374,15 +444,25 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  uint32_t crank = 0;
+  if (P.pair) {
+    crank = cluster_ctarank();
+    cluster_sync_all();  // the peer's barriers are initialised before anything is multicast
+  }
 
-  const int first_item = blockIdx.x, item_step = gridDim.x;
+  // work items: (range, query tile) -- or (range, query-tile pair) for paired CTAs, the two CTAs
+  // of a cluster taking the two tiles of the pair and walking the same database range
+  const int first_item = P.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_step = P.pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int tq_div = P.pair ? P.tiles_q2 : P.tiles_q;
 
   if (warp == EPI_WARPS) {
     // ======================================================================== TMA producer
     if (lane == 0) {
       uint32_t icount = 0, ccount = 0, tcount = 0;
       for (int item = first_item; item < P.items; item += item_step, icount++) {
-        const int sp = item / P.tiles_q, qt = item - sp * P.tiles_q;
+        const int sp = item / tq_div;
+        const int qt = P.pair ? (item - sp * tq_div) * 2 + (int)crank : item - sp * tq_div;
         const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
         // query tile: wait until the MMAs of the previous item have drained A
         mbar_wait(bar(Smem::a_empty), (icount & 1) ^ 1);
@@ -401,8 +481,15 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
             const uint32_t st = ccount % STAGES;
             mbar_wait(bar(Smem::b_empty + st), ((ccount / STAGES) & 1) ^ 1);
             mbar_expect_tx(bar(Smem::b_full + st), B_CHUNK_BYTES);
-            tma_load_2d(sbase + Smem::b_off + st * B_CHUNK_BYTES, &map_b, bar(Smem::b_full + st),
-                        kc * KC, jta * TN);
+            if (P.pair) {
+              // my half of the chunk (128 rows), delivered to both CTAs of the cluster
+              tma_load_2d_mc(sbase + Smem::b_off + st * B_CHUNK_BYTES + crank * (B_CHUNK_BYTES / 2),
+                             &map_bh, bar(Smem::b_full + st), kc * KC,
+                             jta * TN + (int)crank * (TN / 2), (uint16_t)3);
+            } else {
+              tma_load_2d(sbase + Smem::b_off + st * B_CHUNK_BYTES, &map_b, bar(Smem::b_full + st),
+                          kc * KC, jta * TN);
+            }
           }
         }
       }
@@ -412,7 +499,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     if (lane == 0) {
       uint32_t icount = 0, ccount = 0, tcount = 0;
       for (int item = first_item; item < P.items; item += item_step, icount++) {
-        const int sp = item / P.tiles_q;
+        const int sp = item / tq_div;
         const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
         mbar_wait(bar(Smem::a_full), icount & 1);
         for (int jt = jt0; jt < jt1; jt++, tcount++) {
@@ -433,7 +520,12 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
               tc_mma_tf32(d_tmem, adesc + (uint64_t)(2 * k8), bdesc + (uint64_t)(2 * k8),
                           IDESC_TF32, (kc | k8) != 0);
             }
-            tc_commit(bar(Smem::b_empty + st));  // smem slot reusable once these MMAs retire
+            // smem slot reusable once these MMAs retire (paired: tell both CTAs, either may
+            // multicast into the slot next)
+            if (P.pair)
+              tc_commit_mc(bar(Smem::b_empty + st), (uint16_t)3);
+            else
+              tc_commit(bar(Smem::b_empty + st));
           }
           tc_commit(bar(Smem::t_full + buf));  // accumulator complete
         }
@@ -450,7 +542,8 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * HALF_N;
     uint32_t tcount = 0;
     for (int item = first_item; item < P.items; item += item_step) {
-      const int sp = item / P.tiles_q, qt = item - sp * P.tiles_q;
+      const int sp = item / tq_div;
+      const int qt = P.pair ? (item - sp * tq_div) * 2 + (int)crank : item - sp * tq_div;
       const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
       const int q = qt * TM + t;
       const bool valid = q < P.nq;
@@ -488,8 +581,8 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
           if (P.debug & 8) {  // bring-up: math on whatever the registers hold, no TMEM traffic
 #pragma unroll
             for (int c = 0; c < 16; c++) va[c] = vb[c] = 0x3f800000u + c + jt;
-            process_group<0, false>(va, bn, thr, best, margin, mylist, cnt, P.cap, n0);
-            process_group<1, false>(vb, bn, thr, best, margin, mylist, cnt, P.cap, n0);
+            process_group<false>(va, bn, thr, best, margin, mylist, cnt, P.cap, n0);
+            process_group<false>(vb, bn + 16, thr, best, margin, mylist, cnt, P.cap, n0 + 16);
           } else if (P.debug & 4) {  // bring-up: TMEM traffic only
 #pragma unroll 1
             for (int g = 0; g < 8; g++) {
@@ -497,31 +590,17 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
               tc_wait_ld();
             }
           } else {
-#define YB_TILE_GROUPS(K1FLAG)                                                              \
-  tc_ld16(ta, va);                                                                          \
-  tc_wait_ld();                                                                             \
-  tc_ld16(ta + 16, vb);                                                                     \
-  process_group<0, K1FLAG>(va, bn, thr, best, margin, mylist, cnt, P.cap, n0);              \
-  tc_wait_ld();                                                                             \
-  tc_ld16(ta + 32, va);                                                                     \
-  process_group<1, K1FLAG>(vb, bn, thr, best, margin, mylist, cnt, P.cap, n0);              \
-  tc_wait_ld();                                                                             \
-  tc_ld16(ta + 48, vb);                                                                     \
-  process_group<2, K1FLAG>(va, bn, thr, best, margin, mylist, cnt, P.cap, n0);              \
-  tc_wait_ld();                                                                             \
-  tc_ld16(ta + 64, va);                                                                     \
-  process_group<3, K1FLAG>(vb, bn, thr, best, margin, mylist, cnt, P.cap, n0);              \
-  tc_wait_ld();                                                                             \
-  tc_ld16(ta + 80, vb);                                                                     \
-  process_group<4, K1FLAG>(va, bn, thr, best, margin, mylist, cnt, P.cap, n0);              \
-  tc_wait_ld();                                                                             \
-  tc_ld16(ta + 96, va);                                                                     \
-  process_group<5, K1FLAG>(vb, bn, thr, best, margin, mylist, cnt, P.cap, n0);              \
-  tc_wait_ld();                                                                             \
-  tc_ld16(ta + 112, vb);                                                                    \
-  process_group<6, K1FLAG>(va, bn, thr, best, margin, mylist, cnt, P.cap, n0);              \
-  tc_wait_ld();                                                                             \
-  process_group<7, K1FLAG>(vb, bn, thr, best, margin, mylist, cnt, P.cap, n0);
+#define YB_TILE_GROUPS(K1FLAG)                                                                  \
+  tc_ld16(ta, va);                                                                              \
+  _Pragma("unroll 1") for (int gg = 0; gg < 4; gg++) {                                          \
+    tc_wait_ld();                                                                               \
+    tc_ld16(ta + gg * 32 + 16, vb);                                                             \
+    process_group<K1FLAG>(va, bn + gg * 32, thr, best, margin, mylist, cnt, P.cap, n0 + gg * 32); \
+    tc_wait_ld();                                                                               \
+    if (gg < 3) tc_ld16(ta + gg * 32 + 32, va);                                                 \
+    process_group<K1FLAG>(vb, bn + gg * 32 + 16, thr, best, margin, mylist, cnt, P.cap,         \
+                          n0 + gg * 32 + 16);                                                   \
+  }
             if (k1) {
               YB_TILE_GROUPS(true)
             } else {
@@ -611,6 +690,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 
   tc_fence_before();
   __syncthreads();
+  if (P.pair) cluster_sync_all();  // nobody leaves while the peer can still write into it
   if (warp == EPI_WARPS + 1) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -657,6 +737,14 @@ static int make_map(CUtensorMap *m, const float *ptr, long rows, int d, int box_
   return 0;
 }
 
+// Independent CTAs (default) or CTA pairs that multicast the database chunks (YAEL_B200_PAIR=1).
+// Measured on the bench shape: pairing halves the L2->SM traffic but does not shorten the pass
+// (6.02 vs 5.90 ms) -- the L2 feed is not what bounds this kernel -- so it stays opt-in.
+int tf32_pair_mode() {
+  const char *e = getenv("YAEL_B200_PAIR");
+  return e ? (atoi(e) != 0) : 0;
+}
+
 int tf32_kprime_for(int k) {
   int a = 2 * k, b = k + 32 < 8 * k ? k + 32 : 8 * k;
   return a > b ? a : b;
@@ -672,8 +760,9 @@ Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kp) {
   int cap = pow2_ceil(8 * kp);
   if (cap < 512) cap = 512;
   if (cap > MAXL) cap = MAXL;
-  const int G = sm_count();
-  const int tiles_q = (nq + TM - 1) / TM;
+  const int pair = tf32_pair_mode();
+  const int G = pair ? sm_count() / 2 : sm_count();          // schedulable units (CTAs or pairs)
+  const int tiles_q = pair ? ((nq + TM - 1) / TM + 1) / 2 : (nq + TM - 1) / TM;  // tiles or pairs
   const int nbt = nbt_logical;
   // database ranges: the smallest split count whose last wave is at least 90 % full; every
   // range at least 8 tiles long
@@ -698,7 +787,8 @@ Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kp) {
   p.kprime = kp;
   p.cap = cap;
   long items = (long)tiles_q * p.splits;
-  p.ctas = (int)(items < G ? items : G);
+  p.ctas = (int)(items < G ? items : G) * (pair ? 2 : 1);
+  p.pair = pair;
   p.ws_bytes = Carver::need(sizeof(float2) * (size_t)p.ctas * 2 * TM * cap) + 256;
   p.ok = 1;
   return p;
@@ -719,10 +809,11 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
                        void *ws, cudaStream_t st) {
   if ((((uintptr_t)base) & 15) || (((uintptr_t)query) & 15))
     return fail(6, "tf32 path needs 16-byte aligned matrices");
-  CUtensorMap mq, mb;
+  CUtensorMap mq, mb, mbh;
   int rc;
   if ((rc = make_map(&mq, query, nq, d, TM))) return rc;
   if ((rc = make_map(&mb, base, nb, d, TN))) return rc;
+  if ((rc = make_map(&mbh, base, nb, d, TN / 2))) return rc;
   Tf32Params P = {};
   P.nq = nq; P.nb = nb; P.d = d;
   P.nkc = (d + KC - 1) / KC;
@@ -732,7 +823,9 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   P.range_tiles = (P.nbt + plan.splits - 1) / plan.splits;
   P.splits = plan.splits;
   P.lists = plan.lists;
-  P.items = P.tiles_q * P.splits;
+  P.pair = plan.pair;
+  P.tiles_q2 = (P.tiles_q + 1) / 2;
+  P.items = (plan.pair ? P.tiles_q2 : P.tiles_q) * P.splits;
   P.kprime = plan.kprime;
   P.cap = plan.cap;
   P.bnorm = bnorm_padded;
@@ -757,8 +850,26 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
                                       TF32_SMEM_BYTES, cudaGetErrorString(e));
     attr = true;
   }
-  k_knn_tf32<<<plan.ctas, TF32_THREADS, TF32_SMEM_BYTES, st>>>(mq, mb, P);
-  YB_LAUNCH_CHECK();
+  if (plan.pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(plan.ctas);
+    cfg.blockDim = dim3(TF32_THREADS);
+    cfg.dynamicSmemBytes = TF32_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_knn_tf32, mq, mb, mbh, P);
+    if (e != cudaSuccess) return fail(2, "k_knn_tf32 cluster launch: %s", cudaGetErrorString(e));
+    count_launch();
+  } else {
+    k_knn_tf32<<<plan.ctas, TF32_THREADS, TF32_SMEM_BYTES, st>>>(mq, mb, mbh, P);
+    YB_LAUNCH_CHECK();
+  }
   return 0;
 }
 
