@@ -756,6 +756,8 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
         YB_LAUNCH_CHECK();
         thr_l1 = thr1;
       }
+      if ((rc = fill_f32(sscore, (long)nq * sstride, __builtin_inff(), st))) return rc;
+      YB_CUDA(cudaMemsetAsync(sid, 0xff, sizeof(int) * (size_t)nq * sstride, st));
       if ((rc = tf32_shortlist(splan, nq, nb, dpad, nbt_s, kSampleStride, base_c, query_c, an, thr_l1,
                                sscore, sid, sthr, stfws, st)))
         return rc;
@@ -764,6 +766,8 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
       k_threshold_from_kmin<<<(nq + 255) / 256, 256, 0, st>>>(ssel, svals, nq, j2, thr_init);
       YB_LAUNCH_CHECK();
     }
+    if ((rc = fill_f32(cscore, (long)nq * stride, __builtin_inff(), st))) return rc;
+    YB_CUDA(cudaMemsetAsync(cid, 0xff, sizeof(int) * (size_t)nq * stride, st));
     {
       ProfScope ps(1, st);
       if ((rc = tf32_shortlist(plan, nq, nb, dpad, nbt, 1, base_c, query_c, an, thr_init, cscore, cid,

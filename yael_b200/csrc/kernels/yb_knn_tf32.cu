@@ -407,133 +407,32 @@ __device__ __forceinline__ void process_group(const uint32_t (&v)[16], const flo
   }
 }
 
-// ------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(TF32_THREADS, 1)
-k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_b,
-           const __grid_constant__ CUtensorMap map_bh, const Tf32Params P) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  const uint32_t sbase = smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// ------------------------------------------------------------------ epilogue role
+struct EpiCtx {
+  unsigned char *smem;
+  uint32_t sbase, tmem_base;
+  int warp, lane;
+  int first_item, item_step, tq_div;
+  int pair;            // 0: independent CTAs; 1: multicast pairs; 2: cta_group::2 pairs
+  uint32_t crank;
+  uint32_t t_empty_addr0, t_empty_addr1;  // where to signal "accumulator buffer drained" (local or leader CTA)
+  int t_empty_remote;        // the address is a shared::cluster address of the peer CTA
+  int n_full0, n_empty0, t_full0;  // barrier indices (the two kernels have different ring depths)
+};
+
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+
+__device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &E) {
+  unsigned char *smem = E.smem;
+  const uint32_t sbase = E.sbase, tmem_base = E.tmem_base;
+  const int warp = E.warp, lane = E.lane;
+  const int first_item = E.first_item, item_step = E.item_step, tq_div = E.tq_div;
+  const uint32_t crank = E.crank;
   auto bar = [&](int i) { return sbase + Smem::bar_off + 8 * i; };
-  volatile uint32_t *tmem_ptr_smem = (volatile uint32_t *)(smem + Smem::tmem_ptr_off);
-
-  if (threadIdx.x == 0) {
-    mbar_init(bar(Smem::a_full), 1);
-    mbar_init(bar(Smem::a_empty), 1);
-    for (int i = 0; i < STAGES; i++) {
-      mbar_init(bar(Smem::b_full + i), 1);
-      mbar_init(bar(Smem::b_empty + i), P.pair ? 2 : 1);  // paired: both CTAs' MMAs must be done
-    }
-    for (int i = 0; i < NBN; i++) {
-      mbar_init(bar(Smem::n_full + i), 1);
-      mbar_init(bar(Smem::n_empty + i), EPI_THREADS);
-    }
-    for (int i = 0; i < 2; i++) {
-      mbar_init(bar(Smem::t_full + i), 1);
-      mbar_init(bar(Smem::t_empty + i), EPI_THREADS);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == EPI_WARPS + 1) {  // TMEM: all 512 columns (2 accumulator buffers of 256)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     sbase + Smem::tmem_ptr_off),
-                 "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-  uint32_t crank = 0;
-  if (P.pair) {
-    crank = cluster_ctarank();
-    cluster_sync_all();  // the peer's barriers are initialised before anything is multicast
-  }
-
-  // work items: (range, query tile) -- or (range, query-tile pair) for paired CTAs, the two CTAs
-  // of a cluster taking the two tiles of the pair and walking the same database range
-  const int first_item = P.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int item_step = P.pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int tq_div = P.pair ? P.tiles_q2 : P.tiles_q;
-
-  if (warp == EPI_WARPS) {
-    // ======================================================================== TMA producer
-    if (lane == 0) {
-      uint32_t icount = 0, ccount = 0, tcount = 0;
-      for (int item = first_item; item < P.items; item += item_step, icount++) {
-        const int sp = item / tq_div;
-        const int qt = P.pair ? (item - sp * tq_div) * 2 + (int)crank : item - sp * tq_div;
-        const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
-        // query tile: wait until the MMAs of the previous item have drained A
-        mbar_wait(bar(Smem::a_empty), (icount & 1) ^ 1);
-        mbar_expect_tx(bar(Smem::a_full), (uint32_t)(P.nkc * A_CHUNK_BYTES));
-        for (int kc = 0; kc < P.nkc; kc++)
-          tma_load_2d(sbase + Smem::a_off + kc * A_CHUNK_BYTES, &map_q, bar(Smem::a_full), kc * KC,
-                      qt * TM);
-        for (int jt = jt0; jt < jt1; jt++, tcount++) {
-          const uint32_t slot = tcount % NBN;
-          mbar_wait(bar(Smem::n_empty + slot), ((tcount / NBN) & 1) ^ 1);
-          mbar_expect_tx(bar(Smem::n_full + slot), TN * 4);
-          const int jta = jt * P.tile_stride;  // actual database tile
-          bulk_load_1d(sbase + Smem::bn_off + slot * TN * 4, P.bnorm + (size_t)jta * TN, TN * 4,
-                       bar(Smem::n_full + slot));
-          for (int kc = 0; kc < P.nkc; kc++, ccount++) {
-            const uint32_t st = ccount % STAGES;
-            mbar_wait(bar(Smem::b_empty + st), ((ccount / STAGES) & 1) ^ 1);
-            mbar_expect_tx(bar(Smem::b_full + st), B_CHUNK_BYTES);
-            if (P.pair) {
-              // my half of the chunk (128 rows), delivered to both CTAs of the cluster
-              tma_load_2d_mc(sbase + Smem::b_off + st * B_CHUNK_BYTES + crank * (B_CHUNK_BYTES / 2),
-                             &map_bh, bar(Smem::b_full + st), kc * KC,
-                             jta * TN + (int)crank * (TN / 2), (uint16_t)3);
-            } else {
-              tma_load_2d(sbase + Smem::b_off + st * B_CHUNK_BYTES, &map_b, bar(Smem::b_full + st),
-                          kc * KC, jta * TN);
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == EPI_WARPS + 1) {
-    // ======================================================================== MMA issuer
-    if (lane == 0) {
-      uint32_t icount = 0, ccount = 0, tcount = 0;
-      for (int item = first_item; item < P.items; item += item_step, icount++) {
-        const int sp = item / tq_div;
-        const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
-        mbar_wait(bar(Smem::a_full), icount & 1);
-        for (int jt = jt0; jt < jt1; jt++, tcount++) {
-          const uint32_t buf = tcount & 1;
-          mbar_wait(bar(Smem::t_empty + buf), ((tcount >> 1) & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * TN;
-          for (int kc = 0; kc < P.nkc; kc++, ccount++) {
-            const uint32_t st = ccount % STAGES;
-            mbar_wait(bar(Smem::b_full + st), (ccount / STAGES) & 1);
-            tc_fence_after();
-            const int nk8 = (kc == P.nkc - 1) ? P.last_k8 : 4;
-            const uint64_t adesc = smem_desc_sw128(sbase + Smem::a_off + kc * A_CHUNK_BYTES);
-            const uint64_t bdesc = smem_desc_sw128(sbase + Smem::b_off + st * B_CHUNK_BYTES);
-            for (int k8 = 0; k8 < nk8; k8++) {
-              if (P.debug & 2) break;
-              // advancing K inside the 128-byte swizzle span: +32 bytes = +2 in 16-byte units
-              tc_mma_tf32(d_tmem, adesc + (uint64_t)(2 * k8), bdesc + (uint64_t)(2 * k8),
-                          IDESC_TF32, (kc | k8) != 0);
-            }
-            // smem slot reusable once these MMAs retire (paired: tell both CTAs, either may
-            // multicast into the slot next)
-            if (P.pair)
-              tc_commit_mc(bar(Smem::b_empty + st), (uint16_t)3);
-            else
-              tc_commit(bar(Smem::b_empty + st));
-          }
-          tc_commit(bar(Smem::t_full + buf));  // accumulator complete
-        }
-        tc_commit(bar(Smem::a_empty));  // query tile no longer needed
-      }
-    }
-  } else {
-    // ======================================================================== epilogue
+  {
     const int quarter = warp & 3, half = warp >> 2;
     const int t = quarter * 32 + lane;  // query row inside the tile == TMEM lane
     int *hist = (int *)(smem + Smem::hist_off) + warp * 256;
@@ -543,7 +442,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     uint32_t tcount = 0;
     for (int item = first_item; item < P.items; item += item_step) {
       const int sp = item / tq_div;
-      const int qt = P.pair ? (item - sp * tq_div) * 2 + (int)crank : item - sp * tq_div;
+      const int qt = E.pair ? (item - sp * tq_div) * 2 + (int)crank : item - sp * tq_div;
       const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
       const int q = qt * TM + t;
       const bool valid = q < P.nq;
@@ -554,8 +453,8 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       int cnt = 0;
       for (int jt = jt0; jt < jt1; jt++, tcount++) {
         const uint32_t buf = tcount & 1, slot = tcount % NBN;
-        mbar_wait(bar(Smem::n_full + slot), (tcount / NBN) & 1);
-        mbar_wait(bar(Smem::t_full + buf), (tcount >> 1) & 1);
+        mbar_wait(bar(E.n_full0 + slot), (tcount / NBN) & 1);
+        mbar_wait(bar(E.t_full0 + buf), (tcount >> 1) & 1);
         tc_fence_after();
         const float *bn = (const float *)(smem + Smem::bn_off + slot * TN * 4) + half * HALF_N;
         const int n0 = jt * P.tile_stride * TN + half * HALF_N;
@@ -609,10 +508,18 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 #undef YB_TILE_GROUPS
           }
         }
-        // accumulator buffer and |b|^2 slot are free again
+        // accumulator buffer and |b|^2 slot are free again: ONE arrival per warp (256 per-thread
+        // arrivals on the same barrier word serialise and cost more than the tile's math)
         tc_fence_before();
-        mbar_arrive(bar(Smem::t_empty + buf));
-        mbar_arrive(bar(Smem::n_empty + slot));
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t te = buf ? E.t_empty_addr1 : E.t_empty_addr0;
+          if (E.t_empty_remote)
+            mbar_arrive_cluster(te);
+          else
+            mbar_arrive(te);
+          mbar_arrive(bar(E.n_empty0 + slot));
+        }
         // keep room for a full half tile of appends in every list of the warp
         unsigned need = __ballot_sync(0xffffffffu, !k1 && cnt > P.cap - HALF_N);
         while (need) {
@@ -670,22 +577,165 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
           }
         }
         __syncwarp();
-        if (valid) {
-          const size_t o = ((size_t)q * P.lists + sp * 2 + half) * P.kprime;
-          P.out_thr[(size_t)q * P.lists + sp * 2 + half] = thr;
-          for (int e = 0; e < P.kprime; e++) {
-            if (e < cnt) {
-              const float2 x = mylist[e];
-              P.out_score[o + e] = x.x;
-              P.out_id[o + e] = __float_as_int(x.y);
+        if (valid) P.out_thr[(size_t)q * P.lists + sp * 2 + half] = thr;
+        // publish: the warp copies its 32 lists one after the other with coalesced accesses.
+        // Only the valid entries are written -- the caller pre-fills the output with
+        // (+inf, -1), and with tight thresholds a list holds a few dozen entries, not k'.
+        for (int owner = 0; owner < 32; owner++) {
+          const int n = __shfl_sync(0xffffffffu, valid ? cnt : 0, owner);
+          if (n == 0) continue;
+          const float2 *l = (const float2 *)__shfl_sync(0xffffffffu, (unsigned long long)mylist, owner);
+          const int qo = __shfl_sync(0xffffffffu, q, owner);
+          const size_t o = ((size_t)qo * P.lists + sp * 2 + half) * P.kprime;
+          for (int e = lane; e < n; e += 32) {
+            const float2 x = l[e];
+            P.out_score[o + e] = x.x;
+            P.out_id[o + e] = __float_as_int(x.y);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(TF32_THREADS, 1)
+k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_b,
+           const __grid_constant__ CUtensorMap map_bh, const Tf32Params P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto bar = [&](int i) { return sbase + Smem::bar_off + 8 * i; };
+  volatile uint32_t *tmem_ptr_smem = (volatile uint32_t *)(smem + Smem::tmem_ptr_off);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(Smem::a_full), 1);
+    mbar_init(bar(Smem::a_empty), 1);
+    for (int i = 0; i < STAGES; i++) {
+      mbar_init(bar(Smem::b_full + i), 1);
+      mbar_init(bar(Smem::b_empty + i), P.pair ? 2 : 1);  // paired: both CTAs' MMAs must be done
+    }
+    for (int i = 0; i < NBN; i++) {
+      mbar_init(bar(Smem::n_full + i), 1);
+      mbar_init(bar(Smem::n_empty + i), EPI_WARPS);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(bar(Smem::t_full + i), 1);
+      mbar_init(bar(Smem::t_empty + i), EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == EPI_WARPS + 1) {  // TMEM: all 512 columns (2 accumulator buffers of 256)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     sbase + Smem::tmem_ptr_off),
+                 "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  uint32_t crank = 0;
+  if (P.pair) {
+    crank = cluster_ctarank();
+    cluster_sync_all();  // the peer's barriers are initialised before anything is multicast
+  }
+
+  // work items: (range, query tile) -- or (range, query-tile pair) for paired CTAs, the two CTAs
+  // of a cluster taking the two tiles of the pair and walking the same database range
+  const int first_item = P.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_step = P.pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int tq_div = P.pair ? P.tiles_q2 : P.tiles_q;
+  EpiCtx ectx;
+  ectx.smem = smem; ectx.sbase = sbase; ectx.tmem_base = tmem_base; ectx.warp = warp; ectx.lane = lane;
+  ectx.first_item = first_item; ectx.item_step = item_step; ectx.tq_div = tq_div;
+  ectx.pair = P.pair; ectx.crank = crank;
+  ectx.t_empty_addr0 = bar(Smem::t_empty + 0); ectx.t_empty_addr1 = bar(Smem::t_empty + 1);
+  ectx.t_empty_remote = 0;
+  ectx.n_full0 = Smem::n_full; ectx.n_empty0 = Smem::n_empty; ectx.t_full0 = Smem::t_full;
+
+  if (warp == EPI_WARPS) {
+    // ======================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t icount = 0, ccount = 0, tcount = 0;
+      for (int item = first_item; item < P.items; item += item_step, icount++) {
+        const int sp = item / tq_div;
+        const int qt = P.pair ? (item - sp * tq_div) * 2 + (int)crank : item - sp * tq_div;
+        const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
+        // query tile: wait until the MMAs of the previous item have drained A
+        mbar_wait(bar(Smem::a_empty), (icount & 1) ^ 1);
+        mbar_expect_tx(bar(Smem::a_full), (uint32_t)(P.nkc * A_CHUNK_BYTES));
+        for (int kc = 0; kc < P.nkc; kc++)
+          tma_load_2d(sbase + Smem::a_off + kc * A_CHUNK_BYTES, &map_q, bar(Smem::a_full), kc * KC,
+                      qt * TM);
+        for (int jt = jt0; jt < jt1; jt++, tcount++) {
+          const uint32_t slot = tcount % NBN;
+          mbar_wait(bar(Smem::n_empty + slot), ((tcount / NBN) & 1) ^ 1);
+          mbar_expect_tx(bar(Smem::n_full + slot), TN * 4);
+          const int jta = jt * P.tile_stride;  // actual database tile
+          bulk_load_1d(sbase + Smem::bn_off + slot * TN * 4, P.bnorm + (size_t)jta * TN, TN * 4,
+                       bar(Smem::n_full + slot));
+          for (int kc = 0; kc < P.nkc; kc++, ccount++) {
+            const uint32_t st = ccount % STAGES;
+            mbar_wait(bar(Smem::b_empty + st), ((ccount / STAGES) & 1) ^ 1);
+            if ((P.debug & 16) && jt > jt0) {  // bring-up: no TMA traffic after the first tile
+              mbar_arrive(bar(Smem::b_full + st));
+              continue;
+            }
+            mbar_expect_tx(bar(Smem::b_full + st), B_CHUNK_BYTES);
+            if (P.pair) {
+              // my half of the chunk (128 rows), delivered to both CTAs of the cluster
+              tma_load_2d_mc(sbase + Smem::b_off + st * B_CHUNK_BYTES + crank * (B_CHUNK_BYTES / 2),
+                             &map_bh, bar(Smem::b_full + st), kc * KC,
+                             jta * TN + (int)crank * (TN / 2), (uint16_t)3);
             } else {
-              P.out_score[o + e] = inf;
-              P.out_id[o + e] = -1;
+              tma_load_2d(sbase + Smem::b_off + st * B_CHUNK_BYTES, &map_b, bar(Smem::b_full + st),
+                          kc * KC, jta * TN);
             }
           }
         }
       }
     }
+  } else if (warp == EPI_WARPS + 1) {
+    // ======================================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t icount = 0, ccount = 0, tcount = 0;
+      for (int item = first_item; item < P.items; item += item_step, icount++) {
+        const int sp = item / tq_div;
+        const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
+        mbar_wait(bar(Smem::a_full), icount & 1);
+        for (int jt = jt0; jt < jt1; jt++, tcount++) {
+          const uint32_t buf = tcount & 1;
+          mbar_wait(bar(Smem::t_empty + buf), ((tcount >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * TN;
+          for (int kc = 0; kc < P.nkc; kc++, ccount++) {
+            const uint32_t st = ccount % STAGES;
+            mbar_wait(bar(Smem::b_full + st), (ccount / STAGES) & 1);
+            tc_fence_after();
+            const int nk8 = (kc == P.nkc - 1) ? P.last_k8 : 4;
+            const uint64_t adesc = smem_desc_sw128(sbase + Smem::a_off + kc * A_CHUNK_BYTES);
+            const uint64_t bdesc = smem_desc_sw128(sbase + Smem::b_off + st * B_CHUNK_BYTES);
+            for (int k8 = 0; k8 < nk8; k8++) {
+              if (P.debug & 2) break;
+              // advancing K inside the 128-byte swizzle span: +32 bytes = +2 in 16-byte units
+              tc_mma_tf32(d_tmem, adesc + (uint64_t)(2 * k8), bdesc + (uint64_t)(2 * k8),
+                          IDESC_TF32, (kc | k8) != 0);
+            }
+            // smem slot reusable once these MMAs retire (paired: tell both CTAs, either may
+            // multicast into the slot next)
+            if (P.pair)
+              tc_commit_mc(bar(Smem::b_empty + st), (uint16_t)3);
+            else
+              tc_commit(bar(Smem::b_empty + st));
+          }
+          tc_commit(bar(Smem::t_full + buf));  // accumulator complete
+        }
+        tc_commit(bar(Smem::a_empty));  // query tile no longer needed
+      }
+    }
+  } else {
+    run_epilogue(P, ectx);
   }
 
   tc_fence_before();
@@ -694,6 +744,199 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
   if (warp == EPI_WARPS + 1) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------ the 2-SM kernel
+// Same roles and the same epilogue as k_knn_tf32, but two CTAs of a cluster form one MMA unit:
+// tcgen05.mma.cta_group::2, M = 256 (each CTA's 128 queries), N = 256 with HALF of every
+// database chunk (128 rows, 16 KB) in each CTA's shared memory.  Per SM and MMA instruction the
+// tensor core then reads 4 KB of A + 4 KB of B instead of 4 + 8: single-CTA SS-mode MMAs are
+// shared-memory-bandwidth bound at about half the nominal rate (measured: 254 cycles per
+// M128 N256 K8 instruction against a 128-cycle floor), which is why every peak GEMM on this
+// part is a "2sm" kernel.  The smaller B stage also doubles the pipeline depth (8 stages).
+//   * only the leader CTA (cluster rank 0) issues MMAs; it waits on ITS full barriers, which
+//     both CTAs' TMA loads complete (cta_group::2 loads signal the leader's barrier)
+//   * tcgen05.commit.cta_group::2 ... multicast releases the smem slots / publishes the
+//     accumulators in both CTAs
+//   * the peer's epilogue threads signal "accumulator drained" on the leader's barrier
+constexpr int STAGES2 = 8;
+constexpr int B2_CHUNK_BYTES = (TN / 2) * KC * 4;  // 16 KB: this CTA's half of a chunk
+struct Smem2 {
+  static constexpr int a_off = 0;
+  static constexpr int b_off = MAX_NKC * A_CHUNK_BYTES;
+  static constexpr int bn_off = b_off + STAGES2 * B2_CHUNK_BYTES;
+  static constexpr int hist_off = bn_off + NBN * TN * 4;
+  static constexpr int bar_off = hist_off + EPI_WARPS * 256 * 4;
+  static constexpr int a_full = 0, a_empty = 1, b_full = 2, b_empty = b_full + STAGES2,
+                       n_full = b_empty + STAGES2, n_empty = n_full + NBN,
+                       t_full = n_empty + NBN, t_empty = t_full + 2, nbar = t_empty + 2;
+  static constexpr int tmem_ptr_off = bar_off + nbar * 8;
+  static constexpr int total = tmem_ptr_off + 16;
+};
+static_assert(Smem2::bn_off == Smem::bn_off && Smem2::hist_off == Smem::hist_off,
+              "run_epilogue() addresses |b|^2 tiles and histograms through Smem::");
+static_assert(Smem2::bar_off == Smem::bar_off, "barrier block must sit at the same offset");
+constexpr int TF32_SMEM2_BYTES = Smem2::total;
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
+
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *map,
+                                                uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+          "r"(bar),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D=F32, A=B=TF32, K-major, N=256, M=256 (two CTAs x 128)
+constexpr uint32_t IDESC_TF32_2SM = (1u << 4) | (2u << 7) | (2u << 10) |
+                                    ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__global__ void __launch_bounds__(TF32_THREADS, 1)
+k_knn_tf32_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_bh,
+               const Tf32Params P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto bar = [&](int i) { return sbase + Smem2::bar_off + 8 * i; };
+  volatile uint32_t *tmem_ptr_smem = (volatile uint32_t *)(smem + Smem2::tmem_ptr_off);
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(Smem2::a_full), 1);
+    mbar_init(bar(Smem2::a_empty), 1);
+    for (int i = 0; i < STAGES2; i++) {
+      mbar_init(bar(Smem2::b_full + i), 1);
+      mbar_init(bar(Smem2::b_empty + i), 1);
+    }
+    for (int i = 0; i < NBN; i++) {
+      mbar_init(bar(Smem2::n_full + i), 1);
+      mbar_init(bar(Smem2::n_empty + i), EPI_WARPS);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(bar(Smem2::t_full + i), 1);
+      mbar_init(bar(Smem2::t_empty + i), 2 * EPI_WARPS);  // both CTAs' epilogue warps (leader's copy)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == EPI_WARPS + 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     sbase + Smem2::tmem_ptr_off),
+                 "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated in both
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int first_item = (int)(blockIdx.x >> 1), item_step = (int)(gridDim.x >> 1);
+  const int tq_div = P.tiles_q2;
+
+  if (warp == EPI_WARPS) {
+    // ======================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t icount = 0, ccount = 0, tcount = 0;
+      for (int item = first_item; item < P.items; item += item_step, icount++) {
+        const int sp = item / tq_div;
+        const int qt = (item - sp * tq_div) * 2 + (int)crank;
+        const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
+        mbar_wait(bar(Smem2::a_empty), (icount & 1) ^ 1);
+        if (leader)  // the leader's barrier collects the bytes of BOTH CTAs
+          mbar_expect_tx(bar(Smem2::a_full), (uint32_t)(2 * P.nkc * A_CHUNK_BYTES));
+        for (int kc = 0; kc < P.nkc; kc++)
+          tma_load_2d_2sm(sbase + Smem2::a_off + kc * A_CHUNK_BYTES, &map_q,
+                          bar(Smem2::a_full) & PEER_BIT_MASK, kc * KC, qt * TM);
+        for (int jt = jt0; jt < jt1; jt++, tcount++) {
+          const uint32_t slot = tcount % NBN;
+          mbar_wait(bar(Smem2::n_empty + slot), ((tcount / NBN) & 1) ^ 1);
+          mbar_expect_tx(bar(Smem2::n_full + slot), TN * 4);
+          const int jta = jt * P.tile_stride;
+          bulk_load_1d(sbase + Smem2::bn_off + slot * TN * 4, P.bnorm + (size_t)jta * TN, TN * 4,
+                       bar(Smem2::n_full + slot));
+          for (int kc = 0; kc < P.nkc; kc++, ccount++) {
+            const uint32_t st = ccount % STAGES2;
+            mbar_wait(bar(Smem2::b_empty + st), ((ccount / STAGES2) & 1) ^ 1);
+            if (leader) mbar_expect_tx(bar(Smem2::b_full + st), 2 * B2_CHUNK_BYTES);
+            // this CTA's half of the chunk: rows [crank*128, +128) of the tile
+            tma_load_2d_2sm(sbase + Smem2::b_off + st * B2_CHUNK_BYTES, &map_bh,
+                            bar(Smem2::b_full + st) & PEER_BIT_MASK, kc * KC,
+                            jta * TN + (int)crank * (TN / 2));
+          }
+        }
+      }
+    }
+  } else if (warp == EPI_WARPS + 1) {
+    // ======================================================================== MMA issuer
+    if (leader && lane == 0) {
+      uint32_t icount = 0, ccount = 0, tcount = 0;
+      for (int item = first_item; item < P.items; item += item_step, icount++) {
+        const int sp = item / tq_div;
+        const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
+        mbar_wait(bar(Smem2::a_full), icount & 1);
+        for (int jt = jt0; jt < jt1; jt++, tcount++) {
+          const uint32_t buf = tcount & 1;
+          mbar_wait(bar(Smem2::t_empty + buf), ((tcount >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * TN;
+          for (int kc = 0; kc < P.nkc; kc++, ccount++) {
+            const uint32_t st = ccount % STAGES2;
+            mbar_wait(bar(Smem2::b_full + st), (ccount / STAGES2) & 1);
+            tc_fence_after();
+            const int nk8 = (kc == P.nkc - 1) ? P.last_k8 : 4;
+            const uint64_t adesc = smem_desc_sw128(sbase + Smem2::a_off + kc * A_CHUNK_BYTES);
+            const uint64_t bdesc = smem_desc_sw128(sbase + Smem2::b_off + st * B2_CHUNK_BYTES);
+            for (int k8 = 0; k8 < nk8; k8++)
+              tc_mma_tf32_2sm(d_tmem, adesc + (uint64_t)(2 * k8), bdesc + (uint64_t)(2 * k8),
+                              IDESC_TF32_2SM, (kc | k8) != 0);
+            tc_commit_2sm(bar(Smem2::b_empty + st), (uint16_t)3);
+          }
+          tc_commit_2sm(bar(Smem2::t_full + buf), (uint16_t)3);
+        }
+        tc_commit_2sm(bar(Smem2::a_empty), (uint16_t)3);
+      }
+    }
+  } else {
+    EpiCtx ectx;
+    ectx.smem = smem; ectx.sbase = sbase; ectx.tmem_base = tmem_base; ectx.warp = warp; ectx.lane = lane;
+    ectx.first_item = first_item; ectx.item_step = item_step; ectx.tq_div = tq_div;
+    ectx.pair = 2; ectx.crank = crank;
+    // "accumulator drained" goes to the LEADER's barrier (the only MMA issuer)
+    uint32_t a0, a1;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(a0) : "r"(bar(Smem2::t_empty + 0)));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(a1) : "r"(bar(Smem2::t_empty + 1)));
+    ectx.t_empty_addr0 = a0; ectx.t_empty_addr1 = a1;
+    ectx.t_empty_remote = 1;
+    ectx.n_full0 = Smem2::n_full; ectx.n_empty0 = Smem2::n_empty; ectx.t_full0 = Smem2::t_full;
+    run_epilogue(P, ectx);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves (or frees TMEM) while the pair is still working
+  if (warp == EPI_WARPS + 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -741,8 +984,8 @@ static int make_map(CUtensorMap *m, const float *ptr, long rows, int d, int box_
 // Measured on the bench shape: pairing halves the L2->SM traffic but does not shorten the pass
 // (6.02 vs 5.90 ms) -- the L2 feed is not what bounds this kernel -- so it stays opt-in.
 int tf32_pair_mode() {
-  const char *e = getenv("YAEL_B200_PAIR");
-  return e ? (atoi(e) != 0) : 0;
+  const char *e = getenv("YAEL_B200_PAIR");  // 0 independent CTAs, 1 multicast pairs, 2 cta_group::2
+  return e ? atoi(e) : 0;
 }
 
 int tf32_kprime_for(int k) {
@@ -764,11 +1007,11 @@ Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kp) {
   const int G = pair ? sm_count() / 2 : sm_count();          // schedulable units (CTAs or pairs)
   const int tiles_q = pair ? ((nq + TM - 1) / TM + 1) / 2 : (nq + TM - 1) / TM;  // tiles or pairs
   const int nbt = nbt_logical;
-  // database ranges: the smallest split count whose last wave is at least 90 % full; every
+  // database ranges: the smallest split count whose last wave is at least 97 % full; every
   // range at least 8 tiles long
   int best_s = 1;
   double best_eff = 0.0;
-  for (int s = 1; s <= 16; s++) {
+  for (int s = 1; s <= 32; s++) {
     if (s > 1 && nbt / s < 8) break;
     int range = (nbt + s - 1) / s;
     int s_eff = (nbt + range - 1) / range;
@@ -779,7 +1022,7 @@ Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kp) {
       best_eff = eff;
       best_s = s;
     }
-    if (eff >= 0.9) break;
+    if (eff >= 0.97) break;
   }
   int range = (nbt + best_s - 1) / best_s;
   p.splits = (nbt + range - 1) / range;
@@ -850,7 +1093,30 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
                                       TF32_SMEM_BYTES, cudaGetErrorString(e));
     attr = true;
   }
-  if (plan.pair) {
+  if (plan.pair == 2) {
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaError_t e = cudaFuncSetAttribute(k_knn_tf32_2sm, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           TF32_SMEM2_BYTES);
+      if (e != cudaSuccess) return fail(6, "cannot reserve shared memory: %s", cudaGetErrorString(e));
+      attr2 = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(plan.ctas);
+    cfg.blockDim = dim3(TF32_THREADS);
+    cfg.dynamicSmemBytes = TF32_SMEM2_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_knn_tf32_2sm, mq, mbh, P);
+    if (e != cudaSuccess) return fail(2, "k_knn_tf32_2sm cluster launch: %s", cudaGetErrorString(e));
+    count_launch();
+  } else if (plan.pair) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(plan.ctas);
     cfg.blockDim = dim3(TF32_THREADS);
