@@ -58,10 +58,12 @@ struct RerankArgs {
   int k1;                  // k == 1: nn_single_full start value (-1, 1e30f), nn.c:404-407
 };
 
+constexpr int RR_T = 128;  // threads per query in the re-rank kernels
+
 template <int MODE>
-__global__ void __launch_bounds__(128) k_rerank(RerankArgs A) {
+__global__ void __launch_bounds__(RR_T) k_rerank(RerankArgs A) {
   extern __shared__ unsigned char smem_raw[];
-  __shared__ float tile[4][32][33];
+  __shared__ float tile[RR_T / 32][32][33];
   __shared__ double qn_sh;
   const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = A.d;
@@ -77,12 +79,12 @@ __global__ void __launch_bounds__(128) k_rerank(RerankArgs A) {
                                     ? reinterpret_cast<unsigned long long *>(smem_raw + off)
                                     : A.gsort + (size_t)q * m_pad;
 
-  for (int t = tid; t < d; t += 128) qs[t] = A.query[(size_t)q * d + t];
+  for (int t = tid; t < d; t += RR_T) qs[t] = A.query[(size_t)q * d + t];
   int ki = m;
   if (MODE == 0) {
-    for (int j = tid; j < m; j += 128) ids[j] = A.idx[(size_t)q * m + j];
+    for (int j = tid; j < m; j += RR_T) ids[j] = A.idx[(size_t)q * m + j];
   } else {
-    for (int j = tid; j < m; j += 128) {
+    for (int j = tid; j < m; j += RR_T) {
       int pos = A.sel ? A.sel[(size_t)q * m + j] : j;
       ids[j] = pos >= 0 ? A.cand_id[(size_t)q * A.cand_stride + pos] : -1;
     }
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(128) k_rerank(RerankArgs A) {
   __syncthreads();
   const double qn = qn_sh;
 
-  for (int c0 = warp * 32; c0 < ki; c0 += 128) {
+  for (int c0 = warp * 32; c0 < ki; c0 += RR_T) {
     const int c = c0 + lane;
     const int id = c < ki ? ids[c] : -1;
     const float *rowp = id >= 0 ? A.base + (size_t)id * d : nullptr;
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(128) k_rerank(RerankArgs A) {
     }
   }
   __syncthreads();
-  for (int j = tid; j < m_pad; j += 128) {
+  for (int j = tid; j < m_pad; j += RR_T) {
     unsigned long long key = ~0ull;
     if (j < ki && ids[j] >= 0) {
       uint32_t fk = float_key(dv[j]);
@@ -148,22 +150,22 @@ __global__ void __launch_bounds__(128) k_rerank(RerankArgs A) {
   if (MODE == 1) {
     // order by (distance, id): positions are not ids, so fold the id in instead
     __syncthreads();
-    for (int j = tid; j < m_pad; j += 128) {
+    for (int j = tid; j < m_pad; j += RR_T) {
       unsigned long long key = sortbuf[j];
       if (key != ~0ull) sortbuf[j] = (key & 0xffffffff00000000ull) | (unsigned)ids[(int)(uint32_t)key];
     }
   }
-  bitonic_sort_u64(sortbuf, m_pad, tid, 128, [] { __syncthreads(); });
+  bitonic_sort_u64(sortbuf, m_pad, tid, RR_T, [] { __syncthreads(); });
 
   if (MODE == 0) {
-    for (int j = tid; j < ki; j += 128) {
+    for (int j = tid; j < ki; j += RR_T) {
       int pos = (int)(uint32_t)sortbuf[j];
       A.dis[(size_t)q * m + j] = dv[pos];
       A.idx[(size_t)q * m + j] = ids[pos];
     }
   } else {
     const int k = A.k;
-    for (int j = tid; j < k; j += 128) {
+    for (int j = tid; j < k; j += RR_T) {
       unsigned long long key = j < m_pad ? sortbuf[j] : ~0ull;
       uint32_t fk = (uint32_t)(key >> 32);
       uint32_t bits = (fk & 0x80000000u) ? (fk & 0x7fffffffu) : ~fk;
@@ -183,41 +185,52 @@ __global__ void __launch_bounds__(128) k_rerank(RerankArgs A) {
     // (TF32 score >= the largest selected score).  With T the smallest of those bounds, its
     // exact score is >= T - E_q, so the k-th exact distance D_k (score S_k = D_k - |q|^2)
     // cannot be beaten by such a row when S_k + E_q < T.  T = +inf: nothing was ever refused.
-    if (tid == 0) {
+    // (the reductions over lists / candidates / coordinates are done by warp 0 in parallel: a
+    // single thread chasing 200 dependent global loads used to dominate this kernel)
+    if (warp == 0) {
       const float inf = __uint_as_float(0x7f800000u);
       float T = inf;
+      int nvalid = 0;
+      float mx = -inf;
+      double qcn = 0.0;
       if (!A.all_listed) {
-        for (int l = 0; l < A.lists; l++) T = fminf(T, A.cand_thr[(size_t)q * A.lists + l]);
-        int nvalid = 0;
-        float mx = -inf;
-        for (int j = 0; j < m; j++) {
+        for (int l = lane; l < A.lists; l += 32) T = fminf(T, A.cand_thr[(size_t)q * A.lists + l]);
+        for (int j = lane; j < m; j += 32) {
           int pos = A.sel ? A.sel[(size_t)q * m + j] : j;
-          if (pos >= 0 && A.cand_id[(size_t)q * A.cand_stride + pos] >= 0) {
+          if (pos >= 0 && ids[j] >= 0) {
             nvalid++;
             mx = fmaxf(mx, A.cand_score[(size_t)q * A.cand_stride + pos]);
           }
         }
+        const float *qc = A.query_c + (size_t)q * A.qc_ld;
+        for (int t = lane; t < d; t += 32) qcn += (double)qc[t] * (double)qc[t];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          T = fminf(T, __shfl_xor_sync(0xffffffffu, T, o));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
+          qcn += __shfl_xor_sync(0xffffffffu, qcn, o);
+        }
         if (nvalid == m) T = fminf(T, mx);  // the merge may have dropped rows at or above mx
       }
-      int flag = 0;
-      if (T < inf) {
-        unsigned long long key = (k - 1) < m_pad ? sortbuf[k - 1] : ~0ull;
-        if (key == ~0ull) {
-          flag = 1;  // fewer than k candidates survived although rows were dropped
-        } else {
-          uint32_t fk = (uint32_t)(key >> 32);
-          uint32_t bits = (fk & 0x80000000u) ? (fk & 0x7fffffffu) : ~fk;
-          // the tensor pass scored CENTRED operands: S_c(b) = |q-b|^2 - |q-mu|^2
-          double qcn = 0.0;
-          const float *qc = A.query_c + (size_t)q * A.qc_ld;
-          for (int t = 0; t < d; t++) qcn += (double)qc[t] * (double)qc[t];
-          double Dk = (double)__uint_as_float(bits);
-          double E = (double)A.err_scale * sqrt(qcn) * (double)(*A.bmax) +
-                     4e-5 * (fabs(Dk) + qcn) + 2e-6 * (fabs(Dk) + qn);
-          if (!((Dk - qcn) + E < (double)T)) flag = 1;
+      if (lane == 0) {
+        int flag = 0;
+        if (T < inf) {
+          unsigned long long key = (k - 1) < m_pad ? sortbuf[k - 1] : ~0ull;
+          if (key == ~0ull) {
+            flag = 1;  // fewer than k candidates survived although rows were dropped
+          } else {
+            uint32_t fk = (uint32_t)(key >> 32);
+            uint32_t bits = (fk & 0x80000000u) ? (fk & 0x7fffffffu) : ~fk;
+            // the tensor pass scored CENTRED operands: S_c(b) = |q-b|^2 - |q-mu|^2
+            double Dk = (double)__uint_as_float(bits);
+            double E = (double)A.err_scale * sqrt(qcn) * (double)(*A.bmax) +
+                       4e-5 * (fabs(Dk) + qcn) + 2e-6 * (fabs(Dk) + qn);
+            if (!((Dk - qcn) + E < (double)T)) flag = 1;
+          }
         }
+        A.uncert_flags[q] = flag;
       }
-      A.uncert_flags[q] = flag;
     }
   }
 }
@@ -269,8 +282,8 @@ static size_t rerank_smem_bytes(int d, int m, int m_pad) {
 static void rerank_attrs() {
   static bool done = false;
   if (!done) {
-    cudaFuncSetAttribute(k_rerank<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_rerank<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_rerank<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_rerank<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     done = true;
   }
 }
@@ -380,13 +393,15 @@ static const float kTf32ErrScale = 1.05f / 256.0f;
 // margin (for k-means on unstructured data this is the difference between a margin that
 // covers every centroid and one that covers one or two).  The exact re-rank always reads the
 // caller's original rows.
-constexpr int CM_ROWS = 1024;  // rows per block in the column-mean reduction
+constexpr int CM_ROWS = 256;    // rows per block in the column-mean reduction
+constexpr int CM_BLOCKS = 128;  // the mean is taken over at most CM_BLOCKS * CM_ROWS sampled rows
+                                // (any shift vector is valid; a sampled mean is as good)
 
 __global__ void __launch_bounds__(256)
-k_col_partial(const float *__restrict__ x, long n, int d, float *__restrict__ psum,
-              int *__restrict__ pcnt) {
+k_col_partial(const float *__restrict__ x, long n, int d, long block_step,
+              float *__restrict__ psum, int *__restrict__ pcnt) {
   // thread t owns columns t, t+256, ...; sequential over the block's rows (deterministic)
-  const long r0 = (long)blockIdx.x * CM_ROWS, r1 = min(n, r0 + CM_ROWS);
+  const long r0 = (long)blockIdx.x * block_step, r1 = min(n, r0 + CM_ROWS);
   for (int c = threadIdx.x; c < d; c += 256) {
     float s = 0.f;
     int m = 0;
@@ -415,37 +430,48 @@ __global__ void k_col_final(const float *__restrict__ psum, const int *__restric
   mu[c] = m > 0 ? (float)(s / (double)m) : 0.f;
 }
 
-// out[r][0..dpad) = x[r][c] - mu[c] (zero padded to dpad columns)
-__global__ void k_center(const float *__restrict__ x, long n, int d, int dpad,
-                         const float *__restrict__ mu, float *__restrict__ out) {
-  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n * dpad) return;
-  long r = t / dpad;
-  int c = (int)(t - r * dpad);
-  out[t] = c < d ? __fsub_rn(x[r * d + c], mu[c]) : 0.f;
+// one warp per row: out[r][0..dpad) = x[r][c] - mu[c] (zero padded), optionally norm[r] = |out[r]|^2
+__global__ void __launch_bounds__(256)
+k_center_rows(const float *__restrict__ x, long n, int d, int dpad, const float *__restrict__ mu,
+              float *__restrict__ out, float *__restrict__ norm) {
+  const long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  float s = 0.f;
+  for (int c = lane; c < dpad; c += 32) {
+    float v = c < d ? __fsub_rn(x[r * d + c], __ldg(mu + c)) : 0.f;
+    out[r * dpad + c] = v;
+    s = fmaf(v, v, s);
+  }
+  if (norm) {
+    s = warp_sum(s);
+    if (lane == 0) norm[r] = s;
+  }
 }
 
 static size_t center_ws_bytes(long nb, int d) {
-  long nblk = (nb + CM_ROWS - 1) / CM_ROWS;
-  return 2 * Carver::need(sizeof(float) * (size_t)nblk * d) + Carver::need(sizeof(float) * d);
+  (void)nb;
+  return 2 * Carver::need(sizeof(float) * (size_t)CM_BLOCKS * d) + Carver::need(sizeof(float) * d);
 }
 
-// base_c / query_c: centred copies with row pitch dpad (multiple of 4 floats)
+// base_c / query_c: centred copies with row pitch dpad (multiple of 4 floats); bnorm[nb] = |b-mu|^2
 static int center_operands(int nq, int nb, int d, int dpad, const float *base, const float *query,
-                           float *base_c, float *query_c, void *ws, cudaStream_t st) {
+                           float *base_c, float *query_c, float *bnorm, void *ws, cudaStream_t st) {
   Carver c(ws);
   int nblk = (int)(((long)nb + CM_ROWS - 1) / CM_ROWS);
-  float *psum = c.take<float>((size_t)nblk * d);
-  int *pcnt = c.take<int>((size_t)nblk * d);
+  if (nblk > CM_BLOCKS) nblk = CM_BLOCKS;
+  long step = nblk > 0 ? (long)nb / nblk : CM_ROWS;
+  if (step < CM_ROWS) step = CM_ROWS;
+  float *psum = c.take<float>((size_t)CM_BLOCKS * d);
+  int *pcnt = c.take<int>((size_t)CM_BLOCKS * d);
   float *mu = c.take<float>(d);
-  k_col_partial<<<nblk, 256, 0, st>>>(base, nb, d, psum, pcnt);
+  k_col_partial<<<nblk, 256, 0, st>>>(base, nb, d, step, psum, pcnt);
   YB_LAUNCH_CHECK();
   k_col_final<<<(d + 127) / 128, 128, 0, st>>>(psum, pcnt, nblk, d, mu);
   YB_LAUNCH_CHECK();
-  long tb = (long)nb * dpad, tq = (long)nq * dpad;
-  k_center<<<(unsigned)((tb + 255) / 256), 256, 0, st>>>(base, nb, d, dpad, mu, base_c);
+  k_center_rows<<<(unsigned)(((long)nb + 7) / 8), 256, 0, st>>>(base, nb, d, dpad, mu, base_c, bnorm);
   YB_LAUNCH_CHECK();
-  k_center<<<(unsigned)((tq + 255) / 256), 256, 0, st>>>(query, nq, d, dpad, mu, query_c);
+  k_center_rows<<<(unsigned)(((long)nq + 7) / 8), 256, 0, st>>>(query, nq, d, dpad, mu, query_c, nullptr);
   YB_LAUNCH_CHECK();
   return 0;
 }
@@ -603,8 +629,7 @@ static int knn_tf32_nearest(int nq, int nb, int d, const float *base, const floa
     int rc;
     {
       ProfScope ps(0, st);
-      if ((rc = center_operands(nq, nb, d, dpad, base, query, base_c, query_c, cws, st))) return rc;
-      if ((rc = row_norms_seq(base_c, nb, dpad, dpad, an, nullptr, st))) return rc;
+      if ((rc = center_operands(nq, nb, d, dpad, base, query, base_c, query_c, an, cws, st))) return rc;
       if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
       YB_CUDA(cudaMemsetAsync(scal, 0, 64, st));
       k_sqrt_max<<<2 * sm_count(), 256, 0, st>>>(an, nb, scal);
@@ -653,7 +678,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
   const int m = kp;                     // candidates per query that are re-ranked
   const int m_pad = pow2_ceil(m < 2 ? 2 : m);
   size_t smem = rerank_smem_bytes(d, m, m_pad);
-  if (smem > 200 * 1024) return -1000;
+  if (smem > 160 * 1024) return -1000;
   const long padded = tf32_padded_rows(nb);
   const int nbt = tf32_tiles(nb);
   const bool need_sel = plan.lists > 1;
@@ -675,7 +700,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
   const int sstride = sample_ok ? splan.lists * j2 : 1;
   // level 1: t1 tiles spread over the database, j1-th smallest -> about 3*j2 rows of level 2
   int t1 = nbt_s / 8;
-  if (t1 > 32) t1 = 32;
+  if (t1 > 16) t1 = 16;
   const int stride1 = t1 > 0 ? nbt / t1 : 1;
   const long rows1 = (long)t1 * 256;
   int j1 = t1 > 0 ? (int)((3L * j2 * t1 + nbt_s - 1) / nbt_s) : 0;
@@ -724,8 +749,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
     int rc;
     {
       ProfScope ps(0, st);
-      if ((rc = center_operands(nq, nb, d, dpad, base, query, base_c, query_c, cws, st))) return rc;
-      if ((rc = row_norms_seq(base_c, nb, dpad, dpad, an, nullptr, st))) return rc;
+      if ((rc = center_operands(nq, nb, d, dpad, base, query, base_c, query_c, an, cws, st))) return rc;
       if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
       YB_CUDA(cudaMemsetAsync(scal, 0, 64, st));
       k_sqrt_max<<<2 * sm_count(), 256, 0, st>>>(an, nb, scal);
@@ -792,7 +816,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
     rerank_attrs();
     {
       ProfScope ps(3, st);
-      k_rerank<1><<<nq, 128, smem, st>>>(A);
+      k_rerank<1><<<nq, RR_T, smem, st>>>(A);
       YB_LAUNCH_CHECK();
     }
     k_collect_flags<<<(nq + 255) / 256, 256, 0, st>>>(flags, nq, flag_list, (int *)(scal + 1));
@@ -859,9 +883,9 @@ extern "C" int yb_knn_reorder_shortlist(int nq, int nb, int d, int k, const floa
   A.nq = nq; A.nb = nb; A.d = d; A.k = k; A.base = base; A.query = query;
   A.idx = idx; A.dis = dis; A.m = k; A.m_pad = m_pad; A.gsort = (unsigned long long *)ws.p;
   size_t smem = rerank_smem_bytes(d, k, m_pad);
-  if (smem > 200 * 1024) return fail(3, "knn_reorder_shortlist: d=%d k=%d too large for one CTA", d, k);
+  if (smem > 160 * 1024) return fail(3, "knn_reorder_shortlist: d=%d k=%d too large for one CTA", d, k);
   rerank_attrs();
-  k_rerank<0><<<nq, 128, smem, st>>>(A);
+  k_rerank<0><<<nq, RR_T, smem, st>>>(A);
   YB_LAUNCH_CHECK();
   return 0;
 }

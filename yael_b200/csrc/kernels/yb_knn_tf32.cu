@@ -466,11 +466,23 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
             tc_wait_ld();
             if (valid) {
               const long col0 = (long)jt * TN + half * HALF_N + g * 32;  // logical column
+              float *drow = P.dump + (size_t)q * P.dump_ld + col0;
+              if (col0 + 32 <= P.dump_ld && (P.dump_ld & 3) == 0) {
 #pragma unroll
-              for (int c = 0; c < 32; c++)
-                if (col0 + c < P.dump_ld)
-                  P.dump[(size_t)q * P.dump_ld + col0 + c] =
-                      fmaf(__uint_as_float(v[c]), -2.0f, bn[g * 32 + c]);
+                for (int c4 = 0; c4 < 8; c4++) {  // 128 contiguous bytes per thread
+                  float4 o;
+                  o.x = fmaf(__uint_as_float(v[c4 * 4 + 0]), -2.0f, bn[g * 32 + c4 * 4 + 0]);
+                  o.y = fmaf(__uint_as_float(v[c4 * 4 + 1]), -2.0f, bn[g * 32 + c4 * 4 + 1]);
+                  o.z = fmaf(__uint_as_float(v[c4 * 4 + 2]), -2.0f, bn[g * 32 + c4 * 4 + 2]);
+                  o.w = fmaf(__uint_as_float(v[c4 * 4 + 3]), -2.0f, bn[g * 32 + c4 * 4 + 3]);
+                  *reinterpret_cast<float4 *>(drow + c4 * 4) = o;
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < 32; c++)
+                  if (col0 + c < P.dump_ld)
+                    drow[c] = fmaf(__uint_as_float(v[c]), -2.0f, bn[g * 32 + c]);
+              }
             }
           }
         } else if (!(P.debug & 1)) {
