@@ -487,14 +487,14 @@ static int redo_flagged_exact(int nq, int nb, int d, int k, const float *base, c
   YB_CUDA(cudaStreamSynchronize(st));
   *n_flag_out = n_flag;
   if (n_flag <= 0) return 0;
-  float *qsub = nullptr, *dsub = nullptr;
-  int *asub = nullptr, *rows = nullptr;
-  void *ews = nullptr;
-  YB_CUDA(cudaMalloc(&qsub, sizeof(float) * (size_t)n_flag * d));
-  YB_CUDA(cudaMalloc(&dsub, sizeof(float) * (size_t)n_flag * k));
-  YB_CUDA(cudaMalloc(&asub, sizeof(int) * (size_t)n_flag * k));
-  YB_CUDA(cudaMalloc(&rows, sizeof(int) * (size_t)n_flag));
-  YB_CUDA(cudaMalloc(&ews, knn_exact_ws_bytes(n_flag, nb, k)));
+  // pooled blocks sized in steps of 4096 queries, so that a k-means loop (which lands here with
+  // a slightly different count every iteration) reuses them instead of paying cudaMalloc/cudaFree
+  const int n_cap = (n_flag + 4095) & ~4095;
+  float *qsub = (float *)yb_malloc(sizeof(float) * (size_t)n_cap * d);
+  float *dsub = (float *)yb_malloc(sizeof(float) * (size_t)n_cap * k);
+  int *asub = (int *)yb_malloc(sizeof(int) * (size_t)n_cap * k);
+  int *rows = (int *)yb_malloc(sizeof(int) * (size_t)n_cap);
+  void *ews = yb_malloc(knn_exact_ws_bytes(n_cap, nb, k));
   YB_CUDA(cudaMemcpyAsync(rows, flag_list, sizeof(int) * (size_t)n_flag, cudaMemcpyDeviceToDevice, st));
   long tot = (long)n_flag * d;
   k_gather_rows<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(query, rows, n_flag, d, qsub);
@@ -511,7 +511,7 @@ static int redo_flagged_exact(int nq, int nb, int d, int k, const float *base, c
     count_launch();
     cudaStreamSynchronize(st);
   }
-  cudaFree(qsub); cudaFree(dsub); cudaFree(asub); cudaFree(rows); cudaFree(ews);
+  yb_free(qsub); yb_free(dsub); yb_free(asub); yb_free(rows); yb_free(ews);
   return rc;
 }
 
