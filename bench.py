@@ -202,6 +202,76 @@ def measure_tf32_peak(torch, dev):
         return None
 
 
+def measure_extras(torch, L, dev):
+    """The other two BASELINE shapes, device-resident, one GPU (reported beside the headline;
+    the headline line above stays the kNN workload):
+      - k-means, BASELINE configs[3]: n = 10M, d = 128, k = 65536 (iterations/s, 2 iterations)
+      - Hamming kNN, BASELINE configs[2]: 10M x 64-bit codes, 10k queries, k = 100"""
+    out = {}
+    try:
+        del_later = []
+        torch.manual_seed(1236)
+        nbh, nqh = 10_000_000, 10_000
+        hb = torch.randint(0, 256, (nbh, 8), device=dev, dtype=torch.uint8)
+        hq = torch.randint(0, 256, (nqh, 8), device=dev, dtype=torch.uint8)
+        hi = torch.empty((nqh, 100), device=dev, dtype=torch.int32)
+        hd = torch.empty((nqh, 100), device=dev, dtype=torch.int16)
+        best = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = L.yb_nn_hamming(nqh, nbh, 8, 100, hb.data_ptr(), hq.data_ptr(), hi.data_ptr(), hd.data_ptr(), 0,
+                                 C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            e1.record()
+            e1.synchronize()
+            if rc == 0:
+                best = min(best, e0.elapsed_time(e1))
+        pairs = nqh * nbh / (best * 1e-3)
+        out["hamming_knn_10Mx64bit_10kq_k100"] = {
+            "queries_per_s": nqh / (best * 1e-3), "ms": best, "pair_distances_per_s": pairs,
+            "roofline": {"bound": "popcount pipe (2 POPC per 64-bit pair, 16 POPC/clk/SM, 148 SMs, 1.9 GHz)",
+                         "achieved": pairs, "peak": 148 * 8 * 1.9e9, "frac": pairs / (148 * 8 * 1.9e9),
+                         "unit": "pairs/s",
+                         "note": "algorithmic HBM traffic is 86 MB (13 us at peak): not HBM bound"}}
+        del hb, hq, hi, hd
+        torch.cuda.empty_cache()
+    except Exception as e:  # extras never break the headline line
+        out["hamming_error"] = str(e)
+    try:
+        from yael_b200.ynumpy import KMEANS_INIT_USER, KMEANS_QUIET
+        n, d, k, niter = 10_000_000, 128, 65536, 2
+        torch.manual_seed(1237)
+        v = torch.rand((n, d), device=dev, dtype=torch.float32)
+        cent = v[torch.randperm(n, device=dev)[:k]].cpu().numpy().copy()
+        nassign = np.empty(k, np.int32)
+        f, i = C.POINTER(C.c_float), C.POINTER(C.c_int)
+        L.yb_prof_enable(1)
+        L.yb_prof_ms(1, None, 1)
+        times = []
+        for _ in range(2):
+            c = cent.copy()
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            q = L.yb_kmeans_dev(d, n, k, niter, v.data_ptr(), KMEANS_INIT_USER | KMEANS_QUIET, 1, 1,
+                                c.ctypes.data_as(f), None, None, nassign.ctypes.data_as(i), None, None)
+            torch.cuda.synchronize()
+            times.append((time.perf_counter() - t) / niter)
+        cnt = C.c_long(0)
+        tms = L.yb_prof_ms(1, C.byref(cnt), 1)
+        kms = tms / max(1, cnt.value)
+        L.yb_prof_enable(0)
+        out["kmeans_10Mx128_k65536"] = {
+            "iter_per_s": 1.0 / min(times), "s_per_iter": min(times), "qerr": float(q),
+            "assignment_tf32_kernel_ms": kms,
+            "assignment_tflops": 2.0 * n * k * d / (kms * 1e-3) / 1e12,
+            "note": "one GPU, points resident in HBM, centroids from a seeded permutation (USER init)"}
+        del v
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["kmeans_error"] = str(e)
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -220,11 +290,14 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    # a real (non-default) stream: the library launches on the stream handle it is given, and the
+    # CUDA events below must sit on that same stream (handle 0 would mean "the library's own")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     base_h, query_h = gen_data(rank)
     base = torch.from_numpy(base_h).to(dev)
     query = torch.from_numpy(query_h).to(dev)
-    stream = torch.cuda.current_stream()
-    sp = C.c_void_p(stream.cuda_stream)
     searcher = ydist.ShardedKnn(base, K, rank=rank, world=world)
 
     def step():
@@ -340,6 +413,10 @@ def run_ours(args):
 
     cpu = cpu_reference_rate(base_h, query_h)
 
+    extras = None
+    if world == 1 and not args.no_extras:
+        extras = measure_extras(torch, L, dev)
+
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
@@ -357,7 +434,7 @@ def run_ours(args):
             "phase_ms": phase_ms,
         },
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": roof, "cpu_baseline": cpu,
+        "roofline": roof, "cpu_baseline": cpu, "extras": extras,
     }))
     if world > 1:
         dist.destroy_process_group()
@@ -369,6 +446,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the k-means / Hamming side measurements (N=1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
