@@ -46,6 +46,10 @@ int fvecs_new_read(const char *fname, int *d_out, float **vf);
 int ivecs_new_read(const char *fname, int *d_out, int **vi);
 int bvecs_new_read(const char *fname, int *d_out, unsigned char **v_out);
 int fvecs_write(const char *fname, int d, int n, const float *vf); /* vector.c:1459-1472 */
+int fvecs_read_txt(const char *fname, int d, int n, float *v);     /* vector.c:939-964 */
+int b2fvecs_read(const char *fname, int d, int n, float *v);        /* vector.c:923-936 */
+int fvecs_write_txt(const char *fname, int d, int n, const float *vf); /* vector.c:1475-1491 */
+int ivecs_write_txt(const char *fname, int d, int n, const int *v);    /* vector.c:1279-1295 */
 int ivecs_write(const char *fname, int d, int n, const int *v);    /* vector.c:1494-1537 */
 #ifdef __cplusplus
 }

@@ -3,13 +3,13 @@
  *
  * Two layers are exported by the library:
  *
- *  1. The DROP-IN layer: yael's own C prototypes (include/yael/*.h -- knn_full,
+ *  1. The DROP-IN layer: yael's own C prototypes (include/yael/ headers -- knn_full,
  *     knn_full_thread, compute_cross_distances, fvec_k_min, kmeans, compute_hamming,
  *     nn_hamming ...).  Host pointers in, host pointers out, exactly what a program
  *     linked against the reference's libyael.so binds (yael/Makefile:31-39).
  *
  *  2. This layer (prefix yb_): the same operations on DEVICE pointers and a caller
- *     stream, used by the drop-in layer itself (yael_b200/csrc/host/*.c), by the
+ *     stream, used by the drop-in layer itself (yael_b200/csrc/host/), by the
  *     multi-GPU plumbing (yael_b200/dist.py hands in torch tensors' data_ptr()) and by
  *     bench.py's HBM-resident timing.  Plain C: pointers, sizes, an opaque stream
  *     handle (cudaStream_t passed as void*).  No C++ or torch types.
@@ -28,7 +28,8 @@
 extern "C" {
 #endif
 
-typedef void *yb_stream_t; /* cudaStream_t; NULL = the library's own per-device stream */
+typedef void *yb_stream_t; /* cudaStream_t; NULL = the library's own per-device (non-blocking)
+                              stream; pass cudaStreamLegacy (0x1) for the legacy default stream */
 
 /* ---- runtime ------------------------------------------------------------------ */
 const char *yb_version(void);

@@ -1,0 +1,87 @@
+"""2 GPUs, NCCL (skipped on a single-GPU box): the sharded paths of yael_b200/dist.py end to end --
+database-sharded kNN and Hamming kNN (all-gather + merge) and point-sharded k-means (all-reduce
+hook of the C host loop) -- against the single-GPU result."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    try:
+        import yael_b200
+        return yael_b200.lib().yb_device_count()
+    except Exception:
+        return 0
+
+
+def _worker(rank, world, port, q):
+    import faulthandler
+    faulthandler.dump_traceback_later(100, exit=True)  # a stuck collective must not hang the box
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    import yael_b200
+    from yael_b200 import dist as ydist, ynumpy
+    torch.cuda.set_device(rank)
+    yael_b200.lib().yb_set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    ok = True
+    detail = {}
+    try:
+        r = np.random.RandomState(0)
+        base = r.random_sample((40000, 64)).astype(np.float32)
+        query = r.random_sample((500, 64)).astype(np.float32)
+        k = 20
+        lo, hi = ydist.shard_bounds(len(base), world)[rank]
+        s = ydist.ShardedKnn(torch.from_numpy(base[lo:hi]).to(dev), k, rank=rank, world=world, id_offset=lo)
+        idx, dis = s.search(torch.from_numpy(query).to(dev))
+        widx, wdis = ynumpy.knn(query, base, k)
+        detail['knn'] = bool(np.array_equal(idx.cpu().numpy(), widx) and np.array_equal(dis.cpu().numpy(), wdis))
+        # Hamming: bit-identical for any shard count
+        codes = r.randint(0, 256, (30000, 8)).astype(np.uint8)
+        qc = r.randint(0, 256, (200, 8)).astype(np.uint8)
+        lo, hi = ydist.shard_bounds(len(codes), world)[rank]
+        h = ydist.ShardedHamming(torch.from_numpy(codes[lo:hi]).to(dev), 15, rank=rank, world=world, id_offset=lo)
+        hi_, hd_ = h.search(torch.from_numpy(qc).to(dev))
+        wi, wd = ynumpy.knn_hamming(qc, codes, 15)
+        detail['hamming'] = bool(np.array_equal(hi_.cpu().numpy(), wi) and
+                                 np.array_equal(hd_.cpu().numpy().view(np.uint16), wd))
+        # k-means: sharded points, all-reduced sums; same assignments, centroids within 1e-4
+        v = r.random_sample((20000, 32)).astype(np.float32)
+        init = v[:64].copy()
+        lo, hi = ydist.shard_bounds(len(v), world)[rank]
+        cent, qerr, assign, nassign = ydist.sharded_kmeans(torch.from_numpy(v[lo:hi]).to(dev), 64, 5, init, len(v))
+        wc, wq, _, wa, wn = ynumpy.kmeans(v, 64, niter=5, verbose=False, init=init, output="all")
+        detail['kmeans_counts'] = bool(np.array_equal(nassign, wn) and np.array_equal(assign, wa[lo:hi]))
+        detail['kmeans_cent_maxdiff'] = float(np.abs(cent - wc).max())
+        detail['kmeans_qerr'] = (float(qerr), float(wq))
+        ok = detail['knn'] and detail['hamming'] and detail['kmeans_counts'] and \
+            detail['kmeans_cent_maxdiff'] < 1e-4 and abs(qerr - wq) < 1e-4 * wq
+        q.put((rank, bool(ok) if ok else detail))
+    except Exception as e:  # report instead of hanging the peer
+        q.put((rank, "error: %r" % (e,)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_sharded_paths_match_single_gpu():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=150) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)], res

@@ -318,3 +318,80 @@ int fvecs_write(const char *fname, int d, int n, const float *vf) { /* vector.c:
 int ivecs_write(const char *fname, int d, int n, const int *v) { /* vector.c:1521-1534 */
   return vecs_write(fname, sizeof(int), d, n, v, "ivecs_write");
 }
+
+/* ---- text / byte-vector variants used by progs/knn.c and progs/kmeans.c ---- */
+int fvecs_read_txt(const char *fname, int d, int n, float *v) { /* vector.c:939-964 */
+  FILE *f = fopen(fname, "r");
+  if (!f) {
+    fprintf(stderr, "fvecs_read_txt: could not open %s\n", fname);
+    perror("");
+    return -1;
+  }
+  long i;
+  for (i = 0; i < (long)n * d; i++) {
+    if (fscanf(f, "%f", v + i) != 1) {
+      if (feof(f)) break;
+      perror("fvecs_read_txt error 1");
+      fclose(f);
+      return -1;
+    }
+  }
+  fclose(f);
+  return (int)(i / d);
+}
+
+int b2fvecs_read(const char *fname, int d, int n, float *v) { /* vector.c:923-936: bytes -> floats */
+  int d_file, n_file;
+  if (bvecs_fsize(fname, &d_file, &n_file) < 0 || d_file != d || n > n_file) {
+    fprintf(stderr, "b2fvecs_read %s: expected %d vectors of dimension %d, file has %d x %d\n", fname,
+            n, d, n_file, d_file);
+    abort();
+  }
+  FILE *f = fopen(fname, "r");
+  if (!f) {
+    fprintf(stderr, "b2fvecs_read: Unable to open %s\n", fname);
+    abort();
+  }
+  unsigned char *row = bvec_new(d);
+  for (long i = 0; i < n; i++) {
+    int dd;
+    if (fread(&dd, sizeof(int), 1, f) != 1 || dd != d || fread(row, 1, d, f) != (size_t)d) {
+      fprintf(stderr, "b2fvecs_read %s: short read\n", fname);
+      abort();
+    }
+    for (int j = 0; j < d; j++) v[i * d + j] = row[j];
+  }
+  free(row);
+  fclose(f);
+  return n;
+}
+
+int fvecs_write_txt(const char *fname, int d, int n, const float *vf) { /* vector.c:1475-1491 */
+  int ret = 0;
+  FILE *fo = fopen(fname, "w");
+  if (!fo) {
+    perror("fvecs_write_txt: cannot open file");
+    return -1;
+  }
+  for (int i = 0; i < n; i++) {
+    for (int j = 0; j < d; j++) fprintf(fo, "%f ", vf[(long)i * d + j]);
+    ret += fprintf(fo, "\n");
+  }
+  fclose(fo);
+  return ret;
+}
+
+int ivecs_write_txt(const char *fname, int d, int n, const int *v) { /* vector.c:1279-1295 */
+  int ret = 0;
+  FILE *fo = fopen(fname, "w");
+  if (!fo) {
+    perror("ivecs_write_txt: cannot open file");
+    return -1;
+  }
+  for (int i = 0; i < n; i++) {
+    for (int j = 0; j < d; j++) fprintf(fo, "%d ", v[(long)i * d + j]);
+    ret += fprintf(fo, "\n");
+  }
+  fclose(fo);
+  return ret;
+}

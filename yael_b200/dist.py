@@ -28,7 +28,11 @@ def shard_bounds(n, world):
 
 
 def _stream_ptr(torch):
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """torch's current stream as the handle the C ABI expects.  Handle 0 would mean "the library's
+    own stream" there, so the legacy default stream is passed as cudaStreamLegacy (0x1): our
+    kernels and the NCCL collectives torch enqueues then share one stream order."""
+    h = torch.cuda.current_stream().cuda_stream
+    return C.c_void_p(h if h else 1)
 
 
 def allgather_lists(dist, torch, idx, dis, world):
@@ -36,7 +40,8 @@ def allgather_lists(dist, torch, idx, dis, world):
     gi = torch.empty((world,) + tuple(idx.shape), dtype=idx.dtype, device=idx.device)
     gd = torch.empty((world,) + tuple(dis.shape), dtype=dis.dtype, device=dis.device)
     dist.all_gather_into_tensor(gi.view(-1), idx.reshape(-1).contiguous())
-    dist.all_gather_into_tensor(gd.view(-1), dis.reshape(-1).contiguous())
+    # NCCL has no 16-bit integer type: ship the uint16 Hamming distances as raw bytes
+    dist.all_gather_into_tensor(gd.view(-1).view(torch.uint8), dis.reshape(-1).contiguous().view(torch.uint8))
     return gi, gd
 
 
@@ -184,7 +189,7 @@ def sharded_kmeans(v_shard, k, niter, init_centroids, n_total, flags=0, seed=0, 
     qerr = lib().yb_kmeans_dev(d, n, k, niter, v_shard.data_ptr(), flags | KMEANS_INIT_USER | KMEANS_QUIET,
                                seed, 1, cent.ctypes.data_as(f), None, assign.ctypes.data_as(i),
                                nassign.ctypes.data_as(i), C.cast(C.pointer(comm), C.c_void_p),
-                               C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                               _stream_ptr(torch))
     if qerr < 0:
         raise RuntimeError("kmeans: clustering failed. Is dataset diverse enough?")
     return cent, qerr, assign, nassign
