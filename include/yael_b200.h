@@ -152,6 +152,9 @@ int yb_nn_hamming(int nq, int nb, int ncodes, int k, const uint8_t *base, const 
                   int *assign, uint16_t *dis, int id_offset, yb_stream_t s);
 int yb_nn_hamming_merge(int nq, int k, int G, const int *assign_in, const uint16_t *dis_in,
                         int *assign_out, uint16_t *dis_out, yb_stream_t s);
+/* micro-benchmark: measured 64-bit xor+popcount pair rate of the whole GPU (the ceiling the
+ * Hamming scan is reported against) */
+double yb_debug_popc_pairs_per_s(yb_stream_t s);
 /* match_hamming_count / match_hamming_thres_prealloc (yael/hamming.c:283-300, 563-700):
  * pairs with distance <= ht, emitted query-major / base-ascending.  count is a device
  * size_t; idx receives (qid, bid) interleaved. */

@@ -143,6 +143,7 @@ DEVICE = {
     "yb_kmeans_scale": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
     "yb_kmeans_dev": (C.c_float, [C.c_int] * 4 + [_vp, C.c_int, C.c_long, C.c_int, _f, _f, _i, _i, _vp, _vp]),
     "yb_debug_tf32_scores": (C.c_int, [C.c_int] * 3 + [_vp, _vp, _vp, _vp]),
+    "yb_debug_popc_pairs_per_s": (C.c_double, [_vp]),
     "yb_compute_hamming": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "yb_nn_hamming": (C.c_int, [C.c_int] * 4 + [_vp, _vp, _vp, _vp, C.c_int, _vp]),
     "yb_nn_hamming_merge": (C.c_int, [C.c_int] * 3 + [_vp, _vp, _vp, _vp, _vp]),
@@ -164,6 +165,8 @@ def lib():
         L = C.CDLL(LIB_PATH)
         for table in (DROPIN, DEVICE):
             for name, (res, args) in table.items():
+                if name.startswith("yb_debug_") and os.environ.get("YAEL_B200_LIB") and not hasattr(L, name):
+                    continue  # A/B runs against an older build (developer override only)
                 fn = getattr(L, name)  # AttributeError here = header/library mismatch
                 fn.restype = res
                 fn.argtypes = args

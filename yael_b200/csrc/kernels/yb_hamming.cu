@@ -333,6 +333,30 @@ k_scan_u64(const unsigned long long *__restrict__ in, long n, unsigned long long
   }
 }
 
+// Micro-benchmark of the popcount pipe (SURVEY.md 8(d) asks for a measured ceiling): every
+// thread runs `iters` rounds of 8 independent 64-bit xor+popc chains on registers.
+__global__ void __launch_bounds__(256) k_popc_rate(unsigned long long seed, int iters,
+                                                    unsigned *__restrict__ sink) {
+  unsigned long long x[8];
+  unsigned acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    x[j] = seed * (threadIdx.x + 1 + 131 * j) + blockIdx.x;
+    acc[j] = 0;
+  }
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      acc[j] += __popcll(x[j] ^ (unsigned long long)acc[j]);
+      x[j] += 0x9E3779B97F4A7C15ull;
+    }
+  }
+  unsigned t = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) t += acc[j];
+  if (t == 0xdeadbeefu) sink[0] = t;  // keep the work alive
+}
+
 // ------------------------------------------------------------------ host helpers
 static int words_for(int ncodes) {
   int w = (ncodes + 7) / 8;
@@ -497,4 +521,29 @@ extern "C" int yb_match_hamming_thres(const uint8_t *bs1, const uint8_t *bs2, in
                                        int ht, int ncodes, int *idx, uint16_t *hams,
                                        unsigned long long *count, yb_stream_t s) {
   return match_impl(bs1, bs2, n1, n2, ht, ncodes, idx, hams, count, true, s);
+}
+
+// Measured ceiling of the popcount pipe: 64-bit xor+popc pair evaluations per second with every
+// SM saturated (8 independent chains per thread, 8 warps per scheduler).
+extern "C" double yb_debug_popc_pairs_per_s(yb_stream_t s) {
+  Guard g;
+  cudaStream_t st = stream_of(s);
+  unsigned *sink = (unsigned *)yb_malloc(64);
+  const int iters = 4096, blocks = sm_count() * 8;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  k_popc_rate<<<blocks, 256, 0, st>>>(12345, 64, sink);  // warm-up
+  cudaEventRecord(e0, st);
+  k_popc_rate<<<blocks, 256, 0, st>>>(12345, iters, sink);
+  cudaEventRecord(e1, st);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  yb_free(sink);
+  count_launch(2);
+  if (ms <= 0.f) return 0.0;
+  return (double)blocks * 256.0 * iters * 8.0 / (ms * 1e-3);
 }

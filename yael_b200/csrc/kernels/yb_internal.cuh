@@ -40,10 +40,25 @@ int tf32_pair_mode();
 // the list's range that is NOT listed has a TF32 score >= out_thr[q][l].  thr_init[q] (may be
 // NULL) is the initial admission threshold.  bnorm_padded: |b|^2 for tf32_padded_rows(nb) rows,
 // the padding filled with +inf.
+// Optional output placement of a shortlist pass: several passes (row ranges of one database) can
+// publish into one set of arrays [nq][lists_ld][kprime]; out_cnt[q][l] receives the number of
+// entries of every list, which lets the merge skip the empty slots.
+struct Tf32Out {
+  int *out_cnt;
+  int lists_ld;
+  int list0;
+  int id0;
+  float *gmin;   // group-minimum mode (tf32_group_min)
+  long gmin_ld;
+  int gsize;
+};
+int tf32_group_min(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical, int tile_stride,
+                   const float *base, const float *query, const float *bnorm_padded, float *gmin,
+                   long ld, int gsize, void *ws, cudaStream_t st);
 int tf32_shortlist(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical, int tile_stride,
                    const float *base, const float *query, const float *bnorm_padded,
                    const float *thr_init, float *out_score, int *out_id, float *out_thr, void *ws,
-                   cudaStream_t st);
+                   cudaStream_t st, const Tf32Out *oo = nullptr);
 int tf32_scores(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical, int tile_stride,
                 const float *base, const float *query, const float *bnorm_padded, float *scores,
                 long ld, void *ws, cudaStream_t st);

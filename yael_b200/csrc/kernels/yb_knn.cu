@@ -114,11 +114,15 @@ __global__ void __launch_bounds__(RR_T) k_rerank(RerankArgs A) {
     double nd = 0.0;
     for (int t0 = 0; t0 < d; t0 += 32) {
       const int w = min(32, d - t0);
-#pragma unroll 4
+      // all 32 row loads of the chunk in flight before the first one is consumed
+      float gv[32];
+#pragma unroll
       for (int r = 0; r < 32; r++) {
         const float *p = (const float *)__shfl_sync(0xffffffffu, (unsigned long long)rowp, r);
-        tile[warp][r][lane] = (p != nullptr && lane < w) ? __ldg(p + t0 + lane) : 0.f;
+        gv[r] = (p != nullptr && lane < w) ? __ldg(p + t0 + lane) : 0.f;
       }
+#pragma unroll
+      for (int r = 0; r < 32; r++) tile[warp][r][lane] = gv[r];
       __syncwarp();
       if (rowp != nullptr) {
         for (int t = 0; t < w; t++) {
@@ -379,6 +383,238 @@ __global__ void k_threshold_from_kmin(const int *__restrict__ idx, const float *
                                               : __uint_as_float(0x7f800000u);
 }
 
+// ------------------------------------------------------------------ shortlist merge
+// One CTA per query: the union of the query's shortlists (cnt[q][l] entries each, a few dozen
+// with sampled thresholds) -> positions of its kp smallest TF32 scores (ties by position),
+// and/or the kp-th smallest score itself.  Replaces "pre-fill every slot with +inf, then
+// radix-select over lists * k' slots": only the published entries are ever touched.
+//   gather   lists are placed at the exclusive prefix sum of their counts (deterministic)
+//   select   MSB radix select (8-bit digits) of the kp-th smallest 64-bit key (score key << 32
+//            | position; keys are unique), every thread holding its keys in registers -- a
+//            full bitonic sort of ~3k' keys per query is bound by shared-memory bandwidth and
+//            costs as much as the radix select over all slots it was meant to replace
+//   emit     ordered compaction of the keys <= that key
+// Unions larger than the buffer (or more lists than ML_LISTS) are folded in list by list with
+// a sort (keep the kp best, append): rare, adversarial inputs only.
+constexpr int ML_T = 128;
+constexpr int ML_CAP = 2048;     // needs kp + k' <= ML_CAP
+constexpr int ML_PER = ML_CAP / ML_T;
+constexpr int ML_LISTS = 1024;
+
+__device__ __forceinline__ int ml_block_excl_scan(int v, int *wtot, int &total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();  // wtot may still be read from a previous call
+  if (lane == 31) wtot[warp] = inc;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < ML_T / 32; w++) {
+    if (w < warp) base += wtot[w];
+    tot += wtot[w];
+  }
+  total = tot;
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(ML_T)
+k_merge_lists(const int *__restrict__ cnt, const float *__restrict__ score, int lists, int kprime,
+              int kp, int *__restrict__ sel, float *__restrict__ thr_out) {
+  __shared__ unsigned long long buf[ML_CAP];
+  __shared__ int loff[ML_LISTS];
+  __shared__ int hist[256];
+  __shared__ int wtot[ML_T / 32];
+  __shared__ unsigned long long prefix_sh;
+  __shared__ int rank_sh;
+  const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int *c = cnt + (size_t)q * lists;
+  const float *sc = score + (size_t)q * lists * kprime;
+  const float inf = __uint_as_float(0x7f800000u);
+
+  // ---- gather
+  const int per = (lists + ML_T - 1) / ML_T;  // contiguous lists per thread
+  int mine = 0;
+  for (int l = tid * per; l < min(lists, (tid + 1) * per); l++) mine += c[l];
+  int total;
+  int off = ml_block_excl_scan(mine, wtot, total);
+  int n;
+  if (total <= ML_CAP && lists <= ML_LISTS) {
+    for (int l = tid * per; l < min(lists, (tid + 1) * per); l++) {
+      loff[l] = off;
+      off += c[l];
+    }
+    __syncthreads();
+    for (int l = warp; l < lists; l += ML_T / 32) {
+      const int m = c[l], b = loff[l];
+      for (int e = lane; e < m; e += 32)
+        buf[b + e] = ((unsigned long long)float_key(sc[(size_t)l * kprime + e]) << 32) |
+                     (unsigned)(l * kprime + e);
+    }
+    n = total;
+    __syncthreads();
+  } else {
+    n = 0;
+    for (int l = 0; l < lists; l++) {
+      const int m = c[l];
+      if (m == 0) continue;
+      if (n + m > ML_CAP) {  // keep the kp best so far
+        const int n_pad = pow2_ceil(n);
+        for (int j = n + tid; j < n_pad; j += ML_T) buf[j] = ~0ull;
+        __syncthreads();
+        bitonic_sort_u64(buf, n_pad, tid, ML_T, [] { __syncthreads(); });
+        n = min(n, kp);
+      }
+      for (int e = tid; e < m; e += ML_T)
+        buf[n + e] = ((unsigned long long)float_key(sc[(size_t)l * kprime + e]) << 32) |
+                     (unsigned)(l * kprime + e);
+      n += m;
+      __syncthreads();
+    }
+  }
+
+  // ---- select: kstar = the kp-th smallest key (only when more than kp keys are present)
+  unsigned long long kreg[ML_PER];
+#pragma unroll
+  for (int j = 0; j < ML_PER; j++) {
+    const int i = j * ML_T + tid;
+    kreg[j] = i < n ? buf[i] : ~0ull;  // ~0 is never a key: its position field would be 2^32-1
+  }
+  unsigned long long kstar = ~0ull - 1;  // n <= kp: everything is selected
+  if (n > kp) {
+    unsigned long long prefix = 0;
+    int rank = kp - 1;
+    const bool wide_pos = (long)lists * kprime > 65536;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      if (!wide_pos && (shift == 24 || shift == 16)) continue;  // those position bits are all 0
+      const unsigned long long hi_mask = shift == 56 ? 0ull : (~0ull << (shift + 8));
+      for (int b = tid; b < 256; b += ML_T) hist[b] = 0;
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < ML_PER; j++)
+        if (kreg[j] != ~0ull && (kreg[j] & hi_mask) == prefix)
+          atomicAdd(&hist[(int)(kreg[j] >> shift) & 255], 1);
+      __syncthreads();
+      if (warp == 0) {
+        int h[8], ssum = 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+          h[b] = hist[lane * 8 + b];
+          ssum += h[b];
+        }
+        int inc = ssum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        int below = inc - ssum;
+        if (below <= rank && rank < inc) {
+          int b = 0;
+          while (below + h[b] <= rank) below += h[b++];
+          prefix_sh = prefix | ((unsigned long long)(lane * 8 + b) << shift);
+          rank_sh = rank - below;
+        }
+      }
+      __syncthreads();
+      prefix = prefix_sh;
+      rank = rank_sh;
+    }
+    kstar = prefix;
+  }
+
+  // ---- emit
+  if (sel) {
+    int mysel = 0;
+#pragma unroll
+    for (int j = 0; j < ML_PER; j++) mysel += (kreg[j] <= kstar);
+    int tot2;
+    int o = ml_block_excl_scan(mysel, wtot, tot2);
+    int *out = sel + (size_t)q * kp;
+#pragma unroll
+    for (int j = 0; j < ML_PER; j++)
+      if (kreg[j] <= kstar) out[o++] = (int)(uint32_t)kreg[j];
+    for (int j = tot2 + tid; j < kp; j += ML_T) out[j] = -1;
+  }
+  if (thr_out && tid == 0) {
+    float t = inf;
+    if (n >= kp) {
+      unsigned long long kk = kstar;
+      if (n == kp) {  // the largest key present
+        kk = 0;
+        for (int i = 0; i < n; i++) kk = buf[i] > kk ? buf[i] : kk;
+      }
+      const uint32_t fk = (uint32_t)(kk >> 32);
+      t = __uint_as_float((fk & 0x80000000u) ? (fk & 0x7fffffffu) : ~fk);
+    }
+    thr_out[q] = t;
+  }
+}
+
+// thr[q] = the j-th smallest of vals[q][0..n) (n <= RK_T * RK_PER; +inf when n < j): MSB radix
+// select on the order-preserving keys, every thread holding its values in registers.
+constexpr int RK_T = 256;
+constexpr int RK_PER = 16;
+
+__global__ void __launch_bounds__(RK_T)
+k_row_kth(const float *__restrict__ vals, long ld, int n, int j, float *__restrict__ thr) {
+  __shared__ int hist[256];
+  __shared__ uint32_t prefix_sh;
+  __shared__ int rank_sh;
+  const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float *row = vals + (size_t)q * ld;
+  uint32_t kreg[RK_PER];
+#pragma unroll
+  for (int i = 0; i < RK_PER; i++) {
+    const int c = i * RK_T + tid;
+    kreg[i] = c < n ? float_key(row[c]) : 0xffffffffu;  // absent = the NaN key (sorts last)
+  }
+  if (n < j) {
+    if (tid == 0) thr[q] = __uint_as_float(0x7f800000u);
+    return;
+  }
+  uint32_t prefix = 0;
+  int rank = j - 1;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    const uint32_t hi_mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+    hist[tid] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RK_PER; i++)
+      if ((kreg[i] & hi_mask) == prefix) atomicAdd(&hist[(kreg[i] >> shift) & 255], 1);
+    __syncthreads();
+    if (warp == 0) {
+      int h[8], ssum = 0;
+#pragma unroll
+      for (int b = 0; b < 8; b++) {
+        h[b] = hist[lane * 8 + b];
+        ssum += h[b];
+      }
+      int inc = ssum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      int below = inc - ssum;
+      if (below <= rank && rank < inc) {
+        int b = 0;
+        while (below + h[b] <= rank) below += h[b++];
+        prefix_sh = prefix | ((uint32_t)(lane * 8 + b) << shift);
+        rank_sh = rank - below;
+      }
+    }
+    __syncthreads();
+    prefix = prefix_sh;
+    rank = rank_sh;
+  }
+  if (tid == 0) thr[q] = __uint_as_float((prefix & 0x80000000u) ? (prefix & 0x7fffffffu) : ~prefix);
+}
+
 // TF32 operands keep 10 explicit mantissa bits; the hardware drops (or rounds) the rest, so
 // each operand carries a relative error < 2^-10 and each product < 2^-9 (+2^-20); with
 // Cauchy-Schwarz the score |b|^2 - 2<q,b> is off by at most 2 * 2^-9 * |q||b|.  5 % head
@@ -449,6 +685,56 @@ k_center_rows(const float *__restrict__ x, long n, int d, int dpad, const float 
   }
 }
 
+// d % 4 == 0 (pitch == d): one warp per 4 rows, 16-byte accesses, the 4 row loads in flight
+// together.  Same arithmetic per element as k_center_rows (the norm is a TF32-pass operand:
+// only its order of summation differs, which the error model covers).
+__global__ void __launch_bounds__(256)
+k_center_rows_v4(const float *__restrict__ x, long n, int d, const float *__restrict__ mu,
+                 float *__restrict__ out, float *__restrict__ norm) {
+  const long r0 = ((long)blockIdx.x * 8 + (threadIdx.x >> 5)) * 4;
+  const int lane = threadIdx.x & 31;
+  const int d4 = d >> 2;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = lane; c < d4; c += 32) {
+    const float4 m = __ldg(reinterpret_cast<const float4 *>(mu) + c);
+    float4 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (r0 + i < n) v[i] = __ldg(reinterpret_cast<const float4 *>(x + (r0 + i) * d) + c);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (r0 + i < n) {
+        float4 o;
+        o.x = __fsub_rn(v[i].x, m.x);
+        o.y = __fsub_rn(v[i].y, m.y);
+        o.z = __fsub_rn(v[i].z, m.z);
+        o.w = __fsub_rn(v[i].w, m.w);
+        reinterpret_cast<float4 *>(out + (r0 + i) * d)[c] = o;
+        s[i] = fmaf(o.x, o.x, s[i]);
+        s[i] = fmaf(o.y, o.y, s[i]);
+        s[i] = fmaf(o.z, o.z, s[i]);
+        s[i] = fmaf(o.w, o.w, s[i]);
+      }
+  }
+  if (norm) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      float t = warp_sum(s[i]);
+      if (lane == 0 && r0 + i < n) norm[r0 + i] = t;
+    }
+  }
+}
+
+static void launch_center_rows(const float *x, long n, int d, int dpad, const float *mu, float *out,
+                               float *norm, cudaStream_t st) {
+  if (n <= 0) return;
+  if (dpad == d && (((uintptr_t)x | (uintptr_t)out | (uintptr_t)mu) & 15) == 0)
+    k_center_rows_v4<<<(unsigned)((n + 31) / 32), 256, 0, st>>>(x, n, d, mu, out, norm);
+  else
+    k_center_rows<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(x, n, d, dpad, mu, out, norm);
+  count_launch();
+}
+
 static size_t center_ws_bytes(long nb, int d) {
   (void)nb;
   return 2 * Carver::need(sizeof(float) * (size_t)CM_BLOCKS * d) + Carver::need(sizeof(float) * d);
@@ -469,10 +755,9 @@ static int center_operands(int nq, int nb, int d, int dpad, const float *base, c
   YB_LAUNCH_CHECK();
   k_col_final<<<(d + 127) / 128, 128, 0, st>>>(psum, pcnt, nblk, d, mu);
   YB_LAUNCH_CHECK();
-  k_center_rows<<<(unsigned)(((long)nb + 7) / 8), 256, 0, st>>>(base, nb, d, dpad, mu, base_c, bnorm);
-  YB_LAUNCH_CHECK();
-  k_center_rows<<<(unsigned)(((long)nq + 7) / 8), 256, 0, st>>>(query, nq, d, dpad, mu, query_c, nullptr);
-  YB_LAUNCH_CHECK();
+  launch_center_rows(base, nb, d, dpad, mu, base_c, bnorm, st);
+  launch_center_rows(query, nq, d, dpad, mu, query_c, nullptr, st);
+  YB_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -682,6 +967,8 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
   const long padded = tf32_padded_rows(nb);
   const int nbt = tf32_tiles(nb);
   const bool need_sel = plan.lists > 1;
+  // merge by list counts (k_merge_lists) instead of pre-fill + radix select over every slot
+  const bool fast_merge = need_sel && 2 * kp <= ML_CAP;
 
   // Sampling pre-passes (large databases).  A threshold tau_q with "about 3x the wanted number
   // of rows below it" turns the streaming top-k into a plain filter: lists hardly ever fill up,
@@ -709,21 +996,35 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
   const bool level1_ok = sample_ok && t1 >= 8 && (size_t)nq * rows1 * 4 <= ((size_t)1 << 30) &&
                          (l1plan = tf32_plan_tiles(nq, t1, dpad, 8)).ok;
 
+  // single-level sampling: the sample pass emits the minimum of every group of gsize columns
+  // and the threshold is an order statistic of those minima (with j2 << groups the j2 smallest
+  // rows sit in distinct groups, so this is the j2-th smallest sampled score give or take a
+  // rank or two) -- no lists, no second pass.  Falls back to the two-level scheme when the
+  // minima of one query do not fit k_row_kth's registers.
+  const long srows = (long)nbt_s * 256;
+  int gsize = 16;
+  while (gsize < 128 && (srows / gsize > RK_T * RK_PER || (size_t)nq * (srows / gsize) * 4 > ((size_t)256 << 20)))
+    gsize *= 2;
+  const long gcols = srows / gsize;
+  const bool gmin_ok = sample_ok && gcols <= RK_T * RK_PER && (long)j2 * 4 <= gcols &&
+                       (size_t)nq * gcols * 4 <= ((size_t)512 << 20) && !getenv("YAEL_B200_TWO_LEVEL");
   size_t need = Carver::need(sizeof(float) * (size_t)padded) + Carver::need(64) +
                 Carver::need(sizeof(float) * (size_t)nq * stride) +
                 Carver::need(sizeof(int) * (size_t)nq * stride) +
                 Carver::need(sizeof(float) * (size_t)nq * plan.lists) +
                 Carver::need(sizeof(int) * (size_t)nq * kp) +
                 2 * Carver::need(sizeof(int) * (size_t)nq) + kmin_ws_bytes(nq, kp) +
+                Carver::need(sizeof(int) * (size_t)nq * plan.lists) +
                 Carver::need(plan.ws_bytes) + 1024 +
                 Carver::need(sizeof(float) * (size_t)nb * dpad) +
                 Carver::need(sizeof(float) * (size_t)nq * dpad) + center_ws_bytes(nb, d);
   if (sample_ok)
     need += Carver::need(sizeof(float) * (size_t)nq * sstride) +
             Carver::need(sizeof(int) * (size_t)nq * sstride) +
-            Carver::need(sizeof(float) * (size_t)nq * splan.lists) +
+            2 * Carver::need(sizeof(float) * (size_t)nq * splan.lists) +
             2 * Carver::need(sizeof(int) * (size_t)nq * j2) + 2 * Carver::need(sizeof(float) * (size_t)nq) +
             kmin_ws_bytes(nq, j2) + Carver::need(splan.ws_bytes);
+  if (gmin_ok) need += Carver::need(sizeof(float) * (size_t)nq * gcols);
   if (level1_ok)
     need += Carver::need(sizeof(float) * (size_t)nq * rows1) +
             2 * Carver::need(sizeof(int) * (size_t)nq * j1) + kmin_ws_bytes(nq, j1) +
@@ -738,6 +1039,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
     int *cid = c.take<int>((size_t)nq * stride);
     float *cthr = c.take<float>((size_t)nq * plan.lists);
     int *sel = c.take<int>((size_t)nq * kp);
+    int *ccnt = c.take<int>((size_t)nq * plan.lists);
     int *flags = c.take<int>(nq);
     int *flag_list = c.take<int>(nq);
     void *kws = c.take<char>(kmin_ws_bytes(nq, kp));
@@ -760,6 +1062,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
       float *sscore = c.take<float>((size_t)nq * sstride);
       int *sid = c.take<int>((size_t)nq * sstride);
       float *sthr = c.take<float>((size_t)nq * splan.lists);
+      int *scnt = c.take<int>((size_t)nq * splan.lists);
       int *ssel = c.take<int>((size_t)nq * j2);
       float *svals = (float *)c.take<int>((size_t)nq * j2);
       thr_init = c.take<float>(nq);
@@ -767,7 +1070,16 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
       void *skws = c.take<char>(kmin_ws_bytes(nq, j2));
       void *stfws = c.take<char>(splan.ws_bytes);
       const float *thr_l1 = nullptr;
+      if (gmin_ok) {
+        float *gm = c.take<float>((size_t)nq * gcols);
+        if ((rc = tf32_group_min(splan, nq, nb, dpad, nbt_s, kSampleStride, base_c, query_c, an, gm,
+                                 gcols, gsize, stfws, st)))
+          return rc;
+        k_row_kth<<<nq, RK_T, 0, st>>>(gm, gcols, (int)gcols, j2, thr_init);
+        YB_LAUNCH_CHECK();
+      } else {
       if (level1_ok) {
+        ProfScope ps1(11, st);
         float *slab = c.take<float>((size_t)nq * rows1);
         int *sel1 = c.take<int>((size_t)nq * j1);
         float *vals1 = (float *)c.take<int>((size_t)nq * j1);
@@ -780,25 +1092,42 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
         YB_LAUNCH_CHECK();
         thr_l1 = thr1;
       }
-      if ((rc = fill_f32(sscore, (long)nq * sstride, __builtin_inff(), st))) return rc;
-      YB_CUDA(cudaMemsetAsync(sid, 0xff, sizeof(int) * (size_t)nq * sstride, st));
-      if ((rc = tf32_shortlist(splan, nq, nb, dpad, nbt_s, kSampleStride, base_c, query_c, an, thr_l1,
-                               sscore, sid, sthr, stfws, st)))
-        return rc;
-      if ((rc = kmin_rows(sscore, sstride, sstride, nq, j2, +1, ssel, svals, 0, 0, skws, st)))
-        return rc;
-      k_threshold_from_kmin<<<(nq + 255) / 256, 256, 0, st>>>(ssel, svals, nq, j2, thr_init);
-      YB_LAUNCH_CHECK();
+      if (fast_merge) {
+        Tf32Out so = {scnt, 0, 0, 0};
+        if ((rc = tf32_shortlist(splan, nq, nb, dpad, nbt_s, kSampleStride, base_c, query_c, an, thr_l1,
+                                 sscore, sid, sthr, stfws, st, &so)))
+          return rc;
+        k_merge_lists<<<nq, ML_T, 0, st>>>(scnt, sscore, splan.lists, j2, j2, nullptr, thr_init);
+        YB_LAUNCH_CHECK();
+      } else {
+        if ((rc = fill_f32(sscore, (long)nq * sstride, __builtin_inff(), st))) return rc;
+        YB_CUDA(cudaMemsetAsync(sid, 0xff, sizeof(int) * (size_t)nq * sstride, st));
+        if ((rc = tf32_shortlist(splan, nq, nb, dpad, nbt_s, kSampleStride, base_c, query_c, an, thr_l1,
+                                 sscore, sid, sthr, stfws, st)))
+          return rc;
+        if ((rc = kmin_rows(sscore, sstride, sstride, nq, j2, +1, ssel, svals, 0, 0, skws, st)))
+          return rc;
+        k_threshold_from_kmin<<<(nq + 255) / 256, 256, 0, st>>>(ssel, svals, nq, j2, thr_init);
+        YB_LAUNCH_CHECK();
+      }
+      }  // two-level scheme
     }
-    if ((rc = fill_f32(cscore, (long)nq * stride, __builtin_inff(), st))) return rc;
-    YB_CUDA(cudaMemsetAsync(cid, 0xff, sizeof(int) * (size_t)nq * stride, st));
+    if (!fast_merge) {
+      if ((rc = fill_f32(cscore, (long)nq * stride, __builtin_inff(), st))) return rc;
+      YB_CUDA(cudaMemsetAsync(cid, 0xff, sizeof(int) * (size_t)nq * stride, st));
+    }
     {
       ProfScope ps(1, st);
+      Tf32Out mo = {ccnt, 0, 0, 0};
       if ((rc = tf32_shortlist(plan, nq, nb, dpad, nbt, 1, base_c, query_c, an, thr_init, cscore, cid,
-                               cthr, tfws, st)))
+                               cthr, tfws, st, fast_merge ? &mo : nullptr)))
         return rc;
     }
-    if (need_sel) {
+    if (fast_merge) {
+      ProfScope ps(2, st);
+      k_merge_lists<<<nq, ML_T, 0, st>>>(ccnt, cscore, plan.lists, kp, kp, sel, nullptr);
+      YB_LAUNCH_CHECK();
+    } else if (need_sel) {
       // merge the per-list shortlists: the kp smallest TF32 scores of the union
       ProfScope ps(2, st);
       if ((rc = kmin_rows(cscore, stride, stride, nq, kp, +1, sel, nullptr, 0, 0, kws, st)))

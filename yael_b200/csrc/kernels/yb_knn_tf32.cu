@@ -221,6 +221,14 @@ struct Tf32Params {
   float *out_thr;      // [nq][lists] final admission threshold of every list: each row of the
                        // list's range that is NOT in the list has a score >= this value
   int tile_stride;     // logical tile j covers database tile j * tile_stride (sampling pass)
+  float *gmin;         // [nq][gmin_ld] group-minimum mode (lists are not produced): the smallest
+                       // score of every run of gsize (16, 32, 64 or 128) LOGICAL columns
+  long gmin_ld;
+  int gsize;
+  int *out_cnt;        // [nq][lists_ld] entries published per list (NULL: not wanted)
+  int lists_ld;        // lists per query in the OUTPUT arrays (several passes may share them)
+  int list0;           // first output list of this pass
+  int id0;             // added to every published row id (pass over a row range of the database)
   const float *k1_margin;  // [nq] k = 1 mode (NULL = top-k' mode): admit s < best_so_far + margin
   int pair;            // 1: CTAs run as clusters of 2 that share every database chunk: each CTA
                        // fetches half of it and multicasts it to both (L2->SM traffic halves)
@@ -407,6 +415,24 @@ __device__ __forceinline__ void process_group(const uint32_t (&v)[16], const flo
   }
 }
 
+// smallest score of 16 accumulator columns (sampling pass)
+__device__ __forceinline__ float group_min16(const uint32_t (&v)[16], const float *bn) {
+  float sc[16];
+#pragma unroll
+  for (int c4 = 0; c4 < 4; c4++) {
+    const float4 b4 = *reinterpret_cast<const float4 *>(bn + c4 * 4);
+    sc[c4 * 4 + 0] = fmaf(__uint_as_float(v[c4 * 4 + 0]), -2.0f, b4.x);
+    sc[c4 * 4 + 1] = fmaf(__uint_as_float(v[c4 * 4 + 1]), -2.0f, b4.y);
+    sc[c4 * 4 + 2] = fmaf(__uint_as_float(v[c4 * 4 + 2]), -2.0f, b4.z);
+    sc[c4 * 4 + 3] = fmaf(__uint_as_float(v[c4 * 4 + 3]), -2.0f, b4.w);
+  }
+  float m01 = fminf(fminf(sc[0], sc[1]), fminf(sc[2], sc[3]));
+  float m23 = fminf(fminf(sc[4], sc[5]), fminf(sc[6], sc[7]));
+  float m45 = fminf(fminf(sc[8], sc[9]), fminf(sc[10], sc[11]));
+  float m67 = fminf(fminf(sc[12], sc[13]), fminf(sc[14], sc[15]));
+  return fminf(fminf(m01, m23), fminf(m45, m67));
+}
+
 // ------------------------------------------------------------------ epilogue role
 struct EpiCtx {
   unsigned char *smem;
@@ -457,7 +483,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
         mbar_wait(bar(E.t_full0 + buf), (tcount >> 1) & 1);
         tc_fence_after();
         const float *bn = (const float *)(smem + Smem::bn_off + slot * TN * 4) + half * HALF_N;
-        const int n0 = jt * P.tile_stride * TN + half * HALF_N;
+        const int n0 = jt * P.tile_stride * TN + half * HALF_N + P.id0;
         if (P.dump) {
 #pragma unroll 1
           for (int g = 0; g < HALF_N / 32; g++) {
@@ -483,6 +509,32 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
                   if (col0 + c < P.dump_ld)
                     drow[c] = fmaf(__uint_as_float(v[c]), -2.0f, bn[g * 32 + c]);
               }
+            }
+          }
+        } else if (P.gmin) {
+          // sampling pass: only the minimum of every column group leaves the SM
+          uint32_t va[16], vb[16];
+          const uint32_t ta = lane_addr + buf * TN;
+          const int per_half = HALF_N / P.gsize;  // values this thread emits for the tile
+          float *grow = P.gmin + (size_t)(valid ? q : 0) * P.gmin_ld + ((long)jt * 2 + half) * per_half;
+          const int fold = P.gsize >> 4;          // 16-column groups per emitted value
+          float gm = inf;
+          tc_ld16(ta, va);
+#pragma unroll 1
+          for (int gg = 0; gg < 4; gg++) {
+            tc_wait_ld();
+            tc_ld16(ta + gg * 32 + 16, vb);
+            gm = fminf(gm, group_min16(va, bn + gg * 32));
+            if (((2 * gg + 1) % fold) == 0) {
+              if (valid) grow[(2 * gg + 1) / fold - 1] = gm;
+              gm = inf;
+            }
+            tc_wait_ld();
+            if (gg < 3) tc_ld16(ta + gg * 32 + 32, va);
+            gm = fminf(gm, group_min16(vb, bn + gg * 32 + 16));
+            if (((2 * gg + 2) % fold) == 0) {
+              if (valid) grow[(2 * gg + 2) / fold - 1] = gm;
+              gm = inf;
             }
           }
         } else if (!(P.debug & 1)) {
@@ -547,10 +599,10 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           }
         }
       }
-      if (!P.dump && k1) {
+      if (!P.dump && !P.gmin && k1) {
         // k = 1: publish the candidates within the margin of the final best score
         if (valid) {
-          const size_t l = (size_t)q * P.lists + sp * 2 + half;
+          const size_t l = (size_t)q * P.lists_ld + P.list0 + sp * 2 + half;
           const size_t o = l * P.kprime;
           int nout = 0;
           bool over = best != best;  // NaN: the list overflowed
@@ -572,8 +624,9 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           }
           // out_thr: every unlisted row of this list's range scores >= thr; NaN = overflow
           P.out_thr[l] = over ? __uint_as_float(0x7fc00000u) : thr;
+          if (P.out_cnt) P.out_cnt[l] = nout;
         }
-      } else if (!P.dump) {
+      } else if (!P.dump && !P.gmin) {
         // final compaction of over-full lists, then publish the shortlist of this item
         unsigned need = __ballot_sync(0xffffffffu, cnt > P.kprime);
         while (need) {
@@ -589,7 +642,11 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           }
         }
         __syncwarp();
-        if (valid) P.out_thr[(size_t)q * P.lists + sp * 2 + half] = thr;
+        if (valid) {
+          const size_t l = (size_t)q * P.lists_ld + P.list0 + sp * 2 + half;
+          P.out_thr[l] = thr;
+          if (P.out_cnt) P.out_cnt[l] = cnt;
+        }
         // publish: the warp copies its 32 lists one after the other with coalesced accesses.
         // Only the valid entries are written -- the caller pre-fills the output with
         // (+inf, -1), and with tight thresholds a list holds a few dozen entries, not k'.
@@ -598,7 +655,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           if (n == 0) continue;
           const float2 *l = (const float2 *)__shfl_sync(0xffffffffu, (unsigned long long)mylist, owner);
           const int qo = __shfl_sync(0xffffffffu, q, owner);
-          const size_t o = ((size_t)qo * P.lists + sp * 2 + half) * P.kprime;
+          const size_t o = ((size_t)qo * P.lists_ld + P.list0 + sp * 2 + half) * P.kprime;
           for (int e = lane; e < n; e += 32) {
             const float2 x = l[e];
             P.out_score[o + e] = x.x;
@@ -1061,7 +1118,7 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
                        int tile_stride, const float *base, const float *query,
                        const float *bnorm_padded, const float *thr_init, const float *k1_margin,
                        float *out_score, int *out_id, float *out_thr, float *dump, long dump_ld,
-                       void *ws, cudaStream_t st) {
+                       void *ws, cudaStream_t st, const Tf32Out *oo = nullptr) {
   if ((((uintptr_t)base) & 15) || (((uintptr_t)query) & 15))
     return fail(6, "tf32 path needs 16-byte aligned matrices");
   CUtensorMap mq, mb, mbh;
@@ -1091,6 +1148,13 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   P.thr_init = thr_init;
   P.k1_margin = k1_margin;
   P.tile_stride = tile_stride;
+  P.gmin = oo ? oo->gmin : nullptr;
+  P.gmin_ld = oo ? oo->gmin_ld : 0;
+  P.gsize = oo ? oo->gsize : 16;
+  P.out_cnt = oo ? oo->out_cnt : nullptr;
+  P.lists_ld = (oo && oo->lists_ld > 0) ? oo->lists_ld : plan.lists;
+  P.list0 = oo ? oo->list0 : 0;
+  P.id0 = oo ? oo->id0 : 0;
   {
     const char *e = getenv("YAEL_B200_TF32_DEBUG");
     P.debug = e ? atoi(e) : 0;
@@ -1154,9 +1218,9 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
 int tf32_shortlist(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical, int tile_stride,
                    const float *base, const float *query, const float *bnorm_padded,
                    const float *thr_init, float *out_score, int *out_id, float *out_thr, void *ws,
-                   cudaStream_t st) {
+                   cudaStream_t st, const Tf32Out *oo) {
   return launch_tf32(plan, nq, nb, d, nbt_logical, tile_stride, base, query, bnorm_padded,
-                     thr_init, nullptr, out_score, out_id, out_thr, nullptr, 0, ws, st);
+                     thr_init, nullptr, out_score, out_id, out_thr, nullptr, 0, ws, st, oo);
 }
 
 // k = 1 mode: per list the (at most plan.kprime) rows whose TF32 score is within k1_margin[q]
@@ -1184,6 +1248,19 @@ int tf32_scores(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical, in
                 long ld, void *ws, cudaStream_t st) {
   return launch_tf32(plan, nq, nb, d, nbt_logical, tile_stride, base, query, bnorm_padded, nullptr,
                      nullptr, nullptr, nullptr, nullptr, scores, ld, ws, st);
+}
+
+// group minima of the logical tiles: gmin[q][(2*j + h) * (128/gsize) + g] = the smallest score
+// among columns [g*gsize, (g+1)*gsize) of half h of logical tile j
+int tf32_group_min(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical, int tile_stride,
+                   const float *base, const float *query, const float *bnorm_padded, float *gmin,
+                   long ld, int gsize, void *ws, cudaStream_t st) {
+  Tf32Out oo = {};
+  oo.gmin = gmin;
+  oo.gmin_ld = ld;
+  oo.gsize = gsize;
+  return launch_tf32(plan, nq, nb, d, nbt_logical, tile_stride, base, query, bnorm_padded, nullptr,
+                     nullptr, nullptr, nullptr, nullptr, nullptr, 0, ws, st, &oo);
 }
 
 long tf32_padded_rows(int nb) { return (long)((nb + TN - 1) / TN) * TN; }
