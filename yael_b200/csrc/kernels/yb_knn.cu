@@ -383,6 +383,108 @@ __global__ void k_threshold_from_kmin(const int *__restrict__ idx, const float *
                                               : __uint_as_float(0x7f800000u);
 }
 
+// ------------------------------------------------------------------ block radix select
+// The key of 0-based rank `rank` among the keys the CTA's threads hold in registers (kreg;
+// `absent` marks unused slots; rank < number of present keys).  MSB radix select with 8-bit
+// digits that STARTS AT THE HIGHEST BIT IN WHICH THE KEYS DIFFER: scores of one query share
+// sign, exponent and often the top mantissa bits, and a first pass over those bits would push
+// every key through one or two shared-memory atomics addresses.  For 64-bit keys (score key
+// << 32 | position) the all-zero bits between the position field (low_bits wide) and bit 32
+// are skipped the same way.
+struct SelectSmem {
+  int hist[256];
+  unsigned long long red[2 * 8];
+  unsigned long long prefix;
+  int rank;
+};
+
+template <int T, int PER, typename K>
+__device__ __forceinline__ K block_select_rank(const K (&kreg)[PER], K absent, int rank, int low_bits,
+                                               SelectSmem &sm) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr bool WIDE = sizeof(K) == 8;
+  K mn = absent, mx = 0;
+  bool any = false;
+#pragma unroll
+  for (int j = 0; j < PER; j++)
+    if (kreg[j] != absent) {
+      mn = any ? (kreg[j] < mn ? kreg[j] : mn) : kreg[j];
+      mx = kreg[j] > mx ? kreg[j] : mx;
+      any = true;
+    }
+  unsigned long long a = any ? (unsigned long long)mn : ~0ull, b = any ? (unsigned long long)mx : 0ull;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    unsigned long long a2 = __shfl_xor_sync(0xffffffffu, a, o), b2 = __shfl_xor_sync(0xffffffffu, b, o);
+    a = a2 < a ? a2 : a;
+    b = b2 > b ? b2 : b;
+  }
+  __syncthreads();
+  if (lane == 0) {
+    sm.red[warp] = a;
+    sm.red[8 + warp] = b;
+  }
+  __syncthreads();
+  a = ~0ull;
+  b = 0;
+#pragma unroll
+  for (int w = 0; w < T / 32; w++) {
+    a = sm.red[w] < a ? sm.red[w] : a;
+    b = sm.red[8 + w] > b ? sm.red[8 + w] : b;
+  }
+  const unsigned long long diff = a ^ b;
+  if (diff == 0) return (K)a;
+  const int top = 63 - __clzll((long long)diff);
+  K decided = top >= (int)(8 * sizeof(K)) - 1 ? (K)0 : (K)(~(K)0 << (top + 1));
+  K prefix = (K)b & decided;
+  int floor_bit = (WIDE && top >= 32) ? 32 : 0;
+  int shift = max(top - 7, floor_bit);
+  if (WIDE && top < 32) shift = max(0, min(top + 1, low_bits) - 8);
+  while (true) {
+    for (int h = tid; h < 256; h += T) sm.hist[h] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PER; j++)
+      if (kreg[j] != absent && (kreg[j] & decided) == prefix)
+        atomicAdd(&sm.hist[(int)(kreg[j] >> shift) & 255], 1);
+    __syncthreads();
+    if (warp == 0) {
+      int h[8], ssum = 0;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        h[c] = sm.hist[lane * 8 + c];
+        ssum += h[c];
+      }
+      int inc = ssum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      int below = inc - ssum;
+      if (below <= rank && rank < inc) {
+        int c = 0;
+        while (below + h[c] <= rank) below += h[c++];
+        sm.prefix = (unsigned long long)(lane * 8 + c);
+        sm.rank = rank - below;
+      }
+    }
+    __syncthreads();
+    const K dmask = (K)0xff << shift;
+    prefix = (prefix & ~dmask) | ((K)sm.prefix << shift);
+    decided |= dmask;
+    rank = sm.rank;
+    if (shift == floor_bit) {
+      if (floor_bit == 0) break;
+      floor_bit = 0;  // continue in the position field
+      shift = max(0, low_bits - 8);
+    } else {
+      shift = max(shift - 8, floor_bit);
+    }
+  }
+  return prefix;
+}
+
 // ------------------------------------------------------------------ shortlist merge
 // One CTA per query: the union of the query's shortlists (cnt[q][l] entries each, a few dozen
 // with sampled thresholds) -> positions of its kp smallest TF32 scores (ties by position),
@@ -427,10 +529,8 @@ k_merge_lists(const int *__restrict__ cnt, const float *__restrict__ score, int 
               int kp, int *__restrict__ sel, float *__restrict__ thr_out) {
   __shared__ unsigned long long buf[ML_CAP];
   __shared__ int loff[ML_LISTS];
-  __shared__ int hist[256];
+  __shared__ SelectSmem ssm;
   __shared__ int wtot[ML_T / 32];
-  __shared__ unsigned long long prefix_sh;
-  __shared__ int rank_sh;
   const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int *c = cnt + (size_t)q * lists;
   const float *sc = score + (size_t)q * lists * kprime;
@@ -486,45 +586,9 @@ k_merge_lists(const int *__restrict__ cnt, const float *__restrict__ score, int 
   }
   unsigned long long kstar = ~0ull - 1;  // n <= kp: everything is selected
   if (n > kp) {
-    unsigned long long prefix = 0;
-    int rank = kp - 1;
-    const bool wide_pos = (long)lists * kprime > 65536;
-    for (int shift = 56; shift >= 0; shift -= 8) {
-      if (!wide_pos && (shift == 24 || shift == 16)) continue;  // those position bits are all 0
-      const unsigned long long hi_mask = shift == 56 ? 0ull : (~0ull << (shift + 8));
-      for (int b = tid; b < 256; b += ML_T) hist[b] = 0;
-      __syncthreads();
-#pragma unroll
-      for (int j = 0; j < ML_PER; j++)
-        if (kreg[j] != ~0ull && (kreg[j] & hi_mask) == prefix)
-          atomicAdd(&hist[(int)(kreg[j] >> shift) & 255], 1);
-      __syncthreads();
-      if (warp == 0) {
-        int h[8], ssum = 0;
-#pragma unroll
-        for (int b = 0; b < 8; b++) {
-          h[b] = hist[lane * 8 + b];
-          ssum += h[b];
-        }
-        int inc = ssum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          int t = __shfl_up_sync(0xffffffffu, inc, o);
-          if (lane >= o) inc += t;
-        }
-        int below = inc - ssum;
-        if (below <= rank && rank < inc) {
-          int b = 0;
-          while (below + h[b] <= rank) below += h[b++];
-          prefix_sh = prefix | ((unsigned long long)(lane * 8 + b) << shift);
-          rank_sh = rank - below;
-        }
-      }
-      __syncthreads();
-      prefix = prefix_sh;
-      rank = rank_sh;
-    }
-    kstar = prefix;
+    int low_bits = 1;
+    while (low_bits < 32 && ((long)1 << low_bits) < (long)lists * kprime) low_bits++;
+    kstar = block_select_rank<ML_T, ML_PER, unsigned long long>(kreg, ~0ull, kp - 1, low_bits, ssm);
   }
 
   // ---- emit
@@ -562,10 +626,8 @@ constexpr int RK_PER = 16;
 
 __global__ void __launch_bounds__(RK_T)
 k_row_kth(const float *__restrict__ vals, long ld, int n, int j, float *__restrict__ thr) {
-  __shared__ int hist[256];
-  __shared__ uint32_t prefix_sh;
-  __shared__ int rank_sh;
-  const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  __shared__ SelectSmem ssm;
+  const int q = blockIdx.x, tid = threadIdx.x;
   const float *row = vals + (size_t)q * ld;
   uint32_t kreg[RK_PER];
 #pragma unroll
@@ -577,41 +639,7 @@ k_row_kth(const float *__restrict__ vals, long ld, int n, int j, float *__restri
     if (tid == 0) thr[q] = __uint_as_float(0x7f800000u);
     return;
   }
-  uint32_t prefix = 0;
-  int rank = j - 1;
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    const uint32_t hi_mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
-    hist[tid] = 0;
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < RK_PER; i++)
-      if ((kreg[i] & hi_mask) == prefix) atomicAdd(&hist[(kreg[i] >> shift) & 255], 1);
-    __syncthreads();
-    if (warp == 0) {
-      int h[8], ssum = 0;
-#pragma unroll
-      for (int b = 0; b < 8; b++) {
-        h[b] = hist[lane * 8 + b];
-        ssum += h[b];
-      }
-      int inc = ssum;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      int below = inc - ssum;
-      if (below <= rank && rank < inc) {
-        int b = 0;
-        while (below + h[b] <= rank) below += h[b++];
-        prefix_sh = prefix | ((uint32_t)(lane * 8 + b) << shift);
-        rank_sh = rank - below;
-      }
-    }
-    __syncthreads();
-    prefix = prefix_sh;
-    rank = rank_sh;
-  }
+  const uint32_t prefix = block_select_rank<RK_T, RK_PER, uint32_t>(kreg, 0xffffffffu, j - 1, 0, ssm);
   if (tid == 0) thr[q] = __uint_as_float((prefix & 0x80000000u) ? (prefix & 0x7fffffffu) : ~prefix);
 }
 

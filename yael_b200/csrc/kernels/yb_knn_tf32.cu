@@ -154,6 +154,44 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same two, for a warp that walks the issue loop with ALL lanes (warp-uniform control flow,
+// operands identical in every lane) and lets elect.sync pick the issuing lane inside the
+// instruction's own predicate.  Under `if (lane == 0)` ptxas cannot tell that one lane is
+// active and wraps every tcgen05 instruction in a vote/broadcast loop (ELECT, 5 x
+// R2UR.BROADCAST, BRA.U.ANY): 170 instructions per 4 MMAs, which made the ISSUE warp the
+// kernel's critical path whenever the epilogue warps of its scheduler were busy.  elect.sync
+// returns the same leader for the same mask every time, so one thread owns all MMAs and commits.
+__device__ __forceinline__ void tc_mma_tf32_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc_elect(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+      "}" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
 // 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -767,8 +805,11 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     }
   } else if (warp == EPI_WARPS + 1) {
     // ======================================================================== MMA issuer
-    if (lane == 0) {
+    // every lane walks the loop; elect.sync inside the tcgen05 wrappers picks the issuing lane
+    {
       uint32_t icount = 0, ccount = 0, tcount = 0;
+      const bool skip_mma = (P.debug & 2) != 0;
+      const bool ring_aligned = P.nkc == STAGES && P.last_k8 == 4;
       for (int item = first_item; item < P.items; item += item_step, icount++) {
         const int sp = item / tq_div;
         const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
@@ -778,29 +819,55 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
           mbar_wait(bar(Smem::t_empty + buf), ((tcount >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * TN;
+          if (ring_aligned && !skip_mma) {
+            // d = 128 (K chunks == ring depth): chunk kc always sits in stage kc, so every
+            // descriptor below is loop invariant and the body is wait, 4 MMAs, commit
+#pragma unroll
+            for (int kc = 0; kc < STAGES; kc++) {
+              mbar_wait(bar(Smem::b_full + kc), tcount & 1);
+              tc_fence_after();
+              const uint64_t adesc = smem_desc_sw128(sbase + Smem::a_off + kc * A_CHUNK_BYTES);
+              const uint64_t bdesc = smem_desc_sw128(sbase + Smem::b_off + kc * B_CHUNK_BYTES);
+              tc_mma_tf32_elect(d_tmem, adesc, bdesc, IDESC_TF32, kc != 0);
+              tc_mma_tf32_elect(d_tmem, adesc + 2, bdesc + 2, IDESC_TF32, 1);
+              tc_mma_tf32_elect(d_tmem, adesc + 4, bdesc + 4, IDESC_TF32, 1);
+              tc_mma_tf32_elect(d_tmem, adesc + 6, bdesc + 6, IDESC_TF32, 1);
+              if (P.pair)
+                tc_commit_mc_elect(bar(Smem::b_empty + kc), (uint16_t)3);
+              else
+                tc_commit_elect(bar(Smem::b_empty + kc));
+            }
+            ccount += STAGES;
+          } else
           for (int kc = 0; kc < P.nkc; kc++, ccount++) {
             const uint32_t st = ccount % STAGES;
             mbar_wait(bar(Smem::b_full + st), (ccount / STAGES) & 1);
             tc_fence_after();
-            const int nk8 = (kc == P.nkc - 1) ? P.last_k8 : 4;
             const uint64_t adesc = smem_desc_sw128(sbase + Smem::a_off + kc * A_CHUNK_BYTES);
             const uint64_t bdesc = smem_desc_sw128(sbase + Smem::b_off + st * B_CHUNK_BYTES);
-            for (int k8 = 0; k8 < nk8; k8++) {
-              if (P.debug & 2) break;
-              // advancing K inside the 128-byte swizzle span: +32 bytes = +2 in 16-byte units
-              tc_mma_tf32(d_tmem, adesc + (uint64_t)(2 * k8), bdesc + (uint64_t)(2 * k8),
-                          IDESC_TF32, (kc | k8) != 0);
+            // advancing K inside the 128-byte swizzle span: +32 bytes = +2 in 16-byte units
+            if (!skip_mma) {
+              if (kc != P.nkc - 1 || P.last_k8 == 4) {
+                tc_mma_tf32_elect(d_tmem, adesc, bdesc, IDESC_TF32, kc != 0);
+                tc_mma_tf32_elect(d_tmem, adesc + 2, bdesc + 2, IDESC_TF32, 1);
+                tc_mma_tf32_elect(d_tmem, adesc + 4, bdesc + 4, IDESC_TF32, 1);
+                tc_mma_tf32_elect(d_tmem, adesc + 6, bdesc + 6, IDESC_TF32, 1);
+              } else {
+                for (int k8 = 0; k8 < P.last_k8; k8++)
+                  tc_mma_tf32_elect(d_tmem, adesc + (uint64_t)(2 * k8), bdesc + (uint64_t)(2 * k8),
+                                    IDESC_TF32, (kc | k8) != 0);
+              }
             }
             // smem slot reusable once these MMAs retire (paired: tell both CTAs, either may
             // multicast into the slot next)
             if (P.pair)
-              tc_commit_mc(bar(Smem::b_empty + st), (uint16_t)3);
+              tc_commit_mc_elect(bar(Smem::b_empty + st), (uint16_t)3);
             else
-              tc_commit(bar(Smem::b_empty + st));
+              tc_commit_elect(bar(Smem::b_empty + st));
           }
-          tc_commit(bar(Smem::t_full + buf));  // accumulator complete
+          tc_commit_elect(bar(Smem::t_full + buf));  // accumulator complete
         }
-        tc_commit(bar(Smem::a_empty));  // query tile no longer needed
+        tc_commit_elect(bar(Smem::a_empty));  // query tile no longer needed
       }
     }
   } else {
