@@ -489,6 +489,12 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
                : "memory");
 }
 
+// MODE selects what the epilogue does with a tile (one kernel instantiation per mode: the hot
+// loop of each stays compact and contiguous in the instruction cache, and carries no per-tile
+// mode branches)
+enum : int { EPI_LISTS = 0, EPI_NEAREST = 1, EPI_DUMP = 2, EPI_GMIN = 3 };
+
+template <int MODE>
 __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &E) {
   unsigned char *smem = E.smem;
   const uint32_t sbase = E.sbase, tmem_base = E.tmem_base;
@@ -512,7 +518,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
       const bool valid = q < P.nq;
       float thr = valid ? (P.thr_init ? P.thr_init[q] : inf) : -inf;
       float best = inf;
-      const bool k1 = P.k1_margin != nullptr;
+      constexpr bool k1 = MODE == EPI_NEAREST;
       const float margin = (k1 && valid) ? P.k1_margin[q] : 0.f;
       int cnt = 0;
       for (int jt = jt0; jt < jt1; jt++, tcount++) {
@@ -522,7 +528,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
         tc_fence_after();
         const float *bn = (const float *)(smem + Smem::bn_off + slot * TN * 4) + half * HALF_N;
         const int n0 = jt * P.tile_stride * TN + half * HALF_N + P.id0;
-        if (P.dump) {
+        if (MODE == EPI_DUMP) {
 #pragma unroll 1
           for (int g = 0; g < HALF_N / 32; g++) {
             uint32_t v[32];
@@ -549,7 +555,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
               }
             }
           }
-        } else if (P.gmin) {
+        } else if (MODE == EPI_GMIN) {
           // sampling pass: only the minimum of every column group leaves the SM
           uint32_t va[16], vb[16];
           const uint32_t ta = lane_addr + buf * TN;
@@ -637,7 +643,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           }
         }
       }
-      if (!P.dump && !P.gmin && k1) {
+      if (MODE == EPI_NEAREST) {
         // k = 1: publish the candidates within the margin of the final best score
         if (valid) {
           const size_t l = (size_t)q * P.lists_ld + P.list0 + sp * 2 + half;
@@ -664,7 +670,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           P.out_thr[l] = over ? __uint_as_float(0x7fc00000u) : thr;
           if (P.out_cnt) P.out_cnt[l] = nout;
         }
-      } else if (!P.dump && !P.gmin) {
+      } else if (MODE == EPI_LISTS) {
         // final compaction of over-full lists, then publish the shortlist of this item
         unsigned need = __ballot_sync(0xffffffffu, cnt > P.kprime);
         while (need) {
@@ -706,6 +712,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
 }
 
 // ------------------------------------------------------------------ the kernel
+template <int MODE>
 __global__ void __launch_bounds__(TF32_THREADS, 1)
 k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_b,
            const __grid_constant__ CUtensorMap map_bh, const Tf32Params P) {
@@ -871,7 +878,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       }
     }
   } else {
-    run_epilogue(P, ectx);
+    run_epilogue<MODE>(P, ectx);
   }
 
   tc_fence_before();
@@ -946,6 +953,7 @@ __device__ __forceinline__ void tc_mma_tf32_2sm(uint32_t d_tmem, uint64_t a_desc
 constexpr uint32_t IDESC_TF32_2SM = (1u << 4) | (2u << 7) | (2u << 10) |
                                     ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
+template <int MODE>
 __global__ void __launch_bounds__(TF32_THREADS, 1)
 k_knn_tf32_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_bh,
                const Tf32Params P) {
@@ -1064,7 +1072,7 @@ k_knn_tf32_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     ectx.t_empty_addr0 = a0; ectx.t_empty_addr1 = a1;
     ectx.t_empty_remote = 1;
     ectx.n_full0 = Smem2::n_full; ectx.n_empty0 = Smem2::n_empty; ectx.t_full0 = Smem2::t_full;
-    run_epilogue(P, ectx);
+    run_epilogue<MODE>(P, ectx);
   }
 
   tc_fence_before();
@@ -1181,6 +1189,47 @@ Tf32Plan tf32_plan(int nq, int nb, int d, int k) {
   return tf32_plan_tiles(nq, (nb + TN - 1) / TN, d, tf32_kprime_for(k));
 }
 
+template <int MODE>
+static int launch_mode(const Tf32Plan &plan, const CUtensorMap &mq, const CUtensorMap &mb,
+                       const CUtensorMap &mbh, const Tf32Params &P, cudaStream_t st) {
+  static bool attr = false, attr2 = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_knn_tf32<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TF32_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(6, "cannot reserve %d bytes of shared memory: %s",
+                                      TF32_SMEM_BYTES, cudaGetErrorString(e));
+    attr = true;
+  }
+  if (plan.pair) {
+    if (plan.pair == 2 && !attr2) {
+      cudaError_t e = cudaFuncSetAttribute(k_knn_tf32_2sm<MODE>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, TF32_SMEM2_BYTES);
+      if (e != cudaSuccess) return fail(6, "cannot reserve shared memory: %s", cudaGetErrorString(e));
+      attr2 = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(plan.ctas);
+    cfg.blockDim = dim3(TF32_THREADS);
+    cfg.dynamicSmemBytes = plan.pair == 2 ? TF32_SMEM2_BYTES : TF32_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = plan.pair == 2 ? cudaLaunchKernelEx(&cfg, k_knn_tf32_2sm<MODE>, mq, mbh, P)
+                                   : cudaLaunchKernelEx(&cfg, k_knn_tf32<MODE>, mq, mb, mbh, P);
+    if (e != cudaSuccess) return fail(2, "k_knn_tf32 cluster launch: %s", cudaGetErrorString(e));
+    count_launch();
+  } else {
+    k_knn_tf32<MODE><<<plan.ctas, TF32_THREADS, TF32_SMEM_BYTES, st>>>(mq, mb, mbh, P);
+    YB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical,
                        int tile_stride, const float *base, const float *query,
                        const float *bnorm_padded, const float *thr_init, const float *k1_margin,
@@ -1228,58 +1277,13 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   }
   P.dump = dump;
   P.dump_ld = dump_ld;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_knn_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TF32_SMEM_BYTES);
-    if (e != cudaSuccess) return fail(6, "cannot reserve %d bytes of shared memory: %s",
-                                      TF32_SMEM_BYTES, cudaGetErrorString(e));
-    attr = true;
+  const int mode = dump ? EPI_DUMP : (P.gmin ? EPI_GMIN : (k1_margin ? EPI_NEAREST : EPI_LISTS));
+  switch (mode) {
+    case EPI_DUMP: return launch_mode<EPI_DUMP>(plan, mq, mb, mbh, P, st);
+    case EPI_GMIN: return launch_mode<EPI_GMIN>(plan, mq, mb, mbh, P, st);
+    case EPI_NEAREST: return launch_mode<EPI_NEAREST>(plan, mq, mb, mbh, P, st);
+    default: return launch_mode<EPI_LISTS>(plan, mq, mb, mbh, P, st);
   }
-  if (plan.pair == 2) {
-    static bool attr2 = false;
-    if (!attr2) {
-      cudaError_t e = cudaFuncSetAttribute(k_knn_tf32_2sm, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           TF32_SMEM2_BYTES);
-      if (e != cudaSuccess) return fail(6, "cannot reserve shared memory: %s", cudaGetErrorString(e));
-      attr2 = true;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(plan.ctas);
-    cfg.blockDim = dim3(TF32_THREADS);
-    cfg.dynamicSmemBytes = TF32_SMEM2_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_knn_tf32_2sm, mq, mbh, P);
-    if (e != cudaSuccess) return fail(2, "k_knn_tf32_2sm cluster launch: %s", cudaGetErrorString(e));
-    count_launch();
-  } else if (plan.pair) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(plan.ctas);
-    cfg.blockDim = dim3(TF32_THREADS);
-    cfg.dynamicSmemBytes = TF32_SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_knn_tf32, mq, mb, mbh, P);
-    if (e != cudaSuccess) return fail(2, "k_knn_tf32 cluster launch: %s", cudaGetErrorString(e));
-    count_launch();
-  } else {
-    k_knn_tf32<<<plan.ctas, TF32_THREADS, TF32_SMEM_BYTES, st>>>(mq, mb, mbh, P);
-    YB_LAUNCH_CHECK();
-  }
-  return 0;
 }
 
 int tf32_shortlist(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical, int tile_stride,
