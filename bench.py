@@ -54,17 +54,52 @@ def gen_data(rank):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md).  NVML is polled
+    in-process every 2 ms (a timed region of a few tens of milliseconds sees dozens of samples;
+    an `nvidia-smi -lms 100` child, the fallback, may see none).  Samples are time-stamped and
+    only those taken between mark_begin() and mark_end() are reported."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+               ("sw_power_cap", 0x4))
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, uuid=None):
         self.gpu = gpu_index
+        self.uuid = uuid
+        self.samples = []   # (t, sm_mhz, sm_max_mhz, reason_bits)
         self.lines = []
         self.proc = None
+        self.nvml = None
+        self.stop_flag = False
+        self.t0 = self.t1 = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = self.gpu
+                if vis:
+                    try:
+                        idx = int(vis.split(",")[self.gpu])
+                    except Exception:
+                        idx = self.gpu
+                h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml, self.h = pynvml, h
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
@@ -75,11 +110,41 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                try:
+                    bits = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    bits = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((time.perf_counter(), sm, self.mx, bits))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.th.join(timeout=1)
+            sel = [x for x in self.samples
+                   if (self.t0 is None or x[0] >= self.t0) and (self.t1 is None or x[0] <= self.t1)]
+            if not sel:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            reasons = sorted({name for name, bit in self.REASONS for x in sel if x[3] & bit})
+            return {"sm_mhz": float(np.median([x[1] for x in sel])), "sm_max_mhz": float(sel[0][2]),
+                    "reasons": reasons, "samples": len(sel), "source": "nvml, 2 ms polling"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -105,7 +170,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ----------------------------------------------------------------------------- CPU baseline
@@ -319,15 +384,21 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local, uuid)
     sampler.start()
     L.yb_launch_count(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
     e0.record(stream)
     for _ in range(args.steps):
         step()
     e1.record(stream)
     torch.cuda.synchronize()
+    sampler.mark_end()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()
@@ -447,7 +518,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true",

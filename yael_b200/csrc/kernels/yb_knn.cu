@@ -1009,6 +1009,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
   const int nbt_s = (nbt + kSampleStride - 1) / kSampleStride;
   int j2 = (3 * kp + kSampleStride - 1) / kSampleStride;
   if (j2 < 32) j2 = 32;
+  if (const char *e = getenv("YAEL_B200_J2")) j2 = atoi(e) > 0 ? atoi(e) : j2;  // experiment knob
   Tf32Plan splan = {};
   if (use_sample) splan = tf32_plan_tiles(nq, nbt_s, dpad, j2);
   const bool sample_ok = use_sample && splan.ok;

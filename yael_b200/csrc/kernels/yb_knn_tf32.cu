@@ -357,6 +357,21 @@ __device__ __forceinline__ float warp_select_compact(float2 *list, int n, int kp
   return __uint_as_float(bits);
 }
 
+// (d0, d1) = (a0, a1) * (-2, -2) + (c0, c1), one packed instruction
+__device__ __forceinline__ void ffma2_m2(float &d0, float &d1, uint32_t a0, uint32_t a1, float c0,
+                                         float c1) {
+  asm("{\n\t"
+      ".reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%6, %6};\n\t"
+      "mov.b64 rc, {%4, %5};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t"
+      "}"
+      : "=f"(d0), "=f"(d1)
+      : "r"(a0), "r"(a1), "f"(c0), "f"(c1), "f"(-2.0f));
+}
+
 // 16 accumulator columns of one query.  Fast path: scores and their minimum (one FFMA and one
 // FMNMX per candidate); only when the minimum beats the query's admission threshold -- rare once
 // the threshold is tight -- are the 16 candidates tested one by one and appended to the query's
@@ -429,10 +444,9 @@ __device__ __forceinline__ void process_group(const uint32_t (&v)[16], const flo
 #pragma unroll
   for (int c4 = 0; c4 < 4; c4++) {
     const float4 b4 = *reinterpret_cast<const float4 *>(bn + c4 * 4);
-    sc[c4 * 4 + 0] = fmaf(__uint_as_float(v[c4 * 4 + 0]), -2.0f, b4.x);
-    sc[c4 * 4 + 1] = fmaf(__uint_as_float(v[c4 * 4 + 1]), -2.0f, b4.y);
-    sc[c4 * 4 + 2] = fmaf(__uint_as_float(v[c4 * 4 + 2]), -2.0f, b4.z);
-    sc[c4 * 4 + 3] = fmaf(__uint_as_float(v[c4 * 4 + 3]), -2.0f, b4.w);
+    // two packed FMAs (fma.rn.f32x2: same rounding as the scalar fmaf, half the issue slots)
+    ffma2_m2(sc[c4 * 4 + 0], sc[c4 * 4 + 1], v[c4 * 4 + 0], v[c4 * 4 + 1], b4.x, b4.y);
+    ffma2_m2(sc[c4 * 4 + 2], sc[c4 * 4 + 3], v[c4 * 4 + 2], v[c4 * 4 + 3], b4.z, b4.w);
   }
   // fminf ignores NaN operands, which is what we want: a NaN score is never admitted
   float m01 = fminf(fminf(sc[0], sc[1]), fminf(sc[2], sc[3]));
