@@ -92,6 +92,14 @@ int yb_cross_distances_alt(int distance_type, int d, int na, int nb, const float
  * strict '<' from (-1, 1e30), lowest id on ties. */
 int yb_knn_l2(int nq, int nb, int d, int k, const float *base, const float *query,
               const float *b_weights, int *assign, float *dis, int id_offset, yb_stream_t s);
+/* yb_knn_l2 for a database that is still in HOST memory (what knn_full() receives,
+ * yael/nn.c:451): the host->device transfer is overlapped with the scan -- the sample tiles the
+ * admission thresholds are computed from travel first, the rest follows in large 2-D copies and
+ * every chunk is scanned as soon as it has landed.  base_dev: device scratch for nb*d floats
+ * (holds the database on return).  query/assign/dis are device pointers.  Same results as
+ * yb_knn_l2. */
+int yb_knn_l2_hostbase(int nq, int nb, int d, int k, const float *base_host, float *base_dev,
+                       const float *query, int *assign, float *dis, int id_offset, yb_stream_t s);
 /* merge G per-shard results laid out [G][nq][k] into [nq][k] by (distance, id); padded
  * entries (id < 0) sort last.  The exchange step of the sharded k-NN. */
 int yb_knn_merge(int nq, int k, int G, const int *assign_in, const float *dis_in,

@@ -125,3 +125,58 @@ def test_kmeans_assignment_tf32(yn, ob, tf32_engine):
     assert mism.mean() < 1e-3
     np.testing.assert_allclose(dis, wd, rtol=1e-5)
     np.testing.assert_allclose(cent, wc, atol=1e-4)
+
+
+# ---------------------------------------------------------------- database fed from host memory
+def _resident_knn(L, b, q, k):
+    db, dq = DevArray(b), DevArray(q)
+    oi = DevArray(shape=(q.shape[0], k), dtype=np.int32)
+    od = DevArray(shape=(q.shape[0], k), dtype=np.float32)
+    rc = L.yb_knn_l2(q.shape[0], b.shape[0], b.shape[1], k, db.ptr, dq.ptr, None, oi.ptr, od.ptr, 0, None)
+    assert rc == 0, L.yb_last_error()
+    L.yb_sync(None)
+    out = oi.get(), od.get()
+    for a in (db, dq, oi, od):
+        a.free()
+    return out
+
+
+@pytest.mark.parametrize("nb,d,k,chunks", [(200003, 128, 10, None), (262144 + 4096 + 300, 96, 100, 3),
+                                           (196608 + 100, 128, 7, 8), (400000, 64, 32, 2)])
+def test_knn_host_database_streamed_equals_resident(yn, tf32_engine, monkeypatch, nb, d, k, chunks):
+    """knn_full() on a host-resident database overlaps the transfer with the scan (sample tiles
+    first, chunked tensor passes, yb_knn_l2_hostbase); the result must be the resident path's,
+    bit for bit, ragged tails and any chunk count included."""
+    if chunks:
+        monkeypatch.setenv("YAEL_B200_H2D_CHUNKS", str(chunks))
+    r = rs(nb + d + k)
+    b = r.rand(nb, d).astype(np.float32)
+    q = r.rand(300, d).astype(np.float32)
+    idx, dis = yn.knn(q, b, k)          # host arrays -> streamed path
+    assert tf32_engine.yb_last_knn_engine() == 1
+    widx, wdis = _resident_knn(tf32_engine, b, q, k)
+    assert np.array_equal(dis, wdis)
+    assert np.array_equal(idx, widx)
+    monkeypatch.setenv("YAEL_B200_NO_STREAMED_H2D", "1")
+    idx2, dis2 = yn.knn(q, b, k)        # copy-then-scan
+    assert np.array_equal(dis2, wdis) and np.array_equal(idx2, widx)
+
+
+def test_knn_host_database_streamed_sorted_rows(yn, ob, tf32_engine):
+    """Rows sorted by cluster (position correlates with content): thresholds come from sample
+    tiles spread over the whole database, so nothing degrades; checked against the oracle."""
+    r = rs(99)
+    nb, d, k = 230000, 128, 20
+    centers = r.rand(64, d).astype(np.float32) * 4
+    lab = np.sort(r.randint(0, 64, nb))
+    b = (centers[lab] + r.randn(nb, d) * 0.05).astype(np.float32)
+    q = (centers[r.randint(0, 64, 200)] + r.randn(200, d) * 0.05).astype(np.float32)
+    idx, dis = yn.knn(q, b, k)
+    n_streamed = tf32_engine.yb_last_knn_uncertified()
+    widx, wdis = ob.orc_knn(b, q, k, canonical=True)
+    check_knn(idx, dis, widx, wdis)
+    ridx, rdis = _resident_knn(tf32_engine, b, q, k)
+    assert np.array_equal(dis, rdis) and np.array_equal(idx, ridx)
+    # tight clusters defeat the TF32 certificate for many queries in BOTH paths (they are then
+    # answered by the exact engine); feeding from the host must not make that worse
+    assert n_streamed <= tf32_engine.yb_last_knn_uncertified() + 5

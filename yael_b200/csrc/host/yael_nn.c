@@ -35,12 +35,24 @@ void knn_full(int distance_type, int nq, int nb, int d, int k, const float *b, c
               const float *b_weights, int *assign, float *dis) {
   assert(k <= nb); /* yael/nn.c:456 */
   if (nq <= 0 || k <= 0) return;
-  ybh_arg ab = ybh_in(b, sizeof(float) * (size_t)nb * d);
+  /* L2 on a host-resident database: the transfer is overlapped with the scan inside
+   * yb_knn_l2_hostbase (which falls back to copy-then-scan for shapes that do not qualify) */
+  const int l2 = (distance_type == 2 || distance_type == 12);
+  const int feed_host = l2 && !b_weights && !ybh_is_device_ptr(b);
+  ybh_arg ab;
+  if (feed_host) {
+    ab = ybh_out((void *)b, sizeof(float) * (size_t)nb * d); /* device scratch, no copy */
+  } else {
+    ab = ybh_in(b, sizeof(float) * (size_t)nb * d);
+  }
   ybh_arg aq = ybh_in(q, sizeof(float) * (size_t)nq * d);
   ybh_arg aw = ybh_in(b_weights, sizeof(float) * (size_t)nb);
   ybh_arg oa = ybh_out(assign, sizeof(int) * (size_t)nq * k);
   ybh_arg od = ybh_out(dis, sizeof(float) * (size_t)nq * k);
-  if (distance_type == 2 || distance_type == 12) {
+  if (feed_host) {
+    YBH_CHECK(yb_knn_l2_hostbase(nq, nb, d, k, b, (float *)ab.dev, (const float *)aq.dev,
+                                 (int *)oa.dev, (float *)od.dev, 0, NULL));
+  } else if (l2) {
     YBH_CHECK(yb_knn_l2(nq, nb, d, k, (const float *)ab.dev, (const float *)aq.dev,
                         (const float *)aw.dev, (int *)oa.dev, (float *)od.dev, 0, NULL));
   } else if ((distance_type >= 1 && distance_type <= 6) || distance_type == 16) {

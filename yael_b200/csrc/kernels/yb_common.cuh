@@ -14,6 +14,7 @@ namespace yb {
 int fail(int code, const char *fmt, ...);
 // stream to launch on: the caller's, or the library's own stream for the current device
 cudaStream_t stream_of(yb_stream_t s);
+cudaStream_t copy_stream();  // per-device stream for host->device feeds
 // grow-only cached workspace of the current device; valid until the next reserve() call
 // on the same device.  The whole library serialises HOST-side submission behind one mutex
 // (Guard); scratch_done() records the stream position after which the block may be reused

@@ -694,12 +694,26 @@ __global__ void k_col_final(const float *__restrict__ psum, const int *__restric
   mu[c] = m > 0 ? (float)(s / (double)m) : 0.f;
 }
 
+// Logical -> physical row index: identity, or "the first `rows` rows of every `stride` rows"
+// (the sample tiles of a database that is still arriving from the host).
+struct RowMap {
+  long rows, stride;  // rows == 0: identity
+  __host__ __device__ long operator()(long r) const {
+    return rows ? (r / rows) * stride + (r % rows) : r;
+  }
+  __host__ __device__ long count(long n) const {  // logical rows that map below n (upper bound)
+    return rows ? ((n + stride - 1) / stride) * rows : n;
+  }
+};
+
 // one warp per row: out[r][0..dpad) = x[r][c] - mu[c] (zero padded), optionally norm[r] = |out[r]|^2
 __global__ void __launch_bounds__(256)
 k_center_rows(const float *__restrict__ x, long n, int d, int dpad, const float *__restrict__ mu,
-              float *__restrict__ out, float *__restrict__ norm) {
-  const long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+              float *__restrict__ out, float *__restrict__ norm, RowMap rm) {
+  const long rl = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  if (rl >= rm.count(n)) return;
+  const long r = rm(rl);
   if (r >= n) return;
   float s = 0.f;
   for (int c = lane; c < dpad; c += 32) {
@@ -718,8 +732,10 @@ k_center_rows(const float *__restrict__ x, long n, int d, int dpad, const float 
 // only its order of summation differs, which the error model covers).
 __global__ void __launch_bounds__(256)
 k_center_rows_v4(const float *__restrict__ x, long n, int d, const float *__restrict__ mu,
-                 float *__restrict__ out, float *__restrict__ norm) {
-  const long r0 = ((long)blockIdx.x * 8 + (threadIdx.x >> 5)) * 4;
+                 float *__restrict__ out, float *__restrict__ norm, RowMap rm) {
+  const long rl0 = ((long)blockIdx.x * 8 + (threadIdx.x >> 5)) * 4;
+  if (rl0 >= rm.count(n)) return;
+  const long r0 = rm(rl0);  // blocks are multiples of 4 rows: the 4 rows stay consecutive
   const int lane = threadIdx.x & 31;
   const int d4 = d >> 2;
   float s[4] = {0.f, 0.f, 0.f, 0.f};
@@ -754,12 +770,13 @@ k_center_rows_v4(const float *__restrict__ x, long n, int d, const float *__rest
 }
 
 static void launch_center_rows(const float *x, long n, int d, int dpad, const float *mu, float *out,
-                               float *norm, cudaStream_t st) {
+                               float *norm, cudaStream_t st, RowMap rm = RowMap{0, 0}) {
   if (n <= 0) return;
-  if (dpad == d && (((uintptr_t)x | (uintptr_t)out | (uintptr_t)mu) & 15) == 0)
-    k_center_rows_v4<<<(unsigned)((n + 31) / 32), 256, 0, st>>>(x, n, d, mu, out, norm);
+  const long nl = rm.count(n);
+  if (dpad == d && (((uintptr_t)x | (uintptr_t)out | (uintptr_t)mu) & 15) == 0 && (rm.rows % 4) == 0)
+    k_center_rows_v4<<<(unsigned)((nl + 31) / 32), 256, 0, st>>>(x, n, d, mu, out, norm, rm);
   else
-    k_center_rows<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(x, n, d, dpad, mu, out, norm);
+    k_center_rows<<<(unsigned)((nl + 7) / 8), 256, 0, st>>>(x, n, d, dpad, mu, out, norm, rm);
   count_launch();
 }
 
@@ -1188,6 +1205,230 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
   return 0;
 }
 
+// ------------------------------------------------------------------ engine 1, database in host memory
+// knn_full() on a host-resident database is a PCIe transfer (517 MB, 9.5 ms for the bench
+// shape) followed by 5 ms of kernels.  Here the two overlap: the SAMPLE tiles (tile 0 of every
+// group of 16 tiles: a 2-D copy, 1/16 of the bytes) go first, the centring vector, the centred
+// queries and the admission thresholds are computed from them exactly as in the resident path,
+// and the rest of the database follows in a few large 2-D copies; each chunk is centred and
+// scanned by its own tensor pass as soon as its copy has landed, all passes publishing into one
+// set of shortlists.  Merge, exact re-rank, certificate and fallback are the resident path's.
+// Returns -1000 when the shape does not qualify (caller copies the database and calls the
+// resident path).
+int knn_tf32_streamed(int nq, int nb, int d, int k, const float *base_host, float *base,
+                      const float *query, int *assign, float *dis, int id_offset, int force,
+                      int *engine_out, long *uncert_out, cudaStream_t st) {
+  if (force == 0 || k < 2) return -1000;
+  const int dpad = (d + 3) & ~3;
+  Tf32Plan plan0 = tf32_plan(nq, nb, dpad, k);
+  if (!plan0.ok) return -1000;
+  const int kp = plan0.kprime, m = kp;
+  const int m_pad = pow2_ceil(m < 2 ? 2 : m);
+  const size_t smem = rerank_smem_bytes(d, m, m_pad);
+  if (smem > 160 * 1024 || 2 * kp > ML_CAP) return -1000;
+  const size_t row_bytes = sizeof(float) * (size_t)d;
+  const size_t total_bytes = row_bytes * (size_t)nb;
+  const long kGroupRows = 16L * 256;
+  const size_t pitch = (size_t)kGroupRows * row_bytes;
+  if (total_bytes < ((size_t)96 << 20) || pitch > ((size_t)1 << 30)) return -1000;
+  const long padded = tf32_padded_rows(nb);
+  const int nbt = tf32_tiles(nb);
+  const int kSampleStride = 16;
+  const int nbt_s = (nbt + kSampleStride - 1) / kSampleStride;
+  int j2 = (3 * kp + kSampleStride - 1) / kSampleStride;
+  if (j2 < 32) j2 = 32;
+  Tf32Plan splan = tf32_plan_tiles(nq, nbt_s, dpad, j2);
+  if (!splan.ok) return -1000;
+  const long srows = (long)nbt_s * 256;
+  int gsize = 16;
+  while (gsize < 128 && (srows / gsize > RK_T * RK_PER || (size_t)nq * (srows / gsize) * 4 > ((size_t)256 << 20)))
+    gsize *= 2;
+  const long gcols = srows / gsize;
+  if (gcols > RK_T * RK_PER || (long)j2 * 4 > gcols || (size_t)nq * gcols * 4 > ((size_t)512 << 20))
+    return -1000;
+
+  // chunks of whole 16-tile groups
+  const long ngroups = ((long)nb + kGroupRows - 1) / kGroupRows;
+  const long nfg = (long)nb / kGroupRows, rem = (long)nb % kGroupRows;
+  constexpr int kMaxChunks = 16;
+  int C = (int)(total_bytes / ((size_t)64 << 20));
+  if (const char *e = getenv("YAEL_B200_H2D_CHUNKS")) C = atoi(e) > 0 ? atoi(e) : C;
+  if (C < 2) C = 2;
+  if (C > kMaxChunks) C = kMaxChunks;
+  if (C > ngroups) C = (int)ngroups;
+  Tf32Plan cplan[kMaxChunks];
+  long g0[kMaxChunks + 1];
+  int list0[kMaxChunks + 1];
+  size_t tf_ws = splan.ws_bytes;
+  list0[0] = 0;
+  for (int c = 0; c < C; c++) {
+    g0[c] = ngroups * c / C;
+    const long g1 = ngroups * (c + 1) / C;
+    const long r0 = g0[c] * kGroupRows, r1 = g1 * kGroupRows < nb ? g1 * kGroupRows : nb;
+    cplan[c] = tf32_plan_tiles(nq, tf32_tiles((int)(r1 - r0)), dpad, kp);
+    if (!cplan[c].ok) return -1000;
+    if (cplan[c].ws_bytes > tf_ws) tf_ws = cplan[c].ws_bytes;
+    list0[c + 1] = list0[c] + cplan[c].lists;
+  }
+  g0[C] = ngroups;
+  const int lists = list0[C];
+  if (lists > ML_LISTS) return -1000;
+  const size_t stride = (size_t)lists * kp;
+
+  size_t need = Carver::need(sizeof(float) * (size_t)padded) + Carver::need(64) +
+                2 * Carver::need(sizeof(float) * (size_t)nq * stride) +
+                2 * Carver::need(sizeof(float) * (size_t)nq * lists) +
+                Carver::need(sizeof(int) * (size_t)nq * kp) + 2 * Carver::need(sizeof(int) * (size_t)nq) +
+                Carver::need(tf_ws) + 1024 + Carver::need(sizeof(float) * (size_t)nb * dpad) +
+                Carver::need(sizeof(float) * (size_t)nq * dpad) + center_ws_bytes(nb, d) +
+                Carver::need(sizeof(float) * (size_t)nq * gcols) + Carver::need(sizeof(float) * (size_t)nq);
+  int n_flag = 0;
+  cudaStream_t cs = copy_stream();
+  cudaEvent_t ev_begin = nullptr, ev_sample = nullptr, ev_chunk[kMaxChunks] = {};
+  auto new_event = [](cudaEvent_t *e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming); };
+  YB_CUDA(new_event(&ev_begin));
+  YB_CUDA(new_event(&ev_sample));
+  for (int c = 0; c < C; c++) YB_CUDA(new_event(&ev_chunk[c]));
+  struct EventGuard {
+    cudaEvent_t *a, *b, *c;
+    int n;
+    ~EventGuard() {
+      cudaEventDestroy(*a);
+      cudaEventDestroy(*b);
+      for (int i = 0; i < n; i++) cudaEventDestroy(c[i]);
+    }
+  } eguard = {&ev_begin, &ev_sample, ev_chunk, C};
+  {
+    ScratchScope ws(need, st);
+    Carver c(ws.p);
+    float *an = c.take<float>(padded);
+    float *scal = c.take<float>(16);
+    float *cscore = c.take<float>((size_t)nq * stride);
+    int *cid = c.take<int>((size_t)nq * stride);
+    float *cthr = c.take<float>((size_t)nq * lists);
+    int *ccnt = c.take<int>((size_t)nq * lists);
+    int *sel = c.take<int>((size_t)nq * kp);
+    int *flags = c.take<int>(nq);
+    int *flag_list = c.take<int>(nq);
+    void *tfws = c.take<char>(tf_ws);
+    float *base_c = c.take<float>((size_t)nb * dpad);
+    float *query_c = c.take<float>((size_t)nq * dpad);
+    char *cws = c.take<char>(center_ws_bytes(nb, d));
+    float *gm = c.take<float>((size_t)nq * gcols);
+    float *thr_init = c.take<float>(nq);
+    int rc;
+
+    // ---- copy stream: sample tiles first (the staging buffer may still be read by earlier
+    // work on the compute stream: order behind it)
+    YB_CUDA(cudaEventRecord(ev_begin, st));
+    YB_CUDA(cudaStreamWaitEvent(cs, ev_begin, 0));
+    if (nfg > 0)
+      YB_CUDA(cudaMemcpy2DAsync(base, pitch, base_host, pitch, 256 * row_bytes, (size_t)nfg,
+                                cudaMemcpyHostToDevice, cs));
+    if (rem > 0) {
+      const long r = nfg * kGroupRows, n = rem < 256 ? rem : 256;
+      YB_CUDA(cudaMemcpyAsync(base + r * d, base_host + r * d, (size_t)n * row_bytes,
+                              cudaMemcpyHostToDevice, cs));
+    }
+    YB_CUDA(cudaEventRecord(ev_sample, cs));
+
+    // ---- compute stream: centring vector, queries, sample tiles, thresholds
+    YB_CUDA(cudaStreamWaitEvent(st, ev_sample, 0));
+    Carver cc(cws);
+    float *psum = cc.take<float>((size_t)CM_BLOCKS * d);
+    int *pcnt = cc.take<int>((size_t)CM_BLOCKS * d);
+    float *mu = cc.take<float>(d);
+    {
+      ProfScope ps(0, st);
+      int nblk = ngroups < CM_BLOCKS ? (int)ngroups : CM_BLOCKS;
+      const long step = (ngroups / nblk) * kGroupRows;  // blocks start on sample tiles
+      k_col_partial<<<nblk, 256, 0, st>>>(base, nb, d, step, psum, pcnt);
+      YB_LAUNCH_CHECK();
+      k_col_final<<<(d + 127) / 128, 128, 0, st>>>(psum, pcnt, nblk, d, mu);
+      YB_LAUNCH_CHECK();
+      launch_center_rows(query, nq, d, dpad, mu, query_c, nullptr, st);
+      launch_center_rows(base, nb, d, dpad, mu, base_c, an, st, RowMap{256, kGroupRows});
+      YB_CUDA(cudaGetLastError());
+      if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
+      YB_CUDA(cudaMemsetAsync(scal, 0, 64, st));
+    }
+    {
+      ProfScope ps(10, st);
+      if ((rc = tf32_group_min(splan, nq, nb, dpad, nbt_s, kSampleStride, base_c, query_c, an, gm,
+                               gcols, gsize, tfws, st)))
+        return rc;
+      k_row_kth<<<nq, RK_T, 0, st>>>(gm, gcols, (int)gcols, j2, thr_init);
+      YB_LAUNCH_CHECK();
+    }
+
+    // ---- chunks: copy, centre, scan
+    for (int ch = 0; ch < C; ch++) {
+      const long ga = g0[ch], gb = g0[ch + 1];
+      const long gfull = gb < nfg ? gb : nfg;
+      if (gfull > ga) {
+        const long r = ga * kGroupRows + 256;
+        YB_CUDA(cudaMemcpy2DAsync(base + r * d, pitch, base_host + r * d, pitch,
+                                  (size_t)(kGroupRows - 256) * row_bytes, (size_t)(gfull - ga),
+                                  cudaMemcpyHostToDevice, cs));
+      }
+      if (gb > nfg && rem > 256) {  // the partial last group
+        const long r = nfg * kGroupRows + 256;
+        YB_CUDA(cudaMemcpyAsync(base + r * d, base_host + r * d, (size_t)(nb - r) * row_bytes,
+                                cudaMemcpyHostToDevice, cs));
+      }
+      YB_CUDA(cudaEventRecord(ev_chunk[ch], cs));
+      YB_CUDA(cudaStreamWaitEvent(st, ev_chunk[ch], 0));
+      const long r0 = ga * kGroupRows, r1 = gb * kGroupRows < nb ? gb * kGroupRows : nb;
+      {
+        ProfScope ps(0, st);
+        launch_center_rows(base + r0 * d, r1 - r0, d, dpad, mu, base_c + r0 * dpad, an + r0, st);
+        YB_CUDA(cudaGetLastError());
+      }
+      {
+        ProfScope ps(1, st);
+        Tf32Out oo = {};
+        oo.out_cnt = ccnt;
+        oo.lists_ld = lists;
+        oo.list0 = list0[ch];
+        oo.id0 = (int)r0;
+        if ((rc = tf32_shortlist(cplan[ch], nq, (int)(r1 - r0), dpad, tf32_tiles((int)(r1 - r0)), 1,
+                                 base_c + r0 * dpad, query_c, an + r0, thr_init, cscore, cid, cthr,
+                                 tfws, st, &oo)))
+          return rc;
+      }
+    }
+    k_sqrt_max<<<2 * sm_count(), 256, 0, st>>>(an, nb, scal);
+    YB_LAUNCH_CHECK();
+    {
+      ProfScope ps(2, st);
+      k_merge_lists<<<nq, ML_T, 0, st>>>(ccnt, cscore, lists, kp, kp, sel, nullptr);
+      YB_LAUNCH_CHECK();
+    }
+    RerankArgs A = {};
+    A.nq = nq; A.nb = nb; A.d = d; A.k = k; A.base = base; A.query = query;
+    A.dis = dis; A.assign = assign; A.id_offset = id_offset;
+    A.cand_id = cid; A.cand_score = cscore; A.sel = sel;
+    A.cand_stride = (int)stride; A.m = m; A.all_listed = 0;
+    A.cand_thr = cthr; A.lists = lists; A.query_c = query_c; A.qc_ld = dpad;
+    A.err_scale = kTf32ErrScale; A.bmax = scal; A.uncert_flags = flags;
+    A.gsort = nullptr; A.m_pad = m_pad; A.k1 = 0;
+    rerank_attrs();
+    {
+      ProfScope ps(3, st);
+      k_rerank<1><<<nq, RR_T, smem, st>>>(A);
+      YB_LAUNCH_CHECK();
+    }
+    k_collect_flags<<<(nq + 255) / 256, 256, 0, st>>>(flags, nq, flag_list, (int *)(scal + 1));
+    YB_LAUNCH_CHECK();
+    if ((rc = redo_flagged_exact(nq, nb, d, k, base, query, assign, dis, id_offset, flag_list,
+                                 (int *)(scal + 1), &n_flag, st)))
+      return rc;
+  }
+  *engine_out = 1;
+  *uncert_out = n_flag;
+  return 0;
+}
+
 }  // namespace yb
 
 using namespace yb;
@@ -1210,6 +1451,25 @@ extern "C" int yb_knn_l2(int nq, int nb, int d, int k, const float *base, const 
   g_last_uncert = 0;
   ScratchScope ws(knn_exact_ws_bytes(nq, nb, k), st);
   return knn_exact(nq, nb, d, k, base, query, b_weights, assign, dis, id_offset, ws.p, st);
+}
+
+// knn_full() with the database in HOST memory (pinned for full PCIe speed; pageable works):
+// base_dev is device scratch for nb*d floats that holds the database when the call returns.
+extern "C" int yb_knn_l2_hostbase(int nq, int nb, int d, int k, const float *base_host,
+                                   float *base_dev, const float *query, int *assign, float *dis,
+                                   int id_offset, yb_stream_t s) {
+  if (nq <= 0) return 0;
+  if (k <= 0 || k > nb) return fail(3, "yb_knn_l2_hostbase: need 0 < k <= nb (k=%d, nb=%d)", k, nb);
+  Guard g;
+  cudaStream_t st = stream_of(s);
+  const char *off = getenv("YAEL_B200_NO_STREAMED_H2D");
+  if (!(off && atoi(off))) {
+    int rc = knn_tf32_streamed(nq, nb, d, k, base_host, base_dev, query, assign, dis, id_offset,
+                               g_engine_force, &g_last_engine, &g_last_uncert, st);
+    if (rc != -1000) return rc;
+  }
+  YB_CUDA(cudaMemcpyAsync(base_dev, base_host, sizeof(float) * (size_t)nb * d, cudaMemcpyHostToDevice, st));
+  return yb_knn_l2(nq, nb, d, k, base_dev, query, nullptr, assign, dis, id_offset, s);
 }
 
 extern "C" int yb_knn_merge(int nq, int k, int G, const int *assign_in, const float *dis_in,

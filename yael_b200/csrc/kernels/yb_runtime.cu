@@ -17,6 +17,7 @@ constexpr int kMaxDev = 16;
 
 struct DevState {
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // host->device feeds that overlap the compute stream
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
   cudaEvent_t scratch_ev = nullptr;  // completion of the last op that used the scratch
@@ -73,6 +74,12 @@ int fail(int code, const char *fmt, ...) {
 
 Guard::Guard() { g_mutex.lock(); }
 Guard::~Guard() { g_mutex.unlock(); }
+
+cudaStream_t copy_stream() {
+  DevState &st = g_dev[cur_dev()];
+  if (!st.copy_stream) cudaStreamCreateWithFlags(&st.copy_stream, cudaStreamNonBlocking);
+  return st.copy_stream;
+}
 
 cudaStream_t stream_of(yb_stream_t s) {
   if (s) return (cudaStream_t)s;
