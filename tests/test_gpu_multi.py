@@ -45,6 +45,18 @@ def _worker(rank, world, port, q):
         idx, dis = s.search(torch.from_numpy(query).to(dev))
         widx, wdis = ynumpy.knn(query, base, k)
         detail['knn'] = bool(np.array_equal(idx.cpu().numpy(), widx) and np.array_equal(dis.cpu().numpy(), wdis))
+        # end-to-end on host buffers: the shard is fed over PCIe while it is scanned
+        big = r.random_sample((420000, 128)).astype(np.float32)
+        bq = r.random_sample((64, 128)).astype(np.float32)
+        lo, hi = ydist.shard_bounds(len(big), world)[rank]
+        s2 = ydist.ShardedKnn(torch.empty((hi - lo, 128), dtype=torch.float32, device=dev), 10, rank=rank,
+                              world=world, id_offset=lo)
+        oi = np.empty((64, 10), np.int32)
+        od = np.empty((64, 10), np.float32)
+        s2.search_host(np.ascontiguousarray(big[lo:hi]), bq, oi, od)
+        wi2, wd2 = ynumpy.knn(bq, big, 10)
+        detail['knn_host'] = bool(np.array_equal(oi, wi2) and np.array_equal(od, wd2))
+        del big, s2
         # Hamming: bit-identical for any shard count
         codes = r.randint(0, 256, (30000, 8)).astype(np.uint8)
         qc = r.randint(0, 256, (200, 8)).astype(np.uint8)
@@ -63,7 +75,7 @@ def _worker(rank, world, port, q):
         detail['kmeans_counts'] = bool(np.array_equal(nassign, wn) and np.array_equal(assign, wa[lo:hi]))
         detail['kmeans_cent_maxdiff'] = float(np.abs(cent - wc).max())
         detail['kmeans_qerr'] = (float(qerr), float(wq))
-        ok = detail['knn'] and detail['hamming'] and detail['kmeans_counts'] and \
+        ok = detail['knn'] and detail['knn_host'] and detail['hamming'] and detail['kmeans_counts'] and \
             detail['kmeans_cent_maxdiff'] < 1e-4 and abs(qerr - wq) < 1e-4 * wq
         q.put((rank, bool(ok) if ok else detail))
     except Exception as e:  # report instead of hanging the peer

@@ -92,9 +92,20 @@ class ShardedKnn:
                                   base_host.ctypes.data_as(f), query_host.ctypes.data_as(f), None,
                                   idx_out.ctypes.data_as(i), dis_out.ctypes.data_as(f), 1)
             return
-        self.base.copy_(torch.from_numpy(base_host), non_blocking=True)
+        # the shard travels over PCIe while it is being scanned (yb_knn_l2_hostbase), then the
+        # usual all-gather + merge
         q = torch.from_numpy(query_host).to(self.base.device, non_blocking=True)
-        oi, od = self.search(q)
+        idx = torch.empty((nq, self.k), dtype=torch.int32, device=q.device)
+        dis = torch.empty((nq, self.k), dtype=torch.float32, device=q.device)
+        check(lib().yb_knn_l2_hostbase(nq, base_host.shape[0], d, self.k, base_host.ctypes.data,
+                                       self.base.data_ptr(), q.data_ptr(), idx.data_ptr(),
+                                       dis.data_ptr(), self.id_offset, _stream_ptr(torch)),
+              "yb_knn_l2_hostbase")
+        import torch.distributed as dist
+        gi, gd = allgather_lists(dist, torch, idx, dis, self.world)
+        oi, od = torch.empty_like(idx), torch.empty_like(dis)
+        check(lib().yb_knn_merge(nq, self.k, self.world, gi.data_ptr(), gd.data_ptr(),
+                                 oi.data_ptr(), od.data_ptr(), _stream_ptr(torch)), "yb_knn_merge")
         torch.from_numpy(idx_out).copy_(oi, non_blocking=True)
         torch.from_numpy(dis_out).copy_(od, non_blocking=True)
         torch.cuda.synchronize()
