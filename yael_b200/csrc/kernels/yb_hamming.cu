@@ -142,20 +142,40 @@ k_nn_hamming_scan(int nq, long nb, int k, int cap, const unsigned long long *__r
         if (__any_sync(0xffffffffu, cnt[qq] > cap - 32)) compact(qq);
       const int cn = min(32, tn - c0);
       if (cn == 32) {
-#pragma unroll 8
-        for (int c = 0; c < 32; c++) {
-          unsigned long long code[W];
+        // 8 codes at a time: distances stay in registers and ONE branch decides whether any
+        // of the 8 x HQT pairs beats its threshold (rare once the lists are warm).  Per pair
+        // that leaves xor, popc, add and a predicate-accumulating compare; the predicated
+        // append sequence the compiler otherwise issues for every pair cost more slots than
+        // the popcounts.
+#pragma unroll 1
+        for (int c8 = 0; c8 < 32; c8 += 8) {
+          int dd[HQT][8];
+          bool any = false;
 #pragma unroll
-          for (int w = 0; w < W; w++) code[w] = tile[(c0 + c) * W + w];
+          for (int j = 0; j < 8; j++) {
+            unsigned long long code[W];
 #pragma unroll
-          for (int qq = 0; qq < HQT; qq++) {
-            int dist = 0;
+            for (int w = 0; w < W; w++) code[w] = tile[(c0 + c8 + j) * W + w];
 #pragma unroll
-            for (int w = 0; w < W; w++) dist += __popcll(code[w] ^ qc[qq][w]);
-            if (dist < thr[qq]) {
-              my[qq][(size_t)cnt[qq] * HT] =
-                  ((unsigned long long)dist << 32) | (unsigned)(int)(t0 + c0 + c + id_offset);
-              cnt[qq]++;
+            for (int qq = 0; qq < HQT; qq++) {
+              int dist = 0;
+#pragma unroll
+              for (int w = 0; w < W; w++) dist += __popcll(code[w] ^ qc[qq][w]);
+              dd[qq][j] = dist;
+              any |= dist < thr[qq];
+            }
+          }
+          if (any) {
+#pragma unroll
+            for (int qq = 0; qq < HQT; qq++) {
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                if (dd[qq][j] < thr[qq]) {
+                  my[qq][(size_t)cnt[qq] * HT] = ((unsigned long long)dd[qq][j] << 32) |
+                                                 (unsigned)(int)(t0 + c0 + c8 + j + id_offset);
+                  cnt[qq]++;
+                }
+              }
             }
           }
         }
@@ -427,9 +447,30 @@ extern "C" int yb_nn_hamming(int nq, int nb, int ncodes, int k, const uint8_t *b
   Guard g;
   cudaStream_t st = stream_of(s);
   const int gx = (nq + HQT * HT - 1) / (HQT * HT);
-  // splits: fill the machine about 4 CTAs deep, keep every split at least 4 tiles long
-  int S = (4 * sm_count() + gx - 1) / gx;
+  // splits: every CTA of the grid is resident at once (up to 7 per SM: 32 KB of shared memory
+  // each) and all CTAs cost the same, so the pass lasts as long as the fullest SM: pick the
+  // split count whose grid fills whole "layers" of SMs best (gx * S just below a multiple of
+  // the SM count), 4 to 7 CTAs per SM, every split at least 4 tiles long.  On the BASELINE
+  // shape (gx = 40): S = 15 -> 600 CTAs, some SMs run 5 and most 4 (69.3 ms); S = 18 -> 720
+  // CTAs, 5 per SM nearly everywhere (60.4 ms).
+  const int sms = sm_count();
+  int S = (4 * sms + gx - 1) / gx;
+  {
+    double best_eff = 0.0;
+    for (int cand = 1; cand <= 4096; cand++) {
+      const long items = (long)gx * cand;
+      const long per_sm = (items + sms - 1) / sms;
+      if (per_sm > 7) break;
+      if (per_sm < 4 && cand > 1) continue;
+      const double eff = (double)items / (double)(per_sm * sms);
+      if (eff > best_eff + 0.005) {
+        best_eff = eff;
+        S = cand;
+      }
+    }
+  }
   long max_s = ((long)nb + 4 * HTILE - 1) / (4 * HTILE);
+  if (const char *e = getenv("YAEL_B200_HAM_SPLITS")) S = atoi(e) > 0 ? atoi(e) : S;  // experiment knob
   if (S > max_s) S = (int)max_s;
   if (S < 1) S = 1;
   int cap = k + 64 > 2 * k ? k + 64 : 2 * k;
