@@ -372,13 +372,6 @@ __device__ __forceinline__ void ffma2_m2(float &d0, float &d1, uint32_t a0, uint
       : "r"(a0), "r"(a1), "f"(c0), "f"(c1), "f"(-2.0f));
 }
 
-// 16 accumulator columns of one query.  Fast path: scores and their minimum (one FFMA and one
-// FMNMX per candidate); only when the minimum beats the query's admission threshold -- rare once
-// the threshold is tight -- are the 16 candidates tested one by one and appended to the query's
-// list in global memory.
-// Slow paths, out of line and with the 16 scores passed BY VALUE (registers, no stack traffic in
-// the caller): the hot loop has to stay small -- an earlier fully inlined version stalled mostly
-// on instruction fetch.
 #define YB_SC16_PARAMS float s0, float s1, float s2, float s3, float s4, float s5, float s6, float s7, \
                        float s8, float s9, float s10, float s11, float s12, float s13, float s14, float s15
 #define YB_SC16_ARGS(a) a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], \
@@ -491,7 +484,7 @@ struct EpiCtx {
   uint32_t sbase, tmem_base;
   int warp, lane;
   int first_item, item_step, tq_div;
-  int pair;            // 0: independent CTAs; 1: multicast pairs; 2: cta_group::2 pairs
+  int pair;            // 0: independent CTAs; 1: multicast pairs
   uint32_t crank;
   uint32_t t_empty_addr0, t_empty_addr1;  // where to signal "accumulator buffer drained" (local or leader CTA)
   int t_empty_remote;        // the address is a shared::cluster address of the peer CTA
@@ -904,200 +897,6 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
   }
 }
 
-// ------------------------------------------------------------------ the 2-SM kernel
-// Same roles and the same epilogue as k_knn_tf32, but two CTAs of a cluster form one MMA unit:
-// tcgen05.mma.cta_group::2, M = 256 (each CTA's 128 queries), N = 256 with HALF of every
-// database chunk (128 rows, 16 KB) in each CTA's shared memory.  Per SM and MMA instruction the
-// tensor core then reads 4 KB of A + 4 KB of B instead of 4 + 8: single-CTA SS-mode MMAs are
-// shared-memory-bandwidth bound at about half the nominal rate (measured: 254 cycles per
-// M128 N256 K8 instruction against a 128-cycle floor), which is why every peak GEMM on this
-// part is a "2sm" kernel.  The smaller B stage also doubles the pipeline depth (8 stages).
-//   * only the leader CTA (cluster rank 0) issues MMAs; it waits on ITS full barriers, which
-//     both CTAs' TMA loads complete (cta_group::2 loads signal the leader's barrier)
-//   * tcgen05.commit.cta_group::2 ... multicast releases the smem slots / publishes the
-//     accumulators in both CTAs
-//   * the peer's epilogue threads signal "accumulator drained" on the leader's barrier
-constexpr int STAGES2 = 8;
-constexpr int B2_CHUNK_BYTES = (TN / 2) * KC * 4;  // 16 KB: this CTA's half of a chunk
-struct Smem2 {
-  static constexpr int a_off = 0;
-  static constexpr int b_off = MAX_NKC * A_CHUNK_BYTES;
-  static constexpr int bn_off = b_off + STAGES2 * B2_CHUNK_BYTES;
-  static constexpr int hist_off = bn_off + NBN * TN * 4;
-  static constexpr int bar_off = hist_off + EPI_WARPS * 256 * 4;
-  static constexpr int a_full = 0, a_empty = 1, b_full = 2, b_empty = b_full + STAGES2,
-                       n_full = b_empty + STAGES2, n_empty = n_full + NBN,
-                       t_full = n_empty + NBN, t_empty = t_full + 2, nbar = t_empty + 2;
-  static constexpr int tmem_ptr_off = bar_off + nbar * 8;
-  static constexpr int total = tmem_ptr_off + 16;
-};
-static_assert(Smem2::bn_off == Smem::bn_off && Smem2::hist_off == Smem::hist_off,
-              "run_epilogue() addresses |b|^2 tiles and histograms through Smem::");
-static_assert(Smem2::bar_off == Smem::bar_off, "barrier block must sit at the same offset");
-constexpr int TF32_SMEM2_BYTES = Smem2::total;
-constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
-
-__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *map,
-                                                uint32_t leader_bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit_2sm(uint32_t bar, uint16_t mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
-          "r"(bar),
-      "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                                uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// D=F32, A=B=TF32, K-major, N=256, M=256 (two CTAs x 128)
-constexpr uint32_t IDESC_TF32_2SM = (1u << 4) | (2u << 7) | (2u << 10) |
-                                    ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-
-template <int MODE>
-__global__ void __launch_bounds__(TF32_THREADS, 1)
-k_knn_tf32_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_bh,
-               const Tf32Params P) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  const uint32_t sbase = smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  auto bar = [&](int i) { return sbase + Smem2::bar_off + 8 * i; };
-  volatile uint32_t *tmem_ptr_smem = (volatile uint32_t *)(smem + Smem2::tmem_ptr_off);
-  const uint32_t crank = cluster_ctarank();
-  const bool leader = crank == 0;
-
-  if (threadIdx.x == 0) {
-    mbar_init(bar(Smem2::a_full), 1);
-    mbar_init(bar(Smem2::a_empty), 1);
-    for (int i = 0; i < STAGES2; i++) {
-      mbar_init(bar(Smem2::b_full + i), 1);
-      mbar_init(bar(Smem2::b_empty + i), 1);
-    }
-    for (int i = 0; i < NBN; i++) {
-      mbar_init(bar(Smem2::n_full + i), 1);
-      mbar_init(bar(Smem2::n_empty + i), EPI_WARPS);
-    }
-    for (int i = 0; i < 2; i++) {
-      mbar_init(bar(Smem2::t_full + i), 1);
-      mbar_init(bar(Smem2::t_empty + i), 2 * EPI_WARPS);  // both CTAs' epilogue warps (leader's copy)
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == EPI_WARPS + 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     sbase + Smem2::tmem_ptr_off),
-                 "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated in both
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-
-  const int first_item = (int)(blockIdx.x >> 1), item_step = (int)(gridDim.x >> 1);
-  const int tq_div = P.tiles_q2;
-
-  if (warp == EPI_WARPS) {
-    // ======================================================================== TMA producer
-    if (lane == 0) {
-      uint32_t icount = 0, ccount = 0, tcount = 0;
-      for (int item = first_item; item < P.items; item += item_step, icount++) {
-        const int sp = item / tq_div;
-        const int qt = (item - sp * tq_div) * 2 + (int)crank;
-        const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
-        mbar_wait(bar(Smem2::a_empty), (icount & 1) ^ 1);
-        if (leader)  // the leader's barrier collects the bytes of BOTH CTAs
-          mbar_expect_tx(bar(Smem2::a_full), (uint32_t)(2 * P.nkc * A_CHUNK_BYTES));
-        for (int kc = 0; kc < P.nkc; kc++)
-          tma_load_2d_2sm(sbase + Smem2::a_off + kc * A_CHUNK_BYTES, &map_q,
-                          bar(Smem2::a_full) & PEER_BIT_MASK, kc * KC, qt * TM);
-        for (int jt = jt0; jt < jt1; jt++, tcount++) {
-          const uint32_t slot = tcount % NBN;
-          mbar_wait(bar(Smem2::n_empty + slot), ((tcount / NBN) & 1) ^ 1);
-          mbar_expect_tx(bar(Smem2::n_full + slot), TN * 4);
-          const int jta = jt * P.tile_stride;
-          bulk_load_1d(sbase + Smem2::bn_off + slot * TN * 4, P.bnorm + (size_t)jta * TN, TN * 4,
-                       bar(Smem2::n_full + slot));
-          for (int kc = 0; kc < P.nkc; kc++, ccount++) {
-            const uint32_t st = ccount % STAGES2;
-            mbar_wait(bar(Smem2::b_empty + st), ((ccount / STAGES2) & 1) ^ 1);
-            if (leader) mbar_expect_tx(bar(Smem2::b_full + st), 2 * B2_CHUNK_BYTES);
-            // this CTA's half of the chunk: rows [crank*128, +128) of the tile
-            tma_load_2d_2sm(sbase + Smem2::b_off + st * B2_CHUNK_BYTES, &map_bh,
-                            bar(Smem2::b_full + st) & PEER_BIT_MASK, kc * KC,
-                            jta * TN + (int)crank * (TN / 2));
-          }
-        }
-      }
-    }
-  } else if (warp == EPI_WARPS + 1) {
-    // ======================================================================== MMA issuer
-    if (leader && lane == 0) {
-      uint32_t icount = 0, ccount = 0, tcount = 0;
-      for (int item = first_item; item < P.items; item += item_step, icount++) {
-        const int sp = item / tq_div;
-        const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
-        mbar_wait(bar(Smem2::a_full), icount & 1);
-        for (int jt = jt0; jt < jt1; jt++, tcount++) {
-          const uint32_t buf = tcount & 1;
-          mbar_wait(bar(Smem2::t_empty + buf), ((tcount >> 1) & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * TN;
-          for (int kc = 0; kc < P.nkc; kc++, ccount++) {
-            const uint32_t st = ccount % STAGES2;
-            mbar_wait(bar(Smem2::b_full + st), (ccount / STAGES2) & 1);
-            tc_fence_after();
-            const int nk8 = (kc == P.nkc - 1) ? P.last_k8 : 4;
-            const uint64_t adesc = smem_desc_sw128(sbase + Smem2::a_off + kc * A_CHUNK_BYTES);
-            const uint64_t bdesc = smem_desc_sw128(sbase + Smem2::b_off + st * B2_CHUNK_BYTES);
-            for (int k8 = 0; k8 < nk8; k8++)
-              tc_mma_tf32_2sm(d_tmem, adesc + (uint64_t)(2 * k8), bdesc + (uint64_t)(2 * k8),
-                              IDESC_TF32_2SM, (kc | k8) != 0);
-            tc_commit_2sm(bar(Smem2::b_empty + st), (uint16_t)3);
-          }
-          tc_commit_2sm(bar(Smem2::t_full + buf), (uint16_t)3);
-        }
-        tc_commit_2sm(bar(Smem2::a_empty), (uint16_t)3);
-      }
-    }
-  } else {
-    EpiCtx ectx;
-    ectx.smem = smem; ectx.sbase = sbase; ectx.tmem_base = tmem_base; ectx.warp = warp; ectx.lane = lane;
-    ectx.first_item = first_item; ectx.item_step = item_step; ectx.tq_div = tq_div;
-    ectx.pair = 2; ectx.crank = crank;
-    // "accumulator drained" goes to the LEADER's barrier (the only MMA issuer)
-    uint32_t a0, a1;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(a0) : "r"(bar(Smem2::t_empty + 0)));
-    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(a1) : "r"(bar(Smem2::t_empty + 1)));
-    ectx.t_empty_addr0 = a0; ectx.t_empty_addr1 = a1;
-    ectx.t_empty_remote = 1;
-    ectx.n_full0 = Smem2::n_full; ectx.n_empty0 = Smem2::n_empty; ectx.t_full0 = Smem2::t_full;
-    run_epilogue<MODE>(P, ectx);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // nobody leaves (or frees TMEM) while the pair is still working
-  if (warp == EPI_WARPS + 1) {
-    __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
-  }
-}
-
 __global__ void k_fill_f32(float *p, long n, float v) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -1142,8 +941,8 @@ static int make_map(CUtensorMap *m, const float *ptr, long rows, int d, int box_
 // Measured on the bench shape: pairing halves the L2->SM traffic but does not shorten the pass
 // (6.02 vs 5.90 ms) -- the L2 feed is not what bounds this kernel -- so it stays opt-in.
 int tf32_pair_mode() {
-  const char *e = getenv("YAEL_B200_PAIR");  // 0 independent CTAs, 1 multicast pairs, 2 cta_group::2
-  return e ? atoi(e) : 0;
+  const char *e = getenv("YAEL_B200_PAIR");  // 0 independent CTAs, 1 multicast pairs
+  return (e && atoi(e) != 0) ? 1 : 0;
 }
 
 int tf32_kprime_for(int k) {
@@ -1206,7 +1005,7 @@ Tf32Plan tf32_plan(int nq, int nb, int d, int k) {
 template <int MODE>
 static int launch_mode(const Tf32Plan &plan, const CUtensorMap &mq, const CUtensorMap &mb,
                        const CUtensorMap &mbh, const Tf32Params &P, cudaStream_t st) {
-  static bool attr = false, attr2 = false;
+  static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(k_knn_tf32<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          TF32_SMEM_BYTES);
@@ -1215,16 +1014,10 @@ static int launch_mode(const Tf32Plan &plan, const CUtensorMap &mq, const CUtens
     attr = true;
   }
   if (plan.pair) {
-    if (plan.pair == 2 && !attr2) {
-      cudaError_t e = cudaFuncSetAttribute(k_knn_tf32_2sm<MODE>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, TF32_SMEM2_BYTES);
-      if (e != cudaSuccess) return fail(6, "cannot reserve shared memory: %s", cudaGetErrorString(e));
-      attr2 = true;
-    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(plan.ctas);
     cfg.blockDim = dim3(TF32_THREADS);
-    cfg.dynamicSmemBytes = plan.pair == 2 ? TF32_SMEM2_BYTES : TF32_SMEM_BYTES;
+    cfg.dynamicSmemBytes = TF32_SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -1233,8 +1026,7 @@ static int launch_mode(const Tf32Plan &plan, const CUtensorMap &mq, const CUtens
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = plan.pair == 2 ? cudaLaunchKernelEx(&cfg, k_knn_tf32_2sm<MODE>, mq, mbh, P)
-                                   : cudaLaunchKernelEx(&cfg, k_knn_tf32<MODE>, mq, mb, mbh, P);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_knn_tf32<MODE>, mq, mb, mbh, P);
     if (e != cudaSuccess) return fail(2, "k_knn_tf32 cluster launch: %s", cudaGetErrorString(e));
     count_launch();
   } else {
