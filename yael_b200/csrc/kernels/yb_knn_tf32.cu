@@ -968,7 +968,7 @@ Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kp) {
   // range at least 8 tiles long
   int best_s = 1;
   double best_eff = 0.0;
-  for (int s = 1; s <= 32; s++) {
+  for (int s = 1; s <= 160; s++) {  // up to one range per SM for a single query tile
     if (s > 1 && nbt / s < 8) break;
     int range = (nbt + s - 1) / s;
     int s_eff = (nbt + range - 1) / range;
