@@ -869,33 +869,63 @@ __global__ void __launch_bounds__(128)
 k_rerank_k1(int nq, int d, int slots, int lists, const float *__restrict__ base,
             const float *__restrict__ query, const int *__restrict__ cand_id,
             const float *__restrict__ cand_thr, int *__restrict__ assign, float *__restrict__ dis,
-            int id_offset, int *__restrict__ flags) {
-  const int q = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+            int id_offset, int *__restrict__ flags, const double *__restrict__ qnorm) {
+  // One warp per query, a handful of candidates each (the rows within the TF32 margin of the
+  // best score).  The candidate rows and the query are brought into shared memory with
+  // coalesced loads, all in flight together; then lane c walks candidate c sequentially -- the
+  // reference's order of operations (nn.c:100-129: float norm of the base row, double norm of
+  // the query, one FMA chain for the dot product), so distances equal the oracle's bit for bit.
+  constexpr int RB = 8;          // candidates per batch
+  constexpr int RP = 128 + 1;    // row pitch (d <= 128 on this path), odd: no bank conflicts
+  __shared__ float rows[4][RB][RP];
+  __shared__ float qs[4][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 4 + warp;
   if (q >= nq) return;
   const float *qrow = query + (size_t)q * d;
+  for (int t = lane; t < d; t += 32) qs[warp][t] = qrow[t];
   unsigned long long best = ~0ull;
-  double qn = 0.0;
-  bool have_qn = false;
+  const double qn = qnorm[q];  // sequential double sum of squares (k_row_norms_seq, nn.c:108-120)
   for (int s0 = 0; s0 < slots; s0 += 32) {
     const int slot = s0 + lane;
     const int id = slot < slots ? cand_id[(size_t)q * slots + slot] : -1;
-    if (id >= 0) {
-      if (!have_qn) {
-        for (int t = 0; t < d; t++) qn += (double)__fmul_rn(qrow[t], qrow[t]);
-        have_qn = true;
+    unsigned todo = __ballot_sync(0xffffffffu, id >= 0);
+    while (todo) {
+      // this batch: the first RB candidates of `todo`; lane c < nb_ takes candidate c
+      int src[RB];
+      int nb_ = 0;
+#pragma unroll
+      for (int c = 0; c < RB; c++) {
+        src[c] = todo ? __ffs(todo) - 1 : -1;
+        if (todo) {
+          todo &= todo - 1;
+          nb_++;
+        }
       }
-      const float *brow = base + (size_t)id * d;
-      float nf = 0.f, dot = 0.f;
-      for (int t = 0; t < d; t++) {
-        const float v = __ldg(brow + t);
-        nf = __fadd_rn(nf, __fmul_rn(v, v));
-        dot = fmaf(v, qrow[t], dot);
+      __syncwarp();
+      int myid = -1;
+#pragma unroll
+      for (int c = 0; c < RB; c++) {
+        if (src[c] < 0) break;
+        const int idc = __shfl_sync(0xffffffffu, id, src[c]);
+        if (c == lane) myid = idc;
+        const float *brow = base + (size_t)idc * d;
+        for (int t = lane; t < d; t += 32) rows[warp][c][t] = __ldg(brow + t);
       }
-      const float dist = __fadd_rn((float)(qn + (double)nf), __fmul_rn(-2.0f, dot));
-      const uint32_t fk = float_key(dist);
-      if (!is_nan_key(fk)) {
-        unsigned long long key = ((unsigned long long)fk << 32) | (unsigned)id;
-        best = key < best ? key : best;
+      __syncwarp();
+      if (lane < nb_) {
+        float nf = 0.f, dot = 0.f;
+        for (int t = 0; t < d; t++) {
+          const float v = rows[warp][lane][t];
+          nf = __fadd_rn(nf, __fmul_rn(v, v));
+          dot = fmaf(v, qs[warp][t], dot);
+        }
+        const float dist = __fadd_rn((float)(qn + (double)nf), __fmul_rn(-2.0f, dot));
+        const uint32_t fk = float_key(dist);
+        if (!is_nan_key(fk)) {
+          unsigned long long key = ((unsigned long long)fk << 32) | (unsigned)myid;
+          best = key < best ? key : best;
+        }
       }
     }
   }
@@ -939,13 +969,15 @@ static int knn_tf32_nearest(int nq, int nb, int d, const float *base, const floa
                 Carver::need(sizeof(float) * (size_t)nq * slots) +
                 Carver::need(sizeof(int) * (size_t)nq * slots) +
                 Carver::need(sizeof(float) * (size_t)nq * plan.lists) +
-                2 * Carver::need(sizeof(int) * (size_t)nq) + Carver::need(plan.ws_bytes) + 1024;
+                2 * Carver::need(sizeof(int) * (size_t)nq) + Carver::need(plan.ws_bytes) + 1024 +
+                Carver::need(sizeof(double) * (size_t)nq);
   int n_flag = 0;
   {
     ScratchScope ws(need, st);
     Carver c(ws.p);
     float *an = c.take<float>(padded);
     float *scal = c.take<float>(16);
+    double *qnorm = c.take<double>(nq);
     float *margin = c.take<float>(nq);
     float *cscore = c.take<float>((size_t)nq * slots);
     int *cid = c.take<int>((size_t)nq * slots);
@@ -975,8 +1007,9 @@ static int knn_tf32_nearest(int nq, int nb, int d, const float *base, const floa
     }
     {
       ProfScope ps(3, st);
+      if ((rc = row_norms_seq(query, nq, d, d, nullptr, qnorm, st))) return rc;
       k_rerank_k1<<<(nq + 3) / 4, 128, 0, st>>>(nq, d, slots, plan.lists, base, query, cid, cthr,
-                                                assign, dis, id_offset, flags);
+                                                assign, dis, id_offset, flags, qnorm);
       YB_LAUNCH_CHECK();
     }
     k_collect_flags<<<(nq + 255) / 256, 256, 0, st>>>(flags, nq, flag_list, (int *)(scal + 1));
