@@ -37,6 +37,23 @@ void match_hamming_thres(const uint8 *bs1, const uint8 *bs2, int n1, int n2, int
 /* yael/hamming.c:704-748: idx receives (qid, bid) interleaved, hams the scores */
 size_t match_hamming_thres_prealloc(const uint8 *bs1, const uint8 *bs2, int n1, int n2, int ht,
                                     int ncodes, int *idx, uint16 *hams);
+/* yael/hamming.c:368-395: number of pairs i < j of one set with distance <= ht */
+void crossmatch_hamming_count(const uint8 *dbs, int n, int ht, int ncodes, size_t *nptr);
+/* yael/hamming.c:751-790: the pairs themselves (qid = i, bid = j, i < j, in (i, j) order);
+ * *hmptr is malloc'd here (bufsize: the reference's initial guess, ignored), caller frees */
+void crossmatch_hamming(const uint8 *dbs, long n, int ht, int ncodes, long bufsize,
+                        hammatch_t **hmptr, size_t *nptr);
+/* yael/hamming.c:793-829: the same into caller memory sized by crossmatch_hamming_count;
+ * idx receives (i, j) interleaved; returns the number of pairs */
+size_t crossmatch_hamming_prealloc(const uint8 *dbs, long n, int ht, int ncodes, int *idx,
+                                   uint16 *hams);
+/* yael/hamming.c:832-843: the reference's OpenMP variant (built there only under _OPENMP,
+ * yael/hamming.h:69-75); the GPU path has no thread count to honour -- same result as
+ * compute_hamming.  (match_hamming_thres_nt, hamming.c:846-903, is NOT provided: it is compiled
+ * out of the reference's default build and returns block-local ids from a block index that
+ * only covers all pairs when n1 and n2 span equally many 128-blocks.) */
+void compute_hamming_thread(uint16 *dis, const uint8 *a, const uint8 *b, int na, int nb,
+                            int ncodes);
 #ifdef __cplusplus
 }
 #endif

@@ -171,6 +171,12 @@ int yb_match_hamming_count(const uint8_t *bs1, const uint8_t *bs2, int n1, int n
 int yb_match_hamming_thres(const uint8_t *bs1, const uint8_t *bs2, int n1, int n2, int ht,
                            int ncodes, int *idx, uint16_t *hams, unsigned long long *count,
                            yb_stream_t s);
+/* crossmatch_hamming_count / crossmatch_hamming_prealloc (yael/hamming.c:368-395, 793-829):
+ * pairs i < j of one code set with distance <= ht, emitted as (i, j) in (i, j) order. */
+int yb_crossmatch_hamming_count(const uint8_t *dbs, int n, int ht, int ncodes,
+                                unsigned long long *count, yb_stream_t s);
+int yb_crossmatch_hamming(const uint8_t *dbs, int n, int ht, int ncodes, int *idx,
+                          uint16_t *hams, unsigned long long *count, yb_stream_t s);
 
 #ifdef __cplusplus
 }

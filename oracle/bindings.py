@@ -92,6 +92,9 @@ def oracle():
         L.orc_match_hamming_count.argtypes = [_u8, _u8, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
         L.orc_match_hamming_thres_prealloc.argtypes = [_u8, _u8, C.c_int, C.c_int, C.c_int, C.c_int, _i, _u16]
         L.orc_match_hamming_thres_prealloc.restype = C.c_size_t
+        L.orc_crossmatch_hamming_count.argtypes = [_u8, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+        L.orc_crossmatch_hamming_prealloc.argtypes = [_u8, C.c_long, C.c_int, C.c_int, _i, _u16]
+        L.orc_crossmatch_hamming_prealloc.restype = C.c_size_t
         _oracle = L
     return _oracle
 
@@ -121,6 +124,9 @@ def ref():
         L.match_hamming_count.argtypes = [_u8, _u8, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
         L.match_hamming_thres_prealloc.argtypes = [_u8, _u8, C.c_int, C.c_int, C.c_int, C.c_int, _i, _u16]
         L.match_hamming_thres_prealloc.restype = C.c_size_t
+        L.crossmatch_hamming_count.argtypes = [_u8, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+        L.crossmatch_hamming_prealloc.argtypes = [_u8, C.c_long, C.c_int, C.c_int, _i, _u16]
+        L.crossmatch_hamming_prealloc.restype = C.c_size_t
         L.ivec_new_random_perm_r.argtypes = [C.c_int, C.c_uint]
         L.ivec_new_random_perm_r.restype = C.POINTER(C.c_int)
         L.fvec_randn_r.argtypes = [_f, C.c_long, C.c_uint]

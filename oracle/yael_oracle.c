@@ -833,3 +833,29 @@ size_t orc_match_hamming_thres_prealloc(const uint8_t *bs1, const uint8_t *bs2, 
     }
   return cnt;
 }
+
+void orc_crossmatch_hamming_count(const uint8_t *dbs, int n, int ht, int ncodes, size_t *nptr) {
+  /* yael/hamming.c:310-395: pairs i < j of one set, score <= ht */
+  size_t cnt = 0;
+  for (long i = 0; i < n; i++)
+    for (long j = i + 1; j < n; j++)
+      if ((int)ham_words(dbs + (size_t)i * ncodes, dbs + (size_t)j * ncodes, ncodes) <= ht) cnt++;
+  *nptr = cnt;
+}
+
+size_t orc_crossmatch_hamming_prealloc(const uint8_t *dbs, long n, int ht, int ncodes, int *idx,
+                                       uint16_t *hams) {
+  /* yael/hamming.c:793-829: (i, j) interleaved, i outer / j = i+1.. inner */
+  size_t cnt = 0;
+  for (long i = 0; i < n; i++)
+    for (long j = i + 1; j < n; j++) {
+      unsigned h = ham_words(dbs + (size_t)i * ncodes, dbs + (size_t)j * ncodes, ncodes);
+      if ((int)h <= ht) {
+        idx[2 * cnt] = (int)i;
+        idx[2 * cnt + 1] = (int)j;
+        hams[cnt] = (uint16_t)h;
+        cnt++;
+      }
+    }
+  return cnt;
+}

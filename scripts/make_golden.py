@@ -97,3 +97,21 @@ mham = np.empty(n.value, np.uint16)
 L.match_hamming_thres_prealloc(ob.u8p(ha), ob.u8p(hb), 23, 31, 28, 8, ob.ip(midx), ob.u16p(mham))
 hout["match_ht28_idx"], hout["match_ht28_ham"] = midx, mham
 save("hamming", **hout)
+
+# 9. Hamming cross-matching inside one set (crossmatch_hamming_count / _prealloc,
+#    yael/hamming.c:368-395, 793-829) for 4 / 8 / 16 / 5 byte codes, planted near-duplicates
+cout = {}
+rc = np.random.RandomState(8)
+for nc, ht in ((4, 10), (8, 24), (16, 52), (5, 14)):
+    db = rc.randint(0, 256, (300, nc)).astype(np.uint8)
+    db[::37] = db[3]            # exact duplicates (distance 0)
+    db[5::41, 0] ^= 0x11        # and near-duplicates of whatever sits there
+    n = C.c_size_t(0)
+    L.crossmatch_hamming_count(ob.u8p(db), 300, ht, nc, C.byref(n))
+    cidx = np.empty((n.value, 2), np.int32)
+    cham = np.empty(n.value, np.uint16)
+    m = L.crossmatch_hamming_prealloc(ob.u8p(db), 300, ht, nc, ob.ip(cidx), ob.u16p(cham))
+    assert m == n.value
+    cout["db%d" % nc], cout["ht%d" % nc] = db, np.int32(ht)
+    cout["idx%d" % nc], cout["ham%d" % nc] = cidx, cham
+save("hamming_crossmatch", **cout)

@@ -157,6 +157,29 @@ def test_match_hamming_self_consistency(yn, ob):
         assert np.array_equal(scores, full.T[qi, bj])
 
 
+def test_crossmatch_hamming_matches_oracle(yn, ob):
+    # crossmatch_hamming* (yael/hamming.c:310-395, 751-829): pairs i < j of one set, (i, j) order;
+    # sizes straddle the 256-row scan blocks, thresholds from "nothing" to "everything"
+    import ctypes as C
+    r = rs(5)
+    for n, nc in ((1, 8), (2, 8), (257, 8), (1500, 16), (700, 4), (513, 24)):
+        db = r.randint(0, 256, (n, nc)).astype(np.uint8)
+        if n > 10:
+            db[::7] = db[1]
+        for ht in (-1, 0, nc * 3, nc * 8):
+            pairs, scores = yn.crossmatch_hamming(db, ht)
+            m = C.c_size_t(0)
+            ob.oracle().orc_crossmatch_hamming_count(ob.u8p(db), n, ht, nc, C.byref(m))
+            assert len(scores) == m.value
+            if ht == nc * 8:
+                assert m.value == n * (n - 1) // 2
+            widx = np.empty((m.value, 2), np.int32)
+            wham = np.empty(m.value, np.uint16)
+            if m.value:
+                ob.oracle().orc_crossmatch_hamming_prealloc(ob.u8p(db), n, ht, nc, ob.ip(widx), ob.u16p(wham))
+            assert np.array_equal(pairs, widx) and np.array_equal(scores, wham)
+
+
 def test_kmeans_step_teacher_forced(yn, ob):
     r = rs(1234)
     v = r.rand(20000, 32).astype(np.float32)

@@ -121,6 +121,13 @@ def test_hamming_golden(yn):
     assert np.array_equal(pairs, g["match_ht28_idx"]) and np.array_equal(scores, g["match_ht28_ham"])
 
 
+def test_crossmatch_hamming_golden(yn):
+    g = gold("hamming_crossmatch")
+    for nc in (4, 8, 16, 5):
+        pairs, scores = yn.crossmatch_hamming(g["db%d" % nc], int(g["ht%d" % nc]))
+        assert np.array_equal(pairs, g["idx%d" % nc]) and np.array_equal(scores, g["ham%d" % nc])
+
+
 def test_knn_merge_equals_unsharded(yn):
     # the multi-GPU exchange step on one device: G shard results -> merged == single search
     L = yael_b200.lib()

@@ -121,6 +121,26 @@ def test_hamming_golden(ob):
     assert np.array_equal(idx, g["match_ht28_idx"]) and np.array_equal(ham, g["match_ht28_ham"])
 
 
+def test_crossmatch_hamming_golden(ob):
+    # crossmatch_hamming_count / _prealloc of the compiled reference (yael/hamming.c:368-395, 793-829)
+    import ctypes as C
+    g = gold("hamming_crossmatch")
+    for nc in (4, 8, 16, 5):
+        db, ht = g["db%d" % nc], int(g["ht%d" % nc])
+        n = C.c_size_t(0)
+        ob.oracle().orc_crossmatch_hamming_count(ob.u8p(db), len(db), ht, nc, C.byref(n))
+        assert n.value == len(g["ham%d" % nc])
+        idx = np.empty((n.value, 2), np.int32)
+        ham = np.empty(n.value, np.uint16)
+        m = ob.oracle().orc_crossmatch_hamming_prealloc(ob.u8p(db), len(db), ht, nc, ob.ip(idx), ob.u16p(ham))
+        assert m == n.value
+        assert np.array_equal(idx, g["idx%d" % nc]) and np.array_equal(ham, g["ham%d" % nc])
+        # independent check: upper triangle of the unpackbits distance matrix
+        full = np.unpackbits(db[:, None, :] ^ db[None, :, :], axis=2).sum(2)
+        i, j = np.nonzero(np.triu(full <= ht, 1))
+        assert np.array_equal(idx[:, 0], i) and np.array_equal(idx[:, 1], j)
+
+
 def test_nn_hamming_oracle_is_stable_select(ob):
     r = np.random.RandomState(9)
     b = r.randint(0, 256, (3000, 8)).astype(np.uint8)

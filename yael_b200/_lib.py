@@ -75,6 +75,11 @@ DROPIN = {
     "match_hamming_thres": (None, [_u8, _u8, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t,
                                    C.POINTER(_vp), C.POINTER(C.c_size_t)]),
     "match_hamming_thres_prealloc": (C.c_size_t, [_u8, _u8, C.c_int, C.c_int, C.c_int, C.c_int, _i, _u16]),
+    "crossmatch_hamming_count": (None, [_u8, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "crossmatch_hamming": (None, [_u8, C.c_long, C.c_int, C.c_int, C.c_long, C.POINTER(_vp),
+                                  C.POINTER(C.c_size_t)]),
+    "crossmatch_hamming_prealloc": (C.c_size_t, [_u8, C.c_long, C.c_int, C.c_int, _i, _u16]),
+    "compute_hamming_thread": (None, [_u16, _u8, _u8, C.c_int, C.c_int, C.c_int]),
     # include/yael/binheap.h  (reference yael/binheap.h:31-87)
     "fbinheap_new": (_vp, [C.c_int]),
     "fbinheap_sizeof": (C.c_size_t, [C.c_int]),
@@ -150,6 +155,8 @@ DEVICE = {
     "yb_nn_hamming_merge": (C.c_int, [C.c_int] * 3 + [_vp, _vp, _vp, _vp, _vp]),
     "yb_match_hamming_count": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "yb_match_hamming_thres": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "yb_crossmatch_hamming_count": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "yb_crossmatch_hamming": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

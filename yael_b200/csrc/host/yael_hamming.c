@@ -102,3 +102,64 @@ void match_hamming_thres(const uint8 *bs1, const uint8 *bs2, int n1, int n2, int
   *hmptr = hm;
   *nptr = n;
 }
+
+void compute_hamming_thread(uint16 *dis, const uint8 *a, const uint8 *b, int na, int nb,
+                            int ncodes) { /* hamming.c:832-843 */
+  compute_hamming(dis, a, b, na, nb, ncodes);
+}
+
+void crossmatch_hamming_count(const uint8 *dbs, int n, int ht, int ncodes, size_t *nptr) {
+  /* hamming.c:368-395 */
+  ybh_arg a1 = ybh_in(dbs, (size_t)(n > 0 ? n : 0) * ncodes);
+  unsigned long long *cnt = (unsigned long long *)yb_malloc(sizeof(unsigned long long));
+  unsigned long long h = 0;
+  YBH_CHECK(yb_crossmatch_hamming_count((const uint8_t *)a1.dev, n, ht, ncodes, cnt, NULL));
+  YBH_CHECK(yb_d2h(&h, cnt, sizeof(h), NULL));
+  ybh_sync();
+  yb_free(cnt);
+  ybh_finish(&a1, 0);
+  *nptr = (size_t)h;
+}
+
+size_t crossmatch_hamming_prealloc(const uint8 *dbs, long n, int ht, int ncodes, int *idx,
+                                   uint16 *hams) { /* hamming.c:793-829 */
+  size_t m = 0;
+  assert(n <= 0x7fffffffL); /* ids are int in the reference too */
+  crossmatch_hamming_count(dbs, (int)n, ht, ncodes, &m);
+  if (m == 0) return 0;
+  ybh_arg a1 = ybh_in(dbs, (size_t)n * ncodes);
+  ybh_arg oi = ybh_out(idx, sizeof(int) * 2 * m);
+  ybh_arg oh = ybh_out(hams, sizeof(uint16) * m);
+  unsigned long long *cnt = (unsigned long long *)yb_malloc(sizeof(unsigned long long));
+  YBH_CHECK(yb_crossmatch_hamming((const uint8_t *)a1.dev, (int)n, ht, ncodes, (int *)oi.dev,
+                                  (uint16_t *)oh.dev, cnt, NULL));
+  ybh_finish(&oi, 1);
+  ybh_finish(&oh, 1);
+  yb_free(cnt);
+  ybh_finish(&a1, 0);
+  ybh_sync();
+  return m;
+}
+
+void crossmatch_hamming(const uint8 *dbs, long n, int ht, int ncodes, long bufsize,
+                        hammatch_t **hmptr, size_t *nptr) { /* hamming.c:751-790 */
+  (void)bufsize;
+  size_t m = 0;
+  assert(n <= 0x7fffffffL);
+  crossmatch_hamming_count(dbs, (int)n, ht, ncodes, &m);
+  hammatch_t *hm = (hammatch_t *)malloc(sizeof(hammatch_t) * (m ? m : 1));
+  if (m) {
+    int *idx = (int *)malloc(sizeof(int) * 2 * m);
+    uint16 *hams = (uint16 *)malloc(sizeof(uint16) * m);
+    crossmatch_hamming_prealloc(dbs, n, ht, ncodes, idx, hams);
+    for (size_t i = 0; i < m; i++) {
+      hm[i].qid = idx[2 * i];
+      hm[i].bid = idx[2 * i + 1];
+      hm[i].score = hams[i];
+    }
+    free(idx);
+    free(hams);
+  }
+  *hmptr = hm;
+  *nptr = m;
+}

@@ -265,13 +265,15 @@ k_nn_hamming_merge(long nq, int k, int G, const int *__restrict__ ain,
 }
 
 // ------------------------------------------------------------------ threshold matching
-// one CTA per query row i: count / emit base ids j (ascending) with distance <= ht
+// one CTA per query row i: count / emit base ids j (ascending) with distance <= ht.
+// cross != 0: bs2 is the same set and only pairs j > i count (crossmatch_hamming*,
+// yael/hamming.c:310-395, 751-829: i outer, j = i+1.. inner -- the emission order kept here).
 template <int W, bool EMIT>
 __global__ void __launch_bounds__(256)
 k_match_rows(const unsigned long long *__restrict__ bs1, const unsigned long long *__restrict__ bs2,
              long n2, int ht, unsigned long long *__restrict__ row_counts,
              const unsigned long long *__restrict__ row_offsets, int *__restrict__ idx,
-             uint16_t *__restrict__ hams) {
+             uint16_t *__restrict__ hams, int cross) {
   __shared__ int wtot[8];
   __shared__ unsigned long long running;
   const long i = blockIdx.x;
@@ -282,10 +284,10 @@ k_match_rows(const unsigned long long *__restrict__ bs1, const unsigned long lon
   if (tid == 0) running = EMIT ? row_offsets[i] : 0ull;
   unsigned long long local = 0;
   __syncthreads();
-  for (long j0 = 0; j0 < n2; j0 += 256) {
+  for (long j0 = cross ? ((i + 1) & ~255L) : 0L; j0 < n2; j0 += 256) {
     long j = j0 + tid;
     int h = 0x7fffffff;
-    if (j < n2) {
+    if (j < n2 && (!cross || j > i)) {
       h = 0;
 #pragma unroll
       for (int w = 0; w < W; w++) h += __popcll(qc[w] ^ bs2[j * W + w]);
@@ -520,7 +522,7 @@ extern "C" int yb_nn_hamming_merge(int nq, int k, int G, const int *assign_in,
 
 static int match_impl(const uint8_t *bs1, const uint8_t *bs2, int n1, int n2, int ht, int ncodes,
                       int *idx, uint16_t *hams, unsigned long long *count, bool emit,
-                      yb_stream_t s) {
+                      yb_stream_t s, int cross = 0) {
   const int W = words_for(ncodes);
   if (!W) return fail(3, "match_hamming: codes of %d bytes are not supported (max 64)", ncodes);
   Guard g;
@@ -536,17 +538,18 @@ static int match_impl(const uint8_t *bs1, const uint8_t *bs2, int n1, int n2, in
   const unsigned long long *p1, *p2;
   int rc;
   if ((rc = packed_codes(bs1, n1, ncodes, W, c.take<unsigned long long>((size_t)W * n1), &p1, st))) return rc;
-  if ((rc = packed_codes(bs2, n2, ncodes, W, c.take<unsigned long long>((size_t)W * n2), &p2, st))) return rc;
+  if (cross) p2 = p1;
+  else if ((rc = packed_codes(bs2, n2, ncodes, W, c.take<unsigned long long>((size_t)W * n2), &p2, st))) return rc;
   unsigned long long *rc_cnt = c.take<unsigned long long>(n1);
   unsigned long long *rc_off = c.take<unsigned long long>(n1);
   YB_DISPATCH_W(W, (k_match_rows<WW, false><<<n1, 256, 0, st>>>(p1, p2, n2, ht, rc_cnt, nullptr,
-                                                                nullptr, nullptr)));
+                                                                nullptr, nullptr, cross)));
   YB_LAUNCH_CHECK();
   k_scan_u64<<<1, 1024, 0, st>>>(rc_cnt, n1, rc_off, count);
   YB_LAUNCH_CHECK();
   if (emit) {
     YB_DISPATCH_W(W, (k_match_rows<WW, true><<<n1, 256, 0, st>>>(p1, p2, n2, ht, nullptr, rc_off,
-                                                                 idx, hams)));
+                                                                 idx, hams, cross)));
     YB_LAUNCH_CHECK();
   }
   return 0;
@@ -562,6 +565,18 @@ extern "C" int yb_match_hamming_thres(const uint8_t *bs1, const uint8_t *bs2, in
                                        int ht, int ncodes, int *idx, uint16_t *hams,
                                        unsigned long long *count, yb_stream_t s) {
   return match_impl(bs1, bs2, n1, n2, ht, ncodes, idx, hams, count, true, s);
+}
+
+// crossmatch_hamming_count / crossmatch_hamming_prealloc (yael/hamming.c:368-395, 793-829): all
+// pairs i < j of ONE set within ht, emitted as (i, j) in (i, j) order.
+extern "C" int yb_crossmatch_hamming_count(const uint8_t *dbs, int n, int ht, int ncodes,
+                                            unsigned long long *count, yb_stream_t s) {
+  return match_impl(dbs, dbs, n, n, ht, ncodes, nullptr, nullptr, count, false, s, 1);
+}
+
+extern "C" int yb_crossmatch_hamming(const uint8_t *dbs, int n, int ht, int ncodes, int *idx,
+                                      uint16_t *hams, unsigned long long *count, yb_stream_t s) {
+  return match_impl(dbs, dbs, n, n, ht, ncodes, idx, hams, count, true, s, 1);
 }
 
 // Measured ceiling of the popcount pipe: 64-bit xor+popc pair evaluations per second with every

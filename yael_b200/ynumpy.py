@@ -209,3 +209,18 @@ def match_hamming(a, b, ht):
                                            a.shape[0], b.shape[0], ht, a.shape[1], _ip(pairs),
                                            scores.ctypes.data_as(_u16))
     return pairs, scores
+
+
+def crossmatch_hamming(a, ht):
+    """crossmatch_hamming_count + crossmatch_hamming_prealloc (yael/hamming.c:368-395, 793-829):
+    all pairs i < j of ONE code set within ht; returns (pairs[n, 2] as (i, j), scores[n])."""
+    _check_row_uint8(a)
+    _lib.require_gpu()
+    n = C.c_size_t(0)
+    lib().crossmatch_hamming_count(a.ctypes.data_as(_u8), a.shape[0], ht, a.shape[1], C.byref(n))
+    pairs = np.empty((n.value, 2), dtype=np.int32)
+    scores = np.empty(n.value, dtype=np.uint16)
+    if n.value:
+        lib().crossmatch_hamming_prealloc(a.ctypes.data_as(_u8), a.shape[0], ht, a.shape[1],
+                                          _ip(pairs), scores.ctypes.data_as(_u16))
+    return pairs, scores
