@@ -50,7 +50,9 @@ void yb_set_knn_engine(int engine);
 /* phase timing with CUDA events on the launching stream (off by default).  Phases:
  * 0 row norms, 1 tcgen05 TF32 shortlist kernel, 2 shortlist merge-select, 3 exact FP32 re-rank,
  * 4 exact-engine fallback, 5 exact distance slab (k_l2_simt), 6 per-row select (k_kmin_rows),
- * 7 Hamming scan, 8 k-means accumulate (sort + segmented sums), 9 k-means scale */
+ * 7 Hamming popcount scan, 8 k-means accumulate (sort + segmented sums), 9 k-means scale,
+ * 10 / 11 k-NN admission-threshold sampling, 12 Hamming code expansion (+-1 E4M3), 13 Hamming
+ * threshold sampling, 14 Hamming tcgen05 E4M3 pass, 15 Hamming order + certify */
 void yb_prof_enable(int on);
 double yb_prof_ms(int phase, long *count, int reset);
 
@@ -158,6 +160,15 @@ int yb_compute_hamming(uint16_t *dis, const uint8_t *a, const uint8_t *b, int na
  * (distance, id); padding id -1 / distance 0xffff. */
 int yb_nn_hamming(int nq, int nb, int ncodes, int k, const uint8_t *base, const uint8_t *query,
                   int *assign, uint16_t *dis, int id_offset, yb_stream_t s);
+/* engine of yb_nn_hamming: 0 = popcount scan (CUDA cores), 1 = exact E4M3 contraction on the
+ * tensor cores (falls back per query to the scan), -1 = automatic (default; also
+ * YAEL_B200_HAMMING_ENGINE).  yb_last_hamming_engine / _fallbacks describe the last call. */
+void yb_set_hamming_engine(int engine);
+int yb_last_hamming_engine(void);
+long yb_last_hamming_fallbacks(void);
+/* bring-up / tests: raw scores of the E4M3 pass, scores[q][n] = 4 * hamming(query q, base n) */
+int yb_debug_hamming_tc_scores(int nq, int nb, int ncodes, const uint8_t *base,
+                               const uint8_t *query, float *scores, yb_stream_t s);
 int yb_nn_hamming_merge(int nq, int k, int G, const int *assign_in, const uint16_t *dis_in,
                         int *assign_out, uint16_t *dis_out, yb_stream_t s);
 /* micro-benchmark: measured 64-bit xor+popcount pair rate of the whole GPU (the ceiling the

@@ -392,7 +392,9 @@ static int words_for(int ncodes) {
 // codes as W-word rows: the caller's buffer when it already has that shape, else a repack
 static int packed_codes(const uint8_t *src, long n, int ncodes, int W, unsigned long long *tmp,
                         const unsigned long long **out, cudaStream_t st) {
-  if (ncodes == W * 8 && (((uintptr_t)src) & 7) == 0) {
+  const bool force = W < 0;  // always repack (the caller wants its own aligned copy)
+  if (force) W = -W;
+  if (!force && ncodes == W * 8 && (((uintptr_t)src) & 7) == 0) {
     *out = (const unsigned long long *)src;
     return 0;
   }
@@ -439,15 +441,10 @@ extern "C" int yb_compute_hamming(uint16_t *dis, const uint8_t *a, const uint8_t
   return 0;
 }
 
-extern "C" int yb_nn_hamming(int nq, int nb, int ncodes, int k, const uint8_t *base,
-                              const uint8_t *query, int *assign, uint16_t *dis, int id_offset,
-                              yb_stream_t s) {
-  if (nq <= 0) return 0;
-  if (k <= 0 || k > nb) return fail(3, "nn_hamming: need 0 < k <= nb (k=%d, nb=%d)", k, nb);
-  const int W = words_for(ncodes);
-  if (!W) return fail(3, "nn_hamming: codes of %d bytes are not supported (max 64)", ncodes);
-  Guard g;
-  cudaStream_t st = stream_of(s);
+// engine 0: the popcount scan (caller holds the Guard)
+static int nn_hamming_popc(int nq, int nb, int ncodes, int W, int k, const uint8_t *base,
+                           const uint8_t *query, int *assign, uint16_t *dis, int id_offset,
+                           cudaStream_t st) {
   const int gx = (nq + HQT * HT - 1) / (HQT * HT);
   // splits: every CTA of the grid is resident at once (up to 7 per SM: 32 KB of shared memory
   // each) and all CTAs cost the same, so the pass lasts as long as the fullest SM: pick the
@@ -503,6 +500,114 @@ extern "C" int yb_nn_hamming(int nq, int nb, int ncodes, int k, const uint8_t *b
                                                      m_pad);
   YB_LAUNCH_CHECK();
   return 0;
+}
+
+// gather / scatter of the queries the tensor path could not certify
+__global__ void k_ham_gather_codes(const uint8_t *__restrict__ src, const int *__restrict__ rows,
+                                   long n, int ncodes, uint8_t *__restrict__ dst) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n * ncodes) dst[t] = src[(size_t)rows[t / ncodes] * ncodes + t % ncodes];
+}
+__global__ void k_ham_scatter(const int *__restrict__ rows, long n, int k,
+                              const int *__restrict__ a_src, const uint16_t *__restrict__ d_src,
+                              int *__restrict__ a_dst, uint16_t *__restrict__ d_dst) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n * k) {
+    const size_t o = (size_t)rows[t / k] * k + t % k;
+    a_dst[o] = a_src[t];
+    d_dst[o] = d_src[t];
+  }
+}
+
+static int g_ham_force = -1;
+static int g_ham_last_engine = 0;
+static long g_ham_last_fallbacks = 0;
+
+static int ham_engine_choice() {
+  if (g_ham_force >= 0) return g_ham_force;
+  if (const char *e = getenv("YAEL_B200_HAMMING_ENGINE")) return atoi(e);
+  return -1;
+}
+
+extern "C" void yb_set_hamming_engine(int engine) { g_ham_force = engine; }
+extern "C" int yb_last_hamming_engine(void) { return g_ham_last_engine; }
+extern "C" long yb_last_hamming_fallbacks(void) { return g_ham_last_fallbacks; }
+
+extern "C" int yb_nn_hamming(int nq, int nb, int ncodes, int k, const uint8_t *base,
+                              const uint8_t *query, int *assign, uint16_t *dis, int id_offset,
+                              yb_stream_t s) {
+  if (nq <= 0) return 0;
+  if (k <= 0 || k > nb) return fail(3, "nn_hamming: need 0 < k <= nb (k=%d, nb=%d)", k, nb);
+  const int W = words_for(ncodes);
+  if (!W) return fail(3, "nn_hamming: codes of %d bytes are not supported (max 64)", ncodes);
+  Guard g;
+  cudaStream_t st = stream_of(s);
+  g_ham_last_engine = 0;
+  g_ham_last_fallbacks = 0;
+  // engine 1 (tensor cores) pays off once the scan is compute bound: at least a few tiles of
+  // queries against at least 128 database tiles; k <= 384 (list capacity of the fused epilogue)
+  const int choice = ham_engine_choice();
+  const bool want_tc = choice == 1 || (choice < 0 && nq >= 256 && nb >= 32768 && (double)nq * nb >= 2e8);
+  if (want_tc && hamming_tc_supported(nq, nb, W, k)) {
+    int *flag_list = nullptr;
+    int n_flag = 0;
+    int rc;
+    {
+      // packed copies when the caller's codes are not already W aligned words per row
+      const bool bp = !(ncodes == W * 8 && (((uintptr_t)base) & 15) == 0);
+      const bool qp = !(ncodes == W * 8 && (((uintptr_t)query) & 15) == 0);
+      unsigned long long *tb = bp ? (unsigned long long *)yb_malloc(8ull * W * nb) : nullptr;
+      unsigned long long *tq = qp ? (unsigned long long *)yb_malloc(8ull * W * nq) : nullptr;
+      const unsigned long long *pb = (const unsigned long long *)base, *pq = (const unsigned long long *)query;
+      if (bp && (rc = packed_codes(base, nb, ncodes, -W, tb, &pb, st))) return rc;
+      if (qp && (rc = packed_codes(query, nq, ncodes, -W, tq, &pq, st))) return rc;
+      rc = hamming_tc(nq, nb, W, k, pb, pq, assign, dis, id_offset, &flag_list, &n_flag, st);
+      if (tb) yb_free(tb);
+      if (tq) yb_free(tq);
+    }
+    if (rc == 0) {
+      g_ham_last_engine = 1;
+      g_ham_last_fallbacks = n_flag;
+      if (n_flag > 0) {  // the uncertified queries go through the scan
+        uint8_t *qsub = (uint8_t *)yb_malloc((size_t)n_flag * ncodes);
+        int *asub = (int *)yb_malloc(sizeof(int) * (size_t)n_flag * k);
+        uint16_t *dsub = (uint16_t *)yb_malloc(sizeof(uint16_t) * (size_t)n_flag * k);
+        long tot = (long)n_flag * ncodes;
+        k_ham_gather_codes<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(query, flag_list, n_flag, ncodes, qsub);
+        count_launch();
+        rc = nn_hamming_popc(n_flag, nb, ncodes, W, k, base, qsub, asub, dsub, id_offset, st);
+        if (!rc) {
+          tot = (long)n_flag * k;
+          k_ham_scatter<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(flag_list, n_flag, k, asub, dsub, assign, dis);
+          count_launch();
+          cudaStreamSynchronize(st);  // the pooled blocks below are reused by later calls
+        }
+        yb_free(qsub); yb_free(asub); yb_free(dsub); yb_free(flag_list);
+      }
+      return rc;
+    }
+    if (rc != -1000) return rc;
+  }
+  return nn_hamming_popc(nq, nb, ncodes, W, k, base, query, assign, dis, id_offset, st);
+}
+
+extern "C" int yb_debug_hamming_tc_scores(int nq, int nb, int ncodes, const uint8_t *base,
+                                           const uint8_t *query, float *scores, yb_stream_t s) {
+  const int W = words_for(ncodes);
+  if (!W || nq <= 0 || nb <= 0) return fail(3, "hamming_tc_scores: unsupported shape");
+  Guard g;
+  cudaStream_t st = stream_of(s);
+  unsigned long long *tb = (unsigned long long *)yb_malloc(8ull * W * nb);
+  unsigned long long *tq = (unsigned long long *)yb_malloc(8ull * W * nq);
+  const unsigned long long *pb, *pq;
+  int rc;
+  if ((rc = packed_codes(base, nb, ncodes, -W, tb, &pb, st))) return rc;
+  if ((rc = packed_codes(query, nq, ncodes, -W, tq, &pq, st))) return rc;
+  rc = hamming_tc_scores(nq, nb, W, pb, pq, scores, st);
+  cudaStreamSynchronize(st);
+  yb_free(tb);
+  yb_free(tq);
+  return rc;
 }
 
 extern "C" int yb_nn_hamming_merge(int nq, int k, int G, const int *assign_in,

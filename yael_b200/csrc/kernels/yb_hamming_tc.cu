@@ -1,0 +1,292 @@
+// yb_hamming_tc.cu -- nn_hamming on the tensor cores (engine 1 of yb_nn_hamming).
+//
+// At the BASELINE shape (10^4 queries x 10^7 codes) the popcount scan of yb_hamming.cu is bound
+// by the POPC pipe (16 / clk / SM), not by HBM: 10^11 pairs cost >= 43 ms however the codes are
+// loaded.  The same distances are an exact dense contraction: write every bit as +-1,
+//     <q, b> = (#equal bits) - (#different bits) = bits - 2 * ham(q, b),
+// so with |b|^2 replaced by the constant 2 * bits the score of the distance GEMM kernel
+// (yb_knn_tf32.cu: s = |b|^2 - 2 <q, b>) is  s = 4 * ham(q, b)  -- and with E4M3 operands
+// (+1.0 = 0x38, -1.0 = 0xB8; tcgen05.mma kind::f8f6f4, FP32 accumulation) every product and
+// every partial sum is a small integer, i.e. the result is EXACT, not approximate.  The pass
+// therefore needs no re-rank: it reuses the fused threshold/top-k epilogue of k_knn_tf32 and a
+// finishing kernel orders the admitted (distance, id) pairs and certifies them:
+//
+//   every row that is not in a list has score >= T (the smallest list threshold); the k best
+//   listed pairs are the answer iff the k-th of them has score < T.  Scores are integers and
+//   ties are ordered by id, so this is bit-exact against compute_hamming + stable selection
+//   (yael/hamming.c:177-219; oracle orc_nn_hamming).  Queries that fail the test (lists that
+//   had to drop ties, adversarial row order) are re-done by the popcount scan.
+//
+// Work: 2 MMAs (K = 32 each) per 128 x 256 tile for 64-bit codes, so the pass is bound by the
+// epilogue (one FFMA + one FMNMX per pair instead of 2 POPC + xor/add/compare).
+#include <stdlib.h>
+
+#include "yb_common.cuh"
+#include "yb_internal.cuh"
+
+namespace yb {
+
+// ------------------------------------------------------------------ operand expansion
+// one thread per 16 bits -> 16 E4M3 bytes (one 128-bit store); element i of a row is bit i
+__global__ void __launch_bounds__(256)
+k_ham_expand(const unsigned long long *__restrict__ codes, long nwords, uint4 *__restrict__ out) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nwords * 4) return;
+  const unsigned bits = (unsigned)(codes[t >> 2] >> (16 * (int)(t & 3))) & 0xffffu;
+  auto four = [](unsigned x) {  // 4 bits -> 4 bytes: 0xB8 (-1.0) with the sign cleared where the bit is set
+    const unsigned spread = (x & 1u) | ((x & 2u) << 7) | ((x & 4u) << 14) | ((x & 8u) << 21);
+    return 0xB8B8B8B8u ^ (spread << 7);
+  };
+  uint4 o;
+  o.x = four(bits & 15u);
+  o.y = four((bits >> 4) & 15u);
+  o.z = four((bits >> 8) & 15u);
+  o.w = four((bits >> 12) & 15u);
+  out[t] = o;
+}
+
+__global__ void k_thr_bump(float *__restrict__ thr, int n, float add) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) thr[i] += add;  // +inf stays +inf
+}
+
+__global__ void k_ham_collect(const int *__restrict__ flags, int nq, int *list, int *count) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nq && flags[q]) list[atomicAdd(count, 1)] = q;
+}
+
+// ------------------------------------------------------------------ finish: order + certify
+// One CTA per query: gather the entries of its lists as (distance << 32 | row) keys, sort them,
+// emit the k smallest and flag the query when they are not provably the answer.
+constexpr int HF_T = 256;
+constexpr int HF_CAP = 8192;      // keys per query held in shared memory (64 KB)
+constexpr int HF_LISTS = 1024;    // lists per query
+
+__global__ void __launch_bounds__(HF_T)
+k_ham_tc_finish(int nq, int k, int lists, int kp, const int *__restrict__ cnt,
+                const float *__restrict__ score, const int *__restrict__ id,
+                const float *__restrict__ lthr, int id_offset, int *__restrict__ assign,
+                uint16_t *__restrict__ dis, int *__restrict__ flags) {
+  extern __shared__ unsigned long long keys[];
+  __shared__ int loff[HF_LISTS + 1];
+  __shared__ float lthr_s[HF_LISTS];
+  __shared__ float tmin_s;
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int *qcnt = cnt + (size_t)q * lists;
+  for (int l = tid; l < lists; l += HF_T) {
+    loff[l + 1] = qcnt[l];
+    lthr_s[l] = lthr[(size_t)q * lists + l];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    float t = __uint_as_float(0x7f800000u);
+    for (int l = 0; l < lists; l++) {
+      const int c = loff[l + 1];
+      loff[l] = acc;
+      acc += c;
+      t = fminf(t, lthr_s[l]);
+    }
+    loff[lists] = acc;
+    tmin_s = t;
+  }
+  __syncthreads();
+  const int total = loff[lists];
+  if (total > HF_CAP || total < k) {  // uniform over the CTA
+    if (tid == 0) flags[q] = 1;
+    return;
+  }
+  int m_pad = 2;
+  while (m_pad < total) m_pad <<= 1;
+  for (int l = warp; l < lists; l += HF_T / 32) {
+    const int o = loff[l], n = loff[l + 1] - o;
+    const size_t src = ((size_t)q * lists + l) * kp;
+    for (int e = lane; e < n; e += 32) {
+      const unsigned dist = (unsigned)__float2int_rn(score[src + e] * 0.25f);
+      keys[o + e] = ((unsigned long long)dist << 32) | (unsigned)id[src + e];
+    }
+  }
+  for (int e = total + tid; e < m_pad; e += HF_T) keys[e] = ~0ull;
+  bitonic_sort_u64(keys, m_pad, tid, HF_T, [] { __syncthreads(); });
+  // certificate: every unlisted row has score >= tmin, the k-th listed one must be below it
+  const float sk = 4.0f * (float)(unsigned)(keys[k - 1] >> 32);
+  const bool ok = sk < tmin_s;
+  if (tid == 0) flags[q] = ok ? 0 : 1;
+  if (!ok) return;
+  for (int j = tid; j < k; j += HF_T) {
+    const unsigned long long v = keys[j];
+    assign[(size_t)q * k + j] = (int)(unsigned)v + id_offset;
+    dis[(size_t)q * k + j] = (uint16_t)(v >> 32);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+static int expand_codes(const unsigned long long *codes, long n, int W, void *out, cudaStream_t st) {
+  const long threads = n * W * 4;
+  if (threads <= 0) return 0;
+  k_ham_expand<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(codes, n * W, (uint4 *)out);
+  YB_LAUNCH_CHECK();
+  return 0;
+}
+
+// sampling geometry: every `stride`-th tile is scored once, the minima of runs of `gsize` columns
+// are kept (at most row_kth_max_n() of them per query), the j2-th smallest of those is the
+// admission threshold -- about j2 * stride rows of the whole database are at or below it
+struct HamSample {
+  int ok, stride, nbt_s, gsize, j2;
+  long gcols;
+};
+static HamSample ham_sample_geometry(int nbt, int k) {
+  HamSample s = {};
+  if (nbt < 128) return s;
+  const int maxn = row_kth_max_n();
+  s.stride = (nbt + 2047) / 2048;
+  if (s.stride < 16) s.stride = 16;
+  s.nbt_s = (nbt + s.stride - 1) / s.stride;
+  const long srows = (long)s.nbt_s * 256;
+  s.gsize = 16;
+  while (s.gsize < 128 && srows / s.gsize > maxn) s.gsize *= 2;
+  s.gcols = srows / s.gsize;
+  s.j2 = (3 * k + s.stride - 1) / s.stride;
+  if (s.j2 < 32) s.j2 = 32;
+  s.ok = s.gcols <= maxn && (long)s.j2 * 4 <= s.gcols;
+  return s;
+}
+
+bool hamming_tc_supported(int nq, int nb, int W, int k) {
+  if (W < 1 || W > 8 || nq < 1 || nb < 1 || k < 1 || k > nb) return false;
+  Tf32Plan plan = tf32_plan(nq, nb, 16 * W, k);
+  return plan.ok && !plan.pair && plan.lists <= HF_LISTS;
+}
+
+// pb / pq: codes packed as W 64-bit words per row.  Results for every query whose certificate
+// holds are written to assign / dis; the others are listed in flag_list_out (device memory from
+// yb_malloc, owned by the caller when *n_flag_out > 0).  Returns -1000 when the shape does not
+// qualify.
+int hamming_tc(int nq, int nb, int W, int k, const unsigned long long *pb,
+               const unsigned long long *pq, int *assign, uint16_t *dis, int id_offset,
+               int **flag_list_out, int *n_flag_out, cudaStream_t st) {
+  *flag_list_out = nullptr;
+  *n_flag_out = 0;
+  if (!hamming_tc_supported(nq, nb, W, k)) return -1000;
+  const int dfl = 16 * W;       // row pitch in floats (64 * W one-byte elements)
+  const int bits = 64 * W;
+  Tf32Plan plan = tf32_plan(nq, nb, dfl, k);
+  plan.f8 = 1;
+  const int kp = plan.kprime;
+  const int nbt = tf32_tiles(nb);
+  const long padded = tf32_padded_rows(nb);
+  const HamSample sg = ham_sample_geometry(nbt, k);
+  Tf32Plan splan = {};
+  if (sg.ok) {
+    splan = tf32_plan_tiles(nq, sg.nbt_s, dfl, sg.j2);
+    splan.f8 = 1;
+  }
+  const bool sample = sg.ok && splan.ok && !splan.pair;
+  const size_t stride = (size_t)plan.lists * kp;
+  size_t need = Carver::need(64ull * W * nb) + Carver::need(64ull * W * nq) +
+                Carver::need(sizeof(float) * (size_t)padded) +
+                Carver::need(sizeof(float) * nq * stride) + Carver::need(sizeof(int) * nq * stride) +
+                2 * Carver::need(sizeof(float) * (size_t)nq * plan.lists) +
+                3 * Carver::need(sizeof(int) * (size_t)nq) + Carver::need(64) +
+                Carver::need(plan.ws_bytes) + 1024;
+  if (sample)
+    need += Carver::need(sizeof(float) * (size_t)nq * sg.gcols) + Carver::need(splan.ws_bytes);
+  int n_flag = 0;
+  {
+    ScratchScope ws(need, st);
+    Carver c(ws.p);
+    void *base8 = c.take<char>(64ull * W * nb);
+    void *query8 = c.take<char>(64ull * W * nq);
+    float *an = c.take<float>(padded);
+    float *cscore = c.take<float>(nq * stride);
+    int *cid = c.take<int>(nq * stride);
+    float *cthr = c.take<float>((size_t)nq * plan.lists);
+    int *ccnt = c.take<int>((size_t)nq * plan.lists);
+    float *thr_init = c.take<float>(nq);
+    int *flags = c.take<int>(nq);
+    int *flag_list = c.take<int>(nq);
+    int *flag_count = c.take<int>(16);
+    void *tfws = c.take<char>(plan.ws_bytes);
+    int rc;
+    {
+      ProfScope ps(12, st);
+      if ((rc = expand_codes(pb, nb, W, base8, st))) return rc;
+      if ((rc = expand_codes(pq, nq, W, query8, st))) return rc;
+      if ((rc = fill_f32(an, nb, 2.0f * (float)bits, st))) return rc;
+      if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
+      YB_CUDA(cudaMemsetAsync(flag_count, 0, 64, st));
+    }
+    const float *thr0 = nullptr;
+    if (sample) {
+      ProfScope ps(13, st);
+      float *gm = c.take<float>((size_t)nq * sg.gcols);
+      void *stfws = c.take<char>(splan.ws_bytes);
+      if ((rc = tf32_group_min(splan, nq, nb, dfl, sg.nbt_s, sg.stride, (const float *)base8,
+                               (const float *)query8, an, gm, sg.gcols, sg.gsize, stfws, st)))
+        return rc;
+      if ((rc = row_kth(gm, sg.gcols, nq, (int)sg.gcols, sg.j2, thr_init, st))) return rc;
+      // scores are multiples of 4: admit the ties AT the order statistic as well
+      k_thr_bump<<<(nq + 255) / 256, 256, 0, st>>>(thr_init, nq, 2.0f);
+      YB_LAUNCH_CHECK();
+      thr0 = thr_init;
+    }
+    {
+      ProfScope ps(14, st);
+      Tf32Out mo = {ccnt, 0, 0, 0};
+      if ((rc = tf32_shortlist(plan, nq, nb, dfl, nbt, 1, (const float *)base8, (const float *)query8,
+                               an, thr0, cscore, cid, cthr, tfws, st, &mo)))
+        return rc;
+    }
+    {
+      ProfScope ps(15, st);
+      static bool attr = false;
+      if (!attr) {
+        YB_CUDA(cudaFuncSetAttribute(k_ham_tc_finish, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     HF_CAP * 8));
+        attr = true;
+      }
+      k_ham_tc_finish<<<nq, HF_T, HF_CAP * 8, st>>>(nq, k, plan.lists, kp, ccnt, cscore, cid, cthr,
+                                                    id_offset, assign, dis, flags);
+      YB_LAUNCH_CHECK();
+      k_ham_collect<<<(nq + 255) / 256, 256, 0, st>>>(flags, nq, flag_list, flag_count);
+      YB_LAUNCH_CHECK();
+    }
+    YB_CUDA(cudaMemcpyAsync(&n_flag, flag_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    YB_CUDA(cudaStreamSynchronize(st));
+    if (n_flag > 0) {
+      int *keep = (int *)yb_malloc(sizeof(int) * (size_t)n_flag);
+      YB_CUDA(cudaMemcpyAsync(keep, flag_list, sizeof(int) * (size_t)n_flag, cudaMemcpyDeviceToDevice, st));
+      *flag_list_out = keep;
+    }
+  }
+  *n_flag_out = n_flag;
+  return 0;
+}
+
+// raw scores of the E4M3 pass, s[q][n] = 4 * ham(q, n), for tests and bring-up
+int hamming_tc_scores(int nq, int nb, int W, const unsigned long long *pb,
+                      const unsigned long long *pq, float *scores, cudaStream_t st) {
+  const int dfl = 16 * W;
+  Tf32Plan plan = tf32_plan(nq, nb, dfl, 1);
+  if (!plan.ok || plan.pair) return fail(3, "hamming tensor path does not support this shape");
+  plan.f8 = 1;
+  const long padded = tf32_padded_rows(nb);
+  ScratchScope ws(Carver::need(64ull * W * nb) + Carver::need(64ull * W * nq) +
+                      Carver::need(4ull * padded) + Carver::need(plan.ws_bytes),
+                  st);
+  Carver c(ws.p);
+  void *base8 = c.take<char>(64ull * W * nb);
+  void *query8 = c.take<char>(64ull * W * nq);
+  float *an = c.take<float>(padded);
+  void *tfws = c.take<char>(plan.ws_bytes);
+  int rc;
+  if ((rc = expand_codes(pb, nb, W, base8, st))) return rc;
+  if ((rc = expand_codes(pq, nq, W, query8, st))) return rc;
+  if ((rc = fill_f32(an, nb, 128.0f * (float)W, st))) return rc;
+  if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
+  return tf32_scores(plan, nq, nb, dfl, tf32_tiles(nb), 1, (const float *)base8,
+                     (const float *)query8, an, scores, nb, tfws, st);
+}
+
+}  // namespace yb

@@ -28,6 +28,8 @@ struct Tf32Plan {
   int ctas;        // persistent grid size
   int pair;        // CTAs launched as clusters of 2 sharing the database stream
   size_t ws_bytes; // workspace for buffers + shortlists
+  int f8;          // operands are E4M3 bytes (kind::f8f6f4) instead of floats (kind::tf32): `base`
+                   // and `query` then point to [rows][4*d] BYTE matrices (the Hamming path)
 };
 Tf32Plan tf32_plan(int nq, int nb, int d, int k);
 Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kprime);
@@ -66,6 +68,18 @@ Tf32Plan tf32_plan_nearest(int nq, int nb, int d);
 int tf32_nearest(const Tf32Plan &plan, int nq, int nb, int d, const float *base, const float *query,
                  const float *bnorm_padded, const float *k1_margin, float *out_score, int *out_id,
                  float *out_thr, void *ws, cudaStream_t st);
+// yb_knn.cu: thr[r] = the j-th smallest of vals[r][0..n) for nrow rows (n <= row_kth_max_n())
+int row_kth(const float *vals, long ld, int nrow, int n, int j, float *thr, cudaStream_t st);
+int row_kth_max_n();
+
+// yb_hamming_tc.cu: nn_hamming as an exact E4M3 contraction on the tensor cores
+bool hamming_tc_supported(int nq, int nb, int W, int k);
+int hamming_tc(int nq, int nb, int W, int k, const unsigned long long *pb,
+               const unsigned long long *pq, int *assign, uint16_t *dis, int id_offset,
+               int **flag_list_out, int *n_flag_out, cudaStream_t st);
+int hamming_tc_scores(int nq, int nb, int W, const unsigned long long *pb,
+                      const unsigned long long *pq, float *scores, cudaStream_t st);
+
 long tf32_padded_rows(int nb);
 int tf32_tiles(int nb);
 int fill_f32(float *p, long n, float v, cudaStream_t st);

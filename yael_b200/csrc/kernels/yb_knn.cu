@@ -643,6 +643,15 @@ k_row_kth(const float *__restrict__ vals, long ld, int n, int j, float *__restri
   if (tid == 0) thr[q] = __uint_as_float((prefix & 0x80000000u) ? (prefix & 0x7fffffffu) : ~prefix);
 }
 
+int row_kth_max_n() { return RK_T * RK_PER; }
+int row_kth(const float *vals, long ld, int nrow, int n, int j, float *thr, cudaStream_t st) {
+  if (nrow <= 0) return 0;
+  if (n > RK_T * RK_PER) return fail(3, "row_kth: %d values per row exceed %d", n, RK_T * RK_PER);
+  k_row_kth<<<nrow, RK_T, 0, st>>>(vals, ld, n, j, thr);
+  YB_LAUNCH_CHECK();
+  return 0;
+}
+
 // TF32 operands keep 10 explicit mantissa bits; the hardware drops (or rounds) the rest, so
 // each operand carries a relative error < 2^-10 and each product < 2^-9 (+2^-20); with
 // Cauchy-Schwarz the score |b|^2 - 2<q,b> is off by at most 2 * 2^-9 * |q||b|.  5 % head

@@ -173,6 +173,21 @@ __device__ __forceinline__ void tc_mma_tf32_elect(uint32_t d_tmem, uint64_t a_de
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f8f6f4 with E4M3 operands (one byte per element, K = 32 per instruction, FP32
+// accumulate): the Hamming path feeds it +-1.0 (0x38 / 0xB8), for which every product and every
+// partial sum is an exactly representable integer.
+__device__ __forceinline__ void tc_mma_f8_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
   asm volatile(
       "{\n\t"
@@ -235,6 +250,20 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 // instruction descriptor, kind::tf32: D=F32, A=B=TF32, both K-major, N=256, M=128
 constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) |
                                 ((uint32_t)(TM >> 4) << 24);
+
+// instruction descriptor, kind::f8f6f4: D=F32, A=B=E4M3 (format 0), both K-major, N=256, M=128
+constexpr uint32_t IDESC_F8 = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+// the operand kind is a template parameter of the kernel: the issue loop of the TF32
+// instantiations is unchanged by the existence of the FP8 ones
+template <bool F8>
+__device__ __forceinline__ void tc_mma_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                             uint32_t accumulate) {
+  if (F8)
+    tc_mma_f8_elect(d_tmem, a_desc, b_desc, IDESC_F8, accumulate);
+  else
+    tc_mma_tf32_elect(d_tmem, a_desc, b_desc, IDESC_TF32, accumulate);
+}
 
 // ------------------------------------------------------------------ parameters
 struct Tf32Params {
@@ -719,7 +748,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int MODE>
+template <int MODE, bool F8>
 __global__ void __launch_bounds__(TF32_THREADS, 1)
 k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_b,
            const __grid_constant__ CUtensorMap map_bh, const Tf32Params P) {
@@ -777,6 +806,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 
   if (warp == EPI_WARPS) {
     // ======================================================================== TMA producer
+    constexpr int KCE = F8 ? KC * 4 : KC;  // elements per 128-byte K chunk (TMA coordinates)
     if (lane == 0) {
       uint32_t icount = 0, ccount = 0, tcount = 0;
       for (int item = first_item; item < P.items; item += item_step, icount++) {
@@ -787,7 +817,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         mbar_wait(bar(Smem::a_empty), (icount & 1) ^ 1);
         mbar_expect_tx(bar(Smem::a_full), (uint32_t)(P.nkc * A_CHUNK_BYTES));
         for (int kc = 0; kc < P.nkc; kc++)
-          tma_load_2d(sbase + Smem::a_off + kc * A_CHUNK_BYTES, &map_q, bar(Smem::a_full), kc * KC,
+          tma_load_2d(sbase + Smem::a_off + kc * A_CHUNK_BYTES, &map_q, bar(Smem::a_full), kc * KCE,
                       qt * TM);
         for (int jt = jt0; jt < jt1; jt++, tcount++) {
           const uint32_t slot = tcount % NBN;
@@ -807,11 +837,11 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
             if (P.pair) {
               // my half of the chunk (128 rows), delivered to both CTAs of the cluster
               tma_load_2d_mc(sbase + Smem::b_off + st * B_CHUNK_BYTES + crank * (B_CHUNK_BYTES / 2),
-                             &map_bh, bar(Smem::b_full + st), kc * KC,
+                             &map_bh, bar(Smem::b_full + st), kc * KCE,
                              jta * TN + (int)crank * (TN / 2), (uint16_t)3);
             } else {
               tma_load_2d(sbase + Smem::b_off + st * B_CHUNK_BYTES, &map_b, bar(Smem::b_full + st),
-                          kc * KC, jta * TN);
+                          kc * KCE, jta * TN);
             }
           }
         }
@@ -842,10 +872,10 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
               tc_fence_after();
               const uint64_t adesc = smem_desc_sw128(sbase + Smem::a_off + kc * A_CHUNK_BYTES);
               const uint64_t bdesc = smem_desc_sw128(sbase + Smem::b_off + kc * B_CHUNK_BYTES);
-              tc_mma_tf32_elect(d_tmem, adesc, bdesc, IDESC_TF32, kc != 0);
-              tc_mma_tf32_elect(d_tmem, adesc + 2, bdesc + 2, IDESC_TF32, 1);
-              tc_mma_tf32_elect(d_tmem, adesc + 4, bdesc + 4, IDESC_TF32, 1);
-              tc_mma_tf32_elect(d_tmem, adesc + 6, bdesc + 6, IDESC_TF32, 1);
+              tc_mma_elect<F8>(d_tmem, adesc, bdesc, kc != 0);
+              tc_mma_elect<F8>(d_tmem, adesc + 2, bdesc + 2, 1);
+              tc_mma_elect<F8>(d_tmem, adesc + 4, bdesc + 4, 1);
+              tc_mma_elect<F8>(d_tmem, adesc + 6, bdesc + 6, 1);
               if (P.pair)
                 tc_commit_mc_elect(bar(Smem::b_empty + kc), (uint16_t)3);
               else
@@ -862,14 +892,14 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
             // advancing K inside the 128-byte swizzle span: +32 bytes = +2 in 16-byte units
             if (!skip_mma) {
               if (kc != P.nkc - 1 || P.last_k8 == 4) {
-                tc_mma_tf32_elect(d_tmem, adesc, bdesc, IDESC_TF32, kc != 0);
-                tc_mma_tf32_elect(d_tmem, adesc + 2, bdesc + 2, IDESC_TF32, 1);
-                tc_mma_tf32_elect(d_tmem, adesc + 4, bdesc + 4, IDESC_TF32, 1);
-                tc_mma_tf32_elect(d_tmem, adesc + 6, bdesc + 6, IDESC_TF32, 1);
+                tc_mma_elect<F8>(d_tmem, adesc, bdesc, kc != 0);
+                tc_mma_elect<F8>(d_tmem, adesc + 2, bdesc + 2, 1);
+                tc_mma_elect<F8>(d_tmem, adesc + 4, bdesc + 4, 1);
+                tc_mma_elect<F8>(d_tmem, adesc + 6, bdesc + 6, 1);
               } else {
                 for (int k8 = 0; k8 < P.last_k8; k8++)
-                  tc_mma_tf32_elect(d_tmem, adesc + (uint64_t)(2 * k8), bdesc + (uint64_t)(2 * k8),
-                                    IDESC_TF32, (kc | k8) != 0);
+                  tc_mma_elect<F8>(d_tmem, adesc + (uint64_t)(2 * k8), bdesc + (uint64_t)(2 * k8),
+                                   (kc | k8) != 0);
               }
             }
             // smem slot reusable once these MMAs retire (paired: tell both CTAs, either may
@@ -934,6 +964,23 @@ static int make_map(CUtensorMap *m, const float *ptr, long rows, int d, int box_
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(6, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+  return 0;
+}
+
+// the same over a row-major [rows][pitch] byte matrix (E4M3 operands of the Hamming path):
+// box = 128 bytes x box_rows; `pitch` (bytes per row, a multiple of 16) may be smaller than the
+// box, the rest of the 128-byte span then reads as zero
+static int make_map_u8(CUtensorMap *m, const void *ptr, long rows, int pitch, int box_rows) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return fail(6, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch};
+  cuuint32_t box[2] = {(cuuint32_t)(KC * 4), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(6, "cuTensorMapEncodeTiled (u8) failed with code %d", (int)r);
   return 0;
 }
 
@@ -1002,12 +1049,12 @@ Tf32Plan tf32_plan(int nq, int nb, int d, int k) {
   return tf32_plan_tiles(nq, (nb + TN - 1) / TN, d, tf32_kprime_for(k));
 }
 
-template <int MODE>
+template <int MODE, bool F8 = false>
 static int launch_mode(const Tf32Plan &plan, const CUtensorMap &mq, const CUtensorMap &mb,
                        const CUtensorMap &mbh, const Tf32Params &P, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_knn_tf32<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_knn_tf32<MODE, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          TF32_SMEM_BYTES);
     if (e != cudaSuccess) return fail(6, "cannot reserve %d bytes of shared memory: %s",
                                       TF32_SMEM_BYTES, cudaGetErrorString(e));
@@ -1026,11 +1073,11 @@ static int launch_mode(const Tf32Plan &plan, const CUtensorMap &mq, const CUtens
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_knn_tf32<MODE>, mq, mb, mbh, P);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_knn_tf32<MODE, F8>, mq, mb, mbh, P);
     if (e != cudaSuccess) return fail(2, "k_knn_tf32 cluster launch: %s", cudaGetErrorString(e));
     count_launch();
   } else {
-    k_knn_tf32<MODE><<<plan.ctas, TF32_THREADS, TF32_SMEM_BYTES, st>>>(mq, mb, mbh, P);
+    k_knn_tf32<MODE, F8><<<plan.ctas, TF32_THREADS, TF32_SMEM_BYTES, st>>>(mq, mb, mbh, P);
     YB_LAUNCH_CHECK();
   }
   return 0;
@@ -1045,13 +1092,24 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
     return fail(6, "tf32 path needs 16-byte aligned matrices");
   CUtensorMap mq, mb, mbh;
   int rc;
-  if ((rc = make_map(&mq, query, nq, d, TM))) return rc;
-  if ((rc = make_map(&mb, base, nb, d, TN))) return rc;
-  if ((rc = make_map(&mbh, base, nb, d, TN / 2))) return rc;
   Tf32Params P = {};
   P.nq = nq; P.nb = nb; P.d = d;
-  P.nkc = (d + KC - 1) / KC;
-  P.last_k8 = (d - (P.nkc - 1) * KC + 7) / 8;
+  if (plan.f8) {
+    // E4M3 operands: d floats of pitch = 4*d bytes = 4*d elements per row; a K chunk is the same
+    // 128-byte swizzle span (128 elements), an MMA covers 32 of them
+    const int pitch = 4 * d;
+    if ((rc = make_map_u8(&mq, query, nq, pitch, TM))) return rc;
+    if ((rc = make_map_u8(&mb, base, nb, pitch, TN))) return rc;
+    if ((rc = make_map_u8(&mbh, base, nb, pitch, TN / 2))) return rc;
+    P.nkc = (pitch + 127) / 128;
+    P.last_k8 = (pitch - (P.nkc - 1) * 128 + 31) / 32;
+  } else {
+    if ((rc = make_map(&mq, query, nq, d, TM))) return rc;
+    if ((rc = make_map(&mb, base, nb, d, TN))) return rc;
+    if ((rc = make_map(&mbh, base, nb, d, TN / 2))) return rc;
+    P.nkc = (d + KC - 1) / KC;
+    P.last_k8 = (d - (P.nkc - 1) * KC + 7) / 8;
+  }
   P.tiles_q = (nq + TM - 1) / TM;
   P.nbt = nbt_logical;
   P.range_tiles = (P.nbt + plan.splits - 1) / plan.splits;
@@ -1084,6 +1142,15 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   P.dump = dump;
   P.dump_ld = dump_ld;
   const int mode = dump ? EPI_DUMP : (P.gmin ? EPI_GMIN : (k1_margin ? EPI_NEAREST : EPI_LISTS));
+  if (plan.f8) {
+    if (plan.pair) return fail(6, "the E4M3 operand kind has no paired-CTA variant");
+    switch (mode) {
+      case EPI_DUMP: return launch_mode<EPI_DUMP, true>(plan, mq, mb, mbh, P, st);
+      case EPI_GMIN: return launch_mode<EPI_GMIN, true>(plan, mq, mb, mbh, P, st);
+      case EPI_LISTS: return launch_mode<EPI_LISTS, true>(plan, mq, mb, mbh, P, st);
+      default: return fail(6, "the E4M3 operand kind has no k = 1 margin mode");
+    }
+  }
   switch (mode) {
     case EPI_DUMP: return launch_mode<EPI_DUMP>(plan, mq, mb, mbh, P, st);
     case EPI_GMIN: return launch_mode<EPI_GMIN>(plan, mq, mb, mbh, P, st);
