@@ -169,6 +169,11 @@ long yb_last_hamming_fallbacks(void);
 /* bring-up / tests: raw scores of the E4M3 pass, scores[q][n] = 4 * hamming(query q, base n) */
 int yb_debug_hamming_tc_scores(int nq, int nb, int ncodes, const uint8_t *base,
                                const uint8_t *query, float *scores, yb_stream_t s);
+/* bring-up / tests: the PACKED pass (`slots` consecutive database rows share one accumulator):
+ * out[q][c] = -2 * (dot_0 + 2^8 dot_1 + 2^16 dot_2), dot_i = bits - 2 hamming(q, row slots*c+i),
+ * c < ceil(nb / slots); absent rows contribute 0 */
+int yb_debug_hamming_tc_packed(int nq, int nb, int ncodes, int slots, const uint8_t *base,
+                               const uint8_t *query, float *out, yb_stream_t s);
 int yb_nn_hamming_merge(int nq, int k, int G, const int *assign_in, const uint16_t *dis_in,
                         int *assign_out, uint16_t *dis_out, yb_stream_t s);
 /* micro-benchmark: measured 64-bit xor+popcount pair rate of the whole GPU (the ceiling the

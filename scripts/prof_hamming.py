@@ -20,12 +20,29 @@ base = torch.randint(0, 256, (nb, nc), device="cuda", dtype=torch.uint8)
 query = torch.randint(0, 256, (nq, nc), device="cuda", dtype=torch.uint8)
 idx = torch.empty((nq, k), device="cuda", dtype=torch.int32)
 dis = torch.empty((nq, k), device="cuda", dtype=torch.int16)
-for rep in range(3):
-    torch.cuda.synchronize()
-    t = time.perf_counter()
-    rc = L.yb_nn_hamming(nq, nb, nc, k, base.data_ptr(), query.data_ptr(), idx.data_ptr(), dis.data_ptr(), 0, None)
-    assert rc == 0, L.yb_last_error()
-    L.yb_sync(None)
-    dt = time.perf_counter() - t
-    print("rep %d: %.3f ms -> %.0f q/s, %.3e pairs/s" % (rep, dt * 1e3, nq / dt, nq * nb / dt))
-print(idx[0, :5].tolist(), dis[0, :5].tolist())
+for engine in (0, 1):
+    L.yb_set_hamming_engine(engine)
+    L.yb_prof_enable(1)
+    L.yb_prof_ms(0, None, 1)
+    for rep in range(3):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        rc = L.yb_nn_hamming(nq, nb, nc, k, base.data_ptr(), query.data_ptr(), idx.data_ptr(), dis.data_ptr(), 0, None)
+        assert rc == 0, L.yb_last_error()
+        L.yb_sync(None)
+        dt = time.perf_counter() - t
+        print("engine %d (used %d, %d scan fallbacks) rep %d: %.3f ms -> %.0f q/s, %.3e pairs/s" %
+              (engine, L.yb_last_hamming_engine(), L.yb_last_hamming_fallbacks(), rep, dt * 1e3, nq / dt,
+               nq * nb / dt))
+    cnt = C.c_long(0)
+    for ph, name in ((7, "popcount scan"), (12, "expand"), (13, "sample"), (14, "e4m3 pass"), (15, "order+certify")):
+        ms = L.yb_prof_ms(ph, C.byref(cnt), 0)
+        if cnt.value:
+            print("  phase %-14s %.3f ms avg over %d" % (name, ms / cnt.value, cnt.value))
+    L.yb_prof_enable(0)
+    print(idx[0, :5].tolist(), dis[0, :5].tolist())
+    if engine == 0:
+        ref = (idx.clone(), dis.clone())
+    else:
+        print("engines agree:", bool(torch.equal(ref[0], idx) and torch.equal(ref[1], dis)))
+L.yb_set_hamming_engine(-1)

@@ -157,3 +157,33 @@ def test_baseline_shape_tensor_equals_popcount_engine():
     assert gd[3, 0] == 0
     # on iid codes the certificate holds for (nearly) every query
     assert out[1][2] <= nq // 20, "fallbacks: %d" % out[1][2]
+
+
+@pytest.mark.parametrize("nq,nb,nc,slots", [(128, 768, 8, 3), (130, 2000, 8, 3), (77, 1001, 4, 3),
+                                            (64, 1000, 16, 2), (200, 5000, 8, 2), (50, 999, 5, 3)])
+def test_packed_accumulators_are_exact(nq, nb, nc, slots):
+    # `slots` consecutive database rows share one FP32 accumulator at scales 1, 2^8, 2^16: the
+    # tensor core must deliver dot_0 + 2^8 dot_1 + 2^16 dot_2 EXACTLY (integers below 2^23)
+    L = yael_b200.lib()
+    r = rs(nq + nb + nc + slots)
+    base = r.randint(0, 256, (nb, nc)).astype(np.uint8)
+    query = r.randint(0, 256, (nq, nc)).astype(np.uint8)
+    base[::7] = query[0]                     # ham 0 -> dot = +bits in every slot position
+    base[3::11] = ~query[min(2, nq - 1)]     # ham = bits -> dot = -bits
+    ncomb = (nb + slots - 1) // slots
+    db, dq = DevArray(base), DevArray(query)
+    out = DevArray(shape=(nq, ncomb), dtype=np.float32)
+    rc = L.yb_debug_hamming_tc_packed(nq, nb, nc, slots, db.ptr, dq.ptr, out.ptr, None)
+    assert rc == 0, L.yb_last_error()
+    L.yb_sync(None)
+    got = out.get().astype(np.float64)
+    W = 1 if nc <= 8 else 2
+    bits = 64 * W   # codes are zero-padded to W words: padded bits are equal on both sides
+    ham = np.unpackbits(query[:, None, :] ^ base[None, :, :], axis=2).sum(2).astype(np.int64)
+    dot = bits - 2 * ham                                   # [nq][nb]
+    pad = ncomb * slots - nb
+    dot = np.concatenate([dot, np.zeros((nq, pad), np.int64)], axis=1).reshape(nq, ncomb, slots)
+    want = -2.0 * sum(dot[:, :, i] * float(256 ** i) for i in range(slots))
+    assert np.array_equal(got, want)
+    for a in (db, dq, out):
+        a.free()

@@ -157,6 +157,7 @@ DEVICE = {
     "yb_last_hamming_engine": (C.c_int, []),
     "yb_last_hamming_fallbacks": (C.c_long, []),
     "yb_debug_hamming_tc_scores": (C.c_int, [C.c_int] * 3 + [_vp, _vp, _vp, _vp]),
+    "yb_debug_hamming_tc_packed": (C.c_int, [C.c_int] * 4 + [_vp, _vp, _vp, _vp]),
     "yb_match_hamming_count": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "yb_match_hamming_thres": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "yb_crossmatch_hamming_count": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),

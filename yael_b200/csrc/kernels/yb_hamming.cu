@@ -591,6 +591,25 @@ extern "C" int yb_nn_hamming(int nq, int nb, int ncodes, int k, const uint8_t *b
   return nn_hamming_popc(nq, nb, ncodes, W, k, base, query, assign, dis, id_offset, st);
 }
 
+extern "C" int yb_debug_hamming_tc_packed(int nq, int nb, int ncodes, int slots, const uint8_t *base,
+                                           const uint8_t *query, float *out, yb_stream_t s) {
+  const int W = words_for(ncodes);
+  if (!W || nq <= 0 || nb <= 0) return fail(3, "hamming_tc_packed: unsupported shape");
+  Guard g;
+  cudaStream_t st = stream_of(s);
+  unsigned long long *tb = (unsigned long long *)yb_malloc(8ull * W * nb);
+  unsigned long long *tq = (unsigned long long *)yb_malloc(8ull * W * nq);
+  const unsigned long long *pb, *pq;
+  int rc;
+  if ((rc = packed_codes(base, nb, ncodes, -W, tb, &pb, st))) return rc;
+  if ((rc = packed_codes(query, nq, ncodes, -W, tq, &pq, st))) return rc;
+  rc = hamming_tc_packed_dump(nq, nb, W, slots, pb, pq, out, st);
+  cudaStreamSynchronize(st);
+  yb_free(tb);
+  yb_free(tq);
+  return rc;
+}
+
 extern "C" int yb_debug_hamming_tc_scores(int nq, int nb, int ncodes, const uint8_t *base,
                                            const uint8_t *query, float *scores, yb_stream_t s) {
   const int W = words_for(ncodes);

@@ -27,21 +27,37 @@
 namespace yb {
 
 // ------------------------------------------------------------------ operand expansion
-// one thread per 16 bits -> 16 E4M3 bytes (one 128-bit store); element i of a row is bit i
+// Codes -> E4M3 rows.  An output row holds `slots` copies ("slots") of 64*W elements; element j
+// of slot i is +-scale_i (bit set: +), scale = 1, 16, 256 (0x38, 0x58, 0x78).  Queries
+// (interleave = 0) repeat their own code in every slot; the database (interleave = 1) packs
+// `slots` CONSECUTIVE rows into one combined row (row slots*c + i in slot i; absent rows are
+// zeros).  With both sides scaled the accumulator of (query, combined row c) is
+//     acc = dot_0 + 2^8 dot_1 + 2^16 dot_2,   dot_i = <q, b_{slots*c+i}> = bits - 2 ham_i,
+// every MMA (K = 32 elements) lying inside one slot: one 32-bit TMEM word carries up to three
+// distances.  One thread per 16 bits -> 16 bytes (one 128-bit store).
 __global__ void __launch_bounds__(256)
-k_ham_expand(const unsigned long long *__restrict__ codes, long nwords, uint4 *__restrict__ out) {
+k_ham_expand(const unsigned long long *__restrict__ codes, long n_src, int W, int slots,
+             int interleave, long n_out, uint4 *__restrict__ out) {
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nwords * 4) return;
-  const unsigned bits = (unsigned)(codes[t >> 2] >> (16 * (int)(t & 3))) & 0xffffu;
-  auto four = [](unsigned x) {  // 4 bits -> 4 bytes: 0xB8 (-1.0) with the sign cleared where the bit is set
-    const unsigned spread = (x & 1u) | ((x & 2u) << 7) | ((x & 4u) << 14) | ((x & 8u) << 21);
-    return 0xB8B8B8B8u ^ (spread << 7);
-  };
-  uint4 o;
-  o.x = four(bits & 15u);
-  o.y = four((bits >> 4) & 15u);
-  o.z = four((bits >> 8) & 15u);
-  o.w = four((bits >> 12) & 15u);
+  const int units = slots * W * 4;  // 16-byte units per output row
+  if (t >= n_out * units) return;
+  const long row_out = t / units;
+  const int u = (int)(t - row_out * units);
+  const int slot = u / (W * 4), w16 = u - slot * (W * 4);
+  const long src = interleave ? row_out * slots + slot : row_out;
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (src < n_src) {
+    const unsigned bits = (unsigned)(codes[src * W + (w16 >> 2)] >> (16 * (w16 & 3))) & 0xffffu;
+    const unsigned neg = (slot == 0 ? 0xB8B8B8B8u : (slot == 1 ? 0xD8D8D8D8u : 0xF8F8F8F8u));
+    auto four = [neg](unsigned x) {  // 4 bits -> 4 bytes: -scale with the sign cleared where the bit is set
+      const unsigned spread = (x & 1u) | ((x & 2u) << 7) | ((x & 4u) << 14) | ((x & 8u) << 21);
+      return neg ^ (spread << 7);
+    };
+    o.x = four(bits & 15u);
+    o.y = four((bits >> 4) & 15u);
+    o.z = four((bits >> 8) & 15u);
+    o.w = four((bits >> 12) & 15u);
+  }
   out[t] = o;
 }
 
@@ -121,10 +137,12 @@ k_ham_tc_finish(int nq, int k, int lists, int kp, const int *__restrict__ cnt,
 }
 
 // ------------------------------------------------------------------ host side
-static int expand_codes(const unsigned long long *codes, long n, int W, void *out, cudaStream_t st) {
-  const long threads = n * W * 4;
+static int expand_codes(const unsigned long long *codes, long n_src, int W, int slots,
+                        int interleave, long n_out, void *out, cudaStream_t st) {
+  const long threads = n_out * slots * W * 4;
   if (threads <= 0) return 0;
-  k_ham_expand<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(codes, n * W, (uint4 *)out);
+  k_ham_expand<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(codes, n_src, W, slots, interleave,
+                                                                  n_out, (uint4 *)out);
   YB_LAUNCH_CHECK();
   return 0;
 }
@@ -211,8 +229,8 @@ int hamming_tc(int nq, int nb, int W, int k, const unsigned long long *pb,
     int rc;
     {
       ProfScope ps(12, st);
-      if ((rc = expand_codes(pb, nb, W, base8, st))) return rc;
-      if ((rc = expand_codes(pq, nq, W, query8, st))) return rc;
+      if ((rc = expand_codes(pb, nb, W, 1, 0, nb, base8, st))) return rc;
+      if ((rc = expand_codes(pq, nq, W, 1, 0, nq, query8, st))) return rc;
       if ((rc = fill_f32(an, nb, 2.0f * (float)bits, st))) return rc;
       if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
       YB_CUDA(cudaMemsetAsync(flag_count, 0, 64, st));
@@ -281,12 +299,40 @@ int hamming_tc_scores(int nq, int nb, int W, const unsigned long long *pb,
   float *an = c.take<float>(padded);
   void *tfws = c.take<char>(plan.ws_bytes);
   int rc;
-  if ((rc = expand_codes(pb, nb, W, base8, st))) return rc;
-  if ((rc = expand_codes(pq, nq, W, query8, st))) return rc;
+  if ((rc = expand_codes(pb, nb, W, 1, 0, nb, base8, st))) return rc;
+  if ((rc = expand_codes(pq, nq, W, 1, 0, nq, query8, st))) return rc;
   if ((rc = fill_f32(an, nb, 128.0f * (float)W, st))) return rc;
   if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
   return tf32_scores(plan, nq, nb, dfl, tf32_tiles(nb), 1, (const float *)base8,
                      (const float *)query8, an, scores, nb, tfws, st);
+}
+
+// raw accumulators of the PACKED E4M3 pass (bring-up / tests): out[q][c] = -2 * acc(q, combined
+// row c), c < ceil(nb / slots)
+int hamming_tc_packed_dump(int nq, int nb, int W, int slots, const unsigned long long *pb,
+                           const unsigned long long *pq, float *out, cudaStream_t st) {
+  if (slots < 1 || slots > 3 || slots * W > 8) return fail(3, "hamming packed dump: %d slots of %d words", slots, W);
+  const int dfl = 16 * W * slots;
+  const int nc = (nb + slots - 1) / slots;
+  Tf32Plan plan = tf32_plan(nq, nc, dfl, 1);
+  if (!plan.ok || plan.pair) return fail(3, "hamming tensor path does not support this shape");
+  plan.f8 = 1;
+  const long padded = tf32_padded_rows(nc);
+  const size_t rowb = 64ull * W * slots;
+  ScratchScope ws(Carver::need(rowb * nc) + Carver::need(rowb * nq) + Carver::need(4ull * padded) +
+                      Carver::need(plan.ws_bytes),
+                  st);
+  Carver c(ws.p);
+  void *base8 = c.take<char>(rowb * nc);
+  void *query8 = c.take<char>(rowb * nq);
+  float *an = c.take<float>(padded);
+  void *tfws = c.take<char>(plan.ws_bytes);
+  int rc;
+  if ((rc = expand_codes(pb, nb, W, slots, 1, nc, base8, st))) return rc;
+  if ((rc = expand_codes(pq, nq, W, slots, 0, nq, query8, st))) return rc;
+  if ((rc = fill_f32(an, padded, 0.0f, st))) return rc;
+  return tf32_scores(plan, nq, nc, dfl, tf32_tiles(nc), 1, (const float *)base8,
+                     (const float *)query8, an, out, nc, tfws, st);
 }
 
 }  // namespace yb

@@ -80,6 +80,8 @@ int hamming_tc(int nq, int nb, int W, int k, const unsigned long long *pb,
 int hamming_tc_scores(int nq, int nb, int W, const unsigned long long *pb,
                       const unsigned long long *pq, float *scores, cudaStream_t st);
 
+int hamming_tc_packed_dump(int nq, int nb, int W, int slots, const unsigned long long *pb,
+                           const unsigned long long *pq, float *out, cudaStream_t st);
 long tf32_padded_rows(int nb);
 int tf32_tiles(int nb);
 int fill_f32(float *p, long n, float v, cudaStream_t st);
