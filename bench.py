@@ -392,6 +392,95 @@ def measure_extras(torch, L, dev):
     return out
 
 
+def measure_extras_sharded(torch, dist, ydist, L, dev, rank, world):
+    """N > 1: the other two BASELINE shapes SHARDED over the ranks, total work fixed:
+      - k-means, BASELINE configs[3]: n = 10M points split over the ranks, k = 65536, d = 128; one
+        all-reduce of (k*d sums, k counts, qerr) per iteration through the C host loop's hook
+      - Hamming kNN, BASELINE configs[2]: 10M codes split over the ranks, all-gather + merge
+    Every rank runs the same collectives in the same order; a failure on one rank is turned into a
+    flag that all ranks agree on before the next collective."""
+    out = {}
+
+    def all_ok(ok):
+        t = torch.tensor([1 if ok else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- Hamming, database sharded
+    try:
+        nbh, nqh, kh = 10_000_000, 10_000, 100
+        lo, hi = ydist.shard_bounds(nbh, world)[rank]
+        g = torch.Generator(device=dev)
+        g.manual_seed(1236 + rank)
+        hb = torch.randint(0, 256, (hi - lo, 8), device=dev, dtype=torch.uint8, generator=g)
+        gq = torch.Generator(device=dev)
+        gq.manual_seed(99)
+        hq = torch.randint(0, 256, (nqh, 8), device=dev, dtype=torch.uint8, generator=gq)
+        sh = ydist.ShardedHamming(hb, kh, rank=rank, world=world, id_offset=lo)
+        ok = True
+    except Exception as e:
+        ok = False
+        out["hamming_error"] = str(e)
+    if all_ok(ok):
+        best = 1e9
+        for _ in range(3):
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sh.search(hq)
+            e1.record()
+            e1.synchronize()
+            best = min(best, max_over_ranks(e0.elapsed_time(e1)))
+        out["hamming_knn_10Mx64bit_10kq_k100_sharded"] = {
+            "queries_per_s": nqh / (best * 1e-3), "ms": best, "ranks": world,
+            "engine": int(L.yb_last_hamming_engine()), "scaling": "strong (10M codes split over the ranks)"}
+        del hb, hq, sh
+        torch.cuda.empty_cache()
+
+    # ---- k-means, points sharded
+    try:
+        n, d, k, niter = 10_000_000, 128, 65536, 2
+        lo, hi = ydist.shard_bounds(n, world)[rank]
+        g = torch.Generator(device=dev)
+        g.manual_seed(1237 + rank)
+        v = torch.rand((hi - lo, d), device=dev, dtype=torch.float32, generator=g)
+        cent = v[:k].contiguous() if rank == 0 else torch.empty((k, d), device=dev, dtype=torch.float32)
+        ok = v.shape[0] >= k or rank != 0
+    except Exception as e:
+        ok = False
+        out["kmeans_error"] = str(e)
+    if all_ok(ok):
+        dist.broadcast(cent, 0)
+        c0 = cent.cpu().numpy()
+        times = []
+        okrun = True
+        for _ in range(2):
+            dist.barrier()
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            try:
+                _, q, _, _ = ydist.sharded_kmeans(v, k, niter, c0, n)
+            except Exception as e:  # the all-reduce hook returns an error code instead of raising
+                okrun = False
+                out["kmeans_error"] = str(e)
+            torch.cuda.synchronize()
+            times.append(max_over_ranks((time.perf_counter() - t) / niter))
+            if not all_ok(okrun):
+                break
+        if okrun and times:
+            out["kmeans_10Mx128_k65536_sharded"] = {
+                "iter_per_s": 1.0 / min(times), "s_per_iter": min(times), "ranks": world, "qerr": float(q),
+                "scaling": "strong (10M points split over the ranks, one all-reduce per iteration)"}
+        del v
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -408,7 +497,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     L.yb_set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
 
     # a real (non-default) stream: the library launches on the stream handle it is given, and the
     # CUDA events below must sit on that same stream (handle 0 would mean "the library's own")
@@ -496,6 +586,13 @@ def run_ours(args):
            "h2d_bytes_per_step": int(base_h.nbytes + query_h.nbytes),
            "d2h_bytes_per_step": int(NQ * K * 8), "ms_per_step": t_e2e * 1e3}
 
+    extras_sharded = None
+    if world > 1 and not args.no_extras:
+        try:
+            extras_sharded = measure_extras_sharded(torch, dist, ydist, L, dev, rank, world)
+        except Exception as e:
+            extras_sharded = {"error": str(e)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -541,7 +638,7 @@ def run_ours(args):
 
     cpu = cpu_reference_rate(base_h, query_h)
 
-    extras = None
+    extras = extras_sharded
     if world == 1 and not args.no_extras:
         extras = measure_extras(torch, L, dev)
 
