@@ -42,7 +42,14 @@ long yb_launch_count(int reset);
 /* which kNN engine the last yb_knn_l2 call used: 1 = tcgen05 TF32 shortlist + FP32 re-rank,
  * 0 = exact FP32 SIMT path; and how many queries failed the shortlist certificate and were
  * re-done by the exact path */
+/* bring-up / tests: raw scores |b|^2 - 2<q,b> of the FP16-operand tensor pass (the default
+ * operand kind of the resident k-NN / k-means passes; YAEL_B200_OPERANDS=tf32 selects FP32 rows
+ * read as TF32).  scores[nq][nb]; returns 7 if a value overflowed FP16 even after scaling. */
+int yb_debug_f16_scores(int nq, int nb, int d, const float *base, const float *query, float *scores,
+                        yb_stream_t s);
 int yb_last_knn_engine(void);
+/* operand kind of the last resident tensor pass: 0 = TF32, 2 = FP16 */
+int yb_last_knn_operands(void);
 long yb_last_knn_uncertified(void);
 /* force an engine for testing: -1 auto (default), 0 exact SIMT only, 1 TF32 whenever legal */
 void yb_set_knn_engine(int engine);

@@ -42,6 +42,78 @@ def test_tf32_scores_within_error_model(nq, nb, d):
         a.free()
 
 
+@pytest.mark.parametrize("nq,nb,d,scale", [(128, 256, 128, 1.0), (130, 700, 128, 1e-6), (77, 1000, 96, 3e4),
+                                           (300, 5000, 64, 1.0), (5, 300, 100, 255.0), (256, 2048, 8, 1.0),
+                                           (64, 1500, 20, 1e-3)])
+def test_f16_scores_within_error_model(nq, nb, d, scale):
+    # FP16 operands (kind::f16), power-of-two scale chosen on the device: rounding to nearest keeps
+    # 11 significant bits per operand, so the score is within 2 * 2^-10 |q||b| of exact
+    L = yael_b200.lib()
+    r = rs(nq + nb + d + 1)
+    base = ((r.rand(nb, d) - 0.3) * scale).astype(np.float32)
+    query = ((r.rand(nq, d) - 0.3) * scale).astype(np.float32)
+    base[7, : d // 2] = 0.0          # zeros and tiny values (sub-normal after conversion)
+    base[9] *= np.float32(1e-7)
+    db, dq = DevArray(base), DevArray(query)
+    out = DevArray(shape=(nq, nb), dtype=np.float32)
+    rc = L.yb_debug_f16_scores(nq, nb, d, db.ptr, dq.ptr, out.ptr, None)
+    assert rc == 0, L.yb_last_error()
+    L.yb_sync(None)
+    got = out.get()
+    b64, q64 = base.astype(np.float64), query.astype(np.float64)
+    exact = (b64 * b64).sum(1)[None, :] - 2.0 * q64 @ b64.T
+    err = np.abs(got - exact)
+    qn, bn = np.linalg.norm(q64, axis=1)[:, None], np.linalg.norm(b64, axis=1)
+    bound = (1.05 / 512.0) * qn * bn.max() + 1e-6 * np.abs(exact) + 1e-30
+    assert np.isfinite(got).all()
+    assert (err <= bound).all(), "max err ratio %g" % (err / bound).max()
+    assert err.max() > 0  # it is a reduced-precision result, not an FP32 one
+    for a in (db, dq, out):
+        a.free()
+
+
+def test_knn_f16_out_of_range_value_falls_back_to_tf32(yn, ob):
+    # the FP16 scale comes from a SAMPLE of the rows (8x head room); an un-sampled outlier beyond it
+    # raises the overflow flag and the pass is repeated on TF32 operands -- same exact result
+    L = yael_b200.lib()
+    L.yb_set_knn_engine(1)
+    try:
+        r = rs(99)
+        nb, nq, d, k = 100000, 64, 64, 10
+        b = r.rand(nb, d).astype(np.float32)
+        q = r.rand(nq, d).astype(np.float32)
+        idx, dis = yn.knn(q, b, k)
+        assert L.yb_last_knn_engine() == 1 and L.yb_last_knn_operands() == 2
+        widx, wdis = ob.orc_knn(b, q, k, ob.DOT_F32_SEQ, canonical=True)
+        check_knn(idx, dis, widx, wdis)
+        b[500] = 1e3  # rows 256..780 are not in the sample: 1e3 >> 8 x the sampled maximum
+        idx, dis = yn.knn(q, b, k)
+        assert L.yb_last_knn_engine() == 1 and L.yb_last_knn_operands() == 0
+        widx, wdis = ob.orc_knn(b, q, k, ob.DOT_F32_SEQ, canonical=True)
+        check_knn(idx, dis, widx, wdis)
+    finally:
+        L.yb_set_knn_engine(-1)
+
+
+@pytest.mark.parametrize("operands", ["tf32", "f16"])
+def test_knn_both_operand_kinds_match_oracle(yn, ob, operands, monkeypatch):
+    monkeypatch.setenv("YAEL_B200_OPERANDS", operands)
+    L = yael_b200.lib()
+    L.yb_set_knn_engine(1)
+    try:
+        r = rs(5)
+        for nb, nq, d, k in ((60000, 300, 128, 100), (50000, 1000, 100, 1), (40000, 100, 24, 7)):
+            b = (r.rand(nb, d) * 200).astype(np.float32)   # SIFT-like magnitudes
+            q = (r.rand(nq, d) * 200).astype(np.float32)
+            idx, dis = yn.knn(q, b, k)
+            assert L.yb_last_knn_engine() == 1
+            assert L.yb_last_knn_operands() == (0 if operands == "tf32" else 2)
+            widx, wdis = ob.orc_knn(b, q, k, ob.DOT_F32_SEQ, canonical=True)
+            check_knn(idx, dis, widx, wdis)
+    finally:
+        L.yb_set_knn_engine(-1)
+
+
 @pytest.fixture
 def tf32_engine():
     L = yael_b200.lib()

@@ -126,6 +126,7 @@ DEVICE = {
     "yb_sync": (C.c_int, [_vp]),
     "yb_launch_count": (C.c_long, [C.c_int]),
     "yb_last_knn_engine": (C.c_int, []),
+    "yb_last_knn_operands": (C.c_int, []),
     "yb_last_knn_uncertified": (C.c_long, []),
     "yb_set_knn_engine": (None, [C.c_int]),
     "yb_prof_enable": (None, [C.c_int]),
@@ -149,6 +150,7 @@ DEVICE = {
     "yb_kmeans_scale": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
     "yb_kmeans_dev": (C.c_float, [C.c_int] * 4 + [_vp, C.c_int, C.c_long, C.c_int, _f, _f, _i, _i, _vp, _vp]),
     "yb_debug_tf32_scores": (C.c_int, [C.c_int] * 3 + [_vp, _vp, _vp, _vp]),
+    "yb_debug_f16_scores": (C.c_int, [C.c_int] * 3 + [_vp, _vp, _vp, _vp]),
     "yb_debug_popc_pairs_per_s": (C.c_double, [_vp]),
     "yb_compute_hamming": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "yb_nn_hamming": (C.c_int, [C.c_int] * 4 + [_vp, _vp, _vp, _vp, C.c_int, _vp]),

@@ -190,7 +190,7 @@ int hamming_tc(int nq, int nb, int W, int k, const unsigned long long *pb,
   const int dfl = 16 * W;       // row pitch in floats (64 * W one-byte elements)
   const int bits = 64 * W;
   Tf32Plan plan = tf32_plan(nq, nb, dfl, k);
-  plan.f8 = 1;
+  plan.kind = 1;
   const int kp = plan.kprime;
   const int nbt = tf32_tiles(nb);
   const long padded = tf32_padded_rows(nb);
@@ -198,7 +198,7 @@ int hamming_tc(int nq, int nb, int W, int k, const unsigned long long *pb,
   Tf32Plan splan = {};
   if (sg.ok) {
     splan = tf32_plan_tiles(nq, sg.nbt_s, dfl, sg.j2);
-    splan.f8 = 1;
+    splan.kind = 1;
   }
   const bool sample = sg.ok && splan.ok && !splan.pair;
   const size_t stride = (size_t)plan.lists * kp;
@@ -288,7 +288,7 @@ int hamming_tc_scores(int nq, int nb, int W, const unsigned long long *pb,
   const int dfl = 16 * W;
   Tf32Plan plan = tf32_plan(nq, nb, dfl, 1);
   if (!plan.ok || plan.pair) return fail(3, "hamming tensor path does not support this shape");
-  plan.f8 = 1;
+  plan.kind = 1;
   const long padded = tf32_padded_rows(nb);
   ScratchScope ws(Carver::need(64ull * W * nb) + Carver::need(64ull * W * nq) +
                       Carver::need(4ull * padded) + Carver::need(plan.ws_bytes),
@@ -316,7 +316,7 @@ int hamming_tc_packed_dump(int nq, int nb, int W, int slots, const unsigned long
   const int nc = (nb + slots - 1) / slots;
   Tf32Plan plan = tf32_plan(nq, nc, dfl, 1);
   if (!plan.ok || plan.pair) return fail(3, "hamming tensor path does not support this shape");
-  plan.f8 = 1;
+  plan.kind = 1;
   const long padded = tf32_padded_rows(nc);
   const size_t rowb = 64ull * W * slots;
   ScratchScope ws(Carver::need(rowb * nc) + Carver::need(rowb * nq) + Carver::need(4ull * padded) +

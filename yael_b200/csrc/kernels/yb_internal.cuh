@@ -28,8 +28,10 @@ struct Tf32Plan {
   int ctas;        // persistent grid size
   int pair;        // CTAs launched as clusters of 2 sharing the database stream
   size_t ws_bytes; // workspace for buffers + shortlists
-  int f8;          // operands are E4M3 bytes (kind::f8f6f4) instead of floats (kind::tf32): `base`
-                   // and `query` then point to [rows][4*d] BYTE matrices (the Hamming path)
+  int kind;        // operand kind: 0 = FP32 rows read as TF32 (kind::tf32); 1 = E4M3 bytes
+                   // (kind::f8f6f4; `base` / `query` point to [rows][4*d] BYTE matrices -- the Hamming
+                   // path); 2 = FP16 (kind::f16; [rows][d] half matrices, d % 8 == 0)
+  const float *acc_scale;  // device scalar a: score = acc * a + |b|^2 (NULL: a = -2)
 };
 Tf32Plan tf32_plan(int nq, int nb, int d, int k);
 Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kprime);

@@ -8,6 +8,8 @@
 // FMA chain, and both order results by (distance, id).
 #include <stdlib.h>
 
+#include <cuda_fp16.h>
+
 #include "yb_common.cuh"
 #include "yb_internal.cuh"
 
@@ -15,6 +17,7 @@ namespace yb {
 
 static int g_engine_force = -1;
 static int g_last_engine = 0;
+static int g_last_operands = 0;  // operand kind of the last tensor pass (0 TF32, 2 FP16)
 static long g_last_uncert = 0;
 
 // ------------------------------------------------------------------ exact re-rank
@@ -50,6 +53,7 @@ struct RerankArgs {
   int qc_ld;
   float err_scale;         // certificate: E_q = err_scale * |q| * max|b|
   const float *bmax;       // device scalar: max |b| (sqrt of max squared norm)
+  const float *err_abs;    // device scalar (or NULL): E_q += err_abs * (|q| + max|b|) (FP16 operands)
   int *assign;
   int id_offset;
   int *uncert_flags;       // [nq] 1 = certificate failed
@@ -230,6 +234,7 @@ __global__ void __launch_bounds__(RR_T) k_rerank(RerankArgs A) {
             double Dk = (double)__uint_as_float(bits);
             double E = (double)A.err_scale * sqrt(qcn) * (double)(*A.bmax) +
                        4e-5 * (fabs(Dk) + qcn) + 2e-6 * (fabs(Dk) + qn);
+            if (A.err_abs) E += (double)(*A.err_abs) * (sqrt(qcn) + (double)(*A.bmax));
             if (!((Dk - qcn) + E < (double)T)) flag = 1;
           }
         }
@@ -658,6 +663,9 @@ int row_kth(const float *vals, long ld, int nrow, int n, int j, float *thr, cuda
 // room covers the FP32 accumulation inside the tensor core, the norm rounding and the 7 mantissa
 // bits of a listed score that carry its column index (relative 2^-16).
 static const float kTf32ErrScale = 1.05f / 256.0f;
+// FP16 operands are rounded to nearest: relative error <= 2^-11 per operand, 2^-10 per product,
+// 2 * 2^-10 |q||b| on the score (plus the absolute term for sub-normal values, scal[5])
+static const float kF16ErrScale = 1.05f / 512.0f;
 
 // ------------------------------------------------------------------ centring
 // Squared L2 distances are translation invariant: |q-b|^2 = |(q-mu)-(b-mu)|^2 for ANY mu.  The
@@ -815,6 +823,199 @@ static int center_operands(int nq, int nb, int d, int dpad, const float *base, c
   return 0;
 }
 
+
+// ------------------------------------------------------------------ FP16 operands
+// The tensor pass can read its operands as FP16 (kind::f16) instead of FP32-as-TF32: the same 10
+// explicit mantissa bits (and round-to-nearest instead of truncation), half the operand bytes,
+// i.e. half as many MMAs, shared-memory operand reads and accumulator passes per tile.  FP16's
+// narrow exponent range is handled by an exact power-of-two scale 2^sigma chosen from a sample
+// of the centred data (8x head room); the kernel's epilogue multiplies the accumulator by
+// -2^(1-2 sigma) in the same FMA that adds |b|^2, so scores, thresholds and the certificate stay
+// in the caller's units.  A finite value that still overflows FP16 raises a flag and the caller
+// repeats the pass with TF32 operands.  scal[] layout (device floats): [0] max |b-mu|,
+// [1] flag count (int), [2] 2^sigma, [3] -2^(1-2 sigma), [4] overflow flag (int),
+// [5] absolute-error coefficient, [6] sampled max |x-mu|.
+__global__ void __launch_bounds__(256)
+k_absmax_sample(const float *__restrict__ x, long n, int d, long block_step,
+                const float *__restrict__ mu, float *__restrict__ out) {
+  const long r0 = (long)blockIdx.x * block_step, r1 = min(n, r0 + CM_ROWS);
+  float m = 0.f;
+  for (int c = threadIdx.x; c < d; c += 256) {
+    const float muc = mu[c];
+    for (long r = r0; r < r1; r++) {
+      const float v = fabsf(x[r * d + c] - muc);
+      if (isfinite(v)) m = fmaxf(m, v);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax((int *)out, __float_as_int(m));  // m >= 0
+}
+
+__global__ void k_pick_scale(float *__restrict__ scal, int d) {
+  const float m = scal[6];
+  int sigma = 0;
+  if (m > 0.f && isfinite(m)) {
+    const float x = 8188.0f / m;
+    int e = 41;
+    if (isfinite(x)) frexpf(x, &e);  // 8188 / m = f * 2^e, f in [0.5, 1): 2^(e-1) <= 8188 / m
+    sigma = e - 1;
+  }
+  sigma = max(-40, min(40, sigma));
+  scal[2] = ldexpf(1.0f, sigma);
+  scal[3] = -ldexpf(1.0f, 1 - 2 * sigma);
+  // values below FP16's normal range round with an ABSOLUTE error <= 2^-25 (scaled units); summed
+  // over a dot product and brought back to the caller's units that is at most
+  // coef * (|q-mu| + |b-mu|), coef = 2 sqrt(d) 2^-25 2^-sigma (2x for the -2<q,b> factor)
+  scal[5] = 2.0f * sqrtf((float)d) * ldexpf(1.0f, -24 - sigma);
+}
+
+__device__ __forceinline__ unsigned pack_h2(float a, float b, float sc, bool &over) {
+  const float x = a * sc, y = b * sc;
+  over |= (fabsf(x) > 65504.0f && fabsf(a) < __int_as_float(0x7f800000)) ||
+          (fabsf(y) > 65504.0f && fabsf(b) < __int_as_float(0x7f800000));
+  const __half2 h = __floats2half2_rn(x, y);
+  return *reinterpret_cast<const unsigned *>(&h);
+}
+
+// one warp per row, any d: out_h[r][0..dh) = fp16((x - mu) * 2^sigma) zero padded; optional FP32
+// copy out_f[r][0..df) and norm[r] = |x - mu|^2 (FP32 values, before the conversion)
+__global__ void __launch_bounds__(256)
+k_center_rows_h(const float *__restrict__ x, long n, int d, int dh, int df,
+                const float *__restrict__ mu, const float *__restrict__ scal,
+                __half *__restrict__ out_h, float *__restrict__ out_f, float *__restrict__ norm,
+                int *__restrict__ oflag) {
+  const long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  const float sc = scal[2];
+  const int dm = dh > df ? dh : df;
+  float s = 0.f;
+  bool over = false;
+  for (int c = lane; c < dm; c += 32) {
+    const float v = c < d ? __fsub_rn(x[r * d + c], __ldg(mu + c)) : 0.f;
+    if (c < dh) {
+      const float w = v * sc;
+      over |= fabsf(w) > 65504.0f && fabsf(v) < __int_as_float(0x7f800000);
+      out_h[r * dh + c] = __float2half_rn(w);
+    }
+    if (out_f && c < df) out_f[r * df + c] = v;
+    s = fmaf(v, v, s);
+  }
+  if (over) *oflag = 1;
+  if (norm) {
+    s = warp_sum(s);
+    if (lane == 0) norm[r] = s;
+  }
+}
+
+// d % 8 == 0, 16-byte aligned: one warp per 4 rows, 2 x 16-byte loads and one 16-byte store per
+// 8 columns
+__global__ void __launch_bounds__(256)
+k_center_rows_h8(const float *__restrict__ x, long n, int d, const float *__restrict__ mu,
+                 const float *__restrict__ scal, __half *__restrict__ out_h,
+                 float *__restrict__ out_f, float *__restrict__ norm, int *__restrict__ oflag) {
+  const long r0 = ((long)blockIdx.x * 8 + (threadIdx.x >> 5)) * 4;
+  if (r0 >= n) return;
+  const int lane = threadIdx.x & 31;
+  const int d8 = d >> 3;
+  const float sc = scal[2];
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  bool over = false;
+  for (int f = lane; f < 4 * d8; f += 32) {
+    const int i = f / d8, c = f - i * d8;
+    if (r0 + i >= n) continue;
+    const float4 m0 = __ldg(reinterpret_cast<const float4 *>(mu) + 2 * c);
+    const float4 m1 = __ldg(reinterpret_cast<const float4 *>(mu) + 2 * c + 1);
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(x + (r0 + i) * d) + 2 * c);
+    const float4 b = __ldg(reinterpret_cast<const float4 *>(x + (r0 + i) * d) + 2 * c + 1);
+    float4 u, w;
+    u.x = __fsub_rn(a.x, m0.x); u.y = __fsub_rn(a.y, m0.y);
+    u.z = __fsub_rn(a.z, m0.z); u.w = __fsub_rn(a.w, m0.w);
+    w.x = __fsub_rn(b.x, m1.x); w.y = __fsub_rn(b.y, m1.y);
+    w.z = __fsub_rn(b.z, m1.z); w.w = __fsub_rn(b.w, m1.w);
+    if (out_f) {
+      reinterpret_cast<float4 *>(out_f + (r0 + i) * d)[2 * c] = u;
+      reinterpret_cast<float4 *>(out_f + (r0 + i) * d)[2 * c + 1] = w;
+    }
+    float t = 0.f;
+    t = fmaf(u.x, u.x, t); t = fmaf(u.y, u.y, t); t = fmaf(u.z, u.z, t); t = fmaf(u.w, u.w, t);
+    t = fmaf(w.x, w.x, t); t = fmaf(w.y, w.y, t); t = fmaf(w.z, w.z, t); t = fmaf(w.w, w.w, t);
+#pragma unroll
+    for (int ii = 0; ii < 4; ii++)
+      if (ii == i) s[ii] += t;
+    uint4 o;
+    o.x = pack_h2(u.x, u.y, sc, over);
+    o.y = pack_h2(u.z, u.w, sc, over);
+    o.z = pack_h2(w.x, w.y, sc, over);
+    o.w = pack_h2(w.z, w.w, sc, over);
+    reinterpret_cast<uint4 *>(out_h + (r0 + i) * d)[c] = o;
+  }
+  if (over) *oflag = 1;
+  if (norm) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float t = warp_sum(s[i]);
+      if (lane == 0 && r0 + i < n) norm[r0 + i] = t;
+    }
+  }
+}
+
+static void launch_center_rows_h(const float *x, long n, int d, int dh, int df, const float *mu,
+                                 const float *scal, __half *out_h, float *out_f, float *norm,
+                                 cudaStream_t st) {
+  if (n <= 0) return;
+  int *oflag = (int *)(scal + 4);
+  const bool fast = dh == d && (d & 7) == 0 && (!out_f || df == d) &&
+                    (((uintptr_t)x | (uintptr_t)out_h | (uintptr_t)mu | (uintptr_t)out_f) & 15) == 0;
+  if (fast)
+    k_center_rows_h8<<<(unsigned)((n + 31) / 32), 256, 0, st>>>(x, n, d, mu, scal, out_h, out_f, norm, oflag);
+  else
+    k_center_rows_h<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(x, n, d, dh, df, mu, scal, out_h, out_f,
+                                                              norm, oflag);
+  count_launch();
+}
+
+// FP16 counterpart of center_operands: base_h / query_h with row pitch dh halfs (multiple of 8);
+// optional FP32 centred queries query_c (pitch df) and their squared norms qcnorm; bnorm[nb].
+// scal must have been zeroed by the caller.
+static int center_operands_h(int nq, int nb, int d, int dh, int df, const float *base,
+                             const float *query, __half *base_h, __half *query_h, float *query_c,
+                             float *bnorm, float *qcnorm, float *scal, void *ws, cudaStream_t st) {
+  Carver c(ws);
+  int nblk = (int)(((long)nb + CM_ROWS - 1) / CM_ROWS);
+  if (nblk > CM_BLOCKS) nblk = CM_BLOCKS;
+  long step = nblk > 0 ? (long)nb / nblk : CM_ROWS;
+  if (step < CM_ROWS) step = CM_ROWS;
+  float *psum = c.take<float>((size_t)CM_BLOCKS * d);
+  int *pcnt = c.take<int>((size_t)CM_BLOCKS * d);
+  float *mu = c.take<float>(d);
+  k_col_partial<<<nblk, 256, 0, st>>>(base, nb, d, step, psum, pcnt);
+  YB_LAUNCH_CHECK();
+  k_col_final<<<(d + 127) / 128, 128, 0, st>>>(psum, pcnt, nblk, d, mu);
+  YB_LAUNCH_CHECK();
+  k_absmax_sample<<<nblk, 256, 0, st>>>(base, nb, d, step, mu, scal + 6);
+  YB_LAUNCH_CHECK();
+  int qblk = (int)(((long)nq + CM_ROWS - 1) / CM_ROWS);
+  if (qblk > CM_BLOCKS) qblk = CM_BLOCKS;
+  long qstep = qblk > 0 ? (long)nq / qblk : CM_ROWS;
+  if (qstep < CM_ROWS) qstep = CM_ROWS;
+  k_absmax_sample<<<qblk, 256, 0, st>>>(query, nq, d, qstep, mu, scal + 6);
+  YB_LAUNCH_CHECK();
+  k_pick_scale<<<1, 1, 0, st>>>(scal, d);
+  YB_LAUNCH_CHECK();
+  launch_center_rows_h(base, nb, d, dh, dh, mu, scal, base_h, nullptr, bnorm, st);
+  launch_center_rows_h(query, nq, d, dh, df, mu, scal, query_h, query_c, qcnorm, st);
+  YB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// operand kind of the resident tensor passes: FP16 unless YAEL_B200_OPERANDS=tf32
+static int tensor_operand_kind() {
+  const char *e = getenv("YAEL_B200_OPERANDS");
+  return (e && (e[0] == 't' || e[0] == 'T')) ? 0 : 2;
+}
+
 // Queries whose certificate failed are re-done by the exact engine (own allocations: rare
 // path).  flag_list / flag_count live in the caller's scratch.
 static int redo_flagged_exact(int nq, int nb, int d, int k, const float *base, const float *query,
@@ -868,6 +1069,16 @@ __global__ void k_k1_margin(const float *__restrict__ query, int nq, int d,
   }
   s = warp_sum(s);
   if (lane == 0) margin[q] = 2.05f * err_scale * sqrtf(s) * (*bmax) + 1e-30f;
+}
+
+// the same from the squared norms of the centred queries (FP16 operand path)
+__global__ void k_k1_margin_n(const float *__restrict__ qcnorm, int nq, const float *__restrict__ bmax,
+                              float err_scale, const float *__restrict__ err_abs,
+                              float *__restrict__ margin) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const float qn = sqrtf(qcnorm[q]);
+  margin[q] = 2.05f * (err_scale * qn * (*bmax) + (*err_abs) * (qn + (*bmax))) + 1e-30f;
 }
 
 // exact re-rank of the few k = 1 candidates: one warp per query, one lane per candidate slot;
@@ -965,15 +1176,18 @@ k_rerank_k1(int nq, int d, int slots, int lists, const float *__restrict__ base,
 
 static int knn_tf32_nearest(int nq, int nb, int d, const float *base, const float *query,
                             int *assign, float *dis, int id_offset, long *uncert_out,
-                            cudaStream_t st) {
-  const int dpad = (d + 3) & ~3;
+                            cudaStream_t st, int kind) {
+  const bool f16 = kind == 2;
+  const int dpad = f16 ? (d + 7) & ~7 : (d + 3) & ~3;
   Tf32Plan plan = tf32_plan_nearest(nq, nb, dpad);
   if (!plan.ok) return -1000;
+  plan.kind = kind;
   const int kp = plan.kprime, slots = plan.lists * kp;
   const long padded = tf32_padded_rows(nb);
   size_t need = Carver::need(sizeof(float) * (size_t)padded) + Carver::need(64) +
-                Carver::need(sizeof(float) * (size_t)nb * dpad) +
-                Carver::need(sizeof(float) * (size_t)nq * dpad) + center_ws_bytes(nb, d) +
+                Carver::need((f16 ? 2 : 4) * (size_t)nb * dpad) +
+                Carver::need((f16 ? 2 : 4) * (size_t)nq * dpad) + center_ws_bytes(nb, d) +
+                Carver::need(sizeof(float) * (size_t)nq) +
                 Carver::need(sizeof(float) * (size_t)nq) +
                 Carver::need(sizeof(float) * (size_t)nq * slots) +
                 Carver::need(sizeof(int) * (size_t)nq * slots) +
@@ -994,18 +1208,31 @@ static int knn_tf32_nearest(int nq, int nb, int d, const float *base, const floa
     int *flags = c.take<int>(nq);
     int *flag_list = c.take<int>(nq);
     void *tfws = c.take<char>(plan.ws_bytes);
-    float *base_c = c.take<float>((size_t)nb * dpad);
-    float *query_c = c.take<float>((size_t)nq * dpad);
+    float *base_c = (float *)c.take<char>((f16 ? 2 : 4) * (size_t)nb * dpad);
+    float *query_c = (float *)c.take<char>((f16 ? 2 : 4) * (size_t)nq * dpad);
+    float *qcnorm = c.take<float>(nq);
     void *cws = c.take<char>(center_ws_bytes(nb, d));
     int rc;
     {
       ProfScope ps(0, st);
-      if ((rc = center_operands(nq, nb, d, dpad, base, query, base_c, query_c, an, cws, st))) return rc;
-      if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
       YB_CUDA(cudaMemsetAsync(scal, 0, 64, st));
+      if (f16) {
+        // no FP32 copy of the centred queries (for k-means they are the 10^7 points): the margin
+        // comes from the norms the conversion kernel emits
+        if ((rc = center_operands_h(nq, nb, d, dpad, dpad, base, query, (__half *)base_c,
+                                    (__half *)query_c, nullptr, an, qcnorm, scal, cws, st)))
+          return rc;
+        plan.acc_scale = scal + 3;
+      } else {
+        if ((rc = center_operands(nq, nb, d, dpad, base, query, base_c, query_c, an, cws, st))) return rc;
+      }
+      if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
       k_sqrt_max<<<2 * sm_count(), 256, 0, st>>>(an, nb, scal);
       YB_LAUNCH_CHECK();
-      k_k1_margin<<<(nq + 3) / 4, 128, 0, st>>>(query_c, nq, dpad, scal, kTf32ErrScale, margin);
+      if (f16)
+        k_k1_margin_n<<<(nq + 255) / 256, 256, 0, st>>>(qcnorm, nq, scal, kF16ErrScale, scal + 5, margin);
+      else
+        k_k1_margin<<<(nq + 3) / 4, 128, 0, st>>>(query_c, nq, dpad, scal, kTf32ErrScale, margin);
       YB_LAUNCH_CHECK();
     }
     {
@@ -1023,6 +1250,12 @@ static int knn_tf32_nearest(int nq, int nb, int d, const float *base, const floa
     }
     k_collect_flags<<<(nq + 255) / 256, 256, 0, st>>>(flags, nq, flag_list, (int *)(scal + 1));
     YB_LAUNCH_CHECK();
+    int overflow = 0;
+    if (f16) {  // read with the flag count: redo_flagged_exact synchronises the stream
+      YB_CUDA(cudaMemcpyAsync(&overflow, scal + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
+      YB_CUDA(cudaStreamSynchronize(st));
+      if (overflow) return -1001;  // a value outside FP16's range: the caller repeats with TF32
+    }
     if ((rc = redo_flagged_exact(nq, nb, d, 1, base, query, assign, dis, id_offset, flag_list,
                                  (int *)(scal + 1), &n_flag, st)))
       return rc;
@@ -1034,17 +1267,21 @@ static int knn_tf32_nearest(int nq, int nb, int d, const float *base, const floa
 // returns -1000 when the tensor-core path does not apply (caller falls through to engine 0)
 int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *query,
                   const float *w, int *assign, float *dis, int id_offset, int force,
-                  int *engine_out, long *uncert_out, cudaStream_t st) {
+                  int *engine_out, long *uncert_out, cudaStream_t st, int kind) {
   if (force == 0 || w != nullptr) return -1000;
-  const int dpad = (d + 3) & ~3;  // the tensor pass runs on centred, pitch-padded copies
+  const bool f16 = kind == 2;
+  // the tensor pass runs on centred, pitch-padded copies (16-byte row pitch: 4 floats / 8 halfs)
+  const int dpad = f16 ? (d + 7) & ~7 : (d + 3) & ~3;
+  const int dqc = (d + 3) & ~3;   // pitch of the FP32 centred queries (certificate)
   Tf32Plan plan = tf32_plan(nq, nb, dpad, k);
   if (!plan.ok) return -1000;
   if (force < 0 && (double)nq * nb < 1e6) return -1000;  // tiny problems: not worth a TMA setup
   if (k == 1) {
-    int rc1 = knn_tf32_nearest(nq, nb, d, base, query, assign, dis, id_offset, uncert_out, st);
+    int rc1 = knn_tf32_nearest(nq, nb, d, base, query, assign, dis, id_offset, uncert_out, st, kind);
     if (rc1 == 0) *engine_out = 1;
     return rc1;
   }
+  plan.kind = kind;
   const int kp = plan.kprime;
   const int stride = plan.lists * kp;  // candidates per query produced by the tensor pass
   const int m = kp;                     // candidates per query that are re-ranked
@@ -1071,6 +1308,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
   if (const char *e = getenv("YAEL_B200_J2")) j2 = atoi(e) > 0 ? atoi(e) : j2;  // experiment knob
   Tf32Plan splan = {};
   if (use_sample) splan = tf32_plan_tiles(nq, nbt_s, dpad, j2);
+  splan.kind = kind;
   const bool sample_ok = use_sample && splan.ok;
   const int sstride = sample_ok ? splan.lists * j2 : 1;
   // level 1: t1 tiles spread over the database, j1-th smallest -> about 3*j2 rows of level 2
@@ -1083,6 +1321,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
   Tf32Plan l1plan = {};
   const bool level1_ok = sample_ok && t1 >= 8 && (size_t)nq * rows1 * 4 <= ((size_t)1 << 30) &&
                          (l1plan = tf32_plan_tiles(nq, t1, dpad, 8)).ok;
+  l1plan.kind = kind;
 
   // single-level sampling: the sample pass emits the minimum of every group of gsize columns
   // and the threshold is an order statistic of those minima (with j2 << groups the j2 smallest
@@ -1104,8 +1343,9 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
                 2 * Carver::need(sizeof(int) * (size_t)nq) + kmin_ws_bytes(nq, kp) +
                 Carver::need(sizeof(int) * (size_t)nq * plan.lists) +
                 Carver::need(plan.ws_bytes) + 1024 +
-                Carver::need(sizeof(float) * (size_t)nb * dpad) +
-                Carver::need(sizeof(float) * (size_t)nq * dpad) + center_ws_bytes(nb, d);
+                Carver::need((f16 ? 2 : 4) * (size_t)nb * dpad) +
+                Carver::need((f16 ? 2 : 4) * (size_t)nq * dpad) +
+                Carver::need(sizeof(float) * (size_t)nq * dqc) + center_ws_bytes(nb, d);
   if (sample_ok)
     need += Carver::need(sizeof(float) * (size_t)nq * sstride) +
             Carver::need(sizeof(int) * (size_t)nq * sstride) +
@@ -1132,16 +1372,26 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
     int *flag_list = c.take<int>(nq);
     void *kws = c.take<char>(kmin_ws_bytes(nq, kp));
     void *tfws = c.take<char>(plan.ws_bytes);
-    float *base_c = c.take<float>((size_t)nb * dpad);
-    float *query_c = c.take<float>((size_t)nq * dpad);
+    // operands of the tensor passes (FP32 rows read as TF32, or FP16) and, for FP16, a separate
+    // FP32 copy of the centred queries for the certificate
+    float *base_c = (float *)c.take<char>((f16 ? 2 : 4) * (size_t)nb * dpad);
+    float *query_c = (float *)c.take<char>((f16 ? 2 : 4) * (size_t)nq * dpad);
+    float *query_cf = f16 ? c.take<float>((size_t)nq * dqc) : query_c;
     void *cws = c.take<char>(center_ws_bytes(nb, d));
     float *thr_init = nullptr;
     int rc;
     {
       ProfScope ps(0, st);
-      if ((rc = center_operands(nq, nb, d, dpad, base, query, base_c, query_c, an, cws, st))) return rc;
-      if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
       YB_CUDA(cudaMemsetAsync(scal, 0, 64, st));
+      if (f16) {
+        if ((rc = center_operands_h(nq, nb, d, dpad, dqc, base, query, (__half *)base_c,
+                                    (__half *)query_c, query_cf, an, nullptr, scal, cws, st)))
+          return rc;
+        plan.acc_scale = splan.acc_scale = l1plan.acc_scale = scal + 3;
+      } else {
+        if ((rc = center_operands(nq, nb, d, dpad, base, query, base_c, query_c, an, cws, st))) return rc;
+      }
+      if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
       k_sqrt_max<<<2 * sm_count(), 256, 0, st>>>(an, nb, scal);
       YB_LAUNCH_CHECK();
     }
@@ -1227,8 +1477,9 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
     A.dis = dis; A.assign = assign; A.id_offset = id_offset;
     A.cand_id = cid; A.cand_score = cscore; A.sel = need_sel ? sel : nullptr;
     A.cand_stride = stride; A.m = m; A.all_listed = (nb <= kp);
-    A.cand_thr = cthr; A.lists = plan.lists; A.query_c = query_c; A.qc_ld = dpad;
-    A.err_scale = kTf32ErrScale; A.bmax = scal; A.uncert_flags = flags;
+    A.cand_thr = cthr; A.lists = plan.lists; A.query_c = query_cf; A.qc_ld = f16 ? dqc : dpad;
+    A.err_scale = f16 ? kF16ErrScale : kTf32ErrScale; A.bmax = scal; A.uncert_flags = flags;
+    A.err_abs = f16 ? scal + 5 : nullptr;
     A.gsort = nullptr; A.m_pad = m_pad; A.k1 = (k == 1);
     rerank_attrs();
     {
@@ -1238,6 +1489,12 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
     }
     k_collect_flags<<<(nq + 255) / 256, 256, 0, st>>>(flags, nq, flag_list, (int *)(scal + 1));
     YB_LAUNCH_CHECK();
+    if (f16) {
+      int overflow = 0;
+      YB_CUDA(cudaMemcpyAsync(&overflow, scal + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
+      YB_CUDA(cudaStreamSynchronize(st));
+      if (overflow) return -1001;  // a value outside FP16's range: the caller repeats with TF32
+    }
     if ((rc = redo_flagged_exact(nq, nb, d, k, base, query, assign, dis, id_offset, flag_list,
                                  (int *)(scal + 1), &n_flag, st)))
       return rc;
@@ -1475,8 +1732,53 @@ int knn_tf32_streamed(int nq, int nb, int d, int k, const float *base_host, floa
 
 using namespace yb;
 
+// Debug / test entry: raw scores s[q][n] = |b_n|^2 - 2 <q, b_n> of the FP16-operand tensor pass
+// (no centring; scale chosen as in the real pipeline).  Returns 7 when a value overflowed FP16.
+extern "C" int yb_debug_f16_scores(int nq, int nb, int d, const float *base, const float *query,
+                                   float *scores, yb_stream_t s) {
+  Guard g;
+  cudaStream_t st = stream_of(s);
+  const int dh = (d + 7) & ~7;
+  Tf32Plan plan = tf32_plan(nq, nb, dh, 1);
+  if (!plan.ok) return fail(3, "tensor path does not support this shape (d=%d)", d);
+  plan.kind = 2;
+  const long padded = tf32_padded_rows(nb);
+  ScratchScope ws(Carver::need(4ull * padded) + Carver::need(64) + Carver::need(4ull * d) +
+                      Carver::need(2ull * nb * dh) + Carver::need(2ull * nq * dh) +
+                      Carver::need(plan.ws_bytes),
+                  st);
+  Carver c(ws.p);
+  float *bn = c.take<float>(padded);
+  float *scal = c.take<float>(16);
+  float *mu = c.take<float>(d);
+  __half *bh = c.take<__half>((size_t)nb * dh);
+  __half *qh = c.take<__half>((size_t)nq * dh);
+  void *tws = c.take<char>(plan.ws_bytes);
+  YB_CUDA(cudaMemsetAsync(scal, 0, 64, st));
+  YB_CUDA(cudaMemsetAsync(mu, 0, 4ull * d, st));
+  k_absmax_sample<<<(nb + CM_ROWS - 1) / CM_ROWS, 256, 0, st>>>(base, nb, d, CM_ROWS, mu, scal + 6);
+  YB_LAUNCH_CHECK();
+  k_absmax_sample<<<(nq + CM_ROWS - 1) / CM_ROWS, 256, 0, st>>>(query, nq, d, CM_ROWS, mu, scal + 6);
+  YB_LAUNCH_CHECK();
+  k_pick_scale<<<1, 1, 0, st>>>(scal, d);
+  YB_LAUNCH_CHECK();
+  launch_center_rows_h(base, nb, d, dh, dh, mu, scal, bh, nullptr, bn, st);
+  launch_center_rows_h(query, nq, d, dh, dh, mu, scal, qh, nullptr, nullptr, st);
+  int rc;
+  if ((rc = fill_f32(bn + nb, padded - nb, __builtin_inff(), st))) return rc;
+  plan.acc_scale = scal + 3;
+  if ((rc = tf32_scores(plan, nq, nb, dh, tf32_tiles(nb), 1, (const float *)bh, (const float *)qh, bn,
+                        scores, nb, tws, st)))
+    return rc;
+  int overflow = 0;
+  YB_CUDA(cudaMemcpyAsync(&overflow, scal + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
+  YB_CUDA(cudaStreamSynchronize(st));
+  return overflow ? fail(7, "a value overflowed FP16") : 0;
+}
+
 extern "C" void yb_set_knn_engine(int engine) { g_engine_force = engine; }
 extern "C" int yb_last_knn_engine(void) { return g_last_engine; }
+extern "C" int yb_last_knn_operands(void) { return g_last_operands; }
 extern "C" long yb_last_knn_uncertified(void) { return g_last_uncert; }
 
 extern "C" int yb_knn_l2(int nq, int nb, int d, int k, const float *base, const float *query,
@@ -1486,8 +1788,12 @@ extern "C" int yb_knn_l2(int nq, int nb, int d, int k, const float *base, const 
   if (k <= 0 || k > nb) return fail(3, "yb_knn_l2: need 0 < k <= nb (k=%d, nb=%d)", k, nb);
   Guard g;
   cudaStream_t st = stream_of(s);
+  g_last_operands = tensor_operand_kind();
   int rc = knn_tf32_path(nq, nb, d, k, base, query, b_weights, assign, dis, id_offset,
-                         g_engine_force, &g_last_engine, &g_last_uncert, st);
+                         g_engine_force, &g_last_engine, &g_last_uncert, st, g_last_operands);
+  if (rc == -1001)  // data outside FP16's range (even scaled): the same pass on TF32 operands
+    g_last_operands = 0, rc = knn_tf32_path(nq, nb, d, k, base, query, b_weights, assign, dis, id_offset,
+                       g_engine_force, &g_last_engine, &g_last_uncert, st, 0);
   if (rc != -1000) return rc;  // -1000: tensor-core path not applicable
   g_last_engine = 0;
   g_last_uncert = 0;

@@ -188,6 +188,21 @@ __device__ __forceinline__ void tc_mma_f8_elect(uint32_t d_tmem, uint64_t a_desc
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f16 with FP16 operands (K = 16 per instruction, FP32 accumulate): the same 10 explicit
+// mantissa bits as TF32 at half the operand bytes -- half as many MMAs, shared-memory operand
+// reads and accumulator passes per tile.
+__device__ __forceinline__ void tc_mma_f16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
   asm volatile(
       "{\n\t"
@@ -251,16 +266,21 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) |
                                 ((uint32_t)(TM >> 4) << 24);
 
-// instruction descriptor, kind::f8f6f4: D=F32, A=B=E4M3 (format 0), both K-major, N=256, M=128
+// instruction descriptor, kind::f8f6f4 with E4M3 operands and kind::f16 with FP16 operands: D=F32,
+// A=B=format 0 (E4M3 resp. F16), both K-major, N=256, M=128
 constexpr uint32_t IDESC_F8 = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+constexpr uint32_t IDESC_F16 = IDESC_F8;
 
-// the operand kind is a template parameter of the kernel: the issue loop of the TF32
-// instantiations is unchanged by the existence of the FP8 ones
-template <bool F8>
+// operand kinds (Tf32Plan::kind).  The kind is a template parameter of the kernel: the issue
+// loop of each instantiation carries no kind branches.
+enum : int { OP_TF32 = 0, OP_F8 = 1, OP_F16 = 2 };
+template <int KIND>
 __device__ __forceinline__ void tc_mma_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                              uint32_t accumulate) {
-  if (F8)
+  if (KIND == OP_F8)
     tc_mma_f8_elect(d_tmem, a_desc, b_desc, IDESC_F8, accumulate);
+  else if (KIND == OP_F16)
+    tc_mma_f16_elect(d_tmem, a_desc, b_desc, IDESC_F16, accumulate);
   else
     tc_mma_tf32_elect(d_tmem, a_desc, b_desc, IDESC_TF32, accumulate);
 }
@@ -300,6 +320,8 @@ struct Tf32Params {
   int pair;            // 1: CTAs run as clusters of 2 that share every database chunk: each CTA
                        // fetches half of it and multicasts it to both (L2->SM traffic halves)
   int tiles_q2;        // query-tile pairs when pair != 0
+  const float *acc_scale;  // device scalar: score = acc * (*acc_scale) + |b|^2 (NULL = -2: operands
+                           // unscaled); FP16 operands are scaled by 2^sigma, *acc_scale = -2^(1-2 sigma)
   int debug;           // bring-up switches (YAEL_B200_TF32_DEBUG): 1 skip epilogue math, 2 skip MMAs
 };
 
@@ -386,9 +408,9 @@ __device__ __forceinline__ float warp_select_compact(float2 *list, int n, int kp
   return __uint_as_float(bits);
 }
 
-// (d0, d1) = (a0, a1) * (-2, -2) + (c0, c1), one packed instruction
+// (d0, d1) = (a0, a1) * (sc, sc) + (c0, c1), one packed instruction (sc = -2 for unscaled operands)
 __device__ __forceinline__ void ffma2_m2(float &d0, float &d1, uint32_t a0, uint32_t a1, float c0,
-                                         float c1) {
+                                         float c1, float sc) {
   asm("{\n\t"
       ".reg .b64 ra, rb, rc, rd;\n\t"
       "mov.b64 ra, {%2, %3};\n\t"
@@ -398,7 +420,7 @@ __device__ __forceinline__ void ffma2_m2(float &d0, float &d1, uint32_t a0, uint
       "mov.b64 {%0, %1}, rd;\n\t"
       "}"
       : "=f"(d0), "=f"(d1)
-      : "r"(a0), "r"(a1), "f"(c0), "f"(c1), "f"(-2.0f));
+      : "r"(a0), "r"(a1), "f"(c0), "f"(c1), "f"(sc));
 }
 
 #define YB_SC16_PARAMS float s0, float s1, float s2, float s3, float s4, float s5, float s6, float s7, \
@@ -461,14 +483,14 @@ __device__ __noinline__ K1State slow_append_k1(YB_SC16_PARAMS, float m, K1State 
 template <bool K1>
 __device__ __forceinline__ void process_group(const uint32_t (&v)[16], const float *bn, float &thr,
                                               float &best, float margin, float2 *mylist, int &cnt,
-                                              int cap, int id0) {
+                                              int cap, int id0, float asc) {
   float sc[16];
 #pragma unroll
   for (int c4 = 0; c4 < 4; c4++) {
     const float4 b4 = *reinterpret_cast<const float4 *>(bn + c4 * 4);
     // two packed FMAs (fma.rn.f32x2: same rounding as the scalar fmaf, half the issue slots)
-    ffma2_m2(sc[c4 * 4 + 0], sc[c4 * 4 + 1], v[c4 * 4 + 0], v[c4 * 4 + 1], b4.x, b4.y);
-    ffma2_m2(sc[c4 * 4 + 2], sc[c4 * 4 + 3], v[c4 * 4 + 2], v[c4 * 4 + 3], b4.z, b4.w);
+    ffma2_m2(sc[c4 * 4 + 0], sc[c4 * 4 + 1], v[c4 * 4 + 0], v[c4 * 4 + 1], b4.x, b4.y, asc);
+    ffma2_m2(sc[c4 * 4 + 2], sc[c4 * 4 + 3], v[c4 * 4 + 2], v[c4 * 4 + 3], b4.z, b4.w, asc);
   }
   // fminf ignores NaN operands, which is what we want: a NaN score is never admitted
   float m01 = fminf(fminf(sc[0], sc[1]), fminf(sc[2], sc[3]));
@@ -490,15 +512,15 @@ __device__ __forceinline__ void process_group(const uint32_t (&v)[16], const flo
 }
 
 // smallest score of 16 accumulator columns (sampling pass)
-__device__ __forceinline__ float group_min16(const uint32_t (&v)[16], const float *bn) {
+__device__ __forceinline__ float group_min16(const uint32_t (&v)[16], const float *bn, float asc) {
   float sc[16];
 #pragma unroll
   for (int c4 = 0; c4 < 4; c4++) {
     const float4 b4 = *reinterpret_cast<const float4 *>(bn + c4 * 4);
-    sc[c4 * 4 + 0] = fmaf(__uint_as_float(v[c4 * 4 + 0]), -2.0f, b4.x);
-    sc[c4 * 4 + 1] = fmaf(__uint_as_float(v[c4 * 4 + 1]), -2.0f, b4.y);
-    sc[c4 * 4 + 2] = fmaf(__uint_as_float(v[c4 * 4 + 2]), -2.0f, b4.z);
-    sc[c4 * 4 + 3] = fmaf(__uint_as_float(v[c4 * 4 + 3]), -2.0f, b4.w);
+    sc[c4 * 4 + 0] = fmaf(__uint_as_float(v[c4 * 4 + 0]), asc, b4.x);
+    sc[c4 * 4 + 1] = fmaf(__uint_as_float(v[c4 * 4 + 1]), asc, b4.y);
+    sc[c4 * 4 + 2] = fmaf(__uint_as_float(v[c4 * 4 + 2]), asc, b4.z);
+    sc[c4 * 4 + 3] = fmaf(__uint_as_float(v[c4 * 4 + 3]), asc, b4.w);
   }
   float m01 = fminf(fminf(sc[0], sc[1]), fminf(sc[2], sc[3]));
   float m23 = fminf(fminf(sc[4], sc[5]), fminf(sc[6], sc[7]));
@@ -544,6 +566,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
     int *hist = (int *)(smem + Smem::hist_off) + warp * 256;
     float2 *mylist = P.scratch + ((size_t)blockIdx.x * (2 * TM) + half * TM + t) * P.cap;
     const float inf = __uint_as_float(0x7f800000u);
+    const float asc = P.acc_scale ? __ldg(P.acc_scale) : -2.0f;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * HALF_N;
     uint32_t tcount = 0;
     for (int item = first_item; item < P.items; item += item_step) {
@@ -577,17 +600,17 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
 #pragma unroll
                 for (int c4 = 0; c4 < 8; c4++) {  // 128 contiguous bytes per thread
                   float4 o;
-                  o.x = fmaf(__uint_as_float(v[c4 * 4 + 0]), -2.0f, bn[g * 32 + c4 * 4 + 0]);
-                  o.y = fmaf(__uint_as_float(v[c4 * 4 + 1]), -2.0f, bn[g * 32 + c4 * 4 + 1]);
-                  o.z = fmaf(__uint_as_float(v[c4 * 4 + 2]), -2.0f, bn[g * 32 + c4 * 4 + 2]);
-                  o.w = fmaf(__uint_as_float(v[c4 * 4 + 3]), -2.0f, bn[g * 32 + c4 * 4 + 3]);
+                  o.x = fmaf(__uint_as_float(v[c4 * 4 + 0]), asc, bn[g * 32 + c4 * 4 + 0]);
+                  o.y = fmaf(__uint_as_float(v[c4 * 4 + 1]), asc, bn[g * 32 + c4 * 4 + 1]);
+                  o.z = fmaf(__uint_as_float(v[c4 * 4 + 2]), asc, bn[g * 32 + c4 * 4 + 2]);
+                  o.w = fmaf(__uint_as_float(v[c4 * 4 + 3]), asc, bn[g * 32 + c4 * 4 + 3]);
                   *reinterpret_cast<float4 *>(drow + c4 * 4) = o;
                 }
               } else {
 #pragma unroll
                 for (int c = 0; c < 32; c++)
                   if (col0 + c < P.dump_ld)
-                    drow[c] = fmaf(__uint_as_float(v[c]), -2.0f, bn[g * 32 + c]);
+                    drow[c] = fmaf(__uint_as_float(v[c]), asc, bn[g * 32 + c]);
               }
             }
           }
@@ -604,14 +627,14 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           for (int gg = 0; gg < 4; gg++) {
             tc_wait_ld();
             tc_ld16(ta + gg * 32 + 16, vb);
-            gm = fminf(gm, group_min16(va, bn + gg * 32));
+            gm = fminf(gm, group_min16(va, bn + gg * 32, asc));
             if (((2 * gg + 1) % fold) == 0) {
               if (valid) grow[(2 * gg + 1) / fold - 1] = gm;
               gm = inf;
             }
             tc_wait_ld();
             if (gg < 3) tc_ld16(ta + gg * 32 + 32, va);
-            gm = fminf(gm, group_min16(vb, bn + gg * 32 + 16));
+            gm = fminf(gm, group_min16(vb, bn + gg * 32 + 16, asc));
             if (((2 * gg + 2) % fold) == 0) {
               if (valid) grow[(2 * gg + 2) / fold - 1] = gm;
               gm = inf;
@@ -624,8 +647,8 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           if (P.debug & 8) {  // bring-up: math on whatever the registers hold, no TMEM traffic
 #pragma unroll
             for (int c = 0; c < 16; c++) va[c] = vb[c] = 0x3f800000u + c + jt;
-            process_group<false>(va, bn, thr, best, margin, mylist, cnt, P.cap, n0);
-            process_group<false>(vb, bn + 16, thr, best, margin, mylist, cnt, P.cap, n0 + 16);
+            process_group<false>(va, bn, thr, best, margin, mylist, cnt, P.cap, n0, asc);
+            process_group<false>(vb, bn + 16, thr, best, margin, mylist, cnt, P.cap, n0 + 16, asc);
           } else if (P.debug & 4) {  // bring-up: TMEM traffic only
 #pragma unroll 1
             for (int g = 0; g < 8; g++) {
@@ -638,11 +661,11 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
   _Pragma("unroll 1") for (int gg = 0; gg < 4; gg++) {                                          \
     tc_wait_ld();                                                                               \
     tc_ld16(ta + gg * 32 + 16, vb);                                                             \
-    process_group<K1FLAG>(va, bn + gg * 32, thr, best, margin, mylist, cnt, P.cap, n0 + gg * 32); \
+    process_group<K1FLAG>(va, bn + gg * 32, thr, best, margin, mylist, cnt, P.cap, n0 + gg * 32, asc); \
     tc_wait_ld();                                                                               \
     if (gg < 3) tc_ld16(ta + gg * 32 + 32, va);                                                 \
     process_group<K1FLAG>(vb, bn + gg * 32 + 16, thr, best, margin, mylist, cnt, P.cap,         \
-                          n0 + gg * 32 + 16);                                                   \
+                          n0 + gg * 32 + 16, asc);                                              \
   }
             if (k1) {
               YB_TILE_GROUPS(true)
@@ -748,7 +771,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int MODE, bool F8>
+template <int MODE, int KIND>
 __global__ void __launch_bounds__(TF32_THREADS, 1)
 k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_b,
            const __grid_constant__ CUtensorMap map_bh, const Tf32Params P) {
@@ -806,7 +829,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 
   if (warp == EPI_WARPS) {
     // ======================================================================== TMA producer
-    constexpr int KCE = F8 ? KC * 4 : KC;  // elements per 128-byte K chunk (TMA coordinates)
+    constexpr int KCE = KIND == OP_F8 ? KC * 4 : (KIND == OP_F16 ? KC * 2 : KC);  // elements per 128-byte K chunk (TMA coordinates)
     if (lane == 0) {
       uint32_t icount = 0, ccount = 0, tcount = 0;
       for (int item = first_item; item < P.items; item += item_step, icount++) {
@@ -872,10 +895,10 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
               tc_fence_after();
               const uint64_t adesc = smem_desc_sw128(sbase + Smem::a_off + kc * A_CHUNK_BYTES);
               const uint64_t bdesc = smem_desc_sw128(sbase + Smem::b_off + kc * B_CHUNK_BYTES);
-              tc_mma_elect<F8>(d_tmem, adesc, bdesc, kc != 0);
-              tc_mma_elect<F8>(d_tmem, adesc + 2, bdesc + 2, 1);
-              tc_mma_elect<F8>(d_tmem, adesc + 4, bdesc + 4, 1);
-              tc_mma_elect<F8>(d_tmem, adesc + 6, bdesc + 6, 1);
+              tc_mma_elect<KIND>(d_tmem, adesc, bdesc, kc != 0);
+              tc_mma_elect<KIND>(d_tmem, adesc + 2, bdesc + 2, 1);
+              tc_mma_elect<KIND>(d_tmem, adesc + 4, bdesc + 4, 1);
+              tc_mma_elect<KIND>(d_tmem, adesc + 6, bdesc + 6, 1);
               if (P.pair)
                 tc_commit_mc_elect(bar(Smem::b_empty + kc), (uint16_t)3);
               else
@@ -892,13 +915,13 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
             // advancing K inside the 128-byte swizzle span: +32 bytes = +2 in 16-byte units
             if (!skip_mma) {
               if (kc != P.nkc - 1 || P.last_k8 == 4) {
-                tc_mma_elect<F8>(d_tmem, adesc, bdesc, kc != 0);
-                tc_mma_elect<F8>(d_tmem, adesc + 2, bdesc + 2, 1);
-                tc_mma_elect<F8>(d_tmem, adesc + 4, bdesc + 4, 1);
-                tc_mma_elect<F8>(d_tmem, adesc + 6, bdesc + 6, 1);
+                tc_mma_elect<KIND>(d_tmem, adesc, bdesc, kc != 0);
+                tc_mma_elect<KIND>(d_tmem, adesc + 2, bdesc + 2, 1);
+                tc_mma_elect<KIND>(d_tmem, adesc + 4, bdesc + 4, 1);
+                tc_mma_elect<KIND>(d_tmem, adesc + 6, bdesc + 6, 1);
               } else {
                 for (int k8 = 0; k8 < P.last_k8; k8++)
-                  tc_mma_elect<F8>(d_tmem, adesc + (uint64_t)(2 * k8), bdesc + (uint64_t)(2 * k8),
+                  tc_mma_elect<KIND>(d_tmem, adesc + (uint64_t)(2 * k8), bdesc + (uint64_t)(2 * k8),
                                    (kc | k8) != 0);
               }
             }
@@ -984,6 +1007,22 @@ static int make_map_u8(CUtensorMap *m, const void *ptr, long rows, int pitch, in
   return 0;
 }
 
+// the same over a row-major [rows][d] FP16 matrix (d a multiple of 8: 16-byte row pitch):
+// box = 64 halfs (128 bytes) x box_rows
+static int make_map_f16(CUtensorMap *m, const void *ptr, long rows, int d, int box_rows) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return fail(6, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)d * 2};
+  cuuint32_t box[2] = {(cuuint32_t)(KC * 2), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(6, "cuTensorMapEncodeTiled (f16) failed with code %d", (int)r);
+  return 0;
+}
+
 // Independent CTAs (default) or CTA pairs that multicast the database chunks (YAEL_B200_PAIR=1).
 // Measured on the bench shape: pairing halves the L2->SM traffic but does not shorten the pass
 // (6.02 vs 5.90 ms) -- the L2 feed is not what bounds this kernel -- so it stays opt-in.
@@ -1049,12 +1088,12 @@ Tf32Plan tf32_plan(int nq, int nb, int d, int k) {
   return tf32_plan_tiles(nq, (nb + TN - 1) / TN, d, tf32_kprime_for(k));
 }
 
-template <int MODE, bool F8 = false>
+template <int MODE, int KIND = OP_TF32>
 static int launch_mode(const Tf32Plan &plan, const CUtensorMap &mq, const CUtensorMap &mb,
                        const CUtensorMap &mbh, const Tf32Params &P, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_knn_tf32<MODE, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_knn_tf32<MODE, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          TF32_SMEM_BYTES);
     if (e != cudaSuccess) return fail(6, "cannot reserve %d bytes of shared memory: %s",
                                       TF32_SMEM_BYTES, cudaGetErrorString(e));
@@ -1073,11 +1112,11 @@ static int launch_mode(const Tf32Plan &plan, const CUtensorMap &mq, const CUtens
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_knn_tf32<MODE, F8>, mq, mb, mbh, P);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_knn_tf32<MODE, KIND>, mq, mb, mbh, P);
     if (e != cudaSuccess) return fail(2, "k_knn_tf32 cluster launch: %s", cudaGetErrorString(e));
     count_launch();
   } else {
-    k_knn_tf32<MODE, F8><<<plan.ctas, TF32_THREADS, TF32_SMEM_BYTES, st>>>(mq, mb, mbh, P);
+    k_knn_tf32<MODE, KIND><<<plan.ctas, TF32_THREADS, TF32_SMEM_BYTES, st>>>(mq, mb, mbh, P);
     YB_LAUNCH_CHECK();
   }
   return 0;
@@ -1094,13 +1133,22 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   int rc;
   Tf32Params P = {};
   P.nq = nq; P.nb = nb; P.d = d;
-  if (plan.f8) {
+  if (plan.kind == OP_F8) {
     // E4M3 operands: d floats of pitch = 4*d bytes = 4*d elements per row; a K chunk is the same
     // 128-byte swizzle span (128 elements), an MMA covers 32 of them
     const int pitch = 4 * d;
     if ((rc = make_map_u8(&mq, query, nq, pitch, TM))) return rc;
     if ((rc = make_map_u8(&mb, base, nb, pitch, TN))) return rc;
     if ((rc = make_map_u8(&mbh, base, nb, pitch, TN / 2))) return rc;
+    P.nkc = (pitch + 127) / 128;
+    P.last_k8 = (pitch - (P.nkc - 1) * 128 + 31) / 32;
+  } else if (plan.kind == OP_F16) {
+    // FP16 operands: d halfs per row (d % 8 == 0); a K chunk holds 64 of them, an MMA 16
+    if (d % 8) return fail(6, "FP16 operands need a row pitch that is a multiple of 8 elements");
+    const int pitch = 2 * d;
+    if ((rc = make_map_f16(&mq, query, nq, d, TM))) return rc;
+    if ((rc = make_map_f16(&mb, base, nb, d, TN))) return rc;
+    if ((rc = make_map_f16(&mbh, base, nb, d, TN / 2))) return rc;
     P.nkc = (pitch + 127) / 128;
     P.last_k8 = (pitch - (P.nkc - 1) * 128 + 31) / 32;
   } else {
@@ -1142,13 +1190,22 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   P.dump = dump;
   P.dump_ld = dump_ld;
   const int mode = dump ? EPI_DUMP : (P.gmin ? EPI_GMIN : (k1_margin ? EPI_NEAREST : EPI_LISTS));
-  if (plan.f8) {
+  P.acc_scale = plan.acc_scale;
+  if (plan.kind == OP_F8) {
     if (plan.pair) return fail(6, "the E4M3 operand kind has no paired-CTA variant");
     switch (mode) {
-      case EPI_DUMP: return launch_mode<EPI_DUMP, true>(plan, mq, mb, mbh, P, st);
-      case EPI_GMIN: return launch_mode<EPI_GMIN, true>(plan, mq, mb, mbh, P, st);
-      case EPI_LISTS: return launch_mode<EPI_LISTS, true>(plan, mq, mb, mbh, P, st);
+      case EPI_DUMP: return launch_mode<EPI_DUMP, OP_F8>(plan, mq, mb, mbh, P, st);
+      case EPI_GMIN: return launch_mode<EPI_GMIN, OP_F8>(plan, mq, mb, mbh, P, st);
+      case EPI_LISTS: return launch_mode<EPI_LISTS, OP_F8>(plan, mq, mb, mbh, P, st);
       default: return fail(6, "the E4M3 operand kind has no k = 1 margin mode");
+    }
+  }
+  if (plan.kind == OP_F16) {
+    switch (mode) {
+      case EPI_DUMP: return launch_mode<EPI_DUMP, OP_F16>(plan, mq, mb, mbh, P, st);
+      case EPI_GMIN: return launch_mode<EPI_GMIN, OP_F16>(plan, mq, mb, mbh, P, st);
+      case EPI_NEAREST: return launch_mode<EPI_NEAREST, OP_F16>(plan, mq, mb, mbh, P, st);
+      default: return launch_mode<EPI_LISTS, OP_F16>(plan, mq, mb, mbh, P, st);
     }
   }
   switch (mode) {
