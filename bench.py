@@ -604,14 +604,17 @@ def run_ours(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    # denominator: MEASURED_PEAKS.json holds the dense bf16 GEMM rate of this pool's B200s;
-    # kind::tf32 runs at half the bf16 rate on tcgen05, so the TF32 roofline is bf16_tflops / 2
-    # ("of measured").  The cuBLAS TF32 GEMM rate measured in this very run is reported beside it.
+    # denominator: MEASURED_PEAKS.json holds the dense bf16 GEMM rate of this pool's B200s ("of
+    # measured").  The resident passes read FP16 operands (kind::f16 runs at the bf16 rate); if the
+    # library fell back to TF32 operands (kind::tf32, half that rate) the peak is bf16_tflops / 2.
+    # The cuBLAS TF32 GEMM rate measured in this very run is reported beside it.
     tf32_meas = measure_tf32_peak(torch, dev) if world == 1 else None
     bf16_peak = peaks.get("bf16_tflops", 1590.0)
-    peak = bf16_peak / 2.0
-    peak_src = ("MEASURED_PEAKS.json bf16_tflops / 2 (TF32 dense = half the bf16 rate), of measured"
-                if peaks else "half of the fallback 1590 TF/s bf16, of fallback")
+    operands = "fp16" if L.yb_last_knn_operands() == 2 else "tf32"
+    peak = bf16_peak if operands == "fp16" else bf16_peak / 2.0
+    src = "MEASURED_PEAKS.json bf16_tflops" if peaks else "fallback 1590 TF/s bf16"
+    peak_src = (src + (" (FP16 operands run at the bf16 rate)" if operands == "fp16" else
+                       " / 2 (TF32 dense = half the bf16 rate)") + (", of measured" if peaks else ", of fallback"))
     roof = None
     if "tf32_shortlist" in phase_ms:
         kms = phase_ms["tf32_shortlist"]
@@ -621,7 +624,12 @@ def run_ours(args):
             traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_knn_tf32_traffic.json")))["dram_bytes_per_launch"]
         except Exception:
             pass
-        roof = {"bound": "tensor", "kernel": "k_knn_tf32 (full pass; the sampling passes are in phase_ms)",
+        roof = {"bound": "tensor",
+                "kernel": "k_knn_tf32<EPI_LISTS, %s> (full pass; the sampling passes are in phase_ms)" % operands,
+                "operands": operands,
+                "note": ("2 MMA passes fewer per tile than TF32, so the pass is paced by draining the 128 x 256 "
+                         "FP32 accumulator from TMEM (64 B/clk/SM: >= 2048 clk per tile, 2062 tiles per SM) and "
+                         "by the admission path, not by the MMA rate -- see DESIGN.md 5.1"),
                 "achieved": ach, "peak": peak,
                 "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "kernel_ms": kms, "peak_source": peak_src,
@@ -646,7 +654,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (tf32 tensor-core shortlist, exact f32 re-rank)",
+        "dtype": "f32 (%s tensor-core shortlist with FP32 accumulation, exact f32 re-rank)" % operands,
         "data": "synthetic uniform[0,1), seeds 1234/1235",
         "config": {
             "workload": WORKLOAD,
@@ -654,7 +662,7 @@ def run_ours(args):
                             "database sharded x%d (1M rows per rank), NCCL all-gather of per-rank "
                             "top-k + merge; value counts query x 1M-shard scans" % world),
             "l2": "database (512 MB) is larger than L2 (126 MB): no flush needed between steps",
-            "engine": "tcgen05 TF32 + FP32 re-rank" if engine == 1 else "exact FP32 SIMT",
+            "engine": ("tcgen05 %s + FP32 re-rank" % operands) if engine == 1 else "exact FP32 SIMT",
             "uncertified_queries_redone_exactly": int(uncert),
             "phase_ms": phase_ms,
         },

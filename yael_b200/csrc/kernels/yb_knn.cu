@@ -834,26 +834,33 @@ static int center_operands(int nq, int nb, int d, int dpad, const float *base, c
 // in the caller's units.  A finite value that still overflows FP16 raises a flag and the caller
 // repeats the pass with TF32 operands.  scal[] layout (device floats): [0] max |b-mu|,
 // [1] flag count (int), [2] 2^sigma, [3] -2^(1-2 sigma), [4] overflow flag (int),
-// [5] absolute-error coefficient, [6] sampled max |x-mu|.
+// [5] absolute-error coefficient, [6] sampled max |x|.
 __global__ void __launch_bounds__(256)
-k_absmax_sample(const float *__restrict__ x, long n, int d, long block_step,
-                const float *__restrict__ mu, float *__restrict__ out) {
+k_absmax_sample(const float *__restrict__ x, long n, int d, long block_step, float *__restrict__ out) {
+  // max |x| over the block's CM_ROWS sampled rows (contiguous in memory: flat, coalesced, 8 loads
+  // in flight per thread).  |x - mu| <= max|x| + max|mu|: k_pick_scale adds the second term.
   const long r0 = (long)blockIdx.x * block_step, r1 = min(n, r0 + CM_ROWS);
+  const float *p = x + r0 * d;
+  const long cnt = (r1 - r0) * d;
   float m = 0.f;
-  for (int c = threadIdx.x; c < d; c += 256) {
-    const float muc = mu[c];
-    for (long r = r0; r < r1; r++) {
-      const float v = fabsf(x[r * d + c] - muc);
-      if (isfinite(v)) m = fmaxf(m, v);
-    }
+  for (long i0 = threadIdx.x; i0 < cnt; i0 += 256 * 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = i0 + j * 256 < cnt ? fabsf(p[i0 + j * 256]) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (isfinite(v[j])) m = fmaxf(m, v[j]);
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) atomicMax((int *)out, __float_as_int(m));  // m >= 0
 }
 
-__global__ void k_pick_scale(float *__restrict__ scal, int d) {
-  const float m = scal[6];
+__global__ void k_pick_scale(float *__restrict__ scal, int d, const float *__restrict__ mu) {
+  float mm = 0.f;
+  for (int c = 0; c < d; c++)
+    if (isfinite(mu[c])) mm = fmaxf(mm, fabsf(mu[c]));
+  const float m = scal[6] + mm;  // >= max |x - mu| over the sample
   int sigma = 0;
   if (m > 0.f && isfinite(m)) {
     const float x = 8188.0f / m;
@@ -994,15 +1001,15 @@ static int center_operands_h(int nq, int nb, int d, int dh, int df, const float 
   YB_LAUNCH_CHECK();
   k_col_final<<<(d + 127) / 128, 128, 0, st>>>(psum, pcnt, nblk, d, mu);
   YB_LAUNCH_CHECK();
-  k_absmax_sample<<<nblk, 256, 0, st>>>(base, nb, d, step, mu, scal + 6);
+  k_absmax_sample<<<nblk, 256, 0, st>>>(base, nb, d, step, scal + 6);
   YB_LAUNCH_CHECK();
   int qblk = (int)(((long)nq + CM_ROWS - 1) / CM_ROWS);
   if (qblk > CM_BLOCKS) qblk = CM_BLOCKS;
   long qstep = qblk > 0 ? (long)nq / qblk : CM_ROWS;
   if (qstep < CM_ROWS) qstep = CM_ROWS;
-  k_absmax_sample<<<qblk, 256, 0, st>>>(query, nq, d, qstep, mu, scal + 6);
+  k_absmax_sample<<<qblk, 256, 0, st>>>(query, nq, d, qstep, scal + 6);
   YB_LAUNCH_CHECK();
-  k_pick_scale<<<1, 1, 0, st>>>(scal, d);
+  k_pick_scale<<<1, 1, 0, st>>>(scal, d, mu);
   YB_LAUNCH_CHECK();
   launch_center_rows_h(base, nb, d, dh, dh, mu, scal, base_h, nullptr, bnorm, st);
   launch_center_rows_h(query, nq, d, dh, df, mu, scal, query_h, query_c, qcnorm, st);
@@ -1756,11 +1763,11 @@ extern "C" int yb_debug_f16_scores(int nq, int nb, int d, const float *base, con
   void *tws = c.take<char>(plan.ws_bytes);
   YB_CUDA(cudaMemsetAsync(scal, 0, 64, st));
   YB_CUDA(cudaMemsetAsync(mu, 0, 4ull * d, st));
-  k_absmax_sample<<<(nb + CM_ROWS - 1) / CM_ROWS, 256, 0, st>>>(base, nb, d, CM_ROWS, mu, scal + 6);
+  k_absmax_sample<<<(nb + CM_ROWS - 1) / CM_ROWS, 256, 0, st>>>(base, nb, d, CM_ROWS, scal + 6);
   YB_LAUNCH_CHECK();
-  k_absmax_sample<<<(nq + CM_ROWS - 1) / CM_ROWS, 256, 0, st>>>(query, nq, d, CM_ROWS, mu, scal + 6);
+  k_absmax_sample<<<(nq + CM_ROWS - 1) / CM_ROWS, 256, 0, st>>>(query, nq, d, CM_ROWS, scal + 6);
   YB_LAUNCH_CHECK();
-  k_pick_scale<<<1, 1, 0, st>>>(scal, d);
+  k_pick_scale<<<1, 1, 0, st>>>(scal, d, mu);
   YB_LAUNCH_CHECK();
   launch_center_rows_h(base, nb, d, dh, dh, mu, scal, bh, nullptr, bn, st);
   launch_center_rows_h(query, nq, d, dh, dh, mu, scal, qh, nullptr, nullptr, st);
