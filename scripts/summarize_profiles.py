@@ -10,6 +10,37 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed.avg.per_cycle_elapsed",
+        "smsp__inst_executed.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_sector_hit_rate.pct",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio"]
+
+
+def one_kernel(rep, out_md, title, note):
+    """--kernel mode: the raw page of ONE captured launch -> a small markdown table."""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(io.StringIO(raw)))
+    m = {n: (u, v) for n, u, v in zip(rr[0], rr[1], rr[2])}
+    with open(out_md, "w") as f:
+        f.write("# %s\n\n%s\n\n| metric | value | unit |\n|---|---:|---|\n" % (title, note))
+        f.write("| kernel | `%s` | |\n" % m.get("Kernel Name", ("", "?"))[1][:90])
+        for k in KEYS:
+            u, v = m.get(k, ("", "nan"))
+            f.write("| `%s` | %s | %s |\n" % (k, v, u))
+    print("wrote", out_md)
+
+
+if sys.argv[1] == "--kernel":  # summarize_profiles.py --kernel <rep> <out.md> <title> <note>
+    one_kernel(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else "")
+    sys.exit(0)
+
 tag, launches, rep = sys.argv[1], sys.argv[2], sys.argv[3]
 bench = sys.argv[4] if len(sys.argv) > 4 else None
 out = os.path.join(ROOT, "profiles")

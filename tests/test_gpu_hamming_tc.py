@@ -187,3 +187,22 @@ def test_packed_accumulators_are_exact(nq, nb, nc, slots):
     assert np.array_equal(got, want)
     for a in (db, dq, out):
         a.free()
+
+
+@pytest.mark.parametrize("slots", ["1", "2", "3"])
+def test_tensor_engine_every_packing_is_bit_exact(yn, ob, tc_engine, monkeypatch, slots):
+    # 64-bit codes default to three database rows per accumulator; YAEL_B200_HAM_SLOTS caps it.
+    # nb not a multiple of the packing, k = 128 (the largest k with three slots), heavy ties.
+    monkeypatch.setenv("YAEL_B200_HAM_SLOTS", slots)
+    r = rs(int(slots) + 40)
+    for nb, nq, nc, k in ((50001, 300, 8, 100), (40003, 64, 8, 128), (35000, 130, 4, 10), (70001, 50, 16, 40)):
+        b = r.randint(0, 256, (nb, nc)).astype(np.uint8)
+        q = r.randint(0, 256, (nq, nc)).astype(np.uint8)
+        b[::17] = q[0]
+        b[-1] = q[1]            # the very last row (a partially filled accumulator) is a hit
+        b[3::5003] = ~q[2]      # distance = every bit
+        idx, dis = yn.knn_hamming(q, b, k)
+        assert tc_engine.yb_last_hamming_engine() == 1
+        widx, wdis = ob.orc_nn_hamming(b, q, k)
+        assert np.array_equal(dis, wdis)
+        assert np.array_equal(idx, widx)

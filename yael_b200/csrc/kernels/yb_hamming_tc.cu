@@ -171,9 +171,34 @@ static HamSample ham_sample_geometry(int nbt, int k) {
   return s;
 }
 
+// database rows per accumulator: 3 for codes of up to 64 bits, 2 for 128 bits (the packed fields
+// are one byte each and the sum must stay below 2^23), 1 beyond; fewer when k' leaves no room for
+// a tile of packed appends.  YAEL_B200_HAM_SLOTS caps it (A/B measurements).
+static int ham_slots_for(int W, int k) {
+  int S = W == 1 ? 3 : (W == 2 ? 2 : 1);
+  if (const char *e = getenv("YAEL_B200_HAM_SLOTS")) {
+    const int cap = atoi(e);
+    if (cap >= 1 && cap < S) S = cap;
+  }
+  while (S > 1 && tf32_kprime_for(k) + 256 * S > 1024) S--;
+  return S;
+}
+
+static Tf32Plan ham_plan(int nq, int nb, int W, int k, int S) {
+  const int nc = (nb + S - 1) / S;
+  Tf32Plan plan = tf32_plan(nq, nc, 16 * W * S, k);
+  plan.kind = 1;
+  if (S > 1) {
+    plan.ham_slots = S;
+    plan.ham_nb = nb;
+    plan.ham_magic = 8388608.0f + (float)(32 * W) * (S == 3 ? 65793.0f : 257.0f);
+  }
+  return plan;
+}
+
 bool hamming_tc_supported(int nq, int nb, int W, int k) {
   if (W < 1 || W > 8 || nq < 1 || nb < 1 || k < 1 || k > nb) return false;
-  Tf32Plan plan = tf32_plan(nq, nb, 16 * W, k);
+  Tf32Plan plan = ham_plan(nq, nb, W, k, ham_slots_for(W, k));
   return plan.ok && !plan.pair && plan.lists <= HF_LISTS;
 }
 
@@ -187,22 +212,27 @@ int hamming_tc(int nq, int nb, int W, int k, const unsigned long long *pb,
   *flag_list_out = nullptr;
   *n_flag_out = 0;
   if (!hamming_tc_supported(nq, nb, W, k)) return -1000;
-  const int dfl = 16 * W;       // row pitch in floats (64 * W one-byte elements)
+  const int S = ham_slots_for(W, k);
+  const int nc = (nb + S - 1) / S;   // combined rows the tensor pass sees
+  const int dfl = 16 * W * S;        // row pitch in floats (64 * W * S one-byte elements)
   const int bits = 64 * W;
-  Tf32Plan plan = tf32_plan(nq, nb, dfl, k);
-  plan.kind = 1;
+  Tf32Plan plan = ham_plan(nq, nb, W, k, S);
   const int kp = plan.kprime;
-  const int nbt = tf32_tiles(nb);
-  const long padded = tf32_padded_rows(nb);
+  const int nbt = tf32_tiles(nc);
+  const long padded = tf32_padded_rows(nc);
   const HamSample sg = ham_sample_geometry(nbt, k);
   Tf32Plan splan = {};
   if (sg.ok) {
     splan = tf32_plan_tiles(nq, sg.nbt_s, dfl, sg.j2);
     splan.kind = 1;
+    splan.ham_slots = plan.ham_slots;
+    splan.ham_nb = plan.ham_nb;
+    splan.ham_magic = plan.ham_magic;
   }
   const bool sample = sg.ok && splan.ok && !splan.pair;
   const size_t stride = (size_t)plan.lists * kp;
-  size_t need = Carver::need(64ull * W * nb) + Carver::need(64ull * W * nq) +
+  const size_t rowb = 64ull * W * S;
+  size_t need = Carver::need(rowb * nc) + Carver::need(rowb * nq) +
                 Carver::need(sizeof(float) * (size_t)padded) +
                 Carver::need(sizeof(float) * nq * stride) + Carver::need(sizeof(int) * nq * stride) +
                 2 * Carver::need(sizeof(float) * (size_t)nq * plan.lists) +
@@ -214,8 +244,8 @@ int hamming_tc(int nq, int nb, int W, int k, const unsigned long long *pb,
   {
     ScratchScope ws(need, st);
     Carver c(ws.p);
-    void *base8 = c.take<char>(64ull * W * nb);
-    void *query8 = c.take<char>(64ull * W * nq);
+    void *base8 = c.take<char>(rowb * nc);
+    void *query8 = c.take<char>(rowb * nq);
     float *an = c.take<float>(padded);
     float *cscore = c.take<float>(nq * stride);
     int *cid = c.take<int>(nq * stride);
@@ -229,10 +259,14 @@ int hamming_tc(int nq, int nb, int W, int k, const unsigned long long *pb,
     int rc;
     {
       ProfScope ps(12, st);
-      if ((rc = expand_codes(pb, nb, W, 1, 0, nb, base8, st))) return rc;
-      if ((rc = expand_codes(pq, nq, W, 1, 0, nq, query8, st))) return rc;
-      if ((rc = fill_f32(an, nb, 2.0f * (float)bits, st))) return rc;
-      if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
+      if ((rc = expand_codes(pb, nb, W, S, S > 1, nc, base8, st))) return rc;
+      if ((rc = expand_codes(pq, nq, W, S, 0, nq, query8, st))) return rc;
+      if (S == 1) {  // one row per accumulator: the float epilogue, s = 2 bits - 2 dot = 4 ham
+        if ((rc = fill_f32(an, nb, 2.0f * (float)bits, st))) return rc;
+        if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
+      } else {       // packed: the integer epilogue does not read |b|^2 (the ring still carries it)
+        if ((rc = fill_f32(an, padded, 0.0f, st))) return rc;
+      }
       YB_CUDA(cudaMemsetAsync(flag_count, 0, 64, st));
     }
     const float *thr0 = nullptr;
@@ -240,7 +274,7 @@ int hamming_tc(int nq, int nb, int W, int k, const unsigned long long *pb,
       ProfScope ps(13, st);
       float *gm = c.take<float>((size_t)nq * sg.gcols);
       void *stfws = c.take<char>(splan.ws_bytes);
-      if ((rc = tf32_group_min(splan, nq, nb, dfl, sg.nbt_s, sg.stride, (const float *)base8,
+      if ((rc = tf32_group_min(splan, nq, nc, dfl, sg.nbt_s, sg.stride, (const float *)base8,
                                (const float *)query8, an, gm, sg.gcols, sg.gsize, stfws, st)))
         return rc;
       if ((rc = row_kth(gm, sg.gcols, nq, (int)sg.gcols, sg.j2, thr_init, st))) return rc;
@@ -252,7 +286,7 @@ int hamming_tc(int nq, int nb, int W, int k, const unsigned long long *pb,
     {
       ProfScope ps(14, st);
       Tf32Out mo = {ccnt, 0, 0, 0};
-      if ((rc = tf32_shortlist(plan, nq, nb, dfl, nbt, 1, (const float *)base8, (const float *)query8,
+      if ((rc = tf32_shortlist(plan, nq, nc, dfl, nbt, 1, (const float *)base8, (const float *)query8,
                                an, thr0, cscore, cid, cthr, tfws, st, &mo)))
         return rc;
     }

@@ -32,6 +32,10 @@ struct Tf32Plan {
                    // (kind::f8f6f4; `base` / `query` point to [rows][4*d] BYTE matrices -- the Hamming
                    // path); 2 = FP16 (kind::f16; [rows][d] half matrices, d % 8 == 0)
   const float *acc_scale;  // device scalar a: score = acc * a + |b|^2 (NULL: a = -2)
+  // kind 1 only: > 1 = packed Hamming passes (yb_hamming_tc.cu): ham_slots consecutive database
+  // rows share one accumulator; ham_nb real rows; ham_magic = 2^23 + (bits/2)(1 + 2^8 [+ 2^16])
+  int ham_slots, ham_nb;
+  float ham_magic;
 };
 Tf32Plan tf32_plan(int nq, int nb, int d, int k);
 Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kprime);

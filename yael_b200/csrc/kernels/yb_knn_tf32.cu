@@ -320,6 +320,13 @@ struct Tf32Params {
   int pair;            // 1: CTAs run as clusters of 2 that share every database chunk: each CTA
                        // fetches half of it and multicasts it to both (L2->SM traffic halves)
   int tiles_q2;        // query-tile pairs when pair != 0
+  // packed Hamming modes (EPI_HAMP / EPI_HAMG): every accumulator carries ham_slots distances of
+  // ham_slots consecutive database rows, acc = dot_0 + 2^8 dot_1 + 2^16 dot_2 (yb_hamming_tc.cu)
+  int order;           // work items: 0 = range-major (CTAs of a wave stream the SAME database range),
+                       // 1 = query-tile-major (a wave covers every range: ~148/splits CTAs per range)
+  int ham_slots;       // 2 or 3
+  int ham_nb;          // real database rows (ids >= ham_nb are padding)
+  float ham_magic;     // 2^23 + (bits/2)(1 + 2^8 [+ 2^16]): fma(acc, -0.5, magic) holds ham_i in byte i
   const float *acc_scale;  // device scalar: score = acc * (*acc_scale) + |b|^2 (NULL = -2: operands
                            // unscaled); FP16 operands are scaled by 2^sigma, *acc_scale = -2^(1-2 sigma)
   int debug;           // bring-up switches (YAEL_B200_TF32_DEBUG): 1 skip epilogue math, 2 skip MMAs
@@ -529,6 +536,77 @@ __device__ __forceinline__ float group_min16(const uint32_t (&v)[16], const floa
   return fminf(fminf(m01, m23), fminf(m45, m67));
 }
 
+// ------------------------------------------------------------------ packed Hamming helpers
+#define YB_U16_PARAMS uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5, \
+                      uint32_t w6, uint32_t w7, uint32_t w8, uint32_t w9, uint32_t w10, uint32_t w11, \
+                      uint32_t w12, uint32_t w13, uint32_t w14, uint32_t w15
+
+// admission threshold of the packed modes: thr is in score units (4 * ham); a row is admitted iff
+// ham < tau = ceil(thr / 4).  The byte test below needs tau <= 128, so thr is capped at 512 (rows
+// at distance >= 128 are then "refused at 512", which the list threshold reports faithfully).
+__device__ __forceinline__ uint32_t ham_tau3(float &thr) {
+  thr = fminf(thr, 512.0f);
+  const int tau = thr > 0.f ? (int)ceilf(thr * 0.25f) : 0;
+  return (uint32_t)tau * 0x010101u;
+}
+
+// w = bits of fma(acc, -0.5, magic): byte i = ham_i.  Scan the 16 words of a group; row id of
+// (word c, slot i) = row0 + c * slots + i.
+__device__ __noinline__ int slow_append_ham(YB_U16_PARAMS, uint32_t tau3, uint32_t mask, int slots,
+                                            float2 *mylist, int cnt, int row0, int nb_real) {
+  const uint32_t w[16] = {w0, w1, w2, w3, w4, w5, w6, w7, w8, w9, w10, w11, w12, w13, w14, w15};
+  const int tau = (int)(tau3 & 0xffu);
+#pragma unroll
+  for (int c = 0; c < 16; c++) {
+    const uint32_t x = w[c];
+    if ((((x - tau3) & ~x) & mask) == 0u) continue;
+    for (int i = 0; i < slots; i++) {
+      const int h = (int)((x >> (8 * i)) & 0xffu);
+      const int row = row0 + c * slots + i;
+      if (h < tau && row < nb_real) {
+        mylist[cnt] = make_float2((float)(4 * h), __int_as_float(row));
+        cnt++;
+      }
+    }
+  }
+  return cnt;
+}
+
+// 16 packed accumulators of one query: per accumulator half an FFMA2, one IADD and one LOP3 decide
+// whether ANY of its (up to three) distances is below the threshold ("has a byte less than tau":
+// ((x - tau * 0x010101) & ~x & 0x808080) != 0, exact for the existence test, tau <= 128)
+__device__ __forceinline__ void process_group_ham(const uint32_t (&v)[16], float magic, uint32_t tau3,
+                                                  uint32_t mask, int slots, float2 *mylist, int &cnt,
+                                                  int row0, int nb_real) {
+  uint32_t w[16];
+  uint32_t orr = 0u;
+#pragma unroll
+  for (int c = 0; c < 16; c += 2) {
+    float y0, y1;
+    ffma2_m2(y0, y1, v[c], v[c + 1], magic, magic, -0.5f);
+    w[c] = __float_as_uint(y0);
+    w[c + 1] = __float_as_uint(y1);
+    orr |= (w[c] - tau3) & ~w[c];
+    orr |= (w[c + 1] - tau3) & ~w[c + 1];
+  }
+  if (orr & mask)
+    cnt = slow_append_ham(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], w[8], w[9], w[10], w[11],
+                          w[12], w[13], w[14], w[15], tau3, mask, slots, mylist, cnt, row0, nb_real);
+}
+
+// smallest distance among the slots of 16 packed accumulators, as a score (sampling pass)
+__device__ __forceinline__ float ham_group_min16(const uint32_t (&v)[16], float magic, int slots) {
+  uint32_t m = 255u;
+#pragma unroll
+  for (int c = 0; c < 16; c++) {
+    const uint32_t x = __float_as_uint(fmaf(__uint_as_float(v[c]), -0.5f, magic));
+    m = min(m, x & 0xffu);
+    m = min(m, (x >> 8) & 0xffu);
+    if (slots == 3) m = min(m, (x >> 16) & 0x7fu);
+  }
+  return (float)(4u * m);
+}
+
 // ------------------------------------------------------------------ epilogue role
 struct EpiCtx {
   unsigned char *smem;
@@ -550,7 +628,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 // MODE selects what the epilogue does with a tile (one kernel instantiation per mode: the hot
 // loop of each stays compact and contiguous in the instruction cache, and carries no per-tile
 // mode branches)
-enum : int { EPI_LISTS = 0, EPI_NEAREST = 1, EPI_DUMP = 2, EPI_GMIN = 3 };
+enum : int { EPI_LISTS = 0, EPI_NEAREST = 1, EPI_DUMP = 2, EPI_GMIN = 3, EPI_HAMP = 4, EPI_HAMG = 5 };
 
 template <int MODE>
 __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &E) {
@@ -570,8 +648,9 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * HALF_N;
     uint32_t tcount = 0;
     for (int item = first_item; item < P.items; item += item_step) {
-      const int sp = item / tq_div;
-      const int qt = E.pair ? (item - sp * tq_div) * 2 + (int)crank : item - sp * tq_div;
+      const int sp = P.order ? item % P.splits : item / tq_div;
+      const int qi = P.order ? item / P.splits : item - sp * tq_div;
+      const int qt = E.pair ? qi * 2 + (int)crank : qi;
       const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
       const int q = qt * TM + t;
       const bool valid = q < P.nq;
@@ -580,6 +659,9 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
       constexpr bool k1 = MODE == EPI_NEAREST;
       const float margin = (k1 && valid) ? P.k1_margin[q] : 0.f;
       int cnt = 0;
+      uint32_t tau3 = 0u;
+      const uint32_t ham_mask = P.ham_slots == 3 ? 0x808080u : 0x8080u;
+      if (MODE == EPI_HAMP) tau3 = ham_tau3(thr);
       for (int jt = jt0; jt < jt1; jt++, tcount++) {
         const uint32_t buf = tcount & 1, slot = tcount % NBN;
         mbar_wait(bar(E.n_full0 + slot), (tcount / NBN) & 1);
@@ -640,6 +722,49 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
               gm = inf;
             }
           }
+        } else if (MODE == EPI_HAMG) {
+          // packed Hamming sampling pass: the smallest distance of every group of packed columns
+          uint32_t va[16], vb[16];
+          const uint32_t ta = lane_addr + buf * TN;
+          const int per_half = HALF_N / P.gsize;  // values this thread emits for the tile
+          float *grow = P.gmin + (size_t)(valid ? q : 0) * P.gmin_ld + ((long)jt * 2 + half) * per_half;
+          const int fold = P.gsize >> 4;          // 16-column groups per emitted value
+          float gm = inf;
+          tc_ld16(ta, va);
+#pragma unroll 1
+          for (int gg = 0; gg < 4; gg++) {
+            tc_wait_ld();
+            tc_ld16(ta + gg * 32 + 16, vb);
+            gm = fminf(gm, ham_group_min16(va, P.ham_magic, P.ham_slots));
+            if (((2 * gg + 1) % fold) == 0) {
+              if (valid) grow[(2 * gg + 1) / fold - 1] = gm;
+              gm = inf;
+            }
+            tc_wait_ld();
+            if (gg < 3) tc_ld16(ta + gg * 32 + 32, va);
+            gm = fminf(gm, ham_group_min16(vb, P.ham_magic, P.ham_slots));
+            if (((2 * gg + 2) % fold) == 0) {
+              if (valid) grow[(2 * gg + 2) / fold - 1] = gm;
+              gm = inf;
+            }
+          }
+        } else if (MODE == EPI_HAMP) {
+          // packed Hamming pass: 8 groups of 16 accumulators (16 * ham_slots database rows each)
+          uint32_t va[16], vb[16];
+          const uint32_t ta = lane_addr + buf * TN;
+          const int r0 = (jt * P.tile_stride * TN + half * HALF_N) * P.ham_slots + P.id0;
+          tc_ld16(ta, va);
+#pragma unroll 1
+          for (int gg = 0; gg < 4; gg++) {
+            tc_wait_ld();
+            tc_ld16(ta + gg * 32 + 16, vb);
+            process_group_ham(va, P.ham_magic, tau3, ham_mask, P.ham_slots, mylist, cnt,
+                              r0 + gg * 32 * P.ham_slots, P.ham_nb);
+            tc_wait_ld();
+            if (gg < 3) tc_ld16(ta + gg * 32 + 32, va);
+            process_group_ham(vb, P.ham_magic, tau3, ham_mask, P.ham_slots, mylist, cnt,
+                              r0 + (gg * 32 + 16) * P.ham_slots, P.ham_nb);
+          }
         } else if (!(P.debug & 1)) {
           // 8 groups of 16 columns, the TMEM load of group g+1 in flight while g is processed
           uint32_t va[16], vb[16];
@@ -688,7 +813,9 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           mbar_arrive(bar(E.n_empty0 + slot));
         }
         // keep room for a full half tile of appends in every list of the warp
-        unsigned need = __ballot_sync(0xffffffffu, !k1 && cnt > P.cap - HALF_N);
+        // (a packed Hamming tile can append ham_slots entries per column)
+        const int room = MODE == EPI_HAMP ? HALF_N * P.ham_slots : HALF_N;
+        unsigned need = __ballot_sync(0xffffffffu, !k1 && cnt > P.cap - room);
         while (need) {
           const int owner = __ffs(need) - 1;
           need &= need - 1;
@@ -701,6 +828,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
             cnt = P.kprime;
           }
         }
+        if (MODE == EPI_HAMP) tau3 = ham_tau3(thr);
       }
       if (MODE == EPI_NEAREST) {
         // k = 1: publish the candidates within the margin of the final best score
@@ -729,7 +857,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           P.out_thr[l] = over ? __uint_as_float(0x7fc00000u) : thr;
           if (P.out_cnt) P.out_cnt[l] = nout;
         }
-      } else if (MODE == EPI_LISTS) {
+      } else if (MODE == EPI_LISTS || MODE == EPI_HAMP) {
         // final compaction of over-full lists, then publish the shortlist of this item
         unsigned need = __ballot_sync(0xffffffffu, cnt > P.kprime);
         while (need) {
@@ -833,8 +961,9 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     if (lane == 0) {
       uint32_t icount = 0, ccount = 0, tcount = 0;
       for (int item = first_item; item < P.items; item += item_step, icount++) {
-        const int sp = item / tq_div;
-        const int qt = P.pair ? (item - sp * tq_div) * 2 + (int)crank : item - sp * tq_div;
+        const int sp = P.order ? item % P.splits : item / tq_div;
+        const int qi = P.order ? item / P.splits : item - sp * tq_div;
+        const int qt = P.pair ? qi * 2 + (int)crank : qi;
         const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
         // query tile: wait until the MMAs of the previous item have drained A
         mbar_wait(bar(Smem::a_empty), (icount & 1) ^ 1);
@@ -878,7 +1007,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       const bool skip_mma = (P.debug & 2) != 0;
       const bool ring_aligned = P.nkc == STAGES && P.last_k8 == 4;
       for (int item = first_item; item < P.items; item += item_step, icount++) {
-        const int sp = item / tq_div;
+        const int sp = P.order ? item % P.splits : item / tq_div;
         const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
         mbar_wait(bar(Smem::a_full), icount & 1);
         for (int jt = jt0; jt < jt1; jt++, tcount++) {
@@ -1191,6 +1320,21 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   P.dump_ld = dump_ld;
   const int mode = dump ? EPI_DUMP : (P.gmin ? EPI_GMIN : (k1_margin ? EPI_NEAREST : EPI_LISTS));
   P.acc_scale = plan.acc_scale;
+  {
+    const char *e = getenv("YAEL_B200_TF32_ORDER");
+    P.order = e ? atoi(e) : 0;
+  }
+  P.ham_slots = plan.ham_slots;
+  P.ham_nb = plan.ham_nb;
+  P.ham_magic = plan.ham_magic;
+  if (plan.kind == OP_F8 && plan.ham_slots > 1 && !dump) {
+    // packed Hamming passes: ham_slots database rows per accumulator, integer epilogue
+    if (plan.pair) return fail(6, "the E4M3 operand kind has no paired-CTA variant");
+    if (plan.kprime + 2 * HALF_N * plan.ham_slots > MAXL)
+      return fail(6, "packed Hamming pass: k' = %d leaves no room for a tile of appends", plan.kprime);
+    if (P.gmin) return launch_mode<EPI_HAMG, OP_F8>(plan, mq, mb, mbh, P, st);
+    return launch_mode<EPI_HAMP, OP_F8>(plan, mq, mb, mbh, P, st);
+  }
   if (plan.kind == OP_F8) {
     if (plan.pair) return fail(6, "the E4M3 operand kind has no paired-CTA variant");
     switch (mode) {
