@@ -532,6 +532,8 @@ def run_ours(args):
     sampler = ClockSampler(local, uuid)
     sampler.start()
     L.yb_launch_count(1)
+    if world > 1:
+        searcher.events = []   # per-search CUDA events: local scan / all-gather / merge
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.mark_begin()
     e0.record(stream)
@@ -544,6 +546,8 @@ def run_ours(args):
         dist.barrier()
     clocks = sampler.stop()
     launches = L.yb_launch_count(0)
+    shard_phase_ms = searcher.phase_ms() if world > 1 else None
+    searcher.events = None
     ms = e0.elapsed_time(e1) / args.steps
     cnt = C.c_long(0)
     phase_ms = {}
@@ -665,6 +669,7 @@ def run_ours(args):
             "engine": ("tcgen05 %s + FP32 re-rank" % operands) if engine == 1 else "exact FP32 SIMT",
             "uncertified_queries_redone_exactly": int(uncert),
             "phase_ms": phase_ms,
+            "shard_phase_ms_rank0": shard_phase_ms,
         },
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roof, "cpu_baseline": cpu, "extras": extras,

@@ -113,6 +113,10 @@ int yb_knn_l2_hostbase(int nq, int nb, int d, int k, const float *base_host, flo
  * entries (id < 0) sort last.  The exchange step of the sharded k-NN. */
 int yb_knn_merge(int nq, int k, int G, const int *assign_in, const float *dis_in,
                  int *assign_out, float *dis_out, yb_stream_t s);
+/* the same with an explicit distance (in elements) between the lists of consecutive shards:
+ * 2 * nq * k when each shard ships ids and distances in ONE [2][nq][k] buffer (one collective) */
+int yb_knn_merge_strided(int nq, int k, int G, const int *assign_in, const float *dis_in,
+                         long shard_stride, int *assign_out, float *dis_out, yb_stream_t s);
 /* knn_reorder_shortlist (yael/nn.c:528-580): exact one-vs-many distances for the listed
  * ids (stop at the first id < 0), re-ordered ascending by (distance, position). */
 int yb_knn_reorder_shortlist(int nq, int nb, int d, int k, const float *base,

@@ -153,6 +153,49 @@ def test_knn_merge_equals_unsharded(yn):
     assert np.array_equal(oi.get(), widx) and np.array_equal(od.get(), wdis)
 
 
+def test_knn_merge_strided_padding_and_unsorted_input():
+    # the merge ranks sorted lists (binary searches) and falls back to a sort for unsorted ones;
+    # both must give the k best by (distance, id), padding (-1, NaN bits) last; the strided entry
+    # reads ids and distances of a shard from one [2][nq][k] block (one collective)
+    L = yael_b200.lib()
+    r = np.random.RandomState(12)
+    nq, k = 37, 25
+    for G in (2, 5, 8):
+        dis = np.sort(r.randint(0, 60, (G, nq, k)).astype(np.float32), axis=2)   # heavy ties
+        ids = np.empty((G, nq, k), np.int32)
+        for g in range(G):
+            for q in range(nq):
+                ids[g, q] = g * 1000 + np.arange(k)      # ascending ids inside equal distances
+        # short lists: the tail of some lists is padding
+        dis[1, ::3, k - 7:] = np.float32(np.nan)
+        ids[1, ::3, k - 7:] = -1
+        keys = (dis.astype(np.float64) * 1e6 + ids).transpose(1, 0, 2).reshape(nq, G * k)
+        keys[np.isnan(keys)] = np.inf
+        order = np.argsort(keys, axis=1, kind="stable")[:, :k]
+        want_i = ids.transpose(1, 0, 2).reshape(nq, G * k)[np.arange(nq)[:, None], order]
+        want_d = dis.transpose(1, 0, 2).reshape(nq, G * k)[np.arange(nq)[:, None], order]
+        for variant in ("plain", "strided", "unsorted"):
+            di, dd = ids.copy(), dis.copy()
+            if variant == "unsorted":   # reverse one list: still the same multiset
+                di[0] = di[0, :, ::-1]
+                dd[0] = dd[0, :, ::-1]
+            oi, od = DevArray(shape=(nq, k), dtype=np.int32), DevArray(shape=(nq, k), dtype=np.float32)
+            if variant == "strided":
+                blk = np.stack([di, dd.view(np.int32)], axis=1)   # [G][2][nq][k]
+                gb = DevArray(blk)
+                rc = L.yb_knn_merge_strided(nq, k, G, gb.ptr, gb.ptr + 4 * nq * k, 2 * nq * k,
+                                            oi.ptr, od.ptr, None)
+            else:
+                gi, gd = DevArray(di), DevArray(dd)
+                rc = L.yb_knn_merge(nq, k, G, gi.ptr, gd.ptr, oi.ptr, od.ptr, None)
+            assert rc == 0, L.yb_last_error()
+            L.yb_sync(None)
+            got_i, got_d = oi.get(), od.get()
+            assert np.array_equal(got_i, want_i), (G, variant)
+            assert np.array_equal(got_d[want_i >= 0], want_d[want_i >= 0])
+            assert (got_i[want_i < 0] == -1).all()
+
+
 def test_hamming_merge_bit_identical_for_any_shard_count(yn):
     L = yael_b200.lib()
     r = np.random.RandomState(4)

@@ -191,7 +191,8 @@ def test_packed_accumulators_are_exact(nq, nb, nc, slots):
 
 @pytest.mark.parametrize("slots", ["1", "2", "3"])
 def test_tensor_engine_every_packing_is_bit_exact(yn, ob, tc_engine, monkeypatch, slots):
-    # 64-bit codes default to three database rows per accumulator; YAEL_B200_HAM_SLOTS caps it.
+    # 64-bit codes can pack up to three database rows per accumulator (default from 8 M rows on);
+    # YAEL_B200_HAM_SLOTS forces a packing.
     # nb not a multiple of the packing, k = 128 (the largest k with three slots), heavy ties.
     monkeypatch.setenv("YAEL_B200_HAM_SLOTS", slots)
     r = rs(int(slots) + 40)

@@ -144,6 +144,7 @@ DEVICE = {
     "yb_knn_l2": (C.c_int, [C.c_int] * 4 + [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "yb_knn_l2_hostbase": (C.c_int, [C.c_int] * 4 + [_vp] * 5 + [C.c_int, _vp]),
     "yb_knn_merge": (C.c_int, [C.c_int] * 3 + [_vp, _vp, _vp, _vp, _vp]),
+    "yb_knn_merge_strided": (C.c_int, [C.c_int] * 3 + [_vp, _vp, C.c_long, _vp, _vp, _vp]),
     "yb_knn_reorder_shortlist": (C.c_int, [C.c_int] * 4 + [_vp, _vp, _vp, _vp, _vp]),
     "yb_k_min_rows": (C.c_int, [_vp, C.c_long, C.c_long, C.c_long, C.c_int, C.c_int, _vp, _vp, _vp]),
     "yb_kmeans_accumulate": (C.c_int, [C.c_int] * 3 + [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),

@@ -171,14 +171,19 @@ static HamSample ham_sample_geometry(int nbt, int k) {
   return s;
 }
 
-// database rows per accumulator: 3 for codes of up to 64 bits, 2 for 128 bits (the packed fields
-// are one byte each and the sum must stay below 2^23), 1 beyond; fewer when k' leaves no room for
-// a tile of packed appends.  YAEL_B200_HAM_SLOTS caps it (A/B measurements).
-static int ham_slots_for(int W, int k) {
-  int S = W == 1 ? 3 : (W == 2 ? 2 : 1);
+// database rows per accumulator.  Codes of up to 64 bits CAN pack 3 rows, 128 bits 2 (the packed
+// fields are one byte each and the sum must stay below 2^23), longer ones 1; fewer when k' leaves
+// no room for a tile of packed appends.  Packing pays only when admissions are sparse, i.e. for
+// very large databases (measured, 10 k queries x 64-bit codes, pass in ms, 1 row vs 3 rows per
+// accumulator: 1.25 M rows 4.0 vs 7.5, 5 M rows 12.0 vs 13.8, 10 M rows 23.0 vs 21.6): the
+// decoder of the packed epilogue scans 48 candidates per call.  Default: pack from 8 M rows on.
+// YAEL_B200_HAM_SLOTS=1|2|3 forces a packing (tests, A/B measurements).
+static int ham_slots_for(int W, int k, long nb) {
+  const int smax = W == 1 ? 3 : (W == 2 ? 2 : 1);
+  int S = nb >= 8000000L ? smax : 1;
   if (const char *e = getenv("YAEL_B200_HAM_SLOTS")) {
-    const int cap = atoi(e);
-    if (cap >= 1 && cap < S) S = cap;
+    const int want = atoi(e);
+    if (want >= 1) S = want < smax ? want : smax;
   }
   while (S > 1 && tf32_kprime_for(k) + 256 * S > 1024) S--;
   return S;
@@ -198,7 +203,7 @@ static Tf32Plan ham_plan(int nq, int nb, int W, int k, int S) {
 
 bool hamming_tc_supported(int nq, int nb, int W, int k) {
   if (W < 1 || W > 8 || nq < 1 || nb < 1 || k < 1 || k > nb) return false;
-  Tf32Plan plan = ham_plan(nq, nb, W, k, ham_slots_for(W, k));
+  Tf32Plan plan = ham_plan(nq, nb, W, k, ham_slots_for(W, k, nb));
   return plan.ok && !plan.pair && plan.lists <= HF_LISTS;
 }
 
@@ -212,7 +217,7 @@ int hamming_tc(int nq, int nb, int W, int k, const unsigned long long *pb,
   *flag_list_out = nullptr;
   *n_flag_out = 0;
   if (!hamming_tc_supported(nq, nb, W, k)) return -1000;
-  const int S = ham_slots_for(W, k);
+  const int S = ham_slots_for(W, k, nb);
   const int nc = (nb + S - 1) / S;   // combined rows the tensor pass sees
   const int dfl = 16 * W * S;        // row pitch in floats (64 * W * S one-byte elements)
   const int bits = 64 * W;

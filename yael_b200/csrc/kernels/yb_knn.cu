@@ -245,11 +245,15 @@ __global__ void __launch_bounds__(RR_T) k_rerank(RerankArgs A) {
 }
 
 // ------------------------------------------------------------------ shard merge
-// One CTA per query: G*k (distance, id) pairs -> k best by (distance, id).
+// One CTA per query: G*k (distance, id) pairs -> k best by (distance, id).  Shard g's list for
+// query q starts at ain / din + g * sstride + q * k.  The lists yb_knn_l2 produces are sorted, so
+// the merge is a RANKING, not a sort: the merged position of an entry is its position in its own
+// list plus, for every other list, the number of entries below it (a binary search in shared
+// memory; keys are distinct because row ids are).  Unsorted input falls back to a bitonic sort.
 __global__ void __launch_bounds__(128)
 k_knn_merge(int k, int G, long nq, const int *__restrict__ ain, const float *__restrict__ din,
-            int *__restrict__ aout, float *__restrict__ dout, unsigned long long *gsort,
-            int m_pad) {
+            long sstride, int *__restrict__ aout, float *__restrict__ dout,
+            unsigned long long *gsort, int m_pad) {
   extern __shared__ unsigned long long ssort[];
   const long q = blockIdx.x;
   const int tid = threadIdx.x, m = G * k;
@@ -258,12 +262,46 @@ k_knn_merge(int k, int G, long nq, const int *__restrict__ ain, const float *__r
     unsigned long long key = ~0ull;
     if (j < m) {
       int g = j / k, r = j - g * k;
-      size_t src = ((size_t)g * nq + q) * k + r;
+      size_t src = (size_t)g * sstride + (size_t)q * k + r;
       int id = ain[src];
       uint32_t fk = float_key(din[src]);
       if (id >= 0 && !is_nan_key(fk)) key = ((unsigned long long)fk << 32) | (unsigned)id;
     }
     buf[j] = key;
+  }
+  __syncthreads();
+  int unsorted = 0;
+  for (int j = tid; j < m; j += 128)
+    if (j % k != 0 && buf[j] < buf[j - 1]) unsorted = 1;
+  if (!__syncthreads_or(unsorted)) {
+    for (int j = tid; j < k; j += 128) {  // padding first; the ranked writes below overwrite it
+      aout[q * k + j] = -1;
+      dout[q * k + j] = __uint_as_float(0xffffffffu);
+    }
+    __syncthreads();
+    for (int j = tid; j < m; j += 128) {
+      const unsigned long long key = buf[j];
+      if (key == ~0ull) continue;
+      const int g = j / k;
+      int rank = j - g * k;
+      for (int o = 0; o < G && rank < k; o++) {
+        if (o == g) continue;
+        const unsigned long long *l = buf + o * k;
+        int lo = 0, hi = k;  // lower_bound: entries of list o below key
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (l[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+      }
+      if (rank < k) {
+        const uint32_t fk = (uint32_t)(key >> 32);
+        const uint32_t bits = (fk & 0x80000000u) ? (fk & 0x7fffffffu) : ~fk;
+        aout[q * k + rank] = (int)(uint32_t)key;
+        dout[q * k + rank] = __uint_as_float(bits);
+      }
+    }
+    return;
   }
   bitonic_sort_u64(buf, m_pad, tid, 128, [] { __syncthreads(); });
   for (int j = tid; j < k; j += 128) {
@@ -1827,8 +1865,12 @@ extern "C" int yb_knn_l2_hostbase(int nq, int nb, int d, int k, const float *bas
   return yb_knn_l2(nq, nb, d, k, base_dev, query, nullptr, assign, dis, id_offset, s);
 }
 
-extern "C" int yb_knn_merge(int nq, int k, int G, const int *assign_in, const float *dis_in,
-                             int *assign_out, float *dis_out, yb_stream_t s) {
+// shard_stride: elements between the lists of consecutive shards (nq * k when every shard's
+// [nq][k] block follows the previous one; 2 * nq * k when ids and distances of a shard travel
+// in one [2][nq][k] buffer, i.e. one collective)
+extern "C" int yb_knn_merge_strided(int nq, int k, int G, const int *assign_in, const float *dis_in,
+                                    long shard_stride, int *assign_out, float *dis_out,
+                                    yb_stream_t s) {
   if (nq <= 0 || k <= 0 || G <= 0) return 0;
   Guard g;
   cudaStream_t st = stream_of(s);
@@ -1836,10 +1878,15 @@ extern "C" int yb_knn_merge(int nq, int k, int G, const int *assign_in, const fl
   size_t wsb = m_pad <= 4096 ? 256 : Carver::need(sizeof(unsigned long long) * (size_t)nq * m_pad);
   ScratchScope ws(wsb, st);
   size_t smem = m_pad <= 4096 ? sizeof(unsigned long long) * (size_t)m_pad : 0;
-  k_knn_merge<<<nq, 128, smem, st>>>(k, G, nq, assign_in, dis_in, assign_out, dis_out,
+  k_knn_merge<<<nq, 128, smem, st>>>(k, G, nq, assign_in, dis_in, shard_stride, assign_out, dis_out,
                                      (unsigned long long *)ws.p, m_pad);
   YB_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int yb_knn_merge(int nq, int k, int G, const int *assign_in, const float *dis_in,
+                             int *assign_out, float *dis_out, yb_stream_t s) {
+  return yb_knn_merge_strided(nq, k, G, assign_in, dis_in, (long)nq * k, assign_out, dis_out, s);
 }
 
 extern "C" int yb_knn_reorder_shortlist(int nq, int nb, int d, int k, const float *base,

@@ -57,7 +57,18 @@ class ShardedKnn:
         if id_offset is None:
             id_offset = rank * base.shape[0]
         self.id_offset = int(id_offset)
+        self.events = None   # set to [] to record (start, local, gathered, merged) CUDA events per search
         _lib.require_gpu()
+
+    def phase_ms(self):
+        """Average milliseconds of the three phases of the recorded searches (world > 1)."""
+        if not self.events:
+            return None
+        self.torch.cuda.synchronize()
+        n = len(self.events)
+        return {"local_scan": sum(a.elapsed_time(b) for a, b, _, _ in self.events) / n,
+                "all_gather": sum(b.elapsed_time(c) for _, b, c, _ in self.events) / n,
+                "merge": sum(c.elapsed_time(d) for _, _, c, d in self.events) / n}
 
     def _local(self, query, idx, dis):
         nq, d = query.shape
@@ -66,19 +77,46 @@ class ShardedKnn:
                               idx.data_ptr(), dis.data_ptr(), self.id_offset,
                               _stream_ptr(self.torch)), "yb_knn_l2")
 
+    def _exchange(self, buf, nq):
+        """buf: this rank's [2][nq][k] int32 block (ids, distance bits).  ONE all-gather, then the
+        merge by (distance, id) on every rank."""
+        torch = self.torch
+        import torch.distributed as dist
+        gbuf = torch.empty((self.world,) + tuple(buf.shape), dtype=torch.int32, device=buf.device)
+        dist.all_gather_into_tensor(gbuf.view(-1), buf.view(-1))
+        return gbuf
+
+    def _merge(self, gbuf, nq):
+        torch = self.torch
+        oi = torch.empty((nq, self.k), dtype=torch.int32, device=gbuf.device)
+        od = torch.empty((nq, self.k), dtype=torch.float32, device=gbuf.device)
+        check(lib().yb_knn_merge_strided(nq, self.k, self.world, gbuf.data_ptr(), gbuf[0, 1].data_ptr(),
+                                         2 * nq * self.k, oi.data_ptr(), od.data_ptr(),
+                                         _stream_ptr(torch)), "yb_knn_merge_strided")
+        return oi, od
+
     def search(self, query):
         torch = self.torch
         nq = query.shape[0]
-        idx = torch.empty((nq, self.k), dtype=torch.int32, device=query.device)
-        dis = torch.empty((nq, self.k), dtype=torch.float32, device=query.device)
+        # ids and distances of this rank side by side: they travel in one collective
+        buf = torch.empty((2, nq, self.k), dtype=torch.int32, device=query.device)
+        idx, dis = buf[0], buf[1].view(torch.float32)
+        ev = None
+        if self.events is not None and self.world > 1:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
         self._local(query, idx, dis)
         if self.world == 1:
             return idx, dis
-        import torch.distributed as dist
-        gi, gd = allgather_lists(dist, torch, idx, dis, self.world)
-        oi, od = torch.empty_like(idx), torch.empty_like(dis)
-        check(lib().yb_knn_merge(nq, self.k, self.world, gi.data_ptr(), gd.data_ptr(),
-                                 oi.data_ptr(), od.data_ptr(), _stream_ptr(torch)), "yb_knn_merge")
+        if ev:
+            ev[1].record()
+        gbuf = self._exchange(buf, nq)
+        if ev:
+            ev[2].record()
+        oi, od = self._merge(gbuf, nq)
+        if ev:
+            ev[3].record()
+            self.events.append(tuple(ev))
         return oi, od
 
     def search_host(self, base_host, query_host, idx_out, dis_out):
@@ -95,17 +133,13 @@ class ShardedKnn:
         # the shard travels over PCIe while it is being scanned (yb_knn_l2_hostbase), then the
         # usual all-gather + merge
         q = torch.from_numpy(query_host).to(self.base.device, non_blocking=True)
-        idx = torch.empty((nq, self.k), dtype=torch.int32, device=q.device)
-        dis = torch.empty((nq, self.k), dtype=torch.float32, device=q.device)
+        buf = torch.empty((2, nq, self.k), dtype=torch.int32, device=q.device)
+        idx, dis = buf[0], buf[1].view(torch.float32)
         check(lib().yb_knn_l2_hostbase(nq, base_host.shape[0], d, self.k, base_host.ctypes.data,
                                        self.base.data_ptr(), q.data_ptr(), idx.data_ptr(),
                                        dis.data_ptr(), self.id_offset, _stream_ptr(torch)),
               "yb_knn_l2_hostbase")
-        import torch.distributed as dist
-        gi, gd = allgather_lists(dist, torch, idx, dis, self.world)
-        oi, od = torch.empty_like(idx), torch.empty_like(dis)
-        check(lib().yb_knn_merge(nq, self.k, self.world, gi.data_ptr(), gd.data_ptr(),
-                                 oi.data_ptr(), od.data_ptr(), _stream_ptr(torch)), "yb_knn_merge")
+        oi, od = self._merge(self._exchange(buf, nq), nq)
         torch.from_numpy(idx_out).copy_(oi, non_blocking=True)
         torch.from_numpy(dis_out).copy_(od, non_blocking=True)
         torch.cuda.synchronize()
