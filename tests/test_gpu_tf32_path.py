@@ -95,6 +95,28 @@ def test_knn_f16_out_of_range_value_falls_back_to_tf32(yn, ob):
         L.yb_set_knn_engine(-1)
 
 
+def test_knn_too_tight_thresholds_are_retried_and_still_exact(yn, ob, monkeypatch):
+    # YAEL_B200_J2 forces admission thresholds far too tight: many queries come up short of
+    # candidates, fail their certificate, and go through the tensor retry (4x looser) and, if need
+    # be, the exact engine -- the result must not change
+    L = yael_b200.lib()
+    L.yb_set_knn_engine(1)
+    try:
+        r = rs(21)
+        nb, nq, d, k = 120000, 400, 64, 50
+        b = r.rand(nb, d).astype(np.float32)
+        q = r.rand(nq, d).astype(np.float32)
+        widx, wdis = ob.orc_knn(b, q, k, ob.DOT_F32_SEQ, canonical=True)
+        for j2 in ("2", "5"):
+            monkeypatch.setenv("YAEL_B200_J2", j2)
+            idx, dis = yn.knn(q, b, k)
+            assert L.yb_last_knn_engine() == 1
+            assert L.yb_last_knn_uncertified() > 0      # the scenario really happened
+            check_knn(idx, dis, widx, wdis)
+    finally:
+        L.yb_set_knn_engine(-1)
+
+
 @pytest.mark.parametrize("operands", ["tf32", "f16"])
 def test_knn_both_operand_kinds_match_oracle(yn, ob, operands, monkeypatch):
     monkeypatch.setenv("YAEL_B200_OPERANDS", operands)

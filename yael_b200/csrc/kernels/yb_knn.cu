@@ -1100,6 +1100,61 @@ static int redo_flagged_exact(int nq, int nb, int d, int k, const float *base, c
   return rc;
 }
 
+// Queries whose certificate failed, first resort: the tensor path once more for just those
+// queries with 4x looser admission thresholds (a fraction of a millisecond for a handful of
+// queries; the exact engine needs ~2 ms however few they are).  What still fails there -- or a
+// shape the tensor path refuses -- goes to the exact engine.
+int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *query,
+                  const float *w, int *assign, float *dis, int id_offset, int force,
+                  int *engine_out, long *uncert_out, cudaStream_t st, int kind, int retry);
+
+static int redo_flagged_tensor(int nq, int nb, int d, int k, const float *base, const float *query,
+                               int *assign, float *dis, int id_offset, const int *flag_list,
+                               const int *flag_count_dev, int *n_flag_out, cudaStream_t st,
+                               int kind) {
+  int n_flag = 0;
+  YB_CUDA(cudaMemcpyAsync(&n_flag, flag_count_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+  YB_CUDA(cudaStreamSynchronize(st));
+  *n_flag_out = n_flag;
+  if (n_flag <= 0) return 0;
+  if (n_flag > nq / 4 || k > nb)  // not a few stragglers: the exact engine directly
+    return redo_flagged_exact(nq, nb, d, k, base, query, assign, dis, id_offset, flag_list,
+                              flag_count_dev, n_flag_out, st);
+  const int n_cap = (n_flag + 255) & ~255;
+  float *qsub = (float *)yb_malloc(sizeof(float) * (size_t)n_cap * d);
+  float *dsub = (float *)yb_malloc(sizeof(float) * (size_t)n_cap * k);
+  int *asub = (int *)yb_malloc(sizeof(int) * (size_t)n_cap * k);
+  int *rows = (int *)yb_malloc(sizeof(int) * (size_t)n_cap);
+  YB_CUDA(cudaMemcpyAsync(rows, flag_list, sizeof(int) * (size_t)n_flag, cudaMemcpyDeviceToDevice, st));
+  long tot = (long)n_flag * d;
+  k_gather_rows<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(query, rows, n_flag, d, qsub);
+  count_launch();
+  int eng = 0;
+  long unc = 0;
+  int rc;
+  {
+    ProfScope ps(4, st);
+    // NOTE: this reserves the device scratch again; the caller no longer reads its own
+    rc = knn_tf32_path(n_flag, nb, d, k, base, qsub, nullptr, asub, dsub, id_offset, 1, &eng, &unc, st,
+                       kind, 1);
+    if (rc == -1000 || rc == -1001) {
+      void *ews = yb_malloc(knn_exact_ws_bytes(n_cap, nb, k));
+      rc = knn_exact(n_flag, nb, d, k, base, qsub, nullptr, asub, dsub, id_offset, ews, st);
+      cudaStreamSynchronize(st);
+      yb_free(ews);
+    }
+  }
+  if (!rc) {
+    tot = (long)n_flag * k;
+    k_scatter_results<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(rows, n_flag, k, asub, dsub,
+                                                                     assign, dis);
+    count_launch();
+    cudaStreamSynchronize(st);
+  }
+  yb_free(qsub); yb_free(dsub); yb_free(asub); yb_free(rows);
+  return rc;
+}
+
 // ------------------------------------------------------------------ engine 1, k = 1
 // margin[q] = 2.05 * E_q with E_q the TF32 score error bound of the query (see kTf32ErrScale)
 __global__ void k_k1_margin(const float *__restrict__ query, int nq, int d,
@@ -1312,7 +1367,7 @@ static int knn_tf32_nearest(int nq, int nb, int d, const float *base, const floa
 // returns -1000 when the tensor-core path does not apply (caller falls through to engine 0)
 int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *query,
                   const float *w, int *assign, float *dis, int id_offset, int force,
-                  int *engine_out, long *uncert_out, cudaStream_t st, int kind) {
+                  int *engine_out, long *uncert_out, cudaStream_t st, int kind, int retry) {
   if (force == 0 || w != nullptr) return -1000;
   const bool f16 = kind == 2;
   // the tensor pass runs on centred, pitch-padded copies (16-byte row pitch: 4 floats / 8 halfs)
@@ -1322,6 +1377,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
   if (!plan.ok) return -1000;
   if (force < 0 && (double)nq * nb < 1e6) return -1000;  // tiny problems: not worth a TMA setup
   if (k == 1) {
+    (void)retry;
     int rc1 = knn_tf32_nearest(nq, nb, d, base, query, assign, dis, id_offset, uncert_out, st, kind);
     if (rc1 == 0) *engine_out = 1;
     return rc1;
@@ -1348,9 +1404,15 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
   const int kSampleStride = 16;
   const bool use_sample = nbt >= 8 * kSampleStride;
   const int nbt_s = (nbt + kSampleStride - 1) / kSampleStride;
-  int j2 = (3 * kp + kSampleStride - 1) / kSampleStride;
-  if (j2 < 32) j2 = 32;
+  // j2-th smallest sampled group minimum: about 16 * j2 rows of the database pass the threshold
+  // (relative spread 1 / sqrt(j2)).  2k' / 16 (25 for k = 100: ~400 rows for the 100 wanted)
+  // leaves a query short of candidates about once in 10^4 (measured with FP16 operands, 10 k
+  // queries: j2 = 38 / 24 / 20 -> 0 uncertified, pass 3.22 / 2.94 / 2.86 ms; j2 = 16 -> 9); such
+  // queries are retried with 4x the threshold rank (redo_flagged_tensor), which costs little.
+  int j2 = (2 * kp + kSampleStride - 1) / kSampleStride;
+  if (j2 < 24) j2 = 24;
   if (const char *e = getenv("YAEL_B200_J2")) j2 = atoi(e) > 0 ? atoi(e) : j2;  // experiment knob
+  if (retry) j2 *= 4;
   Tf32Plan splan = {};
   if (use_sample) splan = tf32_plan_tiles(nq, nbt_s, dpad, j2);
   splan.kind = kind;
@@ -1540,9 +1602,13 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
       YB_CUDA(cudaStreamSynchronize(st));
       if (overflow) return -1001;  // a value outside FP16's range: the caller repeats with TF32
     }
-    if ((rc = redo_flagged_exact(nq, nb, d, k, base, query, assign, dis, id_offset, flag_list,
-                                 (int *)(scal + 1), &n_flag, st)))
-      return rc;
+    if (retry)
+      rc = redo_flagged_exact(nq, nb, d, k, base, query, assign, dis, id_offset, flag_list,
+                              (int *)(scal + 1), &n_flag, st);
+    else
+      rc = redo_flagged_tensor(nq, nb, d, k, base, query, assign, dis, id_offset, flag_list,
+                               (int *)(scal + 1), &n_flag, st, kind);
+    if (rc) return rc;
   }
   *engine_out = 1;
   *uncert_out = n_flag;
@@ -1835,10 +1901,10 @@ extern "C" int yb_knn_l2(int nq, int nb, int d, int k, const float *base, const 
   cudaStream_t st = stream_of(s);
   g_last_operands = tensor_operand_kind();
   int rc = knn_tf32_path(nq, nb, d, k, base, query, b_weights, assign, dis, id_offset,
-                         g_engine_force, &g_last_engine, &g_last_uncert, st, g_last_operands);
+                         g_engine_force, &g_last_engine, &g_last_uncert, st, g_last_operands, 0);
   if (rc == -1001)  // data outside FP16's range (even scaled): the same pass on TF32 operands
     g_last_operands = 0, rc = knn_tf32_path(nq, nb, d, k, base, query, b_weights, assign, dis, id_offset,
-                       g_engine_force, &g_last_engine, &g_last_uncert, st, 0);
+                       g_engine_force, &g_last_engine, &g_last_uncert, st, 0, 0);
   if (rc != -1000) return rc;  // -1000: tensor-core path not applicable
   g_last_engine = 0;
   g_last_uncert = 0;
