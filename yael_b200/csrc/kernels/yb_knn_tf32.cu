@@ -1161,7 +1161,9 @@ int tf32_pair_mode() {
 }
 
 int tf32_kprime_for(int k) {
-  int a = 2 * k, b = k + 32 < 8 * k ? k + 32 : 8 * k;
+  int pct = 200;  // k' = 2k; YAEL_B200_KPRIME_PCT: experiment knob
+  if (const char *e = getenv("YAEL_B200_KPRIME_PCT")) pct = atoi(e) >= 100 ? atoi(e) : pct;
+  int a = (int)((long)k * pct / 100), b = k + 32 < 8 * k ? k + 32 : 8 * k;
   return a > b ? a : b;
 }
 
