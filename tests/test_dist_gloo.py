@@ -39,6 +39,19 @@ def _worker(rank, world, port, q):
             out_i[j], out_d[j] = ii[order], dd[order]
         widx, wdis = ob.orc_knn(base, query, k, canonical=True)
         ok = np.array_equal(out_i, widx) and np.array_equal(out_d, wdis)
+        # the k-NN exchange proper: ids and distance bits of a rank travel as ONE [2][nq][k] block
+        # (ShardedKnn._exchange); the merge reads shard g at gbuf + g * 2*nq*k (ids) and + nq*k (dis)
+        import types
+        buf = torch.empty((2, 37, k), dtype=torch.int32)
+        buf[0] = torch.from_numpy(idx)
+        buf[1] = torch.from_numpy(dis).view(torch.int32)
+        stub = types.SimpleNamespace(torch=torch, world=world)
+        gbuf = ydist.ShardedKnn._exchange(stub, buf, 37)
+        flat = gbuf.numpy().reshape(-1)
+        for g in range(world):
+            ids_g = flat[g * 2 * 37 * k: g * 2 * 37 * k + 37 * k].reshape(37, k)
+            dis_g = flat[g * 2 * 37 * k + 37 * k: (g + 1) * 2 * 37 * k].view(np.float32).reshape(37, k)
+            ok = ok and np.array_equal(ids_g, gi[g]) and np.array_equal(dis_g, gd[g])
         # sharded k-means bookkeeping: all-reduced sums / counts == unsharded accumulation
         v = r.random_sample((600, 4)).astype(np.float32)
         cent = v[:5].copy()
