@@ -641,6 +641,16 @@ def run_ours(args):
                 "cublas_tf32_tflops_this_run": tf32_meas,
                 "frac_of_cublas_tf32": (ach / tf32_meas) if tf32_meas else None,
                 "algorithmic_flops_per_launch": 2.0 * NQ * NB * D}
+        # second bound of this kernel: every 128 x 256 FP32 accumulator tile has to leave TMEM
+        # through tcgen05.ld at 64 B/clk/SM, i.e. 2048 clk per tile whatever the operand type
+        try:
+            tiles = ((NQ + 127) // 128) * ((NB + 255) // 256)
+            sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+            floor_ms = tiles / 148.0 * 2048.0 / (sm_mhz * 1e3)
+            roof["accumulator_drain_floor_ms"] = floor_ms
+            roof["frac_of_accumulator_drain_floor"] = floor_ms / kms
+        except Exception:
+            pass
     elif "exact_slab" in phase_ms:
         kms = phase_ms["exact_slab"]
         roof = {"bound": "tensor", "kernel": "k_l2_simt (exact FP32 engine, CUDA cores)",

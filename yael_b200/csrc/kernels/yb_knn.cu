@@ -1671,9 +1671,24 @@ int knn_tf32_streamed(int nq, int nb, int d, int k, const float *base_host, floa
   int list0[kMaxChunks + 1];
   size_t tf_ws = splan.ws_bytes;
   list0[0] = 0;
+  // The scan of a chunk overlaps the transfer of the next one; only the LAST chunk's scan (and the
+  // merge / re-rank behind it) is exposed after the transfer ends.  So the last two chunks are
+  // small (1/16 and 1/32 of the database) and the others share the rest evenly.
+  long bound[kMaxChunks + 1];
+  {
+    const bool taper = C >= 4 && ngroups >= 64 && !getenv("YAEL_B200_H2D_UNIFORM");
+    const long tail1 = taper ? ngroups / 32 : 0, tail2 = taper ? ngroups / 16 : 0;
+    const int cu = taper ? C - 2 : C;           // evenly sized chunks
+    const long gu = ngroups - tail1 - tail2;    // groups they cover
+    for (int c = 0; c <= cu; c++) bound[c] = gu * c / cu;
+    if (taper) {
+      bound[C - 1] = gu + tail2;
+      bound[C] = ngroups;
+    }
+  }
   for (int c = 0; c < C; c++) {
-    g0[c] = ngroups * c / C;
-    const long g1 = ngroups * (c + 1) / C;
+    g0[c] = bound[c];
+    const long g1 = bound[c + 1];
     const long r0 = g0[c] * kGroupRows, r1 = g1 * kGroupRows < nb ? g1 * kGroupRows : nb;
     cplan[c] = tf32_plan_tiles(nq, tf32_tiles((int)(r1 - r0)), dpad, kp);
     if (!cplan[c].ok) return -1000;
