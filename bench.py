@@ -631,9 +631,9 @@ def run_ours(args):
         roof = {"bound": "tensor",
                 "kernel": "k_knn_tf32<EPI_LISTS, %s> (full pass; the sampling passes are in phase_ms)" % operands,
                 "operands": operands,
-                "note": ("2 MMA passes fewer per tile than TF32, so the pass is paced by draining the 128 x 256 "
-                         "FP32 accumulator from TMEM (64 B/clk/SM: >= 2048 clk per tile, 2062 tiles per SM) and "
-                         "by the admission path, not by the MMA rate -- see DESIGN.md 5.1"),
+                "note": ("FP16 operands need half as many MMAs per tile as TF32, so the pass is paced by draining "
+                         "the 128 x 256 FP32 accumulator from TMEM (64 B/clk/SM: >= 2048 clk per tile, 2062 tiles "
+                         "per SM) and by the admission path, not by the MMA rate -- see DESIGN.md 5.1"),
                 "achieved": ach, "peak": peak,
                 "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "kernel_ms": kms, "peak_source": peak_src,
