@@ -41,7 +41,15 @@ constexpr int STAGES = 4;        // B ring depth
 constexpr int NBN = 4;           // |b|^2 ring depth
 constexpr int A_CHUNK_BYTES = TM * KC * 4;  // 16 KB
 constexpr int B_CHUNK_BYTES = TN * KC * 4;  // 32 KB
-constexpr int EPI_WARPS = 8;
+// Epilogue warps come in TEAMS of 8 (4 TMEM lane quarters x 2 column halves).  With two teams,
+// team b drains accumulator buffer b (every other tile): 4 instead of 2 epilogue warps per
+// scheduler to hide the dependent-issue latency of the score / min chains.
+#ifndef YB_EPI_TEAMS
+#define YB_EPI_TEAMS 1
+#endif
+constexpr int EPI_TEAMS = YB_EPI_TEAMS;
+constexpr int TEAM_WARPS = 8;
+constexpr int EPI_WARPS = TEAM_WARPS * EPI_TEAMS;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int TF32_THREADS = EPI_THREADS + 64;
 constexpr int HALF_N = TN / 2;   // columns per epilogue warp and tile
@@ -639,10 +647,12 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
   const uint32_t crank = E.crank;
   auto bar = [&](int i) { return sbase + Smem::bar_off + 8 * i; };
   {
-    const int quarter = warp & 3, half = warp >> 2;
+    const int team = warp / TEAM_WARPS, w8 = warp % TEAM_WARPS;
+    const int quarter = w8 & 3, half = w8 >> 2;
     const int t = quarter * 32 + lane;  // query row inside the tile == TMEM lane
     int *hist = (int *)(smem + Smem::hist_off) + warp * 256;
-    float2 *mylist = P.scratch + ((size_t)blockIdx.x * (2 * TM) + half * TM + t) * P.cap;
+    float2 *mylist = P.scratch +
+                     (((size_t)blockIdx.x * EPI_TEAMS + team) * (2 * TM) + half * TM + t) * P.cap;
     const float inf = __uint_as_float(0x7f800000u);
     const float asc = P.acc_scale ? __ldg(P.acc_scale) : -2.0f;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * HALF_N;
@@ -664,6 +674,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
       if (MODE == EPI_HAMP) tau3 = ham_tau3(thr);
       for (int jt = jt0; jt < jt1; jt++, tcount++) {
         const uint32_t buf = tcount & 1, slot = tcount % NBN;
+        if (EPI_TEAMS > 1 && (int)buf != team) continue;  // the other team's accumulator buffer
         mbar_wait(bar(E.n_full0 + slot), (tcount / NBN) & 1);
         mbar_wait(bar(E.t_full0 + buf), (tcount >> 1) & 1);
         tc_fence_after();
@@ -833,7 +844,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
       if (MODE == EPI_NEAREST) {
         // k = 1: publish the candidates within the margin of the final best score
         if (valid) {
-          const size_t l = (size_t)q * P.lists_ld + P.list0 + sp * 2 + half;
+          const size_t l = (size_t)q * P.lists_ld + P.list0 + (sp * 2 + half) * EPI_TEAMS + team;
           const size_t o = l * P.kprime;
           int nout = 0;
           bool over = best != best;  // NaN: the list overflowed
@@ -874,7 +885,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
         }
         __syncwarp();
         if (valid) {
-          const size_t l = (size_t)q * P.lists_ld + P.list0 + sp * 2 + half;
+          const size_t l = (size_t)q * P.lists_ld + P.list0 + (sp * 2 + half) * EPI_TEAMS + team;
           P.out_thr[l] = thr;
           if (P.out_cnt) P.out_cnt[l] = cnt;
         }
@@ -886,7 +897,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           if (n == 0) continue;
           const float2 *l = (const float2 *)__shfl_sync(0xffffffffu, (unsigned long long)mylist, owner);
           const int qo = __shfl_sync(0xffffffffu, q, owner);
-          const size_t o = ((size_t)qo * P.lists_ld + P.list0 + sp * 2 + half) * P.kprime;
+          const size_t o = ((size_t)qo * P.lists_ld + P.list0 + (sp * 2 + half) * EPI_TEAMS + team) * P.kprime;
           for (int e = lane; e < n; e += 32) {
             const float2 x = l[e];
             P.out_score[o + e] = x.x;
@@ -918,11 +929,11 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     }
     for (int i = 0; i < NBN; i++) {
       mbar_init(bar(Smem::n_full + i), 1);
-      mbar_init(bar(Smem::n_empty + i), EPI_WARPS);
+      mbar_init(bar(Smem::n_empty + i), TEAM_WARPS);  // a |b|^2 slot belongs to one tile, i.e. one team
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(bar(Smem::t_full + i), 1);
-      mbar_init(bar(Smem::t_empty + i), EPI_WARPS);
+      mbar_init(bar(Smem::t_empty + i), TEAM_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1200,13 +1211,13 @@ Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kp) {
   }
   int range = (nbt + best_s - 1) / best_s;
   p.splits = (nbt + range - 1) / range;
-  p.lists = 2 * p.splits;
+  p.lists = 2 * EPI_TEAMS * p.splits;
   p.kprime = kp;
   p.cap = cap;
   long items = (long)tiles_q * p.splits;
   p.ctas = (int)(items < G ? items : G) * (pair ? 2 : 1);
   p.pair = pair;
-  p.ws_bytes = Carver::need(sizeof(float2) * (size_t)p.ctas * 2 * TM * cap) + 256;
+  p.ws_bytes = Carver::need(sizeof(float2) * (size_t)p.ctas * EPI_TEAMS * 2 * TM * cap) + 256;
   p.ok = 1;
   return p;
 }
@@ -1384,7 +1395,7 @@ Tf32Plan tf32_plan_nearest(int nq, int nb, int d) {
   Tf32Plan p = tf32_plan_tiles(nq, tf32_tiles(nb), d, 8);
   if (p.ok) {
     p.cap = 64;
-    p.ws_bytes = Carver::need(sizeof(float2) * (size_t)p.ctas * 2 * TM * p.cap) + 256;
+    p.ws_bytes = Carver::need(sizeof(float2) * (size_t)p.ctas * EPI_TEAMS * 2 * TM * p.cap) + 256;
   }
   return p;
 }
