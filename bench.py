@@ -631,9 +631,10 @@ def run_ours(args):
         roof = {"bound": "tensor",
                 "kernel": "k_knn_tf32<EPI_LISTS, %s> (full pass; the sampling passes are in phase_ms)" % operands,
                 "operands": operands,
-                "note": ("FP16 operands need half as many MMAs per tile as TF32, so the pass is paced by draining "
-                         "the 128 x 256 FP32 accumulator from TMEM (64 B/clk/SM: >= 2048 clk per tile, 2062 tiles "
-                         "per SM) and by the admission path, not by the MMA rate -- see DESIGN.md 5.1"),
+                "note": ("FP16 operands need half as many MMAs per tile as TF32: TMA + MMA alone take 1.75 ms of "
+                         "this pass (bring-up switches, same shape); the rest is the fused top-k epilogue -- TMEM "
+                         "loads and score / min math that overlap imperfectly (~0.7 ms) and the admission path "
+                         "(~0.4 ms) -- see DESIGN.md 5.1 and profiles/README.md"),
                 "achieved": ach, "peak": peak,
                 "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "kernel_ms": kms, "peak_source": peak_src,
@@ -641,16 +642,6 @@ def run_ours(args):
                 "cublas_tf32_tflops_this_run": tf32_meas,
                 "frac_of_cublas_tf32": (ach / tf32_meas) if tf32_meas else None,
                 "algorithmic_flops_per_launch": 2.0 * NQ * NB * D}
-        # second bound of this kernel: every 128 x 256 FP32 accumulator tile has to leave TMEM
-        # through tcgen05.ld at 64 B/clk/SM, i.e. 2048 clk per tile whatever the operand type
-        try:
-            tiles = ((NQ + 127) // 128) * ((NB + 255) // 256)
-            sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
-            floor_ms = tiles / 148.0 * 2048.0 / (sm_mhz * 1e3)
-            roof["accumulator_drain_floor_ms"] = floor_ms
-            roof["frac_of_accumulator_drain_floor"] = floor_ms / kms
-        except Exception:
-            pass
     elif "exact_slab" in phase_ms:
         kms = phase_ms["exact_slab"]
         roof = {"bound": "tensor", "kernel": "k_l2_simt (exact FP32 engine, CUDA cores)",
