@@ -30,15 +30,18 @@ struct Tf32Plan {
   size_t ws_bytes; // workspace for buffers + shortlists
   int kind;        // operand kind: 0 = FP32 rows read as TF32 (kind::tf32); 1 = E4M3 bytes
                    // (kind::f8f6f4; `base` / `query` point to [rows][4*d] BYTE matrices -- the Hamming
-                   // path); 2 = FP16 (kind::f16; [rows][d] half matrices, d % 8 == 0)
+                   // path); 2 = FP16 (kind::f16; [rows][d] half matrices, d % 8 == 0; k = 1 mode);
+                   // 3 = FP16 with folded norms (the LAST 16 elements of a row carry |b|^2
+                   // (database) resp. 2^15 (queries), see center_operands_h; the database copy is
+                   // padded to tf32_padded_rows(nb) rows; top-k', sampling and dump modes)
   const float *acc_scale;  // device scalar a: score = acc * a + |b|^2 (NULL: a = -2)
   // kind 1 only: > 1 = packed Hamming passes (yb_hamming_tc.cu): ham_slots consecutive database
   // rows share one accumulator; ham_nb real rows; ham_magic = 2^23 + (bits/2)(1 + 2^8 [+ 2^16])
   int ham_slots, ham_nb;
   float ham_magic;
 };
-Tf32Plan tf32_plan(int nq, int nb, int d, int k);
-Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kprime);
+Tf32Plan tf32_plan(int nq, int nb, int d, int k, int kind = 0);
+Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kprime, int kind = 0);
 int tf32_kprime_for(int k);
 int tf32_pair_mode();
 // One pass of the tensor-core kernel over the logical tiles 0..nbt_logical-1, logical tile j being
@@ -70,7 +73,7 @@ int tf32_shortlist(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical,
 int tf32_scores(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical, int tile_stride,
                 const float *base, const float *query, const float *bnorm_padded, float *scores,
                 long ld, void *ws, cudaStream_t st);
-Tf32Plan tf32_plan_nearest(int nq, int nb, int d);
+Tf32Plan tf32_plan_nearest(int nq, int nb, int d, int kind = 0);
 int tf32_nearest(const Tf32Plan &plan, int nq, int nb, int d, const float *base, const float *query,
                  const float *bnorm_padded, const float *k1_margin, float *out_score, int *out_id,
                  float *out_thr, void *ws, cudaStream_t st);

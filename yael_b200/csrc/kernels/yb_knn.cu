@@ -923,10 +923,48 @@ __device__ __forceinline__ unsigned pack_h2(float a, float b, float sc, bool &ov
   return *reinterpret_cast<const unsigned *>(&h);
 }
 
-// one warp per row, any d: out_h[r][0..dh) = fp16((x - mu) * 2^sigma) zero padded; optional FP32
-// copy out_f[r][0..df) and norm[r] = |x - mu|^2 (FP32 values, before the conversion)
+// The 16 extra K elements behind the dh data elements of an FP16 operand row (one MMA K step):
+// database rows (role 1) carry -beta split into three FP16 pieces, beta = 2^(2 sigma - 1) |b-mu|^2
+// / 2^15, queries (role 2) carry 2^15 three times, so that the contraction itself yields
+// 2^(2 sigma) (<q,b> - |b|^2 / 2) and the epilogue needs no |b|^2.  The split is exact (3 x 11
+// bits cover the 24-bit float); beta > 65504 raises the overflow flag like any other value.
+constexpr int kNfExtra = 16;
+__device__ __forceinline__ void write_row_extras(__half *dst, int role, float norm, float sc,
+                                                 int *oflag) {
+  uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+  if (role == 1) {
+    const float w = norm * sc * sc * (0.5f / 32768.0f);
+    if (w > 65504.0f && w < __int_as_float(0x7f800000)) *oflag = 1;
+    const __half h0 = __float2half_rn(w);
+    const float r1 = w - __half2float(h0);
+    const __half h1 = __float2half_rn(r1);
+    const float r2 = r1 - __half2float(h1);
+    const __half h2 = __float2half_rn(r2);
+    const unsigned short n0 = __half_as_ushort(__hneg(h0)), n1 = __half_as_ushort(__hneg(h1)),
+                         n2 = __half_as_ushort(__hneg(h2));
+    a.x = (unsigned)n0 | ((unsigned)n1 << 16);
+    a.y = (unsigned)n2;
+  } else if (role == 2) {
+    a.x = 0x78007800u;  // 32768.0, 32768.0
+    a.y = 0x00007800u;  // 32768.0, 0
+  }
+  reinterpret_cast<uint4 *>(dst)[0] = a;
+  reinterpret_cast<uint4 *>(dst)[1] = b;
+}
+
+// rows [n, n_pad) of the FP16 database copy: zeros with a NaN |b|^2 element (never admitted)
+__global__ void k_fill_pad_rows_h(__half *__restrict__ out_h, long n, long n_pad, int pitch, int dh) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (n_pad - n) * pitch) return;
+  const int c = (int)(t % pitch);
+  out_h[n * pitch + t] = __ushort_as_half(c == dh ? (unsigned short)0x7E00 : (unsigned short)0);
+}
+
+// one warp per row, any d: out_h[r][0..dh) = fp16((x - mu) * 2^sigma) zero padded, row pitch
+// `pitch` halfs (dh, or dh + 16 with the extras above when role != 0); optional FP32 copy
+// out_f[r][0..df) and norm[r] = |x - mu|^2 (FP32 values, before the conversion)
 __global__ void __launch_bounds__(256)
-k_center_rows_h(const float *__restrict__ x, long n, int d, int dh, int df,
+k_center_rows_h(const float *__restrict__ x, long n, int d, int dh, int df, int pitch, int role,
                 const float *__restrict__ mu, const float *__restrict__ scal,
                 __half *__restrict__ out_h, float *__restrict__ out_f, float *__restrict__ norm,
                 int *__restrict__ oflag) {
@@ -942,24 +980,26 @@ k_center_rows_h(const float *__restrict__ x, long n, int d, int dh, int df,
     if (c < dh) {
       const float w = v * sc;
       over |= fabsf(w) > 65504.0f && fabsf(v) < __int_as_float(0x7f800000);
-      out_h[r * dh + c] = __float2half_rn(w);
+      out_h[r * pitch + c] = __float2half_rn(w);
     }
     if (out_f && c < df) out_f[r * df + c] = v;
     s = fmaf(v, v, s);
   }
   if (over) *oflag = 1;
-  if (norm) {
-    s = warp_sum(s);
-    if (lane == 0) norm[r] = s;
+  s = warp_sum(s);
+  if (lane == 0) {
+    if (norm) norm[r] = s;
+    if (role) write_row_extras(out_h + r * pitch + dh, role, s, sc, oflag);
   }
 }
 
 // d % 8 == 0, 16-byte aligned: one warp per 4 rows, 2 x 16-byte loads and one 16-byte store per
 // 8 columns
 __global__ void __launch_bounds__(256)
-k_center_rows_h8(const float *__restrict__ x, long n, int d, const float *__restrict__ mu,
-                 const float *__restrict__ scal, __half *__restrict__ out_h,
-                 float *__restrict__ out_f, float *__restrict__ norm, int *__restrict__ oflag) {
+k_center_rows_h8(const float *__restrict__ x, long n, int d, int pitch, int role,
+                 const float *__restrict__ mu, const float *__restrict__ scal,
+                 __half *__restrict__ out_h, float *__restrict__ out_f, float *__restrict__ norm,
+                 int *__restrict__ oflag) {
   const long r0 = ((long)blockIdx.x * 8 + (threadIdx.x >> 5)) * 4;
   if (r0 >= n) return;
   const int lane = threadIdx.x & 31;
@@ -994,39 +1034,45 @@ k_center_rows_h8(const float *__restrict__ x, long n, int d, const float *__rest
     o.y = pack_h2(u.z, u.w, sc, over);
     o.z = pack_h2(w.x, w.y, sc, over);
     o.w = pack_h2(w.z, w.w, sc, over);
-    reinterpret_cast<uint4 *>(out_h + (r0 + i) * d)[c] = o;
+    reinterpret_cast<uint4 *>(out_h + (r0 + i) * pitch)[c] = o;
   }
   if (over) *oflag = 1;
-  if (norm) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const float t = warp_sum(s[i]);
-      if (lane == 0 && r0 + i < n) norm[r0 + i] = t;
+  for (int i = 0; i < 4; i++) {
+    const float t = warp_sum(s[i]);
+    if (lane == 0 && r0 + i < n) {
+      if (norm) norm[r0 + i] = t;
+      if (role) write_row_extras(out_h + (r0 + i) * pitch + d, role, t, sc, oflag);
     }
   }
 }
 
-static void launch_center_rows_h(const float *x, long n, int d, int dh, int df, const float *mu,
-                                 const float *scal, __half *out_h, float *out_f, float *norm,
-                                 cudaStream_t st) {
+// role 0: plain rows of dh halfs; 1 / 2: database / query rows of dh + 16 halfs (extras)
+static void launch_center_rows_h(const float *x, long n, int d, int dh, int df, int role,
+                                 const float *mu, const float *scal, __half *out_h, float *out_f,
+                                 float *norm, cudaStream_t st) {
   if (n <= 0) return;
   int *oflag = (int *)(scal + 4);
+  const int pitch = role ? dh + kNfExtra : dh;
   const bool fast = dh == d && (d & 7) == 0 && (!out_f || df == d) &&
                     (((uintptr_t)x | (uintptr_t)out_h | (uintptr_t)mu | (uintptr_t)out_f) & 15) == 0;
   if (fast)
-    k_center_rows_h8<<<(unsigned)((n + 31) / 32), 256, 0, st>>>(x, n, d, mu, scal, out_h, out_f, norm, oflag);
+    k_center_rows_h8<<<(unsigned)((n + 31) / 32), 256, 0, st>>>(x, n, d, pitch, role, mu, scal, out_h,
+                                                                out_f, norm, oflag);
   else
-    k_center_rows_h<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(x, n, d, dh, df, mu, scal, out_h, out_f,
-                                                              norm, oflag);
+    k_center_rows_h<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(x, n, d, dh, df, pitch, role, mu, scal,
+                                                              out_h, out_f, norm, oflag);
   count_launch();
 }
 
-// FP16 counterpart of center_operands: base_h / query_h with row pitch dh halfs (multiple of 8);
-// optional FP32 centred queries query_c (pitch df) and their squared norms qcnorm; bnorm[nb].
-// scal must have been zeroed by the caller.
+// FP16 counterpart of center_operands: base_h / query_h with dh data halfs (multiple of 8) plus
+// the 16 extra elements per row (pitch dh + 16); base_h holds tf32_padded_rows(nb) rows, the
+// padding marked NaN; optional FP32 centred queries query_c (pitch df) and their squared norms
+// qcnorm; bnorm[nb].  scal must have been zeroed by the caller.
 static int center_operands_h(int nq, int nb, int d, int dh, int df, const float *base,
                              const float *query, __half *base_h, __half *query_h, float *query_c,
-                             float *bnorm, float *qcnorm, float *scal, void *ws, cudaStream_t st) {
+                             float *bnorm, float *qcnorm, float *scal, void *ws, cudaStream_t st,
+                             bool fold) {
   Carver c(ws);
   int nblk = (int)(((long)nb + CM_ROWS - 1) / CM_ROWS);
   if (nblk > CM_BLOCKS) nblk = CM_BLOCKS;
@@ -1049,8 +1095,16 @@ static int center_operands_h(int nq, int nb, int d, int dh, int df, const float 
   YB_LAUNCH_CHECK();
   k_pick_scale<<<1, 1, 0, st>>>(scal, d, mu);
   YB_LAUNCH_CHECK();
-  launch_center_rows_h(base, nb, d, dh, dh, mu, scal, base_h, nullptr, bnorm, st);
-  launch_center_rows_h(query, nq, d, dh, df, mu, scal, query_h, query_c, qcnorm, st);
+  launch_center_rows_h(base, nb, d, dh, dh, fold ? 1 : 0, mu, scal, base_h, nullptr, bnorm, st);
+  launch_center_rows_h(query, nq, d, dh, df, fold ? 2 : 0, mu, scal, query_h, query_c, qcnorm, st);
+  if (fold) {
+    const long pad = tf32_padded_rows(nb) - nb, tot = pad * (dh + kNfExtra);
+    if (tot > 0) {
+      k_fill_pad_rows_h<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(base_h, nb, tf32_padded_rows(nb),
+                                                                       dh + kNfExtra, dh);
+      count_launch();
+    }
+  }
   YB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1278,14 +1332,16 @@ static int knn_tf32_nearest(int nq, int nb, int d, const float *base, const floa
                             int *assign, float *dis, int id_offset, long *uncert_out,
                             cudaStream_t st, int kind) {
   const bool f16 = kind == 2;
-  const int dpad = f16 ? (d + 7) & ~7 : (d + 3) & ~3;
-  Tf32Plan plan = tf32_plan_nearest(nq, nb, dpad);
+  const int dh = (d + 7) & ~7;                             // FP16: data elements per row
+  const int dpad = f16 ? dh : (d + 3) & ~3;                // operand row pitch in elements
+  // (plain FP16 operands here: folding |b|^2 into K costs a third 128-byte chunk at d = 128, which
+  // the k = 1 epilogue does not win back: 188 ms plain vs 192 ms folded for BASELINE config 4)
+  Tf32Plan plan = tf32_plan_nearest(nq, nb, dpad, kind);
   if (!plan.ok) return -1000;
-  plan.kind = kind;
   const int kp = plan.kprime, slots = plan.lists * kp;
   const long padded = tf32_padded_rows(nb);
   size_t need = Carver::need(sizeof(float) * (size_t)padded) + Carver::need(64) +
-                Carver::need((f16 ? 2 : 4) * (size_t)nb * dpad) +
+                Carver::need((f16 ? 2 : 4) * (size_t)padded * dpad) +
                 Carver::need((f16 ? 2 : 4) * (size_t)nq * dpad) + center_ws_bytes(nb, d) +
                 Carver::need(sizeof(float) * (size_t)nq) +
                 Carver::need(sizeof(float) * (size_t)nq) +
@@ -1308,7 +1364,7 @@ static int knn_tf32_nearest(int nq, int nb, int d, const float *base, const floa
     int *flags = c.take<int>(nq);
     int *flag_list = c.take<int>(nq);
     void *tfws = c.take<char>(plan.ws_bytes);
-    float *base_c = (float *)c.take<char>((f16 ? 2 : 4) * (size_t)nb * dpad);
+    float *base_c = (float *)c.take<char>((f16 ? 2 : 4) * (size_t)padded * dpad);
     float *query_c = (float *)c.take<char>((f16 ? 2 : 4) * (size_t)nq * dpad);
     float *qcnorm = c.take<float>(nq);
     void *cws = c.take<char>(center_ws_bytes(nb, d));
@@ -1319,8 +1375,8 @@ static int knn_tf32_nearest(int nq, int nb, int d, const float *base, const floa
       if (f16) {
         // no FP32 copy of the centred queries (for k-means they are the 10^7 points): the margin
         // comes from the norms the conversion kernel emits
-        if ((rc = center_operands_h(nq, nb, d, dpad, dpad, base, query, (__half *)base_c,
-                                    (__half *)query_c, nullptr, an, qcnorm, scal, cws, st)))
+        if ((rc = center_operands_h(nq, nb, d, dh, dh, base, query, (__half *)base_c,
+                                    (__half *)query_c, nullptr, an, qcnorm, scal, cws, st, false)))
           return rc;
         plan.acc_scale = scal + 3;
       } else {
@@ -1371,9 +1427,11 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
   if (force == 0 || w != nullptr) return -1000;
   const bool f16 = kind == 2;
   // the tensor pass runs on centred, pitch-padded copies (16-byte row pitch: 4 floats / 8 halfs)
-  const int dpad = f16 ? (d + 7) & ~7 : (d + 3) & ~3;
+  const int dh = (d + 7) & ~7;                             // FP16: data elements per row
+  const int dpad = f16 ? dh + kNfExtra : (d + 3) & ~3;     // operand row pitch in elements
   const int dqc = (d + 3) & ~3;   // pitch of the FP32 centred queries (certificate)
-  Tf32Plan plan = tf32_plan(nq, nb, dpad, k);
+  const int opkind = f16 ? 3 : kind;  // FP16 passes of this path fold |b|^2 into the contraction
+  Tf32Plan plan = tf32_plan(nq, nb, dpad, k, opkind);
   if (!plan.ok) return -1000;
   if (force < 0 && (double)nq * nb < 1e6) return -1000;  // tiny problems: not worth a TMA setup
   if (k == 1) {
@@ -1382,7 +1440,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
     if (rc1 == 0) *engine_out = 1;
     return rc1;
   }
-  plan.kind = kind;
+
   const int kp = plan.kprime;
   const int stride = plan.lists * kp;  // candidates per query produced by the tensor pass
   const int m = kp;                     // candidates per query that are re-ranked
@@ -1414,8 +1472,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
   if (const char *e = getenv("YAEL_B200_J2")) j2 = atoi(e) > 0 ? atoi(e) : j2;  // experiment knob
   if (retry) j2 *= 4;
   Tf32Plan splan = {};
-  if (use_sample) splan = tf32_plan_tiles(nq, nbt_s, dpad, j2);
-  splan.kind = kind;
+  if (use_sample) splan = tf32_plan_tiles(nq, nbt_s, dpad, j2, opkind);
   const bool sample_ok = use_sample && splan.ok;
   const int sstride = sample_ok ? splan.lists * j2 : 1;
   // level 1: t1 tiles spread over the database, j1-th smallest -> about 3*j2 rows of level 2
@@ -1427,8 +1484,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
   if (j1 < 12) j1 = 12;
   Tf32Plan l1plan = {};
   const bool level1_ok = sample_ok && t1 >= 8 && (size_t)nq * rows1 * 4 <= ((size_t)1 << 30) &&
-                         (l1plan = tf32_plan_tiles(nq, t1, dpad, 8)).ok;
-  l1plan.kind = kind;
+                         (l1plan = tf32_plan_tiles(nq, t1, dpad, 8, opkind)).ok;
 
   // single-level sampling: the sample pass emits the minimum of every group of gsize columns
   // and the threshold is an order statistic of those minima (with j2 << groups the j2 smallest
@@ -1450,7 +1506,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
                 2 * Carver::need(sizeof(int) * (size_t)nq) + kmin_ws_bytes(nq, kp) +
                 Carver::need(sizeof(int) * (size_t)nq * plan.lists) +
                 Carver::need(plan.ws_bytes) + 1024 +
-                Carver::need((f16 ? 2 : 4) * (size_t)nb * dpad) +
+                Carver::need((f16 ? 2 : 4) * (size_t)padded * dpad) +
                 Carver::need((f16 ? 2 : 4) * (size_t)nq * dpad) +
                 Carver::need(sizeof(float) * (size_t)nq * dqc) + center_ws_bytes(nb, d);
   if (sample_ok)
@@ -1481,7 +1537,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
     void *tfws = c.take<char>(plan.ws_bytes);
     // operands of the tensor passes (FP32 rows read as TF32, or FP16) and, for FP16, a separate
     // FP32 copy of the centred queries for the certificate
-    float *base_c = (float *)c.take<char>((f16 ? 2 : 4) * (size_t)nb * dpad);
+    float *base_c = (float *)c.take<char>((f16 ? 2 : 4) * (size_t)padded * dpad);
     float *query_c = (float *)c.take<char>((f16 ? 2 : 4) * (size_t)nq * dpad);
     float *query_cf = f16 ? c.take<float>((size_t)nq * dqc) : query_c;
     void *cws = c.take<char>(center_ws_bytes(nb, d));
@@ -1491,8 +1547,8 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
       ProfScope ps(0, st);
       YB_CUDA(cudaMemsetAsync(scal, 0, 64, st));
       if (f16) {
-        if ((rc = center_operands_h(nq, nb, d, dpad, dqc, base, query, (__half *)base_c,
-                                    (__half *)query_c, query_cf, an, nullptr, scal, cws, st)))
+        if ((rc = center_operands_h(nq, nb, d, dh, dqc, base, query, (__half *)base_c,
+                                    (__half *)query_c, query_cf, an, nullptr, scal, cws, st, true)))
           return rc;
         plan.acc_scale = splan.acc_scale = l1plan.acc_scale = scal + 3;
       } else {
@@ -1864,21 +1920,20 @@ extern "C" int yb_debug_f16_scores(int nq, int nb, int d, const float *base, con
                                    float *scores, yb_stream_t s) {
   Guard g;
   cudaStream_t st = stream_of(s);
-  const int dh = (d + 7) & ~7;
-  Tf32Plan plan = tf32_plan(nq, nb, dh, 1);
+  const int dh = (d + 7) & ~7, dop = dh + kNfExtra;
+  Tf32Plan plan = tf32_plan(nq, nb, dop, 1, 3);
   if (!plan.ok) return fail(3, "tensor path does not support this shape (d=%d)", d);
-  plan.kind = 2;
   const long padded = tf32_padded_rows(nb);
   ScratchScope ws(Carver::need(4ull * padded) + Carver::need(64) + Carver::need(4ull * d) +
-                      Carver::need(2ull * nb * dh) + Carver::need(2ull * nq * dh) +
+                      Carver::need(2ull * padded * dop) + Carver::need(2ull * nq * dop) +
                       Carver::need(plan.ws_bytes),
                   st);
   Carver c(ws.p);
   float *bn = c.take<float>(padded);
   float *scal = c.take<float>(16);
   float *mu = c.take<float>(d);
-  __half *bh = c.take<__half>((size_t)nb * dh);
-  __half *qh = c.take<__half>((size_t)nq * dh);
+  __half *bh = c.take<__half>((size_t)padded * dop);
+  __half *qh = c.take<__half>((size_t)nq * dop);
   void *tws = c.take<char>(plan.ws_bytes);
   YB_CUDA(cudaMemsetAsync(scal, 0, 64, st));
   YB_CUDA(cudaMemsetAsync(mu, 0, 4ull * d, st));
@@ -1888,12 +1943,19 @@ extern "C" int yb_debug_f16_scores(int nq, int nb, int d, const float *base, con
   YB_LAUNCH_CHECK();
   k_pick_scale<<<1, 1, 0, st>>>(scal, d, mu);
   YB_LAUNCH_CHECK();
-  launch_center_rows_h(base, nb, d, dh, dh, mu, scal, bh, nullptr, bn, st);
-  launch_center_rows_h(query, nq, d, dh, dh, mu, scal, qh, nullptr, nullptr, st);
+  launch_center_rows_h(base, nb, d, dh, dh, 1, mu, scal, bh, nullptr, bn, st);
+  launch_center_rows_h(query, nq, d, dh, dh, 2, mu, scal, qh, nullptr, nullptr, st);
+  {
+    const long tot = (padded - nb) * dop;
+    if (tot > 0) {
+      k_fill_pad_rows_h<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(bh, nb, padded, dop, dh);
+      count_launch();
+    }
+  }
   int rc;
   if ((rc = fill_f32(bn + nb, padded - nb, __builtin_inff(), st))) return rc;
   plan.acc_scale = scal + 3;
-  if ((rc = tf32_scores(plan, nq, nb, dh, tf32_tiles(nb), 1, (const float *)bh, (const float *)qh, bn,
+  if ((rc = tf32_scores(plan, nq, nb, dop, tf32_tiles(nb), 1, (const float *)bh, (const float *)qh, bn,
                         scores, nb, tws, st)))
     return rc;
   int overflow = 0;

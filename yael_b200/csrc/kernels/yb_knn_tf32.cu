@@ -281,13 +281,13 @@ constexpr uint32_t IDESC_F16 = IDESC_F8;
 
 // operand kinds (Tf32Plan::kind).  The kind is a template parameter of the kernel: the issue
 // loop of each instantiation carries no kind branches.
-enum : int { OP_TF32 = 0, OP_F8 = 1, OP_F16 = 2 };
+enum : int { OP_TF32 = 0, OP_F8 = 1, OP_F16 = 2, OP_F16N = 3 };  // F16N: FP16 with |b|^2 folded into K
 template <int KIND>
 __device__ __forceinline__ void tc_mma_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                              uint32_t accumulate) {
   if (KIND == OP_F8)
     tc_mma_f8_elect(d_tmem, a_desc, b_desc, IDESC_F8, accumulate);
-  else if (KIND == OP_F16)
+  else if (KIND == OP_F16 || KIND == OP_F16N)
     tc_mma_f16_elect(d_tmem, a_desc, b_desc, IDESC_F16, accumulate);
   else
     tc_mma_tf32_elect(d_tmem, a_desc, b_desc, IDESC_TF32, accumulate);
@@ -526,6 +526,46 @@ __device__ __forceinline__ void process_group(const uint32_t (&v)[16], const flo
   }
 }
 
+// FP16 operands carry |b|^2 INSIDE the contraction (yb_knn.cu, center_operands_h: three extra K
+// elements per row hold -2^(2 sigma - 1) |b|^2 split into FP16 pieces, the query side 2^15), so the
+// accumulator is acc' = 2^(2 sigma) (<q,b> - |b|^2 / 2) and the score is asc * acc' with
+// asc = -2^(1 - 2 sigma) < 0: no |b|^2 staging, no FMA -- the group test is a MAX tree over the
+// raw accumulators against thr / asc (exact: asc is a power of two).  NaN accumulators (padding
+// rows, NaN data) never win a max and never pass a comparison.
+__device__ __forceinline__ float group_max16(const uint32_t (&v)[16]) {
+  const float m01 = fmaxf(fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])),
+                          fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3])));
+  const float m23 = fmaxf(fmaxf(__uint_as_float(v[4]), __uint_as_float(v[5])),
+                          fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7])));
+  const float m45 = fmaxf(fmaxf(__uint_as_float(v[8]), __uint_as_float(v[9])),
+                          fmaxf(__uint_as_float(v[10]), __uint_as_float(v[11])));
+  const float m67 = fmaxf(fmaxf(__uint_as_float(v[12]), __uint_as_float(v[13])),
+                          fmaxf(__uint_as_float(v[14]), __uint_as_float(v[15])));
+  return fmaxf(fmaxf(m01, m23), fmaxf(m45, m67));
+}
+
+template <bool K1>
+__device__ __forceinline__ void process_group_nf(const uint32_t (&v)[16], float &thr, float &thrp,
+                                                 float &best, float margin, float2 *mylist, int &cnt,
+                                                 int cap, int id0, float asc, float inv_asc) {
+  const float M = group_max16(v);
+  if (M > thrp) {  // <=> asc * M < thr: some score of the group beats the admission threshold
+    float sc[16];
+#pragma unroll
+    for (int c = 0; c < 16; c++) sc[c] = __fmul_rn(asc, __uint_as_float(v[c]));
+    if (K1) {
+      K1State st = {thr, best, cnt};
+      st = slow_append_k1(YB_SC16_ARGS(sc), __fmul_rn(asc, M), st, margin, mylist, cap, id0);
+      thr = st.thr;
+      best = st.best;
+      cnt = st.cnt;
+      thrp = __fmul_rn(thr, inv_asc);
+    } else {
+      cnt = slow_append(YB_SC16_ARGS(sc), thr, mylist, cnt, id0);
+    }
+  }
+}
+
 // smallest score of 16 accumulator columns (sampling pass)
 __device__ __forceinline__ float group_min16(const uint32_t (&v)[16], const float *bn, float asc) {
   float sc[16];
@@ -638,8 +678,9 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 // mode branches)
 enum : int { EPI_LISTS = 0, EPI_NEAREST = 1, EPI_DUMP = 2, EPI_GMIN = 3, EPI_HAMP = 4, EPI_HAMG = 5 };
 
-template <int MODE>
+template <int MODE, int KIND>
 __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &E) {
+  constexpr bool NF = KIND == OP_F16N;  // |b|^2 folded into the contraction
   unsigned char *smem = E.smem;
   const uint32_t sbase = E.sbase, tmem_base = E.tmem_base;
   const int warp = E.warp, lane = E.lane;
@@ -655,6 +696,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
                      (((size_t)blockIdx.x * EPI_TEAMS + team) * (2 * TM) + half * TM + t) * P.cap;
     const float inf = __uint_as_float(0x7f800000u);
     const float asc = P.acc_scale ? __ldg(P.acc_scale) : -2.0f;
+    const float inv_asc = 1.0f / asc;  // exact: asc is a power of two
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * HALF_N;
     uint32_t tcount = 0;
     for (int item = first_item; item < P.items; item += item_step) {
@@ -669,6 +711,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
       constexpr bool k1 = MODE == EPI_NEAREST;
       const float margin = (k1 && valid) ? P.k1_margin[q] : 0.f;
       int cnt = 0;
+      float thrp = __fmul_rn(thr, inv_asc);  // NF: admit iff acc' > thrp (= thr / asc, asc < 0)
       uint32_t tau3 = 0u;
       const uint32_t ham_mask = P.ham_slots == 3 ? 0x808080u : 0x8080u;
       if (MODE == EPI_HAMP) tau3 = ham_tau3(thr);
@@ -693,17 +736,17 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
 #pragma unroll
                 for (int c4 = 0; c4 < 8; c4++) {  // 128 contiguous bytes per thread
                   float4 o;
-                  o.x = fmaf(__uint_as_float(v[c4 * 4 + 0]), asc, bn[g * 32 + c4 * 4 + 0]);
-                  o.y = fmaf(__uint_as_float(v[c4 * 4 + 1]), asc, bn[g * 32 + c4 * 4 + 1]);
-                  o.z = fmaf(__uint_as_float(v[c4 * 4 + 2]), asc, bn[g * 32 + c4 * 4 + 2]);
-                  o.w = fmaf(__uint_as_float(v[c4 * 4 + 3]), asc, bn[g * 32 + c4 * 4 + 3]);
+                  o.x = fmaf(__uint_as_float(v[c4 * 4 + 0]), asc, NF ? 0.f : bn[g * 32 + c4 * 4 + 0]);
+                  o.y = fmaf(__uint_as_float(v[c4 * 4 + 1]), asc, NF ? 0.f : bn[g * 32 + c4 * 4 + 1]);
+                  o.z = fmaf(__uint_as_float(v[c4 * 4 + 2]), asc, NF ? 0.f : bn[g * 32 + c4 * 4 + 2]);
+                  o.w = fmaf(__uint_as_float(v[c4 * 4 + 3]), asc, NF ? 0.f : bn[g * 32 + c4 * 4 + 3]);
                   *reinterpret_cast<float4 *>(drow + c4 * 4) = o;
                 }
               } else {
 #pragma unroll
                 for (int c = 0; c < 32; c++)
                   if (col0 + c < P.dump_ld)
-                    drow[c] = fmaf(__uint_as_float(v[c]), asc, bn[g * 32 + c]);
+                    drow[c] = fmaf(__uint_as_float(v[c]), asc, NF ? 0.f : bn[g * 32 + c]);
               }
             }
           }
@@ -720,14 +763,14 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           for (int gg = 0; gg < 4; gg++) {
             tc_wait_ld();
             tc_ld16(ta + gg * 32 + 16, vb);
-            gm = fminf(gm, group_min16(va, bn + gg * 32, asc));
+            gm = fminf(gm, NF ? __fmul_rn(asc, group_max16(va)) : group_min16(va, bn + gg * 32, asc));
             if (((2 * gg + 1) % fold) == 0) {
               if (valid) grow[(2 * gg + 1) / fold - 1] = gm;
               gm = inf;
             }
             tc_wait_ld();
             if (gg < 3) tc_ld16(ta + gg * 32 + 32, va);
-            gm = fminf(gm, group_min16(vb, bn + gg * 32 + 16, asc));
+            gm = fminf(gm, NF ? __fmul_rn(asc, group_max16(vb)) : group_min16(vb, bn + gg * 32 + 16, asc));
             if (((2 * gg + 2) % fold) == 0) {
               if (valid) grow[(2 * gg + 2) / fold - 1] = gm;
               gm = inf;
@@ -797,11 +840,20 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
   _Pragma("unroll 1") for (int gg = 0; gg < 4; gg++) {                                          \
     tc_wait_ld();                                                                               \
     tc_ld16(ta + gg * 32 + 16, vb);                                                             \
-    process_group<K1FLAG>(va, bn + gg * 32, thr, best, margin, mylist, cnt, P.cap, n0 + gg * 32, asc); \
+    if (NF)                                                                                     \
+      process_group_nf<K1FLAG>(va, thr, thrp, best, margin, mylist, cnt, P.cap, n0 + gg * 32,   \
+                               asc, inv_asc);                                                   \
+    else                                                                                        \
+      process_group<K1FLAG>(va, bn + gg * 32, thr, best, margin, mylist, cnt, P.cap,            \
+                            n0 + gg * 32, asc);                                                 \
     tc_wait_ld();                                                                               \
     if (gg < 3) tc_ld16(ta + gg * 32 + 32, va);                                                 \
-    process_group<K1FLAG>(vb, bn + gg * 32 + 16, thr, best, margin, mylist, cnt, P.cap,         \
-                          n0 + gg * 32 + 16, asc);                                              \
+    if (NF)                                                                                     \
+      process_group_nf<K1FLAG>(vb, thr, thrp, best, margin, mylist, cnt, P.cap,                 \
+                               n0 + gg * 32 + 16, asc, inv_asc);                                \
+    else                                                                                        \
+      process_group<K1FLAG>(vb, bn + gg * 32 + 16, thr, best, margin, mylist, cnt, P.cap,       \
+                            n0 + gg * 32 + 16, asc);                                            \
   }
             if (k1) {
               YB_TILE_GROUPS(true)
@@ -840,6 +892,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           }
         }
         if (MODE == EPI_HAMP) tau3 = ham_tau3(thr);
+        if (NF) thrp = __fmul_rn(thr, inv_asc);
       }
       if (MODE == EPI_NEAREST) {
         // k = 1: publish the candidates within the margin of the final best score
@@ -968,7 +1021,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 
   if (warp == EPI_WARPS) {
     // ======================================================================== TMA producer
-    constexpr int KCE = KIND == OP_F8 ? KC * 4 : (KIND == OP_F16 ? KC * 2 : KC);  // elements per 128-byte K chunk (TMA coordinates)
+    constexpr int KCE = KIND == OP_F8 ? KC * 4 : ((KIND == OP_F16 || KIND == OP_F16N) ? KC * 2 : KC);  // elements per 128-byte K chunk (TMA coordinates)
     if (lane == 0) {
       uint32_t icount = 0, ccount = 0, tcount = 0;
       for (int item = first_item; item < P.items; item += item_step, icount++) {
@@ -1078,7 +1131,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       }
     }
   } else {
-    run_epilogue<MODE>(P, ectx);
+    run_epilogue<MODE, KIND>(P, ectx);
   }
 
   tc_fence_before();
@@ -1180,9 +1233,12 @@ int tf32_kprime_for(int k) {
 
 // Plan a pass over `nbt_logical` database tiles (a sampling pass sees every tile_stride-th tile)
 // that keeps kp candidates per list.
-Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kp) {
+Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kp, int kind) {
   Tf32Plan p = {};
-  if (d < 1 || d > MAX_NKC * KC || (d % 4) != 0) return p;  // TMA: 16-byte row pitch; A resident
+  // TMA: 16-byte row pitch; the query tile (A) is resident: at most MAX_NKC chunks of 128 bytes
+  const bool h = kind == OP_F16 || kind == OP_F16N;
+  const int per_chunk = h ? 2 * KC : KC, mult = h ? 8 : 4;
+  if (d < 1 || d > MAX_NKC * per_chunk || (d % mult) != 0) return p;
   if (nq < 1 || nbt_logical < 1 || kp < 1) return p;
   if (kp + 2 * HALF_N > MAXL) return p;  // the in-register compaction handles MAXL entries
   int cap = pow2_ceil(8 * kp);
@@ -1217,17 +1273,18 @@ Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kp) {
   long items = (long)tiles_q * p.splits;
   p.ctas = (int)(items < G ? items : G) * (pair ? 2 : 1);
   p.pair = pair;
+  p.kind = kind;
   p.ws_bytes = Carver::need(sizeof(float2) * (size_t)p.ctas * EPI_TEAMS * 2 * TM * cap) + 256;
   p.ok = 1;
   return p;
 }
 
-Tf32Plan tf32_plan(int nq, int nb, int d, int k) {
+Tf32Plan tf32_plan(int nq, int nb, int d, int k, int kind) {
   if (nb < 1) {
     Tf32Plan p = {};
     return p;
   }
-  return tf32_plan_tiles(nq, (nb + TN - 1) / TN, d, tf32_kprime_for(k));
+  return tf32_plan_tiles(nq, (nb + TN - 1) / TN, d, tf32_kprime_for(k), kind);
 }
 
 template <int MODE, int KIND = OP_TF32>
@@ -1284,13 +1341,16 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
     if ((rc = make_map_u8(&mbh, base, nb, pitch, TN / 2))) return rc;
     P.nkc = (pitch + 127) / 128;
     P.last_k8 = (pitch - (P.nkc - 1) * 128 + 31) / 32;
-  } else if (plan.kind == OP_F16) {
+  } else if (plan.kind == OP_F16 || plan.kind == OP_F16N) {
     // FP16 operands: d halfs per row (d % 8 == 0); a K chunk holds 64 of them, an MMA 16
     if (d % 8) return fail(6, "FP16 operands need a row pitch that is a multiple of 8 elements");
     const int pitch = 2 * d;
+    // folded norms: the FP16 database copy is padded to whole tiles with rows whose |b|^2 element
+    // is NaN (never admitted): the map covers them, so tail tiles need no masks
+    const long nb_pad = plan.kind == OP_F16N ? tf32_padded_rows(nb) : nb;
     if ((rc = make_map_f16(&mq, query, nq, d, TM))) return rc;
-    if ((rc = make_map_f16(&mb, base, nb, d, TN))) return rc;
-    if ((rc = make_map_f16(&mbh, base, nb, d, TN / 2))) return rc;
+    if ((rc = make_map_f16(&mb, base, nb_pad, d, TN))) return rc;
+    if ((rc = make_map_f16(&mbh, base, nb_pad, d, TN / 2))) return rc;
     P.nkc = (pitch + 127) / 128;
     P.last_k8 = (pitch - (P.nkc - 1) * 128 + 31) / 32;
   } else {
@@ -1357,12 +1417,18 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
       default: return fail(6, "the E4M3 operand kind has no k = 1 margin mode");
     }
   }
-  if (plan.kind == OP_F16) {
+  if (plan.kind == OP_F16) {  // plain FP16 operands: the k = 1 margin mode (k-means)
     switch (mode) {
-      case EPI_DUMP: return launch_mode<EPI_DUMP, OP_F16>(plan, mq, mb, mbh, P, st);
-      case EPI_GMIN: return launch_mode<EPI_GMIN, OP_F16>(plan, mq, mb, mbh, P, st);
       case EPI_NEAREST: return launch_mode<EPI_NEAREST, OP_F16>(plan, mq, mb, mbh, P, st);
-      default: return launch_mode<EPI_LISTS, OP_F16>(plan, mq, mb, mbh, P, st);
+      default: return fail(6, "plain FP16 operands are only instantiated for the k = 1 margin mode");
+    }
+  }
+  if (plan.kind == OP_F16N) {  // FP16 operands with folded norms: top-k', sampling, dump
+    switch (mode) {
+      case EPI_DUMP: return launch_mode<EPI_DUMP, OP_F16N>(plan, mq, mb, mbh, P, st);
+      case EPI_GMIN: return launch_mode<EPI_GMIN, OP_F16N>(plan, mq, mb, mbh, P, st);
+      case EPI_LISTS: return launch_mode<EPI_LISTS, OP_F16N>(plan, mq, mb, mbh, P, st);
+      default: return fail(6, "folded-norm FP16 operands have no k = 1 margin mode");
     }
   }
   switch (mode) {
@@ -1391,8 +1457,8 @@ int tf32_nearest(const Tf32Plan &plan, int nq, int nb, int d, const float *base,
                      k1_margin, out_score, out_id, out_thr, nullptr, 0, ws, st);
 }
 
-Tf32Plan tf32_plan_nearest(int nq, int nb, int d) {
-  Tf32Plan p = tf32_plan_tiles(nq, tf32_tiles(nb), d, 8);
+Tf32Plan tf32_plan_nearest(int nq, int nb, int d, int kind) {
+  Tf32Plan p = tf32_plan_tiles(nq, tf32_tiles(nb), d, 8, kind);
   if (p.ok) {
     p.cap = 64;
     p.ws_bytes = Carver::need(sizeof(float2) * (size_t)p.ctas * EPI_TEAMS * 2 * TM * p.cap) + 256;
