@@ -1427,7 +1427,9 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
   if (force == 0 || w != nullptr) return -1000;
   const bool f16 = kind == 2;
   // the tensor pass runs on centred, pitch-padded copies (16-byte row pitch: 4 floats / 8 halfs)
-  const int dh = (d + 7) & ~7;                             // FP16: data elements per row
+  // FP16: data elements per row, a multiple of 16 (one MMA K step) so that the K steps over the
+  // data never touch the extras behind them
+  const int dh = (d + 15) & ~15;
   const int dpad = f16 ? dh + kNfExtra : (d + 3) & ~3;     // operand row pitch in elements
   const int dqc = (d + 3) & ~3;   // pitch of the FP32 centred queries (certificate)
   const int opkind = f16 ? 3 : kind;  // FP16 passes of this path fold |b|^2 into the contraction
@@ -1920,7 +1922,7 @@ extern "C" int yb_debug_f16_scores(int nq, int nb, int d, const float *base, con
                                    float *scores, yb_stream_t s) {
   Guard g;
   cudaStream_t st = stream_of(s);
-  const int dh = (d + 7) & ~7, dop = dh + kNfExtra;
+  const int dh = (d + 15) & ~15, dop = dh + kNfExtra;
   Tf32Plan plan = tf32_plan(nq, nb, dop, 1, 3);
   if (!plan.ok) return fail(3, "tensor path does not support this shape (d=%d)", d);
   const long padded = tf32_padded_rows(nb);

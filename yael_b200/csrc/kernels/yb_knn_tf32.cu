@@ -270,6 +270,19 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
   desc |= (uint64_t)2 << 61;                         // SWIZZLE_128B
   return desc;
 }
+// K-major, SWIZZLE_32B descriptor: rows of 32 bytes (one MMA K step), 8-row groups 256 bytes
+// apart -- the layout a TMA box of 16 halfs x rows with CU_TENSOR_MAP_SWIZZLE_32B produces.  Used
+// for the 16 extra K elements of the folded-norm FP16 operands, so that they cost 32 bytes per
+// row of shared-memory traffic instead of a whole (zero-filled) 128-byte chunk.
+__device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t saddr) {
+  uint64_t desc = 0;
+  desc |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  desc |= (uint64_t)1 << 16;
+  desc |= (uint64_t)(256 >> 4) << 32;
+  desc |= (uint64_t)1 << 46;
+  desc |= (uint64_t)6 << 61;  // SWIZZLE_32B
+  return desc;
+}
 // instruction descriptor, kind::tf32: D=F32, A=B=TF32, both K-major, N=256, M=128
 constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) |
                                 ((uint32_t)(TM >> 4) << 24);
@@ -330,6 +343,8 @@ struct Tf32Params {
   int tiles_q2;        // query-tile pairs when pair != 0
   // packed Hamming modes (EPI_HAMP / EPI_HAMG): every accumulator carries ham_slots distances of
   // ham_slots consecutive database rows, acc = dot_0 + 2^8 dot_1 + 2^16 dot_2 (yb_hamming_tc.cu)
+  int xk;              // folded-norm FP16: index of the extras chunk (= number of data chunks), its
+  int xcol;            // first column (halfs); -1 / 0 otherwise.  nkc counts the extras chunk too.
   int order;           // work items: 0 = range-major (CTAs of a wave stream the SAME database range),
                        // 1 = query-tile-major (a wave covers every range: ~148/splits CTAs per range)
   int ham_slots;       // 2 or 3
@@ -966,7 +981,8 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
 template <int MODE, int KIND>
 __global__ void __launch_bounds__(TF32_THREADS, 1)
 k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_b,
-           const __grid_constant__ CUtensorMap map_bh, const Tf32Params P) {
+           const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_qx,
+           const __grid_constant__ CUtensorMap map_bx, const Tf32Params P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1031,9 +1047,14 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
         // query tile: wait until the MMAs of the previous item have drained A
         mbar_wait(bar(Smem::a_empty), (icount & 1) ^ 1);
-        mbar_expect_tx(bar(Smem::a_full), (uint32_t)(P.nkc * A_CHUNK_BYTES));
-        for (int kc = 0; kc < P.nkc; kc++)
+        const int nkd = P.xk >= 0 ? P.xk : P.nkc;  // 128-byte data chunks
+        mbar_expect_tx(bar(Smem::a_full),
+                       (uint32_t)(nkd * A_CHUNK_BYTES + (P.xk >= 0 ? TM * 32 : 0)));
+        for (int kc = 0; kc < nkd; kc++)
           tma_load_2d(sbase + Smem::a_off + kc * A_CHUNK_BYTES, &map_q, bar(Smem::a_full), kc * KCE,
+                      qt * TM);
+        if (P.xk >= 0)
+          tma_load_2d(sbase + Smem::a_off + P.xk * A_CHUNK_BYTES, &map_qx, bar(Smem::a_full), P.xcol,
                       qt * TM);
         for (int jt = jt0; jt < jt1; jt++, tcount++) {
           const uint32_t slot = tcount % NBN;
@@ -1047,6 +1068,12 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
             mbar_wait(bar(Smem::b_empty + st), ((ccount / STAGES) & 1) ^ 1);
             if ((P.debug & 16) && jt > jt0) {  // bring-up: no TMA traffic after the first tile
               mbar_arrive(bar(Smem::b_full + st));
+              continue;
+            }
+            if (kc == P.xk) {  // the 16 extra K elements: a 32-byte-wide box
+              mbar_expect_tx(bar(Smem::b_full + st), TN * 32);
+              tma_load_2d(sbase + Smem::b_off + st * B_CHUNK_BYTES, &map_bx, bar(Smem::b_full + st),
+                          P.xcol, jta * TN);
               continue;
             }
             mbar_expect_tx(bar(Smem::b_full + st), B_CHUNK_BYTES);
@@ -1069,7 +1096,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     {
       uint32_t icount = 0, ccount = 0, tcount = 0;
       const bool skip_mma = (P.debug & 2) != 0;
-      const bool ring_aligned = P.nkc == STAGES && P.last_k8 == 4;
+      const bool ring_aligned = P.nkc == STAGES && P.last_k8 == 4 && P.xk < 0;
       for (int item = first_item; item < P.items; item += item_step, icount++) {
         const int sp = P.order ? item % P.splits : item / tq_div;
         const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
@@ -1106,8 +1133,13 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
             const uint64_t adesc = smem_desc_sw128(sbase + Smem::a_off + kc * A_CHUNK_BYTES);
             const uint64_t bdesc = smem_desc_sw128(sbase + Smem::b_off + st * B_CHUNK_BYTES);
             // advancing K inside the 128-byte swizzle span: +32 bytes = +2 in 16-byte units
-            if (!skip_mma) {
-              if (kc != P.nkc - 1 || P.last_k8 == 4) {
+            if (kc == P.xk) {
+              if (!skip_mma)
+                tc_mma_elect<KIND>(d_tmem, smem_desc_sw32(sbase + Smem::a_off + kc * A_CHUNK_BYTES),
+                                   smem_desc_sw32(sbase + Smem::b_off + st * B_CHUNK_BYTES), 1);
+            } else if (!skip_mma) {
+              const int last_data = (P.xk >= 0 ? P.xk : P.nkc) - 1;
+              if (kc != last_data || P.last_k8 == 4) {
                 tc_mma_elect<KIND>(d_tmem, adesc, bdesc, kc != 0);
                 tc_mma_elect<KIND>(d_tmem, adesc + 2, bdesc + 2, 1);
                 tc_mma_elect<KIND>(d_tmem, adesc + 4, bdesc + 4, 1);
@@ -1216,6 +1248,22 @@ static int make_map_f16(CUtensorMap *m, const void *ptr, long rows, int d, int b
   return 0;
 }
 
+// the 16 extra K elements (columns [col0, col0 + 16)) of an FP16 operand matrix with row pitch d
+// halfs: box = 16 halfs (32 bytes) x box_rows, 32-byte swizzle (see smem_desc_sw32)
+static int make_map_f16_extras(CUtensorMap *m, const void *ptr, long rows, int d, int box_rows) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return fail(6, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)d * 2};
+  cuuint32_t box[2] = {16u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(6, "cuTensorMapEncodeTiled (f16 extras) failed with code %d", (int)r);
+  return 0;
+}
+
 // Independent CTAs (default) or CTA pairs that multicast the database chunks (YAEL_B200_PAIR=1).
 // Measured on the bench shape: pairing halves the L2->SM traffic but does not shorten the pass
 // (6.02 vs 5.90 ms) -- the L2 feed is not what bounds this kernel -- so it stays opt-in.
@@ -1289,7 +1337,8 @@ Tf32Plan tf32_plan(int nq, int nb, int d, int k, int kind) {
 
 template <int MODE, int KIND = OP_TF32>
 static int launch_mode(const Tf32Plan &plan, const CUtensorMap &mq, const CUtensorMap &mb,
-                       const CUtensorMap &mbh, const Tf32Params &P, cudaStream_t st) {
+                       const CUtensorMap &mbh, const CUtensorMap &mqx, const CUtensorMap &mbx,
+                       const Tf32Params &P, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(k_knn_tf32<MODE, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1311,11 +1360,11 @@ static int launch_mode(const Tf32Plan &plan, const CUtensorMap &mq, const CUtens
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_knn_tf32<MODE, KIND>, mq, mb, mbh, P);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_knn_tf32<MODE, KIND>, mq, mb, mbh, mqx, mbx, P);
     if (e != cudaSuccess) return fail(2, "k_knn_tf32 cluster launch: %s", cudaGetErrorString(e));
     count_launch();
   } else {
-    k_knn_tf32<MODE, KIND><<<plan.ctas, TF32_THREADS, TF32_SMEM_BYTES, st>>>(mq, mb, mbh, P);
+    k_knn_tf32<MODE, KIND><<<plan.ctas, TF32_THREADS, TF32_SMEM_BYTES, st>>>(mq, mb, mbh, mqx, mbx, P);
     YB_LAUNCH_CHECK();
   }
   return 0;
@@ -1328,10 +1377,11 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
                        void *ws, cudaStream_t st, const Tf32Out *oo = nullptr) {
   if ((((uintptr_t)base) & 15) || (((uintptr_t)query) & 15))
     return fail(6, "tf32 path needs 16-byte aligned matrices");
-  CUtensorMap mq, mb, mbh;
+  CUtensorMap mq, mb, mbh, mqx, mbx;
   int rc;
   Tf32Params P = {};
   P.nq = nq; P.nb = nb; P.d = d;
+  P.xk = -1;
   if (plan.kind == OP_F8) {
     // E4M3 operands: d floats of pitch = 4*d bytes = 4*d elements per row; a K chunk is the same
     // 128-byte swizzle span (128 elements), an MMA covers 32 of them
@@ -1351,14 +1401,31 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
     if ((rc = make_map_f16(&mq, query, nq, d, TM))) return rc;
     if ((rc = make_map_f16(&mb, base, nb_pad, d, TN))) return rc;
     if ((rc = make_map_f16(&mbh, base, nb_pad, d, TN / 2))) return rc;
-    P.nkc = (pitch + 127) / 128;
-    P.last_k8 = (pitch - (P.nkc - 1) * 128 + 31) / 32;
+    if (plan.kind == OP_F16N) {
+      // data columns [0, d - 16) in 128-byte chunks, then the 16 extras as one 32-byte-wide chunk
+      const int dd = d - 16, dbytes = 2 * dd;
+      const int nkd = (dbytes + 127) / 128;
+      if (nkd + 1 > MAX_NKC) return fail(6, "folded-norm FP16 operands: d = %d needs too many chunks", dd);
+      P.xk = nkd;
+      P.xcol = dd;
+      P.nkc = nkd + 1;
+      P.last_k8 = (dbytes - (nkd - 1) * 128 + 31) / 32;
+      if ((rc = make_map_f16_extras(&mqx, query, nq, d, TM))) return rc;
+      if ((rc = make_map_f16_extras(&mbx, base, nb_pad, d, TN))) return rc;
+    } else {
+      P.nkc = (pitch + 127) / 128;
+      P.last_k8 = (pitch - (P.nkc - 1) * 128 + 31) / 32;
+    }
   } else {
     if ((rc = make_map(&mq, query, nq, d, TM))) return rc;
     if ((rc = make_map(&mb, base, nb, d, TN))) return rc;
     if ((rc = make_map(&mbh, base, nb, d, TN / 2))) return rc;
     P.nkc = (d + KC - 1) / KC;
     P.last_k8 = (d - (P.nkc - 1) * KC + 7) / 8;
+  }
+  if (P.xk < 0) {  // unused by the other kinds, but kernel parameters all the same
+    mqx = mq;
+    mbx = mb;
   }
   P.tiles_q = (nq + TM - 1) / TM;
   P.nbt = nbt_logical;
@@ -1405,37 +1472,37 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
     if (plan.pair) return fail(6, "the E4M3 operand kind has no paired-CTA variant");
     if (plan.kprime + 2 * HALF_N * plan.ham_slots > MAXL)
       return fail(6, "packed Hamming pass: k' = %d leaves no room for a tile of appends", plan.kprime);
-    if (P.gmin) return launch_mode<EPI_HAMG, OP_F8>(plan, mq, mb, mbh, P, st);
-    return launch_mode<EPI_HAMP, OP_F8>(plan, mq, mb, mbh, P, st);
+    if (P.gmin) return launch_mode<EPI_HAMG, OP_F8>(plan, mq, mb, mbh, mqx, mbx, P, st);
+    return launch_mode<EPI_HAMP, OP_F8>(plan, mq, mb, mbh, mqx, mbx, P, st);
   }
   if (plan.kind == OP_F8) {
     if (plan.pair) return fail(6, "the E4M3 operand kind has no paired-CTA variant");
     switch (mode) {
-      case EPI_DUMP: return launch_mode<EPI_DUMP, OP_F8>(plan, mq, mb, mbh, P, st);
-      case EPI_GMIN: return launch_mode<EPI_GMIN, OP_F8>(plan, mq, mb, mbh, P, st);
-      case EPI_LISTS: return launch_mode<EPI_LISTS, OP_F8>(plan, mq, mb, mbh, P, st);
+      case EPI_DUMP: return launch_mode<EPI_DUMP, OP_F8>(plan, mq, mb, mbh, mqx, mbx, P, st);
+      case EPI_GMIN: return launch_mode<EPI_GMIN, OP_F8>(plan, mq, mb, mbh, mqx, mbx, P, st);
+      case EPI_LISTS: return launch_mode<EPI_LISTS, OP_F8>(plan, mq, mb, mbh, mqx, mbx, P, st);
       default: return fail(6, "the E4M3 operand kind has no k = 1 margin mode");
     }
   }
   if (plan.kind == OP_F16) {  // plain FP16 operands: the k = 1 margin mode (k-means)
     switch (mode) {
-      case EPI_NEAREST: return launch_mode<EPI_NEAREST, OP_F16>(plan, mq, mb, mbh, P, st);
+      case EPI_NEAREST: return launch_mode<EPI_NEAREST, OP_F16>(plan, mq, mb, mbh, mqx, mbx, P, st);
       default: return fail(6, "plain FP16 operands are only instantiated for the k = 1 margin mode");
     }
   }
   if (plan.kind == OP_F16N) {  // FP16 operands with folded norms: top-k', sampling, dump
     switch (mode) {
-      case EPI_DUMP: return launch_mode<EPI_DUMP, OP_F16N>(plan, mq, mb, mbh, P, st);
-      case EPI_GMIN: return launch_mode<EPI_GMIN, OP_F16N>(plan, mq, mb, mbh, P, st);
-      case EPI_LISTS: return launch_mode<EPI_LISTS, OP_F16N>(plan, mq, mb, mbh, P, st);
+      case EPI_DUMP: return launch_mode<EPI_DUMP, OP_F16N>(plan, mq, mb, mbh, mqx, mbx, P, st);
+      case EPI_GMIN: return launch_mode<EPI_GMIN, OP_F16N>(plan, mq, mb, mbh, mqx, mbx, P, st);
+      case EPI_LISTS: return launch_mode<EPI_LISTS, OP_F16N>(plan, mq, mb, mbh, mqx, mbx, P, st);
       default: return fail(6, "folded-norm FP16 operands have no k = 1 margin mode");
     }
   }
   switch (mode) {
-    case EPI_DUMP: return launch_mode<EPI_DUMP>(plan, mq, mb, mbh, P, st);
-    case EPI_GMIN: return launch_mode<EPI_GMIN>(plan, mq, mb, mbh, P, st);
-    case EPI_NEAREST: return launch_mode<EPI_NEAREST>(plan, mq, mb, mbh, P, st);
-    default: return launch_mode<EPI_LISTS>(plan, mq, mb, mbh, P, st);
+    case EPI_DUMP: return launch_mode<EPI_DUMP>(plan, mq, mb, mbh, mqx, mbx, P, st);
+    case EPI_GMIN: return launch_mode<EPI_GMIN>(plan, mq, mb, mbh, mqx, mbx, P, st);
+    case EPI_NEAREST: return launch_mode<EPI_NEAREST>(plan, mq, mb, mbh, mqx, mbx, P, st);
+    default: return launch_mode<EPI_LISTS>(plan, mq, mb, mbh, mqx, mbx, P, st);
   }
 }
 
