@@ -63,7 +63,13 @@ struct Smem {  // offsets inside the 1024-byte aligned dynamic shared memory blo
   // barriers (8 bytes each)
   static constexpr int a_full = 0, a_empty = 1, b_full = 2, b_empty = b_full + STAGES,
                        n_full = b_empty + STAGES, n_empty = n_full + NBN,
-                       t_full = n_empty + NBN, t_empty = t_full + 2, nbar = t_empty + 2;
+                       t_full = n_empty + NBN, t_empty = t_full + 2, x_full = t_empty + 2,
+                       x_empty = x_full + 2, nbar = x_empty + 2;
+  // folded-norm FP16 with at most two data chunks: the database-side extras (256 rows x 32 bytes)
+  // have their own 2-slot ring in the unused fourth query-chunk slot, so that a tile takes two
+  // stages of the B ring, not three
+  static constexpr int xb_off = a_off + 3 * A_CHUNK_BYTES;
+  static constexpr int XB_BYTES = TN * 32;
   static constexpr int tmem_ptr_off = bar_off + nbar * 8;
   static constexpr int total = tmem_ptr_off + 16;
 };
@@ -345,6 +351,7 @@ struct Tf32Params {
   // ham_slots consecutive database rows, acc = dot_0 + 2^8 dot_1 + 2^16 dot_2 (yb_hamming_tc.cu)
   int xk;              // folded-norm FP16: index of the extras chunk (= number of data chunks), its
   int xcol;            // first column (halfs); -1 / 0 otherwise.  nkc counts the extras chunk too.
+  int xring;           // 1: the database-side extras travel through their own ring (Smem::xb_off)
   int order;           // work items: 0 = range-major (CTAs of a wave stream the SAME database range),
                        // 1 = query-tile-major (a wave covers every range: ~148/splits CTAs per range)
   int ham_slots;       // 2 or 3
@@ -1001,6 +1008,8 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
       mbar_init(bar(Smem::n_empty + i), TEAM_WARPS);  // a |b|^2 slot belongs to one tile, i.e. one team
     }
     for (int i = 0; i < 2; i++) {
+      mbar_init(bar(Smem::x_full + i), 1);
+      mbar_init(bar(Smem::x_empty + i), 1);
       mbar_init(bar(Smem::t_full + i), 1);
       mbar_init(bar(Smem::t_empty + i), TEAM_WARPS);
     }
@@ -1063,7 +1072,15 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
           const int jta = jt * P.tile_stride;  // actual database tile
           bulk_load_1d(sbase + Smem::bn_off + slot * TN * 4, P.bnorm + (size_t)jta * TN, TN * 4,
                        bar(Smem::n_full + slot));
-          for (int kc = 0; kc < P.nkc; kc++, ccount++) {
+          if (P.xring) {  // extras of this tile: own 2-slot ring
+            const uint32_t xs = tcount & 1;
+            mbar_wait(bar(Smem::x_empty + xs), ((tcount >> 1) & 1) ^ 1);
+            mbar_expect_tx(bar(Smem::x_full + xs), Smem::XB_BYTES);
+            tma_load_2d(sbase + Smem::xb_off + xs * Smem::XB_BYTES, &map_bx, bar(Smem::x_full + xs),
+                        P.xcol, jta * TN);
+          }
+          const int nring = P.xring ? P.xk : P.nkc;  // chunks of this tile that use the B ring
+          for (int kc = 0; kc < nring; kc++, ccount++) {
             const uint32_t st = ccount % STAGES;
             mbar_wait(bar(Smem::b_empty + st), ((ccount / STAGES) & 1) ^ 1);
             if ((P.debug & 16) && jt > jt0) {  // bring-up: no TMA traffic after the first tile
@@ -1126,7 +1143,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
             }
             ccount += STAGES;
           } else
-          for (int kc = 0; kc < P.nkc; kc++, ccount++) {
+          for (int kc = 0; kc < (P.xring ? P.xk : P.nkc); kc++, ccount++) {
             const uint32_t st = ccount % STAGES;
             mbar_wait(bar(Smem::b_full + st), (ccount / STAGES) & 1);
             tc_fence_after();
@@ -1156,6 +1173,15 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
               tc_commit_mc_elect(bar(Smem::b_empty + st), (uint16_t)3);
             else
               tc_commit_elect(bar(Smem::b_empty + st));
+          }
+          if (P.xring) {  // the norm term: one MMA over the 16 extra K elements
+            const uint32_t xs = tcount & 1;
+            mbar_wait(bar(Smem::x_full + xs), (tcount >> 1) & 1);
+            tc_fence_after();
+            if (!skip_mma)
+              tc_mma_elect<KIND>(d_tmem, smem_desc_sw32(sbase + Smem::a_off + P.xk * A_CHUNK_BYTES),
+                                 smem_desc_sw32(sbase + Smem::xb_off + xs * Smem::XB_BYTES), 1);
+            tc_commit_elect(bar(Smem::x_empty + xs));
           }
           tc_commit_elect(bar(Smem::t_full + buf));  // accumulator complete
         }
@@ -1401,13 +1427,20 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
     if ((rc = make_map_f16(&mq, query, nq, d, TM))) return rc;
     if ((rc = make_map_f16(&mb, base, nb_pad, d, TN))) return rc;
     if ((rc = make_map_f16(&mbh, base, nb_pad, d, TN / 2))) return rc;
-    if (plan.kind == OP_F16N) {
-      // data columns [0, d - 16) in 128-byte chunks, then the 16 extras as one 32-byte-wide chunk
+    if (plan.kind == OP_F16N && ((d - 16) % 64) != 0) {
+      // the 16 extras fit behind the data inside the last 128-byte chunk: nothing special
+      // (d = 96: 2.49 ms this way, 2.58 ms with a separate extras chunk)
+      P.nkc = (pitch + 127) / 128;
+      P.last_k8 = (pitch - (P.nkc - 1) * 128 + 31) / 32;
+    } else if (plan.kind == OP_F16N) {
+      // data columns [0, d - 16) fill whole 128-byte chunks; the 16 extras travel as one
+      // 32-byte-wide chunk (a zero-filled 128-byte one costs 2.74 ms instead of 2.62 at d = 128)
       const int dd = d - 16, dbytes = 2 * dd;
       const int nkd = (dbytes + 127) / 128;
       if (nkd + 1 > MAX_NKC) return fail(6, "folded-norm FP16 operands: d = %d needs too many chunks", dd);
       P.xk = nkd;
       P.xcol = dd;
+      P.xring = nkd <= 2 && !getenv("YAEL_B200_NO_XRING");
       P.nkc = nkd + 1;
       P.last_k8 = (dbytes - (nkd - 1) * 128 + 31) / 32;
       if ((rc = make_map_f16_extras(&mqx, query, nq, d, TM))) return rc;
