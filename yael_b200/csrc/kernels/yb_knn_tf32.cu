@@ -994,6 +994,12 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto bar = [&](int i) { return sbase + Smem::bar_off + 8 * i; };
+  // the extras-chunk machinery exists only in the folded-norm instantiations: the producer and
+  // issuer loops of every other kind compile exactly as they did without it (the packed Hamming
+  // pass lost 14 % to the mere presence of the run-time checks)
+  constexpr bool NFK = KIND == OP_F16N;
+  const int xk = NFK ? P.xk : -1;
+  const bool xring = NFK && P.xring != 0;
   volatile uint32_t *tmem_ptr_smem = (volatile uint32_t *)(smem + Smem::tmem_ptr_off);
 
   if (threadIdx.x == 0) {
@@ -1056,14 +1062,14 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
         // query tile: wait until the MMAs of the previous item have drained A
         mbar_wait(bar(Smem::a_empty), (icount & 1) ^ 1);
-        const int nkd = P.xk >= 0 ? P.xk : P.nkc;  // 128-byte data chunks
+        const int nkd = xk >= 0 ? xk : P.nkc;  // 128-byte data chunks
         mbar_expect_tx(bar(Smem::a_full),
-                       (uint32_t)(nkd * A_CHUNK_BYTES + (P.xk >= 0 ? TM * 32 : 0)));
+                       (uint32_t)(nkd * A_CHUNK_BYTES + (xk >= 0 ? TM * 32 : 0)));
         for (int kc = 0; kc < nkd; kc++)
           tma_load_2d(sbase + Smem::a_off + kc * A_CHUNK_BYTES, &map_q, bar(Smem::a_full), kc * KCE,
                       qt * TM);
-        if (P.xk >= 0)
-          tma_load_2d(sbase + Smem::a_off + P.xk * A_CHUNK_BYTES, &map_qx, bar(Smem::a_full), P.xcol,
+        if (xk >= 0)
+          tma_load_2d(sbase + Smem::a_off + (xk < 0 ? 0 : xk) * A_CHUNK_BYTES, &map_qx, bar(Smem::a_full), P.xcol,
                       qt * TM);
         for (int jt = jt0; jt < jt1; jt++, tcount++) {
           const uint32_t slot = tcount % NBN;
@@ -1072,14 +1078,14 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
           const int jta = jt * P.tile_stride;  // actual database tile
           bulk_load_1d(sbase + Smem::bn_off + slot * TN * 4, P.bnorm + (size_t)jta * TN, TN * 4,
                        bar(Smem::n_full + slot));
-          if (P.xring) {  // extras of this tile: own 2-slot ring
+          if (xring) {  // extras of this tile: own 2-slot ring
             const uint32_t xs = tcount & 1;
             mbar_wait(bar(Smem::x_empty + xs), ((tcount >> 1) & 1) ^ 1);
             mbar_expect_tx(bar(Smem::x_full + xs), Smem::XB_BYTES);
             tma_load_2d(sbase + Smem::xb_off + xs * Smem::XB_BYTES, &map_bx, bar(Smem::x_full + xs),
                         P.xcol, jta * TN);
           }
-          const int nring = P.xring ? P.xk : P.nkc;  // chunks of this tile that use the B ring
+          const int nring = xring ? xk : P.nkc;  // chunks of this tile that use the B ring
           for (int kc = 0; kc < nring; kc++, ccount++) {
             const uint32_t st = ccount % STAGES;
             mbar_wait(bar(Smem::b_empty + st), ((ccount / STAGES) & 1) ^ 1);
@@ -1087,7 +1093,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
               mbar_arrive(bar(Smem::b_full + st));
               continue;
             }
-            if (kc == P.xk) {  // the 16 extra K elements: a 32-byte-wide box
+            if (kc == xk) {  // the 16 extra K elements: a 32-byte-wide box
               mbar_expect_tx(bar(Smem::b_full + st), TN * 32);
               tma_load_2d(sbase + Smem::b_off + st * B_CHUNK_BYTES, &map_bx, bar(Smem::b_full + st),
                           P.xcol, jta * TN);
@@ -1113,7 +1119,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     {
       uint32_t icount = 0, ccount = 0, tcount = 0;
       const bool skip_mma = (P.debug & 2) != 0;
-      const bool ring_aligned = P.nkc == STAGES && P.last_k8 == 4 && P.xk < 0;
+      const bool ring_aligned = P.nkc == STAGES && P.last_k8 == 4 && xk < 0;
       for (int item = first_item; item < P.items; item += item_step, icount++) {
         const int sp = P.order ? item % P.splits : item / tq_div;
         const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
@@ -1143,19 +1149,19 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
             }
             ccount += STAGES;
           } else
-          for (int kc = 0; kc < (P.xring ? P.xk : P.nkc); kc++, ccount++) {
+          for (int kc = 0; kc < (xring ? xk : P.nkc); kc++, ccount++) {
             const uint32_t st = ccount % STAGES;
             mbar_wait(bar(Smem::b_full + st), (ccount / STAGES) & 1);
             tc_fence_after();
             const uint64_t adesc = smem_desc_sw128(sbase + Smem::a_off + kc * A_CHUNK_BYTES);
             const uint64_t bdesc = smem_desc_sw128(sbase + Smem::b_off + st * B_CHUNK_BYTES);
             // advancing K inside the 128-byte swizzle span: +32 bytes = +2 in 16-byte units
-            if (kc == P.xk) {
+            if (kc == xk) {
               if (!skip_mma)
                 tc_mma_elect<KIND>(d_tmem, smem_desc_sw32(sbase + Smem::a_off + kc * A_CHUNK_BYTES),
                                    smem_desc_sw32(sbase + Smem::b_off + st * B_CHUNK_BYTES), 1);
             } else if (!skip_mma) {
-              const int last_data = (P.xk >= 0 ? P.xk : P.nkc) - 1;
+              const int last_data = (xk >= 0 ? xk : P.nkc) - 1;
               if (kc != last_data || P.last_k8 == 4) {
                 tc_mma_elect<KIND>(d_tmem, adesc, bdesc, kc != 0);
                 tc_mma_elect<KIND>(d_tmem, adesc + 2, bdesc + 2, 1);
@@ -1174,12 +1180,12 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
             else
               tc_commit_elect(bar(Smem::b_empty + st));
           }
-          if (P.xring) {  // the norm term: one MMA over the 16 extra K elements
+          if (xring) {  // the norm term: one MMA over the 16 extra K elements
             const uint32_t xs = tcount & 1;
             mbar_wait(bar(Smem::x_full + xs), (tcount >> 1) & 1);
             tc_fence_after();
             if (!skip_mma)
-              tc_mma_elect<KIND>(d_tmem, smem_desc_sw32(sbase + Smem::a_off + P.xk * A_CHUNK_BYTES),
+              tc_mma_elect<KIND>(d_tmem, smem_desc_sw32(sbase + Smem::a_off + (xk < 0 ? 0 : xk) * A_CHUNK_BYTES),
                                  smem_desc_sw32(sbase + Smem::xb_off + xs * Smem::XB_BYTES), 1);
             tc_commit_elect(bar(Smem::x_empty + xs));
           }
