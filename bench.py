@@ -631,10 +631,10 @@ def run_ours(args):
         roof = {"bound": "tensor",
                 "kernel": "k_knn_tf32<EPI_LISTS, %s> (full pass; the sampling passes are in phase_ms)" % operands,
                 "operands": operands,
-                "note": ("FP16 operands need half as many MMAs per tile as TF32: TMA + MMA alone take 1.75 ms of "
-                         "this pass (bring-up switches, same shape); the rest is the fused top-k epilogue -- TMEM "
-                         "loads and score / min math that overlap imperfectly (~0.7 ms) and the admission path "
-                         "(~0.4 ms) -- see DESIGN.md 5.1 and profiles/README.md"),
+                "note": ("FP16 operands (half as many MMAs per tile as TF32) with |b|^2 folded into the "
+                         "contraction: the epilogue is a MAX tree over raw accumulators; ncu: tensor pipe 52 % "
+                         "busy; the pass is paced by the fused top-k epilogue and the operand feed, not by the MMA "
+                         "rate -- decomposition in DESIGN.md 5.1 and profiles/README.md"),
                 "achieved": ach, "peak": peak,
                 "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "kernel_ms": kms, "peak_source": peak_src,
