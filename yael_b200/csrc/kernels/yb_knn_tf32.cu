@@ -1,27 +1,33 @@
 // yb_knn_tf32.cu -- the distance GEMM of knn_full / nn_single_full (yael/nn.c:54-67,92-129,
-// 383-525) as a tcgen05 TF32 tensor-core kernel with the per-query top-k fused into its
-// epilogue.  The nq x nb distance matrix never reaches HBM.
+// 383-525) as a tcgen05 tensor-core kernel with the per-query top-k fused into its epilogue.  The
+// nq x nb distance matrix never reaches HBM.  (The file keeps its first name: the kernel started
+// with TF32 operands only.)
 //
 // What it computes: for every query q and database row b the SCORE s = |b|^2 - 2 <q,b> with
-// TF32 operands and FP32 accumulation (|q|^2 is constant per query and irrelevant for the
-// ranking), and per (query, database range) the k' smallest scores with their row ids.  The
-// caller (yb_knn.cu) re-ranks those in exact FP32 and certifies the result.
+// reduced-precision operands and FP32 accumulation (|q|^2 is constant per query and irrelevant
+// for the ranking), and per (query, database range) the k' smallest scores with their row ids.
+// The caller (yb_knn.cu) re-ranks those in exact FP32 and certifies the result.  Operand kinds
+// (template parameter KIND, one instantiation per kind and epilogue mode):
+//   OP_TF32  FP32 rows read as TF32 (kind::tf32, K = 8 per MMA): fallback, streamed host path
+//   OP_F16   FP16 rows (kind::f16, K = 16): the k = 1 margin mode of k-means
+//   OP_F16N  FP16 rows that carry |b|^2 in 16 extra K elements (folded norms): the epilogue is a
+//            MAX tree over raw accumulators -- top-k', sampling and dump modes of k-NN
+//   OP_F8    E4M3 +-1 rows (kind::f8f6f4, K = 32): Hamming distances, exact (yb_hamming_tc.cu)
 //
 // Shape of the kernel (one persistent CTA per SM, 320 threads, warp-specialised):
 //   warp 8   TMA producer: query tile A (128 rows x d, resident in smem for a whole work item),
-//            database chunks B (256 rows x 32 floats, 4-stage ring), |b|^2 tiles (1-D bulk copy)
-//   warp 9   MMA issuer: tcgen05.mma.cta_group::1.kind::tf32, M=128 (queries) x N=256 (rows) x
-//            K=8 per instruction, SWIZZLE_128B K-major operands straight from the TMA layout,
+//            database chunks B (256 rows x 128 bytes, 4-stage ring), |b|^2 tiles (1-D bulk copy)
+//   warp 9   MMA issuer: tcgen05.mma.cta_group::1, M=128 (queries) x N=256 (rows) x 32 bytes of K
+//            per instruction, SWIZZLE_128B K-major operands straight from the TMA layout,
 //            accumulators in TMEM, double buffered (2 x 256 columns) so the epilogue of tile t
 //            overlaps the MMAs of tile t+1
 //   warps 0-7 epilogue: two warps per scheduler.  Thread (w, lane) owns query 32*(w%4)+lane of
 //            the tile (its TMEM lane) for the column half w/4 of every tile.  tcgen05.ld brings
-//            32 columns at a time; s = fma(acc, -2, |b|^2); a candidate with s < thr (the running
-//            k'-th best of this thread's list, a register) is appended to the list in
-//            L2-resident scratch by PREDICATED stores (no branch per candidate).  When a list
-//            fills up the warp compacts it cooperatively (keys in registers, 4-pass radix
-//            select) and tightens thr.  This replaces the reference's binheap
-//            (yael/binheap.c:139-156) with the same strict '<' admission rule.
+//            16 columns at a time; a group whose best score beats thr (the query's admission
+//            threshold, a register) is scanned and its candidates appended to the query's list in
+//            L2-resident scratch.  When a list fills up the warp compacts it cooperatively (keys
+//            in registers, 4-pass radix select) and tightens thr.  This replaces the reference's
+//            binheap (yael/binheap.c:139-156) with the same strict '<' admission rule.
 // Work items are (query tile, database range) pairs walked range-major so that the CTAs that
 // run concurrently stream the same database range and share it through L2.
 #include <cuda.h>
