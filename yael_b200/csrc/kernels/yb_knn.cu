@@ -1332,10 +1332,14 @@ static int knn_tf32_nearest(int nq, int nb, int d, const float *base, const floa
                             int *assign, float *dis, int id_offset, long *uncert_out,
                             cudaStream_t st, int kind) {
   const bool f16 = kind == 2;
-  const int dh = (d + 7) & ~7;                             // FP16: data elements per row
-  const int dpad = f16 ? dh : (d + 3) & ~3;                // operand row pitch in elements
-  // (plain FP16 operands here: folding |b|^2 into K costs a third 128-byte chunk at d = 128, which
-  // the k = 1 epilogue does not win back: 188 ms plain vs 192 ms folded for BASELINE config 4)
+  // FP16 operands with folded norms (kind 3; the extras travel as a 32-byte chunk through their own
+  // ring: BASELINE config 4 pass 186.8 -> 176.4 ms) unless YAEL_B200_K1_FOLD=0 (plain kind 2, FMA
+  // epilogue)
+  const char *kf = getenv("YAEL_B200_K1_FOLD");
+  const bool fold = f16 && !(kf && atoi(kf) == 0);
+  if (fold) kind = 3;
+  const int dh = fold ? (d + 15) & ~15 : (d + 7) & ~7;     // FP16: data elements per row
+  const int dpad = f16 ? dh + (fold ? kNfExtra : 0) : (d + 3) & ~3;  // operand row pitch in elements
   Tf32Plan plan = tf32_plan_nearest(nq, nb, dpad, kind);
   if (!plan.ok) return -1000;
   const int kp = plan.kprime, slots = plan.lists * kp;
@@ -1376,7 +1380,7 @@ static int knn_tf32_nearest(int nq, int nb, int d, const float *base, const floa
         // no FP32 copy of the centred queries (for k-means they are the 10^7 points): the margin
         // comes from the norms the conversion kernel emits
         if ((rc = center_operands_h(nq, nb, d, dh, dh, base, query, (__half *)base_c,
-                                    (__half *)query_c, nullptr, an, qcnorm, scal, cws, st, false)))
+                                    (__half *)query_c, nullptr, an, qcnorm, scal, cws, st, fold)))
           return rc;
         plan.acc_scale = scal + 3;
       } else {

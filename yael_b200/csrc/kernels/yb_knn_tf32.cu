@@ -1540,7 +1540,7 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
       case EPI_DUMP: return launch_mode<EPI_DUMP, OP_F16N>(plan, mq, mb, mbh, mqx, mbx, P, st);
       case EPI_GMIN: return launch_mode<EPI_GMIN, OP_F16N>(plan, mq, mb, mbh, mqx, mbx, P, st);
       case EPI_LISTS: return launch_mode<EPI_LISTS, OP_F16N>(plan, mq, mb, mbh, mqx, mbx, P, st);
-      default: return fail(6, "folded-norm FP16 operands have no k = 1 margin mode");
+      default: return launch_mode<EPI_NEAREST, OP_F16N>(plan, mq, mb, mbh, mqx, mbx, P, st);
     }
   }
   switch (mode) {
