@@ -176,7 +176,9 @@ class ClockSampler:
 # ----------------------------------------------------------------------------- CPU baseline
 def cpu_reference_rate(base, query, target_s=15.0, max_q=NQ):
     """Time the reference's own CPU implementation (knn_full_thread, yael/nn.c:679-699) on a
-    bounded sample: all host threads, OPENBLAS_NUM_THREADS=1 (yael threads itself)."""
+    bounded sample: all host threads, OPENBLAS_NUM_THREADS=1 (yael threads itself).  Returns the
+    cpu_baseline object and the reference's ANSWER for the sampled queries (n, idx, dis), which
+    run_ours compares with the GPU result outside any timed region."""
     from oracle import bindings as ob
     cores = len(os.sched_getaffinity(0))
     if ob.have_ref():
@@ -193,10 +195,38 @@ def cpu_reference_rate(base, query, target_s=15.0, max_q=NQ):
     n = int(min(max_q, max(probe, rate * target_s)))
     n = max(cores, (n // cores) * cores)
     t = time.perf_counter()
-    fn(base, query[:n])
+    widx, wdis = fn(base, query[:n])
     dt = time.perf_counter() - t
-    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": "%d of %d queries against the full 1M x 128 database, k=100, %.1f s" % (n, NQ, dt)}
+    return ({"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind,
+             "sample": "%d of %d queries against the full 1M x 128 database, k=100, %.1f s" % (n, NQ, dt)},
+            (n, widx, wdis))
+
+
+def knn_parity(idx, dis, widx, wdis, base, query, config):
+    """GPU result against the reference's for the same queries (north-star tolerance: distances
+    within 1e-5 relative, ids identical except for ties inside that tolerance).  A differing id is
+    accepted only if its OWN distance to the query, recomputed in float64, is within the tolerance
+    of the reference's distance at that rank."""
+    n = widx.shape[0]
+    idx, dis = idx[:n], dis[:n]
+    valid = widx >= 0
+    rel = np.abs(dis[valid].astype(np.float64) - wdis[valid]) / np.maximum(np.abs(wdis[valid]), 1e-30)
+    diff = (idx != widx) & valid
+    ties_ok = True
+    b64 = None
+    for qi, j in zip(*np.nonzero(diff)):
+        own = ((base[idx[qi, j]].astype(np.float64) - query[qi].astype(np.float64)) ** 2).sum()
+        if abs(own - float(wdis[qi, j])) > 1e-5 * max(abs(float(wdis[qi, j])), 1e-6) + 2e-6 * float(
+                (query[qi].astype(np.float64) ** 2).sum()):
+            ties_ok = False
+    dup_free = all(len(set(r.tolist())) == len(r) for r in idx[np.unique(np.nonzero(diff)[0])])
+    del b64
+    return {"config": config, "n_queries": int(n), "checked_against": "reference CPU result of cpu_baseline",
+            "ids_identical": int((~diff).all(axis=1).sum()), "ids_differing_entries": int(diff.sum()),
+            "ids_equal_outside_ties": bool(ties_ok and dup_free and np.array_equal(valid, idx >= 0)),
+            "max_rel_dis": float(rel.max()) if rel.size else 0.0,
+            "distances_bit_identical": bool(np.array_equal(dis[valid], wdis[valid])),
+            "ok": bool(ties_ok and dup_free and (rel.max() if rel.size else 0.0) <= 1e-5)}
 
 
 def run_reference(args):
@@ -267,129 +297,339 @@ def measure_tf32_peak(torch, dev):
         return None
 
 
-def measure_extras(torch, L, dev):
-    """The other two BASELINE shapes, device-resident, one GPU (reported beside the headline;
-    the headline line above stays the kNN workload):
-      - k-means, BASELINE configs[3]: n = 10M, d = 128, k = 65536 (iterations/s, 2 iterations)
-      - Hamming kNN, BASELINE configs[2]: 10M x 64-bit codes, 10k queries, k = 100"""
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def _phase_means(L, names):
+    cnt = C.c_long(0)
     out = {}
-    try:
-        del_later = []
-        torch.manual_seed(1236)
-        nbh, nqh = 10_000_000, 10_000
-        hb = torch.randint(0, 256, (nbh, 8), device=dev, dtype=torch.uint8)
-        hq = torch.randint(0, 256, (nqh, 8), device=dev, dtype=torch.uint8)
-        hi = torch.empty((nqh, 100), device=dev, dtype=torch.int32)
-        hd = torch.empty((nqh, 100), device=dev, dtype=torch.int16)
-        sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-        def time_engine(engine, reps):
-            L.yb_set_hamming_engine(engine)
-            best = 1e9
-            for _ in range(reps):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                rc = L.yb_nn_hamming(nqh, nbh, 8, 100, hb.data_ptr(), hq.data_ptr(), hi.data_ptr(), hd.data_ptr(), 0, sp)
-                e1.record()
-                e1.synchronize()
-                if rc == 0:
-                    best = min(best, e0.elapsed_time(e1))
-            used, fb = L.yb_last_hamming_engine(), L.yb_last_hamming_fallbacks()
-            L.yb_set_hamming_engine(-1)
-            return best, used, fb
-
-        peak_pairs = L.yb_debug_popc_pairs_per_s(sp)
-        if not peak_pairs or peak_pairs <= 0:
-            peak_pairs = 148 * 8 * 1.9e9
-        # engine 0: popcount scan on the CUDA cores (what the north star names)
-        ms0, used0, _ = time_engine(0, 2)
-        res0 = (hi.clone(), hd.clone())
-        # engine 1 (default at this size): exact E4M3 contraction on the tensor cores
-        time_engine(1, 1)
-        L.yb_prof_enable(1)
-        L.yb_prof_ms(12, None, 1)
-        ms1, used1, fb1 = time_engine(1, 3)
-        cnt = C.c_long(0)
-        ph = {}
-        for pid, name in ((12, "expand_codes"), (13, "sample_thresholds"), (14, "e4m3_pass"),
-                          (15, "order_and_certify"), (7, "scan_fallback")):
-            t = L.yb_prof_ms(pid, C.byref(cnt), 0)
-            if cnt.value:
-                ph[name] = t / cnt.value
-        L.yb_prof_ms(0, None, 1)
-        L.yb_prof_enable(0)
-        same = bool(torch.equal(res0[0], hi) and torch.equal(res0[1], hd))
-        best = min(ms0, ms1) if used1 == 1 else ms0
-        pairs = nqh * nbh / (best * 1e-3)
-        bf16 = 1637.4
-        try:
-            bf16 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", bf16)
-        except Exception:
-            pass
-        entry = {
-            "queries_per_s": nqh / (best * 1e-3), "ms": best, "pair_distances_per_s": pairs,
-            "engines": {
-                "popcount_scan": {
-                    "ms": ms0, "queries_per_s": nqh / (ms0 * 1e-3),
-                    "roofline": {"bound": "popcount pipe: 64-bit xor+popc pair rate MEASURED in this run by a "
-                                          "register-only micro-benchmark (yb_debug_popc_pairs_per_s)",
-                                 "achieved": nqh * nbh / (ms0 * 1e-3), "peak": peak_pairs,
-                                 "frac": nqh * nbh / (ms0 * 1e-3) / peak_pairs, "unit": "pairs/s"}},
-            },
-            "engines_agree_bit_for_bit": same,
-            "note": "algorithmic HBM traffic is 86 MB (13 us at peak): not HBM bound"}
-        if used1 == 1:
-            kms = ph.get("e4m3_pass", ms1)
-            ops = 2.0 * nqh * nbh * 64
-            entry["engines"]["tensor_e4m3"] = {
-                "ms": ms1, "queries_per_s": nqh / (ms1 * 1e-3), "phase_ms": ph,
-                "queries_redone_by_the_scan": int(fb1),
-                "roofline": {"bound": "tensor", "kernel": "k_knn_tf32<EPI_LISTS, F8> (kind::f8f6f4, +-1 operands)",
-                             "achieved": ops / (kms * 1e-3) / 1e12, "peak": 2.0 * bf16, "unit": "TFLOP/s",
-                             "frac": ops / (kms * 1e-3) / 1e12 / (2.0 * bf16),
-                             "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (fp8 dense = twice the bf16 rate)",
-                             "algorithmic_flops_per_launch": ops,
-                             "note": "K = 64 per tile: two MMAs against a 128 x 256 epilogue, so the pass is "
-                                     "epilogue bound by construction; pairs/s vs the popcount ceiling: %.2f"
-                                     % (nqh * nbh / (kms * 1e-3) / peak_pairs)}}
-        out["hamming_knn_10Mx64bit_10kq_k100"] = entry
-        del hb, hq, hi, hd
-        torch.cuda.empty_cache()
-    except Exception as e:  # extras never break the headline line
-        out["hamming_error"] = str(e)
-    try:
-        from yael_b200.ynumpy import KMEANS_INIT_USER, KMEANS_QUIET
-        n, d, k, niter = 10_000_000, 128, 65536, 2
-        torch.manual_seed(1237)
-        v = torch.rand((n, d), device=dev, dtype=torch.float32)
-        cent = v[torch.randperm(n, device=dev)[:k]].cpu().numpy().copy()
-        nassign = np.empty(k, np.int32)
-        f, i = C.POINTER(C.c_float), C.POINTER(C.c_int)
-        L.yb_prof_enable(1)
-        L.yb_prof_ms(1, None, 1)
-        times = []
-        for _ in range(2):
-            c = cent.copy()
-            torch.cuda.synchronize()
-            t = time.perf_counter()
-            q = L.yb_kmeans_dev(d, n, k, niter, v.data_ptr(), KMEANS_INIT_USER | KMEANS_QUIET, 1, 1,
-                                c.ctypes.data_as(f), None, None, nassign.ctypes.data_as(i), None, None)
-            torch.cuda.synchronize()
-            times.append((time.perf_counter() - t) / niter)
-        cnt = C.c_long(0)
-        tms = L.yb_prof_ms(1, C.byref(cnt), 1)
-        kms = tms / max(1, cnt.value)
-        L.yb_prof_enable(0)
-        out["kmeans_10Mx128_k65536"] = {
-            "iter_per_s": 1.0 / min(times), "s_per_iter": min(times), "qerr": float(q),
-            "assignment_tf32_kernel_ms": kms,
-            "assignment_tflops": 2.0 * n * k * d / (kms * 1e-3) / 1e12,
-            "note": "one GPU, points resident in HBM, centroids from a seeded permutation (USER init)"}
-        del v
-        torch.cuda.empty_cache()
-    except Exception as e:
-        out["kmeans_error"] = str(e)
+    for pid, name in names:
+        t = L.yb_prof_ms(pid, C.byref(cnt), 0)
+        if cnt.value:
+            out[name] = t / cnt.value
     return out
+
+
+def measure_hamming(torch, L, dev):
+    """BASELINE configs[2]: Hamming k-NN, 10M x 64-bit packed codes, 10k queries, k = 100, one GPU.
+    value: yb_nn_hamming on HBM-resident codes (CUDA events).  e2e: the drop-in nn_hamming() on
+    pinned HOST buffers (copies inside the timed region).  roofline: both engines.  cpu_baseline:
+    the reference's compute_hamming (yael/hamming.c:177-219) over database blocks + stable select
+    on a >= 1e9-pair slice, all host threads.  parity: the GPU answer for that slice's queries
+    against the CPU answer, bit for bit."""
+    nbh, nqh, kh = 10_000_000, 10_000, 100
+    torch.manual_seed(1236)
+    hb = torch.randint(0, 256, (nbh, 8), device=dev, dtype=torch.uint8)
+    hq = torch.randint(0, 256, (nqh, 8), device=dev, dtype=torch.uint8)
+    hi = torch.empty((nqh, kh), device=dev, dtype=torch.int32)
+    hd = torch.empty((nqh, kh), device=dev, dtype=torch.int16)
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def time_engine(engine, reps):
+        L.yb_set_hamming_engine(engine)
+        best = 1e9
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = L.yb_nn_hamming(nqh, nbh, 8, kh, hb.data_ptr(), hq.data_ptr(), hi.data_ptr(), hd.data_ptr(), 0, sp)
+            e1.record()
+            e1.synchronize()
+            if rc == 0:
+                best = min(best, e0.elapsed_time(e1))
+        used, fb = L.yb_last_hamming_engine(), L.yb_last_hamming_fallbacks()
+        L.yb_set_hamming_engine(-1)
+        return best, used, fb
+
+    peak_pairs = L.yb_debug_popc_pairs_per_s(sp)
+    if not peak_pairs or peak_pairs <= 0:
+        peak_pairs = 148 * 8 * 1.9e9
+    time_engine(0, 1)                      # warm-up
+    L.yb_prof_enable(1)
+    L.yb_prof_ms(7, None, 1)
+    ms0, used0, _ = time_engine(0, 3)      # engine 0: popcount scan on the CUDA cores
+    ph0 = _phase_means(L, ((7, "popcount_scan"),))
+    L.yb_prof_ms(0, None, 1)
+    res0 = (hi.clone(), hd.clone())
+    for _ in range(3):
+        time_engine(1, 1)                  # engine 1 warm-up (>= 3 steps)
+    L.yb_prof_ms(12, None, 1)
+    ms1, used1, fb1 = time_engine(1, 5)    # engine 1: exact E4M3 contraction on the tensor cores
+    ph = _phase_means(L, ((12, "expand_codes"), (13, "sample_thresholds"), (14, "e4m3_pass"),
+                          (15, "order_and_certify"), (7, "scan_fallback")))
+    L.yb_prof_ms(0, None, 1)
+    L.yb_prof_enable(0)
+    gpu_idx = hi.cpu().numpy()
+    gpu_dis = hd.cpu().numpy().view(np.uint16)
+    same = bool(torch.equal(res0[0], hi) and torch.equal(res0[1], hd))
+    best = min(ms0, ms1) if used1 == 1 else ms0
+    bf16 = _peaks().get("bf16_tflops", 1590.0)
+    scan_ms = ph0.get("popcount_scan", ms0)
+    block = {
+        "metric": "Hamming kNN queries/s (10M x 64-bit codes, 10k queries, k=100)",
+        "value": nqh / (best * 1e-3), "unit": "queries/s", "ms_per_step": best,
+        "dtype": "u8 codes, u16 distances (bit-exact)",
+        "config": {"workload": "Hamming kNN: 10M x 64-bit packed codes, 10000 queries, k=100 (BASELINE configs[2])",
+                   "engine_used": "tensor_e4m3" if (used1 == 1 and ms1 <= ms0) else "popcount_scan",
+                   "l2": "80 MB of codes fit in L2; expanded operands (640 MB) do not"},
+        "pair_distances_per_s": nqh * nbh / (best * 1e-3),
+        "engines_agree_bit_for_bit": same,
+        "roofline": {"bound": "hbm", "kernel": "k_nn_hamming_scan (engine 0, what the north star names)",
+                     "achieved": 86e6 / (scan_ms * 1e-3) / 1e9, "peak": _peaks().get("hbm_gbs", 6450.0),
+                     "unit": "GB/s", "frac": 86e6 / (scan_ms * 1e-3) / 1e9 / _peaks().get("hbm_gbs", 6450.0),
+                     "traffic": None, "kernel_ms": scan_ms,
+                     "algorithmic_bytes_per_launch": 86e6,
+                     "note": "HBM is NOT what bounds this scan (86 MB algorithmic = 13 us at peak): at 10k "
+                             "queries it is bound by the popcount pipe -- see roofline_popc"},
+        "roofline_popc": {"bound": "popcount pipe: 64-bit xor+popc pair rate MEASURED in this run by a "
+                                   "register-only micro-benchmark (yb_debug_popc_pairs_per_s)",
+                          "kernel": "k_nn_hamming_scan", "achieved": nqh * nbh / (scan_ms * 1e-3),
+                          "peak": peak_pairs, "frac": nqh * nbh / (scan_ms * 1e-3) / peak_pairs,
+                          "unit": "pairs/s", "kernel_ms": scan_ms},
+        "engines": {"popcount_scan": {"ms": ms0, "queries_per_s": nqh / (ms0 * 1e-3)}},
+    }
+    if used1 == 1:
+        kms = ph.get("e4m3_pass", ms1)
+        ops = 2.0 * nqh * nbh * 64
+        block["engines"]["tensor_e4m3"] = {"ms": ms1, "queries_per_s": nqh / (ms1 * 1e-3), "phase_ms": ph,
+                                           "queries_redone_by_the_scan": int(fb1)}
+        block["roofline_tensor"] = {
+            "bound": "tensor", "kernel": "k_knn_tf32<EPI_HAMP, F8> (kind::f8f6f4, +-1 operands)",
+            "achieved": ops / (kms * 1e-3) / 1e12, "peak": 2.0 * bf16, "unit": "TFLOP/s",
+            "frac": ops / (kms * 1e-3) / 1e12 / (2.0 * bf16), "kernel_ms": kms,
+            "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (fp8 dense = twice the bf16 rate)",
+            "algorithmic_flops_per_launch": ops,
+            "pairs_per_s_vs_popcount_ceiling": nqh * nbh / (kms * 1e-3) / peak_pairs}
+
+    # ---- e2e: nn_hamming() on pinned host buffers
+    hb_h = hb.cpu().pin_memory()
+    hq_h = hq.cpu().pin_memory()
+    oi_h = torch.empty((nqh, kh), dtype=torch.int32).pin_memory()
+    od_h = torch.empty((nqh, kh), dtype=torch.int16).pin_memory()
+    u8, u16, i32 = C.POINTER(C.c_uint8), C.POINTER(C.c_uint16), C.POINTER(C.c_int)
+
+    def e2e_step():
+        L.nn_hamming(nqh, nbh, 8, kh, C.cast(hb_h.data_ptr(), u8), C.cast(hq_h.data_ptr(), u8),
+                     C.cast(oi_h.data_ptr(), i32), C.cast(od_h.data_ptr(), u16))
+
+    for _ in range(3):
+        e2e_step()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        e2e_step()
+    te = (time.perf_counter() - t0) / 5
+    block["e2e"] = {"value": nqh / te, "unit": "queries/s", "ms_per_step": te * 1e3,
+                    "h2d_bytes_per_step": int(nbh * 8 + nqh * 8), "d2h_bytes_per_step": int(nqh * kh * 6),
+                    "call": "nn_hamming() on pinned host buffers"}
+    e2e_same = bool(np.array_equal(oi_h.numpy(), gpu_idx) and np.array_equal(od_h.numpy().view(np.uint16), gpu_dis))
+
+    # ---- CPU baseline + parity on a >= 1e9-pair slice (100 queries x 10M codes)
+    try:
+        from oracle import bindings as ob
+        ns = 100
+        cores = len(os.sched_getaffinity(0))
+        t = time.perf_counter()
+        widx, wdis, kind = ob.ref_nn_hamming_blocked(hb_h.numpy(), hq_h.numpy()[:ns], kh, threads=cores)
+        dt = time.perf_counter() - t
+        block["cpu_baseline"] = {"value": ns / dt, "unit": "queries/s", "cores": cores, "kind": kind,
+                                 "sample": "%d of %d queries x 10M codes (%.1e pairs): compute_hamming over 1M-code "
+                                           "blocks on %d threads + stable (distance, id) select, %.1f s"
+                                           % (ns, nqh, ns * nbh, cores, dt)}
+        block["parity"] = {"config": "C3: 10M x 64-bit codes, k=100", "n_queries": ns,
+                           "pairs_checked": int(ns * nbh),
+                           "ids_bit_identical": bool(np.array_equal(gpu_idx[:ns], widx)),
+                           "distances_bit_identical": bool(np.array_equal(gpu_dis[:ns], wdis)),
+                           "e2e_call_equals_resident_call": e2e_same,
+                           "ok": bool(np.array_equal(gpu_idx[:ns], widx) and np.array_equal(gpu_dis[:ns], wdis) and same)}
+    except Exception as e:
+        block["cpu_baseline_error"] = str(e)
+    del hb, hq, hi, hd, hb_h, hq_h
+    torch.cuda.empty_cache()
+    return block
+
+
+def measure_kmeans(torch, L, dev, niter=10):
+    """BASELINE configs[3] on one GPU: k-means, n = 10M, d = 128, k = 65536, `niter` iterations from a
+    seeded permutation of the points (KMEANS_INIT_USER).  value: iterations/s with the points
+    resident in HBM (yb_kmeans_dev).  e2e: the drop-in kmeans() on pinned HOST points.  roofline:
+    the assignment's tensor pass (tensor) and the centroid update (HBM).  cpu_baseline: the
+    reference's assignment (knn_full_thread k = 1, yael/kmeans.c:242) on a slice of the points
+    against all 65536 centroids, scaled to an iteration; plus the reference's kmeans() on BASELINE
+    configs[0].  parity: the teacher-forced GPU step on that slice against the reference's."""
+    from yael_b200.ynumpy import KMEANS_INIT_USER, KMEANS_QUIET
+    n, d, k = 10_000_000, 128, 65536
+    torch.manual_seed(1237)
+    v = torch.rand((n, d), device=dev, dtype=torch.float32)
+    cent0 = v[torch.randperm(n, device=dev)[:k]].cpu().numpy().copy()
+    nassign = np.empty(k, np.int32)
+    f, i = C.POINTER(C.c_float), C.POINTER(C.c_int)
+    flags = KMEANS_INIT_USER | KMEANS_QUIET
+
+    def run(niter_, ptr):
+        c = cent0.copy()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        q = L.yb_kmeans_dev(d, n, k, niter_, ptr, flags, 1, 1, c.ctypes.data_as(f), None, None,
+                            nassign.ctypes.data_as(i), None, None)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t, q, c
+
+    run(3, v.data_ptr())                                     # warm-up: 3 iterations
+    L.yb_prof_enable(1)
+    L.yb_prof_ms(1, None, 1)
+    L.yb_launch_count(1)
+    tt, q, cent = run(niter, v.data_ptr())
+    launches = L.yb_launch_count(0)
+    ph = _phase_means(L, ((0, "center_and_convert"), (1, "tensor_pass"), (3, "rerank_k1"), (4, "exact_fallback"),
+                          (8, "update_sort_and_sums"), (9, "scale")))
+    L.yb_prof_ms(0, None, 1)
+    L.yb_prof_enable(0)
+    s_iter = tt / niter
+    pk = _peaks()
+    bf16, hbm = pk.get("bf16_tflops", 1590.0), pk.get("hbm_gbs", 6450.0)
+    operands = "fp16" if L.yb_last_knn_operands() == 2 else "tf32"
+    tpeak = bf16 if operands == "fp16" else bf16 / 2.0
+    kms = ph.get("tensor_pass", s_iter * 1e3)
+    flops = 2.0 * n * k * d
+    ubytes = 4.0 * n * d + 4.0 * n + 4.0 * k * d + 4.0 * k
+    ums = ph.get("update_sort_and_sums")
+    block = {
+        "metric": "k-means iter/s (10M x 128, k=65536)", "value": 1.0 / s_iter, "unit": "iter/s",
+        "ms_per_step": s_iter * 1e3, "steps": niter, "warmup": 3, "qerr": float(q),
+        "dtype": "f32 (%s tensor-core shortlist, exact f32 re-rank and sums)" % operands,
+        "config": {"workload": "k-means at scale: n=10M, d=128, k=65536, %d iterations (BASELINE configs[3]), one GPU" % niter,
+                   "init": "KMEANS_INIT_USER: rows of a seeded permutation", "phase_ms": ph,
+                   "uncertified_points_last_iteration": int(L.yb_last_knn_uncertified())},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "k_knn_tf32<EPI_NEAREST, %s> (assignment, k = 1 margin mode)" % operands,
+                     "achieved": flops / (kms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                     "frac": flops / (kms * 1e-3) / 1e12 / tpeak, "traffic": None, "kernel_ms": kms,
+                     "algorithmic_flops_per_launch": flops,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops" if pk else "fallback 1590 TF/s bf16"},
+    }
+    if ums:
+        block["roofline_update"] = {
+            "bound": "hbm", "kernel": "centroid update: id sort (k_rs_*) + k_segsum + k_combine + qerr",
+            "achieved": ubytes / (ums * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+            "frac": ubytes / (ums * 1e-3) / 1e9 / hbm, "traffic": None, "kernel_ms": ums,
+            "algorithmic_bytes_per_launch": ubytes,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if pk else "fallback 6450 GB/s"}
+
+    # ---- parity + CPU baseline: a slice of the points, teacher-forced against the same centroids
+    try:
+        from oracle import bindings as ob
+        cores = len(os.sched_getaffinity(0))
+        ns = 100_000
+        vs = v[:ns].contiguous()
+        ga = torch.empty(ns, device=dev, dtype=torch.int32)
+        gd = torch.empty(ns, device=dev, dtype=torch.float32)
+        cd = torch.from_numpy(cent0).to(dev)
+        sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        rc = L.yb_knn_l2(ns, k, d, 1, cd.data_ptr(), vs.data_ptr(), None, ga.data_ptr(), gd.data_ptr(), 0, sp)
+        assert rc == 0, L.yb_last_error()
+        sums = torch.empty((k, d), device=dev, dtype=torch.float32)
+        cnts = torch.empty(k, device=dev, dtype=torch.int32)
+        qe = torch.empty(1, device=dev, dtype=torch.float64)
+        rc = L.yb_kmeans_accumulate(d, ns, k, vs.data_ptr(), ga.data_ptr(), gd.data_ptr(), sums.data_ptr(),
+                                    cnts.data_ptr(), qe.data_ptr(), 0, sp)
+        assert rc == 0, L.yb_last_error()
+        torch.cuda.synchronize()
+        vs_h = vs.cpu().numpy()
+        t = time.perf_counter()
+        if ob.have_ref():
+            wa, wd = ob.ref_knn(cent0, vs_h, 1, nt=cores)
+            kind = "reference"
+        else:
+            wa, wd = ob.orc_knn(cent0, vs_h, 1, nt=cores)
+            kind = "port"
+        dt = time.perf_counter() - t
+        wa, wd = wa[:, 0], wd[:, 0]
+        a, dd = ga.cpu().numpy(), gd.cpu().numpy()
+        diff = a != wa
+        own_ok = True
+        for j in np.nonzero(diff)[0]:
+            own = ((cent0[a[j]].astype(np.float64) - vs_h[j].astype(np.float64)) ** 2).sum()
+            if abs(own - float(wd[j])) > 1e-5 * abs(float(wd[j])) + 2e-6 * float((vs_h[j].astype(np.float64) ** 2).sum()):
+                own_ok = False
+        rel = np.abs(dd.astype(np.float64) - wd) / np.maximum(np.abs(wd), 1e-30)
+        # centroid sums of the slice under the REFERENCE's assignment, in float64
+        ws = np.zeros((k, d), np.float64)
+        np.add.at(ws, wa, vs_h.astype(np.float64))
+        wc = np.bincount(wa, minlength=k)
+        gs, gc = sums.cpu().numpy(), cnts.cpu().numpy()
+        same_rows = (gc == wc) & (gc > 0)
+        if diff.any():  # rows touched by a flipped tie differ legitimately
+            touched = np.zeros(k, bool)
+            touched[a[diff]] = True
+            touched[wa[diff]] = True
+            same_rows &= ~touched
+        cerr = np.abs(gs[same_rows] / gc[same_rows, None] - ws[same_rows] / wc[same_rows, None]).max() if same_rows.any() else 0.0
+        block["parity"] = {"config": "C4: teacher-forced step, %d-point slice x 65536 centroids, d=128" % ns,
+                           "n_points": ns, "checked_against": "%s knn_full_thread(k=1) + float64 sums" % kind,
+                           "assign_identical": int((~diff).sum()), "assign_differing": int(diff.sum()),
+                           "assign_equal_outside_ties": bool(own_ok), "max_rel_dis": float(rel.max()),
+                           "distances_bit_identical": bool(np.array_equal(dd, wd)),
+                           "max_abs_centroid_err_vs_float64": float(cerr),
+                           "ok": bool(own_ok and rel.max() <= 1e-5 and cerr <= 1e-4)}
+        cpu_iter_s = dt * (n / ns)
+        block["cpu_baseline"] = {"value": 1.0 / cpu_iter_s, "unit": "iter/s", "cores": cores, "kind": kind,
+                                 "sample": "assignment (knn_full_thread, k=1: >99%% of an iteration) of %d of the 10M points "
+                                           "against all 65536 centroids on %d threads: %.1f s, scaled x%d to one iteration"
+                                           % (ns, cores, dt, n // ns)}
+        # BASELINE configs[0], the reference's own CPU-runnable case, in full
+        v1 = np.random.RandomState(1234).random_sample((100000, 128)).astype(np.float32)
+        t = time.perf_counter()
+        if ob.have_ref():
+            ob.ref_kmeans(v1, 256, 20, ob.KMEANS_QUIET | cores, 1234)
+        else:
+            ob.orc_kmeans(v1, 256, 20, ob.KMEANS_QUIET | cores, 1234)
+        dt1 = time.perf_counter() - t
+        v1d = torch.from_numpy(v1).to(dev)
+        c1 = np.zeros((256, 128), np.float32)
+        torch.cuda.synchronize()
+        best1 = 1e9
+        for _ in range(3):
+            t = time.perf_counter()
+            L.yb_kmeans_dev(128, 100000, 256, 20, v1d.data_ptr(), KMEANS_QUIET, 1234, 1, c1.ctypes.data_as(f),
+                            None, None, None, None, None)
+            torch.cuda.synchronize()
+            best1 = min(best1, time.perf_counter() - t)
+        block["config0_kmeans_100k_k256_20it"] = {"cpu_iter_per_s": 20.0 / dt1, "cpu_kind": kind, "cpu_cores": cores,
+                                                  "gpu_iter_per_s": 20.0 / best1}
+        del vs, ga, gd, cd, sums, cnts, v1d
+    except Exception as e:
+        block["cpu_baseline_error"] = str(e)
+
+    # ---- e2e: the drop-in kmeans() on pinned host points
+    try:
+        vh = torch.empty((n, d), dtype=torch.float32).pin_memory()
+        vh.copy_(v)
+        torch.cuda.synchronize()
+
+        def e2e_call(niter_):
+            c = cent0.copy()
+            t = time.perf_counter()
+            L.kmeans(d, n, k, niter_, C.cast(vh.data_ptr(), f), flags, 1, 1, c.ctypes.data_as(f), None, None,
+                     nassign.ctypes.data_as(i))
+            return time.perf_counter() - t, c
+
+        e2e_call(1)
+        te, ce = e2e_call(niter)
+        block["e2e"] = {"value": niter / te, "unit": "iter/s", "ms_per_step": te / niter * 1e3,
+                        "h2d_bytes_per_step": int((n * d * 4 + k * d * 4) / niter),
+                        "d2h_bytes_per_step": int((k * d * 4 + k * 4) / niter),
+                        "call": "kmeans() on pinned host points, %d iterations per call: the 5.12 GB of points "
+                                "cross PCIe once per call" % niter,
+                        "equals_resident_run": bool(np.array_equal(ce, cent))}
+        del vh
+    except Exception as e:
+        block["e2e_error"] = str(e)
+    del v
+    torch.cuda.empty_cache()
+    return block
 
 
 def measure_extras_sharded(torch, dist, ydist, L, dev, rank, world):
@@ -590,6 +830,34 @@ def run_ours(args):
            "h2d_bytes_per_step": int(base_h.nbytes + query_h.nbytes),
            "d2h_bytes_per_step": int(NQ * K * 8), "ms_per_step": t_e2e * 1e3}
 
+    # ---- results for the parity checks (outside every timed region)
+    L.yb_set_knn_engine(-1)
+    loc_i = torch.empty((NQ, K), dtype=torch.int32, device=dev)
+    loc_d = torch.empty((NQ, K), dtype=torch.float32, device=dev)
+    searcher._local_into(query, loc_i, loc_d, 0)          # this rank's shard alone, local ids
+    torch.cuda.synchronize()
+    res_idx, res_dis = loc_i.cpu().numpy(), loc_d.cpu().numpy()
+    parity_sharded = None
+    if world > 1:
+        # the merged answer of the sharded search == ONE search of the concatenated shards, for the
+        # first 256 queries (every rank gathers all shards over NCCL and checks; rank 0 reports)
+        nchk = 256
+        mi, md = searcher.search(query)
+        allb = torch.empty((world, NB, D), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(allb.view(-1), base.view(-1))
+        one_i = torch.empty((nchk, K), dtype=torch.int32, device=dev)
+        one_d = torch.empty((nchk, K), dtype=torch.float32, device=dev)
+        rc = L.yb_knn_l2(nchk, world * NB, D, K, allb.data_ptr(), query.data_ptr(), None, one_i.data_ptr(),
+                         one_d.data_ptr(), 0, ydist._stream_ptr(torch))
+        torch.cuda.synchronize()
+        ok = rc == 0 and bool(torch.equal(one_i, mi[:nchk]) and torch.equal(one_d, md[:nchk]))
+        flag = torch.tensor([1 if ok else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity_sharded = {"config": "%d shards of 1M x 128 merged vs one search of the %dM-row database" % (world, world),
+                          "n_queries": nchk, "ids_and_distances_bit_identical_on_every_rank": bool(flag.item())}
+        del allb
+        torch.cuda.empty_cache()
+
     extras_sharded = None
     if world > 1 and not args.no_extras:
         try:
@@ -623,11 +891,15 @@ def run_ours(args):
     if "tf32_shortlist" in phase_ms:
         kms = phase_ms["tf32_shortlist"]
         ach = 2.0 * NQ * NB * D / (kms * 1e-3) / 1e12
-        traffic = None
-        try:  # DRAM bytes of this kernel from the committed ncu --set full capture
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_knn_tf32_traffic.json")))["dram_bytes_per_launch"]
-        except Exception:
-            pass
+        traffic = traffic_src = None
+        for name in ("r2_knn_tf32_traffic.json", "r1_knn_tf32_traffic.json"):
+            try:  # DRAM bytes of this kernel from the committed ncu --set full capture (not re-measured here)
+                tj = json.load(open(os.path.join(ROOT, "profiles", name)))
+                traffic = tj["dram_bytes_per_launch"]
+                traffic_src = "profiles/%s (ncu --set full capture at commit %s)" % (name, tj.get("commit", "see file"))
+                break
+            except Exception:
+                pass
         roof = {"bound": "tensor",
                 "kernel": "k_knn_tf32<EPI_LISTS, %s> (full pass; the sampling passes are in phase_ms)" % operands,
                 "operands": operands,
@@ -636,7 +908,7 @@ def run_ours(args):
                          "busy; the pass is paced by the fused top-k epilogue and the operand feed, not by the MMA "
                          "rate -- decomposition in DESIGN.md 5.1 and profiles/README.md"),
                 "achieved": ach, "peak": peak,
-                "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "kernel_ms": kms, "peak_source": peak_src,
                 "frac_of_bf16_peak": ach / bf16_peak,
                 "cublas_tf32_tflops_this_run": tf32_meas,
@@ -649,11 +921,25 @@ def run_ours(args):
                 "frac": 2.0 * NQ * NB * D / (kms * 1e-3) / 1e12 / peak, "traffic": None,
                 "peak_source": peak_src}
 
-    cpu = cpu_reference_rate(base_h, query_h)
+    cpu, (n_ref, widx, wdis) = cpu_reference_rate(base_h, query_h)
+    # parity at the BASELINE size: the reference's answer for the sampled queries against the GPU's
+    # (rank 0's shard; for N > 1 the local search of that shard, before the merge)
+    parity = knn_parity(res_idx, res_dis, widx, wdis, base_h, query_h,
+                        "C2: 1M x 128 database, k=100 (BASELINE configs[1])")
 
-    extras = extras_sharded
+    kmeans_block = hamming_block = None
     if world == 1 and not args.no_extras:
-        extras = measure_extras(torch, L, dev)
+        try:
+            hamming_block = measure_hamming(torch, L, dev)
+        except Exception as e:  # the side blocks never break the headline line
+            hamming_block = {"error": str(e)}
+        try:
+            kmeans_block = measure_kmeans(torch, L, dev, args.kmeans_iters)
+        except Exception as e:
+            kmeans_block = {"error": str(e)}
+    elif extras_sharded:
+        kmeans_block = extras_sharded.get("kmeans_10Mx128_k65536_sharded") or {"error": extras_sharded.get("kmeans_error")}
+        hamming_block = extras_sharded.get("hamming_knn_10Mx64bit_10kq_k100_sharded") or {"error": extras_sharded.get("hamming_error")}
 
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -673,7 +959,8 @@ def run_ours(args):
             "shard_phase_ms_rank0": shard_phase_ms,
         },
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": roof, "cpu_baseline": cpu, "extras": extras,
+        "roofline": roof, "cpu_baseline": cpu, "parity": parity, "parity_sharded": parity_sharded,
+        "kmeans": kmeans_block, "hamming": hamming_block,
     }))
     if world > 1:
         dist.destroy_process_group()
@@ -686,7 +973,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true",
-                    help="skip the k-means / Hamming side measurements (N=1 only)")
+                    help="skip the k-means / Hamming blocks")
+    ap.add_argument("--kmeans-iters", type=int, default=10,
+                    help="iterations of the k-means block (BASELINE configs[3] names 10)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

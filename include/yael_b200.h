@@ -101,6 +101,12 @@ int yb_cross_distances_alt(int distance_type, int d, int na, int nb, const float
  * strict '<' from (-1, 1e30), lowest id on ties. */
 int yb_knn_l2(int nq, int nb, int d, int k, const float *base, const float *query,
               const float *b_weights, int *assign, float *dis, int id_offset, yb_stream_t s);
+/* knn_full for the other distance types (1 L1, 3/4 chi2, 5 histogram intersection, 6/16 dot
+ * product, 2/12 L2 with double / FP32 accumulation): compute_cross_distances_alt
+ * (yael/nn.c:280-350) in query chunks + the per-base weights of yael/nn.c:497-500 + the per-row
+ * select; k == 1 follows nn_single_full (start (-1, 1e30f), strict '<') for every type. */
+int yb_knn_alt(int distance_type, int nq, int nb, int d, int k, const float *base,
+               const float *query, const float *b_weights, int *assign, float *dis, yb_stream_t s);
 /* yb_knn_l2 for a database that is still in HOST memory (what knn_full() receives,
  * yael/nn.c:451): the host->device transfer is overlapped with the scan -- the sample tiles the
  * admission thresholds are computed from travel first, the rest follows in large 2-D copies and

@@ -35,6 +35,15 @@ def build(quiet=True):
         raise RuntimeError("oracle build failed:\n" + out.stdout + out.stderr)
     if not quiet:
         print(out.stdout)
+    # the reference's own CLIs (progs/knn.c, progs/kmeans.c), unmodified, linked against the
+    # PRODUCT library: the drop-in check of tests/test_gpu_cli_and_edges.py.  Needs the reference
+    # tree (this container) and the built product; the binaries travel to the GPU box.
+    ref_root = os.environ.get("YAEL_REF", "/root/reference")
+    product = os.path.join(os.path.dirname(HERE), "yael_b200", "libyael_b200.so")
+    if os.path.exists(os.path.join(ref_root, "progs", "knn.c")) and os.path.exists(product):
+        out = subprocess.run(["make", "-C", HERE, "progs"], capture_output=True, text=True)
+        if out.returncode != 0:
+            raise RuntimeError("oracle progs build failed:\n" + out.stdout + out.stderr)
 
 
 def fp(a):
@@ -249,3 +258,47 @@ def ref_k_min(val, k):
     idx = np.empty(k, np.int32)
     ref().fvec_k_min(fp(val), val.shape[0], ip(idx), k)
     return idx
+
+
+def ref_nn_hamming_blocked(base, query, k, block=1 << 20, threads=None):
+    """Hamming k-NN the way SURVEY.md 8(c)-4 defines the oracle for the NEW nn_hamming: the
+    reference's compute_hamming (yael/hamming.c:177-219; the compiled reference when present, else
+    the restatement) over database blocks -- one block per host thread at a time -- followed by a
+    stable (distance, id) selection.  Returns (idx[nq][k], dis[nq][k], kind)."""
+    from concurrent.futures import ThreadPoolExecutor
+    base = np.ascontiguousarray(base, np.uint8)
+    query = np.ascontiguousarray(query, np.uint8)
+    nq, nc = query.shape
+    nb = base.shape[0]
+    assert k <= nb
+    use_ref = have_ref()
+    fn = ref().compute_hamming if use_ref else oracle().orc_compute_hamming
+    threads = threads or len(os.sched_getaffinity(0))
+    starts = list(range(0, nb, block))
+    # upper bound on every query's k-th distance from the first block (exact selection there)
+    b0 = base[:min(nb, max(block, k))]
+    d0 = np.empty((b0.shape[0], nq), np.uint16)
+    fn(u16p(d0), u8p(query), u8p(b0), nq, b0.shape[0], nc)
+    bound = np.partition(d0, k - 1, axis=0)[k - 1]          # [nq]
+
+    def scan(s):
+        blk = base[s:s + block]
+        d = np.empty((blk.shape[0], nq), np.uint16)
+        fn(u16p(d), u8p(query), u8p(blk), nq, blk.shape[0], nc)   # dis[j * nq + i] = ham(q_i, b_j)
+        j, i = np.nonzero(d <= bound[None, :])
+        return i.astype(np.int32), (j + s).astype(np.int64), d[j, i]
+
+    with ThreadPoolExecutor(threads) as ex:
+        parts = list(ex.map(scan, starts))
+    qi = np.concatenate([p[0] for p in parts])
+    bj = np.concatenate([p[1] for p in parts])
+    dv = np.concatenate([p[2] for p in parts])
+    order = np.lexsort((bj, dv, qi))                       # by query, then (distance, id)
+    qi, bj, dv = qi[order], bj[order], dv[order]
+    first = np.searchsorted(qi, np.arange(nq))
+    idx = np.empty((nq, k), np.int32)
+    dis = np.empty((nq, k), np.uint16)
+    for q in range(nq):
+        idx[q] = bj[first[q]:first[q] + k]
+        dis[q] = dv[first[q]:first[q] + k]
+    return idx, dis, ("reference" if use_ref else "port")

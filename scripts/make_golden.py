@@ -20,7 +20,12 @@ assert ob.have_ref(), "build oracle/_ref first (make -C oracle)"
 L = ob.ref()
 
 
+ONLY = set(sys.argv[1:])  # fixture names to (re)write; none given = all
+
+
 def save(name, **kw):
+    if ONLY and name not in ONLY:
+        return
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **kw)
     print(name, {k: getattr(v, "shape", v) for k, v in kw.items()})
 
@@ -115,3 +120,20 @@ for nc, ht in ((4, 10), (8, 24), (16, 52), (5, 14)):
     cout["db%d" % nc], cout["ht%d" % nc] = db, np.int32(ht)
     cout["idx%d" % nc], cout["ham%d" % nc] = cidx, cham
 save("hamming_crossmatch", **cout)
+
+# 10. knn_full with the other distance types and per-base weights (yael/nn.c:280-350, 497-500),
+#     k = 1 (nn_single_full, yael/nn.c:383-446) and k = 5; positive data so chi2 is well defined
+ra = np.random.RandomState(10)
+ab = (ra.random_sample((300, 12)) + 0.05).astype(np.float32)
+aq = (ra.random_sample((40, 12)) + 0.05).astype(np.float32)
+aw = (0.5 + 1.5 * ra.random_sample(300)).astype(np.float32)
+aout = {"base": ab, "query": aq, "weights": aw}
+for t in (1, 2, 3, 4, 5, 6, 16):
+    for k in (1, 5):
+        for wname, w in (("", None), ("w", aw)):
+            i_ = np.empty((40, k), np.int32)
+            d_ = np.empty((40, k), np.float32)
+            L.knn_full_thread(t, 40, 300, 12, k, ob.fp(ab), ob.fp(aq), ob.fp(w) if w is not None else None,
+                              ob.ip(i_), ob.fp(d_), 2)
+            aout["idx_t%d_k%d%s" % (t, k, wname)], aout["dis_t%d_k%d%s" % (t, k, wname)] = i_, d_
+save("knn_alt_weighted", **aout)

@@ -1,4 +1,5 @@
-"""Tiny device-memory helper for tests that call the yb_ device-level C ABI directly."""
+"""Tiny device-memory helper for tests that call the yb_ device-level C ABI directly, and the
+k-NN comparison rule shared by the GPU parity tests."""
 import ctypes as C
 
 import numpy as np
@@ -33,3 +34,24 @@ class DevArray:
         if self.ptr:
             yael_b200.lib().yb_free(self.ptr)
             self.ptr = None
+
+
+def check_knn(idx, dis, widx, wdis, b, q, rtol=1e-5):
+    """North-star tolerance: distances within 1e-5 relative of the oracle's, ids identical except
+    for ties inside that tolerance.  A differing id is accepted only if ITS OWN distance to the
+    query, recomputed here in float64 from the rows, is within the tolerance of the oracle's
+    distance at that rank (a wrong id carrying a right distance does not pass), and no id may
+    appear twice in a result list."""
+    valid = widx >= 0
+    assert np.array_equal(valid, idx >= 0)
+    np.testing.assert_allclose(dis[valid], wdis[valid], rtol=rtol, atol=1e-6)
+    diff = (idx != widx) & valid
+    if diff.any():
+        b64 = b.astype(np.float64)
+        for qi, j in zip(*np.nonzero(diff)):
+            own = ((b64[idx[qi, j]] - q[qi].astype(np.float64)) ** 2).sum()
+            tol = rtol * max(abs(float(wdis[qi, j])), 1e-6) + 2e-6 * float((q[qi].astype(np.float64) ** 2).sum())
+            assert abs(own - float(wdis[qi, j])) <= tol, (qi, j, idx[qi, j], widx[qi, j], own, wdis[qi, j])
+        for qi in np.unique(np.nonzero(diff)[0]):
+            row = idx[qi][idx[qi] >= 0]
+            assert len(set(row.tolist())) == len(row), "duplicate id in the result list of query %d" % qi

@@ -140,3 +140,50 @@ def test_python_frontend_argument_checks():
         ynumpy._check_row_float32(np.zeros((2, 2), np.float64))
     with pytest.raises(TypeError):
         ynumpy._check_row_float32(np.zeros((4, 4), np.float32)[:, ::2])
+
+
+def test_host_only_entry_points_hamming_and_recompute_exact_dists(ob):
+    """hamming() (yael/hamming.c:66-78) and knn_recompute_exact_dists() (yael/nn.c:583-600) stay on
+    the host (a scalar popcount; pointer chasing over a partially loaded base): compare with the
+    oracle / the compiled reference and with numpy."""
+    import yael_b200
+    L = yael_b200.lib()
+    u8 = C.POINTER(C.c_uint8)
+    r = np.random.RandomState(3)
+    for nc in (4, 8, 16, 5, 24):
+        a = r.randint(0, 256, nc).astype(np.uint8)
+        b = r.randint(0, 256, nc).astype(np.uint8)
+        want = int(np.unpackbits(a ^ b).sum())
+        assert L.hamming(a.ctypes.data_as(u8), b.ctypes.data_as(u8), nc) == want
+        assert ob.oracle().orc_hamming(ob.u8p(a), ob.u8p(b), nc) == want
+    # knn_recompute_exact_dists: base rows [label0, label0 + nb) are loaded; per query, entries
+    # kp[q].. of the (label-sorted) shortlist are recomputed until a label falls outside
+    f, i = C.POINTER(C.c_float), C.POINTER(C.c_int)
+    nq, nb, d, k, label0 = 7, 50, 12, 9, 100
+    b = r.random_sample((nb, d)).astype(np.float32)
+    v = r.random_sample((nq, d)).astype(np.float32)
+    idx = np.sort(r.randint(label0, label0 + 2 * nb, (nq, k)), axis=1).astype(np.int32)
+    kp0 = np.array([0, 2, 0, 1, 0, 0, 3], np.int32)
+
+    def run(fn):
+        kp = kp0.copy()
+        dis = np.full((nq, k), -1.0, np.float32)
+        fn(nq, nb, d, k, b.ctypes.data_as(f), v.ctypes.data_as(f), label0, kp.ctypes.data_as(i),
+           idx.ctypes.data_as(i), dis.ctypes.data_as(f))
+        return kp, dis
+
+    kp, dis = run(L.knn_recompute_exact_dists)
+    for q in range(nq):
+        j = int(kp0[q])
+        while j < k and idx[q, j] - label0 < nb:
+            row = b[idx[q, j] - label0].astype(np.float64)
+            assert dis[q, j] == np.float32(((row - v[q].astype(np.float64)) ** 2).sum()) or \
+                abs(dis[q, j] - ((row - v[q]) ** 2).sum()) < 1e-5
+            j += 1
+        assert kp[q] == j and (dis[q, j:] == -1.0).all() and (dis[q, :kp0[q]] == -1.0).all()
+    if ob.have_ref():
+        R = ob.ref()
+        R.knn_recompute_exact_dists.argtypes = [C.c_int] * 4 + [f, f, C.c_int, i, i, f]
+        R.knn_recompute_exact_dists.restype = None
+        rkp, rdis = run(R.knn_recompute_exact_dists)
+        assert np.array_equal(kp, rkp) and np.array_equal(dis, rdis)

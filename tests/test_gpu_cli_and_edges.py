@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 import yael_b200
+from devmem import check_knn
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -105,9 +106,7 @@ def test_tensor_engine_any_dimension(yn, ob, d):
     finally:
         L.yb_set_knn_engine(-1)
     widx, wdis = ob.orc_knn(b, q, 10, canonical=True)
-    np.testing.assert_allclose(dis, wdis, rtol=1e-5, atol=1e-7)
-    mism = idx != widx
-    assert np.all(np.abs(dis[mism] - wdis[mism]) <= 1e-5 * np.abs(wdis[mism]) + 1e-7)
+    check_knn(idx, dis, widx, wdis, b, q)
 
 
 def test_large_k_and_high_dimension_use_exact_engine(yn, ob):

@@ -128,6 +128,33 @@ def test_crossmatch_hamming_golden(yn):
         assert np.array_equal(pairs, g["idx%d" % nc]) and np.array_equal(scores, g["ham%d" % nc])
 
 
+@pytest.mark.parametrize("t", [1, 2, 3, 4, 5, 6, 16])
+def test_knn_alt_types_and_weights_golden(yn, t):
+    """knn_full with every distance type of compute_cross_distances_alt (yael/nn.c:280-350), with
+    and without the per-base weights (yael/nn.c:497-500), k = 1 (nn_single_full) and k = 5, against
+    the compiled reference (scripts/make_golden.py section 10)."""
+    g = gold("knn_alt_weighted")
+    b, q, w = g["base"], g["query"], g["weights"]
+    for k in (1, 5):
+        for wname, ww in (("", None), ("w", w)):
+            if ww is None:
+                idx, dis = yn.knn(q, b, k, distance_type=t)
+            else:
+                idx, dis = yn.knn_weighted(q, b, ww, k, distance_type=t)
+            widx, wdis = g["idx_t%d_k%d%s" % (t, k, wname)], g["dis_t%d_k%d%s" % (t, k, wname)]
+            assert np.array_equal(idx, widx), (t, k, wname)
+            if t == 16:   # sgemm in the reference: summation order inside BLAS edge tiles
+                np.testing.assert_allclose(dis, wdis, rtol=2e-6)
+            else:
+                assert np.array_equal(dis, wdis), (t, k, wname)
+
+
+def test_kmeans_l1_is_refused_loudly(yn):
+    v = np.random.RandomState(0).random_sample((100, 4)).astype(np.float32)
+    with pytest.raises(NotImplementedError):
+        yn.kmeans(v, 4, distance_type=1, verbose=False)
+
+
 def test_knn_merge_equals_unsharded(yn):
     # the multi-GPU exchange step on one device: G shard results -> merged == single search
     L = yael_b200.lib()
@@ -249,6 +276,35 @@ def test_drop_in_wrappers(yn, ob):
     L.compute_cross_distances_nonpacked(16, 500, 40, b.ctypes.data_as(f), 16, q.ctypes.data_as(f), 16,
                                         outp.ctypes.data_as(f), 600)
     assert np.array_equal(outp[:, :500], ob.orc_cross(b, q)) and (outp[:, 500:] == -7.0).all()
+
+
+def test_drop_in_thin_wrappers(ob):
+    """knn / knn_thread / nn_thread / compute_cross_distances_thread (yael/nn.c:624-632, 704-726,
+    777-792): thin calls into knn_full / compute_cross_distances; knn and knn_thread return a
+    malloc'd block the caller frees."""
+    L = yael_b200.lib()
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    f, i = C.POINTER(C.c_float), C.POINTER(C.c_int)
+    r = np.random.RandomState(15)
+    b = r.random_sample((700, 24)).astype(np.float32)
+    q = r.random_sample((33, 24)).astype(np.float32)
+    widx, wdis = ob.orc_knn(b, q, 6, canonical=True)
+    for name, extra in (("knn", ()), ("knn_thread", (3,))):
+        vw = np.empty((33, 6), np.int32)
+        p = getattr(L, name)(33, 700, 24, 6, b.ctypes.data_as(f), q.ctypes.data_as(f), vw.ctypes.data_as(i), *extra)
+        got = np.ctypeslib.as_array(p, shape=(33, 6)).copy()
+        libc.free(C.cast(p, C.c_void_p))
+        assert np.array_equal(vw, widx) and np.array_equal(got, wdis), name
+    w1i, w1d = ob.orc_knn(b, q, 1)
+    vw = np.empty(33, np.int32)
+    tot = L.nn_thread(33, 700, 24, b.ctypes.data_as(f), q.ctypes.data_as(f), vw.ctypes.data_as(i), 5)
+    assert np.array_equal(vw, w1i[:, 0])
+    assert tot == pytest.approx(float(w1d.astype(np.float64).sum()), rel=1e-6)
+    out = np.empty((33, 700), np.float32)
+    L.compute_cross_distances_thread(24, 700, 33, b.ctypes.data_as(f), q.ctypes.data_as(f),
+                                     out.ctypes.data_as(f), 4)
+    assert np.array_equal(out, ob.orc_cross(b, q))
 
 
 def test_device_pointers_accepted_by_drop_in_api(ob):

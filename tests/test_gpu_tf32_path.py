@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import yael_b200
-from devmem import DevArray
+from devmem import DevArray, check_knn
 
 pytestmark = pytest.mark.gpu
 
@@ -85,12 +85,12 @@ def test_knn_f16_out_of_range_value_falls_back_to_tf32(yn, ob):
         idx, dis = yn.knn(q, b, k)
         assert L.yb_last_knn_engine() == 1 and L.yb_last_knn_operands() == 2
         widx, wdis = ob.orc_knn(b, q, k, ob.DOT_F32_SEQ, canonical=True)
-        check_knn(idx, dis, widx, wdis)
+        check_knn(idx, dis, widx, wdis, b, q)
         b[500] = 1e3  # rows 256..780 are not in the sample: 1e3 >> 8 x the sampled maximum
         idx, dis = yn.knn(q, b, k)
         assert L.yb_last_knn_engine() == 1 and L.yb_last_knn_operands() == 0
         widx, wdis = ob.orc_knn(b, q, k, ob.DOT_F32_SEQ, canonical=True)
-        check_knn(idx, dis, widx, wdis)
+        check_knn(idx, dis, widx, wdis, b, q)
     finally:
         L.yb_set_knn_engine(-1)
 
@@ -112,7 +112,7 @@ def test_knn_too_tight_thresholds_are_retried_and_still_exact(yn, ob, monkeypatc
             idx, dis = yn.knn(q, b, k)
             assert L.yb_last_knn_engine() == 1
             assert L.yb_last_knn_uncertified() > 0      # the scenario really happened
-            check_knn(idx, dis, widx, wdis)
+            check_knn(idx, dis, widx, wdis, b, q)
     finally:
         L.yb_set_knn_engine(-1)
 
@@ -131,7 +131,7 @@ def test_knn_both_operand_kinds_match_oracle(yn, ob, operands, monkeypatch):
             assert L.yb_last_knn_engine() == 1
             assert L.yb_last_knn_operands() == (0 if operands == "tf32" else 2)
             widx, wdis = ob.orc_knn(b, q, k, ob.DOT_F32_SEQ, canonical=True)
-            check_knn(idx, dis, widx, wdis)
+            check_knn(idx, dis, widx, wdis, b, q)
     finally:
         L.yb_set_knn_engine(-1)
 
@@ -144,20 +144,6 @@ def tf32_engine():
     L.yb_set_knn_engine(-1)
 
 
-def check_knn(idx, dis, widx, wdis, rtol=1e-5):
-    # distances within tolerance everywhere
-    valid = widx >= 0
-    assert np.array_equal(valid, idx >= 0)
-    np.testing.assert_allclose(dis[valid], wdis[valid], rtol=rtol, atol=1e-6)
-    # ids identical except inside ties
-    diff = (idx != widx) & valid
-    if diff.any():
-        qs, js = np.nonzero(diff)
-        for q, j in zip(qs, js):
-            # the id we returned must be a legitimate member at that distance
-            assert abs(dis[q, j] - wdis[q, j]) <= rtol * max(abs(wdis[q, j]), 1e-6)
-
-
 @pytest.mark.parametrize("nq,nb,d,k", [(256, 20000, 128, 10), (100, 5000, 128, 100), (1000, 30000, 96, 1),
                                         (130, 3000, 64, 5), (64, 100000, 32, 50), (700, 2500, 128, 100)])
 def test_knn_tf32_engine_matches_oracle(yn, ob, tf32_engine, nq, nb, d, k):
@@ -167,7 +153,7 @@ def test_knn_tf32_engine_matches_oracle(yn, ob, tf32_engine, nq, nb, d, k):
     idx, dis = yn.knn(q, b, k)
     assert tf32_engine.yb_last_knn_engine() == 1
     widx, wdis = ob.orc_knn(b, q, k, ob.DOT_F32_SEQ, canonical=True)
-    check_knn(idx, dis, widx, wdis)
+    check_knn(idx, dis, widx, wdis, b, q)
     # uniform data never needs the exact fallback in bulk
     assert tf32_engine.yb_last_knn_uncertified() <= nq // 20
 
@@ -203,7 +189,7 @@ def test_knn_tf32_nan_and_padding(yn, ob, tf32_engine):
     q = r.rand(150, 32).astype(np.float32)
     idx, dis = yn.knn(q, b, 20)
     widx, wdis = ob.orc_knn(b, q, 20, canonical=True)
-    check_knn(idx, dis, widx, wdis)
+    check_knn(idx, dis, widx, wdis, b, q)
     assert not np.isin(idx, np.arange(5, 3000, 7)).any()
 
 
@@ -268,9 +254,74 @@ def test_knn_host_database_streamed_sorted_rows(yn, ob, tf32_engine):
     idx, dis = yn.knn(q, b, k)
     n_streamed = tf32_engine.yb_last_knn_uncertified()
     widx, wdis = ob.orc_knn(b, q, k, canonical=True)
-    check_knn(idx, dis, widx, wdis)
+    check_knn(idx, dis, widx, wdis, b, q)
     ridx, rdis = _resident_knn(tf32_engine, b, q, k)
     assert np.array_equal(dis, rdis) and np.array_equal(idx, ridx)
     # tight clusters defeat the TF32 certificate for many queries in BOTH paths (they are then
     # answered by the exact engine); feeding from the host must not make that worse
     assert n_streamed <= tf32_engine.yb_last_knn_uncertified() + 5
+
+
+# ---------------------------------------------------------------- queries at the centring vector
+def _thin_shell(r, nb, d, center, radius, ulps):
+    """Rows on a thin shell around `center`: |b - center|^2 = radius^2 (1 + j 2^-22), j < ulps, so
+    their exact distances to the centre are a few FP32 ulps apart."""
+    u = r.randn(nb, d)
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    scale = radius * np.sqrt(1.0 + r.randint(0, ulps, nb) * 2.0 ** -22)
+    return (center[None, :] + u * scale[:, None]).astype(np.float32)
+
+
+@pytest.mark.parametrize("k", [1, 10])
+def test_knn_queries_at_and_near_the_column_mean(yn, ob, tf32_engine, k):
+    """The Cauchy-Schwarz part of the tensor-score error bound is proportional to |q - mu| and
+    vanishes for a query AT the centring vector, while the FP32 roundings of |b - mu|^2 and of the
+    accumulator do not: the certificate / the k = 1 margin carry an absolute term for them.  Rows on
+    a thin shell around the mean (distances 1-4 ulp apart) must therefore fail the certificate and be
+    answered by the exact engine -- never a wrong id."""
+    r = rs(31 + k)
+    nb, d = 30000, 64                       # <= 32768 rows: the device's mean is over all of them
+    center = (r.rand(d) * 3 + 1).astype(np.float64)
+    b = _thin_shell(r, nb, d, center, 2.0, 5)
+    mu = b.astype(np.float64).mean(0)
+    q = np.stack([mu, mu + 1e-6 * r.randn(d), mu * (1 + 1e-7), mu + 1e-4 * r.randn(d),
+                  mu + 1e-2 * r.randn(d)] + [b[i] * 0.5 + mu * 0.5 for i in range(11)]).astype(np.float32)
+    idx, dis = yn.knn(q, b, k)
+    assert tf32_engine.yb_last_knn_engine() == 1
+    widx, wdis = ob.orc_knn(b, q, k, canonical=True)
+    assert np.array_equal(dis, wdis)
+    assert np.array_equal(idx, widx)
+    # the near-mean queries cannot be certified on the tensor path: they went to the exact engine
+    assert tf32_engine.yb_last_knn_uncertified() >= 3
+
+
+def test_knn_query_at_the_mean_with_separated_rows(yn, ob, tf32_engine):
+    # same query positions, but rows at well separated radii: the tensor path certifies them
+    r = rs(77)
+    nb, d, k = 30000, 64, 10
+    center = (r.rand(d) * 3 + 1).astype(np.float64)
+    u = r.randn(nb, d)
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    b = (center[None, :] + u * (0.5 + 2.0 * r.rand(nb))[:, None]).astype(np.float32)
+    mu = b.astype(np.float64).mean(0)
+    q = np.stack([mu, mu + 1e-6 * r.randn(d), mu + 1e-3 * r.randn(d)]).astype(np.float32)
+    idx, dis = yn.knn(q, b, k)
+    widx, wdis = ob.orc_knn(b, q, k, canonical=True)
+    assert np.array_equal(dis, wdis) and np.array_equal(idx, widx)
+
+
+def test_kmeans_points_at_the_centroid_mean(yn, ob, tf32_engine):
+    """k-means assignment (k = 1 margin mode): points at / near the mean of the centroids, centroids
+    on a thin shell around it.  The margin must not collapse with |q - mu|."""
+    r = rs(5)
+    k, d, n = 512, 32, 40000
+    center = (r.rand(d) * 2).astype(np.float64)
+    c0 = _thin_shell(r, k, d, center, 1.5, 5)
+    mu = c0.astype(np.float64).mean(0)
+    v = np.concatenate([np.tile(mu, (2000, 1)), mu + 1e-6 * r.randn(2000, d), mu + 1e-3 * r.randn(6000, d),
+                        c0[r.randint(0, k, n - 10000)] + 0.05 * r.randn(n - 10000, d)]).astype(np.float32)
+    cent, qerr, dis, assign, nassign = yn.kmeans(v, k, niter=1, verbose=False, init=c0, output="all")
+    _, wc, wa, wd, wn = ob.orc_kmeans_step(v, c0)
+    assert np.array_equal(dis, wd)
+    assert np.array_equal(assign, wa)
+    assert np.array_equal(nassign, wn)

@@ -142,6 +142,7 @@ DEVICE = {
     "yb_distances_1": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp]),
     "yb_cross_distances_alt": (C.c_int, [C.c_int] * 4 + [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp]),
     "yb_knn_l2": (C.c_int, [C.c_int] * 4 + [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "yb_knn_alt": (C.c_int, [C.c_int] * 5 + [_vp, _vp, _vp, _vp, _vp, _vp]),
     "yb_knn_l2_hostbase": (C.c_int, [C.c_int] * 4 + [_vp] * 5 + [C.c_int, _vp]),
     "yb_knn_merge": (C.c_int, [C.c_int] * 3 + [_vp, _vp, _vp, _vp, _vp]),
     "yb_knn_merge_strided": (C.c_int, [C.c_int] * 3 + [_vp, _vp, C.c_long, _vp, _vp, _vp]),

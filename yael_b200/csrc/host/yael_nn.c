@@ -13,23 +13,6 @@
 #include "../../../include/yael/vector.h"
 #include "yb_host.h"
 
-/* generic distance types: distance slab + per-row select, in query chunks */
-static void knn_alt(int type, int nq, int nb, int d, int k, const float *b_dev,
-                    const float *q_dev, const float *w_dev, int *assign_dev, float *dis_dev) {
-  size_t budget = (size_t)1 << 30;
-  size_t rows = budget / (sizeof(float) * (size_t)nb);
-  if (rows < 1) rows = 1;
-  if (rows > (size_t)nq) rows = nq;
-  float *slab = (float *)yb_malloc(sizeof(float) * rows * (size_t)nb);
-  (void)w_dev;
-  for (long q0 = 0; q0 < nq; q0 += (long)rows) {
-    int nr = (int)(nq - q0 < (long)rows ? nq - q0 : (long)rows);
-    YBH_CHECK(yb_cross_distances_alt(type, d, nb, nr, b_dev, d, q_dev + q0 * d, d, slab, nb, NULL));
-    YBH_CHECK(yb_k_min_rows(slab, nb, nb, nr, k, +1, assign_dev + q0 * k, dis_dev + q0 * k, NULL));
-  }
-  yb_free(slab);
-}
-
 /* yael/nn.c:451-525 (k > 1) and 383-446 (k == 1) */
 void knn_full(int distance_type, int nq, int nb, int d, int k, const float *b, const float *q,
               const float *b_weights, int *assign, float *dis) {
@@ -56,13 +39,8 @@ void knn_full(int distance_type, int nq, int nb, int d, int k, const float *b, c
     YBH_CHECK(yb_knn_l2(nq, nb, d, k, (const float *)ab.dev, (const float *)aq.dev,
                         (const float *)aw.dev, (int *)oa.dev, (float *)od.dev, 0, NULL));
   } else if ((distance_type >= 1 && distance_type <= 6) || distance_type == 16) {
-    if (b_weights) {
-      fprintf(stderr, "yael_b200: knn_full: b_weights with distance_type %d is not supported\n",
-              distance_type);
-      abort();
-    }
-    knn_alt(distance_type, nq, nb, d, k, (const float *)ab.dev, (const float *)aq.dev, NULL,
-            (int *)oa.dev, (float *)od.dev);
+    YBH_CHECK(yb_knn_alt(distance_type, nq, nb, d, k, (const float *)ab.dev, (const float *)aq.dev,
+                         (const float *)aw.dev, (int *)oa.dev, (float *)od.dev, NULL));
   } else {
     fprintf(stderr, "yael_b200: knn_full: unknown distance_type %d\n", distance_type);
     abort();

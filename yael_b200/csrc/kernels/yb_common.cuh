@@ -16,8 +16,8 @@ int fail(int code, const char *fmt, ...);
 cudaStream_t stream_of(yb_stream_t s);
 cudaStream_t copy_stream();  // per-device stream for host->device feeds
 // grow-only cached workspace of the current device; valid until the next reserve() call
-// on the same device.  The whole library serialises HOST-side submission behind one mutex
-// (Guard); scratch_done() records the stream position after which the block may be reused
+// on the same device.  Calls on one device serialise their HOST-side submission behind that
+// device's mutex (Guard); scratch_done() records the stream position after which the block may be reused
 // from another stream.
 void *scratch_reserve(size_t bytes, cudaStream_t on);
 void scratch_done(cudaStream_t on);
@@ -33,10 +33,22 @@ struct ProfScope {
   ~ProfScope() { prof_end(h, st); }
 };
 
-struct Guard {  // RAII lock of the library-wide mutex (the reference promises re-entrancy:
-  Guard();      // doc/index.rst:55-58; callers may come from several host threads)
-  ~Guard();
+struct Guard {  // RAII lock of the CURRENT DEVICE's mutex (the reference promises re-entrancy:
+  int dev;      // doc/index.rst:55-58; callers may come from several host threads): calls on one
+  Guard();      // device serialise their host-side submission, calls on different devices -- one
+  ~Guard();     // host thread per GPU -- run concurrently
 };
+int dev_index();  // the current device
+// run `f` (cudaFuncSetAttribute and the like) once per DEVICE: function attributes belong to the
+// device that is current when they are set
+template <typename F>
+inline void once_per_device(bool (&done)[64], F f) {
+  const int dv = dev_index();
+  if (!done[dv]) {
+    f();
+    done[dv] = true;
+  }
+}
 
 struct ScratchScope {  // reserve in the constructor, publish completion in the destructor
   cudaStream_t st;

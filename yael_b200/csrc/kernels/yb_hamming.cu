@@ -520,8 +520,8 @@ __global__ void k_ham_scatter(const int *__restrict__ rows, long n, int k,
 }
 
 static int g_ham_force = -1;
-static int g_ham_last_engine = 0;
-static long g_ham_last_fallbacks = 0;
+static thread_local int g_ham_last_engine = 0;
+static thread_local long g_ham_last_fallbacks = 0;
 
 static int ham_engine_choice() {
   if (g_ham_force >= 0) return g_ham_force;

@@ -297,12 +297,10 @@ int hamming_tc(int nq, int nb, int W, int k, const unsigned long long *pb,
     }
     {
       ProfScope ps(15, st);
-      static bool attr = false;
-      if (!attr) {
-        YB_CUDA(cudaFuncSetAttribute(k_ham_tc_finish, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     HF_CAP * 8));
-        attr = true;
-      }
+      static bool attr[64] = {};
+      once_per_device(attr, [] {
+        cudaFuncSetAttribute(k_ham_tc_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, HF_CAP * 8);
+      });
       k_ham_tc_finish<<<nq, HF_T, HF_CAP * 8, st>>>(nq, k, plan.lists, kp, ccnt, cscore, cid, cthr,
                                                     id_offset, assign, dis, flags);
       YB_LAUNCH_CHECK();

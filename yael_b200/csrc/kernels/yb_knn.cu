@@ -16,9 +16,23 @@
 namespace yb {
 
 static int g_engine_force = -1;
-static int g_last_engine = 0;
-static int g_last_operands = 0;  // operand kind of the last tensor pass (0 TF32, 2 FP16)
-static long g_last_uncert = 0;
+static thread_local int g_last_engine = 0;
+static thread_local int g_last_operands = 0;  // operand kind of the last tensor pass (0 TF32, 2 FP16)
+static thread_local long g_last_uncert = 0;
+
+// Absolute part of the tensor-score error bound, as a fraction of max|b - mu|^2: the squared norm of
+// a centred row is an FP32 sum (<= ~10 roundings of 2^-24 for d <= 144 as the conversion kernel
+// sums it) and the accumulator acc' = <q,b> - |b|^2/2 is rounded (towards zero, 2^-23, plus the
+// alignment loss of the 16 products of an instruction, <= 2^-20 of the largest one) once per MMA,
+// 9 to 18 MMAs per tile, at a magnitude of up to |b|^2/2 + |q||b|.  The |q||b| share of that is
+// inside the 5 % head room of the Cauchy-Schwarz term; the |b|^2 share is NOT proportional to |q|
+// and needs its own term: 2 * 18 * (2^-23 + 2^-20) / 2 + 10 * 2^-24 < 2.3e-5.
+constexpr float kAccAbs = 2.3e-5f;
+// Rounding of the reference's own FP32 distance (sequential float norm, sequential FMA dot product,
+// two float additions; yael/nn.c:100-129) relative to |q|^2 + |b|^2 of the UNCENTRED rows: what two
+// exact near-ties may be swapped by in the reference's ranking.  2e-6 = 33 x 2^-24 covers the
+// random-walk growth of a d <= 1000 chain with a wide margin.
+constexpr float kRefRound = 2e-6f;
 
 // ------------------------------------------------------------------ exact re-rank
 // One CTA (4 warps) per query.  Candidates come as ids; each warp takes 32 candidates at a
@@ -54,6 +68,7 @@ struct RerankArgs {
   float err_scale;         // certificate: E_q = err_scale * |q| * max|b|
   const float *bmax;       // device scalar: max |b| (sqrt of max squared norm)
   const float *err_abs;    // device scalar (or NULL): E_q += err_abs * (|q| + max|b|) (FP16 operands)
+  const float *mu_norm;    // device scalar: |mu|, the norm of the centring vector (reference-rounding term)
   int *assign;
   int id_offset;
   int *uncert_flags;       // [nq] 1 = certificate failed
@@ -232,9 +247,16 @@ __global__ void __launch_bounds__(RR_T) k_rerank(RerankArgs A) {
             uint32_t bits = (fk & 0x80000000u) ? (fk & 0x7fffffffu) : ~fk;
             // the tensor pass scored CENTRED operands: S_c(b) = |q-b|^2 - |q-mu|^2
             double Dk = (double)__uint_as_float(bits);
-            double E = (double)A.err_scale * sqrt(qcn) * (double)(*A.bmax) +
-                       4e-5 * (fabs(Dk) + qcn) + 2e-6 * (fabs(Dk) + qn);
-            if (A.err_abs) E += (double)(*A.err_abs) * (sqrt(qcn) + (double)(*A.bmax));
+            // E_q: operand rounding (Cauchy-Schwarz term) + an ABSOLUTE term for the FP32 steps
+            // that do not shrink with |q - mu| (kAccAbs: rounding of |b - mu|^2 and of the tensor
+            // core's FP32 accumulation, whose partial sums are of size |b - mu|^2 / 2 however small
+            // the query is) + the rounding of the REFERENCE's own FP32 arithmetic, which works on
+            // the uncentred rows (kRefRound * (|q|^2 + max|b|^2), |b| <= |b - mu| + |mu|).
+            const double bmx = (double)(*A.bmax), mun = A.mu_norm ? (double)(*A.mu_norm) : 0.0;
+            double E = (double)A.err_scale * sqrt(qcn) * bmx + (double)kAccAbs * bmx * bmx +
+                       4e-5 * (fabs(Dk) + qcn) +
+                       (double)kRefRound * (fabs(Dk) + qn + (bmx + mun) * (bmx + mun));
+            if (A.err_abs) E += (double)(*A.err_abs) * (sqrt(qcn) + bmx);
             if (!((Dk - qcn) + E < (double)T)) flag = 1;
           }
         }
@@ -327,12 +349,11 @@ static size_t rerank_smem_bytes(int d, int m, int m_pad) {
 }
 
 static void rerank_attrs() {
-  static bool done = false;
-  if (!done) {
+  static bool done[64] = {};
+  once_per_device(done, [] {
     cudaFuncSetAttribute(k_rerank<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_rerank<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    done = true;
-  }
+  });
 }
 
 // ------------------------------------------------------------------ engine 0
@@ -824,6 +845,18 @@ k_center_rows_v4(const float *__restrict__ x, long n, int d, const float *__rest
   }
 }
 
+// scal[7] = |mu| (norm of the centring vector): enters the reference-rounding term of the
+// certificate and of the k = 1 margin
+__global__ void k_mu_norm(const float *__restrict__ mu, int d, float *__restrict__ out) {
+  float s = 0.f;
+  for (int c = threadIdx.x; c < d; c += 32) {
+    const float v = mu[c];
+    if (isfinite(v)) s = fmaf(v, v, s);
+  }
+  s = warp_sum(s);
+  if (threadIdx.x == 0) *out = sqrtf(s);
+}
+
 static void launch_center_rows(const float *x, long n, int d, int dpad, const float *mu, float *out,
                                float *norm, cudaStream_t st, RowMap rm = RowMap{0, 0}) {
   if (n <= 0) return;
@@ -842,7 +875,8 @@ static size_t center_ws_bytes(long nb, int d) {
 
 // base_c / query_c: centred copies with row pitch dpad (multiple of 4 floats); bnorm[nb] = |b-mu|^2
 static int center_operands(int nq, int nb, int d, int dpad, const float *base, const float *query,
-                           float *base_c, float *query_c, float *bnorm, void *ws, cudaStream_t st) {
+                           float *base_c, float *query_c, float *bnorm, float *mu_norm, void *ws,
+                           cudaStream_t st) {
   Carver c(ws);
   int nblk = (int)(((long)nb + CM_ROWS - 1) / CM_ROWS);
   if (nblk > CM_BLOCKS) nblk = CM_BLOCKS;
@@ -854,6 +888,8 @@ static int center_operands(int nq, int nb, int d, int dpad, const float *base, c
   k_col_partial<<<nblk, 256, 0, st>>>(base, nb, d, step, psum, pcnt);
   YB_LAUNCH_CHECK();
   k_col_final<<<(d + 127) / 128, 128, 0, st>>>(psum, pcnt, nblk, d, mu);
+  YB_LAUNCH_CHECK();
+  k_mu_norm<<<1, 32, 0, st>>>(mu, d, mu_norm);
   YB_LAUNCH_CHECK();
   launch_center_rows(base, nb, d, dpad, mu, base_c, bnorm, st);
   launch_center_rows(query, nq, d, dpad, mu, query_c, nullptr, st);
@@ -1085,6 +1121,8 @@ static int center_operands_h(int nq, int nb, int d, int dh, int df, const float 
   YB_LAUNCH_CHECK();
   k_col_final<<<(d + 127) / 128, 128, 0, st>>>(psum, pcnt, nblk, d, mu);
   YB_LAUNCH_CHECK();
+  k_mu_norm<<<1, 32, 0, st>>>(mu, d, scal + 7);
+  YB_LAUNCH_CHECK();
   k_absmax_sample<<<nblk, 256, 0, st>>>(base, nb, d, step, scal + 6);
   YB_LAUNCH_CHECK();
   int qblk = (int)(((long)nq + CM_ROWS - 1) / CM_ROWS);
@@ -1210,9 +1248,22 @@ static int redo_flagged_tensor(int nq, int nb, int d, int k, const float *base, 
 }
 
 // ------------------------------------------------------------------ engine 1, k = 1
-// margin[q] = 2.05 * E_q with E_q the TF32 score error bound of the query (see kTf32ErrScale)
+// margin[q] = 2.05 * E_q + 2 * delta_q.  E_q bounds the error of a tensor score (operand rounding:
+// err_scale |q-mu| max|b-mu|, sub-normal FP16 values: err_abs, and the ABSOLUTE term kAccAbs
+// max|b-mu|^2 for the FP32 roundings that do not shrink with |q-mu|: a query AT the centring
+// vector still sees scores of size |b-mu|^2 rounded in FP32); delta_q = kRefRound ((|q-mu|+|mu|)^2
+// + (max|b-mu|+|mu|)^2) bounds the rounding of the reference's own FP32 distance, so the row the
+// reference's arithmetic ranks first is a candidate even when it is an exact near-tie.
+// scal[0] = max|b-mu|, scal[7] = |mu|.
+__device__ __forceinline__ float k1_margin_of(float qn, float bmax, float mun, float err_scale,
+                                              float err_abs) {
+  const float e = err_scale * qn * bmax + err_abs * (qn + bmax) + kAccAbs * bmax * bmax;
+  const float dl = kRefRound * ((qn + mun) * (qn + mun) + (bmax + mun) * (bmax + mun));
+  return 2.05f * e + 2.0f * dl + 1e-30f;
+}
+
 __global__ void k_k1_margin(const float *__restrict__ query, int nq, int d,
-                            const float *__restrict__ bmax, float err_scale,
+                            const float *__restrict__ scal, float err_scale,
                             float *__restrict__ margin) {
   const int q = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (q >= nq) return;
@@ -1222,17 +1273,15 @@ __global__ void k_k1_margin(const float *__restrict__ query, int nq, int d,
     s = fmaf(v, v, s);
   }
   s = warp_sum(s);
-  if (lane == 0) margin[q] = 2.05f * err_scale * sqrtf(s) * (*bmax) + 1e-30f;
+  if (lane == 0) margin[q] = k1_margin_of(sqrtf(s), scal[0], scal[7], err_scale, 0.f);
 }
 
-// the same from the squared norms of the centred queries (FP16 operand path)
-__global__ void k_k1_margin_n(const float *__restrict__ qcnorm, int nq, const float *__restrict__ bmax,
-                              float err_scale, const float *__restrict__ err_abs,
-                              float *__restrict__ margin) {
+// the same from the squared norms of the centred queries (FP16 operand path; scal[5] = err_abs)
+__global__ void k_k1_margin_n(const float *__restrict__ qcnorm, int nq, const float *__restrict__ scal,
+                              float err_scale, float *__restrict__ margin) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq) return;
-  const float qn = sqrtf(qcnorm[q]);
-  margin[q] = 2.05f * (err_scale * qn * (*bmax) + (*err_abs) * (qn + (*bmax))) + 1e-30f;
+  margin[q] = k1_margin_of(sqrtf(qcnorm[q]), scal[0], scal[7], err_scale, scal[5]);
 }
 
 // exact re-rank of the few k = 1 candidates: one warp per query, one lane per candidate slot;
@@ -1384,13 +1433,13 @@ static int knn_tf32_nearest(int nq, int nb, int d, const float *base, const floa
           return rc;
         plan.acc_scale = scal + 3;
       } else {
-        if ((rc = center_operands(nq, nb, d, dpad, base, query, base_c, query_c, an, cws, st))) return rc;
+        if ((rc = center_operands(nq, nb, d, dpad, base, query, base_c, query_c, an, scal + 7, cws, st))) return rc;
       }
       if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
       k_sqrt_max<<<2 * sm_count(), 256, 0, st>>>(an, nb, scal);
       YB_LAUNCH_CHECK();
       if (f16)
-        k_k1_margin_n<<<(nq + 255) / 256, 256, 0, st>>>(qcnorm, nq, scal, kF16ErrScale, scal + 5, margin);
+        k_k1_margin_n<<<(nq + 255) / 256, 256, 0, st>>>(qcnorm, nq, scal, kF16ErrScale, margin);
       else
         k_k1_margin<<<(nq + 3) / 4, 128, 0, st>>>(query_c, nq, dpad, scal, kTf32ErrScale, margin);
       YB_LAUNCH_CHECK();
@@ -1558,7 +1607,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
           return rc;
         plan.acc_scale = splan.acc_scale = l1plan.acc_scale = scal + 3;
       } else {
-        if ((rc = center_operands(nq, nb, d, dpad, base, query, base_c, query_c, an, cws, st))) return rc;
+        if ((rc = center_operands(nq, nb, d, dpad, base, query, base_c, query_c, an, scal + 7, cws, st))) return rc;
       }
       if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
       k_sqrt_max<<<2 * sm_count(), 256, 0, st>>>(an, nb, scal);
@@ -1649,6 +1698,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
     A.cand_thr = cthr; A.lists = plan.lists; A.query_c = query_cf; A.qc_ld = f16 ? dqc : dpad;
     A.err_scale = f16 ? kF16ErrScale : kTf32ErrScale; A.bmax = scal; A.uncert_flags = flags;
     A.err_abs = f16 ? scal + 5 : nullptr;
+    A.mu_norm = scal + 7;
     A.gsort = nullptr; A.m_pad = m_pad; A.k1 = (k == 1);
     rerank_attrs();
     {
@@ -1838,6 +1888,8 @@ int knn_tf32_streamed(int nq, int nb, int d, int k, const float *base_host, floa
       YB_CUDA(cudaGetLastError());
       if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
       YB_CUDA(cudaMemsetAsync(scal, 0, 64, st));
+      k_mu_norm<<<1, 32, 0, st>>>(mu, d, scal + 7);
+      YB_LAUNCH_CHECK();
     }
     {
       ProfScope ps(10, st);
@@ -1898,6 +1950,7 @@ int knn_tf32_streamed(int nq, int nb, int d, int k, const float *base_host, floa
     A.cand_stride = (int)stride; A.m = m; A.all_listed = 0;
     A.cand_thr = cthr; A.lists = lists; A.query_c = query_c; A.qc_ld = dpad;
     A.err_scale = kTf32ErrScale; A.bmax = scal; A.uncert_flags = flags;
+    A.mu_norm = scal + 7;
     A.gsort = nullptr; A.m_pad = m_pad; A.k1 = 0;
     rerank_attrs();
     {
@@ -1968,6 +2021,44 @@ extern "C" int yb_debug_f16_scores(int nq, int nb, int d, const float *base, con
   YB_CUDA(cudaMemcpyAsync(&overflow, scal + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
   YB_CUDA(cudaStreamSynchronize(st));
   return overflow ? fail(7, "a value overflowed FP16") : 0;
+}
+
+// dists[j][i] *= w[i] (yael/nn.c:497-500), j < nr queries, i < nb base vectors
+__global__ void k_weight_slab(float *__restrict__ slab, long nb, long nr, const float *__restrict__ w) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nb * nr) slab[t] = __fmul_rn(slab[t], __ldg(w + t % nb));
+}
+
+// knn_full for the distance types that are not a contraction (yael/nn.c:451-525 with
+// compute_cross_distances_alt, 280-350): distance slab -> optional per-base weights -> per-row
+// select, in query chunks.  k == 1 follows nn_single_full (yael/nn.c:404-440): strict '<' from
+// (-1, 1e30f) for every distance type.
+extern "C" int yb_knn_alt(int distance_type, int nq, int nb, int d, int k, const float *base,
+                          const float *query, const float *b_weights, int *assign, float *dis,
+                          yb_stream_t s) {
+  if (nq <= 0) return 0;
+  if (k <= 0 || k > nb) return fail(3, "yb_knn_alt: need 0 < k <= nb (k=%d, nb=%d)", k, nb);
+  Guard g;
+  cudaStream_t st = stream_of(s);
+  const size_t rows = exact_chunk_rows(nq, nb);
+  // pooled blocks, not the device workspace: the distance call below reserves that itself
+  float *slab = (float *)yb_malloc(sizeof(float) * rows * (size_t)nb);
+  void *kws = yb_malloc(kmin_ws_bytes((long)rows, k));
+  int rc = 0;
+  for (long q0 = 0; q0 < nq && !rc; q0 += (long)rows) {
+    const long nr = nq - q0 < (long)rows ? nq - q0 : (long)rows;
+    rc = yb_cross_distances_alt(distance_type, d, nb, (int)nr, base, d, query + q0 * d, d, slab, nb, s);
+    if (!rc && b_weights) {
+      const long tot = nr * nb;
+      k_weight_slab<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(slab, nb, nr, b_weights);
+      count_launch();
+    }
+    if (!rc)
+      rc = kmin_rows(slab, nb, nb, nr, k, +1, assign + q0 * k, dis + q0 * k, 0, k == 1 ? 1 : 0, kws, st);
+  }
+  yb_free(slab);
+  yb_free(kws);
+  return rc;
 }
 
 extern "C" void yb_set_knn_engine(int engine) { g_engine_force = engine; }

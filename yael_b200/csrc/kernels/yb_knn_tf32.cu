@@ -1377,13 +1377,15 @@ template <int MODE, int KIND = OP_TF32>
 static int launch_mode(const Tf32Plan &plan, const CUtensorMap &mq, const CUtensorMap &mb,
                        const CUtensorMap &mbh, const CUtensorMap &mqx, const CUtensorMap &mbx,
                        const Tf32Params &P, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_knn_tf32<MODE, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TF32_SMEM_BYTES);
-    if (e != cudaSuccess) return fail(6, "cannot reserve %d bytes of shared memory: %s",
-                                      TF32_SMEM_BYTES, cudaGetErrorString(e));
-    attr = true;
+  static bool attr[64] = {};  // per device: function attributes belong to the current device
+  cudaError_t ae = cudaSuccess;
+  once_per_device(attr, [&ae] {
+    ae = cudaFuncSetAttribute(k_knn_tf32<MODE, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              TF32_SMEM_BYTES);
+  });
+  if (ae != cudaSuccess) {
+    attr[dev_index()] = false;
+    return fail(6, "cannot reserve %d bytes of shared memory: %s", TF32_SMEM_BYTES, cudaGetErrorString(ae));
   }
   if (plan.pair) {
     cudaLaunchConfig_t cfg = {};

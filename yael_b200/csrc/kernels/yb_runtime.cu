@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -13,7 +14,7 @@
 
 namespace {
 
-constexpr int kMaxDev = 16;
+constexpr int kMaxDev = 64;
 
 struct DevState {
   cudaStream_t stream = nullptr;
@@ -26,31 +27,46 @@ struct DevState {
   int sms = 0;
 };
 
+// A pooled block remembers where the streams of its device stood when it was freed: whoever gets
+// it next waits (on the host) for those positions, so a kernel that was still reading the block
+// on one stream can never see the writes of its next user on another.
 struct PoolBlock {
   void *p;
   size_t bytes;
   int dev;
   bool free_;
+  cudaEvent_t ev[3];
+  int nev;
 };
 std::vector<PoolBlock> g_pool;
+std::mutex g_pool_mutex;
 
 DevState g_dev[kMaxDev];
-std::recursive_mutex g_mutex;
+// one lock per device: calls on different devices (one host thread per GPU) run concurrently,
+// calls on the same device serialise their host-side submission
+std::recursive_mutex g_dev_mutex[kMaxDev];
+cudaStream_t g_last_caller_stream[kMaxDev];  // the last caller-provided stream seen per device
 thread_local char g_err[512] = "";
-long g_launches = 0;
+std::atomic<long> g_launches{0};
 
 int cur_dev() {
   int d = 0;
   if (cudaGetDevice(&d) != cudaSuccess) return 0;
-  return d < kMaxDev ? d : 0;
+  if (d >= kMaxDev) {
+    fprintf(stderr, "yael_b200: device index %d exceeds the supported %d devices\n", d, kMaxDev);
+    abort();
+  }
+  return d;
 }
 
 
 void pool_trim(int dev) {
-  std::lock_guard<std::recursive_mutex> lk(g_mutex);
+  std::lock_guard<std::mutex> lk(g_pool_mutex);
   cudaDeviceSynchronize();
   for (size_t i = 0; i < g_pool.size();) {
     if (g_pool[i].free_ && (dev < 0 || g_pool[i].dev == dev)) {
+      for (int e = 0; e < 3; e++)
+        if (g_pool[i].ev[e]) cudaEventDestroy(g_pool[i].ev[e]);
       cudaFree(g_pool[i].p);
       g_pool[i] = g_pool.back();
       g_pool.pop_back();
@@ -72,20 +88,29 @@ int fail(int code, const char *fmt, ...) {
   return code;
 }
 
-Guard::Guard() { g_mutex.lock(); }
-Guard::~Guard() { g_mutex.unlock(); }
+Guard::Guard() : dev(cur_dev()) { g_dev_mutex[dev].lock(); }
+Guard::~Guard() { g_dev_mutex[dev].unlock(); }
+
+int dev_index() { return cur_dev(); }
 
 cudaStream_t copy_stream() {
-  DevState &st = g_dev[cur_dev()];
+  const int dev = cur_dev();
+  DevState &st = g_dev[dev];
+  std::lock_guard<std::recursive_mutex> lk(g_dev_mutex[dev]);
   if (!st.copy_stream) cudaStreamCreateWithFlags(&st.copy_stream, cudaStreamNonBlocking);
   return st.copy_stream;
 }
 
 cudaStream_t stream_of(yb_stream_t s) {
-  if (s) return (cudaStream_t)s;
-  DevState &st = g_dev[cur_dev()];
-  if (!st.stream) {
-    if (cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking) != cudaSuccess) {
+  const int dev = cur_dev();
+  if (s) {
+    g_last_caller_stream[dev] = (cudaStream_t)s;
+    return (cudaStream_t)s;
+  }
+  DevState &st = g_dev[dev];
+  if (!st.stream) {  // lazy creation under the device lock (callers may not hold it)
+    std::lock_guard<std::recursive_mutex> lk(g_dev_mutex[dev]);
+    if (!st.stream && cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking) != cudaSuccess) {
       fprintf(stderr, "yael_b200: cannot create a CUDA stream: %s\n",
               cudaGetErrorString(cudaGetLastError()));
       abort();
@@ -137,7 +162,7 @@ int sm_count() {
   return st.sms;
 }
 
-void count_launch(long n) { g_launches += n; }
+void count_launch(long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---- optional phase timing (bench.py roofline): CUDA event pairs on the launching stream
 struct ProfSpan {
@@ -147,6 +172,7 @@ struct ProfSpan {
 static bool g_prof_on = false;
 static std::vector<ProfSpan> g_spans;
 static std::vector<cudaEvent_t> g_ev_pool;
+static std::mutex g_prof_mutex;
 
 static cudaEvent_t prof_event() {
   if (!g_ev_pool.empty()) {
@@ -161,6 +187,7 @@ static cudaEvent_t prof_event() {
 
 int prof_begin(int phase, cudaStream_t st) {
   if (!g_prof_on) return -1;
+  std::lock_guard<std::mutex> lk(g_prof_mutex);
   ProfSpan s = {phase, prof_event(), prof_event()};
   cudaEventRecord(s.a, st);
   g_spans.push_back(s);
@@ -168,7 +195,9 @@ int prof_begin(int phase, cudaStream_t st) {
 }
 
 void prof_end(int handle, cudaStream_t st) {
-  if (handle >= 0 && handle < (int)g_spans.size()) cudaEventRecord(g_spans[handle].b, st);
+  if (handle < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mutex);
+  if (handle < (int)g_spans.size()) cudaEventRecord(g_spans[handle].b, st);
 }
 
 }  // namespace yb
@@ -200,8 +229,8 @@ int yb_sync(yb_stream_t s) {
 }
 
 long yb_launch_count(int reset) {
-  long v = g_launches;
-  if (reset) g_launches = 0;
+  long v = g_launches.load();
+  if (reset) g_launches.store(0);
   return v;
 }
 
@@ -212,7 +241,7 @@ void *yb_malloc(size_t bytes) {
   bytes = (bytes + 511) & ~(size_t)511;
   int dev = cur_dev();
   {
-    std::lock_guard<std::recursive_mutex> lk(g_mutex);
+    std::unique_lock<std::mutex> lk(g_pool_mutex);
     PoolBlock *best = nullptr;
     for (auto &b : g_pool)
       if (b.free_ && b.dev == dev && b.bytes >= bytes && b.bytes <= bytes + (bytes >> 2) + 4096 &&
@@ -220,7 +249,18 @@ void *yb_malloc(size_t bytes) {
         best = &b;
     if (best) {
       best->free_ = false;
-      return best->p;
+      void *p = best->p;
+      cudaEvent_t ev[3];
+      const int nev = best->nev;
+      for (int e = 0; e < nev; e++) ev[e] = best->ev[e];
+      lk.unlock();
+      // earlier users of the block (any stream of this device) are done before it is handed out
+      for (int e = 0; e < nev; e++)
+        if (cudaEventQuery(ev[e]) != cudaSuccess) {
+          cudaGetLastError();
+          cudaEventSynchronize(ev[e]);
+        }
+      return p;
     }
   }
   void *p = nullptr;
@@ -234,19 +274,44 @@ void *yb_malloc(size_t bytes) {
     fprintf(stderr, "yael_b200: cudaMalloc(%zu): %s\n", bytes, cudaGetErrorString(e));
     abort();
   }
-  std::lock_guard<std::recursive_mutex> lk(g_mutex);
-  g_pool.push_back({p, bytes, dev, false});
+  std::lock_guard<std::mutex> lk(g_pool_mutex);
+  PoolBlock nb = {p, bytes, dev, false, {nullptr, nullptr, nullptr}, 0};
+  g_pool.push_back(nb);
   return p;
 }
 
 void yb_free(void *p) {
   if (!p) return;
-  std::lock_guard<std::recursive_mutex> lk(g_mutex);
-  for (auto &b : g_pool)
-    if (b.p == p) {
-      b.free_ = true;
-      return;
-    }
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    for (auto &b : g_pool)
+      if (b.p == p) {
+        // stream positions at the time of the free: own stream, copy stream, last caller stream
+        int cur = 0;
+        const bool same_dev = cudaGetDevice(&cur) == cudaSuccess && cur == b.dev;
+        if (!same_dev) cudaSetDevice(b.dev);
+        const DevState &ds = g_dev[b.dev];
+        cudaStream_t ss[3] = {ds.stream, ds.copy_stream, g_last_caller_stream[b.dev]};
+        int n = 0;
+        for (int i = 0; i < 3; i++) {
+          if (!ss[i] || (i == 2 && (ss[2] == ss[0] || ss[2] == ss[1]))) continue;
+          if (!b.ev[n] && cudaEventCreateWithFlags(&b.ev[n], cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            b.ev[n] = nullptr;
+            continue;
+          }
+          if (cudaEventRecord(b.ev[n], ss[i]) != cudaSuccess) {
+            cudaGetLastError();  // a caller stream that no longer exists: nothing can be pending on it
+            continue;
+          }
+          n++;
+        }
+        b.nev = n;
+        if (!same_dev) cudaSetDevice(cur);
+        b.free_ = true;
+        return;
+      }
+  }
   cudaFree(p);  // not ours
 }
 
@@ -272,13 +337,13 @@ int yb_d2h(void *dst, const void *src, size_t bytes, yb_stream_t s) {
 }
 
 void yb_prof_enable(int on) {
-  yb::Guard g;
+  std::lock_guard<std::mutex> lk(yb::g_prof_mutex);
   yb::g_prof_on = on != 0;
 }
 
 // total milliseconds (and number of spans via *count) recorded for a phase; reset drops them
 double yb_prof_ms(int phase, long *count, int reset) {
-  yb::Guard g;
+  std::lock_guard<std::mutex> lk(yb::g_prof_mutex);
   double ms = 0.0;
   long n = 0;
   for (auto &s : yb::g_spans) {

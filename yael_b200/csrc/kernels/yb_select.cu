@@ -237,12 +237,11 @@ int kmin_rows(const float *val, long n, long ld, long nrow, int k, int sign, int
   if (k > n) return fail(3, "k_min: k=%d exceeds n=%ld", k, n);
   int k_pad = pow2_ceil(k < 2 ? 2 : k);
   size_t smem = (k_pad <= KSMEM_SORT && k > 1) ? sizeof(unsigned long long) * (size_t)k_pad : 0;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};
+  once_per_device(attr_done, [] {
     cudaFuncSetAttribute(k_kmin_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(sizeof(unsigned long long) * KSMEM_SORT));
-    attr_done = true;
-  }
+  });
   k_kmin_rows<<<(unsigned)nrow, KT, smem, st>>>(val, n, ld, k, sign, idx, vals, id_offset, flags,
                                                 (unsigned long long *)ws, k_pad);
   YB_LAUNCH_CHECK();

@@ -70,12 +70,17 @@ class ShardedKnn:
                 "all_gather": sum(b.elapsed_time(c) for _, b, c, _ in self.events) / n,
                 "merge": sum(c.elapsed_time(d) for _, _, c, d in self.events) / n}
 
-    def _local(self, query, idx, dis):
+    def _local_into(self, query, idx, dis, id_offset):
+        torch = self.torch
+        assert query.is_cuda and query.dtype == torch.float32 and query.is_contiguous()
         nq, d = query.shape
         nb = self.base.shape[0]
         check(lib().yb_knn_l2(nq, nb, d, self.k, self.base.data_ptr(), query.data_ptr(), None,
-                              idx.data_ptr(), dis.data_ptr(), self.id_offset,
-                              _stream_ptr(self.torch)), "yb_knn_l2")
+                              idx.data_ptr(), dis.data_ptr(), int(id_offset),
+                              _stream_ptr(torch)), "yb_knn_l2")
+
+    def _local(self, query, idx, dis):
+        self._local_into(query, idx, dis, self.id_offset)
 
     def _exchange(self, buf, nq):
         """buf: this rank's [2][nq][k] int32 block (ids, distance bits).  ONE all-gather, then the

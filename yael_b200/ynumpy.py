@@ -63,8 +63,8 @@ def knn(queries, base, nnn=1, distance_type=2, nt=1):
     return idx, dis
 
 
-def knn_weighted(queries, base, weights, nnn=1, nt=1):
-    """knn_full_thread with the per-base-vector weights of yael/nn.c:497-500."""
+def knn_weighted(queries, base, weights, nnn=1, nt=1, distance_type=2):
+    """knn_full_thread with the per-base-vector weights of yael/nn.c:497-500 (any distance type)."""
     _check_row_float32(base)
     _check_row_float32(queries)
     weights = np.ascontiguousarray(weights, dtype=np.float32)
@@ -73,8 +73,8 @@ def knn_weighted(queries, base, weights, nnn=1, nt=1):
     _lib.require_gpu()
     idx = np.empty((nq, nnn), dtype=np.int32)
     dis = np.empty((nq, nnn), dtype=np.float32)
-    lib().knn_full_thread(2, nq, n, d, nnn, _fp(base), _fp(queries), _fp(weights), _ip(idx),
-                          _fp(dis), nt)
+    lib().knn_full_thread(distance_type, nq, n, d, nnn, _fp(base), _fp(queries), _fp(weights),
+                          _ip(idx), _fp(dis), nt)
     return idx, dis
 
 
@@ -121,10 +121,14 @@ def kmeans(v, k, distance_type=2, nt=1, niter=30, seed=0, redo=1, verbose=True,
         flags |= KMEANS_QUIET
     if distance_type == 2:
         pass
-    elif distance_type == 1:
-        flags |= KMEANS_L1
-    elif distance_type == 3:
-        flags |= KMEANS_CHI2
+    elif distance_type in (1, 3):
+        # KMEANS_L1 / KMEANS_CHI2 (yael/kmeans.h:16-17): medians / Newton steps per coordinate, no
+        # contraction -- outside the B200 hot path; say so instead of reporting a failed clustering
+        raise NotImplementedError("yael_b200.kmeans: distance_type %d (KMEANS_%s) is not provided; "
+                                  "only L2 k-means (distance_type=2) is"
+                                  % (distance_type, "L1" if distance_type == 1 else "CHI2"))
+    else:
+        raise ValueError("kmeans: unknown distance_type %r" % (distance_type,))
     if isinstance(init, np.ndarray):
         assert init.shape == (k, d)
         centroids[:] = init
