@@ -133,6 +133,11 @@ int yb_knn_reorder_shortlist(int nq, int nb, int d, int k, const float *base,
 int yb_debug_tf32_scores(int nq, int nb, int d, const float *base, const float *query,
                          float *scores, yb_stream_t s);
 
+/* bring-up: clock64() attribution of the last tensor pass run with YAEL_B200_TF32_DEBUG bit 512
+ * (out[cta][16]: issuer waits for accumulator / operands / extras, issuer total, epilogue warp 0
+ * waits for an accumulator / drains it / hands it back, epilogue total, tiles) */
+int yb_debug_tf32_clocks(long long *out, int n_cta);
+
 /* ---- k smallest: fvec_k_min / fvecs_k_min (yael/sorting.c:191-255) ---------------- */
 /* nrow arrays of length n (row stride ld) -> idx[nrow][k] (+ optional vals[nrow][k]),
  * ascending by (value, index); sign = +1 for k-min, -1 for k-max (values negated as the

@@ -36,3 +36,15 @@ for ph in range(12):
     ms = L.yb_prof_ms(ph, C.byref(cnt), 0)
     if cnt.value:
         print("phase %d: %.3f ms avg over %d" % (ph, ms / cnt.value, cnt.value))
+
+if int(os.environ.get("YAEL_B200_TF32_DEBUG", "0")) & 512:
+    ck = np.zeros((148, 16), np.int64)
+    L.yb_debug_tf32_clocks(ck.ctypes.data_as(C.c_void_p), 148)
+    m = ck[ck[:, 8] > 0]
+    t = m[:, 8].astype(np.float64)
+    names = ["issuer: wait accumulator", "issuer: wait operands", "issuer: wait extras", "issuer: total",
+             "epilogue: wait accumulator", "epilogue: drain", "epilogue: hand back", "epilogue: total"]
+    print("clock attribution (cycles per tile, mean over %d CTAs, %.0f tiles per CTA; LAST instrumented pass):" % (len(m), t.mean()))
+    for i, nme in enumerate(names):
+        sel = m[:, i] > 0
+        print("  %-28s %8.1f" % (nme, (m[sel, i] / t[sel]).mean() if sel.any() else 0.0))

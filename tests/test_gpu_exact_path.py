@@ -7,6 +7,9 @@ selection is defined as (value, id) order, which the oracle's canonical variants
 import numpy as np
 import pytest
 
+import yael_b200
+from devmem import DevArray
+
 pytestmark = pytest.mark.gpu
 
 
@@ -220,3 +223,35 @@ def test_kmeans_empty_cluster_split(yn, ob):
     want = ob.orc_kmeans(v, 40, 10, ob.KMEANS_QUIET | 1, 5)
     assert np.array_equal(got[4], want[4])
     assert np.array_equal(got[0], want[1])
+
+
+@pytest.mark.parametrize("n,k,d,skew", [(300000, 2048, 128, 0), (200000, 2048, 96, 5000), (150000, 1024, 200, 3000),
+                                         (120000, 1024, 30, 0), (400000, 4096, 64, 70000), (5000, 1024, 16, 0), (600000, 8192, 128, 0)])
+def test_kmeans_accumulate_short_segments_bit_exact(n, k, d, skew):
+    """Centroid update with many centroids (yb_kmeans_accumulate's short-segment path: one-pass
+    scatter + per-segment id sort): sums must equal the reference's strict point-order FP32 sums
+    (yael/kmeans.c:278-283) bit for bit -- also when one cluster is much longer than the in-warp
+    sort (id-range passes) or longer than the path's limit (device-side fall-back to the general
+    radix-sort path)."""
+    L = yael_b200.lib()
+    r = rs(n + k + d)
+    v = r.rand(n, d).astype(np.float32)
+    assign = r.randint(0, k, n).astype(np.int32)
+    if skew:
+        assign[r.permutation(n)[:skew]] = 7
+    assign[assign == 11] = 12                       # an empty cluster
+    dis = r.rand(n).astype(np.float32)
+    dv, da, dd = DevArray(v), DevArray(assign), DevArray(dis)
+    ds = DevArray(shape=(k, d), dtype=np.float32)
+    dn = DevArray(shape=(k,), dtype=np.int32)
+    dq = DevArray(shape=(1,), dtype=np.float64)
+    rc = L.yb_kmeans_accumulate(d, n, k, dv.ptr, da.ptr, dd.ptr, ds.ptr, dn.ptr, dq.ptr, 1, None)  # exact_order
+    assert rc == 0, L.yb_last_error()
+    L.yb_sync(None)
+    want = np.zeros((k, d), np.float32)
+    np.add.at(want, assign, v)                      # unbuffered, in index order, float32 adds
+    assert np.array_equal(dn.get(), np.bincount(assign, minlength=k))
+    assert np.array_equal(ds.get(), want)
+    assert dq.get()[0] == pytest.approx(float(dis.astype(np.float64).sum()), rel=1e-12)
+    for a in (dv, da, dd, ds, dn, dq):
+        a.free()

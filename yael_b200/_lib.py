@@ -151,6 +151,7 @@ DEVICE = {
     "yb_kmeans_accumulate": (C.c_int, [C.c_int] * 3 + [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "yb_kmeans_scale": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
     "yb_kmeans_dev": (C.c_float, [C.c_int] * 4 + [_vp, C.c_int, C.c_long, C.c_int, _f, _f, _i, _i, _vp, _vp]),
+    "yb_debug_tf32_clocks": (C.c_int, [_vp, C.c_int]),
     "yb_debug_tf32_scores": (C.c_int, [C.c_int] * 3 + [_vp, _vp, _vp, _vp]),
     "yb_debug_f16_scores": (C.c_int, [C.c_int] * 3 + [_vp, _vp, _vp, _vp]),
     "yb_debug_popc_pairs_per_s": (C.c_double, [_vp]),

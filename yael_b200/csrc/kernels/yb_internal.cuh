@@ -43,7 +43,7 @@ struct Tf32Plan {
 Tf32Plan tf32_plan(int nq, int nb, int d, int k, int kind = 0);
 Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kprime, int kind = 0);
 int tf32_kprime_for(int k);
-int tf32_pair_mode();
+int tf32_pair_mode(int kind, int tiles_q);
 // One pass of the tensor-core kernel over the logical tiles 0..nbt_logical-1, logical tile j being
 // database tile j*tile_stride (256 rows each).  Produces, for every query, `lists` shortlists of
 // `kprime` candidates: out_score[q][l][e] = |b|^2 - 2<q,b> evaluated with TF32 operands,

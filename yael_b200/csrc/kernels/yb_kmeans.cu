@@ -18,6 +18,14 @@
 
 namespace yb {
 
+// Device-side path selection without a host round trip: `guard` points at the largest cluster size
+// of this iteration (NULL = no selection).  The short-segment kernels run when it is <= SG_LIMIT,
+// the general (radix sort) kernels launched behind them when it is larger; the others return at once.
+constexpr int kSegLimit = 64 * 1024;
+__device__ __forceinline__ bool general_path_skips(const int *guard) {
+  return guard != nullptr && *guard <= kSegLimit;
+}
+
 // out-of-range ids (the reference asserts on them, yael/kmeans.c:281) are not counted: the host
 // loop notices that the histogram does not add up to n
 __global__ void k_hist(const int *__restrict__ assign, long n, int k, int *__restrict__ counts) {
@@ -46,8 +54,9 @@ __device__ __forceinline__ void rs_load(const int *assign, const int2 *in, long 
 
 __global__ void __launch_bounds__(RS_T)
 k_rs_hist(const int *__restrict__ assign, const int2 *__restrict__ in, long n, int shift,
-          int nblocks, unsigned *__restrict__ ghist) {
+          int nblocks, unsigned *__restrict__ ghist, const int *__restrict__ guard) {
   __shared__ unsigned h[256];
+  if (general_path_skips(guard)) return;
   h[threadIdx.x] = 0;
   __syncthreads();
   long b0 = (long)blockIdx.x * RS_BLOCK;
@@ -63,38 +72,73 @@ k_rs_hist(const int *__restrict__ assign, const int2 *__restrict__ in, long n, i
   ghist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];  // digit-major
 }
 
-// exclusive scan of `len` unsigned values by one CTA
-__global__ void __launch_bounds__(1024) k_scan_u32(unsigned *__restrict__ v, long len) {
-  __shared__ unsigned part[1024];
-  const int tid = threadIdx.x;
-  long per = (len + 1023) / 1024;
-  long b = tid * per, e = min(len, b + per);
-  unsigned s = 0;
-  for (long i = b; i < e; i++) s += v[i];
-  part[tid] = s;
-  __syncthreads();
-  if (tid == 0) {
-    unsigned acc = 0;
-    for (int t = 0; t < 1024; t++) {
-      unsigned x = part[t];
-      part[t] = acc;
-      acc += x;
+// exclusive scan of `len` unsigned values by one CTA: tiles of 4096 values (coalesced 16-byte
+// accesses), warp-shuffle scans inside the tile, a running carry between tiles
+__global__ void __launch_bounds__(1024)
+k_scan_u32(unsigned *__restrict__ v, long len, const int *__restrict__ guard) {
+  __shared__ unsigned wsum[32];
+  __shared__ unsigned tile_total;
+  if (general_path_skips(guard)) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned carry = 0;
+  const bool vec = (((uintptr_t)v) & 15) == 0;
+  for (long base = 0; base < len; base += 4096) {
+    const long i = base + (long)tid * 4;
+    unsigned x[4] = {0u, 0u, 0u, 0u};
+    if (vec && i + 4 <= len) {
+      const uint4 q = *reinterpret_cast<const uint4 *>(v + i);
+      x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (i + j < len) x[j] = v[i + j];
     }
-  }
-  __syncthreads();
-  unsigned acc = part[tid];
-  for (long i = b; i < e; i++) {
-    unsigned x = v[i];
-    v[i] = acc;
-    acc += x;
+    const unsigned s = x[0] + x[1] + x[2] + x[3];
+    unsigned inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned w = wsum[lane];
+      unsigned wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      wsum[lane] = wi - w;
+      if (lane == 31) tile_total = wi;
+    }
+    __syncthreads();
+    unsigned off = carry + wsum[warp] + inc - s;
+    if (vec && i + 4 <= len) {
+      uint4 q;
+      q.x = off; q.y = off + x[0]; q.z = q.y + x[1]; q.w = q.z + x[2];
+      *reinterpret_cast<uint4 *>(v + i) = q;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (i + j < len) {
+          v[i + j] = off;
+          off += x[j];
+        }
+    }
+    carry += tile_total;
+    __syncthreads();
   }
 }
 
 __global__ void __launch_bounds__(RS_T)
 k_rs_scatter(const int *__restrict__ assign, const int2 *__restrict__ in, long n, int shift,
-             int nblocks, const unsigned *__restrict__ ghist, int2 *__restrict__ out) {
+             int nblocks, const unsigned *__restrict__ ghist, int2 *__restrict__ out,
+             const int *__restrict__ guard) {
   __shared__ unsigned base[256];          // next output slot of each digit for this block
   __shared__ unsigned short wc[8][256];   // per-warp digit counts of the current round
+  if (general_path_skips(guard)) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   base[tid] = ghist[(size_t)tid * nblocks + blockIdx.x];
   long b0 = (long)blockIdx.x * RS_BLOCK;
@@ -129,7 +173,9 @@ k_rs_scatter(const int *__restrict__ assign, const int2 *__restrict__ in, long n
 
 // ------------------------------------------------------------------ segmented sums
 __global__ void k_piece_counts(const int *__restrict__ counts, int k, int P,
-                               unsigned *__restrict__ seg_start, unsigned *__restrict__ piece_start) {
+                               unsigned *__restrict__ seg_start, unsigned *__restrict__ piece_start,
+                               const int *__restrict__ guard) {
+  if (general_path_skips(guard)) return;
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < k) {
     seg_start[c] = (unsigned)counts[c];
@@ -143,7 +189,8 @@ __global__ void k_piece_counts(const int *__restrict__ counts, int k, int P,
 
 // piece -> centroid map (binary search on piece_start), one thread per piece
 __global__ void k_piece_map(const unsigned *__restrict__ piece_start, int k,
-                            int *__restrict__ piece_cent) {
+                            int *__restrict__ piece_cent, const int *__restrict__ guard) {
+  if (general_path_skips(guard)) return;
   unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= piece_start[k]) return;
   int lo = 0, hi = k - 1;  // last c with piece_start[c] <= p
@@ -169,7 +216,9 @@ template <int NV>
 __global__ void __launch_bounds__(128)
 k_segsum(int d, const float *__restrict__ v, const int2 *__restrict__ order,
          const unsigned *__restrict__ seg_start, const unsigned *__restrict__ piece_start,
-         const int *__restrict__ piece_cent, int k, int P, float *__restrict__ psums) {
+         const int *__restrict__ piece_cent, int k, int P, float *__restrict__ psums,
+         const int *__restrict__ guard) {
+  if (general_path_skips(guard)) return;
   const unsigned p = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (p >= piece_start[k]) return;  // piece_start[k] = number of pieces
@@ -234,8 +283,195 @@ k_segsum(int d, const float *__restrict__ v, const int2 *__restrict__ order,
   }
 }
 
+// ------------------------------------------------------------------ short segments (large k)
+// When the clusters are small (n / k <= SG_AVG: BASELINE config 4 has 153 points per centroid) the
+// multi-pass radix sort above costs more than the row stream it prepares.  Instead:
+//   1. k_scatter_ids   order[cursor[c]++] = i with an integer atomic on the centroid's cursor:
+//      one pass, the points of a centroid land in its segment in ARBITRARY order;
+//   2. k_segsum_sorted one warp per centroid sorts its segment's point ids in shared memory
+//      (bitonic, <= SG_CAP ids at a time) and adds the rows in increasing point id -- the
+//      reference's order (yael/kmeans.c:278-283), so the sums equal the reference's bit for bit
+//      and do not depend on how the atomics were scheduled.  Segments longer than SG_CAP are
+//      walked in passes over id ranges that hold <= SG_CAP ids each.
+// A segment longer than SG_LIMIT (a degenerate clustering) would make that walk quadratic: the
+// kernels below then do nothing (device-side flag maxc[0], no host round trip) and the general
+// path, launched behind them with the opposite guard, does the work.
+constexpr int SG_CAP = 1024;
+constexpr int SG_WARPS = 4;
+constexpr int SG_LIMIT = kSegLimit;
+constexpr int SG_AVG = 1024;
+
+__global__ void k_max_count(const int *__restrict__ counts, int k, int *__restrict__ maxc) {
+  int m = 0;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < k; c += gridDim.x * blockDim.x) m = max(m, counts[c]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(maxc, m);
+}
+
+// seg_start[c] = cursor[c] = counts[c] (scanned afterwards); seg_start[k] = 0
+__global__ void k_seg_counts(const int *__restrict__ counts, int k, unsigned *__restrict__ seg_start) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c <= k) seg_start[c] = c < k ? (unsigned)counts[c] : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+k_scatter_ids(const int *__restrict__ assign, long n, int k, const unsigned *__restrict__ seg_start,
+              unsigned *__restrict__ cursor, int *__restrict__ order, const int *__restrict__ maxc) {
+  if (*maxc > SG_LIMIT) return;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int a = assign[i];
+    if (a >= 0 && a < k) order[seg_start[a] + atomicAdd(&cursor[a], 1u)] = (int)i;
+  }
+}
+
+// sort n_pad (power of two <= SG_CAP) ints in shared memory, one warp
+__device__ __forceinline__ void warp_bitonic_i32(int *a, int n_pad, int lane) {
+  for (int size = 2; size <= n_pad; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncwarp();
+      for (int t = lane; t < (n_pad >> 1); t += 32) {
+        const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const int x = a[lo], y = a[hi];
+        if ((x > y) == up) {
+          a[lo] = y;
+          a[hi] = x;
+        }
+      }
+    }
+  __syncwarp();
+}
+
+// acc[u][x] += rows ids[0..cnt) in list order; R rows in flight
+template <int NV, int NCH, int R>
+__device__ __forceinline__ void seg_accumulate(const float *__restrict__ v, int d, int t0, int lane,
+                                               const int *ids, int cnt, float (&acc)[NCH][NV]) {
+  constexpr int CH = 32 * NV;
+  int e = 0;
+  for (; e + R <= cnt; e += R) {
+    float val[R][NCH][NV];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const float *row = v + (size_t)ids[e + r] * d;
+#pragma unroll
+      for (int u = 0; u < NCH; u++) {
+        const int t = t0 + u * CH + lane * NV;
+        if (t < d) {
+          load_nv<NV>(row + t, val[r][u]);
+        } else {
+#pragma unroll
+          for (int x = 0; x < NV; x++) val[r][u][x] = 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++)
+#pragma unroll
+      for (int u = 0; u < NCH; u++)
+#pragma unroll
+        for (int x = 0; x < NV; x++) acc[u][x] = __fadd_rn(acc[u][x], val[r][u][x]);
+  }
+  for (; e < cnt; e++) {
+    const float *row = v + (size_t)ids[e] * d;
+#pragma unroll
+    for (int u = 0; u < NCH; u++) {
+      const int t = t0 + u * CH + lane * NV;
+      if (t < d) {
+        float x[NV];
+        load_nv<NV>(row + t, x);
+#pragma unroll
+        for (int y = 0; y < NV; y++) acc[u][y] = __fadd_rn(acc[u][y], x[y]);
+      }
+    }
+  }
+}
+
+template <int NV, int NCH>
+__global__ void __launch_bounds__(32 * SG_WARPS)
+k_segsum_sorted(int d, long n, const float *__restrict__ v, const int *__restrict__ order,
+                const unsigned *__restrict__ seg_start, int k, float *__restrict__ sums,
+                const int *__restrict__ maxc) {
+  __shared__ int ids_s[SG_WARPS][SG_CAP];
+  if (*maxc > SG_LIMIT) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * SG_WARPS + warp;
+  if (c >= k) return;
+  int *ids = ids_s[warp];
+  const unsigned first = seg_start[c], last = seg_start[c + 1];
+  const int m = (int)(last - first);
+  constexpr int CH = 32 * NV;
+  constexpr int R = NCH == 1 ? 8 : 4;
+  const unsigned lt = (1u << lane) - 1u;
+  float *out = sums + (size_t)c * d;
+  for (int t0 = 0; t0 < d; t0 += NCH * CH) {
+    float acc[NCH][NV];
+#pragma unroll
+    for (int u = 0; u < NCH; u++)
+#pragma unroll
+      for (int x = 0; x < NV; x++) acc[u][x] = 0.f;
+    if (m <= SG_CAP) {
+      if (t0 == 0) {  // the sorted ids stay in shared memory for the later column blocks
+        const int n_pad = pow2_ceil(m < 2 ? 2 : m);
+        for (int e = lane; e < n_pad; e += 32) ids[e] = e < m ? order[first + e] : 0x7fffffff;
+        warp_bitonic_i32(ids, n_pad, lane);
+      }
+      seg_accumulate<NV, NCH, R>(v, d, t0, lane, ids, m, acc);
+    } else {
+      // passes over id ranges [lo, hi) that hold at most SG_CAP of the segment's ids
+      const long passes = (m + SG_CAP / 2 - 1) / (SG_CAP / 2);
+      const long w0 = (n + passes - 1) / passes;
+      long lo = 0;
+      while (lo < n) {
+        long w = w0, hi;
+        int cnt;
+        for (;;) {
+          hi = lo + w < n ? lo + w : n;
+          cnt = 0;
+          for (unsigned e = first + lane; e < last; e += 32) {
+            const int id = order[e];
+            cnt += (id >= lo && id < hi);
+          }
+          cnt = warp_sum(cnt);
+          if (cnt <= SG_CAP) break;
+          w = (w + 1) / 2;  // ids are distinct: a range of w <= SG_CAP ids always fits
+        }
+        if (cnt > 0) {
+          int pos = 0;
+          for (unsigned e0 = first; e0 < last; e0 += 32) {
+            const int id = e0 + lane < last ? order[e0 + lane] : -1;
+            const bool in = id >= lo && id < hi;
+            const unsigned b = __ballot_sync(0xffffffffu, in);
+            if (in) ids[pos + __popc(b & lt)] = id;
+            pos += __popc(b);
+          }
+          const int n_pad = pow2_ceil(cnt < 2 ? 2 : cnt);
+          __syncwarp();
+          for (int e = cnt + lane; e < n_pad; e += 32) ids[e] = 0x7fffffff;
+          warp_bitonic_i32(ids, n_pad, lane);
+          seg_accumulate<NV, NCH, R>(v, d, t0, lane, ids, cnt, acc);
+          __syncwarp();
+        }
+        lo = hi;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < NCH; u++) {
+      const int t = t0 + u * CH + lane * NV;
+      if (t < d) {
+        if constexpr (NV == 4)
+          *reinterpret_cast<float4 *>(out + t) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+        else
+          out[t] = acc[u][0];
+      }
+    }
+  }
+}
+
 __global__ void k_combine(int d, int k, const unsigned *__restrict__ piece_start,
-                          const float *__restrict__ psums, float *__restrict__ sums) {
+                          const float *__restrict__ psums, float *__restrict__ sums,
+                          const int *__restrict__ guard) {
+  if (general_path_skips(guard)) return;
   long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long)k * d) return;
   int c = (int)(t / d), x = (int)(t - (long)c * d);
@@ -318,14 +554,19 @@ extern "C" int yb_kmeans_accumulate(int d, int n, int k, const float *v, const i
     P = (int)(p < 64 ? 64 : p > 4096 ? 4096 : p);
     if ((long)k >= target) P = 1 << 30;
   }
+  // short segments (many centroids): one-pass scatter + per-segment sort; the general path is
+  // still launched behind it, guarded on the device by the largest cluster size
+  const bool fast = n > 0 && k >= 1024 && (long)n / k <= SG_AVG && P >= (1 << 30) &&
+                    !getenv("YAEL_B200_KMEANS_GENERAL_UPDATE");
   const int nblocks = (int)(((long)n + RS_BLOCK - 1) / RS_BLOCK);
   int passes = 1;
   while (passes < 4 && ((long)k - 1) >> (8 * passes)) passes++;
   const unsigned max_pieces = (unsigned)(k + (P >= (1 << 30) ? 0 : ((long)n + P - 1) / P)) + 1;
   size_t need = 2 * Carver::need(sizeof(int2) * (size_t)(n > 0 ? n : 1)) +
                 Carver::need(4ull * 256 * (nblocks > 0 ? nblocks : 1)) +
-                2 * Carver::need(4ull * (k + 1)) + Carver::need(4ull * max_pieces) +
-                Carver::need(4ull * (size_t)max_pieces * d) + Carver::need(8 * 1024 + 64);
+                3 * Carver::need(4ull * (k + 1)) + Carver::need(4ull * max_pieces) +
+                Carver::need(4ull * (size_t)max_pieces * d) + Carver::need(8 * 1024 + 64) + Carver::need(64) +
+                (fast ? Carver::need(sizeof(int) * (size_t)n) : 0);
   ScratchScope ws(need, st);
   ProfScope ps(8, st);
   Carver c(ws.p);
@@ -334,50 +575,81 @@ extern "C" int yb_kmeans_accumulate(int d, int n, int k, const float *v, const i
   unsigned *ghist = c.take<unsigned>(256ull * (nblocks > 0 ? nblocks : 1));
   unsigned *seg_start = c.take<unsigned>(k + 1);
   unsigned *piece_start = c.take<unsigned>(k + 1);
+  unsigned *cursor = c.take<unsigned>(k + 1);
   int *piece_cent = c.take<int>(max_pieces);
   float *psums = c.take<float>((size_t)max_pieces * d);
   double *part = c.take<double>(1024 + 8);
+  int *maxc = c.take<int>(16);
+  int *forder = fast ? c.take<int>(n) : nullptr;  // the short-segment path's id list
 
   YB_CUDA(cudaMemsetAsync(nassign, 0, sizeof(int) * (size_t)k, st));
+  const bool vec = (d % 4 == 0) && ((((uintptr_t)v) & 15) == 0);
+  const int *guard = nullptr;
   if (n > 0) {
     k_hist<<<4 * sm_count(), 256, 0, st>>>(assign, n, k, nassign);
     YB_LAUNCH_CHECK();
+  }
+  if (fast) {
+    int *order = forder;
+    YB_CUDA(cudaMemsetAsync(maxc, 0, 64, st));
+    YB_CUDA(cudaMemsetAsync(cursor, 0, 4ull * (k + 1), st));
+    k_max_count<<<(k + 1023) / 1024 < 64 ? (k + 1023) / 1024 : 64, 1024, 0, st>>>(nassign, k, maxc);
+    YB_LAUNCH_CHECK();
+    k_seg_counts<<<(k + 1 + 255) / 256, 256, 0, st>>>(nassign, k, seg_start);
+    YB_LAUNCH_CHECK();
+    k_scan_u32<<<1, 1024, 0, st>>>(seg_start, k + 1, nullptr);
+    YB_LAUNCH_CHECK();
+    k_scatter_ids<<<8 * sm_count(), 256, 0, st>>>(assign, n, k, seg_start, cursor, order, maxc);
+    YB_LAUNCH_CHECK();
+    const unsigned grid = (unsigned)((k + SG_WARPS - 1) / SG_WARPS);
+    if (vec && d <= 128)
+      k_segsum_sorted<4, 1><<<grid, 32 * SG_WARPS, 0, st>>>(d, n, v, order, seg_start, k, sums, maxc);
+    else if (vec)
+      k_segsum_sorted<4, 4><<<grid, 32 * SG_WARPS, 0, st>>>(d, n, v, order, seg_start, k, sums, maxc);
+    else
+      k_segsum_sorted<1, 4><<<grid, 32 * SG_WARPS, 0, st>>>(d, n, v, order, seg_start, k, sums, maxc);
+    YB_LAUNCH_CHECK();
+    guard = maxc;  // the general path below runs only if a cluster exceeded SG_LIMIT
+  }
+  if (n > 0) {
     const int2 *in = nullptr;
     int2 *out = bufA;
     for (int p = 0; p < passes; p++) {
-      k_rs_hist<<<nblocks, RS_T, 0, st>>>(assign, in, n, 8 * p, nblocks, ghist);
+      k_rs_hist<<<nblocks, RS_T, 0, st>>>(assign, in, n, 8 * p, nblocks, ghist, guard);
       YB_LAUNCH_CHECK();
-      k_scan_u32<<<1, 1024, 0, st>>>(ghist, 256L * nblocks);
+      k_scan_u32<<<1, 1024, 0, st>>>(ghist, 256L * nblocks, guard);
       YB_LAUNCH_CHECK();
-      k_rs_scatter<<<nblocks, RS_T, 0, st>>>(assign, in, n, 8 * p, nblocks, ghist, out);
+      k_rs_scatter<<<nblocks, RS_T, 0, st>>>(assign, in, n, 8 * p, nblocks, ghist, out, guard);
       YB_LAUNCH_CHECK();
       in = out;
       out = (out == bufA) ? bufB : bufA;
     }
     const int2 *order = in;
-    k_piece_counts<<<(k + 1 + 255) / 256, 256, 0, st>>>(nassign, k, P, seg_start, piece_start);
+    // (the general path gets its own segment offsets: the short-segment kernels may be reading
+    // seg_start while these are enqueued)
+    unsigned *gseg = fast ? cursor : seg_start;
+    k_piece_counts<<<(k + 1 + 255) / 256, 256, 0, st>>>(nassign, k, P, gseg, piece_start, guard);
     YB_LAUNCH_CHECK();
-    k_scan_u32<<<1, 1024, 0, st>>>(seg_start, k + 1);
+    k_scan_u32<<<1, 1024, 0, st>>>(gseg, k + 1, guard);
     YB_LAUNCH_CHECK();
-    k_scan_u32<<<1, 1024, 0, st>>>(piece_start, k + 1);
+    k_scan_u32<<<1, 1024, 0, st>>>(piece_start, k + 1, guard);
     YB_LAUNCH_CHECK();
     // the number of pieces is data dependent (piece_start[k]); launch for the upper bound,
     // surplus threads / warps exit
-    k_piece_map<<<(max_pieces + 255) / 256, 256, 0, st>>>(piece_start, k, piece_cent);
+    k_piece_map<<<(max_pieces + 255) / 256, 256, 0, st>>>(piece_start, k, piece_cent, guard);
     YB_LAUNCH_CHECK();
-    bool vec = (d % 4 == 0) && ((((uintptr_t)v) & 15) == 0);
     if (vec)
-      k_segsum<4><<<(max_pieces + 3) / 4, 128, 0, st>>>(d, v, order, seg_start, piece_start,
-                                                       piece_cent, k, P, psums);
+      k_segsum<4><<<(max_pieces + 3) / 4, 128, 0, st>>>(d, v, order, gseg, piece_start, piece_cent, k, P,
+                                                       psums, guard);
     else
-      k_segsum<1><<<(max_pieces + 3) / 4, 128, 0, st>>>(d, v, order, seg_start, piece_start,
-                                                       piece_cent, k, P, psums);
+      k_segsum<1><<<(max_pieces + 3) / 4, 128, 0, st>>>(d, v, order, gseg, piece_start, piece_cent, k, P,
+                                                       psums, guard);
     YB_LAUNCH_CHECK();
   } else {
     YB_CUDA(cudaMemsetAsync(piece_start, 0, 4ull * (k + 1), st));
   }
   long tot = (long)k * d;
-  k_combine<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d, k, piece_start, psums, sums);
+  k_combine<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d, k, piece_start, psums, sums, guard);
   YB_LAUNCH_CHECK();
   if (qerr) {
     k_sum_dis_partial<<<1024, 256, 0, st>>>(dis, n, part);

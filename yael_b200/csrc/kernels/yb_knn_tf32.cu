@@ -57,7 +57,18 @@ constexpr int EPI_TEAMS = YB_EPI_TEAMS;
 constexpr int TEAM_WARPS = 8;
 constexpr int EPI_WARPS = TEAM_WARPS * EPI_TEAMS;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int TF32_THREADS = EPI_THREADS + 64;
+// 8 epilogue warps (two warpgroups) + one warpgroup holding the TMA producer, the MMA issuer and two
+// idle warps: whole warpgroups, so that setmaxnreg can move registers from the third group (56 per
+// thread are plenty for the two single-lane loops) to the epilogue warps (224 per thread instead of
+// the 168 a 384-thread block gets statically: room for wider TMEM loads without spills)
+constexpr int TF32_THREADS = EPI_THREADS + 128;
+constexpr int REGS_EPI = 224, REGS_AUX = 56;
+__device__ __forceinline__ void regs_epilogue() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+}
+__device__ __forceinline__ void regs_aux() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
+}
 constexpr int HALF_N = TN / 2;   // columns per epilogue warp and tile
 
 struct Smem {  // offsets inside the 1024-byte aligned dynamic shared memory block
@@ -102,6 +113,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "{\n\t"
         ".reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// the same with mbarrier.test_wait (pure spinning, no hardware suspend): bring-up comparison
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}"
         : "=r"(done)
@@ -267,6 +293,21 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 64 consecutive 32-bit columns -> 64 registers per thread
+__device__ __forceinline__ void tc_ld64(uint32_t taddr, uint32_t (&v)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+      : "r"(taddr)
+      : "memory");
+}
+template <int W>
+__device__ __forceinline__ void tc_ldw(uint32_t taddr, uint32_t (&v)[W]) {
+  if constexpr (W == 16) tc_ld16(taddr, v);
+  else if constexpr (W == 32) tc_ld32(taddr, v);
+  else tc_ld64(taddr, v);
+}
 __device__ __forceinline__ void tc_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -317,6 +358,12 @@ __device__ __forceinline__ void tc_mma_elect(uint32_t d_tmem, uint64_t a_desc, u
   else
     tc_mma_tf32_elect(d_tmem, a_desc, b_desc, IDESC_TF32, accumulate);
 }
+
+// bring-up instrumentation (YAEL_B200_TF32_DEBUG bit 512): clock64() deltas of one epilogue warp and
+// of the MMA issuer per CTA: [0] issuer waits for a free accumulator, [1] for operand stages, [2]
+// for the extras, [3] issuer total, [4] epilogue warp 0 waits for an accumulator, [5] drains it,
+// [6] hands it back, [7] epilogue total, [8] tiles
+__device__ long long g_tf32_clk[160][16];
 
 // ------------------------------------------------------------------ parameters
 struct Tf32Params {
@@ -594,6 +641,43 @@ __device__ __forceinline__ void process_group_nf(const uint32_t (&v)[16], float 
   }
 }
 
+// W = 32 or 64 accumulator columns of one query (folded norms): ONE threshold test for the whole
+// load, the 16-column groups are only looked at when it fires.  Every tcgen05.ld + wait::ld round
+// trip costs a warp ~230 cycles however many columns it brings (8 epilogue warps contend for the
+// TMEM read port), so a 128-column half tile is drained in 4 (W = 32) or 2 (W = 64) round trips
+// instead of 8.
+template <bool K1, int W>
+__device__ __forceinline__ void process_wide_nf(const uint32_t (&v)[W], float &thr, float &thrp,
+                                                float &best, float margin, float2 *mylist, int &cnt,
+                                                int cap, int id0, float asc, float inv_asc) {
+  float gm[W / 16];
+#pragma unroll
+  for (int s = 0; s < W / 16; s++) gm[s] = group_max16(reinterpret_cast<const uint32_t(&)[16]>(v[16 * s]));
+  float M = gm[0];
+#pragma unroll
+  for (int s = 1; s < W / 16; s++) M = fmaxf(M, gm[s]);
+  if (M > thrp) {
+#pragma unroll
+    for (int s = 0; s < W / 16; s++) {
+      if (gm[s] > thrp) {
+        float sc[16];
+#pragma unroll
+        for (int c = 0; c < 16; c++) sc[c] = __fmul_rn(asc, __uint_as_float(v[16 * s + c]));
+        if (K1) {
+          K1State st = {thr, best, cnt};
+          st = slow_append_k1(YB_SC16_ARGS(sc), __fmul_rn(asc, gm[s]), st, margin, mylist, cap, id0 + 16 * s);
+          thr = st.thr;
+          best = st.best;
+          cnt = st.cnt;
+          thrp = __fmul_rn(thr, inv_asc);
+        } else {
+          cnt = slow_append(YB_SC16_ARGS(sc), thr, mylist, cnt, id0 + 16 * s);
+        }
+      }
+    }
+  }
+}
+
 // smallest score of 16 accumulator columns (sampling pass)
 __device__ __forceinline__ float group_min16(const uint32_t (&v)[16], const float *bn, float asc) {
   float sc[16];
@@ -696,9 +780,13 @@ struct EpiCtx {
   int n_full0, n_empty0, t_full0;  // barrier indices (the two kernels have different ring depths)
 };
 
+// arrive on a barrier of ANOTHER CTA of the cluster (shared::cluster address from mapa).  Default
+// semantics (release at CTA scope), as CUTLASS' ClusterBarrier::arrive(cta_id) does: what has to be
+// ordered here are tcgen05 operations, which the tcgen05.fence pair around the barrier orders; an
+// explicit .release.cluster made every hand-back cost ~1200 cycles (measured with the clock
+// attribution of YAEL_B200_TF32_DEBUG bit 512).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
-               : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 // MODE selects what the epilogue does with a tile (one kernel instantiation per mode: the hot
@@ -706,7 +794,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 // mode branches)
 enum : int { EPI_LISTS = 0, EPI_NEAREST = 1, EPI_DUMP = 2, EPI_GMIN = 3, EPI_HAMP = 4, EPI_HAMG = 5 };
 
-template <int MODE, int KIND>
+template <int MODE, int KIND, int LDW>
 __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &E) {
   constexpr bool NF = KIND == OP_F16N;  // |b|^2 folded into the contraction
   unsigned char *smem = E.smem;
@@ -727,6 +815,8 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
     const float inv_asc = 1.0f / asc;  // exact: asc is a power of two
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * HALF_N;
     uint32_t tcount = 0;
+    const bool clk_on = (P.debug & 512) && warp == 0;
+    long long ck_wait = 0, ck_work = 0, ck_back = 0, ck_t0 = clk_on ? clock64() : 0, ck_a = 0, ck_b = 0;
     for (int item = first_item; item < P.items; item += item_step) {
       const int sp = P.order ? item % P.splits : item / tq_div;
       const int qi = P.order ? item / P.splits : item - sp * tq_div;
@@ -746,9 +836,16 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
       for (int jt = jt0; jt < jt1; jt++, tcount++) {
         const uint32_t buf = tcount & 1, slot = tcount % NBN;
         if (EPI_TEAMS > 1 && (int)buf != team) continue;  // the other team's accumulator buffer
-        mbar_wait(bar(E.n_full0 + slot), (tcount / NBN) & 1);
-        mbar_wait(bar(E.t_full0 + buf), (tcount >> 1) & 1);
+        bool handed_back = false;
+        if (clk_on) ck_a = clock64();
+        if (!NF) mbar_wait(bar(E.n_full0 + slot), (tcount / NBN) & 1);  // folded norms: no |b|^2 tiles
+        if (P.debug & 256) mbar_wait_spin(bar(E.t_full0 + buf), (tcount >> 1) & 1);
+        else mbar_wait(bar(E.t_full0 + buf), (tcount >> 1) & 1);
         tc_fence_after();
+        if (clk_on) {
+          ck_b = clock64();
+          ck_wait += ck_b - ck_a;
+        }
         const float *bn = (const float *)(smem + Smem::bn_off + slot * TN * 4) + half * HALF_N;
         const int n0 = jt * P.tile_stride * TN + half * HALF_N + P.id0;
         if (MODE == EPI_DUMP) {
@@ -847,6 +944,67 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
             process_group_ham(vb, P.ham_magic, tau3, ham_mask, P.ham_slots, mylist, cnt,
                               r0 + (gg * 32 + 16) * P.ham_slots, P.ham_nb);
           }
+        } else if (NF && LDW == 128 && (MODE == EPI_LISTS || MODE == EPI_NEAREST)) {
+          // The whole half tile (128 accumulators per thread) is pulled into registers with two
+          // 64-column loads and ONE wait, the accumulator buffer is handed back to the MMA issuer
+          // AT ONCE, and only then are the values looked at: the threshold tests overlap the MMAs
+          // of the tile after next instead of sitting inside the buffer's ping-pong cycle
+          // (MMA -> commit -> drain -> hand back -> MMA: with two buffers a tile costs half of
+          // that cycle, and the hand-shake latencies alone are ~1350 of its ~3900 cycles).
+          constexpr bool K1W = MODE == EPI_NEAREST;
+          uint32_t va[64], vb[64];
+          const uint32_t ta = lane_addr + buf * TN;
+          tc_ldw<64>(ta, va);
+          tc_ldw<64>(ta + 64, vb);
+          tc_wait_ld();
+          if (clk_on) {
+            ck_a = clock64();
+            ck_work += ck_a - ck_b;
+            ck_b = ck_a;
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t te = buf ? E.t_empty_addr1 : E.t_empty_addr0;
+            if (E.t_empty_remote)
+              mbar_arrive_cluster(te);
+            else
+              mbar_arrive(te);
+          }
+          handed_back = true;
+          if (!(P.debug & 1)) {
+            process_wide_nf<K1W, 64>(va, thr, thrp, best, margin, mylist, cnt, P.cap, n0, asc, inv_asc);
+            process_wide_nf<K1W, 64>(vb, thr, thrp, best, margin, mylist, cnt, P.cap, n0 + 64, asc, inv_asc);
+          }
+        } else if (NF && LDW > 16 && (MODE == EPI_LISTS || MODE == EPI_NEAREST)) {
+          // HALF_N / LDW wide loads, load g+1 in flight while g is processed
+          constexpr int LW = (LDW == 32 || LDW == 64) ? LDW : 32;  // (LDW = 128 never gets here)
+          if (P.debug & 4) {  // bring-up: TMEM traffic only, LDW columns per load
+            uint32_t va[LW];
+            const uint32_t ta = lane_addr + buf * TN;
+#pragma unroll 1
+            for (int g = 0; g < HALF_N / LW; g++) {
+              tc_ldw<LW>(ta + g * LW, va);
+              tc_wait_ld();
+            }
+          } else if (!(P.debug & 1)) {
+            constexpr int NG = HALF_N / LW;
+            constexpr bool K1W = MODE == EPI_NEAREST;
+            uint32_t va[LW], vb[LW];
+            const uint32_t ta = lane_addr + buf * TN;
+            tc_ldw<LW>(ta, va);
+#pragma unroll 1
+            for (int g = 0; g < NG; g += 2) {
+              tc_wait_ld();
+              tc_ldw<LW>(ta + (g + 1) * LW, vb);
+              process_wide_nf<K1W, LW>(va, thr, thrp, best, margin, mylist, cnt, P.cap, n0 + g * LW, asc,
+                                        inv_asc);
+              tc_wait_ld();
+              if (g + 2 < NG) tc_ldw<LW>(ta + (g + 2) * LW, va);
+              process_wide_nf<K1W, LW>(vb, thr, thrp, best, margin, mylist, cnt, P.cap, n0 + (g + 1) * LW,
+                                        asc, inv_asc);
+            }
+          }
         } else if (!(P.debug & 1)) {
           // 8 groups of 16 columns, the TMEM load of group g+1 in flight while g is processed
           uint32_t va[16], vb[16];
@@ -893,15 +1051,21 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
         }
         // accumulator buffer and |b|^2 slot are free again: ONE arrival per warp (256 per-thread
         // arrivals on the same barrier word serialise and cost more than the tile's math)
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          const uint32_t te = buf ? E.t_empty_addr1 : E.t_empty_addr0;
-          if (E.t_empty_remote)
-            mbar_arrive_cluster(te);
-          else
-            mbar_arrive(te);
-          mbar_arrive(bar(E.n_empty0 + slot));
+        if (clk_on) {
+          ck_a = clock64();
+          ck_work += ck_a - ck_b;
+        }
+        if (!handed_back) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t te = buf ? E.t_empty_addr1 : E.t_empty_addr0;
+            if (E.t_empty_remote)
+              mbar_arrive_cluster(te);
+            else
+              mbar_arrive(te);
+            if (!NF) mbar_arrive(bar(E.n_empty0 + slot));
+          }
         }
         // keep room for a full half tile of appends in every list of the warp
         // (a packed Hamming tile can append ham_slots entries per column)
@@ -921,6 +1085,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
         }
         if (MODE == EPI_HAMP) tau3 = ham_tau3(thr);
         if (NF) thrp = __fmul_rn(thr, inv_asc);
+        if (clk_on) ck_back += clock64() - ck_a;
       }
       if (MODE == EPI_NEAREST) {
         // k = 1: publish the candidates within the margin of the final best score
@@ -987,11 +1152,18 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
         }
       }
     }
+    if (clk_on && lane == 0 && blockIdx.x < 160) {
+      g_tf32_clk[blockIdx.x][4] = ck_wait;
+      g_tf32_clk[blockIdx.x][5] = ck_work;
+      g_tf32_clk[blockIdx.x][6] = ck_back;
+      g_tf32_clk[blockIdx.x][7] = clock64() - ck_t0;
+      g_tf32_clk[blockIdx.x][8] = tcount;
+    }
   }
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int MODE, int KIND>
+template <int MODE, int KIND, int LDW>
 __global__ void __launch_bounds__(TF32_THREADS, 1)
 k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_b,
            const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_qx,
@@ -1058,6 +1230,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 
   if (warp == EPI_WARPS) {
     // ======================================================================== TMA producer
+    regs_aux();
     constexpr int KCE = KIND == OP_F8 ? KC * 4 : ((KIND == OP_F16 || KIND == OP_F16N) ? KC * 2 : KC);  // elements per 128-byte K chunk (TMA coordinates)
     if (lane == 0) {
       uint32_t icount = 0, ccount = 0, tcount = 0;
@@ -1078,12 +1251,15 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
           tma_load_2d(sbase + Smem::a_off + (xk < 0 ? 0 : xk) * A_CHUNK_BYTES, &map_qx, bar(Smem::a_full), P.xcol,
                       qt * TM);
         for (int jt = jt0; jt < jt1; jt++, tcount++) {
-          const uint32_t slot = tcount % NBN;
-          mbar_wait(bar(Smem::n_empty + slot), ((tcount / NBN) & 1) ^ 1);
-          mbar_expect_tx(bar(Smem::n_full + slot), TN * 4);
           const int jta = jt * P.tile_stride;  // actual database tile
-          bulk_load_1d(sbase + Smem::bn_off + slot * TN * 4, P.bnorm + (size_t)jta * TN, TN * 4,
-                       bar(Smem::n_full + slot));
+          if (!NFK) {  // |b|^2 of the tile (the folded-norm kinds carry it in the operands)
+            const uint32_t slot = tcount % NBN;
+            mbar_wait(bar(Smem::n_empty + slot), ((tcount / NBN) & 1) ^ 1);
+            mbar_expect_tx(bar(Smem::n_full + slot), TN * 4);
+            bulk_load_1d(sbase + Smem::bn_off + slot * TN * 4, P.bnorm + (size_t)jta * TN, TN * 4,
+                         bar(Smem::n_full + slot));
+          }
+          if (P.debug & 64) continue;  // bring-up: no operand rings at all (with 16: MMAs on stale data)
           if (xring) {  // extras of this tile: own 2-slot ring
             const uint32_t xs = tcount & 1;
             mbar_wait(bar(Smem::x_empty + xs), ((tcount >> 1) & 1) ^ 1);
@@ -1122,18 +1298,24 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
   } else if (warp == EPI_WARPS + 1) {
     // ======================================================================== MMA issuer
     // every lane walks the loop; elect.sync inside the tcgen05 wrappers picks the issuing lane
+    regs_aux();
     {
       uint32_t icount = 0, ccount = 0, tcount = 0;
       const bool skip_mma = (P.debug & 2) != 0;
       const bool ring_aligned = P.nkc == STAGES && P.last_k8 == 4 && xk < 0;
+      const bool clk_on = (P.debug & 512) != 0;
+      long long ck_acc = 0, ck_ops = 0, ck_x = 0, ck_t0 = clk_on ? clock64() : 0, ck_a = 0;
       for (int item = first_item; item < P.items; item += item_step, icount++) {
         const int sp = P.order ? item % P.splits : item / tq_div;
         const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
         mbar_wait(bar(Smem::a_full), icount & 1);
         for (int jt = jt0; jt < jt1; jt++, tcount++) {
           const uint32_t buf = tcount & 1;
-          mbar_wait(bar(Smem::t_empty + buf), ((tcount >> 1) & 1) ^ 1);
+          if (clk_on) ck_a = clock64();
+          if (P.debug & 256) mbar_wait_spin(bar(Smem::t_empty + buf), ((tcount >> 1) & 1) ^ 1);
+          else mbar_wait(bar(Smem::t_empty + buf), ((tcount >> 1) & 1) ^ 1);
           tc_fence_after();
+          if (clk_on) ck_acc += clock64() - ck_a;
           const uint32_t d_tmem = tmem_base + buf * TN;
           if (ring_aligned && !skip_mma) {
             // d = 128 (K chunks == ring depth): chunk kc always sits in stage kc, so every
@@ -1157,8 +1339,10 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
           } else
           for (int kc = 0; kc < (xring ? xk : P.nkc); kc++, ccount++) {
             const uint32_t st = ccount % STAGES;
-            mbar_wait(bar(Smem::b_full + st), (ccount / STAGES) & 1);
+            if (clk_on) ck_a = clock64();
+            if (!(P.debug & 64)) mbar_wait(bar(Smem::b_full + st), (ccount / STAGES) & 1);
             tc_fence_after();
+            if (clk_on) ck_ops += clock64() - ck_a;
             const uint64_t adesc = smem_desc_sw128(sbase + Smem::a_off + kc * A_CHUNK_BYTES);
             const uint64_t bdesc = smem_desc_sw128(sbase + Smem::b_off + st * B_CHUNK_BYTES);
             // advancing K inside the 128-byte swizzle span: +32 bytes = +2 in 16-byte units
@@ -1169,10 +1353,13 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
             } else if (!skip_mma) {
               const int last_data = (xk >= 0 ? xk : P.nkc) - 1;
               if (kc != last_data || P.last_k8 == 4) {
-                tc_mma_elect<KIND>(d_tmem, adesc, bdesc, kc != 0);
-                tc_mma_elect<KIND>(d_tmem, adesc + 2, bdesc + 2, 1);
-                tc_mma_elect<KIND>(d_tmem, adesc + 4, bdesc + 4, 1);
-                tc_mma_elect<KIND>(d_tmem, adesc + 6, bdesc + 6, 1);
+                const int reps = (P.debug & 32) ? 4 : 1;  // bring-up: marginal cost of an MMA
+                for (int rep = 0; rep < reps; rep++) {
+                  tc_mma_elect<KIND>(d_tmem, adesc, bdesc, kc != 0);
+                  tc_mma_elect<KIND>(d_tmem, adesc + 2, bdesc + 2, 1);
+                  tc_mma_elect<KIND>(d_tmem, adesc + 4, bdesc + 4, 1);
+                  tc_mma_elect<KIND>(d_tmem, adesc + 6, bdesc + 6, 1);
+                }
               } else {
                 for (int k8 = 0; k8 < P.last_k8; k8++)
                   tc_mma_elect<KIND>(d_tmem, adesc + (uint64_t)(2 * k8), bdesc + (uint64_t)(2 * k8),
@@ -1181,6 +1368,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
             }
             // smem slot reusable once these MMAs retire (paired: tell both CTAs, either may
             // multicast into the slot next)
+            if (P.debug & 64) continue;
             if (P.pair)
               tc_commit_mc_elect(bar(Smem::b_empty + st), (uint16_t)3);
             else
@@ -1188,20 +1376,36 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
           }
           if (xring) {  // the norm term: one MMA over the 16 extra K elements
             const uint32_t xs = tcount & 1;
-            mbar_wait(bar(Smem::x_full + xs), (tcount >> 1) & 1);
+            if (clk_on) ck_a = clock64();
+            if (!(P.debug & 64)) mbar_wait(bar(Smem::x_full + xs), (tcount >> 1) & 1);
             tc_fence_after();
+            if (clk_on) ck_x += clock64() - ck_a;
             if (!skip_mma)
               tc_mma_elect<KIND>(d_tmem, smem_desc_sw32(sbase + Smem::a_off + (xk < 0 ? 0 : xk) * A_CHUNK_BYTES),
                                  smem_desc_sw32(sbase + Smem::xb_off + xs * Smem::XB_BYTES), 1);
-            tc_commit_elect(bar(Smem::x_empty + xs));
+            if (!(P.debug & 64)) tc_commit_elect(bar(Smem::x_empty + xs));
           }
-          tc_commit_elect(bar(Smem::t_full + buf));  // accumulator complete
+          if (P.debug & 128) {  // bring-up (skeleton only): plain arrive instead of the commit
+            if (lane == 0) mbar_arrive(bar(Smem::t_full + buf));
+            __syncwarp();
+          } else {
+            tc_commit_elect(bar(Smem::t_full + buf));  // accumulator complete
+          }
         }
         tc_commit_elect(bar(Smem::a_empty));  // query tile no longer needed
       }
+      if (clk_on && lane == 0 && blockIdx.x < 160) {
+        g_tf32_clk[blockIdx.x][0] = ck_acc;
+        g_tf32_clk[blockIdx.x][1] = ck_ops;
+        g_tf32_clk[blockIdx.x][2] = ck_x;
+        g_tf32_clk[blockIdx.x][3] = clock64() - ck_t0;
+      }
     }
+  } else if (warp < EPI_WARPS) {
+    regs_epilogue();
+    run_epilogue<MODE, KIND, LDW>(P, ectx);
   } else {
-    run_epilogue<MODE, KIND>(P, ectx);
+    regs_aux();  // the two idle warps of the third warpgroup
   }
 
   tc_fence_before();
@@ -1210,6 +1414,264 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
   if (warp == EPI_WARPS + 1) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------ the 2-SM kernel (folded-norm FP16)
+// Same roles and the same epilogue as k_knn_tf32<MODE, OP_F16N>, but the two CTAs of a cluster form
+// ONE MMA unit: tcgen05.mma.cta_group::2, M = 256 (each CTA's 128 queries) x N = 256, with HALF of
+// every database chunk (128 rows) in each CTA's shared memory.  Why: a single-CTA SS-mode MMA reads
+// 4 KB of A and 8 KB of B from shared memory per 128-cycle instruction while TMA writes the next
+// 8 KB -- every database byte is written once and read once per tile, 144 KB + 36 KB of A per
+// 1152-cycle tile, i.e. MORE than the 128 B/clk a shared memory delivers: with the folded-norm
+// epilogue out of the way the 1-SM pass is paced by exactly that (bring-up switch 1, "TMA + MMA
+// only": 2.23 of the 2.60 ms).  As a pair each SM holds, writes and reads only its half of B:
+// 36 (A) + 36 (B reads) + 36 (B writes) KB per tile, 94 B/clk.
+//   * only the leader CTA (cluster rank 0) issues MMAs; it waits on ITS full barriers, which both
+//     CTAs' TMA loads complete (cta_group::2 loads can signal the leader's barrier)
+//   * tcgen05.commit.cta_group::2 ... multicast releases the smem slots / publishes the
+//     accumulators in both CTAs
+//   * the peer's epilogue warps signal "accumulator drained" on the leader's barrier
+constexpr int STAGES2 = 8;
+constexpr int B2_CHUNK_BYTES = (TN / 2) * KC * 4;  // 16 KB: this CTA's half of a 128-byte-wide chunk
+constexpr int XB2_BYTES = (TN / 2) * 32;           // this CTA's half of the extras chunk
+struct Smem2 {
+  static constexpr int a_off = 0;
+  static constexpr int b_off = MAX_NKC * A_CHUNK_BYTES;
+  static constexpr int bn_off = b_off + STAGES2 * B2_CHUNK_BYTES;
+  static constexpr int hist_off = bn_off + NBN * TN * 4;
+  static constexpr int bar_off = hist_off + EPI_WARPS * 256 * 4;
+  static constexpr int a_full = 0, a_empty = 1, b_full = 2, b_empty = b_full + STAGES2,
+                       n_full = b_empty + STAGES2, n_empty = n_full + NBN,
+                       t_full = n_empty + NBN, t_empty = t_full + 2, x_full = t_empty + 2,
+                       x_empty = x_full + 2, nbar = x_empty + 2;
+  static constexpr int xb_off = a_off + 3 * A_CHUNK_BYTES;  // 2-slot extras ring (as Smem::xb_off)
+  static constexpr int tmem_ptr_off = bar_off + nbar * 8;
+  static constexpr int total = tmem_ptr_off + 16;
+};
+static_assert(Smem2::bn_off == Smem::bn_off && Smem2::hist_off == Smem::hist_off,
+              "run_epilogue() addresses |b|^2 tiles and histograms through Smem::");
+static_assert(Smem2::bar_off == Smem::bar_off, "barrier block must sit at the same offset");
+constexpr int TF32_SMEM2_BYTES = Smem2::total;
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
+
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *map,
+                                                uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm_elect(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+      "}" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2sm_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                     uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D=F32, A=B=F16, K-major, N=256, M=256 (two CTAs x 128)
+constexpr uint32_t IDESC_F16_2SM = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+template <int MODE, int LDW>
+__global__ void __launch_bounds__(TF32_THREADS, 1)
+k_knn_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_bh,
+          const __grid_constant__ CUtensorMap map_qx, const __grid_constant__ CUtensorMap map_bxh,
+          const Tf32Params P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto bar = [&](int i) { return sbase + Smem2::bar_off + 8 * i; };
+  volatile uint32_t *tmem_ptr_smem = (volatile uint32_t *)(smem + Smem2::tmem_ptr_off);
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int xk = P.xk;                 // index of the extras chunk (-1: the extras sit inside the last data chunk)
+  const bool xring = P.xring != 0;     // extras travel through their own 2-slot ring
+  constexpr int KCE = KC * 2;          // halfs per 128-byte K chunk
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(Smem2::a_full), 1);
+    mbar_init(bar(Smem2::a_empty), 1);
+    for (int i = 0; i < STAGES2; i++) {
+      mbar_init(bar(Smem2::b_full + i), 1);
+      mbar_init(bar(Smem2::b_empty + i), 1);
+    }
+    for (int i = 0; i < NBN; i++) {
+      mbar_init(bar(Smem2::n_full + i), 1);
+      mbar_init(bar(Smem2::n_empty + i), TEAM_WARPS);
+    }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(bar(Smem2::x_full + i), 1);
+      mbar_init(bar(Smem2::x_empty + i), 1);
+      mbar_init(bar(Smem2::t_full + i), 1);
+      mbar_init(bar(Smem2::t_empty + i), 2 * TEAM_WARPS);  // both CTAs' epilogue warps (leader's copy is used)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == EPI_WARPS + 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     sbase + Smem2::tmem_ptr_off),
+                 "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated in both
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int first_item = (int)(blockIdx.x >> 1), item_step = (int)(gridDim.x >> 1);
+  const int tq_div = P.tiles_q2;
+  const int nkd = xk >= 0 ? xk : P.nkc;        // 128-byte data chunks per row
+  const int nring = xring ? xk : P.nkc;        // chunks of a tile that travel through the B ring
+
+  if (warp == EPI_WARPS) {
+    // ======================================================================== TMA producer
+    regs_aux();
+    if (lane == 0) {
+      uint32_t icount = 0, ccount = 0, tcount = 0;
+      for (int item = first_item; item < P.items; item += item_step, icount++) {
+        const int sp = item / tq_div;
+        const int qt = (item - sp * tq_div) * 2 + (int)crank;
+        const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
+        mbar_wait(bar(Smem2::a_empty), (icount & 1) ^ 1);
+        if (leader)  // the leader's barrier collects the bytes of BOTH CTAs
+          mbar_expect_tx(bar(Smem2::a_full), (uint32_t)(2 * (nkd * A_CHUNK_BYTES + (xk >= 0 ? TM * 32 : 0))));
+        for (int kc = 0; kc < nkd; kc++)
+          tma_load_2d_2sm(sbase + Smem2::a_off + kc * A_CHUNK_BYTES, &map_q,
+                          bar(Smem2::a_full) & PEER_BIT_MASK, kc * KCE, qt * TM);
+        if (xk >= 0)
+          tma_load_2d_2sm(sbase + Smem2::a_off + xk * A_CHUNK_BYTES, &map_qx,
+                          bar(Smem2::a_full) & PEER_BIT_MASK, P.xcol, qt * TM);
+        for (int jt = jt0; jt < jt1; jt++, tcount++) {
+          const int jta = jt * P.tile_stride;  // (no |b|^2 tiles: the operands carry the norms)
+          const int row0 = jta * TN + (int)crank * (TN / 2);  // this CTA's half of the tile
+          if (xring) {
+            const uint32_t xs = tcount & 1;
+            mbar_wait(bar(Smem2::x_empty + xs), ((tcount >> 1) & 1) ^ 1);
+            if (leader) mbar_expect_tx(bar(Smem2::x_full + xs), 2 * XB2_BYTES);
+            tma_load_2d_2sm(sbase + Smem2::xb_off + xs * XB2_BYTES, &map_bxh,
+                            bar(Smem2::x_full + xs) & PEER_BIT_MASK, P.xcol, row0);
+          }
+          for (int kc = 0; kc < nring; kc++, ccount++) {
+            const uint32_t st = ccount % STAGES2;
+            mbar_wait(bar(Smem2::b_empty + st), ((ccount / STAGES2) & 1) ^ 1);
+            if (kc == xk) {  // the 16 extra K elements as a 32-byte-wide box in a ring stage
+              if (leader) mbar_expect_tx(bar(Smem2::b_full + st), 2 * XB2_BYTES);
+              tma_load_2d_2sm(sbase + Smem2::b_off + st * B2_CHUNK_BYTES, &map_bxh,
+                              bar(Smem2::b_full + st) & PEER_BIT_MASK, P.xcol, row0);
+              continue;
+            }
+            if (leader) mbar_expect_tx(bar(Smem2::b_full + st), 2 * B2_CHUNK_BYTES);
+            tma_load_2d_2sm(sbase + Smem2::b_off + st * B2_CHUNK_BYTES, &map_bh,
+                            bar(Smem2::b_full + st) & PEER_BIT_MASK, kc * KCE, row0);
+          }
+        }
+      }
+    }
+  } else if (warp == EPI_WARPS + 1) {
+    // ======================================================================== MMA issuer (leader CTA)
+    regs_aux();
+    if (leader) {
+      uint32_t icount = 0, ccount = 0, tcount = 0;
+      const int last_data = nkd - 1;
+      const bool clk_on = (P.debug & 512) != 0;
+      long long ck_acc = 0, ck_ops = 0, ck_x = 0, ck_t0 = clk_on ? clock64() : 0, ck_a = 0;
+      for (int item = first_item; item < P.items; item += item_step, icount++) {
+        const int sp = item / tq_div;
+        const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
+        mbar_wait(bar(Smem2::a_full), icount & 1);
+        for (int jt = jt0; jt < jt1; jt++, tcount++) {
+          const uint32_t buf = tcount & 1;
+          if (clk_on) ck_a = clock64();
+          mbar_wait(bar(Smem2::t_empty + buf), ((tcount >> 1) & 1) ^ 1);
+          tc_fence_after();
+          if (clk_on) ck_acc += clock64() - ck_a;
+          const uint32_t d_tmem = tmem_base + buf * TN;
+          for (int kc = 0; kc < nring; kc++, ccount++) {
+            const uint32_t st = ccount % STAGES2;
+            if (clk_on) ck_a = clock64();
+            mbar_wait(bar(Smem2::b_full + st), (ccount / STAGES2) & 1);
+            tc_fence_after();
+            if (clk_on) ck_ops += clock64() - ck_a;
+            const uint64_t adesc = smem_desc_sw128(sbase + Smem2::a_off + kc * A_CHUNK_BYTES);
+            const uint64_t bdesc = smem_desc_sw128(sbase + Smem2::b_off + st * B2_CHUNK_BYTES);
+            if (kc == xk) {
+              tc_mma_f16_2sm_elect(d_tmem, smem_desc_sw32(sbase + Smem2::a_off + kc * A_CHUNK_BYTES),
+                                   smem_desc_sw32(sbase + Smem2::b_off + st * B2_CHUNK_BYTES), IDESC_F16_2SM, 1);
+            } else if (kc != last_data || P.last_k8 == 4) {
+              tc_mma_f16_2sm_elect(d_tmem, adesc, bdesc, IDESC_F16_2SM, kc != 0);
+              tc_mma_f16_2sm_elect(d_tmem, adesc + 2, bdesc + 2, IDESC_F16_2SM, 1);
+              tc_mma_f16_2sm_elect(d_tmem, adesc + 4, bdesc + 4, IDESC_F16_2SM, 1);
+              tc_mma_f16_2sm_elect(d_tmem, adesc + 6, bdesc + 6, IDESC_F16_2SM, 1);
+            } else {
+              for (int k8 = 0; k8 < P.last_k8; k8++)
+                tc_mma_f16_2sm_elect(d_tmem, adesc + (uint64_t)(2 * k8), bdesc + (uint64_t)(2 * k8),
+                                     IDESC_F16_2SM, (kc | k8) != 0);
+            }
+            tc_commit_2sm_elect(bar(Smem2::b_empty + st), (uint16_t)3);
+          }
+          if (xring) {  // the norm term: one MMA over the 16 extra K elements
+            const uint32_t xs = tcount & 1;
+            if (clk_on) ck_a = clock64();
+            mbar_wait(bar(Smem2::x_full + xs), (tcount >> 1) & 1);
+            tc_fence_after();
+            if (clk_on) ck_x += clock64() - ck_a;
+            tc_mma_f16_2sm_elect(d_tmem, smem_desc_sw32(sbase + Smem2::a_off + xk * A_CHUNK_BYTES),
+                                 smem_desc_sw32(sbase + Smem2::xb_off + xs * XB2_BYTES), IDESC_F16_2SM, 1);
+            tc_commit_2sm_elect(bar(Smem2::x_empty + xs), (uint16_t)3);
+          }
+          tc_commit_2sm_elect(bar(Smem2::t_full + buf), (uint16_t)3);  // accumulators complete in both CTAs
+        }
+        tc_commit_2sm_elect(bar(Smem2::a_empty), (uint16_t)3);  // query tiles no longer needed
+      }
+      if (clk_on && lane == 0 && blockIdx.x < 160) {
+        g_tf32_clk[blockIdx.x][0] = ck_acc;
+        g_tf32_clk[blockIdx.x][1] = ck_ops;
+        g_tf32_clk[blockIdx.x][2] = ck_x;
+        g_tf32_clk[blockIdx.x][3] = clock64() - ck_t0;
+      }
+    }
+  } else if (warp < EPI_WARPS) {
+    regs_epilogue();
+    EpiCtx ectx;
+    ectx.smem = smem; ectx.sbase = sbase; ectx.tmem_base = tmem_base; ectx.warp = warp; ectx.lane = lane;
+    ectx.first_item = first_item; ectx.item_step = item_step; ectx.tq_div = tq_div;
+    ectx.pair = 2; ectx.crank = crank;
+    // "accumulator drained" goes to the LEADER's barrier (the only MMA issuer)
+    uint32_t a0, a1;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(a0) : "r"(bar(Smem2::t_empty + 0)));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(a1) : "r"(bar(Smem2::t_empty + 1)));
+    ectx.t_empty_addr0 = leader ? bar(Smem2::t_empty + 0) : a0;
+    ectx.t_empty_addr1 = leader ? bar(Smem2::t_empty + 1) : a1;
+    ectx.t_empty_remote = leader ? 0 : 1;   // the leader's own warps arrive locally
+    ectx.n_full0 = Smem2::n_full; ectx.n_empty0 = Smem2::n_empty; ectx.t_full0 = Smem2::t_full;
+    run_epilogue<MODE, OP_F16N, LDW>(P, ectx);
+  } else {
+    regs_aux();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves (or frees TMEM) while the pair is still working
+  if (warp == EPI_WARPS + 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -1302,12 +1764,20 @@ static int make_map_f16_extras(CUtensorMap *m, const void *ptr, long rows, int d
   return 0;
 }
 
-// Independent CTAs (default) or CTA pairs that multicast the database chunks (YAEL_B200_PAIR=1).
-// Measured on the bench shape: pairing halves the L2->SM traffic but does not shorten the pass
-// (6.02 vs 5.90 ms) -- the L2 feed is not what bounds this kernel -- so it stays opt-in.
-int tf32_pair_mode() {
-  const char *e = getenv("YAEL_B200_PAIR");  // 0 independent CTAs, 1 multicast pairs
-  return (e && atoi(e) != 0) ? 1 : 0;
+// How the CTAs of the tensor pass are organised (Tf32Plan::pair):
+//   0  independent CTAs
+//   1  clusters of 2 that multicast every database chunk (halves the L2 -> SM traffic; measured
+//      without effect on the pass: the L2 feed is not what bounds it), opt-in
+//   2  clusters of 2 that form ONE cta_group::2 MMA unit (k_knn_2sm): the default for the
+//      folded-norm FP16 kind whenever there are at least two query tiles
+// YAEL_B200_PAIR=0|1|2 overrides (2 only applies to the folded-norm FP16 kind).
+int tf32_pair_mode(int kind, int tiles_q) {
+  int mode = (kind == OP_F16N && tiles_q >= 2) ? 2 : 0;
+  if (const char *e = getenv("YAEL_B200_PAIR")) mode = atoi(e);
+  if (mode == 2 && (kind != OP_F16N || tiles_q < 2)) mode = 0;
+  if (mode == 1 && kind == OP_F8) mode = 0;
+  if (mode != 0 && (sm_count() & 1)) mode = 0;
+  return mode;
 }
 
 int tf32_kprime_for(int k) {
@@ -1330,7 +1800,7 @@ Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kp, int kind) {
   int cap = pow2_ceil(8 * kp);
   if (cap < 512) cap = 512;
   if (cap > MAXL) cap = MAXL;
-  const int pair = tf32_pair_mode();
+  const int pair = tf32_pair_mode(kind, (nq + TM - 1) / TM);
   const int G = pair ? sm_count() / 2 : sm_count();          // schedulable units (CTAs or pairs)
   const int tiles_q = pair ? ((nq + TM - 1) / TM + 1) / 2 : (nq + TM - 1) / TM;  // tiles or pairs
   const int nbt = nbt_logical;
@@ -1373,14 +1843,14 @@ Tf32Plan tf32_plan(int nq, int nb, int d, int k, int kind) {
   return tf32_plan_tiles(nq, (nb + TN - 1) / TN, d, tf32_kprime_for(k), kind);
 }
 
-template <int MODE, int KIND = OP_TF32>
+template <int MODE, int KIND = OP_TF32, int LDW = 16>
 static int launch_mode(const Tf32Plan &plan, const CUtensorMap &mq, const CUtensorMap &mb,
                        const CUtensorMap &mbh, const CUtensorMap &mqx, const CUtensorMap &mbx,
                        const Tf32Params &P, cudaStream_t st) {
   static bool attr[64] = {};  // per device: function attributes belong to the current device
   cudaError_t ae = cudaSuccess;
   once_per_device(attr, [&ae] {
-    ae = cudaFuncSetAttribute(k_knn_tf32<MODE, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ae = cudaFuncSetAttribute(k_knn_tf32<MODE, KIND, LDW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               TF32_SMEM_BYTES);
   });
   if (ae != cudaSuccess) {
@@ -1400,13 +1870,43 @@ static int launch_mode(const Tf32Plan &plan, const CUtensorMap &mq, const CUtens
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_knn_tf32<MODE, KIND>, mq, mb, mbh, mqx, mbx, P);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_knn_tf32<MODE, KIND, LDW>, mq, mb, mbh, mqx, mbx, P);
     if (e != cudaSuccess) return fail(2, "k_knn_tf32 cluster launch: %s", cudaGetErrorString(e));
     count_launch();
   } else {
-    k_knn_tf32<MODE, KIND><<<plan.ctas, TF32_THREADS, TF32_SMEM_BYTES, st>>>(mq, mb, mbh, mqx, mbx, P);
+    k_knn_tf32<MODE, KIND, LDW><<<plan.ctas, TF32_THREADS, TF32_SMEM_BYTES, st>>>(mq, mb, mbh, mqx, mbx, P);
     YB_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+template <int MODE, int LDW>
+static int launch_2sm(const Tf32Plan &plan, const CUtensorMap &mq, const CUtensorMap &mbh,
+                      const CUtensorMap &mqx, const CUtensorMap &mbxh, const Tf32Params &P, cudaStream_t st) {
+  static bool attr[64] = {};
+  cudaError_t ae = cudaSuccess;
+  once_per_device(attr, [&ae] {
+    ae = cudaFuncSetAttribute(k_knn_2sm<MODE, LDW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF32_SMEM2_BYTES);
+  });
+  if (ae != cudaSuccess) {
+    attr[dev_index()] = false;
+    return fail(6, "cannot reserve %d bytes of shared memory: %s", TF32_SMEM2_BYTES, cudaGetErrorString(ae));
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(plan.ctas);
+  cfg.blockDim = dim3(TF32_THREADS);
+  cfg.dynamicSmemBytes = TF32_SMEM2_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_knn_2sm<MODE, LDW>, mq, mbh, mqx, mbxh, P);
+  if (e != cudaSuccess) return fail(2, "k_knn_2sm cluster launch: %s", cudaGetErrorString(e));
+  count_launch();
   return 0;
 }
 
@@ -1417,7 +1917,7 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
                        void *ws, cudaStream_t st, const Tf32Out *oo = nullptr) {
   if ((((uintptr_t)base) & 15) || (((uintptr_t)query) & 15))
     return fail(6, "tf32 path needs 16-byte aligned matrices");
-  CUtensorMap mq, mb, mbh, mqx, mbx;
+  CUtensorMap mq, mb, mbh, mqx, mbx, mbxh;
   int rc;
   Tf32Params P = {};
   P.nq = nq; P.nb = nb; P.d = d;
@@ -1459,6 +1959,7 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
       P.last_k8 = (dbytes - (nkd - 1) * 128 + 31) / 32;
       if ((rc = make_map_f16_extras(&mqx, query, nq, d, TM))) return rc;
       if ((rc = make_map_f16_extras(&mbx, base, nb_pad, d, TN))) return rc;
+      if ((rc = make_map_f16_extras(&mbxh, base, nb_pad, d, TN / 2))) return rc;
     } else {
       P.nkc = (pitch + 127) / 128;
       P.last_k8 = (pitch - (P.nkc - 1) * 128 + 31) / 32;
@@ -1473,6 +1974,7 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   if (P.xk < 0) {  // unused by the other kinds, but kernel parameters all the same
     mqx = mq;
     mbx = mb;
+    mbxh = mbh;
   }
   P.tiles_q = (nq + TM - 1) / TM;
   P.nbt = nbt_logical;
@@ -1537,12 +2039,40 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
       default: return fail(6, "plain FP16 operands are only instantiated for the k = 1 margin mode");
     }
   }
+  // columns per tcgen05.ld of the folded-norm list / nearest epilogues (YAEL_B200_LDW: A/B knob)
+  // 128 = the early hand-back epilogue (whole half tile in registers, buffer released before the
+  // threshold tests).  Measured at the bench shape with the 2-SM kernel: 16 -> 2.51 ms, 32 -> 2.43,
+  // 64 -> 2.50, 128 -> 2.33 (1-SM kernel: 2.52 / 2.47 / 2.50 / 2.40); k-means config 4: 176 -> 150 ms.
+  int ldw = 128;
+  if (const char *e = getenv("YAEL_B200_LDW")) ldw = atoi(e);
+  if (plan.kind == OP_F16N && plan.pair == 2) {  // cta_group::2 pairs (k_knn_2sm)
+    switch (mode) {
+      case EPI_DUMP: return launch_2sm<EPI_DUMP, 16>(plan, mq, mbh, mqx, mbxh, P, st);
+      case EPI_GMIN: return launch_2sm<EPI_GMIN, 16>(plan, mq, mbh, mqx, mbxh, P, st);
+      case EPI_LISTS:
+        if (ldw == 128) return launch_2sm<EPI_LISTS, 128>(plan, mq, mbh, mqx, mbxh, P, st);
+        if (ldw == 64) return launch_2sm<EPI_LISTS, 64>(plan, mq, mbh, mqx, mbxh, P, st);
+        if (ldw == 32) return launch_2sm<EPI_LISTS, 32>(plan, mq, mbh, mqx, mbxh, P, st);
+        return launch_2sm<EPI_LISTS, 16>(plan, mq, mbh, mqx, mbxh, P, st);
+      default:
+        if (ldw == 128) return launch_2sm<EPI_NEAREST, 128>(plan, mq, mbh, mqx, mbxh, P, st);
+        if (ldw == 32) return launch_2sm<EPI_NEAREST, 32>(plan, mq, mbh, mqx, mbxh, P, st);
+        return launch_2sm<EPI_NEAREST, 16>(plan, mq, mbh, mqx, mbxh, P, st);
+    }
+  }
   if (plan.kind == OP_F16N) {  // FP16 operands with folded norms: top-k', sampling, dump
     switch (mode) {
       case EPI_DUMP: return launch_mode<EPI_DUMP, OP_F16N>(plan, mq, mb, mbh, mqx, mbx, P, st);
       case EPI_GMIN: return launch_mode<EPI_GMIN, OP_F16N>(plan, mq, mb, mbh, mqx, mbx, P, st);
-      case EPI_LISTS: return launch_mode<EPI_LISTS, OP_F16N>(plan, mq, mb, mbh, mqx, mbx, P, st);
-      default: return launch_mode<EPI_NEAREST, OP_F16N>(plan, mq, mb, mbh, mqx, mbx, P, st);
+      case EPI_LISTS:
+        if (ldw == 128) return launch_mode<EPI_LISTS, OP_F16N, 128>(plan, mq, mb, mbh, mqx, mbx, P, st);
+        if (ldw == 64) return launch_mode<EPI_LISTS, OP_F16N, 64>(plan, mq, mb, mbh, mqx, mbx, P, st);
+        if (ldw == 32) return launch_mode<EPI_LISTS, OP_F16N, 32>(plan, mq, mb, mbh, mqx, mbx, P, st);
+        return launch_mode<EPI_LISTS, OP_F16N>(plan, mq, mb, mbh, mqx, mbx, P, st);
+      default:
+        if (ldw == 128) return launch_mode<EPI_NEAREST, OP_F16N, 128>(plan, mq, mb, mbh, mqx, mbx, P, st);
+        if (ldw == 32) return launch_mode<EPI_NEAREST, OP_F16N, 32>(plan, mq, mb, mbh, mqx, mbx, P, st);
+        return launch_mode<EPI_NEAREST, OP_F16N>(plan, mq, mb, mbh, mqx, mbx, P, st);
     }
   }
   switch (mode) {
@@ -1618,6 +2148,14 @@ using namespace yb;
 // Debug / test entry: raw TF32 scores s[q][n] = |b_n|^2 - 2 <q, b_n> for every pair (the tensor
 // path with the top-k switched off).  Used by tests to bound the TF32 error against the
 // certificate's model, and for bring-up.
+// bring-up: per-CTA clock attribution of the last instrumented tensor pass (see g_tf32_clk)
+extern "C" int yb_debug_tf32_clocks(long long *out, int n_cta) {
+  if (n_cta > 160) n_cta = 160;
+  YB_CUDA(cudaDeviceSynchronize());
+  YB_CUDA(cudaMemcpyFromSymbol(out, g_tf32_clk, sizeof(long long) * 16 * (size_t)n_cta));
+  return 0;
+}
+
 extern "C" int yb_debug_tf32_scores(int nq, int nb, int d, const float *base, const float *query,
                                     float *scores, yb_stream_t s) {
   Guard g;
