@@ -772,8 +772,6 @@ def run_ours(args):
     sampler = ClockSampler(local, uuid)
     sampler.start()
     L.yb_launch_count(1)
-    if world > 1:
-        searcher.events = []   # per-search CUDA events: local scan / all-gather / merge
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.mark_begin()
     e0.record(stream)
@@ -786,20 +784,39 @@ def run_ours(args):
         dist.barrier()
     clocks = sampler.stop()
     launches = L.yb_launch_count(0)
-    shard_phase_ms = searcher.phase_ms() if world > 1 else None
-    searcher.events = None
+    shard_phase_ms = None
     ms = e0.elapsed_time(e1) / args.steps
     cnt = C.c_long(0)
     phase_ms = {}
     for ph, name in ((0, "center_and_norms"), (10, "sample_thresholds"), (1, "tf32_shortlist"),
                      (2, "merge_select"), (3, "rerank"), (4, "exact_fallback"), (5, "exact_slab"),
-                     (6, "row_select")):
+                     (6, "row_select"), (16, "exchange_all_to_all_plus_all_gather"), (17, "merge_query_slice")):
         t = L.yb_prof_ms(ph, C.byref(cnt), 0)
         if cnt.value:
             phase_ms[name] = t / cnt.value
     L.yb_prof_ms(0, None, 1)
     L.yb_prof_enable(0)
     if world > 1:
+        # the exchange phase is recorded as two spans per search (all-to-all, all-gather)
+        if "exchange_all_to_all_plus_all_gather" in phase_ms:
+            phase_ms["exchange_all_to_all_plus_all_gather"] *= 2
+        shard_phase_ms = {k_: phase_ms[k_] for k_ in ("exchange_all_to_all_plus_all_gather", "merge_query_slice")
+                          if k_ in phase_ms}
+        # A/B in the same run: the round-1 exchange (all-gather of every list to every rank + full merge)
+        ab = ydist.ShardedKnn(base, K, rank=rank, world=world, exchange="torch")
+        for _ in range(3):
+            ab.search(query)
+        dist.barrier()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(args.steps):
+            ab.search(query)
+        a1.record(stream)
+        torch.cuda.synchronize()
+        tab = torch.tensor([a0.elapsed_time(a1) / args.steps], device=dev)
+        dist.all_reduce(tab, op=dist.ReduceOp.MAX)
+        shard_phase_ms["ms_per_step_with_round1_allgather_exchange"] = float(tab.item())
         tmax = torch.tensor([ms], device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms = float(tmax.item())
@@ -950,8 +967,9 @@ def run_ours(args):
         "config": {
             "workload": WORKLOAD,
             "parallelism": ("single GPU" if world == 1 else
-                            "database sharded x%d (1M rows per rank), NCCL all-gather of per-rank "
-                            "top-k + merge; value counts query x 1M-shard scans" % world),
+                            "database sharded x%d (1M rows per rank); query-partitioned NCCL exchange inside "
+                            "the library (all-to-all of list slices, merge of nq/N queries per rank, all-gather "
+                            "of merged slices); value counts query x 1M-shard scans" % world),
             "l2": "database (512 MB) is larger than L2 (126 MB): no flush needed between steps",
             "engine": ("tcgen05 %s + FP32 re-rank" % operands) if engine == 1 else "exact FP32 SIMT",
             "uncertified_queries_redone_exactly": int(uncert),
@@ -966,6 +984,126 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_c5(args):
+    """--workload c5: BASELINE configs[4], exact kNN "deep shape" -- 100M x 96 float32 database sharded
+    by rows over the ranks (generated on the device, shard by shard), 10 000 queries, k = 100, the
+    library's query-partitioned NCCL exchange (reference call shape: progs/knn.c:225).  Prints one
+    JSON line: queries/s against the WHOLE database (strong scaling), the tensor pass's roofline
+    fraction per rank, and two parity objects on a 1M-row sub-database (1M / N rows of every shard):
+    sharded search == ONE search of the concatenation (bit-identical), and the oracle's answer."""
+    import torch
+    import torch.distributed as dist
+    import yael_b200
+    from yael_b200 import dist as ydist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    L = yael_b200.lib()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    L.yb_set_device(local)
+    if world > 1:
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=600))
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    n_total, d, nq, k = args.c5_rows, 96, 10_000, 100
+    lo, hi = ydist.shard_bounds(n_total, world)[rank]
+    base = torch.empty((hi - lo, d), dtype=torch.float32, device=dev)
+    g = torch.Generator(device=dev)
+    step = 4_000_000
+    for a in range(0, hi - lo, step):   # seeded per 4M-row block of the GLOBAL database: same data for any N
+        b = min(hi - lo, a + step)
+        base[a:b].uniform_(0, 1, generator=g.manual_seed(4321 + (lo + a) // 1000))
+    gq = torch.Generator(device=dev)
+    gq.manual_seed(77)
+    query = torch.rand((nq, d), device=dev, dtype=torch.float32, generator=gq)
+    searcher = ydist.ShardedKnn(base, k, rank=rank, world=world, id_offset=lo)
+    for _ in range(max(2, args.warmup)):
+        searcher.search(query)
+    torch.cuda.synchronize()
+    L.yb_prof_enable(1)
+    L.yb_prof_ms(1, None, 1)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    steps = max(2, min(args.steps, 5))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        res_i, res_d = searcher.search(query)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    cnt = C.c_long(0)
+    phase_ms = {}
+    for ph, name in ((0, "center_and_norms"), (10, "sample_thresholds"), (1, "tf32_shortlist"), (2, "merge_select"),
+                     (3, "rerank"), (4, "exact_fallback"), (16, "exchange"), (17, "merge_query_slice")):
+        t = L.yb_prof_ms(ph, C.byref(cnt), 0)
+        if cnt.value:
+            phase_ms[name] = t / cnt.value * (2 if ph == 16 else 1)
+    L.yb_prof_ms(0, None, 1)
+    L.yb_prof_enable(0)
+    uncert = int(L.yb_last_knn_uncertified())
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    # ---- parity on a 1M-row sub-database: sub_n / N rows of every shard
+    sub = args.c5_sub // world
+    sub_base = base[:sub].contiguous()
+    nchk = 512
+    s_sub = ydist.ShardedKnn(sub_base, k, rank=rank, world=world, id_offset=rank * sub)
+    mi, md = s_sub.search(query[:nchk].contiguous())
+    if world > 1:
+        allb = torch.empty((world * sub, d), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(allb.view(-1), sub_base.view(-1))
+    else:
+        allb = sub_base
+    one_i = torch.empty((nchk, k), dtype=torch.int32, device=dev)
+    one_d = torch.empty((nchk, k), dtype=torch.float32, device=dev)
+    rc = L.yb_knn_l2(nchk, world * sub, d, k, allb.data_ptr(), query.data_ptr(), None, one_i.data_ptr(),
+                     one_d.data_ptr(), 0, ydist._stream_ptr(torch))
+    torch.cuda.synchronize()
+    same = rc == 0 and bool(torch.equal(one_i, mi) and torch.equal(one_d, md))
+    if world > 1:
+        f = torch.tensor([1 if same else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(f, op=dist.ReduceOp.MIN)
+        same = bool(f.item())
+    if rank == 0:
+        from oracle import bindings as ob
+        nor = 64
+        bh, qh = allb.cpu().numpy(), query[:nor].cpu().numpy()
+        cores = len(os.sched_getaffinity(0))
+        widx, wdis = (ob.ref_knn(bh, qh, k, nt=cores) if ob.have_ref() else
+                      ob.orc_knn(bh, qh, k, dot_mode=ob.DOT_F32_SEQ, nt=cores))
+        par = knn_parity(mi[:nor].cpu().numpy(), md[:nor].cpu().numpy(), widx, wdis, bh, qh,
+                         "C5 sub-database: %d x 96 (%d rows of each of the %d shards), k=100" % (world * sub, sub, world))
+        peaks = _peaks()
+        bf16 = peaks.get("bf16_tflops", 1590.0)
+        roof = None
+        if "tf32_shortlist" in phase_ms:
+            ach = 2.0 * nq * (hi - lo) * d / (phase_ms["tf32_shortlist"] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "k_knn_tf32<EPI_LISTS, fp16> on this rank's shard",
+                    "achieved": ach, "peak": bf16, "unit": "TFLOP/s", "frac": ach / bf16, "traffic": None,
+                    "kernel_ms": phase_ms["tf32_shortlist"]}
+        print(json.dumps({
+            "metric": "kNN queries/s (%dM x 96 db sharded over %d GPUs, k=100)" % (n_total // 1_000_000, world),
+            "value": nq / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "data": "synthetic uniform[0,1), generated on the device",
+            "config": {"workload": "exact kNN, deep shape: %d x 96 database sharded by rows over %d GPUs, 10000 "
+                                   "queries, k=100, NCCL top-k merge (BASELINE configs[4])" % (n_total, world),
+                       "rows_per_rank": hi - lo, "phase_ms_rank0": phase_ms,
+                       "uncertified_queries_redone_exactly": uncert,
+                       "operands": "fp16" if L.yb_last_knn_operands() == 2 else "tf32"},
+            "roofline": roof,
+            "parity_sharded_vs_one_search": {"n_queries": nchk, "rows": world * sub,
+                                             "ids_and_distances_bit_identical_on_every_rank": same},
+            "parity": par}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -976,7 +1114,14 @@ def main():
                     help="skip the k-means / Hamming blocks")
     ap.add_argument("--kmeans-iters", type=int, default=10,
                     help="iterations of the k-means block (BASELINE configs[3] names 10)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2: the headline (BASELINE configs[1]); c5: 100M x 96 sharded (configs[4])")
+    ap.add_argument("--c5-rows", type=int, default=100_000_000)
+    ap.add_argument("--c5-sub", type=int, default=1_000_000)
     args = ap.parse_args()
+    if args.workload == "c5" and args.impl == "ours":
+        run_c5(args)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -59,7 +59,8 @@ void yb_set_knn_engine(int engine);
  * 4 exact-engine fallback, 5 exact distance slab (k_l2_simt), 6 per-row select (k_kmin_rows),
  * 7 Hamming popcount scan, 8 k-means accumulate (sort + segmented sums), 9 k-means scale,
  * 10 / 11 k-NN admission-threshold sampling, 12 Hamming code expansion (+-1 E4M3), 13 Hamming
- * threshold sampling, 14 Hamming tcgen05 E4M3 pass, 15 Hamming order + certify */
+ * threshold sampling, 14 Hamming tcgen05 E4M3 pass, 15 Hamming order + certify, 16 sharded
+ * exchange (NCCL all-to-all / all-gather / all-reduce), 17 merge of a query slice */
 void yb_prof_enable(int on);
 double yb_prof_ms(int phase, long *count, int reset);
 
@@ -161,10 +162,16 @@ int yb_kmeans_scale(int d, int k, const float *sums, const int *nassign, float *
  * with DEVICE pointers; must leave the global sums in place on every rank */
 typedef struct {
   void *ctx;
-  /* returns 0 on success */
+  /* returns 0 on success.  `sums` has room for 2 * n_int + 4 floats behind its n_float sums (a
+   * hook may pack the counts and qerr there and reduce everything in ONE collective) */
   int (*allreduce_sums)(void *ctx, float *sums, long n_float, int *nassign, long n_int,
                         double *qerr, yb_stream_t s);
   long n_total; /* global number of points (0 = n) */
+  /* optional (may be NULL): ALL n_total points in host memory.  With it the sharded run may use
+   * every initialisation of the reference (random / k-means++ draws are replayed identically on
+   * every rank from these rows) and redo > 1; without it the init must be KMEANS_INIT_USER. */
+  const float *v_host_all;
+  int rank; /* rank 0 prints the progress messages of a verbose run */
 } yb_kmeans_comm_t;
 
 /* kmeans (yael/kmeans.c:332-447) on a device-resident v[n][d]; every other argument as the
@@ -215,6 +222,67 @@ int yb_crossmatch_hamming_count(const uint8_t *dbs, int n, int ht, int ncodes,
                                 unsigned long long *count, yb_stream_t s);
 int yb_crossmatch_hamming(const uint8_t *dbs, int n, int ht, int ncodes, int *idx,
                           uint16_t *hams, unsigned long long *count, yb_stream_t s);
+
+/* ---- sharded hot path: the exchange steps of SURVEY.md 8(e) inside the library ------- */
+/* One NCCL communicator per GPU (NCCL is resolved at run time: libnccl.so.2).  Two ways to get
+ * one: (a) one PROCESS per GPU (torchrun): rank 0 calls yb_comm_unique_id, the caller broadcasts
+ * the 128 bytes, every rank calls yb_comm_create on its device; (b) one host THREAD per GPU in a
+ * single process: yb_comm_create_all (ncclCommInitAll) -- what the drop-in layer's own multi-GPU
+ * mode below uses.  The reference has no counterpart: it is one process with OpenMP threads
+ * (yael/nn.c:665-699), whose slicing rule [n*r/G, n*(r+1)/G) is the sharding rule here. */
+typedef struct yb_comm yb_comm;
+int yb_comm_available(void);              /* 1 when NCCL could be loaded */
+int yb_comm_unique_id(void *id128);       /* 128 bytes */
+yb_comm *yb_comm_create(const void *id128, int rank, int world); /* collective; NULL on failure */
+int yb_comm_create_all(int ndev, const int *devs, yb_comm **out);
+void yb_comm_destroy(yb_comm *c);
+int yb_comm_rank(const yb_comm *c);
+int yb_comm_world(const yb_comm *c);
+int yb_comm_allreduce_f32(yb_comm *c, float *buf, long n, yb_stream_t s);
+int yb_comm_allgather(yb_comm *c, const void *send, void *recv, long bytes_per_rank, yb_stream_t s);
+/* exact k-NN over a database sharded by rows (SPMD: every rank calls with ITS shard
+ * base[nb_local][d], the global id of its first row and the same queries): local search, then a
+ * QUERY-PARTITIONED exchange -- rank r receives queries [r*slice, (r+1)*slice) of every rank's
+ * lists (all-to-all), merges them by (distance, id), and one all-gather distributes the merged
+ * slices.  assign / dis [nq][k] receive the result for the whole database on every rank,
+ * identical for any number of ranks.  (yael/nn.c:451-525 semantics.) */
+int yb_knn_l2_sharded(yb_comm *c, int nq, int nb_local, int d, int k, const float *base,
+                      const float *query, int id_offset, int *assign, float *dis, yb_stream_t s);
+/* the same with the shard still in HOST memory (transfer overlapped with the scan,
+ * yb_knn_l2_hostbase); base_dev: device scratch for nb_local * d floats */
+int yb_knn_l2_sharded_hostbase(yb_comm *c, int nq, int nb_local, int d, int k,
+                               const float *base_host, float *base_dev, const float *query,
+                               int id_offset, int *assign, float *dis, yb_stream_t s);
+int yb_nn_hamming_sharded(yb_comm *c, int nq, int nb_local, int ncodes, int k, const uint8_t *base,
+                          const uint8_t *query, int id_offset, int *assign, uint16_t *dis,
+                          yb_stream_t s);
+/* kmeans (yael/kmeans.c:332-447) on points sharded by rows: v_dev is this rank's shard
+ * [n_local][d], centroids the k initial centroids (identical on every rank) and the result; ONE
+ * all-reduce of (sums | counts | qerr) per iteration on the compute stream.  assign / dis (host,
+ * may be NULL) receive this rank's points' assignment. */
+float yb_kmeans_sharded(yb_comm *c, int d, int n_local, long n_total, int k, int niter,
+                        const float *v_dev, int flags, long seed, float *centroids, float *dis,
+                        int *assign, int *nassign, yb_stream_t s);
+
+/* ---- the drop-in layer's own multi-GPU mode (one process, one host thread per GPU) ---- */
+/* knn_full, nn_hamming and kmeans called with HOST pointers shard large problems over the GPUs
+ * named by YAEL_GPU_DEVICES ("all", or a comma-separated list of ordinals; default: all) -- unless
+ * the process pinned a device with yb_set_device (one process per GPU: the caller shards).
+ * yb_mgpu_set_devices overrides the environment (n = 0: back to it; n = 1: single GPU).
+ * yb_mgpu_device_count: how many GPUs the next qualifying call would use. */
+int yb_mgpu_set_devices(int n, const int *devs);
+int yb_mgpu_device_count(void);
+/* how many GPUs the last knn_full / nn_hamming / kmeans call of this thread used */
+int yb_mgpu_last_used(void);
+/* the sharded bodies: return 0 when done, -1 when the call does not qualify (single GPU, small
+ * problem, k > rows per shard; the caller then takes the one-GPU path), > 0 on failure.  Host
+ * pointers throughout. */
+int yb_mgpu_knn_full(int nq, int nb, int d, int k, const float *base, const float *query,
+                     int *assign, float *dis);
+int yb_mgpu_nn_hamming(int nq, int nb, int ncodes, int k, const uint8_t *base, const uint8_t *query,
+                       int *assign, uint16_t *dis);
+int yb_mgpu_kmeans(int d, int n, int k, int niter, const float *v, int flags, long seed, int redo,
+                   float *centroids, float *dis, int *assign, int *nassign, float *qerr_out);
 
 #ifdef __cplusplus
 }

@@ -39,19 +39,26 @@ def _worker(rank, world, port, q):
             out_i[j], out_d[j] = ii[order], dd[order]
         widx, wdis = ob.orc_knn(base, query, k, canonical=True)
         ok = np.array_equal(out_i, widx) and np.array_equal(out_d, wdis)
-        # the k-NN exchange proper: ids and distance bits of a rank travel as ONE [2][nq][k] block
-        # (ShardedKnn._exchange); the merge reads shard g at gbuf + g * 2*nq*k (ids) and + nq*k (dis)
-        import types
-        buf = torch.empty((2, 37, k), dtype=torch.int32)
-        buf[0] = torch.from_numpy(idx)
-        buf[1] = torch.from_numpy(dis).view(torch.int32)
-        stub = types.SimpleNamespace(torch=torch, world=world)
-        gbuf = ydist.ShardedKnn._exchange(stub, buf, 37)
-        flat = gbuf.numpy().reshape(-1)
-        for g in range(world):
-            ids_g = flat[g * 2 * 37 * k: g * 2 * 37 * k + 37 * k].reshape(37, k)
-            dis_g = flat[g * 2 * 37 * k + 37 * k: (g + 1) * 2 * 37 * k].view(np.float32).reshape(37, k)
-            ok = ok and np.array_equal(ids_g, gi[g]) and np.array_equal(dis_g, gd[g])
+        # the library's exchange is QUERY-PARTITIONED (yb_comm.cu: knn_sharded_impl): 37 queries over
+        # 2 ranks = slices of 19 with one padding row; every rank merges only its slice of every
+        # rank's lists, the merged slices are all-gathered.  Same answer as the full merge.
+        sl, bounds = ydist.query_slices(37, world)
+        ok = ok and sl == 19 and bounds == [(0, 19), (19, 37)]
+
+        def merge(mi, md):   # [world][slice][k] -> [slice][k] by (distance, id); padding sorts last
+            mi, md = mi.numpy(), md.numpy()
+            oi = np.empty(mi.shape[1:], np.int32)
+            od = np.empty(md.shape[1:], np.float32)
+            for j in range(mi.shape[1]):
+                ii, dd = mi[:, j].ravel(), md[:, j].ravel()
+                key_d = np.where(ii < 0, np.inf, dd)
+                order = np.lexsort((ii, key_d))[:k]
+                oi[j], od[j] = ii[order], dd[order]
+            return torch.from_numpy(oi), torch.from_numpy(od)
+
+        pi, pd = ydist.partitioned_exchange_model(dist, torch, torch.from_numpy(idx), torch.from_numpy(dis),
+                                                  rank, world, merge)
+        ok = ok and np.array_equal(pi.numpy(), widx) and np.array_equal(pd.numpy(), wdis)
         # sharded k-means bookkeeping: all-reduced sums / counts == unsharded accumulation
         v = r.random_sample((600, 4)).astype(np.float32)
         cent = v[:5].copy()
@@ -93,3 +100,13 @@ def test_shard_bounds_cover_everything():
             b = shard_bounds(n, w)
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+
+
+def test_query_slices_cover_everything():
+    from yael_b200.dist import query_slices
+    for nq in (1, 7, 37, 10000):
+        for w in (1, 2, 3, 8):
+            sl, b = query_slices(nq, w)
+            assert sl * w >= nq and b[0][0] == 0 and b[-1][1] == nq
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            assert all(hi - lo <= sl for lo, hi in b)

@@ -167,6 +167,28 @@ DEVICE = {
     "yb_match_hamming_thres": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "yb_crossmatch_hamming_count": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "yb_crossmatch_hamming": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    # sharded hot path: NCCL exchange inside the library (yb_comm.cu)
+    "yb_comm_available": (C.c_int, []),
+    "yb_comm_unique_id": (C.c_int, [_vp]),
+    "yb_comm_create": (_vp, [_vp, C.c_int, C.c_int]),
+    "yb_comm_create_all": (C.c_int, [C.c_int, _i, C.POINTER(_vp)]),
+    "yb_comm_destroy": (None, [_vp]),
+    "yb_comm_rank": (C.c_int, [_vp]),
+    "yb_comm_world": (C.c_int, [_vp]),
+    "yb_comm_allreduce_f32": (C.c_int, [_vp, _vp, C.c_long, _vp]),
+    "yb_comm_allgather": (C.c_int, [_vp, _vp, _vp, C.c_long, _vp]),
+    "yb_knn_l2_sharded": (C.c_int, [_vp] + [C.c_int] * 4 + [_vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "yb_knn_l2_sharded_hostbase": (C.c_int, [_vp] + [C.c_int] * 4 + [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "yb_nn_hamming_sharded": (C.c_int, [_vp] + [C.c_int] * 4 + [_vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "yb_kmeans_sharded": (C.c_float, [_vp, C.c_int, C.c_int, C.c_long, C.c_int, C.c_int, _vp, C.c_int,
+                                      C.c_long, _f, _f, _i, _i, _vp]),
+    # the drop-in layer's in-process multi-GPU mode (yb_mgpu.cu)
+    "yb_mgpu_set_devices": (C.c_int, [C.c_int, _i]),
+    "yb_mgpu_device_count": (C.c_int, []),
+    "yb_mgpu_last_used": (C.c_int, []),
+    "yb_mgpu_knn_full": (C.c_int, [C.c_int] * 4 + [_f, _f, _i, _f]),
+    "yb_mgpu_nn_hamming": (C.c_int, [C.c_int] * 4 + [_u8, _u8, _i, _u16]),
+    "yb_mgpu_kmeans": (C.c_int, [C.c_int] * 4 + [_f, C.c_int, C.c_long, C.c_int, _f, _f, _i, _i, _f]),
 }
 
 _lib = None

@@ -31,6 +31,12 @@ void nn_hamming(int nq, int nb, int ncodes, int k, const uint8 *b, const uint8 *
                 uint16 *dis) {
   assert(k <= nb); /* same precondition as knn_full, yael/nn.c:456 */
   if (nq <= 0 || k <= 0) return;
+  if (!ybh_is_device_ptr(b) && !ybh_is_device_ptr(q) && !ybh_is_device_ptr(assign) &&
+      !ybh_is_device_ptr(dis)) { /* large problems: sharded over the box's GPUs (yb_mgpu.cu) */
+    int rc = yb_mgpu_nn_hamming(nq, nb, ncodes, k, b, q, assign, dis);
+    if (rc == 0) return;
+    if (rc > 0) ybh_die("yb_mgpu_nn_hamming", rc);
+  }
   ybh_arg ab = ybh_in(b, (size_t)nb * ncodes);
   ybh_arg aq = ybh_in(q, (size_t)nq * ncodes);
   ybh_arg oa = ybh_out(assign, sizeof(int) * (size_t)nq * k);

@@ -176,7 +176,7 @@ float yb_kmeans_dev(int d, int n, int k, int niter, const float *v_dev, int flag
                     int redo, float *centroids_out, float *dis_out, int *assign_out,
                     int *nassign_out, const yb_kmeans_comm_t *comm, yb_stream_t s) {
   long run, iter_tot = 0;
-  int verbose = !(flags & KMEANS_QUIET);
+  int verbose = !(flags & KMEANS_QUIET) && !(comm && comm->rank != 0);
   if (flags & (KMEANS_L1 | KMEANS_CHI2)) {
     fprintf(stderr, "yael_b200: kmeans: KMEANS_L1 / KMEANS_CHI2 are outside the B200 hot path "
                     "(medians / Newton per coordinate, no contraction) and are not provided\n");
@@ -188,9 +188,10 @@ float yb_kmeans_dev(int d, int n, int k, int niter, const float *v_dev, int flag
     assert(centroids_out != NULL);
     redo = 1;
   }
-  if (comm && !is_user_init) {
+  const float *v_all = comm ? comm->v_host_all : NULL; /* all points, host (sharded run) */
+  if (comm && !is_user_init && !v_all) {
     fprintf(stderr, "yael_b200: sharded kmeans needs KMEANS_INIT_USER (the caller gathers the "
-                    "initial centroids across ranks)\n");
+                    "initial centroids across ranks) or yb_kmeans_comm_t.v_host_all\n");
     abort();
   }
   long n_total = (comm && comm->n_total > 0) ? comm->n_total : n;
@@ -199,7 +200,8 @@ float yb_kmeans_dev(int d, int n, int k, int niter, const float *v_dev, int flag
   km_dev K;
   K.d = d; K.n = n; K.k = k; K.v = v_dev; K.comm = comm; K.s = s; K.n_total = n_total;
   K.cent = (float *)yb_malloc(sizeof(float) * (size_t)k * d);
-  K.sums = (float *)yb_malloc(sizeof(float) * (size_t)k * d);
+  /* room behind the sums for the packed counts / qerr of a one-collective all-reduce hook */
+  K.sums = (float *)yb_malloc(sizeof(float) * ((size_t)k * d + 2 * (size_t)k + 4));
   K.assign = (int *)yb_malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
   K.dis = (float *)yb_malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
   K.nassign = (int *)yb_malloc(sizeof(int) * (size_t)k);
@@ -222,24 +224,40 @@ float yb_kmeans_dev(int d, int n, int k, int niter, const float *v_dev, int flag
     if (is_user_init) {
       YBH_CHECK(yb_h2d(K.cent, centroids_out, sizeof(float) * (size_t)k * d, s));
     } else {
+      /* a sharded run replays the selection on every rank from the host copy of ALL points */
+      const int n_init = (int)n_total;
       if (flags & KMEANS_INIT_BERKELEY) {
-        int nsubset = n;
-        if (n > k * 8 && n > 8192) {
+        int nsubset = n_init;
+        if (n_init > k * 8 && n_init > 8192) {
           nsubset = k * 8;
           if (verbose) printf("Restricting k-means++ initialization to %d points\n", nsubset);
         }
-        kmeanspp_init_dev(d, nsubset, k, v_dev, selected, verbose, rand_r(&seed), s);
+        if (v_all) {
+          float *sub = (float *)yb_malloc(sizeof(float) * (size_t)nsubset * d);
+          YBH_CHECK(yb_h2d(sub, v_all, sizeof(float) * (size_t)nsubset * d, s));
+          kmeanspp_init_dev(d, nsubset, k, sub, selected, verbose, rand_r(&seed), s);
+          yb_free(sub);
+        } else {
+          kmeanspp_init_dev(d, nsubset, k, v_dev, selected, verbose, rand_r(&seed), s);
+        }
       } else {
         /* random_init (kmeans.c:15-20): first k of a seeded Fisher-Yates permutation */
-        int *perm = ivec_new_random_perm_r(n, rand_r(&seed));
+        int *perm = ivec_new_random_perm_r(n_init, rand_r(&seed));
         ivec_cpy(selected, perm, k);
         free(perm);
       }
-      int *sel_dev = (int *)yb_malloc(sizeof(int) * (size_t)k);
-      YBH_CHECK(yb_h2d(sel_dev, selected, sizeof(int) * (size_t)k, s));
-      YBH_CHECK(yb_gather_rows(v_dev, sel_dev, k, d, K.cent, s));
-      YBH_CHECK(yb_sync(s));
-      yb_free(sel_dev);
+      if (v_all) {
+        for (long c = 0; c < k; c++)
+          memcpy(cent_host + (size_t)c * d, v_all + (size_t)selected[c] * d, sizeof(float) * (size_t)d);
+        YBH_CHECK(yb_h2d(K.cent, cent_host, sizeof(float) * (size_t)k * d, s));
+        YBH_CHECK(yb_sync(s));
+      } else {
+        int *sel_dev = (int *)yb_malloc(sizeof(int) * (size_t)k);
+        YBH_CHECK(yb_h2d(sel_dev, selected, sizeof(int) * (size_t)k, s));
+        YBH_CHECK(yb_gather_rows(v_dev, sel_dev, k, d, K.cent, s));
+        YBH_CHECK(yb_sync(s));
+        yb_free(sel_dev);
+      }
     }
     core_ret = kmeans_core_dev(&K, niter, flags, verbose, cent_host, nassign_host, rand_r(&seed),
                                &qerr, &iter_tot);
@@ -271,6 +289,15 @@ float yb_kmeans_dev(int d, int n, int k, int niter, const float *v_dev, int flag
 /* yael/kmeans.c:332-447 */
 float kmeans(int d, int n, int k, int niter, const float *v, int flags, long seed, int redo,
              float *centroids, float *dis, int *assign, int *nassign) {
+  /* large problems on host buffers: points sharded over the box's GPUs (yb_mgpu.cu) */
+  if (!ybh_is_device_ptr(v) && !(centroids && ybh_is_device_ptr(centroids)) &&
+      !(dis && ybh_is_device_ptr(dis)) && !(assign && ybh_is_device_ptr(assign)) &&
+      !(nassign && ybh_is_device_ptr(nassign))) {
+    float q = 0;
+    int rc = yb_mgpu_kmeans(d, n, k, niter, v, flags, seed, redo, centroids, dis, assign, nassign, &q);
+    if (rc == 0) return q;
+    if (rc > 0) ybh_die("yb_mgpu_kmeans", rc);
+  }
   ybh_arg av = ybh_in(v, sizeof(float) * (size_t)n * d);
   /* outputs may be device pointers too: stage through host blocks in that case */
   float *c_h = centroids, *d_h = dis;

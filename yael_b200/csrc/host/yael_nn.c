@@ -22,6 +22,13 @@ void knn_full(int distance_type, int nq, int nb, int d, int k, const float *b, c
    * yb_knn_l2_hostbase (which falls back to copy-then-scan for shapes that do not qualify) */
   const int l2 = (distance_type == 2 || distance_type == 12);
   const int feed_host = l2 && !b_weights && !ybh_is_device_ptr(b);
+  /* large problems on host buffers: sharded over the box's GPUs (yb_mgpu.cu; -1 = does not
+   * qualify, take the one-GPU path below) */
+  if (feed_host && !ybh_is_device_ptr(q) && !ybh_is_device_ptr(assign) && !ybh_is_device_ptr(dis)) {
+    int rc = yb_mgpu_knn_full(nq, nb, d, k, b, q, assign, dis);
+    if (rc == 0) return;
+    if (rc > 0) ybh_die("yb_mgpu_knn_full", rc);
+  }
   ybh_arg ab;
   if (feed_host) {
     ab = ybh_out((void *)b, sizeof(float) * (size_t)nb * d); /* device scratch, no copy */

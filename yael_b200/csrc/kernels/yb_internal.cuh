@@ -2,6 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
+#include <stdint.h>
+
+#include "../../../include/yael_b200.h"
 
 namespace yb {
 
@@ -91,6 +94,17 @@ int hamming_tc_scores(int nq, int nb, int W, const unsigned long long *pb,
 
 int hamming_tc_packed_dump(int nq, int nb, int W, int slots, const unsigned long long *pb,
                            const unsigned long long *pq, float *out, cudaStream_t st);
+// yb_runtime.cu: the process pinned a device with yb_set_device (one process per GPU)
+bool device_pinned();
+// yb_comm.cu: sharded bodies shared by the SPMD entry points and the in-process multi-GPU mode
+int knn_sharded_impl(yb_comm *c, int nq, int nb_local, int d, int k, float *base, const float *base_host,
+                     const float *query, int id_offset, int *assign, float *dis, int *slice_assign,
+                     float *slice_dis, yb_stream_t s);
+int hamming_sharded_impl(yb_comm *c, int nq, int nb_local, int ncodes, int k, const uint8_t *base,
+                         const uint8_t *query, int id_offset, int *assign, uint16_t *dis,
+                         int *slice_assign, uint16_t *slice_dis, yb_stream_t s);
+yb_kmeans_comm_t kmeans_hook(yb_comm *c, long n_total, const float *v_host_all);
+
 long tf32_padded_rows(int nb);
 int tf32_tiles(int nb);
 int fill_f32(float *p, long n, float v, cudaStream_t st);

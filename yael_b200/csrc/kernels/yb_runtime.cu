@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "yb_common.cuh"
+#include "yb_internal.cuh"
 
 namespace {
 
@@ -48,6 +49,7 @@ std::recursive_mutex g_dev_mutex[kMaxDev];
 cudaStream_t g_last_caller_stream[kMaxDev];  // the last caller-provided stream seen per device
 thread_local char g_err[512] = "";
 std::atomic<long> g_launches{0};
+std::atomic<bool> g_pinned{false};
 
 int cur_dev() {
   int d = 0;
@@ -92,6 +94,7 @@ Guard::Guard() : dev(cur_dev()) { g_dev_mutex[dev].lock(); }
 Guard::~Guard() { g_dev_mutex[dev].unlock(); }
 
 int dev_index() { return cur_dev(); }
+bool device_pinned() { return g_pinned.load(); }
 
 cudaStream_t copy_stream() {
   const int dev = cur_dev();
@@ -220,6 +223,7 @@ int yb_device_count(void) {
 
 int yb_set_device(int dev) {
   YB_CUDA(cudaSetDevice(dev));
+  g_pinned.store(true);  // the caller manages devices: the drop-in layer stays on this one
   return 0;
 }
 
