@@ -191,7 +191,8 @@ static int ham_slots_for(int W, int k, long nb) {
 
 static Tf32Plan ham_plan(int nq, int nb, int W, int k, int S) {
   const int nc = (nb + S - 1) / S;
-  Tf32Plan plan = tf32_plan(nq, nc, 16 * W * S, k);
+  // packed passes may run as cta_group::2 pairs (planning kind 4 = OP_F8P, yb_knn_tf32.cu)
+  Tf32Plan plan = tf32_plan(nq, nc, 16 * W * S, k, S > 1 ? 4 : 0);
   plan.kind = 1;
   if (S > 1) {
     plan.ham_slots = S;
@@ -204,7 +205,7 @@ static Tf32Plan ham_plan(int nq, int nb, int W, int k, int S) {
 bool hamming_tc_supported(int nq, int nb, int W, int k) {
   if (W < 1 || W > 8 || nq < 1 || nb < 1 || k < 1 || k > nb) return false;
   Tf32Plan plan = ham_plan(nq, nb, W, k, ham_slots_for(W, k, nb));
-  return plan.ok && !plan.pair && plan.lists <= HF_LISTS;
+  return plan.ok && plan.pair != 1 && plan.lists <= HF_LISTS;
 }
 
 // pb / pq: codes packed as W 64-bit words per row.  Results for every query whose certificate

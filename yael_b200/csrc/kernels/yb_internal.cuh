@@ -30,6 +30,7 @@ struct Tf32Plan {
   int lists;       // shortlists produced per query (2 per range: one per column half)
   int ctas;        // persistent grid size
   int pair;        // CTAs launched as clusters of 2 sharing the database stream
+  int stream;      // query chunks travel through the ring with the database chunks (any d; 2-SM kernel)
   size_t ws_bytes; // workspace for buffers + shortlists
   int kind;        // operand kind: 0 = FP32 rows read as TF32 (kind::tf32); 1 = E4M3 bytes
                    // (kind::f8f6f4; `base` / `query` point to [rows][4*d] BYTE matrices -- the Hamming

@@ -1306,7 +1306,9 @@ k_rerank_k1(int nq, int d, int slots, int lists, const float *__restrict__ base,
   const int q = blockIdx.x * 4 + warp;
   if (q >= nq) return;
   const float *qrow = query + (size_t)q * d;
-  for (int t = lane; t < d; t += 32) qs[warp][t] = qrow[t];
+  const bool one_chunk = d <= 128;  // longer rows go through shared memory 128 coordinates at a time
+  if (one_chunk)
+    for (int t = lane; t < d; t += 32) qs[warp][t] = qrow[t];
   unsigned long long best = ~0ull;
   const double qn = qnorm[q];  // sequential double sum of squares (k_row_norms_seq, nn.c:108-120)
   for (int s0 = 0; s0 < slots; s0 += 32) {
@@ -1325,24 +1327,31 @@ k_rerank_k1(int nq, int d, int slots, int lists, const float *__restrict__ base,
           nb_++;
         }
       }
-      __syncwarp();
       int myid = -1;
+      float nf = 0.f, dot = 0.f;
+      for (int t0 = 0; t0 < d; t0 += 128) {  // the chains run on across the chunks: same order
+        const int dc = d - t0 < 128 ? d - t0 : 128;
+        __syncwarp();
+        if (!one_chunk)
+          for (int t = lane; t < dc; t += 32) qs[warp][t] = qrow[t0 + t];
 #pragma unroll
-      for (int c = 0; c < RB; c++) {
-        if (src[c] < 0) break;
-        const int idc = __shfl_sync(0xffffffffu, id, src[c]);
-        if (c == lane) myid = idc;
-        const float *brow = base + (size_t)idc * d;
-        for (int t = lane; t < d; t += 32) rows[warp][c][t] = __ldg(brow + t);
-      }
-      __syncwarp();
-      if (lane < nb_) {
-        float nf = 0.f, dot = 0.f;
-        for (int t = 0; t < d; t++) {
-          const float v = rows[warp][lane][t];
-          nf = __fadd_rn(nf, __fmul_rn(v, v));
-          dot = fmaf(v, qs[warp][t], dot);
+        for (int c = 0; c < RB; c++) {
+          if (src[c] < 0) break;
+          const int idc = __shfl_sync(0xffffffffu, id, src[c]);
+          if (c == lane) myid = idc;
+          const float *brow = base + (size_t)idc * d + t0;
+          for (int t = lane; t < dc; t += 32) rows[warp][c][t] = __ldg(brow + t);
         }
+        __syncwarp();
+        if (lane < nb_) {
+          for (int t = 0; t < dc; t++) {
+            const float v = rows[warp][lane][t];
+            nf = __fadd_rn(nf, __fmul_rn(v, v));
+            dot = fmaf(v, qs[warp][t], dot);
+          }
+        }
+      }
+      if (lane < nb_) {
         const float dist = __fadd_rn((float)(qn + (double)nf), __fmul_rn(-2.0f, dot));
         const uint32_t fk = float_key(dist);
         if (!is_nan_key(fk)) {

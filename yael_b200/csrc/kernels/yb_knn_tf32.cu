@@ -348,6 +348,7 @@ constexpr uint32_t IDESC_F16 = IDESC_F8;
 // operand kinds (Tf32Plan::kind).  The kind is a template parameter of the kernel: the issue
 // loop of each instantiation carries no kind branches.
 enum : int { OP_TF32 = 0, OP_F8 = 1, OP_F16 = 2, OP_F16N = 3 };  // F16N: FP16 with |b|^2 folded into K
+constexpr int OP_F8P = 4;  // planning only (tf32_plan_tiles): E4M3 in the packed Hamming modes -- may pair up
 template <int KIND>
 __device__ __forceinline__ void tc_mma_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                              uint32_t accumulate) {
@@ -754,6 +755,41 @@ __device__ __forceinline__ void process_group_ham(const uint32_t (&v)[16], float
                           w[12], w[13], w[14], w[15], tau3, mask, slots, mylist, cnt, row0, nb_real);
 }
 
+// W = 64 packed accumulators of one query, converted IN PLACE (v[c] becomes the word whose byte i
+// is ham_i): per accumulator half an FFMA2, one IADD and one LOP3 (acc | ((x - tau3) & ~x)); the
+// 16-word groups are only decoded when their test fires.
+template <int W>
+__device__ __forceinline__ void process_wide_ham(uint32_t (&v)[W], float magic, uint32_t tau3,
+                                                 uint32_t mask, int slots, float2 *mylist, int &cnt,
+                                                 int row0, int nb_real) {
+  uint32_t gm[W / 16];
+#pragma unroll
+  for (int s = 0; s < W / 16; s++) gm[s] = 0u;
+#pragma unroll
+  for (int c = 0; c < W; c += 2) {
+    float y0, y1;
+    ffma2_m2(y0, y1, v[c], v[c + 1], magic, magic, -0.5f);
+    v[c] = __float_as_uint(y0);
+    v[c + 1] = __float_as_uint(y1);
+    gm[c / 16] |= (v[c] - tau3) & ~v[c];
+    gm[c / 16] |= (v[c + 1] - tau3) & ~v[c + 1];
+  }
+  uint32_t any = gm[0];
+#pragma unroll
+  for (int s = 1; s < W / 16; s++) any |= gm[s];
+  if (any & mask) {
+#pragma unroll
+    for (int s = 0; s < W / 16; s++) {
+      if (gm[s] & mask)
+        cnt = slow_append_ham(v[16 * s + 0], v[16 * s + 1], v[16 * s + 2], v[16 * s + 3], v[16 * s + 4],
+                              v[16 * s + 5], v[16 * s + 6], v[16 * s + 7], v[16 * s + 8], v[16 * s + 9],
+                              v[16 * s + 10], v[16 * s + 11], v[16 * s + 12], v[16 * s + 13],
+                              v[16 * s + 14], v[16 * s + 15], tau3, mask, slots, mylist, cnt,
+                              row0 + 16 * s * slots, nb_real);
+    }
+  }
+}
+
 // smallest distance among the slots of 16 packed accumulators, as a score (sampling pass)
 __device__ __forceinline__ float ham_group_min16(const uint32_t (&v)[16], float magic, int slots) {
   uint32_t m = 255u;
@@ -797,6 +833,8 @@ enum : int { EPI_LISTS = 0, EPI_NEAREST = 1, EPI_DUMP = 2, EPI_GMIN = 3, EPI_HAM
 template <int MODE, int KIND, int LDW>
 __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &E) {
   constexpr bool NF = KIND == OP_F16N;  // |b|^2 folded into the contraction
+  // no |b|^2 tiles travel: folded norms, and the packed Hamming modes (integer epilogue)
+  constexpr bool NOBN = NF || MODE == EPI_HAMP || MODE == EPI_HAMG;
   unsigned char *smem = E.smem;
   const uint32_t sbase = E.sbase, tmem_base = E.tmem_base;
   const int warp = E.warp, lane = E.lane;
@@ -838,7 +876,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
         if (EPI_TEAMS > 1 && (int)buf != team) continue;  // the other team's accumulator buffer
         bool handed_back = false;
         if (clk_on) ck_a = clock64();
-        if (!NF) mbar_wait(bar(E.n_full0 + slot), (tcount / NBN) & 1);  // folded norms: no |b|^2 tiles
+        if (!NOBN) mbar_wait(bar(E.n_full0 + slot), (tcount / NBN) & 1);  // (no |b|^2 tiles otherwise)
         if (P.debug & 256) mbar_wait_spin(bar(E.t_full0 + buf), (tcount >> 1) & 1);
         else mbar_wait(bar(E.t_full0 + buf), (tcount >> 1) & 1);
         tc_fence_after();
@@ -926,6 +964,33 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
               if (valid) grow[(2 * gg + 2) / fold - 1] = gm;
               gm = inf;
             }
+          }
+        } else if (MODE == EPI_HAMP && LDW == 128) {
+          // packed Hamming pass, early hand-back (as the folded-norm k-NN epilogue below): the whole
+          // half tile -- 128 accumulators = up to 384 distances per thread -- comes into registers
+          // with two 64-column loads and ONE wait (a tcgen05.ld + wait::ld round trip costs a warp
+          // ~230 cycles however many columns it brings: 8 of them per tile WERE the tile time), the
+          // buffer goes back to the MMA issuer at once, the byte tests run in its shadow
+          uint32_t va[64], vb[64];
+          const uint32_t ta = lane_addr + buf * TN;
+          const int r0 = (jt * P.tile_stride * TN + half * HALF_N) * P.ham_slots + P.id0;
+          tc_ldw<64>(ta, va);
+          tc_ldw<64>(ta + 64, vb);
+          tc_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t te = buf ? E.t_empty_addr1 : E.t_empty_addr0;
+            if (E.t_empty_remote)
+              mbar_arrive_cluster(te);
+            else
+              mbar_arrive(te);
+          }
+          handed_back = true;
+          if (!(P.debug & 1)) {
+            process_wide_ham<64>(va, P.ham_magic, tau3, ham_mask, P.ham_slots, mylist, cnt, r0, P.ham_nb);
+            process_wide_ham<64>(vb, P.ham_magic, tau3, ham_mask, P.ham_slots, mylist, cnt,
+                                 r0 + 64 * P.ham_slots, P.ham_nb);
           }
         } else if (MODE == EPI_HAMP) {
           // packed Hamming pass: 8 groups of 16 accumulators (16 * ham_slots database rows each)
@@ -1064,7 +1129,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
               mbar_arrive_cluster(te);
             else
               mbar_arrive(te);
-            if (!NF) mbar_arrive(bar(E.n_empty0 + slot));
+            if (!NOBN) mbar_arrive(bar(E.n_empty0 + slot));
           }
         }
         // keep room for a full half tile of appends in every list of the warp
@@ -1252,7 +1317,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
                       qt * TM);
         for (int jt = jt0; jt < jt1; jt++, tcount++) {
           const int jta = jt * P.tile_stride;  // actual database tile
-          if (!NFK) {  // |b|^2 of the tile (the folded-norm kinds carry it in the operands)
+          if (!(NFK || MODE == EPI_HAMP || MODE == EPI_HAMG)) {  // |b|^2 of the tile (the folded-norm kinds carry it in the operands, the packed Hamming modes do not use it)
             const uint32_t slot = tcount % NBN;
             mbar_wait(bar(Smem::n_empty + slot), ((tcount / NBN) & 1) ^ 1);
             mbar_expect_tx(bar(Smem::n_full + slot), TN * 4);
@@ -1473,6 +1538,18 @@ __device__ __forceinline__ void tc_commit_2sm_elect(uint32_t bar, uint16_t mask)
       "h"(mask)
       : "memory");
 }
+__device__ __forceinline__ void tc_mma_f8_2sm_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                    uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_mma_f16_2sm_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                                      uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -1488,11 +1565,31 @@ __device__ __forceinline__ void tc_mma_f16_2sm_elect(uint32_t d_tmem, uint64_t a
 // D=F32, A=B=F16, K-major, N=256, M=256 (two CTAs x 128)
 constexpr uint32_t IDESC_F16_2SM = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
-template <int MODE, int LDW>
+// KIND: OP_F16N (k-NN / k-means) or OP_F8 in the packed Hamming modes (neither reads |b|^2 tiles)
+template <int KIND>
+__device__ __forceinline__ void tc_mma_2sm_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                 uint32_t accumulate) {
+  if (KIND == OP_F8)
+    tc_mma_f8_2sm_elect(d_tmem, a_desc, b_desc, IDESC_F16_2SM, accumulate);
+  else
+    tc_mma_f16_2sm_elect(d_tmem, a_desc, b_desc, IDESC_F16_2SM, accumulate);
+}
+
+// STREAM: the query tile is NOT resident -- every ring stage carries a query chunk (16 KB) next to
+// this CTA's half of the database chunk (16 KB), SST stages in the space of the resident query tile
+// plus the B ring.  Lifts the d <= 240 limit of the resident layout (any d; the price is the query
+// chunks re-read from L2 for every database tile, +50 % operand traffic).
+constexpr int SST = 6;
+constexpr int SSTAGE_BYTES = A_CHUNK_BYTES + B2_CHUNK_BYTES;  // 32 KB
+static_assert(SST * SSTAGE_BYTES <= Smem2::bn_off && SST <= STAGES2, "streamed stages overlay a_off..bn_off");
+
+template <int MODE, int LDW, int KIND = OP_F16N, bool STREAM = false>
 __global__ void __launch_bounds__(TF32_THREADS, 1)
 k_knn_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_bh,
           const __grid_constant__ CUtensorMap map_qx, const __grid_constant__ CUtensorMap map_bxh,
           const Tf32Params P) {
+  static_assert(KIND == OP_F16N || (KIND == OP_F8 && (MODE == EPI_HAMP || MODE == EPI_HAMG)),
+                "the 2-SM kernel carries no |b|^2 ring");
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1500,9 +1597,9 @@ k_knn_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
   volatile uint32_t *tmem_ptr_smem = (volatile uint32_t *)(smem + Smem2::tmem_ptr_off);
   const uint32_t crank = cluster_ctarank();
   const bool leader = crank == 0;
-  const int xk = P.xk;                 // index of the extras chunk (-1: the extras sit inside the last data chunk)
-  const bool xring = P.xring != 0;     // extras travel through their own 2-slot ring
-  constexpr int KCE = KC * 2;          // halfs per 128-byte K chunk
+  const int xk = KIND == OP_F16N ? P.xk : -1;  // index of the extras chunk (-1: the extras sit inside the last data chunk)
+  const bool xring = KIND == OP_F16N && !STREAM && P.xring != 0;  // extras travel through their own 2-slot ring
+  constexpr int KCE = KIND == OP_F8 ? KC * 4 : KC * 2;  // elements per 128-byte K chunk
 
   if (threadIdx.x == 0) {
     mbar_init(bar(Smem2::a_full), 1);
@@ -1549,6 +1646,27 @@ k_knn_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
         const int sp = item / tq_div;
         const int qt = (item - sp * tq_div) * 2 + (int)crank;
         const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
+        if (STREAM) {
+          for (int jt = jt0; jt < jt1; jt++) {
+            const int row0 = jt * P.tile_stride * TN + (int)crank * (TN / 2);
+            for (int kc = 0; kc < P.nkc; kc++, ccount++) {
+              const uint32_t st = ccount % SST;
+              mbar_wait(bar(Smem2::b_empty + st), ((ccount / SST) & 1) ^ 1);
+              const uint32_t a_dst = sbase + st * SSTAGE_BYTES, b_dst = a_dst + A_CHUNK_BYTES;
+              const uint32_t fb = bar(Smem2::b_full + st) & PEER_BIT_MASK;
+              if (kc == xk) {  // the 16 extra K elements of both operands: 32-byte-wide boxes
+                if (leader) mbar_expect_tx(bar(Smem2::b_full + st), 2 * (TM * 32 + XB2_BYTES));
+                tma_load_2d_2sm(a_dst, &map_qx, fb, P.xcol, qt * TM);
+                tma_load_2d_2sm(b_dst, &map_bxh, fb, P.xcol, row0);
+              } else {
+                if (leader) mbar_expect_tx(bar(Smem2::b_full + st), 2 * (A_CHUNK_BYTES + B2_CHUNK_BYTES));
+                tma_load_2d_2sm(a_dst, &map_q, fb, kc * KCE, qt * TM);
+                tma_load_2d_2sm(b_dst, &map_bh, fb, kc * KCE, row0);
+              }
+            }
+          }
+          continue;
+        }
         mbar_wait(bar(Smem2::a_empty), (icount & 1) ^ 1);
         if (leader)  // the leader's barrier collects the bytes of BOTH CTAs
           mbar_expect_tx(bar(Smem2::a_full), (uint32_t)(2 * (nkd * A_CHUNK_BYTES + (xk >= 0 ? TM * 32 : 0))));
@@ -1595,7 +1713,7 @@ k_knn_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
       for (int item = first_item; item < P.items; item += item_step, icount++) {
         const int sp = item / tq_div;
         const int jt0 = sp * P.range_tiles, jt1 = min(P.nbt, jt0 + P.range_tiles);
-        mbar_wait(bar(Smem2::a_full), icount & 1);
+        if (!STREAM) mbar_wait(bar(Smem2::a_full), icount & 1);
         for (int jt = jt0; jt < jt1; jt++, tcount++) {
           const uint32_t buf = tcount & 1;
           if (clk_on) ck_a = clock64();
@@ -1603,6 +1721,28 @@ k_knn_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
           tc_fence_after();
           if (clk_on) ck_acc += clock64() - ck_a;
           const uint32_t d_tmem = tmem_base + buf * TN;
+          if (STREAM) {
+            for (int kc = 0; kc < P.nkc; kc++, ccount++) {
+              const uint32_t st = ccount % SST;
+              if (clk_on) ck_a = clock64();
+              mbar_wait(bar(Smem2::b_full + st), (ccount / SST) & 1);
+              tc_fence_after();
+              if (clk_on) ck_ops += clock64() - ck_a;
+              const uint32_t a_src = sbase + st * SSTAGE_BYTES, b_src = a_src + A_CHUNK_BYTES;
+              if (kc == xk) {
+                tc_mma_2sm_elect<KIND>(d_tmem, smem_desc_sw32(a_src), smem_desc_sw32(b_src), 1);
+              } else {
+                const uint64_t adesc = smem_desc_sw128(a_src), bdesc = smem_desc_sw128(b_src);
+                const int steps = (kc != last_data || P.last_k8 == 4) ? 4 : P.last_k8;
+                for (int k8 = 0; k8 < steps; k8++)
+                  tc_mma_2sm_elect<KIND>(d_tmem, adesc + (uint64_t)(2 * k8), bdesc + (uint64_t)(2 * k8),
+                                         (kc | k8) != 0);
+              }
+              tc_commit_2sm_elect(bar(Smem2::b_empty + st), (uint16_t)3);
+            }
+            tc_commit_2sm_elect(bar(Smem2::t_full + buf), (uint16_t)3);
+            continue;
+          }
           for (int kc = 0; kc < nring; kc++, ccount++) {
             const uint32_t st = ccount % STAGES2;
             if (clk_on) ck_a = clock64();
@@ -1612,17 +1752,17 @@ k_knn_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
             const uint64_t adesc = smem_desc_sw128(sbase + Smem2::a_off + kc * A_CHUNK_BYTES);
             const uint64_t bdesc = smem_desc_sw128(sbase + Smem2::b_off + st * B2_CHUNK_BYTES);
             if (kc == xk) {
-              tc_mma_f16_2sm_elect(d_tmem, smem_desc_sw32(sbase + Smem2::a_off + kc * A_CHUNK_BYTES),
-                                   smem_desc_sw32(sbase + Smem2::b_off + st * B2_CHUNK_BYTES), IDESC_F16_2SM, 1);
+              tc_mma_2sm_elect<KIND>(d_tmem, smem_desc_sw32(sbase + Smem2::a_off + kc * A_CHUNK_BYTES),
+                                     smem_desc_sw32(sbase + Smem2::b_off + st * B2_CHUNK_BYTES), 1);
             } else if (kc != last_data || P.last_k8 == 4) {
-              tc_mma_f16_2sm_elect(d_tmem, adesc, bdesc, IDESC_F16_2SM, kc != 0);
-              tc_mma_f16_2sm_elect(d_tmem, adesc + 2, bdesc + 2, IDESC_F16_2SM, 1);
-              tc_mma_f16_2sm_elect(d_tmem, adesc + 4, bdesc + 4, IDESC_F16_2SM, 1);
-              tc_mma_f16_2sm_elect(d_tmem, adesc + 6, bdesc + 6, IDESC_F16_2SM, 1);
+              tc_mma_2sm_elect<KIND>(d_tmem, adesc, bdesc, kc != 0);
+              tc_mma_2sm_elect<KIND>(d_tmem, adesc + 2, bdesc + 2, 1);
+              tc_mma_2sm_elect<KIND>(d_tmem, adesc + 4, bdesc + 4, 1);
+              tc_mma_2sm_elect<KIND>(d_tmem, adesc + 6, bdesc + 6, 1);
             } else {
               for (int k8 = 0; k8 < P.last_k8; k8++)
-                tc_mma_f16_2sm_elect(d_tmem, adesc + (uint64_t)(2 * k8), bdesc + (uint64_t)(2 * k8),
-                                     IDESC_F16_2SM, (kc | k8) != 0);
+                tc_mma_2sm_elect<KIND>(d_tmem, adesc + (uint64_t)(2 * k8), bdesc + (uint64_t)(2 * k8),
+                                       (kc | k8) != 0);
             }
             tc_commit_2sm_elect(bar(Smem2::b_empty + st), (uint16_t)3);
           }
@@ -1632,13 +1772,13 @@ k_knn_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
             mbar_wait(bar(Smem2::x_full + xs), (tcount >> 1) & 1);
             tc_fence_after();
             if (clk_on) ck_x += clock64() - ck_a;
-            tc_mma_f16_2sm_elect(d_tmem, smem_desc_sw32(sbase + Smem2::a_off + xk * A_CHUNK_BYTES),
-                                 smem_desc_sw32(sbase + Smem2::xb_off + xs * XB2_BYTES), IDESC_F16_2SM, 1);
+            tc_mma_2sm_elect<KIND>(d_tmem, smem_desc_sw32(sbase + Smem2::a_off + xk * A_CHUNK_BYTES),
+                                   smem_desc_sw32(sbase + Smem2::xb_off + xs * XB2_BYTES), 1);
             tc_commit_2sm_elect(bar(Smem2::x_empty + xs), (uint16_t)3);
           }
           tc_commit_2sm_elect(bar(Smem2::t_full + buf), (uint16_t)3);  // accumulators complete in both CTAs
         }
-        tc_commit_2sm_elect(bar(Smem2::a_empty), (uint16_t)3);  // query tiles no longer needed
+        if (!STREAM) tc_commit_2sm_elect(bar(Smem2::a_empty), (uint16_t)3);  // query tiles no longer needed
       }
       if (clk_on && lane == 0 && blockIdx.x < 160) {
         g_tf32_clk[blockIdx.x][0] = ck_acc;
@@ -1661,7 +1801,7 @@ k_knn_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
     ectx.t_empty_addr1 = leader ? bar(Smem2::t_empty + 1) : a1;
     ectx.t_empty_remote = leader ? 0 : 1;   // the leader's own warps arrive locally
     ectx.n_full0 = Smem2::n_full; ectx.n_empty0 = Smem2::n_empty; ectx.t_full0 = Smem2::t_full;
-    run_epilogue<MODE, OP_F16N, LDW>(P, ectx);
+    run_epilogue<MODE, KIND, LDW>(P, ectx);
   } else {
     regs_aux();
   }
@@ -1772,10 +1912,11 @@ static int make_map_f16_extras(CUtensorMap *m, const void *ptr, long rows, int d
 //      folded-norm FP16 kind whenever there are at least two query tiles
 // YAEL_B200_PAIR=0|1|2 overrides (2 only applies to the folded-norm FP16 kind).
 int tf32_pair_mode(int kind, int tiles_q) {
-  int mode = (kind == OP_F16N && tiles_q >= 2) ? 2 : 0;
-  if (const char *e = getenv("YAEL_B200_PAIR")) mode = atoi(e);
-  if (mode == 2 && (kind != OP_F16N || tiles_q < 2)) mode = 0;
-  if (mode == 1 && kind == OP_F8) mode = 0;
+  const bool can2 = (kind == OP_F16N || kind == OP_F8P) && tiles_q >= 2;
+  int mode = can2 ? 2 : 0;
+  if (const char *e = getenv(kind == OP_F8P ? "YAEL_B200_HAM_PAIR" : "YAEL_B200_PAIR")) mode = atoi(e);
+  if (mode == 2 && !can2) mode = 0;
+  if (mode == 1 && (kind == OP_F8 || kind == OP_F8P)) mode = 0;
   if (mode != 0 && (sm_count() & 1)) mode = 0;
   return mode;
 }
@@ -1794,13 +1935,22 @@ Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kp, int kind) {
   // TMA: 16-byte row pitch; the query tile (A) is resident: at most MAX_NKC chunks of 128 bytes
   const bool h = kind == OP_F16 || kind == OP_F16N;
   const int per_chunk = h ? 2 * KC : KC, mult = h ? 8 : 4;
-  if (d < 1 || d > MAX_NKC * per_chunk || (d % mult) != 0) return p;
+  if (d < 1 || (d % mult) != 0) return p;
+  // chunks a resident query tile would need (folded norms: the 16 extras are a chunk of their own
+  // when the data fill whole chunks); more than MAX_NKC: only the streamed 2-SM kernel can do it
+  int chunks = (d + per_chunk - 1) / per_chunk;
+  if (kind == OP_F16N && d >= 16 && ((d - 16) % per_chunk) == 0) chunks = (d - 16) / per_chunk + 1;
+  bool stream = chunks > MAX_NKC;
+  if (kind == OP_F16N && getenv("YAEL_B200_STREAM")) stream = atoi(getenv("YAEL_B200_STREAM")) != 0 || stream;
+  if (stream && kind != OP_F16N) return p;
   if (nq < 1 || nbt_logical < 1 || kp < 1) return p;
   if (kp + 2 * HALF_N > MAXL) return p;  // the in-register compaction handles MAXL entries
   int cap = pow2_ceil(8 * kp);
   if (cap < 512) cap = 512;
   if (cap > MAXL) cap = MAXL;
   const int pair = tf32_pair_mode(kind, (nq + TM - 1) / TM);
+  if (stream && pair != 2) return p;  // (fewer than two query tiles, odd SM count: exact engine)
+  p.stream = stream ? 1 : 0;
   const int G = pair ? sm_count() / 2 : sm_count();          // schedulable units (CTAs or pairs)
   const int tiles_q = pair ? ((nq + TM - 1) / TM + 1) / 2 : (nq + TM - 1) / TM;  // tiles or pairs
   const int nbt = nbt_logical;
@@ -1880,13 +2030,13 @@ static int launch_mode(const Tf32Plan &plan, const CUtensorMap &mq, const CUtens
   return 0;
 }
 
-template <int MODE, int LDW>
+template <int MODE, int LDW, int KIND = OP_F16N, bool STREAM = false>
 static int launch_2sm(const Tf32Plan &plan, const CUtensorMap &mq, const CUtensorMap &mbh,
                       const CUtensorMap &mqx, const CUtensorMap &mbxh, const Tf32Params &P, cudaStream_t st) {
   static bool attr[64] = {};
   cudaError_t ae = cudaSuccess;
   once_per_device(attr, [&ae] {
-    ae = cudaFuncSetAttribute(k_knn_2sm<MODE, LDW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF32_SMEM2_BYTES);
+    ae = cudaFuncSetAttribute(k_knn_2sm<MODE, LDW, KIND, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF32_SMEM2_BYTES);
   });
   if (ae != cudaSuccess) {
     attr[dev_index()] = false;
@@ -1904,7 +2054,7 @@ static int launch_2sm(const Tf32Plan &plan, const CUtensorMap &mq, const CUtenso
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k_knn_2sm<MODE, LDW>, mq, mbh, mqx, mbxh, P);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_knn_2sm<MODE, LDW, KIND, STREAM>, mq, mbh, mqx, mbxh, P);
   if (e != cudaSuccess) return fail(2, "k_knn_2sm cluster launch: %s", cudaGetErrorString(e));
   count_launch();
   return 0;
@@ -1951,10 +2101,11 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
       // 32-byte-wide chunk (a zero-filled 128-byte one costs 2.74 ms instead of 2.62 at d = 128)
       const int dd = d - 16, dbytes = 2 * dd;
       const int nkd = (dbytes + 127) / 128;
-      if (nkd + 1 > MAX_NKC) return fail(6, "folded-norm FP16 operands: d = %d needs too many chunks", dd);
+      if (nkd + 1 > MAX_NKC && !plan.stream)
+        return fail(6, "folded-norm FP16 operands: d = %d needs too many chunks", dd);
       P.xk = nkd;
       P.xcol = dd;
-      P.xring = nkd <= 2 && !getenv("YAEL_B200_NO_XRING");
+      P.xring = nkd <= 2 && !plan.stream && !getenv("YAEL_B200_NO_XRING");
       P.nkc = nkd + 1;
       P.last_k8 = (dbytes - (nkd - 1) * 128 + 31) / 32;
       if ((rc = make_map_f16_extras(&mqx, query, nq, d, TM))) return rc;
@@ -2018,10 +2169,19 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   P.ham_magic = plan.ham_magic;
   if (plan.kind == OP_F8 && plan.ham_slots > 1 && !dump) {
     // packed Hamming passes: ham_slots database rows per accumulator, integer epilogue
-    if (plan.pair) return fail(6, "the E4M3 operand kind has no paired-CTA variant");
+    if (plan.pair == 1) return fail(6, "the E4M3 operand kind has no multicast-pair variant");
     if (plan.kprime + 2 * HALF_N * plan.ham_slots > MAXL)
       return fail(6, "packed Hamming pass: k' = %d leaves no room for a tile of appends", plan.kprime);
+    // YAEL_B200_HAM_LDW=16: the round-1 epilogue (8 x 16-column loads per tile), A/B knob
+    int hldw = 128;
+    if (const char *e = getenv("YAEL_B200_HAM_LDW")) hldw = atoi(e);
+    if (plan.pair == 2) {  // cta_group::2 pairs: each SM holds half of every database chunk
+      if (P.gmin) return launch_2sm<EPI_HAMG, 16, OP_F8>(plan, mq, mbh, mqx, mbxh, P, st);
+      if (hldw == 128) return launch_2sm<EPI_HAMP, 128, OP_F8>(plan, mq, mbh, mqx, mbxh, P, st);
+      return launch_2sm<EPI_HAMP, 16, OP_F8>(plan, mq, mbh, mqx, mbxh, P, st);
+    }
     if (P.gmin) return launch_mode<EPI_HAMG, OP_F8>(plan, mq, mb, mbh, mqx, mbx, P, st);
+    if (hldw == 128) return launch_mode<EPI_HAMP, OP_F8, 128>(plan, mq, mb, mbh, mqx, mbx, P, st);
     return launch_mode<EPI_HAMP, OP_F8>(plan, mq, mb, mbh, mqx, mbx, P, st);
   }
   if (plan.kind == OP_F8) {
@@ -2045,6 +2205,15 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   // 64 -> 2.50, 128 -> 2.33 (1-SM kernel: 2.52 / 2.47 / 2.50 / 2.40); k-means config 4: 176 -> 150 ms.
   int ldw = 128;
   if (const char *e = getenv("YAEL_B200_LDW")) ldw = atoi(e);
+  if (plan.kind == OP_F16N && plan.pair == 2 && plan.stream) {  // streamed query chunks: any d
+    switch (mode) {
+      case EPI_DUMP: return launch_2sm<EPI_DUMP, 16, OP_F16N, true>(plan, mq, mbh, mqx, mbxh, P, st);
+      case EPI_GMIN: return launch_2sm<EPI_GMIN, 16, OP_F16N, true>(plan, mq, mbh, mqx, mbxh, P, st);
+      case EPI_LISTS: return launch_2sm<EPI_LISTS, 128, OP_F16N, true>(plan, mq, mbh, mqx, mbxh, P, st);
+      default: return launch_2sm<EPI_NEAREST, 128, OP_F16N, true>(plan, mq, mbh, mqx, mbxh, P, st);
+    }
+  }
+  if (plan.stream) return fail(6, "streamed query chunks need the 2-SM folded-norm kernel");
   if (plan.kind == OP_F16N && plan.pair == 2) {  // cta_group::2 pairs (k_knn_2sm)
     switch (mode) {
       case EPI_DUMP: return launch_2sm<EPI_DUMP, 16>(plan, mq, mbh, mqx, mbxh, P, st);
