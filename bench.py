@@ -632,6 +632,55 @@ def measure_kmeans(torch, L, dev, niter=10):
     return block
 
 
+def measure_cross(torch, L, dev):
+    """compute_cross_distances (yael/nn.c:92-129) at 10 000 x 100 000 x 128: the tensor-core engine
+    (split-precision FP16 operands, both norms folded into the contraction; output-bound: 4 B per pair)
+    beside the exact FP32 engine, CUDA events on the launching stream, and a parity slice against the
+    oracle (north star: within 1e-5 relative)."""
+    from oracle import bindings as ob
+    na, nb, d = 10_000, 100_000, 128
+    g = torch.Generator(device=dev)
+    g.manual_seed(4242)
+    a = torch.rand((na, d), device=dev, generator=g)
+    b = torch.rand((nb, d), device=dev, generator=g)
+    out = torch.empty((nb, na), device=dev)
+    st = torch.cuda.current_stream()
+    sp = C.c_void_p(st.cuda_stream)
+    res = {}
+    for engine, name in ((1, "tensor_split_fp16"), (0, "exact_fp32_simt")):
+        L.yb_set_cross_engine(engine)
+        for _ in range(2):
+            rc = L.yb_cross_distances_l2(d, na, nb, a.data_ptr(), d, b.data_ptr(), d, out.data_ptr(), na, sp)
+            assert rc == 0, L.yb_last_error()
+        torch.cuda.synchronize()
+        reps = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(reps):
+            L.yb_cross_distances_l2(d, na, nb, a.data_ptr(), d, b.data_ptr(), d, out.data_ptr(), na, sp)
+        e1.record(st)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        res[name] = {"ms": ms, "engine_used": int(L.yb_last_cross_engine()),
+                     "pairs_per_s": na * nb / (ms * 1e-3), "output_GBps": 4.0 * na * nb / (ms * 1e-3) / 1e9}
+        if engine == 1:
+            got = out[:2000, :512].cpu().numpy()
+    L.yb_set_cross_engine(-1)
+    ah, bh = a[:512].cpu().numpy(), b[:2000].cpu().numpy()
+    want = ob.orc_cross(ah, bh, ob.DOT_F32_SEQ)
+    rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-30)
+    peaks = _peaks()
+    hbm = peaks.get("hbm_gbs", 6450.0)
+    t = res["tensor_split_fp16"]
+    return {"metric": "compute_cross_distances pairs/s (10k x 100k x 128)", "value": t["pairs_per_s"], "unit": "pairs/s",
+            "ms_per_step": t["ms"], "engines": res,
+            "roofline": {"bound": "hbm", "kernel": "k_knn_2sm<EPI_CROSS> (output: 4 B per pair; operands 0.1 GB)",
+                         "achieved": t["output_GBps"], "peak": hbm, "unit": "GB/s", "frac": t["output_GBps"] / hbm,
+                         "traffic": None, "algorithmic_bytes_per_launch": 4.0 * na * nb + 4.0 * d * (na + nb)},
+            "parity": {"config": "512 x 2000 slice of the 10k x 100k matrix vs the oracle (FP32 FMA chain)",
+                       "max_rel_dis": float(rel.max()), "ok": bool(rel.max() <= 1e-5)}}
+
+
 def measure_extras_sharded(torch, dist, ydist, L, dev, rank, world):
     """N > 1: the other two BASELINE shapes SHARDED over the ranks, total work fixed:
       - k-means, BASELINE configs[3]: n = 10M points split over the ranks, k = 65536, d = 128; one
@@ -944,7 +993,7 @@ def run_ours(args):
     parity = knn_parity(res_idx, res_dis, widx, wdis, base_h, query_h,
                         "C2: 1M x 128 database, k=100 (BASELINE configs[1])")
 
-    kmeans_block = hamming_block = None
+    kmeans_block = hamming_block = cross_block = None
     if world == 1 and not args.no_extras:
         try:
             hamming_block = measure_hamming(torch, L, dev)
@@ -954,6 +1003,10 @@ def run_ours(args):
             kmeans_block = measure_kmeans(torch, L, dev, args.kmeans_iters)
         except Exception as e:
             kmeans_block = {"error": str(e)}
+        try:
+            cross_block = measure_cross(torch, L, dev)
+        except Exception as e:
+            cross_block = {"error": str(e)}
     elif extras_sharded:
         kmeans_block = extras_sharded.get("kmeans_10Mx128_k65536_sharded") or {"error": extras_sharded.get("kmeans_error")}
         hamming_block = extras_sharded.get("hamming_knn_10Mx64bit_10kq_k100_sharded") or {"error": extras_sharded.get("hamming_error")}
@@ -978,7 +1031,7 @@ def run_ours(args):
         },
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roof, "cpu_baseline": cpu, "parity": parity, "parity_sharded": parity_sharded,
-        "kmeans": kmeans_block, "hamming": hamming_block,
+        "kmeans": kmeans_block, "hamming": hamming_block, "cross_distances": cross_block,
     }))
     if world > 1:
         dist.destroy_process_group()

@@ -84,6 +84,13 @@ void yb_release_scratch(void); /* drop the cached workspace of the current devic
  * compute_cross_distances_nonpacked (yael/nn.c:100-129). */
 int yb_cross_distances_l2(int d, int na, int nb, const float *a, int lda, const float *b,
                           int ldb, float *dist2, int ldd, yb_stream_t s);
+/* engine of yb_cross_distances_l2 / compute_cross_distances: 0 = exact FP32 on CUDA cores (the
+ * reference's rounding sequence, bit for bit), 1 = tcgen05 with split-precision FP16 operands and
+ * both norms folded into the contraction (within 1e-5 relative of the exact engine; packed
+ * matrices, na > 128), -1 = automatic: tensor cores for large problems (default;
+ * YAEL_B200_CROSS_ENGINE overrides).  yb_last_cross_engine: what the last call of this thread used. */
+void yb_set_cross_engine(int engine);
+int yb_last_cross_engine(void);
 /* dist2[j] for one query a[d] against nb rows, both norms in double:
  * compute_distances_1_nonpacked (yael/nn.c:132-154). */
 int yb_distances_1(int d, int nb, const float *a, const float *b, int ldb, float *dist2,

@@ -20,7 +20,8 @@ base = torch.randint(0, 256, (nb, nc), device="cuda", dtype=torch.uint8)
 query = torch.randint(0, 256, (nq, nc), device="cuda", dtype=torch.uint8)
 idx = torch.empty((nq, k), device="cuda", dtype=torch.int32)
 dis = torch.empty((nq, k), device="cuda", dtype=torch.int16)
-for engine in (0, 1):
+engines = (1,) if os.environ.get("ONLY_TC") else (0, 1)
+for engine in engines:
     L.yb_set_hamming_engine(engine)
     L.yb_prof_enable(1)
     L.yb_prof_ms(0, None, 1)
@@ -41,8 +42,20 @@ for engine in (0, 1):
             print("  phase %-14s %.3f ms avg over %d" % (name, ms / cnt.value, cnt.value))
     L.yb_prof_enable(0)
     print(idx[0, :5].tolist(), dis[0, :5].tolist())
+    if int(os.environ.get("YAEL_B200_TF32_DEBUG", "0")) & 512 and engine == 1:
+        import numpy as np
+        ck = np.zeros((148, 16), np.int64)
+        L.yb_debug_tf32_clocks(ck.ctypes.data_as(C.c_void_p), 148)
+        m = ck[ck[:, 8] > 0]
+        t = m[:, 8].astype(np.float64)
+        names = ["issuer: wait accumulator", "issuer: wait operands", "issuer: wait extras", "issuer: total",
+                 "epilogue: wait accumulator", "epilogue: drain", "epilogue: hand back", "epilogue: total"]
+        print("clock attribution (cycles per tile, mean over %d CTAs, %.0f tiles per CTA; LAST instrumented pass):" % (len(m), t.mean()))
+        for i, nme in enumerate(names):
+            sel = m[:, i] > 0
+            print("  %-28s %8.1f" % (nme, (m[sel, i] / t[sel]).mean() if sel.any() else 0.0))
     if engine == 0:
         ref = (idx.clone(), dis.clone())
-    else:
+    elif len(engines) > 1:
         print("engines agree:", bool(torch.equal(ref[0], idx) and torch.equal(ref[1], dis)))
 L.yb_set_hamming_engine(-1)

@@ -325,3 +325,46 @@ def test_kmeans_points_at_the_centroid_mean(yn, ob, tf32_engine):
     assert np.array_equal(dis, wd)
     assert np.array_equal(assign, wa)
     assert np.array_equal(nassign, wn)
+
+
+# ---------------------------------------------------------------- d beyond the resident query tile
+@pytest.mark.parametrize("nq,nb,d,k", [(300, 20000, 256, 10), (256, 30000, 384, 100), (400, 8000, 960, 20),
+                                        (1000, 20000, 200, 1), (512, 10000, 960, 1), (260, 5000, 1000, 7)])
+def test_knn_tensor_engine_large_d_matches_oracle(yn, ob, tf32_engine, nq, nb, d, k):
+    # d > 240: the query tile no longer fits in shared memory next to the database ring; the 2-SM kernel
+    # streams the query chunks through the ring with the database chunks (k_knn_2sm<.., STREAM>).
+    # GIST1M has d = 960; the reference has no limit on d (yael/nn.c:451-525).
+    r = rs(nq + nb + d + k)
+    b = r.rand(nb, d).astype(np.float32)
+    q = r.rand(nq, d).astype(np.float32)
+    idx, dis = yn.knn(q, b, k)
+    assert tf32_engine.yb_last_knn_engine() == 1, "d = %d fell back to the exact engine" % d
+    widx, wdis = ob.orc_knn(b, q, k, ob.DOT_F32_SEQ, canonical=True)
+    check_knn(idx, dis, widx, wdis, b, q)
+    assert tf32_engine.yb_last_knn_uncertified() <= nq // 10
+
+
+@pytest.mark.parametrize("d,k", [(128, 100), (96, 10), (64, 1), (128, 1)])
+def test_knn_streamed_query_chunks_equal_resident_tile(yn, tf32_engine, monkeypatch, d, k):
+    # the streamed variant forced at a d the resident layout handles too: identical results
+    r = rs(d + k)
+    b = r.rand(40000, d).astype(np.float32)
+    q = r.rand(520, d).astype(np.float32)
+    i0, d0 = yn.knn(q, b, k)
+    monkeypatch.setenv("YAEL_B200_STREAM", "1")
+    i1, d1 = yn.knn(q, b, k)
+    assert tf32_engine.yb_last_knn_engine() == 1
+    assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+
+
+def test_kmeans_assignment_large_d(yn, ob, tf32_engine):
+    r = rs(99)
+    v = r.rand(20000, 320).astype(np.float32)
+    c0 = v[r.permutation(20000)[:300]].copy()
+    cent, qerr, dis, assign, nassign = yn.kmeans(v, 300, niter=1, verbose=False, init=c0, output="all")
+    q, wc, wa, wd, wn = ob.orc_kmeans_step(v, c0)
+    mism = assign != wa
+    assert np.all(np.abs(dis[mism] - wd[mism]) <= 1e-5 * wd[mism])
+    assert mism.mean() < 1e-3
+    np.testing.assert_allclose(dis, wd, rtol=1e-5)
+    np.testing.assert_allclose(cent, wc, atol=1e-4)

@@ -139,6 +139,8 @@ DEVICE = {
     "yb_d2h": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
     "yb_release_scratch": (None, []),
     "yb_cross_distances_l2": (C.c_int, [C.c_int] * 3 + [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp]),
+    "yb_set_cross_engine": (None, [C.c_int]),
+    "yb_last_cross_engine": (C.c_int, []),
     "yb_distances_1": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp]),
     "yb_cross_distances_alt": (C.c_int, [C.c_int] * 4 + [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp]),
     "yb_knn_l2": (C.c_int, [C.c_int] * 4 + [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),

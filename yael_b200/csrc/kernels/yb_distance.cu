@@ -11,6 +11,8 @@
 // These kernels define the VALUES the library returns.  The tcgen05 TF32 kernel
 // (yb_knn_tf32.cu) only ever produces a shortlist that is re-ranked with the same
 // arithmetic as here (yb_knn.cu: k_rerank).
+#include <stdlib.h>
+
 #include "yb_common.cuh"
 #include "yb_internal.cuh"
 
@@ -283,6 +285,14 @@ int l2_matrix(int d, long na, long nb, const float *a, long lda, const float *b,
 
 using namespace yb;
 
+// engine of yb_cross_distances_l2: 0 = exact FP32 (k_l2_simt: the reference's rounding sequence,
+// bit for bit), 1 = tensor cores with split-precision FP16 operands (within the north star's 1e-5
+// relative; large packed problems), -1 = automatic (YAEL_B200_CROSS_ENGINE overrides)
+static int g_cross_engine = -1;
+static thread_local int g_last_cross_engine = 0;
+extern "C" void yb_set_cross_engine(int engine) { g_cross_engine = engine; }
+extern "C" int yb_last_cross_engine(void) { return g_last_cross_engine; }
+
 extern "C" int yb_cross_distances_l2(int d, int na, int nb, const float *a, int lda,
                                       const float *b, int ldb, float *dist2, int ldd,
                                       yb_stream_t s) {
@@ -290,6 +300,21 @@ extern "C" int yb_cross_distances_l2(int d, int na, int nb, const float *a, int 
   if (d < 0 || lda < d || ldb < d || ldd < na) return fail(3, "yb_cross_distances_l2: bad leading dimension");
   Guard g;
   cudaStream_t st = stream_of(s);
+  g_last_cross_engine = 0;
+  {
+    int engine = g_cross_engine;
+    if (const char *e = getenv("YAEL_B200_CROSS_ENGINE")) engine = atoi(e);
+    const bool packed = lda == d && ldb == d && d >= 1;
+    const bool big = (double)na * nb * d >= 2e9 && na >= 256 && nb >= 1024;
+    if (packed && (engine == 1 || (engine < 0 && big))) {
+      const int rc = cross_l2_tensor(d, na, nb, a, b, dist2, ldd, st);
+      if (rc == 0) {
+        g_last_cross_engine = 1;
+        return 0;
+      }
+      if (rc != -1000 && rc != -1001) return rc;  // does not qualify / out of FP16 range: exact engine
+    }
+  }
   ScratchScope ws(l2_ws_bytes(na, nb), st);
   Carver c(ws.p);
   float *an = c.take<float>(na);

@@ -79,7 +79,7 @@ constexpr int HF_CAP = 8192;      // keys per query held in shared memory (64 KB
 constexpr int HF_LISTS = 1024;    // lists per query
 
 __global__ void __launch_bounds__(HF_T)
-k_ham_tc_finish(int nq, int k, int lists, int kp, const int *__restrict__ cnt,
+k_ham_tc_finish(int nq, int nb, int k, int lists, int kp, const int *__restrict__ cnt,
                 const float *__restrict__ score, const int *__restrict__ id,
                 const float *__restrict__ lthr, int id_offset, int *__restrict__ assign,
                 uint16_t *__restrict__ dis, int *__restrict__ flags) {
@@ -119,14 +119,16 @@ k_ham_tc_finish(int nq, int k, int lists, int kp, const int *__restrict__ cnt,
     const size_t src = ((size_t)q * lists + l) * kp;
     for (int e = lane; e < n; e += 32) {
       const unsigned dist = (unsigned)__float2int_rn(score[src + e] * 0.25f);
-      keys[o + e] = ((unsigned long long)dist << 32) | (unsigned)id[src + e];
+      const unsigned row = (unsigned)id[src + e];
+      // (rows of the tile padding can never be listed -- NaN accumulators -- but cost nothing to refuse)
+      keys[o + e] = row < (unsigned)nb ? (((unsigned long long)dist << 32) | row) : ~0ull;
     }
   }
   for (int e = total + tid; e < m_pad; e += HF_T) keys[e] = ~0ull;
   bitonic_sort_u64(keys, m_pad, tid, HF_T, [] { __syncthreads(); });
   // certificate: every unlisted row has score >= tmin, the k-th listed one must be below it
   const float sk = 4.0f * (float)(unsigned)(keys[k - 1] >> 32);
-  const bool ok = sk < tmin_s;
+  const bool ok = keys[k - 1] != ~0ull && sk < tmin_s;
   if (tid == 0) flags[q] = ok ? 0 : 1;
   if (!ok) return;
   for (int j = tid; j < k; j += HF_T) {
@@ -166,21 +168,32 @@ static HamSample ham_sample_geometry(int nbt, int k) {
   while (s.gsize < 128 && srows / s.gsize > maxn) s.gsize *= 2;
   s.gcols = srows / s.gsize;
   s.j2 = (3 * k + s.stride - 1) / s.stride;
-  if (s.j2 < 32) s.j2 = 32;
+  // floor of the order-statistic rank: Hamming distances fall into coarse classes (x3 rows per unit of
+  // distance at the BASELINE shape), so the threshold snaps to a class boundary and a small rank is
+  // stable.  Measured (10 k queries, k = 100, pass + finish in ms, 0 scan fallbacks throughout):
+  // 10 M rows: rank 32 -> 13.7 + 0.92, 20 -> 12.9 + 0.60, 16 -> 12.2 + 0.39, 12 -> 12.0 + 0.35;
+  // 1.25 M rows: 3.15 + 0.48, 2.51 + 0.30, 2.46 + 0.28, 2.46 + 0.29
+  int j2_floor = 16;
+  if (const char *e = getenv("YAEL_B200_HAM_J2")) j2_floor = atoi(e) > 0 ? atoi(e) : j2_floor;  // A/B knob
+  if (s.j2 < j2_floor) s.j2 = j2_floor;
   s.ok = s.gcols <= maxn && (long)s.j2 * 4 <= s.gcols;
   return s;
 }
 
 // database rows per accumulator.  Codes of up to 64 bits CAN pack 3 rows, 128 bits 2 (the packed
 // fields are one byte each and the sum must stay below 2^23), longer ones 1; fewer when k' leaves
-// no room for a tile of packed appends.  Packing pays only when admissions are sparse, i.e. for
-// very large databases (measured, 10 k queries x 64-bit codes, pass in ms, 1 row vs 3 rows per
-// accumulator: 1.25 M rows 4.0 vs 7.5, 5 M rows 12.0 vs 13.8, 10 M rows 23.0 vs 21.6): the
-// decoder of the packed epilogue scans 48 candidates per call.  Default: pack from 8 M rows on.
-// YAEL_B200_HAM_SLOTS=1|2|3 forces a packing (tests, A/B measurements).
+// no room for a tile of packed appends.  Round 1 packed from 8 M rows on (the float epilogue of the
+// one-row pass cost 2117 clk per tile: 10 M rows 23.0 ms unpacked vs 21.6 packed).  Round 2: with the
+// constant-norm MAX-tree epilogue (operand kind 5: wide TMEM loads, early hand-back, no |b|^2 ring)
+// the one-row pass takes ~1000 clk per 256-row tile and wins at every size (10 M rows: 12.2 ms vs
+// 19.7 packed; 1.25 M: 2.5 vs 6.8) -- the ncu source page of the packed pass showed why packing could
+// not pay: ~57 instructions per 16 accumulators at 0.17 IPC per warp plus a 160-instruction decoder
+// on 15 % of the groups.  Default: one row per accumulator; YAEL_B200_HAM_SLOTS=2|3 selects the packed
+// pass (tests keep it covered, A/B measurements).
 static int ham_slots_for(int W, int k, long nb) {
   const int smax = W == 1 ? 3 : (W == 2 ? 2 : 1);
-  int S = nb >= 8000000L ? smax : 1;
+  (void)nb;
+  int S = 1;
   if (const char *e = getenv("YAEL_B200_HAM_SLOTS")) {
     const int want = atoi(e);
     if (want >= 1) S = want < smax ? want : smax;
@@ -191,13 +204,17 @@ static int ham_slots_for(int W, int k, long nb) {
 
 static Tf32Plan ham_plan(int nq, int nb, int W, int k, int S) {
   const int nc = (nb + S - 1) / S;
-  // packed passes may run as cta_group::2 pairs (planning kind 4 = OP_F8P, yb_knn_tf32.cu)
-  Tf32Plan plan = tf32_plan(nq, nc, 16 * W * S, k, S > 1 ? 4 : 0);
-  plan.kind = 1;
+  // packed passes: E4M3 with the integer epilogue (planning kind 4 = OP_F8P, then kind 1); one row
+  // per accumulator: kind 5 (E4M3, constant |b|^2 = 2 * bits: s = 2 bits - 2 dot = 4 ham) with the
+  // MAX-tree epilogue of the folded-norm k-NN pass.  Both may run as cta_group::2 pairs.
+  Tf32Plan plan = tf32_plan(nq, nc, 16 * W * S, k, S > 1 ? 4 : 5);
   if (S > 1) {
+    plan.kind = 1;
     plan.ham_slots = S;
     plan.ham_nb = nb;
     plan.ham_magic = 8388608.0f + (float)(32 * W) * (S == 3 ? 65793.0f : 257.0f);
+  } else {
+    plan.score_c0 = 128.0f * (float)W;
   }
   return plan;
 }
@@ -229,16 +246,17 @@ int hamming_tc(int nq, int nb, int W, int k, const unsigned long long *pb,
   const HamSample sg = ham_sample_geometry(nbt, k);
   Tf32Plan splan = {};
   if (sg.ok) {
-    splan = tf32_plan_tiles(nq, sg.nbt_s, dfl, sg.j2);
-    splan.kind = 1;
+    splan = tf32_plan_tiles(nq, sg.nbt_s, dfl, sg.j2, S > 1 ? 0 : 5);
+    if (S > 1) splan.kind = 1;
     splan.ham_slots = plan.ham_slots;
     splan.ham_nb = plan.ham_nb;
     splan.ham_magic = plan.ham_magic;
+    splan.score_c0 = plan.score_c0;
   }
-  const bool sample = sg.ok && splan.ok && !splan.pair;
+  const bool sample = sg.ok && splan.ok && splan.pair != 1;
   const size_t stride = (size_t)plan.lists * kp;
   const size_t rowb = 64ull * W * S;
-  size_t need = Carver::need(rowb * nc) + Carver::need(rowb * nq) +
+  size_t need = Carver::need(rowb * (size_t)padded) + Carver::need(rowb * nq) +
                 Carver::need(sizeof(float) * (size_t)padded) +
                 Carver::need(sizeof(float) * nq * stride) + Carver::need(sizeof(int) * nq * stride) +
                 2 * Carver::need(sizeof(float) * (size_t)nq * plan.lists) +
@@ -250,7 +268,7 @@ int hamming_tc(int nq, int nb, int W, int k, const unsigned long long *pb,
   {
     ScratchScope ws(need, st);
     Carver c(ws.p);
-    void *base8 = c.take<char>(rowb * nc);
+    void *base8 = c.take<char>(rowb * (size_t)padded);
     void *query8 = c.take<char>(rowb * nq);
     float *an = c.take<float>(padded);
     float *cscore = c.take<float>(nq * stride);
@@ -267,12 +285,11 @@ int hamming_tc(int nq, int nb, int W, int k, const unsigned long long *pb,
       ProfScope ps(12, st);
       if ((rc = expand_codes(pb, nb, W, S, S > 1, nc, base8, st))) return rc;
       if ((rc = expand_codes(pq, nq, W, S, 0, nq, query8, st))) return rc;
-      if (S == 1) {  // one row per accumulator: the float epilogue, s = 2 bits - 2 dot = 4 ham
-        if ((rc = fill_f32(an, nb, 2.0f * (float)bits, st))) return rc;
-        if ((rc = fill_f32(an + nb, padded - nb, __builtin_inff(), st))) return rc;
-      } else {       // packed: the integer epilogue does not read |b|^2 (the ring still carries it)
-        if ((rc = fill_f32(an, padded, 0.0f, st))) return rc;
+      if (S == 1) {  // one row per accumulator: constant |b|^2; the tile padding is E4M3 NaN (0x7F)
+        if (padded > nc)
+          YB_CUDA(cudaMemsetAsync((char *)base8 + rowb * (size_t)nc, 0x7F, rowb * (size_t)(padded - nc), st));
       }
+      (void)bits;
       YB_CUDA(cudaMemsetAsync(flag_count, 0, 64, st));
     }
     const float *thr0 = nullptr;
@@ -302,7 +319,7 @@ int hamming_tc(int nq, int nb, int W, int k, const unsigned long long *pb,
       once_per_device(attr, [] {
         cudaFuncSetAttribute(k_ham_tc_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, HF_CAP * 8);
       });
-      k_ham_tc_finish<<<nq, HF_T, HF_CAP * 8, st>>>(nq, k, plan.lists, kp, ccnt, cscore, cid, cthr,
+      k_ham_tc_finish<<<nq, HF_T, HF_CAP * 8, st>>>(nq, nb, k, plan.lists, kp, ccnt, cscore, cid, cthr,
                                                     id_offset, assign, dis, flags);
       YB_LAUNCH_CHECK();
       k_ham_collect<<<(nq + 255) / 256, 256, 0, st>>>(flags, nq, flag_list, flag_count);

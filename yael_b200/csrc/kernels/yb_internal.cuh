@@ -35,6 +35,8 @@ struct Tf32Plan {
   int kind;        // operand kind: 0 = FP32 rows read as TF32 (kind::tf32); 1 = E4M3 bytes
                    // (kind::f8f6f4; `base` / `query` point to [rows][4*d] BYTE matrices -- the Hamming
                    // path); 2 = FP16 (kind::f16; [rows][d] half matrices, d % 8 == 0; k = 1 mode);
+                   // 5 = E4M3 bytes whose |b|^2 is one constant (score_c0; Hamming, one row per
+                   // accumulator): no |b|^2 tiles, padding rows are E4M3 NaN;
                    // 3 = FP16 with folded norms (the LAST 16 elements of a row carry |b|^2
                    // (database) resp. 2^15 (queries), see center_operands_h; the database copy is
                    // padded to tf32_padded_rows(nb) rows; top-k', sampling and dump modes)
@@ -43,6 +45,7 @@ struct Tf32Plan {
   // rows share one accumulator; ham_nb real rows; ham_magic = 2^23 + (bits/2)(1 + 2^8 [+ 2^16])
   int ham_slots, ham_nb;
   float ham_magic;
+  float score_c0;  // kind 5 (E4M3, constant |b|^2): score = acc * a + score_c0
 };
 Tf32Plan tf32_plan(int nq, int nb, int d, int k, int kind = 0);
 Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kprime, int kind = 0);
@@ -66,7 +69,14 @@ struct Tf32Out {
   float *gmin;   // group-minimum mode (tf32_group_min)
   long gmin_ld;
   int gsize;
+  int cross;     // dump mode writes out[row * ld + query] (tf32_cross)
 };
+int tf32_cross(const Tf32Plan &plan, int nq, int nb, int d, const float *base, const float *query,
+               float *out, long ld, void *ws, cudaStream_t st);
+// yb_knn.cu: compute_cross_distances on the tensor cores (split-precision FP16 operands, both norms
+// folded into the contraction); -1000: shape does not qualify, -1001: a value left FP16's range
+int cross_l2_tensor(int d, int na, int nb, const float *a, const float *b, float *out, long ldd,
+                    cudaStream_t st);
 int tf32_group_min(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical, int tile_stride,
                    const float *base, const float *query, const float *bnorm_padded, float *gmin,
                    long ld, int gsize, void *ws, cudaStream_t st);

@@ -1147,6 +1147,116 @@ static int center_operands_h(int nq, int nb, int d, int dh, int df, const float 
   return 0;
 }
 
+// ---------------------------------------------------------------- compute_cross_distances, tensor cores
+// Split-precision FP16 operands for the FULL distance matrix (yael/nn.c:100-129 within the north
+// star's 1e-5): a centred, scaled coordinate w = hi + lo (+ r, |r| <= 2^-22 |w|), both halves FP16, and
+//     <a, b> ~ <a_hi, b_hi> + <a_hi, b_lo> + <a_lo, b_hi>
+// is ONE contraction over K = 3 dh: query rows [hi | hi | lo], database rows [hi | lo | hi].  The 16
+// extra K elements carry BOTH norms: database rows -beta pieces x query 2^15 (as write_row_extras)
+// and query rows -alpha pieces x database 2^15, alpha = 2^(2 sigma - 1) |a-mu|^2 / 2^15.  The
+// accumulator is then 2^(2 sigma) (<a,b> - |a|^2/2 - |b|^2/2) and the distance asc * acc: the
+// epilogue only scales and stores.
+__global__ void __launch_bounds__(256)
+k_split_rows_h(const float *__restrict__ x, long n, int d, int dh, int role,
+               const float *__restrict__ mu, const float *__restrict__ scal,
+               __half *__restrict__ out_h, int *__restrict__ oflag) {
+  const long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  const float sc = scal[2];
+  const int pitch = 3 * dh + kNfExtra;
+  __half *row = out_h + r * pitch;
+  float s = 0.f;
+  bool over = false;
+  for (int c = lane; c < dh; c += 32) {
+    const float v = c < d ? __fsub_rn(x[r * d + c], __ldg(mu + c)) : 0.f;
+    const float w = v * sc;
+    over |= fabsf(w) > 65504.0f && fabsf(v) < __int_as_float(0x7f800000);
+    const __half hi = __float2half_rn(w);
+    const __half lo = __float2half_rn(w - __half2float(hi));
+    row[c] = hi;
+    row[dh + c] = role == 1 ? lo : hi;
+    row[2 * dh + c] = role == 1 ? hi : lo;
+    s = fmaf(v, v, s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    const float w = s * sc * sc * (0.5f / 32768.0f);
+    if (w > 65504.0f && w < __int_as_float(0x7f800000)) over = true;
+    const __half h0 = __float2half_rn(w);
+    const float r1 = w - __half2float(h0);
+    const __half h1 = __float2half_rn(r1);
+    const __half h2 = __float2half_rn(r1 - __half2float(h1));
+    const __half big = __ushort_as_half((unsigned short)0x7800);  // 32768.0
+    __half *e = row + 3 * dh;
+    const int own = role == 1 ? 0 : 3, other = role == 1 ? 3 : 0;
+    e[own + 0] = __hneg(h0); e[own + 1] = __hneg(h1); e[own + 2] = __hneg(h2);
+    e[other + 0] = big; e[other + 1] = big; e[other + 2] = big;
+    for (int j = 6; j < kNfExtra; j++) e[j] = __ushort_as_half((unsigned short)0);
+  }
+  if (over) *oflag = 1;
+}
+
+int cross_l2_tensor(int d, int na, int nb, const float *a, const float *b, float *out, long ldd,
+                    cudaStream_t st) {
+  if (d < 1 || na <= 128 || nb < 1) return -1000;  // the 2-SM kernel pairs two query tiles
+  const int dh = (d + 15) & ~15, dop = 3 * dh + kNfExtra;
+  Tf32Plan plan = tf32_plan_tiles(na, tf32_tiles(nb), dop, 1, 3);
+  if (!plan.ok || plan.pair != 2) return -1000;
+  const long padded = tf32_padded_rows(nb);
+  const size_t need = Carver::need(2 * (size_t)padded * dop) + Carver::need(2 * (size_t)na * dop) +
+                      Carver::need(64) + center_ws_bytes(nb, d) + Carver::need(plan.ws_bytes) + 1024;
+  ScratchScope ws(need, st);
+  Carver c(ws.p);
+  __half *b_h = (__half *)c.take<char>(2 * (size_t)padded * dop);
+  __half *a_h = (__half *)c.take<char>(2 * (size_t)na * dop);
+  float *scal = c.take<float>(16);
+  void *cws = c.take<char>(center_ws_bytes(nb, d));
+  void *tws = c.take<char>(plan.ws_bytes);
+  YB_CUDA(cudaMemsetAsync(scal, 0, 64, st));
+  {
+    Carver cc(cws);  // column mean of the database rows and the power-of-two scale (as center_operands_h)
+    int nblk = (int)(((long)nb + CM_ROWS - 1) / CM_ROWS);
+    if (nblk > CM_BLOCKS) nblk = CM_BLOCKS;
+    long step = nblk > 0 ? (long)nb / nblk : CM_ROWS;
+    if (step < CM_ROWS) step = CM_ROWS;
+    float *psum = cc.take<float>((size_t)CM_BLOCKS * d);
+    int *pcnt = cc.take<int>((size_t)CM_BLOCKS * d);
+    float *mu = cc.take<float>(d);
+    k_col_partial<<<nblk, 256, 0, st>>>(b, nb, d, step, psum, pcnt);
+    YB_LAUNCH_CHECK();
+    k_col_final<<<(d + 127) / 128, 128, 0, st>>>(psum, pcnt, nblk, d, mu);
+    YB_LAUNCH_CHECK();
+    k_mu_norm<<<1, 32, 0, st>>>(mu, d, scal + 7);
+    YB_LAUNCH_CHECK();
+    // sampled max |x| with 8x head room; a value that still overflows raises the flag (-1001)
+    k_absmax_sample<<<nblk, 256, 0, st>>>(b, nb, d, step, scal + 6);
+    YB_LAUNCH_CHECK();
+    int qblk = (int)(((long)na + CM_ROWS - 1) / CM_ROWS);
+    if (qblk > CM_BLOCKS) qblk = CM_BLOCKS;
+    long qstep = qblk > 0 ? (long)na / qblk : CM_ROWS;
+    if (qstep < CM_ROWS) qstep = CM_ROWS;
+    k_absmax_sample<<<qblk, 256, 0, st>>>(a, na, d, qstep, scal + 6);
+    YB_LAUNCH_CHECK();
+    k_pick_scale<<<1, 1, 0, st>>>(scal, d, mu);
+    YB_LAUNCH_CHECK();
+    int *oflag = (int *)(scal + 4);
+    k_split_rows_h<<<(unsigned)((nb + 7) / 8), 256, 0, st>>>(b, nb, d, dh, 1, mu, scal, b_h, oflag);
+    YB_LAUNCH_CHECK();
+    k_split_rows_h<<<(unsigned)((na + 7) / 8), 256, 0, st>>>(a, na, d, dh, 2, mu, scal, a_h, oflag);
+    YB_LAUNCH_CHECK();
+    if (padded > nb)
+      YB_CUDA(cudaMemsetAsync(b_h + (size_t)nb * dop, 0, 2 * (size_t)(padded - nb) * dop, st));
+  }
+  plan.acc_scale = scal + 3;
+  int rc = tf32_cross(plan, na, nb, dop, (const float *)b_h, (const float *)a_h, out, ldd, tws, st);
+  if (rc) return rc;
+  int overflow = 0;
+  YB_CUDA(cudaMemcpyAsync(&overflow, scal + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
+  YB_CUDA(cudaStreamSynchronize(st));
+  return overflow ? -1001 : 0;
+}
+
 // operand kind of the resident tensor passes: FP16 unless YAEL_B200_OPERANDS=tf32
 static int tensor_operand_kind() {
   const char *e = getenv("YAEL_B200_OPERANDS");

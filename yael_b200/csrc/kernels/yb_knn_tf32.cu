@@ -349,10 +349,14 @@ constexpr uint32_t IDESC_F16 = IDESC_F8;
 // loop of each instantiation carries no kind branches.
 enum : int { OP_TF32 = 0, OP_F8 = 1, OP_F16 = 2, OP_F16N = 3 };  // F16N: FP16 with |b|^2 folded into K
 constexpr int OP_F8P = 4;  // planning only (tf32_plan_tiles): E4M3 in the packed Hamming modes -- may pair up
+// E4M3 rows whose |b|^2 is the SAME constant for every row (+-1 Hamming operands: 2 * bits): no |b|^2
+// tiles, score = asc * acc + c0, the MAX-tree epilogue of the folded-norm kind; padding rows are E4M3
+// NaN (a NaN accumulator is never admitted)
+constexpr int OP_F8C = 5;
 template <int KIND>
 __device__ __forceinline__ void tc_mma_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                              uint32_t accumulate) {
-  if (KIND == OP_F8)
+  if (KIND == OP_F8 || KIND == OP_F8C)
     tc_mma_f8_elect(d_tmem, a_desc, b_desc, IDESC_F8, accumulate);
   else if (KIND == OP_F16 || KIND == OP_F16N)
     tc_mma_f16_elect(d_tmem, a_desc, b_desc, IDESC_F16, accumulate);
@@ -411,6 +415,7 @@ struct Tf32Params {
   int ham_slots;       // 2 or 3
   int ham_nb;          // real database rows (ids >= ham_nb are padding)
   float ham_magic;     // 2^23 + (bits/2)(1 + 2^8 [+ 2^16]): fma(acc, -0.5, magic) holds ham_i in byte i
+  float c0;            // OP_F8C: the constant |b|^2 of every row (0 for the folded-norm FP16 kind)
   const float *acc_scale;  // device scalar: score = acc * (*acc_scale) + |b|^2 (NULL = -2: operands
                            // unscaled); FP16 operands are scaled by 2^sigma, *acc_scale = -2^(1-2 sigma)
   int debug;           // bring-up switches (YAEL_B200_TF32_DEBUG): 1 skip epilogue math, 2 skip MMAs
@@ -623,19 +628,19 @@ __device__ __forceinline__ float group_max16(const uint32_t (&v)[16]) {
 template <bool K1>
 __device__ __forceinline__ void process_group_nf(const uint32_t (&v)[16], float &thr, float &thrp,
                                                  float &best, float margin, float2 *mylist, int &cnt,
-                                                 int cap, int id0, float asc, float inv_asc) {
+                                                 int cap, int id0, float asc, float inv_asc, float c0) {
   const float M = group_max16(v);
-  if (M > thrp) {  // <=> asc * M < thr: some score of the group beats the admission threshold
+  if (M > thrp) {  // <=> asc * M + c0 < thr: some score of the group beats the admission threshold
     float sc[16];
 #pragma unroll
-    for (int c = 0; c < 16; c++) sc[c] = __fmul_rn(asc, __uint_as_float(v[c]));
+    for (int c = 0; c < 16; c++) sc[c] = fmaf(asc, __uint_as_float(v[c]), c0);  // (c0 = 0: == asc * acc)
     if (K1) {
       K1State st = {thr, best, cnt};
-      st = slow_append_k1(YB_SC16_ARGS(sc), __fmul_rn(asc, M), st, margin, mylist, cap, id0);
+      st = slow_append_k1(YB_SC16_ARGS(sc), fmaf(asc, M, c0), st, margin, mylist, cap, id0);
       thr = st.thr;
       best = st.best;
       cnt = st.cnt;
-      thrp = __fmul_rn(thr, inv_asc);
+      thrp = __fmul_rn(thr - c0, inv_asc);
     } else {
       cnt = slow_append(YB_SC16_ARGS(sc), thr, mylist, cnt, id0);
     }
@@ -650,7 +655,7 @@ __device__ __forceinline__ void process_group_nf(const uint32_t (&v)[16], float 
 template <bool K1, int W>
 __device__ __forceinline__ void process_wide_nf(const uint32_t (&v)[W], float &thr, float &thrp,
                                                 float &best, float margin, float2 *mylist, int &cnt,
-                                                int cap, int id0, float asc, float inv_asc) {
+                                                int cap, int id0, float asc, float inv_asc, float c0) {
   float gm[W / 16];
 #pragma unroll
   for (int s = 0; s < W / 16; s++) gm[s] = group_max16(reinterpret_cast<const uint32_t(&)[16]>(v[16 * s]));
@@ -663,14 +668,14 @@ __device__ __forceinline__ void process_wide_nf(const uint32_t (&v)[W], float &t
       if (gm[s] > thrp) {
         float sc[16];
 #pragma unroll
-        for (int c = 0; c < 16; c++) sc[c] = __fmul_rn(asc, __uint_as_float(v[16 * s + c]));
+        for (int c = 0; c < 16; c++) sc[c] = fmaf(asc, __uint_as_float(v[16 * s + c]), c0);
         if (K1) {
           K1State st = {thr, best, cnt};
-          st = slow_append_k1(YB_SC16_ARGS(sc), __fmul_rn(asc, gm[s]), st, margin, mylist, cap, id0 + 16 * s);
+          st = slow_append_k1(YB_SC16_ARGS(sc), fmaf(asc, gm[s], c0), st, margin, mylist, cap, id0 + 16 * s);
           thr = st.thr;
           best = st.best;
           cnt = st.cnt;
-          thrp = __fmul_rn(thr, inv_asc);
+          thrp = __fmul_rn(thr - c0, inv_asc);
         } else {
           cnt = slow_append(YB_SC16_ARGS(sc), thr, mylist, cnt, id0 + 16 * s);
         }
@@ -828,11 +833,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 // MODE selects what the epilogue does with a tile (one kernel instantiation per mode: the hot
 // loop of each stays compact and contiguous in the instruction cache, and carries no per-tile
 // mode branches)
-enum : int { EPI_LISTS = 0, EPI_NEAREST = 1, EPI_DUMP = 2, EPI_GMIN = 3, EPI_HAMP = 4, EPI_HAMG = 5 };
+enum : int { EPI_LISTS = 0, EPI_NEAREST = 1, EPI_DUMP = 2, EPI_GMIN = 3, EPI_HAMP = 4, EPI_HAMG = 5,
+              EPI_CROSS = 6 };  // CROSS: the full distance matrix, out[row * ld + query] (compute_cross_distances)
 
 template <int MODE, int KIND, int LDW>
 __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &E) {
-  constexpr bool NF = KIND == OP_F16N;  // |b|^2 folded into the contraction
+  constexpr bool NF = KIND == OP_F16N || KIND == OP_F8C;  // |b|^2 folded into the contraction / constant
+  const float c0 = KIND == OP_F8C ? P.c0 : 0.f;
   // no |b|^2 tiles travel: folded norms, and the packed Hamming modes (integer epilogue)
   constexpr bool NOBN = NF || MODE == EPI_HAMP || MODE == EPI_HAMG;
   unsigned char *smem = E.smem;
@@ -867,7 +874,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
       constexpr bool k1 = MODE == EPI_NEAREST;
       const float margin = (k1 && valid) ? P.k1_margin[q] : 0.f;
       int cnt = 0;
-      float thrp = __fmul_rn(thr, inv_asc);  // NF: admit iff acc' > thrp (= thr / asc, asc < 0)
+      float thrp = __fmul_rn(thr - c0, inv_asc);  // NF: admit iff acc' > thrp (= (thr - c0) / asc, asc < 0)
       uint32_t tau3 = 0u;
       const uint32_t ham_mask = P.ham_slots == 3 ? 0x808080u : 0x8080u;
       if (MODE == EPI_HAMP) tau3 = ham_tau3(thr);
@@ -899,18 +906,46 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
 #pragma unroll
                 for (int c4 = 0; c4 < 8; c4++) {  // 128 contiguous bytes per thread
                   float4 o;
-                  o.x = fmaf(__uint_as_float(v[c4 * 4 + 0]), asc, NF ? 0.f : bn[g * 32 + c4 * 4 + 0]);
-                  o.y = fmaf(__uint_as_float(v[c4 * 4 + 1]), asc, NF ? 0.f : bn[g * 32 + c4 * 4 + 1]);
-                  o.z = fmaf(__uint_as_float(v[c4 * 4 + 2]), asc, NF ? 0.f : bn[g * 32 + c4 * 4 + 2]);
-                  o.w = fmaf(__uint_as_float(v[c4 * 4 + 3]), asc, NF ? 0.f : bn[g * 32 + c4 * 4 + 3]);
+                  o.x = fmaf(__uint_as_float(v[c4 * 4 + 0]), asc, NF ? c0 : bn[g * 32 + c4 * 4 + 0]);
+                  o.y = fmaf(__uint_as_float(v[c4 * 4 + 1]), asc, NF ? c0 : bn[g * 32 + c4 * 4 + 1]);
+                  o.z = fmaf(__uint_as_float(v[c4 * 4 + 2]), asc, NF ? c0 : bn[g * 32 + c4 * 4 + 2]);
+                  o.w = fmaf(__uint_as_float(v[c4 * 4 + 3]), asc, NF ? c0 : bn[g * 32 + c4 * 4 + 3]);
                   *reinterpret_cast<float4 *>(drow + c4 * 4) = o;
                 }
               } else {
 #pragma unroll
                 for (int c = 0; c < 32; c++)
                   if (col0 + c < P.dump_ld)
-                    drow[c] = fmaf(__uint_as_float(v[c]), asc, NF ? 0.f : bn[g * 32 + c]);
+                    drow[c] = fmaf(__uint_as_float(v[c]), asc, NF ? c0 : bn[g * 32 + c]);
               }
+            }
+          }
+        } else if (MODE == EPI_CROSS) {
+          // compute_cross_distances (yael/nn.c:100-129): dist2[query + ld * row], i.e. the 32 lanes
+          // of a warp (32 consecutive queries) write 128 contiguous bytes per database row.  The
+          // operands carry both norms (cross_l2_tensor, yb_knn.cu), so the value is asc * acc.
+          const uint32_t ta = lane_addr + buf * TN;
+          const long col0 = (long)jt * TN + half * HALF_N;
+          float *ocol = P.dump + (size_t)col0 * P.dump_ld + (valid ? q : 0);
+          uint32_t va[32], vb[32];
+          tc_ld32(ta, va);
+#pragma unroll 1
+          for (int g = 0; g < HALF_N / 32; g += 2) {
+            tc_wait_ld();
+            tc_ld32(ta + (g + 1) * 32, vb);
+            if (valid) {
+#pragma unroll
+              for (int c = 0; c < 32; c++)
+                if (col0 + g * 32 + c < P.nb)
+                  ocol[(size_t)(g * 32 + c) * P.dump_ld] = __fmul_rn(asc, __uint_as_float(va[c]));
+            }
+            tc_wait_ld();
+            if (g + 2 < HALF_N / 32) tc_ld32(ta + (g + 2) * 32, va);
+            if (valid) {
+#pragma unroll
+              for (int c = 0; c < 32; c++)
+                if (col0 + (g + 1) * 32 + c < P.nb)
+                  ocol[(size_t)((g + 1) * 32 + c) * P.dump_ld] = __fmul_rn(asc, __uint_as_float(vb[c]));
             }
           }
         } else if (MODE == EPI_GMIN) {
@@ -926,14 +961,14 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           for (int gg = 0; gg < 4; gg++) {
             tc_wait_ld();
             tc_ld16(ta + gg * 32 + 16, vb);
-            gm = fminf(gm, NF ? __fmul_rn(asc, group_max16(va)) : group_min16(va, bn + gg * 32, asc));
+            gm = fminf(gm, NF ? fmaf(asc, group_max16(va), c0) : group_min16(va, bn + gg * 32, asc));
             if (((2 * gg + 1) % fold) == 0) {
               if (valid) grow[(2 * gg + 1) / fold - 1] = gm;
               gm = inf;
             }
             tc_wait_ld();
             if (gg < 3) tc_ld16(ta + gg * 32 + 32, va);
-            gm = fminf(gm, NF ? __fmul_rn(asc, group_max16(vb)) : group_min16(vb, bn + gg * 32 + 16, asc));
+            gm = fminf(gm, NF ? fmaf(asc, group_max16(vb), c0) : group_min16(vb, bn + gg * 32 + 16, asc));
             if (((2 * gg + 2) % fold) == 0) {
               if (valid) grow[(2 * gg + 2) / fold - 1] = gm;
               gm = inf;
@@ -1002,12 +1037,14 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           for (int gg = 0; gg < 4; gg++) {
             tc_wait_ld();
             tc_ld16(ta + gg * 32 + 16, vb);
-            process_group_ham(va, P.ham_magic, tau3, ham_mask, P.ham_slots, mylist, cnt,
-                              r0 + gg * 32 * P.ham_slots, P.ham_nb);
+            if (!(P.debug & 1))
+              process_group_ham(va, P.ham_magic, tau3, ham_mask, P.ham_slots, mylist, cnt,
+                                r0 + gg * 32 * P.ham_slots, P.ham_nb);
             tc_wait_ld();
             if (gg < 3) tc_ld16(ta + gg * 32 + 32, va);
-            process_group_ham(vb, P.ham_magic, tau3, ham_mask, P.ham_slots, mylist, cnt,
-                              r0 + (gg * 32 + 16) * P.ham_slots, P.ham_nb);
+            if (!(P.debug & 1))
+              process_group_ham(vb, P.ham_magic, tau3, ham_mask, P.ham_slots, mylist, cnt,
+                                r0 + (gg * 32 + 16) * P.ham_slots, P.ham_nb);
           }
         } else if (NF && LDW == 128 && (MODE == EPI_LISTS || MODE == EPI_NEAREST)) {
           // The whole half tile (128 accumulators per thread) is pulled into registers with two
@@ -1038,8 +1075,8 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           }
           handed_back = true;
           if (!(P.debug & 1)) {
-            process_wide_nf<K1W, 64>(va, thr, thrp, best, margin, mylist, cnt, P.cap, n0, asc, inv_asc);
-            process_wide_nf<K1W, 64>(vb, thr, thrp, best, margin, mylist, cnt, P.cap, n0 + 64, asc, inv_asc);
+            process_wide_nf<K1W, 64>(va, thr, thrp, best, margin, mylist, cnt, P.cap, n0, asc, inv_asc, c0);
+            process_wide_nf<K1W, 64>(vb, thr, thrp, best, margin, mylist, cnt, P.cap, n0 + 64, asc, inv_asc, c0);
           }
         } else if (NF && LDW > 16 && (MODE == EPI_LISTS || MODE == EPI_NEAREST)) {
           // HALF_N / LDW wide loads, load g+1 in flight while g is processed
@@ -1063,11 +1100,11 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
               tc_wait_ld();
               tc_ldw<LW>(ta + (g + 1) * LW, vb);
               process_wide_nf<K1W, LW>(va, thr, thrp, best, margin, mylist, cnt, P.cap, n0 + g * LW, asc,
-                                        inv_asc);
+                                        inv_asc, c0);
               tc_wait_ld();
               if (g + 2 < NG) tc_ldw<LW>(ta + (g + 2) * LW, va);
               process_wide_nf<K1W, LW>(vb, thr, thrp, best, margin, mylist, cnt, P.cap, n0 + (g + 1) * LW,
-                                        asc, inv_asc);
+                                        asc, inv_asc, c0);
             }
           }
         } else if (!(P.debug & 1)) {
@@ -1093,7 +1130,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
     tc_ld16(ta + gg * 32 + 16, vb);                                                             \
     if (NF)                                                                                     \
       process_group_nf<K1FLAG>(va, thr, thrp, best, margin, mylist, cnt, P.cap, n0 + gg * 32,   \
-                               asc, inv_asc);                                                   \
+                               asc, inv_asc, c0);                                               \
     else                                                                                        \
       process_group<K1FLAG>(va, bn + gg * 32, thr, best, margin, mylist, cnt, P.cap,            \
                             n0 + gg * 32, asc);                                                 \
@@ -1101,7 +1138,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
     if (gg < 3) tc_ld16(ta + gg * 32 + 32, va);                                                 \
     if (NF)                                                                                     \
       process_group_nf<K1FLAG>(vb, thr, thrp, best, margin, mylist, cnt, P.cap,                 \
-                               n0 + gg * 32 + 16, asc, inv_asc);                                \
+                               n0 + gg * 32 + 16, asc, inv_asc, c0);                            \
     else                                                                                        \
       process_group<K1FLAG>(vb, bn + gg * 32 + 16, thr, best, margin, mylist, cnt, P.cap,       \
                             n0 + gg * 32 + 16, asc);                                            \
@@ -1149,7 +1186,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           }
         }
         if (MODE == EPI_HAMP) tau3 = ham_tau3(thr);
-        if (NF) thrp = __fmul_rn(thr, inv_asc);
+        if (NF) thrp = __fmul_rn(thr - c0, inv_asc);
         if (clk_on) ck_back += clock64() - ck_a;
       }
       if (MODE == EPI_NEAREST) {
@@ -1296,7 +1333,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
   if (warp == EPI_WARPS) {
     // ======================================================================== TMA producer
     regs_aux();
-    constexpr int KCE = KIND == OP_F8 ? KC * 4 : ((KIND == OP_F16 || KIND == OP_F16N) ? KC * 2 : KC);  // elements per 128-byte K chunk (TMA coordinates)
+    constexpr int KCE = (KIND == OP_F8 || KIND == OP_F8C) ? KC * 4 : ((KIND == OP_F16 || KIND == OP_F16N) ? KC * 2 : KC);  // elements per 128-byte K chunk (TMA coordinates)
     if (lane == 0) {
       uint32_t icount = 0, ccount = 0, tcount = 0;
       for (int item = first_item; item < P.items; item += item_step, icount++) {
@@ -1317,7 +1354,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
                       qt * TM);
         for (int jt = jt0; jt < jt1; jt++, tcount++) {
           const int jta = jt * P.tile_stride;  // actual database tile
-          if (!(NFK || MODE == EPI_HAMP || MODE == EPI_HAMG)) {  // |b|^2 of the tile (the folded-norm kinds carry it in the operands, the packed Hamming modes do not use it)
+          if (!(NFK || KIND == OP_F8C || MODE == EPI_HAMP || MODE == EPI_HAMG)) {  // |b|^2 of the tile (the folded-norm kinds carry it in the operands, the packed Hamming modes do not use it)
             const uint32_t slot = tcount % NBN;
             mbar_wait(bar(Smem::n_empty + slot), ((tcount / NBN) & 1) ^ 1);
             mbar_expect_tx(bar(Smem::n_full + slot), TN * 4);
@@ -1569,7 +1606,7 @@ constexpr uint32_t IDESC_F16_2SM = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((u
 template <int KIND>
 __device__ __forceinline__ void tc_mma_2sm_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                                  uint32_t accumulate) {
-  if (KIND == OP_F8)
+  if (KIND == OP_F8 || KIND == OP_F8C)
     tc_mma_f8_2sm_elect(d_tmem, a_desc, b_desc, IDESC_F16_2SM, accumulate);
   else
     tc_mma_f16_2sm_elect(d_tmem, a_desc, b_desc, IDESC_F16_2SM, accumulate);
@@ -1588,7 +1625,7 @@ __global__ void __launch_bounds__(TF32_THREADS, 1)
 k_knn_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_bh,
           const __grid_constant__ CUtensorMap map_qx, const __grid_constant__ CUtensorMap map_bxh,
           const Tf32Params P) {
-  static_assert(KIND == OP_F16N || (KIND == OP_F8 && (MODE == EPI_HAMP || MODE == EPI_HAMG)),
+  static_assert(KIND == OP_F16N || KIND == OP_F8C || (KIND == OP_F8 && (MODE == EPI_HAMP || MODE == EPI_HAMG)),
                 "the 2-SM kernel carries no |b|^2 ring");
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -1599,7 +1636,7 @@ k_knn_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
   const bool leader = crank == 0;
   const int xk = KIND == OP_F16N ? P.xk : -1;  // index of the extras chunk (-1: the extras sit inside the last data chunk)
   const bool xring = KIND == OP_F16N && !STREAM && P.xring != 0;  // extras travel through their own 2-slot ring
-  constexpr int KCE = KIND == OP_F8 ? KC * 4 : KC * 2;  // elements per 128-byte K chunk
+  constexpr int KCE = (KIND == OP_F8 || KIND == OP_F8C) ? KC * 4 : KC * 2;  // elements per 128-byte K chunk
 
   if (threadIdx.x == 0) {
     mbar_init(bar(Smem2::a_full), 1);
@@ -1912,11 +1949,12 @@ static int make_map_f16_extras(CUtensorMap *m, const void *ptr, long rows, int d
 //      folded-norm FP16 kind whenever there are at least two query tiles
 // YAEL_B200_PAIR=0|1|2 overrides (2 only applies to the folded-norm FP16 kind).
 int tf32_pair_mode(int kind, int tiles_q) {
-  const bool can2 = (kind == OP_F16N || kind == OP_F8P) && tiles_q >= 2;
+  const bool ham = kind == OP_F8P || kind == OP_F8C;
+  const bool can2 = (kind == OP_F16N || ham) && tiles_q >= 2;
   int mode = can2 ? 2 : 0;
-  if (const char *e = getenv(kind == OP_F8P ? "YAEL_B200_HAM_PAIR" : "YAEL_B200_PAIR")) mode = atoi(e);
+  if (const char *e = getenv(ham ? "YAEL_B200_HAM_PAIR" : "YAEL_B200_PAIR")) mode = atoi(e);
   if (mode == 2 && !can2) mode = 0;
-  if (mode == 1 && (kind == OP_F8 || kind == OP_F8P)) mode = 0;
+  if (mode == 1 && (kind == OP_F8 || ham)) mode = 0;
   if (mode != 0 && (sm_count() & 1)) mode = 0;
   return mode;
 }
@@ -2072,13 +2110,15 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   Tf32Params P = {};
   P.nq = nq; P.nb = nb; P.d = d;
   P.xk = -1;
-  if (plan.kind == OP_F8) {
+  if (plan.kind == OP_F8 || plan.kind == OP_F8C) {
     // E4M3 operands: d floats of pitch = 4*d bytes = 4*d elements per row; a K chunk is the same
-    // 128-byte swizzle span (128 elements), an MMA covers 32 of them
+    // 128-byte swizzle span (128 elements), an MMA covers 32 of them.  OP_F8C: the database copy is
+    // padded to whole tiles with NaN rows (as the folded-norm FP16 copy)
     const int pitch = 4 * d;
+    const long nbm = plan.kind == OP_F8C ? tf32_padded_rows(nb) : nb;
     if ((rc = make_map_u8(&mq, query, nq, pitch, TM))) return rc;
-    if ((rc = make_map_u8(&mb, base, nb, pitch, TN))) return rc;
-    if ((rc = make_map_u8(&mbh, base, nb, pitch, TN / 2))) return rc;
+    if ((rc = make_map_u8(&mb, base, nbm, pitch, TN))) return rc;
+    if ((rc = make_map_u8(&mbh, base, nbm, pitch, TN / 2))) return rc;
     P.nkc = (pitch + 127) / 128;
     P.last_k8 = (pitch - (P.nkc - 1) * 128 + 31) / 32;
   } else if (plan.kind == OP_F16 || plan.kind == OP_F16N) {
@@ -2158,7 +2198,10 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   }
   P.dump = dump;
   P.dump_ld = dump_ld;
-  const int mode = dump ? EPI_DUMP : (P.gmin ? EPI_GMIN : (k1_margin ? EPI_NEAREST : EPI_LISTS));
+  const int mode = (dump && oo && oo->cross) ? EPI_CROSS
+                   : (dump ? EPI_DUMP : (P.gmin ? EPI_GMIN : (k1_margin ? EPI_NEAREST : EPI_LISTS)));
+  if (mode == EPI_CROSS && !(plan.kind == OP_F16N && plan.pair == 2))
+    return fail(6, "the cross-distance mode needs the 2-SM folded-norm kernel");
   P.acc_scale = plan.acc_scale;
   {
     const char *e = getenv("YAEL_B200_TF32_ORDER");
@@ -2167,6 +2210,24 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   P.ham_slots = plan.ham_slots;
   P.ham_nb = plan.ham_nb;
   P.ham_magic = plan.ham_magic;
+  P.c0 = plan.score_c0;
+  if (plan.kind == OP_F8C) {  // E4M3 with a constant norm: the folded-norm epilogues, no |b|^2 ring
+    if (plan.pair == 1) return fail(6, "the E4M3 operand kind has no multicast-pair variant");
+    if (plan.pair == 2) {
+      switch (mode) {
+        case EPI_DUMP: return launch_2sm<EPI_DUMP, 16, OP_F8C>(plan, mq, mbh, mqx, mbxh, P, st);
+        case EPI_GMIN: return launch_2sm<EPI_GMIN, 16, OP_F8C>(plan, mq, mbh, mqx, mbxh, P, st);
+        case EPI_LISTS: return launch_2sm<EPI_LISTS, 128, OP_F8C>(plan, mq, mbh, mqx, mbxh, P, st);
+        default: return fail(6, "the E4M3 operand kind has no k = 1 margin mode");
+      }
+    }
+    switch (mode) {
+      case EPI_DUMP: return launch_mode<EPI_DUMP, OP_F8C>(plan, mq, mb, mbh, mqx, mbx, P, st);
+      case EPI_GMIN: return launch_mode<EPI_GMIN, OP_F8C>(plan, mq, mb, mbh, mqx, mbx, P, st);
+      case EPI_LISTS: return launch_mode<EPI_LISTS, OP_F8C, 128>(plan, mq, mb, mbh, mqx, mbx, P, st);
+      default: return fail(6, "the E4M3 operand kind has no k = 1 margin mode");
+    }
+  }
   if (plan.kind == OP_F8 && plan.ham_slots > 1 && !dump) {
     // packed Hamming passes: ham_slots database rows per accumulator, integer epilogue
     if (plan.pair == 1) return fail(6, "the E4M3 operand kind has no multicast-pair variant");
@@ -2207,6 +2268,7 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   if (const char *e = getenv("YAEL_B200_LDW")) ldw = atoi(e);
   if (plan.kind == OP_F16N && plan.pair == 2 && plan.stream) {  // streamed query chunks: any d
     switch (mode) {
+      case EPI_CROSS: return launch_2sm<EPI_CROSS, 16, OP_F16N, true>(plan, mq, mbh, mqx, mbxh, P, st);
       case EPI_DUMP: return launch_2sm<EPI_DUMP, 16, OP_F16N, true>(plan, mq, mbh, mqx, mbxh, P, st);
       case EPI_GMIN: return launch_2sm<EPI_GMIN, 16, OP_F16N, true>(plan, mq, mbh, mqx, mbxh, P, st);
       case EPI_LISTS: return launch_2sm<EPI_LISTS, 128, OP_F16N, true>(plan, mq, mbh, mqx, mbxh, P, st);
@@ -2216,6 +2278,7 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   if (plan.stream) return fail(6, "streamed query chunks need the 2-SM folded-norm kernel");
   if (plan.kind == OP_F16N && plan.pair == 2) {  // cta_group::2 pairs (k_knn_2sm)
     switch (mode) {
+      case EPI_CROSS: return launch_2sm<EPI_CROSS, 16>(plan, mq, mbh, mqx, mbxh, P, st);
       case EPI_DUMP: return launch_2sm<EPI_DUMP, 16>(plan, mq, mbh, mqx, mbxh, P, st);
       case EPI_GMIN: return launch_2sm<EPI_GMIN, 16>(plan, mq, mbh, mqx, mbxh, P, st);
       case EPI_LISTS:
@@ -2298,6 +2361,15 @@ int tf32_group_min(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logical,
   oo.gsize = gsize;
   return launch_tf32(plan, nq, nb, d, nbt_logical, tile_stride, base, query, bnorm_padded, nullptr,
                      nullptr, nullptr, nullptr, nullptr, nullptr, 0, ws, st, &oo);
+}
+
+// the full distance matrix out[row * ld + query] = asc * acc (operands carry both norms)
+int tf32_cross(const Tf32Plan &plan, int nq, int nb, int d, const float *base, const float *query,
+               float *out, long ld, void *ws, cudaStream_t st) {
+  Tf32Out oo = {};
+  oo.cross = 1;
+  return launch_tf32(plan, nq, nb, d, tf32_tiles(nb), 1, base, query, nullptr, nullptr, nullptr, nullptr,
+                     nullptr, nullptr, out, ld, ws, st, &oo);
 }
 
 long tf32_padded_rows(int nb) { return (long)((nb + TN - 1) / TN) * TN; }
