@@ -64,7 +64,12 @@ class ClockSampler:
     REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
                ("sw_power_cap", 0x4))
 
-    def __init__(self, gpu_index, uuid=None):
+    def __init__(self, gpu_index, uuid=None, poll_ms=2.0, enabled=True):
+        # N > 1: NVML calls from 8 processes at 500 Hz each contend inside the driver (measured at
+        # N = 8: a poll iteration took ~15 ms instead of 2 and the timed loop ran at 9.2 ms per step
+        # against 4.1 ms without the sampler), so only rank 0 samples there, at a lower rate
+        self.poll_s = poll_ms * 1e-3
+        self.enabled = enabled
         self.gpu = gpu_index
         self.uuid = uuid
         self.samples = []   # (t, sm_mhz, sm_max_mhz, reason_bits)
@@ -75,6 +80,8 @@ class ClockSampler:
         self.t0 = self.t1 = None
 
     def start(self):
+        if not self.enabled:
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -122,7 +129,7 @@ class ClockSampler:
                 self.samples.append((time.perf_counter(), sm, self.mx, bits))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.poll_s)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -135,6 +142,8 @@ class ClockSampler:
         self.t1 = time.perf_counter()
 
     def stop(self):
+        if not self.enabled:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["not sampled on this rank"]}
         if self.nvml is not None:
             self.stop_flag = True
             self.th.join(timeout=1)
@@ -144,7 +153,7 @@ class ClockSampler:
                 return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
             reasons = sorted({name for name, bit in self.REASONS for x in sel if x[3] & bit})
             return {"sm_mhz": float(np.median([x[1] for x in sel])), "sm_max_mhz": float(sel[0][2]),
-                    "reasons": reasons, "samples": len(sel), "source": "nvml, 2 ms polling"}
+                    "reasons": reasons, "samples": len(sel), "source": "nvml, %g ms polling" % (self.poll_s * 1e3)}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -270,6 +279,31 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def _bind_to_gpu_numa_node(torch, dev):
+    """Restrict this process to the CPUs of the NUMA node the GPU is attached to (sysfs), so that the
+    pinned host buffers allocated next are node-local.  Returns the node, or None when the topology is
+    not exposed / the node's CPUs are not available to this process."""
+    try:
+        bus = torch.cuda.get_device_properties(dev).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(dev), "pci_domain_id", 0)
+        devid = getattr(torch.cuda.get_device_properties(dev), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, devid)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def measure_tf32_peak(torch, dev):
     """cuBLAS TF32 GEMM throughput measured the way MEASURED_PEAKS.json measures bf16
     (8192^3, best of 10): the denominator for the kind::tf32 kernel."""
@@ -717,6 +751,9 @@ def measure_extras_sharded(torch, dist, ydist, L, dev, rank, world):
         out["hamming_error"] = str(e)
     if all_ok(ok):
         best = 1e9
+        sh.search(hq)
+        L.yb_prof_enable(1)
+        L.yb_prof_ms(0, None, 1)
         for _ in range(3):
             dist.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -725,9 +762,16 @@ def measure_extras_sharded(torch, dist, ydist, L, dev, rank, world):
             e1.record()
             e1.synchronize()
             best = min(best, max_over_ranks(e0.elapsed_time(e1)))
+        ph = _phase_means(L, ((12, "expand_codes"), (13, "sample_thresholds"), (14, "e4m3_pass"),
+                              (15, "order_and_certify"), (7, "popcount_scan"), (16, "exchange_x2"),
+                              (17, "merge_query_slice")))
+        L.yb_prof_ms(0, None, 1)
+        L.yb_prof_enable(0)
         out["hamming_knn_10Mx64bit_10kq_k100_sharded"] = {
             "queries_per_s": nqh / (best * 1e-3), "ms": best, "ranks": world,
-            "engine": int(L.yb_last_hamming_engine()), "scaling": "strong (10M codes split over the ranks)"}
+            "engine": int(L.yb_last_hamming_engine()), "scaling": "strong (10M codes split over the ranks)",
+            "phase_ms_rank0": ph,
+            "exchange": "peer memory" if (sh.comm and L.yb_comm_p2p(sh.comm.handle)) else "nccl"}
         del hb, hq, sh
         torch.cuda.empty_cache()
 
@@ -748,9 +792,14 @@ def measure_extras_sharded(torch, dist, ydist, L, dev, rank, world):
         c0 = cent.cpu().numpy()
         times = []
         okrun = True
-        for _ in range(2):
+        niter = 5
+        ph = {}
+        for rep in range(2):
             dist.barrier()
             torch.cuda.synchronize()
+            if rep == 1:
+                L.yb_prof_enable(1)
+                L.yb_prof_ms(0, None, 1)
             t = time.perf_counter()
             try:
                 _, q, _, _ = ydist.sharded_kmeans(v, k, niter, c0, n)
@@ -759,11 +808,18 @@ def measure_extras_sharded(torch, dist, ydist, L, dev, rank, world):
                 out["kmeans_error"] = str(e)
             torch.cuda.synchronize()
             times.append(max_over_ranks((time.perf_counter() - t) / niter))
+            if rep == 1:
+                ph = _phase_means(L, ((0, "center_and_convert"), (1, "tensor_pass"), (3, "rerank_k1"),
+                                      (4, "exact_fallback"), (8, "update_sort_and_sums"), (16, "all_reduce"),
+                                      (9, "scale")))
+                L.yb_prof_ms(0, None, 1)
+                L.yb_prof_enable(0)
             if not all_ok(okrun):
                 break
         if okrun and times:
             out["kmeans_10Mx128_k65536_sharded"] = {
                 "iter_per_s": 1.0 / min(times), "s_per_iter": min(times), "ranks": world, "qerr": float(q),
+                "iterations_timed": niter, "phase_ms_rank0": ph,
                 "scaling": "strong (10M points split over the ranks, one all-reduce per iteration)"}
         del v
         torch.cuda.empty_cache()
@@ -818,7 +874,9 @@ def run_ours(args):
         uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
     except Exception:
         uuid = None
-    sampler = ClockSampler(local, uuid)
+    poll_ms = float(os.environ.get("BENCH_CLOCK_POLL_MS", "2" if world == 1 else "20"))
+    sampler = ClockSampler(local, uuid, poll_ms=poll_ms,
+                           enabled=(rank == 0 and os.environ.get("BENCH_CLOCKS", "on") != "off"))
     sampler.start()
     L.yb_launch_count(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -872,6 +930,9 @@ def run_ours(args):
     value = world * NQ / (ms * 1e-3)
 
     # ---- end to end through the drop-in C call with pinned host buffers
+    # N > 1: every rank feeds its own 517 MB shard over its own PCIe link at the same time; allocate the
+    # pinned buffers from the NUMA node the GPU hangs off (first touch under a node-local CPU affinity)
+    numa = _bind_to_gpu_numa_node(torch, dev) if world > 1 else None
     bh = torch.from_numpy(base_h).pin_memory()
     qh = torch.from_numpy(query_h).pin_memory()
     idx_h = torch.empty((NQ, K), dtype=torch.int32).pin_memory()
@@ -895,6 +956,8 @@ def run_ours(args):
     e2e = {"value": world * NQ / t_e2e, "unit": UNIT,
            "h2d_bytes_per_step": int(base_h.nbytes + query_h.nbytes),
            "d2h_bytes_per_step": int(NQ * K * 8), "ms_per_step": t_e2e * 1e3}
+    if world > 1:
+        e2e["pinned_buffers_numa_node_rank0"] = numa
 
     # ---- results for the parity checks (outside every timed region)
     L.yb_set_knn_engine(-1)
@@ -1020,9 +1083,11 @@ def run_ours(args):
         "config": {
             "workload": WORKLOAD,
             "parallelism": ("single GPU" if world == 1 else
-                            "database sharded x%d (1M rows per rank); query-partitioned NCCL exchange inside "
-                            "the library (all-to-all of list slices, merge of nq/N queries per rank, all-gather "
-                            "of merged slices); value counts query x 1M-shard scans" % world),
+                            "database sharded x%d (1M rows per rank); query-partitioned exchange inside the "
+                            "library (list slices to their owners, merge of nq/N queries per rank, merged slices "
+                            "to everybody) over %s; value counts query x 1M-shard scans"
+                            % (world, "peer memory (NVLink stores + flag barrier)"
+                               if (searcher.comm and L.yb_comm_p2p(searcher.comm.handle)) else "NCCL send/recv")),
             "l2": "database (512 MB) is larger than L2 (126 MB): no flush needed between steps",
             "engine": ("tcgen05 %s + FP32 re-rank" % operands) if engine == 1 else "exact FP32 SIMT",
             "uncertified_queries_redone_exactly": int(uncert),

@@ -243,6 +243,10 @@ int yb_comm_unique_id(void *id128);       /* 128 bytes */
 yb_comm *yb_comm_create(const void *id128, int rank, int world); /* collective; NULL on failure */
 int yb_comm_create_all(int ndev, const int *devs, yb_comm **out);
 void yb_comm_destroy(yb_comm *c);
+/* 1 when the exchange steps of this communicator run over peer memory (every rank's segment mapped
+ * into every other's address space: NVLink stores + a flag barrier, no NCCL kernel on the path;
+ * YAEL_B200_NO_P2P=1 / YAEL_B200_P2P_MB size the segments), 0 when they use NCCL send / recv */
+int yb_comm_p2p(const yb_comm *c);
 int yb_comm_rank(const yb_comm *c);
 int yb_comm_world(const yb_comm *c);
 int yb_comm_allreduce_f32(yb_comm *c, float *buf, long n, yb_stream_t s);

@@ -175,6 +175,7 @@ DEVICE = {
     "yb_comm_create": (_vp, [_vp, C.c_int, C.c_int]),
     "yb_comm_create_all": (C.c_int, [C.c_int, _i, C.POINTER(_vp)]),
     "yb_comm_destroy": (None, [_vp]),
+    "yb_comm_p2p": (C.c_int, [_vp]),
     "yb_comm_rank": (C.c_int, [_vp]),
     "yb_comm_world": (C.c_int, [_vp]),
     "yb_comm_allreduce_f32": (C.c_int, [_vp, _vp, C.c_long, _vp]),

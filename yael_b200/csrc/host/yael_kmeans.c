@@ -77,18 +77,25 @@ static int kmeans_core_dev(km_dev *K, int niter, int flags, int verbose, float *
   const int d = K->d, n = K->n, k = K->k;
   double qerr = HUGE_VAL, qerr_old;
   int tot_moved = 0, iter;
+  /* YAEL_B200_KM_TRACE=1: host-side timeline of every iteration on stderr (ms since the iteration
+   * started: calls returned = work QUEUED, not finished, until the sync) */
+  const int trace = getenv("YAEL_B200_KM_TRACE") != NULL && (!K->comm || K->comm->rank == 0);
   for (iter = 1; iter <= niter; iter++) {
+    double t0 = trace ? getmillisecs() : 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
     (*iter_tot)++;
     /* assignment: knn_full_thread(2, n, k, d, 1, centroids, v, ...) (kmeans.c:242-244) */
     YBH_CHECK(yb_knn_l2(n, k, d, 1, K->cent, K->v, NULL, K->assign, K->dis, 0, K->s));
+    if (trace) t1 = getmillisecs();
     /* histogram + sums + qerr (kmeans.c:249-251, 278-283, 310) */
     YBH_CHECK(yb_kmeans_accumulate(d, n, k, K->v, K->assign, K->dis, K->sums, K->nassign, K->qerr,
                                    K->exact_order, K->s));
+    if (trace) t2 = getmillisecs();
     if (K->comm && K->comm->allreduce_sums) {
       int rc = K->comm->allreduce_sums(K->comm->ctx, K->sums, (long)k * d, K->nassign, k, K->qerr,
                                        K->s);
       if (rc) ybh_die("kmeans: allreduce hook", rc);
     }
+    if (trace) t3 = getmillisecs();
     /* normalise by the counts (kmeans.c:286-288) and optionally to unit norm (291-293) */
     YBH_CHECK(yb_kmeans_scale(d, k, K->sums, K->nassign, K->cent,
                               (flags & KMEANS_NORMALIZE_CENTS) ? 1 : 0, K->s));
@@ -96,6 +103,11 @@ static int kmeans_core_dev(km_dev *K, int niter, int flags, int verbose, float *
     YBH_CHECK(yb_d2h(nassign_host, K->nassign, sizeof(int) * (size_t)k, K->s));
     YBH_CHECK(yb_d2h(&q_new, K->qerr, sizeof(double), K->s));
     YBH_CHECK(yb_sync(K->s));
+    if (trace) {
+      t4 = getmillisecs();
+      fprintf(stderr, "kmeans trace iter %d: assign queued %.3f, accumulate queued %.3f, all-reduce queued "
+                      "%.3f, synced %.3f ms\n", iter, t1 - t0, t2 - t0, t3 - t0, t4 - t0);
+    }
     long tot = 0;
     int empties = 0, c;
     for (c = 0; c < k; c++) {
