@@ -188,6 +188,20 @@ float yb_kmeans_dev(int d, int n, int k, int niter, const float *v_dev, int flag
                     int redo, float *centroids, float *dis, int *assign, int *nassign,
                     const yb_kmeans_comm_t *comm, yb_stream_t s);
 
+/* ---- consumers of the k = 1 search: VLAD / bag of features (yael/vlad.c:10-139) ------- */
+/* desc[k][d] = sum over the listed points (list == NULL: points 0 .. n_list-1), in LIST ORDER, of
+ * fl32(v_i - centroids[assign_i]) (times weights[i] when given): the reference's summation order,
+ * so the descriptor is bit-identical to vlad_compute / _weighted / one subset of _subsets.
+ * k <= 16384. */
+int yb_vlad_accumulate(int k, int d, const float *centroids, long n_list, const int *list,
+                       const float *v, const int *assign, const float *weights, float *desc,
+                       yb_stream_t s);
+/* desc[k] = how many listed entries of assign[0 .. n_assign) name each centroid (bof_compute,
+ * bof_compute_ma, one subset of bof_compute_subsets); desc_f (may be NULL) receives the counts as
+ * floats */
+int yb_bof_accumulate(int k, long n_list, const int *list, const int *assign, long n_assign, int *desc,
+                      float *desc_f, yb_stream_t s);
+
 /* ---- Hamming: yael/hamming.c:66-219 ------------------------------------------------ */
 /* dis[j*na + i] = popcount(a_i xor b_j), uint16 (compute_hamming, yael/hamming.c:177-219) */
 int yb_compute_hamming(uint16_t *dis, const uint8_t *a, const uint8_t *b, int na, int nb,

@@ -302,3 +302,79 @@ def ref_nn_hamming_blocked(base, query, k, block=1 << 20, threads=None):
         idx[q] = bj[first[q]:first[q] + k]
         dis[q] = dv[first[q]:first[q] + k]
     return idx, dis, ("reference" if use_ref else "port")
+
+
+# ---- consumers of the k = 1 search: VLAD / bag of features (yael/vlad.c)
+def _subsets(subsets):
+    idx = np.ascontiguousarray(np.concatenate([np.asarray(s, np.int32) for s in subsets]) if subsets
+                               else np.zeros(0, np.int32), np.int32)
+    ends = np.ascontiguousarray(np.cumsum([len(s) for s in subsets]), np.int32)
+    return idx, ends
+
+
+def _vlad_family(L, prefix, dot, cent, v, weights=None, subsets=None, ma=None, bof=False):
+    """One calling convention for the oracle (orc_*, extra dot_mode argument) and the compiled
+    reference (vlad_* / bof_*)."""
+    cent, v = f32(cent), f32(v)
+    k, d = cent.shape
+    n = v.shape[0]
+    extra = [] if dot is None else [dot]
+    if subsets is not None:
+        idx, ends = _subsets(subsets)
+        out = np.zeros((len(subsets), k) if bof else (len(subsets), k, d), np.float32)
+        fn = getattr(L, prefix + ("bof_compute_subsets" if bof else "vlad_compute_subsets"))
+        fn.argtypes = [C.c_int, C.c_int, _f, C.c_int, _f, C.c_int, _i, _i, _f] + [C.c_int] * len(extra)
+        fn.restype = None
+        fn(k, d, fp(cent), n, fp(v), len(subsets), ip(idx), ip(ends), fp(out), *extra)
+        return out
+    if bof:
+        out = np.zeros(k, np.int32)
+        if prefix:   # oracle: one entry point for ma >= 1
+            fn = L.orc_bof_compute_ma
+            fn.argtypes = [C.c_int, C.c_int, _f, C.c_int, _f, _i, C.c_int, C.c_int]
+            fn.restype = None
+            fn(k, d, fp(cent), n, fp(v), ip(out), ma or 1, dot)
+        elif ma:
+            fn = L.bof_compute_ma
+            fn.argtypes = [C.c_int, C.c_int, _f, C.c_int, _f, _i, C.c_int, C.c_float, C.c_int]
+            fn.restype = None
+            fn(k, d, fp(cent), n, fp(v), ip(out), ma, 0.0, 1)
+        else:
+            fn = L.bof_compute
+            fn.argtypes = [C.c_int, C.c_int, _f, C.c_int, _f, _i]
+            fn.restype = None
+            fn(k, d, fp(cent), n, fp(v), ip(out))
+        return out
+    out = np.zeros((k, d), np.float32)
+    if prefix:
+        fn = L.orc_vlad_compute
+        fn.argtypes = [C.c_int, C.c_int, _f, C.c_int, _f, _f, _f, C.c_int]
+        fn.restype = None
+        fn(k, d, fp(cent), n, fp(v), fp(f32(weights)) if weights is not None else None, fp(out), dot)
+    elif weights is not None:
+        fn = L.vlad_compute_weighted
+        fn.argtypes = [C.c_int, C.c_int, _f, C.c_int, _f, _f, _f]
+        fn.restype = None
+        fn(k, d, fp(cent), n, fp(v), fp(f32(weights)), fp(out))
+    else:
+        fn = L.vlad_compute
+        fn.argtypes = [C.c_int, C.c_int, _f, C.c_int, _f, _f]
+        fn.restype = None
+        fn(k, d, fp(cent), n, fp(v), fp(out))
+    return out
+
+
+def orc_vlad(cent, v, weights=None, subsets=None, dot_mode=DOT_F32_SEQ):
+    return _vlad_family(oracle(), "orc_", dot_mode, cent, v, weights=weights, subsets=subsets)
+
+
+def orc_bof(cent, v, ma=None, subsets=None, dot_mode=DOT_F32_SEQ):
+    return _vlad_family(oracle(), "orc_", dot_mode, cent, v, subsets=subsets, ma=ma, bof=True)
+
+
+def ref_vlad(cent, v, weights=None, subsets=None):
+    return _vlad_family(ref(), "", None, cent, v, weights=weights, subsets=subsets)
+
+
+def ref_bof(cent, v, ma=None, subsets=None):
+    return _vlad_family(ref(), "", None, cent, v, subsets=subsets, ma=ma, bof=True)

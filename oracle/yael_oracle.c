@@ -859,3 +859,76 @@ size_t orc_crossmatch_hamming_prealloc(const uint8_t *dbs, long n, int ht, int n
     }
   return cnt;
 }
+
+/* ---- consumers of the k = 1 search: VLAD / bag of features (yael/vlad.c:10-139) ---- */
+/* yael/vlad.c:10-49: assign = nn() (yael/nn.c:608-621 -> knn_full, k = 1), then, for the points in
+ * increasing order, desc[assign_i] += fl32(v_i - c) (times w_i: vlad.c:45); floats throughout */
+void orc_vlad_compute(int k, int d, const float *centroids, int n, const float *v,
+                      const float *weights, float *desc, int dot_mode) {
+  int *assign = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  float *dis = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+  orc_knn_full(n, k, d, 1, centroids, v, NULL, assign, dis, dot_mode, 1);
+  memset(desc, 0, sizeof(float) * (size_t)k * d);
+  for (long i = 0; i < n; i++) {
+    const float *c = centroids + (size_t)assign[i] * d;
+    float *o = desc + (size_t)assign[i] * d;
+    for (int j = 0; j < d; j++) {
+      float r = v[i * d + j] - c[j];
+      if (weights) r = r * weights[i];
+      o[j] += r;
+    }
+  }
+  free(assign);
+  free(dis);
+}
+
+/* yael/vlad.c:52-79: one descriptor per subset, summed in LIST order */
+void orc_vlad_compute_subsets(int k, int d, const float *centroids, int n, const float *v,
+                              int n_subset, const int *subset_indexes, const int *subset_ends,
+                              float *desc, int dot_mode) {
+  int *assign = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  float *dis = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+  orc_knn_full(n, k, d, 1, centroids, v, NULL, assign, dis, dot_mode, 1);
+  memset(desc, 0, sizeof(float) * (size_t)k * d * n_subset);
+  int begin = 0;
+  for (int ss = 0; ss < n_subset; ss++) {
+    float *dss = desc + (size_t)ss * k * d;
+    for (int ii = begin; ii < subset_ends[ss]; ii++) {
+      const long i = subset_indexes[ii];
+      for (int j = 0; j < d; j++)
+        dss[(size_t)assign[i] * d + j] += v[i * d + j] - centroids[(size_t)assign[i] * d + j];
+    }
+    begin = subset_ends[ss];
+  }
+  free(assign);
+  free(dis);
+}
+
+/* yael/vlad.c:110-138: histogram of the ma nearest centroids of every point (ma = 1: bof_compute) */
+void orc_bof_compute_ma(int k, int d, const float *centroids, int n, const float *v, int *desc, int ma,
+                        int dot_mode) {
+  int *assign = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1) * ma);
+  float *dis = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1) * ma);
+  orc_knn_full(n, k, d, ma, centroids, v, NULL, assign, dis, dot_mode, 1);
+  memset(desc, 0, sizeof(int) * (size_t)k);
+  for (long i = 0; i < (long)n * ma; i++) desc[assign[i]]++;
+  free(assign);
+  free(dis);
+}
+
+/* yael/vlad.c:82-107: one float histogram per subset */
+void orc_bof_compute_subsets(int k, int d, const float *centroids, int n, const float *v, int n_subset,
+                             const int *subset_indexes, const int *subset_ends, float *desc,
+                             int dot_mode) {
+  int *assign = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  float *dis = (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+  orc_knn_full(n, k, d, 1, centroids, v, NULL, assign, dis, dot_mode, 1);
+  memset(desc, 0, sizeof(float) * (size_t)k * n_subset);
+  int begin = 0;
+  for (int ss = 0; ss < n_subset; ss++) {
+    for (int ii = begin; ii < subset_ends[ss]; ii++) desc[(size_t)ss * k + assign[subset_indexes[ii]]] += 1.0f;
+    begin = subset_ends[ss];
+  }
+  free(assign);
+  free(dis);
+}

@@ -137,3 +137,16 @@ for t in (1, 2, 3, 4, 5, 6, 16):
                               ob.ip(i_), ob.fp(d_), 2)
             aout["idx_t%d_k%d%s" % (t, k, wname)], aout["dis_t%d_k%d%s" % (t, k, wname)] = i_, d_
 save("knn_alt_weighted", **aout)
+
+# 11. consumers of the k = 1 search (yael/vlad.c:10-139): VLAD (plain, weighted, subsets) and bag of
+#     features (plain, multiple assignment, subsets); SIFT-like codebook size, ragged subsets
+rv = np.random.RandomState(11)
+vc = rv.random_sample((64, 32)).astype(np.float32)
+vv = rv.random_sample((3000, 32)).astype(np.float32)
+vw = (0.25 + rv.random_sample(3000)).astype(np.float32)
+subs = [rv.permutation(3000)[:700].tolist(), list(range(1000, 1900)), [], [5, 5, 5, 2999, 0]]
+sidx, sends = ob._subsets(subs)
+save("vlad_bof", centroids=vc, v=vv, weights=vw, subset_indexes=sidx, subset_ends=sends,
+     vlad=ob.ref_vlad(vc, vv), vlad_weighted=ob.ref_vlad(vc, vv, weights=vw),
+     vlad_subsets=ob.ref_vlad(vc, vv, subsets=subs), bof=ob.ref_bof(vc, vv), bof_ma3=ob.ref_bof(vc, vv, ma=3),
+     bof_subsets=ob.ref_bof(vc, vv, subsets=subs))

@@ -166,3 +166,22 @@ def test_oracle_matches_compiled_reference_fresh_inputs(ob):
     r0 = ob.ref_kmeans(v, 32, 10, ob.KMEANS_QUIET | 2, 4321)
     r1 = ob.orc_kmeans(v, 32, 10, ob.KMEANS_QUIET | 2, 4321)
     assert np.array_equal(r0[1], r1[1]) and np.array_equal(r0[4], r1[4])
+
+
+def _golden_subsets(g):
+    ends = g["subset_ends"]
+    idx = g["subset_indexes"]
+    return [idx[(ends[i - 1] if i else 0):ends[i]].tolist() for i in range(len(ends))]
+
+
+def test_vlad_bof_golden(ob):
+    # yael/vlad.c:10-139, golden from the compiled reference (scripts/make_golden.py, fixture 11)
+    g = gold("vlad_bof")
+    c, v, subs = g["centroids"], g["v"], _golden_subsets(g)
+    assert np.array_equal(ob.orc_vlad(c, v), g["vlad"])
+    assert np.array_equal(ob.orc_vlad(c, v, weights=g["weights"]), g["vlad_weighted"])
+    assert np.array_equal(ob.orc_vlad(c, v, subsets=subs), g["vlad_subsets"])
+    assert np.array_equal(ob.orc_bof(c, v), g["bof"])
+    assert np.array_equal(ob.orc_bof(c, v, ma=3), g["bof_ma3"])
+    assert np.array_equal(ob.orc_bof(c, v, subsets=subs), g["bof_subsets"])
+    assert g["bof"].sum() == len(v) and g["bof_ma3"].sum() == 3 * len(v)

@@ -80,6 +80,13 @@ DROPIN = {
                                   C.POINTER(C.c_size_t)]),
     "crossmatch_hamming_prealloc": (C.c_size_t, [_u8, C.c_long, C.c_int, C.c_int, _i, _u16]),
     "compute_hamming_thread": (None, [_u16, _u8, _u8, C.c_int, C.c_int, C.c_int]),
+    # include/yael/vlad.h  (reference yael/vlad.h:9-49)
+    "vlad_compute": (None, [C.c_int, C.c_int, _f, C.c_int, _f, _f]),
+    "vlad_compute_weighted": (None, [C.c_int, C.c_int, _f, C.c_int, _f, _f, _f]),
+    "vlad_compute_subsets": (None, [C.c_int, C.c_int, _f, C.c_int, _f, C.c_int, _i, _i, _f]),
+    "bof_compute": (None, [C.c_int, C.c_int, _f, C.c_int, _f, _i]),
+    "bof_compute_ma": (None, [C.c_int, C.c_int, _f, C.c_int, _f, _i, C.c_int, C.c_float, C.c_int]),
+    "bof_compute_subsets": (None, [C.c_int, C.c_int, _f, C.c_int, _f, C.c_int, _i, _i, _f]),
     # include/yael/binheap.h  (reference yael/binheap.h:31-87)
     "fbinheap_new": (_vp, [C.c_int]),
     "fbinheap_sizeof": (C.c_size_t, [C.c_int]),
@@ -165,6 +172,8 @@ DEVICE = {
     "yb_last_hamming_fallbacks": (C.c_long, []),
     "yb_debug_hamming_tc_scores": (C.c_int, [C.c_int] * 3 + [_vp, _vp, _vp, _vp]),
     "yb_debug_hamming_tc_packed": (C.c_int, [C.c_int] * 4 + [_vp, _vp, _vp, _vp]),
+    "yb_vlad_accumulate": (C.c_int, [C.c_int, C.c_int, _vp, C.c_long, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "yb_bof_accumulate": (C.c_int, [C.c_int, C.c_long, _vp, _vp, C.c_long, _vp, _vp, _vp]),
     "yb_match_hamming_count": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "yb_match_hamming_thres": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "yb_crossmatch_hamming_count": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),

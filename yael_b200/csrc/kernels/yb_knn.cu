@@ -1454,7 +1454,8 @@ k_rerank_k1(int nq, int d, int slots, int lists, const float *__restrict__ base,
         }
         __syncwarp();
         if (lane < nb_) {
-          for (int t = 0; t < dc; t++) {
+#pragma unroll 16
+          for (int t = 0; t < dc; t++) {  // (unrolled: the shared-memory loads run ahead of the chains)
             const float v = rows[warp][lane][t];
             nf = __fadd_rn(nf, __fmul_rn(v, v));
             dot = fmaf(v, qs[warp][t], dot);
@@ -1496,6 +1497,9 @@ k_rerank_k1(int nq, int d, int slots, int lists, const float *__restrict__ base,
   }
 }
 
+// (Round 2 tried a LANE per query -- 32 queries per warp, candidate and query rows staged through
+// padded shared tiles, the query norm fused in: bit-identical, but 24.1 ms against 14.5 ms at
+// BASELINE configs[3]: the staging loop's loads are only four deep.  Not kept; profiles/README.md.)
 static int knn_tf32_nearest(int nq, int nb, int d, const float *base, const float *query,
                             int *assign, float *dis, int id_offset, long *uncert_out,
                             cudaStream_t st, int kind) {

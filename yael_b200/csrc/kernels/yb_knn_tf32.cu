@@ -948,6 +948,51 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
                   ocol[(size_t)((g + 1) * 32 + c) * P.dump_ld] = __fmul_rn(asc, __uint_as_float(vb[c]));
             }
           }
+        } else if (MODE == EPI_GMIN && NF && LDW == 128) {
+          // sampling pass, early hand-back: the half tile comes into registers with two 64-column
+          // loads and one wait, the buffer goes back at once, then the 8 group maxima are folded to
+          // the requested group size (16 / 32 / 64 / 128 columns) and stored
+          uint32_t va[64], vb[64];
+          const uint32_t ta = lane_addr + buf * TN;
+          tc_ldw<64>(ta, va);
+          tc_ldw<64>(ta + 64, vb);
+          tc_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t te = buf ? E.t_empty_addr1 : E.t_empty_addr0;
+            if (E.t_empty_remote)
+              mbar_arrive_cluster(te);
+            else
+              mbar_arrive(te);
+          }
+          handed_back = true;
+          float g[8];
+#pragma unroll
+          for (int s4 = 0; s4 < 4; s4++) {
+            g[s4] = group_max16(reinterpret_cast<const uint32_t(&)[16]>(va[16 * s4]));
+            g[4 + s4] = group_max16(reinterpret_cast<const uint32_t(&)[16]>(vb[16 * s4]));
+          }
+          if (valid) {
+            const int per_half = HALF_N / P.gsize;
+            float *grow = P.gmin + (size_t)q * P.gmin_ld + ((long)jt * 2 + half) * per_half;
+            // (a maximum of raw accumulators is a minimum of scores: asc < 0; NaN never wins fmaxf)
+            if (P.gsize == 16) {
+#pragma unroll
+              for (int i = 0; i < 8; i++) grow[i] = fmaf(asc, g[i], c0);
+            } else if (P.gsize == 32) {
+#pragma unroll
+              for (int i = 0; i < 4; i++) grow[i] = fmaf(asc, fmaxf(g[2 * i], g[2 * i + 1]), c0);
+            } else if (P.gsize == 64) {
+#pragma unroll
+              for (int i = 0; i < 2; i++)
+                grow[i] = fmaf(asc, fmaxf(fmaxf(g[4 * i], g[4 * i + 1]), fmaxf(g[4 * i + 2], g[4 * i + 3])), c0);
+            } else {
+              const float a = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+              const float b = fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7]));
+              grow[0] = fmaf(asc, fmaxf(a, b), c0);
+            }
+          }
         } else if (MODE == EPI_GMIN) {
           // sampling pass: only the minimum of every column group leaves the SM
           uint32_t va[16], vb[16];
@@ -2216,14 +2261,14 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
     if (plan.pair == 2) {
       switch (mode) {
         case EPI_DUMP: return launch_2sm<EPI_DUMP, 16, OP_F8C>(plan, mq, mbh, mqx, mbxh, P, st);
-        case EPI_GMIN: return launch_2sm<EPI_GMIN, 16, OP_F8C>(plan, mq, mbh, mqx, mbxh, P, st);
+        case EPI_GMIN: return launch_2sm<EPI_GMIN, 128, OP_F8C>(plan, mq, mbh, mqx, mbxh, P, st);
         case EPI_LISTS: return launch_2sm<EPI_LISTS, 128, OP_F8C>(plan, mq, mbh, mqx, mbxh, P, st);
         default: return fail(6, "the E4M3 operand kind has no k = 1 margin mode");
       }
     }
     switch (mode) {
       case EPI_DUMP: return launch_mode<EPI_DUMP, OP_F8C>(plan, mq, mb, mbh, mqx, mbx, P, st);
-      case EPI_GMIN: return launch_mode<EPI_GMIN, OP_F8C>(plan, mq, mb, mbh, mqx, mbx, P, st);
+      case EPI_GMIN: return launch_mode<EPI_GMIN, OP_F8C, 128>(plan, mq, mb, mbh, mqx, mbx, P, st);
       case EPI_LISTS: return launch_mode<EPI_LISTS, OP_F8C, 128>(plan, mq, mb, mbh, mqx, mbx, P, st);
       default: return fail(6, "the E4M3 operand kind has no k = 1 margin mode");
     }
@@ -2270,7 +2315,7 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
     switch (mode) {
       case EPI_CROSS: return launch_2sm<EPI_CROSS, 16, OP_F16N, true>(plan, mq, mbh, mqx, mbxh, P, st);
       case EPI_DUMP: return launch_2sm<EPI_DUMP, 16, OP_F16N, true>(plan, mq, mbh, mqx, mbxh, P, st);
-      case EPI_GMIN: return launch_2sm<EPI_GMIN, 16, OP_F16N, true>(plan, mq, mbh, mqx, mbxh, P, st);
+      case EPI_GMIN: return launch_2sm<EPI_GMIN, 128, OP_F16N, true>(plan, mq, mbh, mqx, mbxh, P, st);
       case EPI_LISTS: return launch_2sm<EPI_LISTS, 128, OP_F16N, true>(plan, mq, mbh, mqx, mbxh, P, st);
       default: return launch_2sm<EPI_NEAREST, 128, OP_F16N, true>(plan, mq, mbh, mqx, mbxh, P, st);
     }
@@ -2280,7 +2325,9 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
     switch (mode) {
       case EPI_CROSS: return launch_2sm<EPI_CROSS, 16>(plan, mq, mbh, mqx, mbxh, P, st);
       case EPI_DUMP: return launch_2sm<EPI_DUMP, 16>(plan, mq, mbh, mqx, mbxh, P, st);
-      case EPI_GMIN: return launch_2sm<EPI_GMIN, 16>(plan, mq, mbh, mqx, mbxh, P, st);
+      case EPI_GMIN:
+        if (ldw == 16) return launch_2sm<EPI_GMIN, 16>(plan, mq, mbh, mqx, mbxh, P, st);
+        return launch_2sm<EPI_GMIN, 128>(plan, mq, mbh, mqx, mbxh, P, st);
       case EPI_LISTS:
         if (ldw == 128) return launch_2sm<EPI_LISTS, 128>(plan, mq, mbh, mqx, mbxh, P, st);
         if (ldw == 64) return launch_2sm<EPI_LISTS, 64>(plan, mq, mbh, mqx, mbxh, P, st);
@@ -2295,7 +2342,9 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   if (plan.kind == OP_F16N) {  // FP16 operands with folded norms: top-k', sampling, dump
     switch (mode) {
       case EPI_DUMP: return launch_mode<EPI_DUMP, OP_F16N>(plan, mq, mb, mbh, mqx, mbx, P, st);
-      case EPI_GMIN: return launch_mode<EPI_GMIN, OP_F16N>(plan, mq, mb, mbh, mqx, mbx, P, st);
+      case EPI_GMIN:
+        if (ldw == 16) return launch_mode<EPI_GMIN, OP_F16N>(plan, mq, mb, mbh, mqx, mbx, P, st);
+        return launch_mode<EPI_GMIN, OP_F16N, 128>(plan, mq, mb, mbh, mqx, mbx, P, st);
       case EPI_LISTS:
         if (ldw == 128) return launch_mode<EPI_LISTS, OP_F16N, 128>(plan, mq, mb, mbh, mqx, mbx, P, st);
         if (ldw == 64) return launch_mode<EPI_LISTS, OP_F16N, 64>(plan, mq, mb, mbh, mqx, mbx, P, st);

@@ -228,3 +228,53 @@ def crossmatch_hamming(a, ht):
         lib().crossmatch_hamming_prealloc(a.ctypes.data_as(_u8), a.shape[0], ht, a.shape[1],
                                           _ip(pairs), scores.ctypes.data_as(_u16))
     return pairs, scores
+
+
+# ---- consumers of the k = 1 search (include/yael/vlad.h; not in the reference's ynumpy: same
+# ---- call shapes as the C functions, arrays in / arrays out)
+def _subset_arrays(subsets):
+    idx = np.ascontiguousarray(np.concatenate([np.asarray(s, np.int32) for s in subsets]) if len(subsets)
+                               else np.zeros(0, np.int32), np.int32)
+    ends = np.ascontiguousarray(np.cumsum([len(s) for s in subsets]), np.int32)
+    return idx, ends
+
+
+def vlad(centroids, v, weights=None, subsets=None):
+    """vlad_compute / vlad_compute_weighted / vlad_compute_subsets (yael/vlad.c:10-79)."""
+    _check_row_float32(centroids)
+    _check_row_float32(v)
+    k, d = centroids.shape
+    n = v.shape[0]
+    _lib.require_gpu()
+    if subsets is not None:
+        idx, ends = _subset_arrays(subsets)
+        desc = np.zeros((len(subsets), k, d), np.float32)
+        lib().vlad_compute_subsets(k, d, _fp(centroids), n, _fp(v), len(subsets), _ip(idx), _ip(ends), _fp(desc))
+        return desc
+    desc = np.zeros((k, d), np.float32)
+    if weights is not None:
+        w = np.ascontiguousarray(weights, np.float32)
+        lib().vlad_compute_weighted(k, d, _fp(centroids), n, _fp(v), _fp(w), _fp(desc))
+    else:
+        lib().vlad_compute(k, d, _fp(centroids), n, _fp(v), _fp(desc))
+    return desc
+
+
+def bof(centroids, v, ma=None, subsets=None):
+    """bof_compute / bof_compute_ma / bof_compute_subsets (yael/vlad.c:82-139)."""
+    _check_row_float32(centroids)
+    _check_row_float32(v)
+    k, d = centroids.shape
+    n = v.shape[0]
+    _lib.require_gpu()
+    if subsets is not None:
+        idx, ends = _subset_arrays(subsets)
+        desc = np.zeros((len(subsets), k), np.float32)
+        lib().bof_compute_subsets(k, d, _fp(centroids), n, _fp(v), len(subsets), _ip(idx), _ip(ends), _fp(desc))
+        return desc
+    desc = np.zeros(k, np.int32)
+    if ma:
+        lib().bof_compute_ma(k, d, _fp(centroids), n, _fp(v), _ip(desc), int(ma), 0.0, 1)
+    else:
+        lib().bof_compute(k, d, _fp(centroids), n, _fp(v), _ip(desc))
+    return desc
