@@ -684,6 +684,42 @@ __device__ __forceinline__ void process_wide_nf(const uint32_t (&v)[W], float &t
   }
 }
 
+// The same for the top-k' mode with the COMMON admission handled inline: a fired group almost always
+// holds exactly one value beyond the threshold -- its maximum, which the tree already produced -- so
+// a 16-bit mask of `v > thrp` (independent compares, no chain through the list counter) finds its
+// column and the entry is written without the out-of-line call (whose 16 dependent test / store /
+// count steps cost a warp ~230 clk, about 1.6 times per tile at 400 admissions per query).  Two or
+// more admissions in one group of 16 take the old path.
+template <int W>
+__device__ __forceinline__ void process_wide_lists(const uint32_t (&v)[W], float thr, float thrp,
+                                                   float2 *mylist, int &cnt, int id0, float asc, float c0) {
+  float gm[W / 16];
+#pragma unroll
+  for (int s = 0; s < W / 16; s++) gm[s] = group_max16(reinterpret_cast<const uint32_t(&)[16]>(v[16 * s]));
+  float M = gm[0];
+#pragma unroll
+  for (int s = 1; s < W / 16; s++) M = fmaxf(M, gm[s]);
+  if (M > thrp) {
+#pragma unroll
+    for (int s = 0; s < W / 16; s++) {
+      if (gm[s] > thrp) {
+        unsigned m = 0u;
+#pragma unroll
+        for (int c = 0; c < 16; c++) m |= (__uint_as_float(v[16 * s + c]) > thrp) ? (1u << c) : 0u;
+        if (__popc(m) == 1) {
+          mylist[cnt] = make_float2(fmaf(asc, gm[s], c0), __int_as_float(id0 + 16 * s + __ffs(m) - 1));
+          cnt++;
+        } else {
+          float sc[16];
+#pragma unroll
+          for (int c = 0; c < 16; c++) sc[c] = fmaf(asc, __uint_as_float(v[16 * s + c]), c0);
+          cnt = slow_append(YB_SC16_ARGS(sc), thr, mylist, cnt, id0 + 16 * s);
+        }
+      }
+    }
+  }
+}
+
 // smallest score of 16 accumulator columns (sampling pass)
 __device__ __forceinline__ float group_min16(const uint32_t (&v)[16], const float *bn, float asc) {
   float sc[16];
@@ -700,6 +736,53 @@ __device__ __forceinline__ float group_min16(const uint32_t (&v)[16], const floa
   float m45 = fminf(fminf(sc[8], sc[9]), fminf(sc[10], sc[11]));
   float m67 = fminf(fminf(sc[12], sc[13]), fminf(sc[14], sc[15]));
   return fminf(fminf(m01, m23), fminf(m45, m67));
+}
+
+// k = 1 margin mode, the common admission inline (as process_wide_lists): a fired group nearly always
+// holds ONE value within the margin -- its maximum.  It is appended, and when it beats the best
+// score so far the threshold follows (slow_append_k1's rule: append against the OLD threshold, then
+// best = min, thr = best + margin).  Several admissions in one group, or a list close to its
+// capacity (pruning / overflow handling), take the out-of-line path.
+template <int W>
+__device__ __forceinline__ void process_wide_k1(const uint32_t (&v)[W], float &thr, float &thrp, float &best,
+                                                float margin, float2 *mylist, int &cnt, int cap, int id0,
+                                                float asc, float inv_asc, float c0) {
+  float gm[W / 16];
+#pragma unroll
+  for (int s = 0; s < W / 16; s++) gm[s] = group_max16(reinterpret_cast<const uint32_t(&)[16]>(v[16 * s]));
+  float M = gm[0];
+#pragma unroll
+  for (int s = 1; s < W / 16; s++) M = fmaxf(M, gm[s]);
+  if (M > thrp) {
+#pragma unroll
+    for (int s = 0; s < W / 16; s++) {
+      if (gm[s] > thrp) {
+        unsigned m = 0u;
+#pragma unroll
+        for (int c = 0; c < 16; c++) m |= (__uint_as_float(v[16 * s + c]) > thrp) ? (1u << c) : 0u;
+        if (__popc(m) == 1 && cnt < cap - 16) {
+          const float sc = fmaf(asc, gm[s], c0);
+          mylist[cnt] = make_float2(sc, __int_as_float(id0 + 16 * s + __ffs(m) - 1));
+          cnt++;
+          if (sc < best) {
+            best = sc;
+            thr = sc + margin;
+            thrp = __fmul_rn(thr - c0, inv_asc);
+          }
+        } else {
+          float sc[16];
+#pragma unroll
+          for (int c = 0; c < 16; c++) sc[c] = fmaf(asc, __uint_as_float(v[16 * s + c]), c0);
+          K1State st = {thr, best, cnt};
+          st = slow_append_k1(YB_SC16_ARGS(sc), fmaf(asc, gm[s], c0), st, margin, mylist, cap, id0 + 16 * s);
+          thr = st.thr;
+          best = st.best;
+          cnt = st.cnt;
+          thrp = __fmul_rn(thr - c0, inv_asc);
+        }
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------ packed Hamming helpers
@@ -878,7 +961,78 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
       uint32_t tau3 = 0u;
       const uint32_t ham_mask = P.ham_slots == 3 ? 0x808080u : 0x8080u;
       if (MODE == EPI_HAMP) tau3 = ham_tau3(thr);
-      for (int jt = jt0; jt < jt1; jt++, tcount++) {
+      // ---- software-pipelined drain (folded-norm / constant-norm kinds, top-k' and k = 1 modes):
+      // the accumulators of tile t+1 are loaded WHILE tile t is being tested.  A half tile is 64
+      // registers (va: columns 0-63, vb: 64-127 of this thread's half): after va of tile t has been
+      // tested it is free, so the epilogue waits for tile t+1's accumulator (long complete by then),
+      // issues its first load into va, tests vb of tile t in the load's shadow, then issues the second
+      // load into vb, waits for both and hands the buffer back.  Per tile the warp no longer pays
+      // "wait for the accumulator + two loads" (~570 of its ~1640 clk) in series with the tests.
+      constexpr bool PIPE = NF && LDW == 128 && EPI_TEAMS == 1 && (MODE == EPI_LISTS || MODE == EPI_NEAREST);
+      const bool piped = PIPE && !(P.debug & (2048 | 512 | 1 | 256));  // (bit 2048: the serial drain, A/B)
+      if (PIPE && piped) {
+        constexpr bool K1W = MODE == EPI_NEAREST;
+        uint32_t va[64], vb[64];
+        auto hand_back = [&](uint32_t b) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t te = b ? E.t_empty_addr1 : E.t_empty_addr0;
+            if (E.t_empty_remote)
+              mbar_arrive_cluster(te);
+            else
+              mbar_arrive(te);
+          }
+        };
+        {  // prologue: the first tile of the item
+          const uint32_t b0 = tcount & 1;
+          mbar_wait(bar(E.t_full0 + b0), (tcount >> 1) & 1);
+          tc_fence_after();
+          const uint32_t ta = lane_addr + b0 * TN;
+          tc_ldw<64>(ta, va);
+          tc_ldw<64>(ta + 64, vb);
+          tc_wait_ld();
+          hand_back(b0);
+        }
+        for (int jt = jt0; jt < jt1; jt++, tcount++) {
+          const int n0 = jt * P.tile_stride * TN + half * HALF_N + P.id0;
+          const bool more = jt + 1 < jt1;
+          const uint32_t nbuf = (tcount + 1) & 1;
+          const uint32_t tan = lane_addr + nbuf * TN;
+          if (!K1W) process_wide_lists<64>(va, thr, thrp, mylist, cnt, n0, asc, c0);
+          else if (P.debug & 1024) process_wide_nf<K1W, 64>(va, thr, thrp, best, margin, mylist, cnt, P.cap, n0, asc, inv_asc, c0);
+          else process_wide_k1<64>(va, thr, thrp, best, margin, mylist, cnt, P.cap, n0, asc, inv_asc, c0);
+          if (more) {
+            mbar_wait(bar(E.t_full0 + nbuf), ((tcount + 1) >> 1) & 1);
+            tc_fence_after();
+            tc_ldw<64>(tan, va);  // in flight while vb is tested
+          }
+          if (!K1W) process_wide_lists<64>(vb, thr, thrp, mylist, cnt, n0 + 64, asc, c0);
+          else if (P.debug & 1024) process_wide_nf<K1W, 64>(vb, thr, thrp, best, margin, mylist, cnt, P.cap, n0 + 64, asc, inv_asc, c0);
+          else process_wide_k1<64>(vb, thr, thrp, best, margin, mylist, cnt, P.cap, n0 + 64, asc, inv_asc, c0);
+          if (more) {
+            tc_ldw<64>(tan + 64, vb);
+            tc_wait_ld();
+            hand_back(nbuf);
+          }
+          // keep room for a full half tile of appends in every list of the warp
+          unsigned need = __ballot_sync(0xffffffffu, !K1W && cnt > P.cap - HALF_N);
+          while (need) {
+            const int owner = __ffs(need) - 1;
+            need &= need - 1;
+            float2 *l = (float2 *)__shfl_sync(0xffffffffu, (unsigned long long)mylist, owner);
+            const int n = __shfl_sync(0xffffffffu, cnt, owner);
+            __syncwarp();
+            const float nt = warp_select_compact(l, n, P.kprime, hist);
+            if (lane == owner) {
+              thr = nt;
+              cnt = P.kprime;
+            }
+          }
+          thrp = __fmul_rn(thr - c0, inv_asc);
+        }
+      }
+      for (int jt = jt0; !(PIPE && piped) && jt < jt1; jt++, tcount++) {
         const uint32_t buf = tcount & 1, slot = tcount % NBN;
         if (EPI_TEAMS > 1 && (int)buf != team) continue;  // the other team's accumulator buffer
         bool handed_back = false;
@@ -1120,8 +1274,13 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           }
           handed_back = true;
           if (!(P.debug & 1)) {
-            process_wide_nf<K1W, 64>(va, thr, thrp, best, margin, mylist, cnt, P.cap, n0, asc, inv_asc, c0);
-            process_wide_nf<K1W, 64>(vb, thr, thrp, best, margin, mylist, cnt, P.cap, n0 + 64, asc, inv_asc, c0);
+            if (!K1W && !(P.debug & 1024)) {  // (bit 1024: the out-of-line admission path only, A/B)
+              process_wide_lists<64>(va, thr, thrp, mylist, cnt, n0, asc, c0);
+              process_wide_lists<64>(vb, thr, thrp, mylist, cnt, n0 + 64, asc, c0);
+            } else {
+              process_wide_nf<K1W, 64>(va, thr, thrp, best, margin, mylist, cnt, P.cap, n0, asc, inv_asc, c0);
+              process_wide_nf<K1W, 64>(vb, thr, thrp, best, margin, mylist, cnt, P.cap, n0 + 64, asc, inv_asc, c0);
+            }
           }
         } else if (NF && LDW > 16 && (MODE == EPI_LISTS || MODE == EPI_NEAREST)) {
           // HALF_N / LDW wide loads, load g+1 in flight while g is processed
