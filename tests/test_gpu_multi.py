@@ -84,12 +84,24 @@ def _worker(rank, world, port, q):
         i4, d4 = s.search(torch.from_numpy(query[:333]).to(dev))
         detail['knn_ragged'] = bool(np.array_equal(i4.cpu().numpy(), widx[:333]) and
                                     np.array_equal(d4.cpu().numpy(), wdis[:333]))
+        # uneven shards with the offsets derived from an all-gather of the shard sizes, and a shard
+        # with FEWER rows than k (the reference only needs k <= n over all rows, nn.c:456)
+        small = r.random_sample((150, 64)).astype(np.float32)
+        cut = 30 if rank == 0 else 150
+        part = small[:30] if rank == 0 else small[30:]
+        s6 = ydist.ShardedKnn(torch.from_numpy(part).to(dev), 50, rank=rank, world=world)
+        i6, d6 = s6.search(torch.from_numpy(query[:40]).to(dev))
+        wi6, wd6 = ynumpy.knn(query[:40], small, 50)
+        detail['knn_uneven_small_shard'] = bool(np.array_equal(i6.cpu().numpy(), wi6) and
+                                                np.array_equal(d6.cpu().numpy(), wd6))
+        del cut
         c5, q5, a5, n5 = ydist.sharded_kmeans(torch.from_numpy(v[lo:hi]).to(dev), 64, 5, init, len(v),
                                               exchange="torch")
         detail['kmeans_torch_exchange'] = bool(np.array_equal(n5, nassign) and np.array_equal(c5, cent))
         ok = detail['knn'] and detail['knn_host'] and detail['hamming'] and detail['kmeans_counts'] and \
             detail['kmeans_cent_maxdiff'] < 1e-4 and abs(qerr - wq) < 1e-4 * wq and \
-            detail['knn_torch_exchange'] and detail['knn_ragged'] and detail['kmeans_torch_exchange']
+            detail['knn_torch_exchange'] and detail['knn_ragged'] and detail['kmeans_torch_exchange'] and \
+            detail['knn_uneven_small_shard']
         q.put((rank, True if ok else repr(detail)))
     except Exception as e:  # report instead of hanging the peer
         q.put((rank, "error: %r" % (e,)))

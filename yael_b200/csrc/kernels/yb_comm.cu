@@ -139,6 +139,26 @@ __global__ void k_pad_rows_u16(unsigned *__restrict__ ids, unsigned short *__res
   }
 }
 
+// a shard with fewer than k rows: its lists [nq][kl] are widened to [nq][k], the tail never selected
+__global__ void k_widen_u32(const unsigned *__restrict__ si, const unsigned *__restrict__ sd, long nq, int kl,
+                            int k, unsigned *__restrict__ di, unsigned *__restrict__ dd) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nq * k) return;
+  const long q = t / k;
+  const int j = (int)(t - q * k);
+  di[t] = j < kl ? si[q * kl + j] : 0xffffffffu;
+  dd[t] = j < kl ? sd[q * kl + j] : 0xffffffffu;
+}
+__global__ void k_widen_u16(const unsigned *__restrict__ si, const unsigned short *__restrict__ sd, long nq, int kl,
+                            int k, unsigned *__restrict__ di, unsigned short *__restrict__ dd) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nq * k) return;
+  const long q = t / k;
+  const int j = (int)(t - q * k);
+  di[t] = j < kl ? si[q * kl + j] : 0xffffffffu;
+  dd[t] = j < kl ? sd[q * kl + j] : (unsigned short)0xffffu;
+}
+
 // ---- peer-memory exchange
 // rows [p*slice, (p+1)*slice) of my lists go to rank p's segment at [me][slice][k]: ids (4 bytes per
 // entry) at off_i, distances (dsz = 4 or 2 bytes per entry) at off_d.  One block column per peer.
@@ -538,8 +558,9 @@ int knn_sharded_impl(yb_comm *c, int nq, int nb_local, int d, int k, float *base
                      float *dis, int *slice_assign, float *slice_dis, yb_stream_t s) {
   const NcclApi *N = nccl();
   if (!N) return fail(8, "NCCL is not available");
-  if (k <= 0 || k > nb_local)
-    return fail(3, "sharded k-NN: every shard needs at least k rows (k=%d, shard rows=%d)", k, nb_local);
+  if (k <= 0 || nb_local <= 0)
+    return fail(3, "sharded k-NN: k = %d, shard rows = %d (every rank needs at least one row)", k, nb_local);
+  const int kl = k < nb_local ? k : nb_local;  // the reference only requires k <= n over ALL rows (nn.c:456)
   Guard g;
   cudaStream_t st = stream_of(s);
   const int G = c->world;
@@ -567,10 +588,20 @@ int knn_sharded_impl(yb_comm *c, int nq, int nb_local, int d, int k, float *base
     all_d = all_i ? (float *)(all_i + rows) : nullptr;
   }
   int rc;
+  int *tmp_i = kl < k ? (int *)yb_malloc(sizeof(int) * (size_t)nq * kl * 2) : nullptr;
+  float *tmp_d = tmp_i ? (float *)(tmp_i + (size_t)nq * kl) : nullptr;
   if (base_host)
-    rc = yb_knn_l2_hostbase(nq, nb_local, d, k, base_host, base, query, loc_i, loc_d, id_offset, s);
+    rc = yb_knn_l2_hostbase(nq, nb_local, d, kl, base_host, base, query, tmp_i ? tmp_i : loc_i,
+                            tmp_d ? tmp_d : loc_d, id_offset, s);
   else
-    rc = yb_knn_l2(nq, nb_local, d, k, base, query, nullptr, loc_i, loc_d, id_offset, s);
+    rc = yb_knn_l2(nq, nb_local, d, kl, base, query, nullptr, tmp_i ? tmp_i : loc_i, tmp_d ? tmp_d : loc_d,
+                   id_offset, s);
+  if (!rc && tmp_i) {
+    k_widen_u32<<<(unsigned)(((long)nq * k + 255) / 256), 256, 0, st>>>((const unsigned *)tmp_i, (const unsigned *)tmp_d,
+                                                                     nq, kl, k, (unsigned *)loc_i, (unsigned *)loc_d);
+    count_launch();
+  }
+  if (tmp_i) yb_free(tmp_i);
   if (!rc && nq_pad > nq) {
     const long from = (long)nq * k, to = (long)nq_pad * k;
     k_pad_rows_u32<<<(unsigned)((to - from + 255) / 256), 256, 0, st>>>((unsigned *)loc_i, (unsigned *)loc_d, from, to);
@@ -651,8 +682,9 @@ int hamming_sharded_impl(yb_comm *c, int nq, int nb_local, int ncodes, int k, co
                          int *slice_assign, uint16_t *slice_dis, yb_stream_t s) {
   const NcclApi *N = nccl();
   if (!N) return fail(8, "NCCL is not available");
-  if (k <= 0 || k > nb_local)
-    return fail(3, "sharded Hamming k-NN: every shard needs at least k rows (k=%d, shard rows=%d)", k, nb_local);
+  if (k <= 0 || nb_local <= 0)
+    return fail(3, "sharded Hamming k-NN: k = %d, shard rows = %d (every rank needs at least one row)", k, nb_local);
+  const int kl = k < nb_local ? k : nb_local;
   Guard g;
   cudaStream_t st = stream_of(s);
   const int G = c->world;
@@ -679,7 +711,16 @@ int hamming_sharded_impl(yb_comm *c, int nq, int nb_local, int ncodes, int k, co
     all_i = (gather && nq_pad != nq) ? (int *)yb_malloc(sizeof(int) * rows + sizeof(uint16_t) * rows) : nullptr;
     all_d = all_i ? (uint16_t *)(all_i + rows) : nullptr;
   }
-  int rc = yb_nn_hamming(nq, nb_local, ncodes, k, base, query, loc_i, loc_d, id_offset, s);
+  int *tmp_i = kl < k ? (int *)yb_malloc((sizeof(int) + sizeof(uint16_t)) * (size_t)nq * kl) : nullptr;
+  uint16_t *tmp_d = tmp_i ? (uint16_t *)(tmp_i + (size_t)nq * kl) : nullptr;
+  int rc = yb_nn_hamming(nq, nb_local, ncodes, kl, base, query, tmp_i ? tmp_i : loc_i, tmp_d ? tmp_d : loc_d,
+                         id_offset, s);
+  if (!rc && tmp_i) {
+    k_widen_u16<<<(unsigned)(((long)nq * k + 255) / 256), 256, 0, st>>>((const unsigned *)tmp_i, tmp_d, nq, kl, k,
+                                                                     (unsigned *)loc_i, loc_d);
+    count_launch();
+  }
+  if (tmp_i) yb_free(tmp_i);
   if (!rc && nq_pad > nq) {
     const long from = (long)nq * k, to = (long)nq_pad * k;
     k_pad_rows_u16<<<(unsigned)((to - from + 255) / 256), 256, 0, st>>>((unsigned *)loc_i, loc_d, from, to);

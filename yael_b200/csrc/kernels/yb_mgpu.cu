@@ -202,7 +202,7 @@ extern "C" int yb_mgpu_knn_full(int nq, int nb, int d, int k, const float *base,
   Pool *P = pool_get();
   if (!P) return -1;
   const int G = P->ndev;
-  if ((long)nb / G < k || nb / G < 4096) return -1;
+  if (nb / G < 4096) return -1;
   const long slice = ((long)nq + G - 1) / G;
   const int rc = run_all(P, [=](int i) -> int {
     const long lo = (long)nb * i / G, hi = (long)nb * (i + 1) / G;
@@ -232,7 +232,7 @@ extern "C" int yb_mgpu_nn_hamming(int nq, int nb, int ncodes, int k, const uint8
   Pool *P = pool_get();
   if (!P) return -1;
   const int G = P->ndev;
-  if ((long)nb / G < k || nb / G < 4096) return -1;
+  if (nb / G < 4096) return -1;
   const long slice = ((long)nq + G - 1) / G;
   const int rc = run_all(P, [=](int i) -> int {
     const long lo = (long)nb * i / G, hi = (long)nb * (i + 1) / G;

@@ -114,6 +114,22 @@ def partitioned_exchange_model(dist, torch, idx, dis, rank, world, merge):
     return oi.reshape(sl * world, k)[:nq], od.reshape(sl * world, k)[:nq]
 
 
+def _shard_offset(torch, base, rank, world, id_offset):
+    """Global id of this rank's first row.  Given explicitly, or derived from the shard sizes of all
+    ranks (one all-gather of a scalar; shards may be uneven)."""
+    if id_offset is not None:
+        return int(id_offset)
+    if world == 1:
+        return 0
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        raise ValueError("id_offset is required when torch.distributed is not initialised")
+    sizes = torch.zeros(world, dtype=torch.int64, device=base.device)
+    mine = torch.tensor([base.shape[0]], dtype=torch.int64, device=base.device)
+    dist.all_gather_into_tensor(sizes, mine)
+    return int(sizes[:rank].sum().item())
+
+
 class ShardedKnn:
     """Exact L2 k-NN over a database sharded by rows.  `base` is THIS rank's shard (a CUDA
     float32 tensor [rows][d]); `id_offset` the global id of its first row (mandatory for uneven
@@ -125,9 +141,7 @@ class ShardedKnn:
         assert base.is_cuda and base.dtype == torch.float32 and base.is_contiguous()
         assert exchange in ("library", "torch")
         self.base, self.k, self.rank, self.world = base, k, rank, world
-        if id_offset is None:
-            id_offset = rank * base.shape[0]
-        self.id_offset = int(id_offset)
+        self.id_offset = _shard_offset(torch, base, rank, world, id_offset)
         self.exchange = exchange
         _lib.require_gpu()
         self.comm = comm
@@ -218,7 +232,7 @@ class ShardedHamming:
         self.torch = torch
         assert base.is_cuda and base.dtype == torch.uint8 and base.is_contiguous()
         self.base, self.k, self.rank, self.world = base, k, rank, world
-        self.id_offset = int(rank * base.shape[0] if id_offset is None else id_offset)
+        self.id_offset = _shard_offset(torch, base, rank, world, id_offset)
         self.exchange = exchange
         _lib.require_gpu()
         self.comm = comm
