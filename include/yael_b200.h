@@ -244,6 +244,20 @@ int yb_crossmatch_hamming_count(const uint8_t *dbs, int n, int ht, int ncodes,
 int yb_crossmatch_hamming(const uint8_t *dbs, int n, int ht, int ncodes, int *idx,
                           uint16_t *hams, unsigned long long *count, yb_stream_t s);
 
+/* ---- further consumers of the path ---------------------------------- */
+/* hkm_quantize (yael/hkm.c:144-162): idx[i] = leaf of point i after nlevel exact k = 1 searches
+ * among the bf children of its current node (nn() semantics, lowest id on exact ties).  levels is a
+ * HOST array of nlevel DEVICE pointers, level l's table being [bf^(l+1)][d]; v, idx: device. */
+int yb_hkm_quantize(int nlevel, int bf, int d, const float *const *levels, long n, const float *v,
+                    int *idx, yb_stream_t s);
+/* GMM E-step (yael/gmm.c:211-367): p[n][k] = posteriors.  inv_sigma = (float)(1.0 / sigma) and
+ * mu_sigma = mu / sigma ([k][d]), mu2[k] = (float) sum_l mu^2 / sigma, logdetnr[k], lg[k] (log
+ * weights or zeros) are the O(k d) tables the reference prepares before its two sgemm calls;
+ * coeffs (may be NULL) receives log(sum) + max per point.  Device pointers. */
+int yb_gmm_posteriors(long n, int k, int d, const float *v, const float *inv_sigma,
+                      const float *mu_sigma, const float *mu2, const float *logdetnr, const float *lg,
+                      float *p, float *coeffs, yb_stream_t s);
+
 /* ---- sharded hot path: the exchange steps of SURVEY.md 8(e) inside the library ------- */
 /* One NCCL communicator per GPU (NCCL is resolved at run time: libnccl.so.2).  Two ways to get
  * one: (a) one PROCESS per GPU (torchrun): rank 0 calls yb_comm_unique_id, the caller broadcasts

@@ -66,6 +66,17 @@ def f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+class HkmT(C.Structure):
+    """hkm_t (yael/hkm.h:11-17)"""
+    _fields_ = [("nlevel", C.c_int), ("bf", C.c_int), ("k", C.c_int), ("d", C.c_int),
+                ("centroids", C.POINTER(_f))]
+
+
+class GmmT(C.Structure):
+    """gmm_t (yael/gmm.h:20-26)"""
+    _fields_ = [("d", C.c_int), ("k", C.c_int), ("w", _f), ("mu", _f), ("sigma", _f)]
+
+
 _oracle = None
 _ref = None
 
@@ -104,6 +115,8 @@ def oracle():
         L.orc_crossmatch_hamming_count.argtypes = [_u8, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
         L.orc_crossmatch_hamming_prealloc.argtypes = [_u8, C.c_long, C.c_int, C.c_int, _i, _u16]
         L.orc_crossmatch_hamming_prealloc.restype = C.c_size_t
+        L.orc_hkm_quantize.argtypes = [C.c_int] * 3 + [_f, C.c_int, _f, _i, C.c_int]
+        L.orc_gmm_compute_p.argtypes = [C.c_int] * 3 + [_f, _f, _f, _f, _f, C.c_int, C.c_int]
         _oracle = L
     return _oracle
 
@@ -140,6 +153,12 @@ def ref():
         L.ivec_new_random_perm_r.restype = C.POINTER(C.c_int)
         L.fvec_randn_r.argtypes = [_f, C.c_long, C.c_uint]
         L.count_cpu.restype = C.c_int
+        L.hkm_quantize.argtypes = [C.POINTER(HkmT), C.c_int, _f, _i]
+        L.hkm_learn.argtypes = [C.c_int] * 4 + [_f, C.c_int, C.c_int, C.c_int, C.POINTER(_i)]
+        L.hkm_learn.restype = C.POINTER(HkmT)
+        L.hkm_delete.argtypes = [C.POINTER(HkmT)]
+        L.gmm_compute_p.argtypes = [C.c_int, _f, C.POINTER(GmmT), _f, C.c_int]
+        L.gmm_compute_p_thread.argtypes = [C.c_int, _f, C.POINTER(GmmT), _f, C.c_int, C.c_int]
         _ref = L
     return _ref
 
@@ -378,3 +397,70 @@ def ref_vlad(cent, v, weights=None, subsets=None):
 
 def ref_bof(cent, v, ma=None, subsets=None):
     return _vlad_family(ref(), "", None, cent, v, subsets=subsets, ma=ma, bof=True)
+
+
+# ---- hierarchical k-means quantiser (yael/hkm.c:144-162) and GMM E-step (yael/gmm.c:305-367)
+def make_hkm(levels, bf):
+    """hkm_t over numpy tables: levels[l] is [bf^(l+1)][d]; returns (struct, keep-alive list)."""
+    levels = [f32(x) for x in levels]
+    d = levels[0].shape[1]
+    for l, x in enumerate(levels):
+        assert x.shape == (bf ** (l + 1), d)
+    ptrs = (_f * len(levels))(*[fp(x) for x in levels])
+    h = HkmT(len(levels), bf, bf ** len(levels), d, C.cast(ptrs, C.POINTER(_f)))
+    return h, (levels, ptrs)
+
+
+def ref_hkm_learn(v, nlevel, bf, niter=10):
+    """hkm_learn of the compiled reference (yael/hkm.c:35-118; kmeans seeds come from lrand48)."""
+    v = f32(v)
+    n, d = v.shape
+    out = _i()
+    h = ref().hkm_learn(n, d, nlevel, bf, fp(v), niter, 1, 0, C.byref(out))
+    levels = [np.ctypeslib.as_array(h.contents.centroids[l], shape=(bf ** (l + 1), d)).copy()
+              for l in range(nlevel)]
+    assign = np.ctypeslib.as_array(out, shape=(n,)).copy()
+    ref().hkm_delete(h)
+    return levels, assign
+
+
+def ref_hkm_quantize(levels, bf, v):
+    v = f32(v)
+    h, keep = make_hkm(levels, bf)
+    idx = np.empty(v.shape[0], np.int32)
+    ref().hkm_quantize(C.byref(h), v.shape[0], fp(v), ip(idx))
+    return idx
+
+
+def orc_hkm_quantize(levels, bf, v, dot_mode=DOT_F32_SEQ):
+    v = f32(v)
+    cat = np.ascontiguousarray(np.concatenate([f32(x).reshape(-1) for x in levels]), np.float32)
+    idx = np.empty(v.shape[0], np.int32)
+    oracle().orc_hkm_quantize(len(levels), bf, v.shape[1], fp(cat), v.shape[0], fp(v), ip(idx), dot_mode)
+    return idx
+
+
+def make_gmm(w, mu, sigma):
+    w, mu, sigma = f32(w), f32(mu), f32(sigma)
+    k, d = mu.shape
+    assert sigma.shape == (k, d) and w.shape == (k,)
+    return GmmT(d, k, fp(w), fp(mu), fp(sigma)), (w, mu, sigma)
+
+
+def ref_gmm_compute_p(w, mu, sigma, v, flags=1, nt=1):
+    v = f32(v)
+    g, keep = make_gmm(w, mu, sigma)
+    p = np.empty((v.shape[0], g.k), np.float32)
+    if nt > 1:
+        ref().gmm_compute_p_thread(v.shape[0], fp(v), C.byref(g), fp(p), flags, nt)
+    else:
+        ref().gmm_compute_p(v.shape[0], fp(v), C.byref(g), fp(p), flags)
+    return p
+
+
+def orc_gmm_compute_p(w, mu, sigma, v, flags=1, dot_mode=DOT_F32_SEQ):
+    v, w, mu, sigma = f32(v), f32(w), f32(mu), f32(sigma)
+    k, d = mu.shape
+    p = np.empty((v.shape[0], k), np.float32)
+    oracle().orc_gmm_compute_p(v.shape[0], d, k, fp(w), fp(mu), fp(sigma), fp(v), fp(p), flags, dot_mode)
+    return p

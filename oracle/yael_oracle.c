@@ -932,3 +932,96 @@ void orc_bof_compute_subsets(int k, int d, const float *centroids, int n, const 
   free(assign);
   free(dis);
 }
+
+/* ------------------------------------------------------------------ */
+/* hierarchical k-means quantiser (yael/hkm.c:144-162)                  */
+/* ------------------------------------------------------------------ */
+
+/* yael/hkm.c:144-162: every point walks the tree; at level l the bf children of its current node
+ * are searched with nn() (yael/nn.c:608-621 -> knn_full, k = 1: lowest id on exact ties) and
+ * vw = vw * bf + child.  centroids = the levels' tables concatenated: level l holds bf^(l+1) rows. */
+void orc_hkm_quantize(int nlevel, int bf, int d, const float *centroids, int n, const float *v,
+                      int *idx, int dot_mode) {
+  for (long i = 0; i < n; i++) {
+    int vw = 0;
+    const float *level = centroids;
+    long rows = bf;
+    for (int l = 0; l < nlevel; l++) {
+      int child;
+      float dis;
+      orc_knn_full(1, bf, d, 1, level + (size_t)vw * d * bf, v + (size_t)d * i, NULL, &child, &dis,
+                   dot_mode, 1);
+      vw = vw * bf + child;
+      level += (size_t)rows * d;
+      rows *= bf;
+    }
+    idx[i] = vw;
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* GMM E-step (yael/gmm.c:211-258 Mahalanobis, :262-300 softmax,        */
+/* :305-367 gmm_compute_p)                                             */
+/* ------------------------------------------------------------------ */
+
+#define ORC_GMM_FLAGS_W 1
+
+/* p[i*k + j] = posterior of mixture component j for point i.  The two sgemm calls of
+ * compute_mahalanobis_sqr (gmm.c:244,254: C += A'B, then C += -2 A'B) are restated with the
+ * selectable dot order; everything around them follows the source's types: double sums for
+ * mu^2/sigma rounded to float (gmm.c:221-226), float v^2 (gmm.c:235-236), (float)(1.0/sigma)
+ * (gmm.c:239-240), float mu/sigma (gmm.c:249-250), the log-domain combination in double
+ * (gmm.c:357), exp in double stored as float and a sequential float sum (gmm.c:279-293). */
+void orc_gmm_compute_p(int n, int d, int k, const float *w, const float *mu, const float *sigma,
+                       const float *v, float *p, int flags, int dot_mode) {
+  if (n == 0) return;
+  float *logdetnr = (float *)xmalloc(sizeof(float) * (size_t)k);
+  float *mu2 = (float *)xmalloc(sizeof(float) * (size_t)k);
+  float *lg = (float *)xmalloc(sizeof(float) * (size_t)k);
+  float *is = (float *)xmalloc(sizeof(float) * (size_t)k * d);
+  float *ms = (float *)xmalloc(sizeof(float) * (size_t)k * d);
+  float *v2 = (float *)xmalloc(sizeof(float) * (size_t)d);
+  for (long j = 0; j < k; j++) {
+    logdetnr[j] = -(long)d / 2.0 * log(2 * M_PI);
+    for (long i = 0; i < d; i++) logdetnr[j] -= 0.5 * log(sigma[j * d + i]);
+    double dt = 0;
+    for (long l = 0; l < d; l++) {
+      double m = mu[j * d + l];
+      dt += m * m / sigma[j * d + l];
+    }
+    mu2[j] = dt;
+    lg[j] = (flags & ORC_GMM_FLAGS_W) ? log(w[j]) : 0.f;
+  }
+  for (long i = 0; i < (long)k * d; i++) {
+    is[i] = 1.0 / sigma[i];
+    ms[i] = mu[i] / sigma[i];
+  }
+  const float norm_to_0 = 16.636;
+  for (long i = 0; i < n; i++) {
+    const float *vi = v + (size_t)i * d;
+    float *pi = p + (size_t)i * k;
+    for (int l = 0; l < d; l++) v2[l] = vi[l] * vi[l];
+    for (long j = 0; j < k; j++) {
+      float c = mu2[j];
+      c = c + orc_dot(is + j * d, v2, d, dot_mode);
+      c = c + (-2.0f) * orc_dot(ms + j * d, vi, d, dot_mode);
+      pi[j] = logdetnr[j] - 0.5 * c + lg[j];
+    }
+    float maxval = -1e30;
+    for (long l = 0; l < k; l++)
+      if (pi[l] > maxval) maxval = pi[l];
+    float s = 0.0;
+    for (long l = 0; l < k; l++) {
+      if (pi[l] >= maxval - norm_to_0) {
+        pi[l] = exp(pi[l] - maxval);
+        s += pi[l];
+      } else
+        pi[l] = 0;
+    }
+    if (s != 0) {
+      float inv = 1.0 / s;
+      for (long l = 0; l < k; l++) pi[l] *= inv;
+    }
+  }
+  free(logdetnr); free(mu2); free(lg); free(is); free(ms); free(v2);
+}

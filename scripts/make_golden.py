@@ -150,3 +150,23 @@ save("vlad_bof", centroids=vc, v=vv, weights=vw, subset_indexes=sidx, subset_end
      vlad=ob.ref_vlad(vc, vv), vlad_weighted=ob.ref_vlad(vc, vv, weights=vw),
      vlad_subsets=ob.ref_vlad(vc, vv, subsets=subs), bof=ob.ref_bof(vc, vv), bof_ma3=ob.ref_bof(vc, vv, ma=3),
      bof_subsets=ob.ref_bof(vc, vv, subsets=subs))
+
+# 12. further consumers: hkm_quantize (yael/hkm.c:144-162) over a tree learned
+#     by the reference's hkm_learn, and the GMM E-step gmm_compute_p (yael/gmm.c:305-367) with and
+#     without the mixture weights
+rh = np.random.RandomState(12)
+hv = rh.random_sample((4000, 16)).astype(np.float32)
+hlevels, hassign = ob.ref_hkm_learn(hv, 3, 5, niter=8)
+hq = rh.random_sample((1500, 16)).astype(np.float32)
+gk, gd = 32, 24
+gmu = rh.random_sample((gk, gd)).astype(np.float32)
+gsigma = (0.02 + 0.1 * rh.random_sample((gk, gd))).astype(np.float32)
+gw = rh.random_sample(gk).astype(np.float32)
+gw /= gw.sum()
+gv = rh.random_sample((600, gd)).astype(np.float32)
+save("hkm_gmm", hkm_level0=hlevels[0], hkm_level1=hlevels[1], hkm_level2=hlevels[2], hkm_learn_assign=hassign,
+     hkm_points=hv, hkm_query=hq, hkm_quantize_query=ob.ref_hkm_quantize(hlevels, 5, hq),
+     hkm_quantize_points=ob.ref_hkm_quantize(hlevels, 5, hv),
+     gmm_w=gw, gmm_mu=gmu, gmm_sigma=gsigma, gmm_v=gv,
+     gmm_p_w=ob.ref_gmm_compute_p(gw, gmu, gsigma, gv, 1), gmm_p_now=ob.ref_gmm_compute_p(gw, gmu, gsigma, gv, 0),
+     gmm_p_w_nt3=ob.ref_gmm_compute_p(gw, gmu, gsigma, gv, 1, nt=3))

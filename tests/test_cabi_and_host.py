@@ -187,3 +187,50 @@ def test_host_only_entry_points_hamming_and_recompute_exact_dists(ob):
         R.knn_recompute_exact_dists.restype = None
         rkp, rdis = run(R.knn_recompute_exact_dists)
         assert np.array_equal(kp, rkp) and np.array_equal(dis, rdis)
+
+
+def test_hkm_and_gmm_files_round_trip(tmp_path):
+    # hkm_write / hkm_read (yael/hkm.c:181-232) and gmm_write / gmm_read (yael/gmm.c:810-836): host
+    # code, no device needed; the byte layout is the reference's (checked against a hand-built file)
+    import yael_b200
+    from yael_b200 import _lib, ynumpy
+    L = yael_b200.lib()
+    r = np.random.RandomState(5)
+    bf, d = 3, 4
+    levels = [r.rand(bf ** (l + 1), d).astype(np.float32) for l in range(2)]
+    h, keep = ynumpy._hkm_struct(levels, bf)
+    path = str(tmp_path / "tree.hkm").encode()
+    L.hkm_write(path, C.byref(h))
+    raw = open(path, "rb").read()
+    want = np.array([2, bf, d], np.int32).tobytes()
+    for x in levels:
+        want += np.array([x.size], np.int32).tobytes() + x.tobytes()
+    assert raw == want
+    h2 = L.hkm_read(path)
+    assert (h2.contents.nlevel, h2.contents.bf, h2.contents.k, h2.contents.d) == (2, bf, bf * bf, d)
+    for l, x in enumerate(levels):
+        got = np.ctypeslib.as_array(h2.contents.centroids[l], shape=x.shape)
+        assert np.array_equal(got, x)
+    node = np.ctypeslib.as_array(L.hkm_get_centroids(h2, 1, 2), shape=(bf, d))
+    assert np.array_equal(node, levels[1][2 * bf:3 * bf])
+    L.hkm_delete(h2)
+
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    k = 5
+    w, mu, sg = r.rand(k).astype(np.float32), r.rand(k, d).astype(np.float32), r.rand(k, d).astype(np.float32)
+    fp_ = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    g = _lib.GmmT(d, k, fp_(w), fp_(mu), fp_(sg))
+    gpath = str(tmp_path / "mix.gmm").encode()
+    f = libc.fopen(gpath, b"w")
+    L.gmm_write(C.byref(g), f)
+    libc.fclose(f)
+    assert open(gpath, "rb").read() == np.array([d, k], np.int32).tobytes() + w.tobytes() + mu.tobytes() + sg.tobytes()
+    f = libc.fopen(gpath, b"r")
+    g2 = L.gmm_read(f)
+    libc.fclose(f)
+    assert (g2.contents.d, g2.contents.k) == (d, k)
+    assert np.array_equal(np.ctypeslib.as_array(g2.contents.sigma, shape=(k, d)), sg)
+    L.gmm_delete(g2)

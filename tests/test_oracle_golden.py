@@ -185,3 +185,24 @@ def test_vlad_bof_golden(ob):
     assert np.array_equal(ob.orc_bof(c, v, ma=3), g["bof_ma3"])
     assert np.array_equal(ob.orc_bof(c, v, subsets=subs), g["bof_subsets"])
     assert g["bof"].sum() == len(v) and g["bof_ma3"].sum() == 3 * len(v)
+
+
+def test_hkm_quantize_and_gmm_posteriors_golden(ob):
+    # yael/hkm.c:144-162 and yael/gmm.c:211-367, golden from the compiled reference
+    # (scripts/make_golden.py, fixture 12): leaves identical; posteriors identical with the
+    # sequential-FMA dot order and within 1e-4 with the float64 order (BLAS order is unspecified)
+    g = gold("hkm_gmm")
+    levels = [g["hkm_level%d" % l] for l in range(3)]
+    assert np.array_equal(ob.orc_hkm_quantize(levels, 5, g["hkm_query"]), g["hkm_quantize_query"])
+    assert np.array_equal(ob.orc_hkm_quantize(levels, 5, g["hkm_points"]), g["hkm_quantize_points"])
+    for flags, name in ((1, "gmm_p_w"), (0, "gmm_p_now")):
+        p = ob.orc_gmm_compute_p(g["gmm_w"], g["gmm_mu"], g["gmm_sigma"], g["gmm_v"], flags)
+        assert np.array_equal(p, g[name])
+        p64 = ob.orc_gmm_compute_p(g["gmm_w"], g["gmm_mu"], g["gmm_sigma"], g["gmm_v"], flags, ob.DOT_F64)
+        np.testing.assert_allclose(p64, g[name], atol=1e-4)
+        np.testing.assert_allclose(g[name].sum(1), 1.0, atol=1e-5)
+    assert np.array_equal(g["gmm_p_w"], g["gmm_p_w_nt3"])   # independent of the thread count
+    if ob.have_ref():
+        assert np.array_equal(ob.ref_hkm_quantize(levels, 5, g["hkm_query"]), g["hkm_quantize_query"])
+        assert np.array_equal(ob.ref_gmm_compute_p(g["gmm_w"], g["gmm_mu"], g["gmm_sigma"], g["gmm_v"], 1),
+                              g["gmm_p_w"])

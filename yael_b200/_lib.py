@@ -33,6 +33,18 @@ class YaelB200Error(RuntimeError):
     pass
 
 
+class HkmT(C.Structure):
+    """hkm_t (include/yael/hkm.h, reference yael/hkm.h:11-17)"""
+    _fields_ = [("nlevel", C.c_int), ("bf", C.c_int), ("k", C.c_int), ("d", C.c_int),
+                ("centroids", C.POINTER(C.POINTER(C.c_float)))]
+
+
+class GmmT(C.Structure):
+    """gmm_t (include/yael/gmm.h, reference yael/gmm.h:20-26)"""
+    _fields_ = [("d", C.c_int), ("k", C.c_int), ("w", C.POINTER(C.c_float)),
+                ("mu", C.POINTER(C.c_float)), ("sigma", C.POINTER(C.c_float))]
+
+
 # (name, restype, argtypes) of the drop-in layer: exactly the reference's prototypes
 DROPIN = {
     # include/yael/nn.h  (reference yael/nn.h:41-214)
@@ -87,6 +99,19 @@ DROPIN = {
     "bof_compute": (None, [C.c_int, C.c_int, _f, C.c_int, _f, _i]),
     "bof_compute_ma": (None, [C.c_int, C.c_int, _f, C.c_int, _f, _i, C.c_int, C.c_float, C.c_int]),
     "bof_compute_subsets": (None, [C.c_int, C.c_int, _f, C.c_int, _f, C.c_int, _i, _i, _f]),
+    # include/yael/hkm.h  (reference yael/hkm.h:21-40)
+    "hkm_learn": (C.POINTER(HkmT), [C.c_int] * 4 + [_f, C.c_int, C.c_int, C.c_int, C.POINTER(_i)]),
+    "hkm_delete": (None, [C.POINTER(HkmT)]),
+    "hkm_quantize": (None, [C.POINTER(HkmT), C.c_int, _f, _i]),
+    "hkm_write": (None, [C.c_char_p, C.POINTER(HkmT)]),
+    "hkm_read": (C.POINTER(HkmT), [C.c_char_p]),
+    "hkm_get_centroids": (_f, [C.POINTER(HkmT), C.c_int, C.c_int]),
+    # include/yael/gmm.h  (reference yael/gmm.h:63-66,121-131)
+    "gmm_compute_p": (None, [C.c_int, _f, C.POINTER(GmmT), _f, C.c_int]),
+    "gmm_compute_p_thread": (None, [C.c_int, _f, C.POINTER(GmmT), _f, C.c_int, C.c_int]),
+    "gmm_delete": (None, [C.POINTER(GmmT)]),
+    "gmm_write": (None, [C.POINTER(GmmT), _vp]),
+    "gmm_read": (C.POINTER(GmmT), [_vp]),
     # include/yael/binheap.h  (reference yael/binheap.h:31-87)
     "fbinheap_new": (_vp, [C.c_int]),
     "fbinheap_sizeof": (C.c_size_t, [C.c_int]),
@@ -174,6 +199,8 @@ DEVICE = {
     "yb_debug_hamming_tc_packed": (C.c_int, [C.c_int] * 4 + [_vp, _vp, _vp, _vp]),
     "yb_vlad_accumulate": (C.c_int, [C.c_int, C.c_int, _vp, C.c_long, _vp, _vp, _vp, _vp, _vp, _vp]),
     "yb_bof_accumulate": (C.c_int, [C.c_int, C.c_long, _vp, _vp, C.c_long, _vp, _vp, _vp]),
+    "yb_hkm_quantize": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_vp), C.c_long, _vp, _vp, _vp]),
+    "yb_gmm_posteriors": (C.c_int, [C.c_long, C.c_int, C.c_int] + [_vp] * 9),
     "yb_match_hamming_count": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "yb_match_hamming_thres": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "yb_crossmatch_hamming_count": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),

@@ -2273,6 +2273,61 @@ extern "C" int yb_knn_reorder_shortlist(int nq, int nb, int d, int k, const floa
   return 0;
 }
 
+// ------------------------------------------------------------------ hkm_quantize (yael/hkm.c:144-162)
+// One level of the tree walk: the bf children of every point's current node are its candidates
+// (ids in the level's table), k_rerank_k1 scores them with the reference's arithmetic and takes the
+// (distance, id) minimum -- nn() with k = 1 (yael/nn.c:608-621, 383-446).
+__global__ void k_hkm_children(const int *__restrict__ vw, long n, int bf, int *__restrict__ cand) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * bf) return;
+  const int node = vw[e / bf];
+  cand[e] = node >= 0 ? node * bf + (int)(e % bf) : -1;
+}
+
+// a point whose children all have NaN distances gets child -1, as in the reference (nn_single_full
+// starts from (-1, 1e30): vw * bf + (-1))
+__global__ void k_hkm_step(const int *__restrict__ vw, long n, int bf, int *__restrict__ next) {
+  const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  if (next[q] < 0) next[q] = vw[q] >= 0 ? vw[q] * bf - 1 : -1;
+}
+
+// idx[i] = leaf of point i.  levels[l]: DEVICE pointer to level l's [bf^(l+1)][d] table (the array of
+// pointers itself is host memory); v, idx: device.
+extern "C" int yb_hkm_quantize(int nlevel, int bf, int d, const float *const *levels, long n,
+                               const float *v, int *idx, yb_stream_t s) {
+  if (n <= 0) return 0;
+  if (nlevel <= 0 || bf <= 0 || d <= 0) return fail(3, "yb_hkm_quantize: nlevel=%d bf=%d d=%d", nlevel, bf, d);
+  if (n > 0x7fffffffL / (bf > 4 ? bf : 4)) return fail(3, "yb_hkm_quantize: n = %ld x bf = %d is too large", n, bf);
+  Guard g;
+  cudaStream_t st = stream_of(s);
+  size_t need = Carver::need(sizeof(int) * (size_t)n * bf) + 3 * Carver::need(sizeof(int) * (size_t)n) +
+                Carver::need(sizeof(float) * (size_t)n) + Carver::need(sizeof(double) * (size_t)n);
+  ScratchScope ws(need, st);
+  Carver c(ws.p);
+  int *cand = c.take<int>((size_t)n * bf);
+  int *cur = c.take<int>(n);
+  int *next = c.take<int>(n);
+  int *flags = c.take<int>(n);
+  float *dis = c.take<float>(n);
+  double *qnorm = c.take<double>(n);
+  YB_CUDA(cudaMemsetAsync(cur, 0, sizeof(int) * (size_t)n, st));
+  int rc;
+  if ((rc = row_norms_seq(v, n, d, d, nullptr, qnorm, st))) return rc;
+  for (int l = 0; l < nlevel; l++) {
+    const long tot = n * bf;
+    k_hkm_children<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cur, n, bf, cand);
+    YB_LAUNCH_CHECK();
+    k_rerank_k1<<<(unsigned)((n + 3) / 4), 128, 0, st>>>((int)n, d, bf, 0, levels[l], v, cand, nullptr,
+                                                         l + 1 == nlevel ? idx : next, dis, 0, flags, qnorm);
+    YB_LAUNCH_CHECK();
+    k_hkm_step<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cur, n, bf, l + 1 == nlevel ? idx : next);
+    YB_LAUNCH_CHECK();
+    int *t = cur; cur = next; next = t;
+  }
+  return 0;
+}
+
 extern "C" int yb_gather_rows(const float *src, const int *rows, int n, int d, float *dst,
                                yb_stream_t s) {
   if (n <= 0 || d <= 0) return 0;

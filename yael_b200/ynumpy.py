@@ -278,3 +278,64 @@ def bof(centroids, v, ma=None, subsets=None):
     else:
         lib().bof_compute(k, d, _fp(centroids), n, _fp(v), _ip(desc))
     return desc
+
+
+# ---- hierarchical k-means quantiser (include/yael/hkm.h, yael/hkm.c)
+def _hkm_struct(levels, bf):
+    levels = [np.ascontiguousarray(x, np.float32) for x in levels]
+    d = levels[0].shape[1]
+    for l, x in enumerate(levels):
+        if x.shape != (bf ** (l + 1), d):
+            raise ValueError("level %d: expected a %d x %d table, got %s" % (l, bf ** (l + 1), d, x.shape))
+    ptrs = (_f * len(levels))(*[_fp(x) for x in levels])
+    h = _lib.HkmT(len(levels), bf, bf ** len(levels), d, C.cast(ptrs, C.POINTER(_f)))
+    return h, (levels, ptrs)
+
+
+def hkm_learn(v, nlevel, bf, niter=20, nt=1, verbose=False):
+    """hkm_learn (yael/hkm.c:35-118): returns (levels, assign): levels[l] is the [bf^(l+1)][d]
+    table of level l, assign the leaf of every learning point."""
+    _check_row_float32(v)
+    _lib.require_gpu()
+    n, d = v.shape
+    out = _i()
+    h = lib().hkm_learn(n, d, nlevel, bf, _fp(v), niter, nt, int(verbose), C.byref(out))
+    levels = [np.ctypeslib.as_array(h.contents.centroids[l], shape=(bf ** (l + 1), d)).copy()
+              for l in range(nlevel)]
+    assign = np.ctypeslib.as_array(out, shape=(n,)).copy()
+    lib().hkm_delete(h)
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    libc.free(C.cast(out, C.c_void_p))  # malloc'd by the library (hkm.c:112-115), freed by the caller
+    return levels, assign
+
+
+def hkm_quantize(levels, bf, v):
+    """hkm_quantize (yael/hkm.c:144-162): the leaf of every row of v."""
+    _check_row_float32(v)
+    _lib.require_gpu()
+    h, keep = _hkm_struct(levels, bf)
+    if v.shape[1] != h.d:
+        raise ValueError("points and tree have different dimensions")
+    idx = np.empty(v.shape[0], np.int32)
+    lib().hkm_quantize(C.byref(h), v.shape[0], _fp(v), _ip(idx))
+    return idx
+
+
+# ---- GMM E-step (include/yael/gmm.h, yael/gmm.c:305-367); gmm_npy = (w, mu, sigma) as in the
+# ---- reference's ynumpy (yael/ynumpy.py:268-300)
+GMM_FLAGS_W = 1
+
+
+def gmm_compute_p(gmm_npy, v, flags=GMM_FLAGS_W):
+    """gmm_compute_p: p[n][k], the posterior of every mixture component for every row of v."""
+    w, mu, sigma = [np.ascontiguousarray(x, np.float32) for x in gmm_npy]
+    _check_row_float32(v)
+    _lib.require_gpu()
+    k, d = mu.shape
+    if sigma.shape != (k, d) or w.shape != (k,) or v.shape[1] != d:
+        raise ValueError("inconsistent mixture / point shapes")
+    g = _lib.GmmT(d, k, _fp(w), _fp(mu), _fp(sigma))
+    p = np.empty((v.shape[0], k), np.float32)
+    lib().gmm_compute_p(v.shape[0], _fp(v), C.byref(g), _fp(p), flags)
+    return p
