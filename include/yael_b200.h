@@ -229,6 +229,9 @@ int yb_nn_hamming_merge(int nq, int k, int G, const int *assign_in, const uint16
 /* micro-benchmark: measured 64-bit xor+popcount pair rate of the whole GPU (the ceiling the
  * Hamming scan is reported against) */
 double yb_debug_popc_pairs_per_s(yb_stream_t s);
+/* bring-up: GB/s written into out[nb][ld] (queries fastest, the layout of compute_cross_distances)
+ * with the store pattern `mode` (yb_distance.cu: 0 = 4 bytes per lane, 1 / 2 = 16 bytes per lane) */
+double yb_debug_store_pattern_gbs(float *out, long ld, int nq, int nb, int mode, yb_stream_t s);
 /* match_hamming_count / match_hamming_thres_prealloc (yael/hamming.c:283-300, 563-700):
  * pairs with distance <= ht, emitted query-major / base-ascending.  count is a device
  * size_t; idx receives (qid, bid) interleaved. */

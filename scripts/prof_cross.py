@@ -9,7 +9,9 @@ import torch
 import yael_b200
 
 L = yael_b200.lib()
-na, nb, d = 10000, 100000, 128
+na = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
+nb = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
+d = int(sys.argv[3]) if len(sys.argv) > 3 else 128
 torch.manual_seed(4242)
 a = torch.rand((na, d), device="cuda")
 b = torch.rand((nb, d), device="cuda")
@@ -26,3 +28,13 @@ for engine in (1, 0):
         assert rc == 0, L.yb_last_error()
         print("engine %d (used %d) rep %d: %.3f ms" % (engine, L.yb_last_cross_engine(), rep, e0.elapsed_time(e1)))
 L.yb_set_cross_engine(-1)
+if int(os.environ.get("YAEL_B200_TF32_DEBUG", "0")) & 512:
+    import numpy as np
+    ck = np.zeros((148, 16), np.int64)
+    L.yb_debug_tf32_clocks(ck.ctypes.data_as(C.c_void_p), 148)
+    print("clock attribution (per CTA totals, mean over CTAs with data):")
+    names = ["issuer: wait accumulator", "issuer: wait operands", "issuer: wait extras", "issuer: total",
+             "epilogue: wait accumulator", "epilogue: drain", "epilogue: hand back", "epilogue: total", "tiles"]
+    for i, nme in enumerate(names):
+        sel = ck[:, i] > 0
+        print("  %-28s %12.0f  (%d CTAs)" % (nme, ck[sel, i].mean() if sel.any() else 0.0, sel.sum()))

@@ -199,6 +199,7 @@ DEVICE = {
     "yb_debug_hamming_tc_packed": (C.c_int, [C.c_int] * 4 + [_vp, _vp, _vp, _vp]),
     "yb_vlad_accumulate": (C.c_int, [C.c_int, C.c_int, _vp, C.c_long, _vp, _vp, _vp, _vp, _vp, _vp]),
     "yb_bof_accumulate": (C.c_int, [C.c_int, C.c_long, _vp, _vp, C.c_long, _vp, _vp, _vp]),
+    "yb_debug_store_pattern_gbs": (C.c_double, [_vp, C.c_long, C.c_int, C.c_int, C.c_int, _vp]),
     "yb_hkm_quantize": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_vp), C.c_long, _vp, _vp, _vp]),
     "yb_gmm_posteriors": (C.c_int, [C.c_long, C.c_int, C.c_int] + [_vp] * 9),
     "yb_match_hamming_count": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),

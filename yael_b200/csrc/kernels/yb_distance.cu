@@ -368,3 +368,68 @@ extern "C" int yb_cross_distances_alt(int type, int d, int na, int nb, const flo
   }
   return 0;
 }
+
+// ------------------------------------------------------------------ bring-up: store patterns
+// The output of compute_cross_distances is dist2[row * ld + query] (yael/nn.c:100-129): a CTA that
+// owns 128 queries writes 512 contiguous bytes per database row, rows ld floats apart.  This
+// micro-benchmark writes a whole [nb][ld] matrix with the access patterns an epilogue can use,
+// work items in the tensor kernel's order (all query tiles of one 256-row tile run concurrently):
+//   mode 0  lane = query, one 4-byte store per row: 128 bytes per warp instruction (the TMEM-lane
+//           layout of the accumulators written as they come)
+//   mode 1  lane = 4 queries, one 16-byte store per row: a warp instruction covers the CTA's 512
+//           bytes of a row (what a tile staged through shared memory can do)
+//   mode 2  as 1, two rows per instruction half-warp each (256 bytes per row piece)
+namespace yb {
+__global__ void __launch_bounds__(256)
+k_dbg_store_pattern(float *__restrict__ out, long ld, int nq, int nb, int mode) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_q = (nq + 127) / 128, tiles_b = (nb + 255) / 256;
+  for (long item = blockIdx.x; item < (long)tiles_q * tiles_b; item += gridDim.x) {
+    const int qt = (int)(item % tiles_q), jt = (int)(item / tiles_q);
+    if (mode == 0) {
+      const int q = qt * 128 + (warp & 3) * 32 + lane;
+      const long r0 = (long)jt * 256 + (warp >> 2) * 128;
+      if (q < nq)
+#pragma unroll 8
+        for (int c = 0; c < 128; c++)
+          if (r0 + c < nb) out[(r0 + c) * ld + q] = (float)c;
+    } else if (mode == 1) {
+      const int q = qt * 128 + lane * 4;
+      const long r0 = (long)jt * 256 + warp * 32;
+      if (q + 3 < nq)
+#pragma unroll 8
+        for (int c = 0; c < 32; c++)
+          if (r0 + c < nb)
+            *reinterpret_cast<float4 *>(out + (r0 + c) * ld + q) = make_float4((float)c, 1.f, 2.f, 3.f);
+    } else {
+      const int q = qt * 128 + (lane & 15) * 4 + (warp & 1) * 64;
+      const long r0 = (long)jt * 256 + (warp >> 1) * 64 + (lane >> 4);
+      if (q + 3 < nq)
+#pragma unroll 8
+        for (int c = 0; c < 64; c += 2)
+          if (r0 + c < nb)
+            *reinterpret_cast<float4 *>(out + (r0 + c) * ld + q) = make_float4((float)c, 1.f, 2.f, 3.f);
+    }
+  }
+}
+}  // namespace yb
+
+extern "C" double yb_debug_store_pattern_gbs(float *out, long ld, int nq, int nb, int mode, yb_stream_t s) {
+  Guard g;
+  cudaStream_t st = stream_of(s);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  yb::k_dbg_store_pattern<<<sm_count(), 256, 0, st>>>(out, ld, nq, nb, mode);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < 3; i++) yb::k_dbg_store_pattern<<<sm_count(), 256, 0, st>>>(out, ld, nq, nb, mode);
+  cudaEventRecord(e1, st);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  count_launch(4);
+  if (ms <= 0.f) return 0.0;
+  return 3.0 * 4.0 * (double)nq * nb / (ms * 1e-3) / 1e9;
+}

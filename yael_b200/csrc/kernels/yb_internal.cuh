@@ -31,6 +31,7 @@ struct Tf32Plan {
   int ctas;        // persistent grid size
   int pair;        // CTAs launched as clusters of 2 sharing the database stream
   int stream;      // query chunks travel through the ring with the database chunks (any d; 2-SM kernel)
+  int nka;         // resident query tile: chunk slots (4; 5 .. 7 = the 2-SM kernel's wide layout; 0: streamed)
   size_t ws_bytes; // workspace for buffers + shortlists
   int kind;        // operand kind: 0 = FP32 rows read as TF32 (kind::tf32); 1 = E4M3 bytes
                    // (kind::f8f6f4; `base` / `query` point to [rows][4*d] BYTE matrices -- the Hamming

@@ -419,6 +419,10 @@ struct Tf32Params {
   const float *acc_scale;  // device scalar: score = acc * (*acc_scale) + |b|^2 (NULL = -2: operands
                            // unscaled); FP16 operands are scaled by 2^sigma, *acc_scale = -2^(1-2 sigma)
   int debug;           // bring-up switches (YAEL_B200_TF32_DEBUG): 1 skip epilogue math, 2 skip MMAs
+  int nka;             // 2-SM kernel, resident query tile: chunk slots it occupies (MAX_NKC .. MAX_NKC_WIDE)
+  int stages2;         // ... and the database ring stages that fit behind it (STAGES2 .. 5)
+  int cross_tma;       // EPI_CROSS: tiles leave through shared memory and TMA stores ...
+  uint32_t cross_stage0, cross_stage1;  // ... staged in these rings (byte offsets, one per column half)
 };
 
 // ------------------------------------------------------------------ warp-cooperative compaction
@@ -902,6 +906,7 @@ struct EpiCtx {
   uint32_t t_empty_addr0, t_empty_addr1;  // where to signal "accumulator buffer drained" (local or leader CTA)
   int t_empty_remote;        // the address is a shared::cluster address of the peer CTA
   int n_full0, n_empty0, t_full0;  // barrier indices (the two kernels have different ring depths)
+  const CUtensorMap *map_out;      // EPI_CROSS with staged TMA stores: the [nb][ld] output matrix
 };
 
 // arrive on a barrier of ANOTHER CTA of the cluster (shared::cluster address from mapa).  Default
@@ -912,6 +917,27 @@ struct EpiCtx {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+
+// TMA store of a staged tile (shared -> global through the output's tensor map: rows and queries
+// beyond the matrix are clipped by the hardware), bulk-group bookkeeping, the generic -> async proxy
+// fence that makes the threads' shared-memory writes visible to it, and a named barrier for the
+// four warps that share a staging buffer.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// EPI_CROSS staging: per column half a ring of three [8 rows][128 queries] float buffers.  Half 0
+// uses the |b|^2 ring + histogram area (12 KB, idle in this mode), half 1 sits behind the barrier
+// block (CROSS_STAGE1_OFF, defined with Smem2): the operand area keeps its full ring.
+constexpr int CROSS_STAGE_BYTES = 8 * TM * 4;
 
 // MODE selects what the epilogue does with a tile (one kernel instantiation per mode: the hot
 // loop of each stays compact and contiguous in the instruction cache, and carries no per-tile
@@ -943,6 +969,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
     const float inv_asc = 1.0f / asc;  // exact: asc is a power of two
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * HALF_N;
     uint32_t tcount = 0;
+    uint32_t cross_buf = 0;  // EPI_CROSS: position in the staging ring
     const bool clk_on = (P.debug & 512) && warp == 0;
     long long ck_wait = 0, ck_work = 0, ck_back = 0, ck_t0 = clk_on ? clock64() : 0, ck_a = 0, ck_b = 0;
     for (int item = first_item; item < P.items; item += item_step) {
@@ -1074,10 +1101,68 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
               }
             }
           }
+        } else if (MODE == EPI_CROSS && P.cross_tma) {
+          // compute_cross_distances (yael/nn.c:100-129): dist2[query + ld * row].  The tile leaves
+          // through shared memory: the four warps of a column half (128 queries) stage 32 database
+          // rows at a time as [32][128] floats -- thread = query, so a warp writes 128 contiguous
+          // bytes per row, no bank conflicts -- and one elected thread hands the 16 KB to a TMA
+          // store: 512 contiguous bytes per output row and no LSU store instructions.  (Storing
+          // straight from the TMEM-lane layout is 128 bytes per warp instruction, 1024 instructions
+          // per tile: measured 4.2 TB/s for that pattern alone against 5.4-6.0 TB/s for 512-byte
+          // pieces, and the tile's stores took 10.9 k of its 12.1 k cycles.)
+          const uint32_t ta = lane_addr + buf * TN;
+          const int row0 = jt * TN + half * HALF_N;
+          const uint32_t stg_off = half ? P.cross_stage1 : P.cross_stage0;
+          const bool el = quarter == 0 && lane == 0;
+          uint32_t va[32], vb[32];
+          // 8 database rows per step through a ring of three 4 KB buffers, ONE barrier per step: at
+          // step j the elected thread waits until the stores up to j-2 have read their buffers
+          // before it joins the barrier, so whoever passes it may write buffer (j+1) % 3 next
+          auto stage_and_store = [&](const uint32_t (&v)[32], int g) {
+#pragma unroll
+            for (int s8 = 0; s8 < 4; s8++) {
+              float *stg = (float *)(smem + stg_off + cross_buf * CROSS_STAGE_BYTES);
+#pragma unroll
+              for (int c = 0; c < 8; c++) stg[c * TM + t] = __fmul_rn(asc, __uint_as_float(v[s8 * 8 + c]));
+              fence_proxy_async_smem();
+              if (el) bulk_wait_read1();
+              named_bar_sync(1 + half, 128);
+              if (el && !(P.debug & 1)) {
+                tma_store_2d(E.map_out, sbase + stg_off + cross_buf * CROSS_STAGE_BYTES, qt * TM,
+                             row0 + g * 32 + s8 * 8);
+                bulk_commit();
+              }
+              cross_buf = cross_buf == 2 ? 0 : cross_buf + 1;
+            }
+          };
+          tc_ld32(ta, va);
+#pragma unroll 1
+          for (int g = 0; g < HALF_N / 32; g += 2) {
+            tc_wait_ld();
+            tc_ld32(ta + (g + 1) * 32, vb);
+            stage_and_store(va, g);
+            tc_wait_ld();
+            if (g + 2 < HALF_N / 32) {
+              tc_ld32(ta + (g + 2) * 32, va);
+            } else {  // the accumulator is in registers / on its way out: hand the buffer back
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                const uint32_t te = buf ? E.t_empty_addr1 : E.t_empty_addr0;
+                if (E.t_empty_remote)
+                  mbar_arrive_cluster(te);
+                else
+                  mbar_arrive(te);
+              }
+              handed_back = true;
+            }
+            stage_and_store(vb, g + 1);
+          }
         } else if (MODE == EPI_CROSS) {
-          // compute_cross_distances (yael/nn.c:100-129): dist2[query + ld * row], i.e. the 32 lanes
-          // of a warp (32 consecutive queries) write 128 contiguous bytes per database row.  The
-          // operands carry both norms (cross_l2_tensor, yb_knn.cu), so the value is asc * acc.
+          // the same without staging (output pitch or address not 16-byte aligned, streamed query
+          // chunks): the 32 lanes of a warp (32 consecutive queries) write 128 contiguous bytes per
+          // database row.  The operands carry both norms (cross_l2_tensor, yb_knn.cu), so the value
+          // is asc * acc.
           const uint32_t ta = lane_addr + buf * TN;
           const long col0 = (long)jt * TN + half * HALF_N;
           float *ocol = P.dump + (size_t)col0 * P.dump_ld + (valid ? q : 0);
@@ -1087,7 +1172,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           for (int g = 0; g < HALF_N / 32; g += 2) {
             tc_wait_ld();
             tc_ld32(ta + (g + 1) * 32, vb);
-            if (valid) {
+            if (valid && !(P.debug & 1)) {
 #pragma unroll
               for (int c = 0; c < 32; c++)
                 if (col0 + g * 32 + c < P.nb)
@@ -1095,7 +1180,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
             }
             tc_wait_ld();
             if (g + 2 < HALF_N / 32) tc_ld32(ta + (g + 2) * 32, va);
-            if (valid) {
+            if (valid && !(P.debug & 1)) {
 #pragma unroll
               for (int c = 0; c < 32; c++)
                 if (col0 + (g + 1) * 32 + c < P.nb)
@@ -1458,6 +1543,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
         }
       }
     }
+    if (MODE == EPI_CROSS && P.cross_tma) bulk_wait0();  // staged tiles have left before the CTA does
     if (clk_on && lane == 0 && blockIdx.x < 160) {
       g_tf32_clk[blockIdx.x][4] = ck_wait;
       g_tf32_clk[blockIdx.x][5] = ck_work;
@@ -1533,6 +1619,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
   ectx.t_empty_addr0 = bar(Smem::t_empty + 0); ectx.t_empty_addr1 = bar(Smem::t_empty + 1);
   ectx.t_empty_remote = 0;
   ectx.n_full0 = Smem::n_full; ectx.n_empty0 = Smem::n_empty; ectx.t_full0 = Smem::t_full;
+  ectx.map_out = nullptr;
 
   if (warp == EPI_WARPS) {
     // ======================================================================== TMA producer
@@ -1739,6 +1826,12 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 //     accumulators in both CTAs
 //   * the peer's epilogue warps signal "accumulator drained" on the leader's barrier
 constexpr int STAGES2 = 8;
+// Wide resident layout: a query tile of up to MAX_NKC_WIDE chunks stays in shared memory and the
+// database ring shrinks to what is left of the same 192 KB (12 - nka stages of 16 KB).  K = 3 d of
+// the tensor-core compute_cross_distances at d = 128 is 7 chunks: resident, the queries are read
+// once per work item instead of once per database tile (half the L2 -> SM operand traffic of the
+// streamed variant, which is what bounded that kernel together with its 4 GB of output).
+constexpr int MAX_NKC_WIDE = 7;
 constexpr int B2_CHUNK_BYTES = (TN / 2) * KC * 4;  // 16 KB: this CTA's half of a 128-byte-wide chunk
 constexpr int XB2_BYTES = (TN / 2) * 32;           // this CTA's half of the extras chunk
 struct Smem2 {
@@ -1759,6 +1852,11 @@ static_assert(Smem2::bn_off == Smem::bn_off && Smem2::hist_off == Smem::hist_off
               "run_epilogue() addresses |b|^2 tiles and histograms through Smem::");
 static_assert(Smem2::bar_off == Smem::bar_off, "barrier block must sit at the same offset");
 constexpr int TF32_SMEM2_BYTES = Smem2::total;
+constexpr int CROSS_STAGE0_OFF = Smem2::bn_off;
+constexpr int CROSS_STAGE1_OFF = (Smem2::total + 1023) & ~1023;
+constexpr int TF32_SMEM2_CROSS_BYTES = CROSS_STAGE1_OFF + 3 * CROSS_STAGE_BYTES;
+static_assert(3 * CROSS_STAGE_BYTES <= Smem2::bar_off - Smem2::bn_off, "half 0 staging overlays |b|^2 + histograms");
+static_assert(TF32_SMEM2_CROSS_BYTES <= 232448, "shared memory per CTA");
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
 
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *map,
@@ -1828,7 +1926,7 @@ template <int MODE, int LDW, int KIND = OP_F16N, bool STREAM = false>
 __global__ void __launch_bounds__(TF32_THREADS, 1)
 k_knn_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_bh,
           const __grid_constant__ CUtensorMap map_qx, const __grid_constant__ CUtensorMap map_bxh,
-          const Tf32Params P) {
+          const __grid_constant__ CUtensorMap map_out, const Tf32Params P) {
   static_assert(KIND == OP_F16N || KIND == OP_F8C || (KIND == OP_F8 && (MODE == EPI_HAMP || MODE == EPI_HAMG)),
                 "the 2-SM kernel carries no |b|^2 ring");
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -1877,6 +1975,8 @@ k_knn_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
   const int tq_div = P.tiles_q2;
   const int nkd = xk >= 0 ? xk : P.nkc;        // 128-byte data chunks per row
   const int nring = xring ? xk : P.nkc;        // chunks of a tile that travel through the B ring
+  const uint32_t b_off = (uint32_t)P.nka * A_CHUNK_BYTES;   // resident layout: the ring starts behind the query tile
+  const uint32_t nst = (uint32_t)P.stages2;                 // ... and has this many stages (8 for nka = 4)
 
   if (warp == EPI_WARPS) {
     // ======================================================================== TMA producer
@@ -1928,16 +2028,16 @@ k_knn_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
                             bar(Smem2::x_full + xs) & PEER_BIT_MASK, P.xcol, row0);
           }
           for (int kc = 0; kc < nring; kc++, ccount++) {
-            const uint32_t st = ccount % STAGES2;
-            mbar_wait(bar(Smem2::b_empty + st), ((ccount / STAGES2) & 1) ^ 1);
+            const uint32_t st = ccount % nst;
+            mbar_wait(bar(Smem2::b_empty + st), ((ccount / nst) & 1) ^ 1);
             if (kc == xk) {  // the 16 extra K elements as a 32-byte-wide box in a ring stage
               if (leader) mbar_expect_tx(bar(Smem2::b_full + st), 2 * XB2_BYTES);
-              tma_load_2d_2sm(sbase + Smem2::b_off + st * B2_CHUNK_BYTES, &map_bxh,
+              tma_load_2d_2sm(sbase + b_off + st * B2_CHUNK_BYTES, &map_bxh,
                               bar(Smem2::b_full + st) & PEER_BIT_MASK, P.xcol, row0);
               continue;
             }
             if (leader) mbar_expect_tx(bar(Smem2::b_full + st), 2 * B2_CHUNK_BYTES);
-            tma_load_2d_2sm(sbase + Smem2::b_off + st * B2_CHUNK_BYTES, &map_bh,
+            tma_load_2d_2sm(sbase + b_off + st * B2_CHUNK_BYTES, &map_bh,
                             bar(Smem2::b_full + st) & PEER_BIT_MASK, kc * KCE, row0);
           }
         }
@@ -1985,16 +2085,16 @@ k_knn_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
             continue;
           }
           for (int kc = 0; kc < nring; kc++, ccount++) {
-            const uint32_t st = ccount % STAGES2;
+            const uint32_t st = ccount % nst;
             if (clk_on) ck_a = clock64();
-            mbar_wait(bar(Smem2::b_full + st), (ccount / STAGES2) & 1);
+            mbar_wait(bar(Smem2::b_full + st), (ccount / nst) & 1);
             tc_fence_after();
             if (clk_on) ck_ops += clock64() - ck_a;
             const uint64_t adesc = smem_desc_sw128(sbase + Smem2::a_off + kc * A_CHUNK_BYTES);
-            const uint64_t bdesc = smem_desc_sw128(sbase + Smem2::b_off + st * B2_CHUNK_BYTES);
+            const uint64_t bdesc = smem_desc_sw128(sbase + b_off + st * B2_CHUNK_BYTES);
             if (kc == xk) {
               tc_mma_2sm_elect<KIND>(d_tmem, smem_desc_sw32(sbase + Smem2::a_off + kc * A_CHUNK_BYTES),
-                                     smem_desc_sw32(sbase + Smem2::b_off + st * B2_CHUNK_BYTES), 1);
+                                     smem_desc_sw32(sbase + b_off + st * B2_CHUNK_BYTES), 1);
             } else if (kc != last_data || P.last_k8 == 4) {
               tc_mma_2sm_elect<KIND>(d_tmem, adesc, bdesc, kc != 0);
               tc_mma_2sm_elect<KIND>(d_tmem, adesc + 2, bdesc + 2, 1);
@@ -2042,6 +2142,7 @@ k_knn_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
     ectx.t_empty_addr1 = leader ? bar(Smem2::t_empty + 1) : a1;
     ectx.t_empty_remote = leader ? 0 : 1;   // the leader's own warps arrive locally
     ectx.n_full0 = Smem2::n_full; ectx.n_empty0 = Smem2::n_empty; ectx.t_full0 = Smem2::t_full;
+    ectx.map_out = &map_out;
     run_epilogue<MODE, KIND, LDW>(P, ectx);
   } else {
     regs_aux();
@@ -2145,6 +2246,22 @@ static int make_map_f16_extras(CUtensorMap *m, const void *ptr, long rows, int d
   return 0;
 }
 
+// the output of compute_cross_distances: dist2[row * ld + query], box = 128 queries x 8 rows of
+// floats, no swizzle (the staging tile is plain row-major); stores beyond na / nb are clipped
+static int make_map_out(CUtensorMap *m, float *ptr, long na, long nb, long ld) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return fail(6, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {(cuuint64_t)na, (cuuint64_t)nb};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TM, 8u};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(6, "cuTensorMapEncodeTiled (output) failed with code %d", (int)r);
+  return 0;
+}
+
 // How the CTAs of the tensor pass are organised (Tf32Plan::pair):
 //   0  independent CTAs
 //   1  clusters of 2 that multicast every database chunk (halves the L2 -> SM traffic; measured
@@ -2182,17 +2299,21 @@ Tf32Plan tf32_plan_tiles(int nq, int nbt_logical, int d, int kp, int kind) {
   // when the data fill whole chunks); more than MAX_NKC: only the streamed 2-SM kernel can do it
   int chunks = (d + per_chunk - 1) / per_chunk;
   if (kind == OP_F16N && d >= 16 && ((d - 16) % per_chunk) == 0) chunks = (d - 16) / per_chunk + 1;
-  bool stream = chunks > MAX_NKC;
+  // (5 .. MAX_NKC_WIDE chunks: the 2-SM kernel's wide resident layout; YAEL_B200_WIDE=0: stream them)
+  const bool wide_ok = kind == OP_F16N && !(getenv("YAEL_B200_WIDE") && atoi(getenv("YAEL_B200_WIDE")) == 0);
+  bool stream = chunks > (wide_ok ? MAX_NKC_WIDE : MAX_NKC);
   if (kind == OP_F16N && getenv("YAEL_B200_STREAM")) stream = atoi(getenv("YAEL_B200_STREAM")) != 0 || stream;
-  if (stream && kind != OP_F16N) return p;
+  const bool wide = !stream && chunks > MAX_NKC;
+  if ((stream || wide) && kind != OP_F16N) return p;
   if (nq < 1 || nbt_logical < 1 || kp < 1) return p;
   if (kp + 2 * HALF_N > MAXL) return p;  // the in-register compaction handles MAXL entries
   int cap = pow2_ceil(8 * kp);
   if (cap < 512) cap = 512;
   if (cap > MAXL) cap = MAXL;
   const int pair = tf32_pair_mode(kind, (nq + TM - 1) / TM);
-  if (stream && pair != 2) return p;  // (fewer than two query tiles, odd SM count: exact engine)
+  if ((stream || wide) && pair != 2) return p;  // (fewer than two query tiles, odd SM count: exact engine)
   p.stream = stream ? 1 : 0;
+  p.nka = stream ? 0 : (chunks > MAX_NKC ? chunks : MAX_NKC);
   const int G = pair ? sm_count() / 2 : sm_count();          // schedulable units (CTAs or pairs)
   const int tiles_q = pair ? ((nq + TM - 1) / TM + 1) / 2 : (nq + TM - 1) / TM;  // tiles or pairs
   const int nbt = nbt_logical;
@@ -2274,20 +2395,22 @@ static int launch_mode(const Tf32Plan &plan, const CUtensorMap &mq, const CUtens
 
 template <int MODE, int LDW, int KIND = OP_F16N, bool STREAM = false>
 static int launch_2sm(const Tf32Plan &plan, const CUtensorMap &mq, const CUtensorMap &mbh,
-                      const CUtensorMap &mqx, const CUtensorMap &mbxh, const Tf32Params &P, cudaStream_t st) {
+                      const CUtensorMap &mqx, const CUtensorMap &mbxh, const Tf32Params &P, cudaStream_t st,
+                      const CUtensorMap *mout = nullptr) {
   static bool attr[64] = {};
   cudaError_t ae = cudaSuccess;
+  constexpr int smem_bytes = MODE == EPI_CROSS ? TF32_SMEM2_CROSS_BYTES : TF32_SMEM2_BYTES;
   once_per_device(attr, [&ae] {
-    ae = cudaFuncSetAttribute(k_knn_2sm<MODE, LDW, KIND, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, TF32_SMEM2_BYTES);
+    ae = cudaFuncSetAttribute(k_knn_2sm<MODE, LDW, KIND, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   });
   if (ae != cudaSuccess) {
     attr[dev_index()] = false;
-    return fail(6, "cannot reserve %d bytes of shared memory: %s", TF32_SMEM2_BYTES, cudaGetErrorString(ae));
+    return fail(6, "cannot reserve %d bytes of shared memory: %s", smem_bytes, cudaGetErrorString(ae));
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(plan.ctas);
   cfg.blockDim = dim3(TF32_THREADS);
-  cfg.dynamicSmemBytes = TF32_SMEM2_BYTES;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -2296,7 +2419,8 @@ static int launch_2sm(const Tf32Plan &plan, const CUtensorMap &mq, const CUtenso
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k_knn_2sm<MODE, LDW, KIND, STREAM>, mq, mbh, mqx, mbxh, P);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_knn_2sm<MODE, LDW, KIND, STREAM>, mq, mbh, mqx, mbxh,
+                                     mout ? *mout : mq, P);
   if (e != cudaSuccess) return fail(2, "k_knn_2sm cluster launch: %s", cudaGetErrorString(e));
   count_launch();
   return 0;
@@ -2345,7 +2469,7 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
       // 32-byte-wide chunk (a zero-filled 128-byte one costs 2.74 ms instead of 2.62 at d = 128)
       const int dd = d - 16, dbytes = 2 * dd;
       const int nkd = (dbytes + 127) / 128;
-      if (nkd + 1 > MAX_NKC && !plan.stream)
+      if (nkd + 1 > (plan.nka > MAX_NKC ? plan.nka : MAX_NKC) && !plan.stream)
         return fail(6, "folded-norm FP16 operands: d = %d needs too many chunks", dd);
       P.xk = nkd;
       P.xcol = dd;
@@ -2402,6 +2526,20 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   }
   P.dump = dump;
   P.dump_ld = dump_ld;
+  P.nka = plan.nka > MAX_NKC ? plan.nka : MAX_NKC;
+  P.stages2 = STAGES2 + MAX_NKC - P.nka;   // the same 192 KB: query tile + ring
+  if (P.nkc > P.nka && !plan.stream) return fail(6, "resident query tile: %d chunks do not fit", P.nkc);
+  CUtensorMap mout;
+  const bool cross = dump && oo && oo->cross;
+  // staged TMA stores need a 16-byte aligned output and row pitch (YAEL_B200_CROSS_TMA=0: the
+  // direct stores, A/B)
+  if (cross && (dump_ld % 4) == 0 && (((uintptr_t)dump) & 15) == 0 &&
+      !(getenv("YAEL_B200_CROSS_TMA") && atoi(getenv("YAEL_B200_CROSS_TMA")) == 0)) {
+    if ((rc = make_map_out(&mout, dump, nq, nb, dump_ld))) return rc;
+    P.cross_tma = 1;
+    P.cross_stage0 = CROSS_STAGE0_OFF;
+    P.cross_stage1 = CROSS_STAGE1_OFF;
+  }
   const int mode = (dump && oo && oo->cross) ? EPI_CROSS
                    : (dump ? EPI_DUMP : (P.gmin ? EPI_GMIN : (k1_margin ? EPI_NEAREST : EPI_LISTS)));
   if (mode == EPI_CROSS && !(plan.kind == OP_F16N && plan.pair == 2))
@@ -2472,7 +2610,7 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   if (const char *e = getenv("YAEL_B200_LDW")) ldw = atoi(e);
   if (plan.kind == OP_F16N && plan.pair == 2 && plan.stream) {  // streamed query chunks: any d
     switch (mode) {
-      case EPI_CROSS: return launch_2sm<EPI_CROSS, 16, OP_F16N, true>(plan, mq, mbh, mqx, mbxh, P, st);
+      case EPI_CROSS: return launch_2sm<EPI_CROSS, 16, OP_F16N, true>(plan, mq, mbh, mqx, mbxh, P, st, P.cross_tma ? &mout : nullptr);
       case EPI_DUMP: return launch_2sm<EPI_DUMP, 16, OP_F16N, true>(plan, mq, mbh, mqx, mbxh, P, st);
       case EPI_GMIN: return launch_2sm<EPI_GMIN, 128, OP_F16N, true>(plan, mq, mbh, mqx, mbxh, P, st);
       case EPI_LISTS: return launch_2sm<EPI_LISTS, 128, OP_F16N, true>(plan, mq, mbh, mqx, mbxh, P, st);
@@ -2482,7 +2620,7 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   if (plan.stream) return fail(6, "streamed query chunks need the 2-SM folded-norm kernel");
   if (plan.kind == OP_F16N && plan.pair == 2) {  // cta_group::2 pairs (k_knn_2sm)
     switch (mode) {
-      case EPI_CROSS: return launch_2sm<EPI_CROSS, 16>(plan, mq, mbh, mqx, mbxh, P, st);
+      case EPI_CROSS: return launch_2sm<EPI_CROSS, 16>(plan, mq, mbh, mqx, mbxh, P, st, P.cross_tma ? &mout : nullptr);
       case EPI_DUMP: return launch_2sm<EPI_DUMP, 16>(plan, mq, mbh, mqx, mbxh, P, st);
       case EPI_GMIN:
         if (ldw == 16) return launch_2sm<EPI_GMIN, 16>(plan, mq, mbh, mqx, mbxh, P, st);
