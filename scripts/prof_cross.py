@@ -16,6 +16,7 @@ torch.manual_seed(4242)
 a = torch.rand((na, d), device="cuda")
 b = torch.rand((nb, d), device="cuda")
 out = torch.empty((nb, na), device="cuda")
+L.yb_prof_enable(1)
 for engine in (1, 0):
     L.yb_set_cross_engine(engine)
     for rep in range(3):
@@ -28,6 +29,11 @@ for engine in (1, 0):
         assert rc == 0, L.yb_last_error()
         print("engine %d (used %d) rep %d: %.3f ms" % (engine, L.yb_last_cross_engine(), rep, e0.elapsed_time(e1)))
 L.yb_set_cross_engine(-1)
+cnt = C.c_long(0)
+for ph in range(12):
+    ms = L.yb_prof_ms(ph, C.byref(cnt), 0)
+    if cnt.value:
+        print("phase %d: %.3f ms avg over %d" % (ph, ms / cnt.value, cnt.value))
 if int(os.environ.get("YAEL_B200_TF32_DEBUG", "0")) & 512:
     import numpy as np
     ck = np.zeros((148, 16), np.int64)

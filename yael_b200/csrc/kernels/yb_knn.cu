@@ -1215,6 +1215,7 @@ int cross_l2_tensor(int d, int na, int nb, const float *a, const float *b, float
   void *tws = c.take<char>(plan.ws_bytes);
   YB_CUDA(cudaMemsetAsync(scal, 0, 64, st));
   {
+    ProfScope ps(0, st);
     Carver cc(cws);  // column mean of the database rows and the power-of-two scale (as center_operands_h)
     int nblk = (int)(((long)nb + CM_ROWS - 1) / CM_ROWS);
     if (nblk > CM_BLOCKS) nblk = CM_BLOCKS;
@@ -1249,7 +1250,11 @@ int cross_l2_tensor(int d, int na, int nb, const float *a, const float *b, float
       YB_CUDA(cudaMemsetAsync(b_h + (size_t)nb * dop, 0, 2 * (size_t)(padded - nb) * dop, st));
   }
   plan.acc_scale = scal + 3;
-  int rc = tf32_cross(plan, na, nb, dop, (const float *)b_h, (const float *)a_h, out, ldd, tws, st);
+  int rc;
+  {
+    ProfScope ps(1, st);
+    rc = tf32_cross(plan, na, nb, dop, (const float *)b_h, (const float *)a_h, out, ldd, tws, st);
+  }
   if (rc) return rc;
   int overflow = 0;
   YB_CUDA(cudaMemcpyAsync(&overflow, scal + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1497,6 +1502,181 @@ k_rerank_k1(int nq, int d, int slots, int lists, const float *__restrict__ base,
   }
 }
 
+// ---- lane-per-query variant (d <= 128, d % 4 == 0, 16-byte aligned rows) ------------------------
+// k_rerank_k1 above spends a whole warp on one query although only one or two lanes have a candidate
+// to walk: ncu shows it ISSUE-bound (91 % issue slots busy, ~1060 warp instructions per query; 14 ms
+// per iteration at BASELINE configs[3]).  Here a warp owns 32 consecutive queries, lane = query: the
+// 32 query rows and, per round, the lanes' next candidate rows are copied into padded shared-memory
+// tiles with cp.async (16 bytes per lane: one instruction moves a whole 512-byte row and needs no
+// registers, so all 32 rows of a tile are in flight together), and every lane walks ITS OWN pair
+// with the same sequence of operations as above (float norm of the base row, one FMA chain, the
+// query norm from k_row_norms_seq) reading float4 from a conflict-free pitch.  Rounds repeat until
+// no lane has a candidate left.  Candidates are first filtered by their tensor score: a row is
+// walked only if its score is within the query's margin of the BEST published score -- the tensor
+// pass admitted against the running best of one list (one column half of one range), so most of what
+// the other lists publish cannot be the nearest row; the margin argument of k1_margin_of holds
+// against the final best a fortiori.
+constexpr int RL_PITCH = 132;                       // floats per staged row: 16-byte aligned, 4 * lane mod 32 banks
+constexpr int RL_WARPS = 2;
+constexpr int RL_CAP = 16;                          // candidates kept per query (more: the query is redone exactly)
+constexpr int RL_WARP_FLOATS = 2 * 32 * RL_PITCH;   // query tile + candidate tile
+constexpr int RL_WARP_BYTES = RL_WARP_FLOATS * 4 + 32 * RL_CAP * 4 + 32 * RL_CAP + 32 * 8;
+constexpr int RL_SMEM_BYTES = RL_WARPS * RL_WARP_BYTES;
+static_assert(RL_WARP_BYTES % 16 == 0, "per-warp block keeps the tiles 16-byte aligned");
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// The (query, candidate) pairs of the warp's 32 queries are FLATTENED before they are walked: lane p
+// of round r takes pair 32 r + p, so a warp needs ceil(pairs / 32) rounds instead of as many as its
+// busiest query has candidates (a lane per query with 2-3 candidates on average but 8 in the worst
+// lane of a warp: 1.9 ms against 1.1 ms for 2.5 M points).
+__global__ void __launch_bounds__(32 * RL_WARPS)
+k_rerank_k1_lanes(int nq, int d, int slots, int lists, const float *__restrict__ base,
+                  const float *__restrict__ query, const int *__restrict__ cand_id,
+                  const float *__restrict__ cand_score, const float *__restrict__ cand_thr,
+                  const float *__restrict__ margin, int *__restrict__ assign, float *__restrict__ dis,
+                  int id_offset, int *__restrict__ flags, const double *__restrict__ qnorm) {
+  extern __shared__ __align__(16) unsigned char rl_sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char *mine = rl_sm + (size_t)warp * RL_WARP_BYTES;
+  float *qt = reinterpret_cast<float *>(mine), *ct = qt + 32 * RL_PITCH;
+  int *flat_id = reinterpret_cast<int *>(mine + RL_WARP_FLOATS * 4);            // [32 * RL_CAP]
+  unsigned char *flat_q = mine + RL_WARP_FLOATS * 4 + 32 * RL_CAP * 4;          // [32 * RL_CAP]
+  unsigned long long *bestk = reinterpret_cast<unsigned long long *>(flat_q + 32 * RL_CAP);  // [32]
+  const long q0 = ((long)blockIdx.x * RL_WARPS + warp) * 32;
+  if (q0 >= nq) return;
+  const long q = q0 + lane;
+  const bool valid = q < nq;
+  const bool col = lane * 4 < d;   // this lane's 16 bytes of a row
+  for (int r = 0; r < 32; r++)
+    if (col && q0 + r < nq) cp_async16(qt + r * RL_PITCH + lane * 4, query + (size_t)(q0 + r) * d + lane * 4);
+  bestk[lane] = ~0ull;
+  // my query's candidates: those whose tensor score is within the margin of the best published one
+  const int *cid = cand_id + (size_t)(valid ? q : 0) * slots;
+  const float *csc = cand_score ? cand_score + (size_t)(valid ? q : 0) * slots : nullptr;
+  float lim = __uint_as_float(0x7f800000u);
+  if (valid && csc) {
+    float sbest = lim;
+    for (int s = 0; s < slots; s++)
+      if (cid[s] >= 0) sbest = fminf(sbest, csc[s]);
+    lim = sbest + (margin ? margin[q] : 0.f);
+  }
+  int mycand[RL_CAP];
+  int n = 0;
+  bool overflow = false;
+  if (valid)
+    for (int s = 0; s < slots; s++) {
+      const int c = cid[s];
+      if (c >= 0 && !(csc && csc[s] > lim)) {
+        if (n < RL_CAP) {
+#pragma unroll
+          for (int e = 0; e < RL_CAP; e++)
+            if (e == n) mycand[e] = c;
+          n++;
+        } else {
+          overflow = true;
+        }
+      }
+    }
+  int off = n;  // exclusive prefix sum of the counts
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, off, o);
+    if (lane >= o) off += t;
+  }
+  const int total = __shfl_sync(0xffffffffu, off, 31);
+  off -= n;
+#pragma unroll
+  for (int e = 0; e < RL_CAP; e++)
+    if (e < n) {
+      flat_id[off + e] = mycand[e];
+      flat_q[off + e] = (unsigned char)lane;
+    }
+  __syncwarp();
+  for (int p0 = 0; p0 < total; p0 += 32) {
+    const int p = p0 + lane;
+    const int id = p < total ? flat_id[p] : -1;
+    const int j = p < total ? flat_q[p] : 0;
+#pragma unroll 8
+    for (int r = 0; r < 32; r++) {
+      const int idr = __shfl_sync(0xffffffffu, id, r);
+      if (idr >= 0 && col) cp_async16(ct + r * RL_PITCH + lane * 4, base + (size_t)idr * d + lane * 4);
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    if (id >= 0) {
+      const float4 *cr = reinterpret_cast<const float4 *>(ct + lane * RL_PITCH);
+      const float4 *qr = reinterpret_cast<const float4 *>(qt + j * RL_PITCH);
+      float nf = 0.f, dot = 0.f;
+#pragma unroll 8
+      for (int t4 = 0; t4 < (d >> 2); t4++) {   // coordinate order, as nn.c:100-129
+        const float4 v = cr[t4], w = qr[t4];
+        nf = __fadd_rn(nf, __fmul_rn(v.x, v.x)); dot = fmaf(v.x, w.x, dot);
+        nf = __fadd_rn(nf, __fmul_rn(v.y, v.y)); dot = fmaf(v.y, w.y, dot);
+        nf = __fadd_rn(nf, __fmul_rn(v.z, v.z)); dot = fmaf(v.z, w.z, dot);
+        nf = __fadd_rn(nf, __fmul_rn(v.w, v.w)); dot = fmaf(v.w, w.w, dot);
+      }
+      const double qn = qnorm[q0 + j];
+      const float dist = __fadd_rn((float)(qn + (double)nf), __fmul_rn(-2.0f, dot));
+      const uint32_t fk = float_key(dist);
+      if (!is_nan_key(fk)) atomicMin(&bestk[j], ((unsigned long long)fk << 32) | (unsigned)id);
+    }
+    __syncwarp();  // the candidate tile is rewritten by the next round; bestk is read after the last
+  }
+  if (!valid) return;
+  int flag = overflow ? 1 : 0;  // more candidates than RL_CAP: the exact engine redoes the query
+  for (int l = 0; l < lists; l++) {
+    const float t = cand_thr[(size_t)q * lists + l];
+    if (t != t) flag = 1;  // NaN: a list overflowed, the candidate set is incomplete
+  }
+  flags[q] = flag;
+  const unsigned long long best = bestk[lane];
+  const uint32_t fk = (uint32_t)(best >> 32);
+  const uint32_t bits = (fk & 0x80000000u) ? (fk & 0x7fffffffu) : ~fk;
+  const float dv = __uint_as_float(bits);
+  if (best != ~0ull && dv < 1e30f) {
+    assign[q] = (int)(uint32_t)best + id_offset;
+    dis[q] = dv;
+  } else {
+    assign[q] = -1;
+    dis[q] = 1e30f;
+  }
+}
+
+// launches the lane-per-query kernel when the shape allows it, else the warp-per-query one
+static int rerank_k1(int nq, int d, int slots, int lists, const float *base, const float *query,
+                     const int *cand_id, const float *cand_score, const float *cand_thr,
+                     const float *margin, int *assign, float *dis, int id_offset, int *flags,
+                     const double *qnorm, cudaStream_t st) {
+  static const bool lanes_on = !(getenv("YAEL_B200_K1_LANES") && atoi(getenv("YAEL_B200_K1_LANES")) == 0);
+  // (without tensor scores nothing filters the candidates and nobody reads the overflow flag: hkm)
+  if (lanes_on && d <= 128 && (d & 3) == 0 && ((((uintptr_t)base) | ((uintptr_t)query)) & 15) == 0 &&
+      (cand_score != nullptr || slots <= RL_CAP)) {
+    static bool attr[64] = {};
+    cudaError_t ae = cudaSuccess;
+    once_per_device(attr, [&ae] {
+      ae = cudaFuncSetAttribute(k_rerank_k1_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_BYTES);
+    });
+    if (ae != cudaSuccess) {
+      attr[dev_index()] = false;
+      return fail(6, "cannot reserve %d bytes of shared memory: %s", RL_SMEM_BYTES, cudaGetErrorString(ae));
+    }
+    const long per_cta = 32L * RL_WARPS;
+    k_rerank_k1_lanes<<<(unsigned)((nq + per_cta - 1) / per_cta), 32 * RL_WARPS, RL_SMEM_BYTES, st>>>(
+        nq, d, slots, lists, base, query, cand_id, cand_score, cand_thr, margin, assign, dis, id_offset, flags, qnorm);
+  } else {
+    k_rerank_k1<<<(nq + 3) / 4, 128, 0, st>>>(nq, d, slots, lists, base, query, cand_id, cand_thr, assign, dis,
+                                              id_offset, flags, qnorm);
+  }
+  YB_LAUNCH_CHECK();
+  return 0;
+}
+
 // (Round 2 tried a LANE per query -- 32 queries per warp, candidate and query rows staged through
 // padded shared tiles, the query norm fused in: bit-identical, but 24.1 ms against 14.5 ms at
 // BASELINE configs[3]: the staging loop's loads are only four deep.  Not kept; profiles/README.md.)
@@ -1576,9 +1756,9 @@ static int knn_tf32_nearest(int nq, int nb, int d, const float *base, const floa
     {
       ProfScope ps(3, st);
       if ((rc = row_norms_seq(query, nq, d, d, nullptr, qnorm, st))) return rc;
-      k_rerank_k1<<<(nq + 3) / 4, 128, 0, st>>>(nq, d, slots, plan.lists, base, query, cid, cthr,
-                                                assign, dis, id_offset, flags, qnorm);
-      YB_LAUNCH_CHECK();
+      if ((rc = rerank_k1(nq, d, slots, plan.lists, base, query, cid, cscore, cthr, margin, assign, dis,
+                          id_offset, flags, qnorm, st)))
+        return rc;
     }
     k_collect_flags<<<(nq + 255) / 256, 256, 0, st>>>(flags, nq, flag_list, (int *)(scal + 1));
     YB_LAUNCH_CHECK();
@@ -2318,9 +2498,9 @@ extern "C" int yb_hkm_quantize(int nlevel, int bf, int d, const float *const *le
     const long tot = n * bf;
     k_hkm_children<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cur, n, bf, cand);
     YB_LAUNCH_CHECK();
-    k_rerank_k1<<<(unsigned)((n + 3) / 4), 128, 0, st>>>((int)n, d, bf, 0, levels[l], v, cand, nullptr,
-                                                         l + 1 == nlevel ? idx : next, dis, 0, flags, qnorm);
-    YB_LAUNCH_CHECK();
+    if ((rc = rerank_k1((int)n, d, bf, 0, levels[l], v, cand, nullptr, nullptr, nullptr,
+                        l + 1 == nlevel ? idx : next, dis, 0, flags, qnorm, st)))
+      return rc;
     k_hkm_step<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cur, n, bf, l + 1 == nlevel ? idx : next);
     YB_LAUNCH_CHECK();
     int *t = cur; cur = next; next = t;
