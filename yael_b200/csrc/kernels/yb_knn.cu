@@ -75,15 +75,27 @@ struct RerankArgs {
   unsigned long long *gsort; // global sort slab when m_pad > 4096
   int m_pad;
   int k1;                  // k == 1: nn_single_full start value (-1, 1e30f), nn.c:404-407
+  int prefetch;            // issue L2 prefetches for every candidate row before the chains start
+  int cpa;                 // rows staged with cp.async into [32][RR_PITCH] tiles at tile_off (d % 4 == 0,
+  unsigned tile_off;       // 16-byte aligned base): a row is one instruction, the chains read float4
 };
 
 constexpr int RR_T = 128;  // threads per query in the re-rank kernels
+constexpr int RR_PITCH = 132;  // floats per staged row (cp.async variant): 16-byte aligned, conflict-free float4 reads
+constexpr int RR_TILE_BYTES = (RR_T / 32) * 32 * RR_PITCH * 4;
+
+__device__ __forceinline__ void rr_cp_async16(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(RR_T) k_rerank(RerankArgs A) {
   extern __shared__ unsigned char smem_raw[];
-  __shared__ float tile[RR_T / 32][32][33];
   __shared__ double qn_sh;
+  // transposition tiles of the scalar path (the cp.async path has its own layout at the same offset)
+  float (*tile)[32][33] = reinterpret_cast<float (*)[32][33]>(smem_raw + A.tile_off);
   const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = A.d;
   const int m = MODE == 0 ? A.k : A.m;
@@ -117,6 +129,14 @@ __global__ void __launch_bounds__(RR_T) k_rerank(RerankArgs A) {
         break;
       }
   }
+  if (A.prefetch) {  // the candidate rows are a gather from HBM: start every line towards L2 now
+    const int lines = (d * 4 + 127) >> 7;
+    for (int e = tid; e < ki * lines; e += RR_T) {
+      const int id = ids[e / lines];
+      if (id >= 0)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.base + (size_t)id * d + (size_t)(e % lines) * 32));
+    }
+  }
   if (tid == 0) {
     double s = 0.0;
     for (int t = 0; t < d; t++) s += (double)__fmul_rn(qs[t], qs[t]);
@@ -125,7 +145,47 @@ __global__ void __launch_bounds__(RR_T) k_rerank(RerankArgs A) {
   __syncthreads();
   const double qn = qn_sh;
 
-  for (int c0 = warp * 32; c0 < ki; c0 += RR_T) {
+  // cp.async variant (the kernel was issue-bound: 32 scalar loads + 32 stores + 32 x 5 chain
+  // instructions per 32 x 32 block): every candidate row of the block comes in with ONE 16-byte
+  // cp.async per lane (128 coordinates at a time), and lane c walks row c reading float4 -- the same
+  // operations in the same order
+  for (int c0 = warp * 32; A.cpa && c0 < ki; c0 += RR_T) {
+    const int c = c0 + lane;
+    const int id = c < ki ? ids[c] : -1;
+    float *wt = reinterpret_cast<float *>(smem_raw + A.tile_off) + (size_t)warp * 32 * RR_PITCH;
+    float nf = 0.f, dot = 0.f;
+    double nd = 0.0;
+    for (int t0 = 0; t0 < d; t0 += 128) {
+      const int w = min(128, d - t0);
+      const bool col = lane * 4 < w;
+#pragma unroll 8
+      for (int r = 0; r < 32; r++) {
+        const int idr = __shfl_sync(0xffffffffu, id, r);
+        if (idr >= 0 && col) rr_cp_async16(wt + r * RR_PITCH + lane * 4, A.base + (size_t)idr * d + t0 + lane * 4);
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncwarp();
+      if (id >= 0) {
+        const float4 *cr = reinterpret_cast<const float4 *>(wt + lane * RR_PITCH);
+        const float4 *qr = reinterpret_cast<const float4 *>(qs + t0);
+#pragma unroll 8
+        for (int t4 = 0; t4 < (w >> 2); t4++) {
+          const float4 v = cr[t4], qv = qr[t4];
+          float sq;
+          sq = __fmul_rn(v.x, v.x); if (MODE == 0) nd += (double)sq; else nf = __fadd_rn(nf, sq); dot = fmaf(v.x, qv.x, dot);
+          sq = __fmul_rn(v.y, v.y); if (MODE == 0) nd += (double)sq; else nf = __fadd_rn(nf, sq); dot = fmaf(v.y, qv.y, dot);
+          sq = __fmul_rn(v.z, v.z); if (MODE == 0) nd += (double)sq; else nf = __fadd_rn(nf, sq); dot = fmaf(v.z, qv.z, dot);
+          sq = __fmul_rn(v.w, v.w); if (MODE == 0) nd += (double)sq; else nf = __fadd_rn(nf, sq); dot = fmaf(v.w, qv.w, dot);
+        }
+      }
+      __syncwarp();
+    }
+    if (c < ki) {
+      float base = MODE == 0 ? (float)(nd + qn) : (float)(qn + (double)nf);
+      dv[c] = id >= 0 ? __fadd_rn(base, __fmul_rn(-2.0f, dot)) : __uint_as_float(0x7fc00000u);
+    }
+  }
+  for (int c0 = warp * 32; !A.cpa && c0 < ki; c0 += RR_T) {
     const int c = c0 + lane;
     const int id = c < ki ? ids[c] : -1;
     const float *rowp = id >= 0 ? A.base + (size_t)id * d : nullptr;
@@ -348,11 +408,31 @@ static size_t rerank_smem_bytes(int d, int m, int m_pad) {
   return b;
 }
 
+// chooses the cp.async row staging when the shape allows it (YAEL_B200_RR_CPA=0: the scalar path)
+// and returns the dynamic shared memory the launch needs
+static size_t rerank_setup(RerankArgs &A, size_t smem) {
+  // Measured at the bench shape (10 k queries x 200 candidates x 128): scalar path 0.431 ms, cp.async
+  // staging 0.470 ms -- a third of the instructions, but 3 instead of 10 CTAs per SM hide less of the
+  // gather latency.  Opt-in (YAEL_B200_RR_CPA=1).
+  static const bool on = getenv("YAEL_B200_RR_CPA") && atoi(getenv("YAEL_B200_RR_CPA")) != 0;
+  static const bool pf = !(getenv("YAEL_B200_RR_PREFETCH") && atoi(getenv("YAEL_B200_RR_PREFETCH")) == 0);
+  A.prefetch = pf ? 1 : 0;
+  A.cpa = 0;
+  A.tile_off = 0;
+  const size_t off = (smem + 15) & ~(size_t)15;
+  A.tile_off = (unsigned)off;
+  if (on && (A.d & 3) == 0 && (((uintptr_t)A.base) & 15) == 0 && off + RR_TILE_BYTES <= 160 * 1024) {
+    A.cpa = 1;
+    return off + RR_TILE_BYTES;
+  }
+  return off + (RR_T / 32) * 32 * 33 * 4;
+}
+
 static void rerank_attrs() {
   static bool done[64] = {};
   once_per_device(done, [] {
-    cudaFuncSetAttribute(k_rerank<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(k_rerank<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_rerank<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_rerank<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   });
 }
 
@@ -2006,7 +2086,7 @@ int knn_tf32_path(int nq, int nb, int d, int k, const float *base, const float *
     rerank_attrs();
     {
       ProfScope ps(3, st);
-      k_rerank<1><<<nq, RR_T, smem, st>>>(A);
+      k_rerank<1><<<nq, RR_T, rerank_setup(A, smem), st>>>(A);
       YB_LAUNCH_CHECK();
     }
     k_collect_flags<<<(nq + 255) / 256, 256, 0, st>>>(flags, nq, flag_list, (int *)(scal + 1));
@@ -2258,7 +2338,7 @@ int knn_tf32_streamed(int nq, int nb, int d, int k, const float *base_host, floa
     rerank_attrs();
     {
       ProfScope ps(3, st);
-      k_rerank<1><<<nq, RR_T, smem, st>>>(A);
+      k_rerank<1><<<nq, RR_T, rerank_setup(A, smem), st>>>(A);
       YB_LAUNCH_CHECK();
     }
     k_collect_flags<<<(nq + 255) / 256, 256, 0, st>>>(flags, nq, flag_list, (int *)(scal + 1));
@@ -2448,7 +2528,7 @@ extern "C" int yb_knn_reorder_shortlist(int nq, int nb, int d, int k, const floa
   size_t smem = rerank_smem_bytes(d, k, m_pad);
   if (smem > 160 * 1024) return fail(3, "knn_reorder_shortlist: d=%d k=%d too large for one CTA", d, k);
   rerank_attrs();
-  k_rerank<0><<<nq, RR_T, smem, st>>>(A);
+  k_rerank<0><<<nq, RR_T, rerank_setup(A, smem), st>>>(A);
   YB_LAUNCH_CHECK();
   return 0;
 }
