@@ -1216,16 +1216,39 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
             const int per_half = HALF_N / P.gsize;
             float *grow = P.gmin + (size_t)q * P.gmin_ld + ((long)jt * 2 + half) * per_half;
             // (a maximum of raw accumulators is a minimum of scores: asc < 0; NaN never wins fmaxf)
-            if (P.gsize == 16) {
+            if (P.gsize == 16 && (P.gmin_ld & 3) == 0) {
+              // two 16-byte stores per thread and tile: the thread's 8 minima are one 32-byte sector
+              // (as 8 scalar stores every warp instruction touched 32 sectors with 4 bytes each: 39 M
+              // partial-sector writes per sampling pass, which paced it -- ncu: tensor pipe 30 %)
+              float4 o0, o1;
+              o0.x = fmaf(asc, g[0], c0); o0.y = fmaf(asc, g[1], c0); o0.z = fmaf(asc, g[2], c0); o0.w = fmaf(asc, g[3], c0);
+              o1.x = fmaf(asc, g[4], c0); o1.y = fmaf(asc, g[5], c0); o1.z = fmaf(asc, g[6], c0); o1.w = fmaf(asc, g[7], c0);
+              reinterpret_cast<float4 *>(grow)[0] = o0;
+              reinterpret_cast<float4 *>(grow)[1] = o1;
+            } else if (P.gsize == 16) {
 #pragma unroll
               for (int i = 0; i < 8; i++) grow[i] = fmaf(asc, g[i], c0);
             } else if (P.gsize == 32) {
+              float o[4];
 #pragma unroll
-              for (int i = 0; i < 4; i++) grow[i] = fmaf(asc, fmaxf(g[2 * i], g[2 * i + 1]), c0);
+              for (int i = 0; i < 4; i++) o[i] = fmaf(asc, fmaxf(g[2 * i], g[2 * i + 1]), c0);
+              if ((P.gmin_ld & 3) == 0) {
+                *reinterpret_cast<float4 *>(grow) = make_float4(o[0], o[1], o[2], o[3]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) grow[i] = o[i];
+              }
             } else if (P.gsize == 64) {
+              float o[2];
 #pragma unroll
               for (int i = 0; i < 2; i++)
-                grow[i] = fmaf(asc, fmaxf(fmaxf(g[4 * i], g[4 * i + 1]), fmaxf(g[4 * i + 2], g[4 * i + 3])), c0);
+                o[i] = fmaf(asc, fmaxf(fmaxf(g[4 * i], g[4 * i + 1]), fmaxf(g[4 * i + 2], g[4 * i + 3])), c0);
+              if ((P.gmin_ld & 1) == 0) {
+                *reinterpret_cast<float2 *>(grow) = make_float2(o[0], o[1]);
+              } else {
+                grow[0] = o[0];
+                grow[1] = o[1];
+              }
             } else {
               const float a = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
               const float b = fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7]));
