@@ -681,6 +681,7 @@ def measure_cross(torch, L, dev):
     st = torch.cuda.current_stream()
     sp = C.c_void_p(st.cuda_stream)
     res = {}
+    kernel_ms = None
     for engine, name in ((1, "tensor_split_fp16"), (0, "exact_fp32_simt")):
         L.yb_set_cross_engine(engine)
         for _ in range(2):
@@ -699,6 +700,19 @@ def measure_cross(torch, L, dev):
                      "pairs_per_s": na * nb / (ms * 1e-3), "output_GBps": 4.0 * na * nb / (ms * 1e-3) / 1e9}
         if engine == 1:
             got = out[:2000, :512].cpu().numpy()
+            # the contraction kernel alone (yb_prof phase 1) and the operand preparation (phase 0),
+            # CUDA events on the launching stream, in a separate profiled round
+            cnt = C.c_long(0)
+            L.yb_prof_enable(1)
+            for pid in (0, 1):
+                L.yb_prof_ms(pid, C.byref(cnt), 1)
+            for _ in range(3):
+                L.yb_cross_distances_l2(d, na, nb, a.data_ptr(), d, b.data_ptr(), d, out.data_ptr(), na, sp)
+            torch.cuda.synchronize()
+            ph = _phase_means(L, ((0, "split_and_scale_operands"), (1, "k_knn_2sm_cross")))
+            L.yb_prof_enable(0)
+            res[name]["phase_ms"] = ph
+            kernel_ms = ph.get("k_knn_2sm_cross")
     L.yb_set_cross_engine(-1)
     ah, bh = a[:512].cpu().numpy(), b[:2000].cpu().numpy()
     want = ob.orc_cross(ah, bh, ob.DOT_F32_SEQ)
@@ -706,13 +720,79 @@ def measure_cross(torch, L, dev):
     peaks = _peaks()
     hbm = peaks.get("hbm_gbs", 6450.0)
     t = res["tensor_split_fp16"]
+    kms = kernel_ms if kernel_ms else t["ms"]
+    kgbs = (4.0 * na * nb + 2.0 * (3 * d + 16) * (na + nb)) / (kms * 1e-3) / 1e9
     return {"metric": "compute_cross_distances pairs/s (10k x 100k x 128)", "value": t["pairs_per_s"], "unit": "pairs/s",
             "ms_per_step": t["ms"], "engines": res,
-            "roofline": {"bound": "hbm", "kernel": "k_knn_2sm<EPI_CROSS> (output: 4 B per pair; operands 0.1 GB)",
-                         "achieved": t["output_GBps"], "peak": hbm, "unit": "GB/s", "frac": t["output_GBps"] / hbm,
-                         "traffic": None, "algorithmic_bytes_per_launch": 4.0 * na * nb + 4.0 * d * (na + nb)},
+            "roofline": {"bound": "hbm",
+                         "kernel": "k_knn_2sm<EPI_CROSS> (output: 4 B per pair through staged TMA stores; split-FP16 "
+                                   "operands 2 (3 d + 16) B per row)",
+                         "achieved": kgbs, "peak": hbm, "unit": "GB/s", "frac": kgbs / hbm,
+                         "kernel_ms": kms, "whole_call_GBps": t["output_GBps"],
+                         "traffic": None,
+                         "algorithmic_bytes_per_launch": 4.0 * na * nb + 2.0 * (3 * d + 16) * (na + nb),
+                         "note": "peak = the measured COPY bandwidth (MEASURED_PEAKS.json); a pure-write kernel "
+                                 "(torch fill_) reaches 7.5 TB/s on these boxes (scripts/prof_write_bw.py)"},
             "parity": {"config": "512 x 2000 slice of the 10k x 100k matrix vs the oracle (FP32 FMA chain)",
                        "max_rel_dis": float(rel.max()), "ok": bool(rel.max() <= 1e-5)}}
+
+
+def measure_consumers(torch, L, dev):
+    """The consumers of SURVEY.md 8(f)-N4 that sit on the path's kernels, timed through the drop-in C
+    API on device-resident inputs and checked against the oracle on a slice: hkm_quantize (3 levels of
+    exact k = 1 searches among 10 children, yael/hkm.c:144-162) and the GMM E-step gmm_compute_p
+    (yael/gmm.c:211-367: two contractions + softmax)."""
+    from oracle import bindings as ob
+    from yael_b200 import _lib as yl
+    f = C.POINTER(C.c_float)
+    r = np.random.RandomState(77)
+    out = {}
+    # hkm_quantize: 1M x 128 points, bf = 10, 3 levels
+    n, d, bf, nl = 1_000_000, 128, 10, 3
+    levels = [r.rand(bf ** (l + 1), d).astype(np.float32) for l in range(nl)]
+    ptrs = (f * nl)(*[x.ctypes.data_as(f) for x in levels])
+    h = yl.HkmT(nl, bf, bf ** nl, d, C.cast(ptrs, C.POINTER(f)))
+    v = torch.rand((n, d), device=dev)
+    idx = torch.empty(n, dtype=torch.int32, device=dev)
+    vp, ip = C.cast(v.data_ptr(), f), C.cast(idx.data_ptr(), C.POINTER(C.c_int))
+    L.hkm_quantize(C.byref(h), n, vp, ip)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        L.hkm_quantize(C.byref(h), n, vp, ip)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / 3 * 1e3
+    sl = 20000
+    want = ob.orc_hkm_quantize(levels, bf, v[:sl].cpu().numpy())
+    out["hkm_quantize"] = {"config": "1M x 128 points, bf = 10, 3 levels (device-resident points)", "ms": ms,
+                           "points_per_s": n / (ms * 1e-3),
+                           "parity": {"n_points": sl, "leaves_identical": bool(np.array_equal(idx[:sl].cpu().numpy(), want))}}
+    del v, idx
+    # gmm_compute_p: 200k x 64 points, 256 components
+    n, d, k = 200_000, 64, 256
+    mu = r.rand(k, d).astype(np.float32)
+    sg = (0.05 + 0.2 * r.rand(k, d)).astype(np.float32)
+    w = r.rand(k).astype(np.float32)
+    w /= w.sum()
+    g = yl.GmmT(d, k, w.ctypes.data_as(f), mu.ctypes.data_as(f), sg.ctypes.data_as(f))
+    v = torch.rand((n, d), device=dev)
+    p = torch.empty((n, k), device=dev)
+    vp, pp = C.cast(v.data_ptr(), f), C.cast(p.data_ptr(), f)
+    L.gmm_compute_p(n, vp, C.byref(g), pp, 1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        L.gmm_compute_p(n, vp, C.byref(g), pp, 1)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / 3 * 1e3
+    sl = 2000
+    want = ob.orc_gmm_compute_p(w, mu, sg, v[:sl].cpu().numpy(), 1)
+    got = p[:sl].cpu().numpy()
+    out["gmm_compute_p"] = {"config": "200k x 64 points, 256 components, GMM_FLAGS_W (device-resident points)",
+                            "ms": ms, "tflops_fp32": 4.0 * n * k * d / (ms * 1e-3) / 1e12,
+                            "parity": {"n_points": sl, "max_abs_err": float(np.abs(got - want).max()),
+                                       "ok": bool(np.abs(got - want).max() <= 1e-5)}}
+    return out
 
 
 def measure_extras_sharded(torch, dist, ydist, L, dev, rank, world):
@@ -1056,7 +1136,7 @@ def run_ours(args):
     parity = knn_parity(res_idx, res_dis, widx, wdis, base_h, query_h,
                         "C2: 1M x 128 database, k=100 (BASELINE configs[1])")
 
-    kmeans_block = hamming_block = cross_block = None
+    kmeans_block = hamming_block = cross_block = consumers_block = None
     if world == 1 and not args.no_extras:
         try:
             hamming_block = measure_hamming(torch, L, dev)
@@ -1070,6 +1150,10 @@ def run_ours(args):
             cross_block = measure_cross(torch, L, dev)
         except Exception as e:
             cross_block = {"error": str(e)}
+        try:
+            consumers_block = measure_consumers(torch, L, dev)
+        except Exception as e:
+            consumers_block = {"error": str(e)}
     elif extras_sharded:
         kmeans_block = extras_sharded.get("kmeans_10Mx128_k65536_sharded") or {"error": extras_sharded.get("kmeans_error")}
         hamming_block = extras_sharded.get("hamming_knn_10Mx64bit_10kq_k100_sharded") or {"error": extras_sharded.get("hamming_error")}
@@ -1097,6 +1181,7 @@ def run_ours(args):
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roof, "cpu_baseline": cpu, "parity": parity, "parity_sharded": parity_sharded,
         "kmeans": kmeans_block, "hamming": hamming_block, "cross_distances": cross_block,
+        "consumers": consumers_block,
     }))
     if world > 1:
         dist.destroy_process_group()
