@@ -33,6 +33,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <cuda_fp16.h>
+
 #include "yb_common.cuh"
 #include "yb_internal.cuh"
 
@@ -302,6 +304,16 @@ __device__ __forceinline__ void tc_ld64(uint32_t taddr, uint32_t (&v)[64]) {
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 128 consecutive columns holding 16-bit accumulators (D = F16), packed two per register:
+// register r = columns (2 r, 2 r + 1) in its (low, high) half -> 64 registers per thread
+__device__ __forceinline__ void tc_ld128p(uint32_t taddr, uint32_t (&v)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.pack::16b.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+      : "r"(taddr)
+      : "memory");
+}
 template <int W>
 __device__ __forceinline__ void tc_ldw(uint32_t taddr, uint32_t (&v)[W]) {
   if constexpr (W == 16) tc_ld16(taddr, v);
@@ -353,10 +365,15 @@ constexpr int OP_F8P = 4;  // planning only (tf32_plan_tiles): E4M3 in the packe
 // tiles, score = asc * acc + c0, the MAX-tree epilogue of the folded-norm kind; padding rows are E4M3
 // NaN (a NaN accumulator is never admitted)
 constexpr int OP_F8C = 5;
+// OP_F8H: the OP_F8C operands with FP16 ACCUMULATORS (D = F16).  The Hamming contraction of +-1
+// operands yields integers of magnitude <= 512, exact in FP16 at every step of the accumulation; the
+// epilogue then drains half the registers per tile (tcgen05.ld ... .pack::16b) and runs its max tree
+// on half2 pairs.  Kernel-side only: plans and operand layouts are those of OP_F8C.
+constexpr int OP_F8H = 6;
 template <int KIND>
 __device__ __forceinline__ void tc_mma_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                              uint32_t accumulate) {
-  if (KIND == OP_F8 || KIND == OP_F8C)
+  if (KIND == OP_F8 || KIND == OP_F8C || KIND == OP_F8H)
     tc_mma_f8_elect(d_tmem, a_desc, b_desc, IDESC_F8, accumulate);
   else if (KIND == OP_F16 || KIND == OP_F16N)
     tc_mma_f16_elect(d_tmem, a_desc, b_desc, IDESC_F16, accumulate);
@@ -724,6 +741,54 @@ __device__ __forceinline__ void process_wide_lists(const uint32_t (&v)[W], float
   }
 }
 
+// The top-k' test on 128 columns of FP16 accumulators, two per register (OP_F8H): the max tree runs
+// on half2 pairs (one HMNMX2 per two columns), a fired group of 16 columns (8 registers) is unpacked
+// and handled like process_wide_lists does.  NaN accumulators (padding rows) never win a maximum.
+__device__ __forceinline__ float h2max(uint32_t x) {
+  const __half2 h = *reinterpret_cast<const __half2 *>(&x);
+  return fmaxf(__low2float(h), __high2float(h));
+}
+__device__ __forceinline__ uint32_t h2m(uint32_t a, uint32_t b) {
+  const __half2 r = __hmax2(*reinterpret_cast<const __half2 *>(&a), *reinterpret_cast<const __half2 *>(&b));
+  return *reinterpret_cast<const uint32_t *>(&r);
+}
+__device__ __forceinline__ void process_wide_lists_h(const uint32_t (&v)[64], float thr, float thrp,
+                                                     float2 *mylist, int &cnt, int id0, float asc, float c0) {
+  uint32_t gm[8];
+#pragma unroll
+  for (int s = 0; s < 8; s++)
+    gm[s] = h2m(h2m(h2m(v[8 * s], v[8 * s + 1]), h2m(v[8 * s + 2], v[8 * s + 3])),
+                h2m(h2m(v[8 * s + 4], v[8 * s + 5]), h2m(v[8 * s + 6], v[8 * s + 7])));
+  const float M = h2max(h2m(h2m(h2m(gm[0], gm[1]), h2m(gm[2], gm[3])), h2m(h2m(gm[4], gm[5]), h2m(gm[6], gm[7]))));
+  if (M > thrp) {
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      const float g = h2max(gm[s]);
+      if (g > thrp) {
+        float x[16];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+          const __half2 h = *reinterpret_cast<const __half2 *>(&v[8 * s + r]);
+          x[2 * r] = __low2float(h);
+          x[2 * r + 1] = __high2float(h);
+        }
+        unsigned m = 0u;
+#pragma unroll
+        for (int c = 0; c < 16; c++) m |= (x[c] > thrp) ? (1u << c) : 0u;
+        if (__popc(m) == 1) {
+          mylist[cnt] = make_float2(fmaf(asc, g, c0), __int_as_float(id0 + 16 * s + __ffs(m) - 1));
+          cnt++;
+        } else {
+          float sc[16];
+#pragma unroll
+          for (int c = 0; c < 16; c++) sc[c] = fmaf(asc, x[c], c0);
+          cnt = slow_append(YB_SC16_ARGS(sc), thr, mylist, cnt, id0 + 16 * s);
+        }
+      }
+    }
+  }
+}
+
 // smallest score of 16 accumulator columns (sampling pass)
 __device__ __forceinline__ float group_min16(const uint32_t (&v)[16], const float *bn, float asc) {
   float sc[16];
@@ -947,8 +1012,8 @@ enum : int { EPI_LISTS = 0, EPI_NEAREST = 1, EPI_DUMP = 2, EPI_GMIN = 3, EPI_HAM
 
 template <int MODE, int KIND, int LDW>
 __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &E) {
-  constexpr bool NF = KIND == OP_F16N || KIND == OP_F8C;  // |b|^2 folded into the contraction / constant
-  const float c0 = KIND == OP_F8C ? P.c0 : 0.f;
+  constexpr bool NF = KIND == OP_F16N || KIND == OP_F8C || KIND == OP_F8H;  // |b|^2 folded into the contraction / constant
+  const float c0 = (KIND == OP_F8C || KIND == OP_F8H) ? P.c0 : 0.f;
   // no |b|^2 tiles travel: folded norms, and the packed Hamming modes (integer epilogue)
   constexpr bool NOBN = NF || MODE == EPI_HAMP || MODE == EPI_HAMG;
   unsigned char *smem = E.smem;
@@ -995,7 +1060,88 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
       // issues its first load into va, tests vb of tile t in the load's shadow, then issues the second
       // load into vb, waits for both and hands the buffer back.  Per tile the warp no longer pays
       // "wait for the accumulator + two loads" (~570 of its ~1640 clk) in series with the tests.
-      constexpr bool PIPE = NF && LDW == 128 && EPI_TEAMS == 1 && (MODE == EPI_LISTS || MODE == EPI_NEAREST);
+      // ---- FP16 accumulators (OP_F8H, top-k' mode): a half tile is ONE packed load of 64 registers;
+      // tile t+1 is loaded into the other register set while tile t is tested (two tiles per trip)
+      constexpr bool HACC = KIND == OP_F8H;
+      if constexpr (HACC && MODE == EPI_LISTS) {
+        uint32_t va[64], vb[64];
+        // 16-bit accumulators still occupy one 32-bit TMEM column each: same column addresses
+        auto hand_back_h = [&](uint32_t b) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t te = b ? E.t_empty_addr1 : E.t_empty_addr0;
+            if (E.t_empty_remote)
+              mbar_arrive_cluster(te);
+            else
+              mbar_arrive(te);
+          }
+        };
+        auto room_check = [&]() {
+          unsigned need = __ballot_sync(0xffffffffu, cnt > P.cap - HALF_N);
+          while (need) {
+            const int owner = __ffs(need) - 1;
+            need &= need - 1;
+            float2 *l = (float2 *)__shfl_sync(0xffffffffu, (unsigned long long)mylist, owner);
+            const int n = __shfl_sync(0xffffffffu, cnt, owner);
+            __syncwarp();
+            const float nt = warp_select_compact(l, n, P.kprime, hist);
+            if (lane == owner) {
+              thr = nt;
+              cnt = P.kprime;
+            }
+          }
+          thrp = __fmul_rn(thr - c0, inv_asc);
+        };
+        {
+          const uint32_t b0 = tcount & 1;
+          mbar_wait(bar(E.t_full0 + b0), (tcount >> 1) & 1);
+          tc_fence_after();
+          tc_ld128p(lane_addr + b0 * TN, va);
+          tc_wait_ld();
+          hand_back_h(b0);
+        }
+        for (int jt = jt0; jt < jt1;) {
+          {  // tile jt sits in va
+            const int n0 = jt * P.tile_stride * TN + half * HALF_N + P.id0;
+            const bool more = jt + 1 < jt1;
+            const uint32_t nbuf = (tcount + 1) & 1;
+            if (more) {
+              mbar_wait(bar(E.t_full0 + nbuf), ((tcount + 1) >> 1) & 1);
+              tc_fence_after();
+              tc_ld128p(lane_addr + nbuf * TN, vb);
+            }
+            if (!(P.debug & 1)) process_wide_lists_h(va, thr, thrp, mylist, cnt, n0, asc, c0);
+            if (more) {
+              tc_wait_ld();
+              hand_back_h(nbuf);
+            }
+            room_check();
+            jt++;
+            tcount++;
+            if (!more) break;
+          }
+          {  // tile jt sits in vb
+            const int n0 = jt * P.tile_stride * TN + half * HALF_N + P.id0;
+            const bool more = jt + 1 < jt1;
+            const uint32_t nbuf = (tcount + 1) & 1;
+            if (more) {
+              mbar_wait(bar(E.t_full0 + nbuf), ((tcount + 1) >> 1) & 1);
+              tc_fence_after();
+              tc_ld128p(lane_addr + nbuf * TN, va);
+            }
+            if (!(P.debug & 1)) process_wide_lists_h(vb, thr, thrp, mylist, cnt, n0, asc, c0);
+            if (more) {
+              tc_wait_ld();
+              hand_back_h(nbuf);
+            }
+            room_check();
+            jt++;
+            tcount++;
+          }
+        }
+      }
+      constexpr bool PIPE = NF && !HACC && LDW == 128 && EPI_TEAMS == 1 && (MODE == EPI_LISTS || MODE == EPI_NEAREST);
       const bool piped = PIPE && !(P.debug & (2048 | 512 | 1 | 256));  // (bit 2048: the serial drain, A/B)
       if (PIPE && piped) {
         constexpr bool K1W = MODE == EPI_NEAREST;
@@ -1059,7 +1205,7 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           thrp = __fmul_rn(thr - c0, inv_asc);
         }
       }
-      for (int jt = jt0; !(PIPE && piped) && jt < jt1; jt++, tcount++) {
+      for (int jt = jt0; !(HACC && MODE == EPI_LISTS) && !(PIPE && piped) && jt < jt1; jt++, tcount++) {
         const uint32_t buf = tcount & 1, slot = tcount % NBN;
         if (EPI_TEAMS > 1 && (int)buf != team) continue;  // the other team's accumulator buffer
         bool handed_back = false;
@@ -1647,7 +1793,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
   if (warp == EPI_WARPS) {
     // ======================================================================== TMA producer
     regs_aux();
-    constexpr int KCE = (KIND == OP_F8 || KIND == OP_F8C) ? KC * 4 : ((KIND == OP_F16 || KIND == OP_F16N) ? KC * 2 : KC);  // elements per 128-byte K chunk (TMA coordinates)
+    constexpr int KCE = (KIND == OP_F8 || KIND == OP_F8C || KIND == OP_F8H) ? KC * 4 : ((KIND == OP_F16 || KIND == OP_F16N) ? KC * 2 : KC);  // elements per 128-byte K chunk (TMA coordinates)
     if (lane == 0) {
       uint32_t icount = 0, ccount = 0, tcount = 0;
       for (int item = first_item; item < P.items; item += item_step, icount++) {
@@ -1668,7 +1814,7 @@ k_knn_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
                       qt * TM);
         for (int jt = jt0; jt < jt1; jt++, tcount++) {
           const int jta = jt * P.tile_stride;  // actual database tile
-          if (!(NFK || KIND == OP_F8C || MODE == EPI_HAMP || MODE == EPI_HAMG)) {  // |b|^2 of the tile (the folded-norm kinds carry it in the operands, the packed Hamming modes do not use it)
+          if (!(NFK || KIND == OP_F8C || KIND == OP_F8H || MODE == EPI_HAMP || MODE == EPI_HAMG)) {  // |b|^2 of the tile (the folded-norm kinds carry it in the operands, the packed Hamming modes do not use it)
             const uint32_t slot = tcount % NBN;
             mbar_wait(bar(Smem::n_empty + slot), ((tcount / NBN) & 1) ^ 1);
             mbar_expect_tx(bar(Smem::n_full + slot), TN * 4);
@@ -1931,7 +2077,9 @@ constexpr uint32_t IDESC_F16_2SM = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((u
 template <int KIND>
 __device__ __forceinline__ void tc_mma_2sm_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                                  uint32_t accumulate) {
-  if (KIND == OP_F8 || KIND == OP_F8C)
+  if (KIND == OP_F8H)   // D = F16: c_format (bits 4-5 of the instruction descriptor) = 0
+    tc_mma_f8_2sm_elect(d_tmem, a_desc, b_desc, IDESC_F16_2SM & ~(3u << 4), accumulate);
+  else if (KIND == OP_F8 || KIND == OP_F8C)
     tc_mma_f8_2sm_elect(d_tmem, a_desc, b_desc, IDESC_F16_2SM, accumulate);
   else
     tc_mma_f16_2sm_elect(d_tmem, a_desc, b_desc, IDESC_F16_2SM, accumulate);
@@ -1950,7 +2098,7 @@ __global__ void __launch_bounds__(TF32_THREADS, 1)
 k_knn_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_bh,
           const __grid_constant__ CUtensorMap map_qx, const __grid_constant__ CUtensorMap map_bxh,
           const __grid_constant__ CUtensorMap map_out, const Tf32Params P) {
-  static_assert(KIND == OP_F16N || KIND == OP_F8C || (KIND == OP_F8 && (MODE == EPI_HAMP || MODE == EPI_HAMG)),
+  static_assert(KIND == OP_F16N || KIND == OP_F8C || KIND == OP_F8H || (KIND == OP_F8 && (MODE == EPI_HAMP || MODE == EPI_HAMG)),
                 "the 2-SM kernel carries no |b|^2 ring");
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -1961,7 +2109,7 @@ k_knn_2sm(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
   const bool leader = crank == 0;
   const int xk = KIND == OP_F16N ? P.xk : -1;  // index of the extras chunk (-1: the extras sit inside the last data chunk)
   const bool xring = KIND == OP_F16N && !STREAM && P.xring != 0;  // extras travel through their own 2-slot ring
-  constexpr int KCE = (KIND == OP_F8 || KIND == OP_F8C) ? KC * 4 : KC * 2;  // elements per 128-byte K chunk
+  constexpr int KCE = (KIND == OP_F8 || KIND == OP_F8C || KIND == OP_F8H) ? KC * 4 : KC * 2;  // elements per 128-byte K chunk
 
   if (threadIdx.x == 0) {
     mbar_init(bar(Smem2::a_full), 1);
@@ -2582,7 +2730,12 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
       switch (mode) {
         case EPI_DUMP: return launch_2sm<EPI_DUMP, 16, OP_F8C>(plan, mq, mbh, mqx, mbxh, P, st);
         case EPI_GMIN: return launch_2sm<EPI_GMIN, 128, OP_F8C>(plan, mq, mbh, mqx, mbxh, P, st);
-        case EPI_LISTS: return launch_2sm<EPI_LISTS, 128, OP_F8C>(plan, mq, mbh, mqx, mbxh, P, st);
+        case EPI_LISTS: {
+          // FP16 accumulators for the full pass (YAEL_B200_HAM_F16ACC=0: FP32, A/B)
+          static const bool hacc = getenv("YAEL_B200_HAM_F16ACC") && atoi(getenv("YAEL_B200_HAM_F16ACC")) != 0;
+          if (hacc) return launch_2sm<EPI_LISTS, 128, OP_F8H>(plan, mq, mbh, mqx, mbxh, P, st);
+          return launch_2sm<EPI_LISTS, 128, OP_F8C>(plan, mq, mbh, mqx, mbxh, P, st);
+        }
         default: return fail(6, "the E4M3 operand kind has no k = 1 margin mode");
       }
     }
