@@ -1,6 +1,6 @@
 """Opcode histogram of every kernel in yael_b200/libyael_b200.so (cuobjdump -sass), the evidence
 that the shipped cubins are hand-written sm_100a code: tcgen05 MMAs (UTCHMMA f16/tf32, UTCQMMA
-f8f6f4), TMA (UTMALDG, UBLKCP), TMEM loads (LDTM), mbarrier waits (SYNCS), packed FP32 (FFMA2),
+f8f6f4), TMA loads and stores (UTMALDG, UTMASTG, UBLKCP), cp.async (LDGSTS), TMEM loads (LDTM), mbarrier waits (SYNCS), packed FP32 (FFMA2),
 three-input min/max (FMNMX3), population counts (POPC).
 
     python scripts/sass_histogram.py > profiles/r2_sass_opcodes.txt
@@ -13,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "yael_b200", "libyael_b200.so")
-KEY = ["UTCHMMA", "UTCQMMA", "UTCIMMA", "UTCOMMA", "UTMALDG", "UBLKCP", "UTCBAR", "LDTM", "STTM", "SYNCS",
+KEY = ["UTCHMMA", "UTCQMMA", "UTCIMMA", "UTCOMMA", "UTMALDG", "UTMASTG", "LDGSTS", "UBLKCP", "UTCBAR", "LDTM", "STTM", "SYNCS",
        "ELECT", "POPC", "FFMA2", "FMNMX3", "FMNMX", "HFMA2", "HMNMX2", "LOP3", "ATOMS", "ATOMG", "RED",
        "LDG", "STG", "LDS", "STS", "SHFL", "MATCH", "BAR"]
 
