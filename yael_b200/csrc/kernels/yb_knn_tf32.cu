@@ -634,16 +634,15 @@ __device__ __forceinline__ void process_group(const uint32_t (&v)[16], const flo
 // asc = -2^(1 - 2 sigma) < 0: no |b|^2 staging, no FMA -- the group test is a MAX tree over the
 // raw accumulators against thr / asc (exact: asc is a power of two).  NaN accumulators (padding
 // rows, NaN data) never win a max and never pass a comparison.
+__device__ __forceinline__ float max3f(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }  // one FMNMX3
 __device__ __forceinline__ float group_max16(const uint32_t (&v)[16]) {
-  const float m01 = fmaxf(fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])),
-                          fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3])));
-  const float m23 = fmaxf(fmaxf(__uint_as_float(v[4]), __uint_as_float(v[5])),
-                          fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7])));
-  const float m45 = fmaxf(fmaxf(__uint_as_float(v[8]), __uint_as_float(v[9])),
-                          fmaxf(__uint_as_float(v[10]), __uint_as_float(v[11])));
-  const float m67 = fmaxf(fmaxf(__uint_as_float(v[12]), __uint_as_float(v[13])),
-                          fmaxf(__uint_as_float(v[14]), __uint_as_float(v[15])));
-  return fmaxf(fmaxf(m01, m23), fmaxf(m45, m67));
+  // eight three-input maxima (FMNMX3 retires two values per instruction; the pairwise tree needed ten)
+  const float a = max3f(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+  const float b = max3f(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+  const float c = max3f(__uint_as_float(v[6]), __uint_as_float(v[7]), __uint_as_float(v[8]));
+  const float d = max3f(__uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
+  const float e = max3f(__uint_as_float(v[12]), __uint_as_float(v[13]), __uint_as_float(v[14]));
+  return fmaxf(max3f(a, b, c), max3f(d, e, __uint_as_float(v[15])));
 }
 
 template <bool K1>
