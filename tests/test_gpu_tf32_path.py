@@ -368,3 +368,47 @@ def test_kmeans_assignment_large_d(yn, ob, tf32_engine):
     assert mism.mean() < 1e-3
     np.testing.assert_allclose(dis, wd, rtol=1e-5)
     np.testing.assert_allclose(cent, wc, atol=1e-4)
+
+
+# ---------------------------------------------------------------- k = 1 re-rank: lane per (query, candidate) pair
+@pytest.mark.parametrize("nq,nb,d", [(1000, 30000, 100), (333, 9000, 36), (2049, 70000, 128), (65, 4000, 8),
+                                     (500, 20000, 124)])
+def test_knn_k1_lane_rerank_matches_oracle_and_warp_kernel(yn, ob, tf32_engine, monkeypatch, nq, nb, d):
+    # k_rerank_k1_lanes (d <= 128, d % 4 == 0): rows shorter than 128 coordinates, a ragged last
+    # warp of queries, and the same answer as the warp-per-query kernel (YAEL_B200_K1_LANES=0)
+    r = rs(nq + nb + d)
+    b = r.rand(nb, d).astype(np.float32)
+    q = r.rand(nq, d).astype(np.float32)
+    b[7] = b[3]                      # exact duplicate rows: the lowest id wins (nn.c:404-440)
+    q[0] = b[3]
+    idx, dis = yn.knn(q, b, 1)
+    assert tf32_engine.yb_last_knn_engine() == 1
+    widx, wdis = ob.orc_knn(b, q, 1, ob.DOT_F32_SEQ, canonical=True)
+    check_knn(idx, dis, widx, wdis, b, q)
+    assert idx[0, 0] == 3
+    import subprocess, sys, os, json
+    code = ("import numpy as np, json, sys; sys.path.insert(0, %r); import yael_b200; from yael_b200 import ynumpy as yn;"
+            "yael_b200.lib().yb_set_knn_engine(1); r = np.random.RandomState(%d);"
+            "b = r.rand(%d, %d).astype(np.float32); q = r.rand(%d, %d).astype(np.float32); b[7] = b[3]; q[0] = b[3];"
+            "i, d = yn.knn(q, b, 1); print(json.dumps([i.ravel().tolist(), d.view(np.int32).ravel().tolist()]))"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), (nq + nb + d) % (2 ** 31), nb, d, nq, d))
+    env = dict(os.environ, YAEL_B200_K1_LANES="0")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    oi, od = json.loads(out.stdout.strip().splitlines()[-1])
+    assert np.array_equal(np.array(oi, np.int32), idx.ravel())
+    assert np.array_equal(np.array(od, np.int32), dis.view(np.int32).ravel())
+
+
+def test_knn_k1_many_near_ties_overflow_goes_to_exact_engine(yn, ob, tf32_engine):
+    # hundreds of rows within the margin of the best score: more than RL_CAP (16) candidates survive the
+    # score filter, the query is flagged and redone by the exact engine -- still the reference's answer
+    r = rs(99)
+    d, nb = 64, 20000
+    centre = r.rand(d).astype(np.float32)
+    b = r.rand(nb, d).astype(np.float32)
+    b[:600] = centre + (1e-6 * r.randn(600, d)).astype(np.float32)
+    q = np.tile(centre, (40, 1)).astype(np.float32) + (1e-6 * r.randn(40, d)).astype(np.float32)
+    idx, dis = yn.knn(q, b, 1)
+    widx, wdis = ob.orc_knn(b, q, 1, ob.DOT_F32_SEQ, canonical=True)
+    check_knn(idx, dis, widx, wdis, b, q)
