@@ -438,6 +438,7 @@ struct Tf32Params {
   int debug;           // bring-up switches (YAEL_B200_TF32_DEBUG): 1 skip epilogue math, 2 skip MMAs
   int nka;             // 2-SM kernel, resident query tile: chunk slots it occupies (MAX_NKC .. MAX_NKC_WIDE)
   int stages2;         // ... and the database ring stages that fit behind it (STAGES2 .. 5)
+  int dephase;         // experiment: cycles the column-half-1 epilogue warps wait once per work item
   int cross_tma;       // EPI_CROSS: tiles leave through shared memory and TMA stores ...
   uint32_t cross_stage0, cross_stage1;  // ... staged in these rings (byte offsets, one per column half)
 };
@@ -1165,6 +1166,14 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
           tc_ldw<64>(ta + 64, vb);
           tc_wait_ld();
           hand_back(b0);
+          // experiment (YAEL_B200_EPI_DEPHASE=<cycles>): the two epilogue warps of a scheduler drain
+          // the two column halves of the SAME tile in lockstep -- both wait for TMEM loads at the same
+          // time, both run their max trees at the same time; a one-time delay of the second half's
+          // warps puts one's tree under the other's wait
+          if (P.dephase > 0 && half == 1) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < P.dephase) {}
+          }
         }
         for (int jt = jt0; jt < jt1; jt++, tcount++) {
           const int n0 = jt * P.tile_stride * TN + half * HALF_N + P.id0;
@@ -2715,6 +2724,10 @@ static int launch_tf32(const Tf32Plan &plan, int nq, int nb, int d, int nbt_logi
   if (mode == EPI_CROSS && !(plan.kind == OP_F16N && plan.pair == 2))
     return fail(6, "the cross-distance mode needs the 2-SM folded-norm kernel");
   P.acc_scale = plan.acc_scale;
+  {
+    const char *e = getenv("YAEL_B200_EPI_DEPHASE");
+    P.dephase = e ? atoi(e) : 0;
+  }
   {
     const char *e = getenv("YAEL_B200_TF32_ORDER");
     P.order = e ? atoi(e) : 0;
