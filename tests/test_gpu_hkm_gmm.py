@@ -132,3 +132,15 @@ def test_gmm_posteriors_device_pointers(yn, ob):
     dv.free()
     dp.free()
     assert np.array_equal(got, yn.gmm_compute_p((w, mu, sigma), v, 1))
+
+
+def test_hkm_quantize_without_levels_is_one_leaf():
+    # yael/hkm.c:144-162 with nlevel = 0: the loop body never runs, every point lands in leaf 0
+    import yael_b200
+    from yael_b200 import _lib
+    L = yael_b200.lib()
+    v = np.random.RandomState(1).rand(100, 8).astype(np.float32)
+    h = _lib.HkmT(0, 4, 1, 8, None)
+    idx = np.full(100, -7, np.int32)
+    L.hkm_quantize(C.byref(h), 100, v.ctypes.data_as(C.POINTER(C.c_float)), idx.ctypes.data_as(C.POINTER(C.c_int)))
+    assert (idx == 0).all()

@@ -2567,7 +2567,12 @@ __global__ void k_hkm_step(const int *__restrict__ vw, long n, int bf, int *__re
 extern "C" int yb_hkm_quantize(int nlevel, int bf, int d, const float *const *levels, long n,
                                const float *v, int *idx, yb_stream_t s) {
   if (n <= 0) return 0;
-  if (nlevel <= 0 || bf <= 0 || d <= 0) return fail(3, "yb_hkm_quantize: nlevel=%d bf=%d d=%d", nlevel, bf, d);
+  if (nlevel == 0) {  // a tree without levels has one leaf (the reference's loop leaves vw = 0)
+    Guard g0;
+    YB_CUDA(cudaMemsetAsync(idx, 0, sizeof(int) * (size_t)n, stream_of(s)));
+    return 0;
+  }
+  if (nlevel < 0 || bf <= 0 || d <= 0) return fail(3, "yb_hkm_quantize: nlevel=%d bf=%d d=%d", nlevel, bf, d);
   if (n > 0x7fffffffL / (bf > 4 ? bf : 4)) return fail(3, "yb_hkm_quantize: n = %ld x bf = %d is too large", n, bf);
   Guard g;
   cudaStream_t st = stream_of(s);
