@@ -1143,6 +1143,73 @@ __device__ __forceinline__ void run_epilogue(const Tf32Params &P, const EpiCtx &
       }
       constexpr bool PIPE = NF && !HACC && LDW == 128 && EPI_TEAMS == 1 && (MODE == EPI_LISTS || MODE == EPI_NEAREST);
       const bool piped = PIPE && !(P.debug & (2048 | 512 | 1 | 256));  // (bit 2048: the serial drain, A/B)
+#ifdef YB_PIPE4
+      // experiment (-DYB_PIPE4, top-k' mode): the half tile as FOUR 32-column register sets; after a
+      // set has been tested the same columns of the next tile are loaded into it, so three of the
+      // four loads of a tile are long complete when the one tcgen05.wait::ld per tile is reached
+      if (PIPE && piped && MODE == EPI_LISTS) {
+        uint32_t r0[32], r1[32], r2[32], r3[32];
+        auto hand_back4 = [&](uint32_t b) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t te = b ? E.t_empty_addr1 : E.t_empty_addr0;
+            if (E.t_empty_remote)
+              mbar_arrive_cluster(te);
+            else
+              mbar_arrive(te);
+          }
+        };
+        {
+          const uint32_t b0 = tcount & 1;
+          mbar_wait(bar(E.t_full0 + b0), (tcount >> 1) & 1);
+          tc_fence_after();
+          const uint32_t ta = lane_addr + b0 * TN;
+          tc_ld32(ta, r0);
+          tc_ld32(ta + 32, r1);
+          tc_ld32(ta + 64, r2);
+          tc_ld32(ta + 96, r3);
+          tc_wait_ld();
+          hand_back4(b0);
+        }
+        for (int jt = jt0; jt < jt1; jt++, tcount++) {
+          const int n0 = jt * P.tile_stride * TN + half * HALF_N + P.id0;
+          const bool more = jt + 1 < jt1;
+          const uint32_t nbuf = (tcount + 1) & 1;
+          const uint32_t tan = lane_addr + nbuf * TN;
+          process_wide_lists<32>(r0, thr, thrp, mylist, cnt, n0, asc, c0);
+          if (more) {
+            mbar_wait(bar(E.t_full0 + nbuf), ((tcount + 1) >> 1) & 1);
+            tc_fence_after();
+            tc_ld32(tan, r0);
+          }
+          process_wide_lists<32>(r1, thr, thrp, mylist, cnt, n0 + 32, asc, c0);
+          if (more) tc_ld32(tan + 32, r1);
+          process_wide_lists<32>(r2, thr, thrp, mylist, cnt, n0 + 64, asc, c0);
+          if (more) tc_ld32(tan + 64, r2);
+          process_wide_lists<32>(r3, thr, thrp, mylist, cnt, n0 + 96, asc, c0);
+          if (more) {
+            tc_ld32(tan + 96, r3);
+            tc_wait_ld();
+            hand_back4(nbuf);
+          }
+          unsigned need = __ballot_sync(0xffffffffu, cnt > P.cap - HALF_N);
+          while (need) {
+            const int owner = __ffs(need) - 1;
+            need &= need - 1;
+            float2 *l = (float2 *)__shfl_sync(0xffffffffu, (unsigned long long)mylist, owner);
+            const int n = __shfl_sync(0xffffffffu, cnt, owner);
+            __syncwarp();
+            const float nt = warp_select_compact(l, n, P.kprime, hist);
+            if (lane == owner) {
+              thr = nt;
+              cnt = P.kprime;
+            }
+          }
+          thrp = __fmul_rn(thr - c0, inv_asc);
+        }
+      } else
+#endif
       if (PIPE && piped) {
         constexpr bool K1W = MODE == EPI_NEAREST;
         uint32_t va[64], vb[64];
