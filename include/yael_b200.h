@@ -60,7 +60,8 @@ void yb_set_knn_engine(int engine);
  * 7 Hamming popcount scan, 8 k-means accumulate (sort + segmented sums), 9 k-means scale,
  * 10 / 11 k-NN admission-threshold sampling, 12 Hamming code expansion (+-1 E4M3), 13 Hamming
  * threshold sampling, 14 Hamming tcgen05 E4M3 pass, 15 Hamming order + certify, 16 sharded
- * exchange (NCCL all-to-all / all-gather / all-reduce), 17 merge of a query slice */
+ * exchange (NCCL all-to-all / all-gather / all-reduce), 17 merge of a query slice, 18 the row stream
+ * of the k-means update alone (k_segsum_sorted, inside phase 8) */
 void yb_prof_enable(int on);
 double yb_prof_ms(int phase, long *count, int reset);
 

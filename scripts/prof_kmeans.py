@@ -33,8 +33,10 @@ for rep in range(2):
     dt = time.perf_counter() - t
     print("rep %d: %d iterations in %.3f s -> %.3f iter/s, qerr %.5f, engine %d uncert %d" %
           (rep, niter, dt, niter / dt, q, L.yb_last_knn_engine(), L.yb_last_knn_uncertified()))
+print("cluster sizes after the run: min %d  median %d  p99 %d  p99.9 %d  max %d  (n/k = %.0f)" % (
+    nassign.min(), np.median(nassign), np.percentile(nassign, 99), np.percentile(nassign, 99.9), nassign.max(), n / k))
 cnt = C.c_long(0)
-for ph in range(12):
+for ph in range(20):
     ms = L.yb_prof_ms(ph, C.byref(cnt), 0)
     if cnt.value:
         print("phase %d: %.3f ms avg over %d" % (ph, ms / cnt.value, cnt.value))

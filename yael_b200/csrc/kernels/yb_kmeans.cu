@@ -21,7 +21,12 @@ namespace yb {
 // Device-side path selection without a host round trip: `guard` points at the largest cluster size
 // of this iteration (NULL = no selection).  The short-segment kernels run when it is <= SG_LIMIT,
 // the general (radix sort) kernels launched behind them when it is larger; the others return at once.
-constexpr int kSegLimit = 64 * 1024;
+// 2048: a longer segment makes the short-segment kernel's id-range passes quadratic and ONE warp's
+// serial walk the critical path -- measured at BASELINE configs[3]: the first iteration after a
+// random-point initialisation has a 12 860-point cluster (p99.9: 3214, median 65) and the row stream
+// took 9.9 ms against 0.9 ms from the second iteration on (largest cluster 316); the general path does
+// that iteration in 2.0 ms.  (Was 65536: only truly degenerate clusterings switched.)
+constexpr int kSegLimit = 2048;
 __device__ __forceinline__ bool general_path_skips(const int *guard) {
   return guard != nullptr && *guard <= kSegLimit;
 }
@@ -546,17 +551,23 @@ extern "C" int yb_kmeans_accumulate(int d, int n, int k, const float *v, const i
   // that would leave the machine idle (few, large clusters) shorter pieces trade the last
   // ulp for parallelism (still deterministic).
   int P;
+  bool many = false;
   if (exact_order) {
     P = 1 << 30;
   } else {
     long target = (long)sm_count() * 32;  // warps wanted in flight
     long p = ((long)n + target - 1) / target;
     P = (int)(p < 64 ? 64 : p > 4096 ? 4096 : p);
-    if ((long)k >= target) P = 1 << 30;
+    // many centroids: the short-segment path below takes the iterations whose clusters are all
+    // small (strict order); the general path only runs when a cluster exceeds kSegLimit -- the first
+    // iteration after a random-point initialisation: 12 860 points in one cluster at BASELINE
+    // configs[3] -- and then walks such clusters in pieces instead of one warp per cluster (9 ms)
+    if ((long)k >= target) P = kSegLimit;
+    many = (long)k >= target;
   }
   // short segments (many centroids): one-pass scatter + per-segment sort; the general path is
   // still launched behind it, guarded on the device by the largest cluster size
-  const bool fast = n > 0 && k >= 1024 && (long)n / k <= SG_AVG && P >= (1 << 30) &&
+  const bool fast = n > 0 && k >= 1024 && (long)n / k <= SG_AVG && (exact_order || many) &&
                     !getenv("YAEL_B200_KMEANS_GENERAL_UPDATE");
   const int nblocks = (int)(((long)n + RS_BLOCK - 1) / RS_BLOCK);
   int passes = 1;
@@ -602,6 +613,7 @@ extern "C" int yb_kmeans_accumulate(int d, int n, int k, const float *v, const i
     k_scatter_ids<<<8 * sm_count(), 256, 0, st>>>(assign, n, k, seg_start, cursor, order, maxc);
     YB_LAUNCH_CHECK();
     const unsigned grid = (unsigned)((k + SG_WARPS - 1) / SG_WARPS);
+    ProfScope pseg(18, st);  // the row stream alone (the update's dominant kernel)
     if (vec && d <= 128)
       k_segsum_sorted<4, 1><<<grid, 32 * SG_WARPS, 0, st>>>(d, n, v, order, seg_start, k, sums, maxc);
     else if (vec)
