@@ -255,3 +255,41 @@ def test_kmeans_accumulate_short_segments_bit_exact(n, k, d, skew):
     assert dq.get()[0] == pytest.approx(float(dis.astype(np.float64).sum()), rel=1e-12)
     for a in (dv, da, dd, ds, dn, dq):
         a.free()
+
+
+@pytest.mark.parametrize("n,k,d,skew", [(600000, 8192, 128, 40000), (600000, 8192, 64, 0)])
+def test_kmeans_accumulate_default_mode_splits_only_long_clusters(n, k, d, skew):
+    """Default (non-exact) mode with many centroids: clusters of at most 2048 points are summed in the
+    reference's strict point order (bit-identical); a longer cluster -- the first iteration after a
+    random-point initialisation has one of 12 860 points at BASELINE configs[3] -- is walked in
+    2048-row pieces by the general path, so its sums carry the rounding of that grouping (checked
+    against float64 at the scale of FP32 accumulation error)."""
+    L = yael_b200.lib()
+    r = rs(n + k + d + skew)
+    v = r.rand(n, d).astype(np.float32)
+    assign = r.randint(0, k, n).astype(np.int32)
+    if skew:
+        assign[r.permutation(n)[:skew]] = 7
+    dis = r.rand(n).astype(np.float32)
+    dv, da, dd = DevArray(v), DevArray(assign), DevArray(dis)
+    ds = DevArray(shape=(k, d), dtype=np.float32)
+    dn = DevArray(shape=(k,), dtype=np.int32)
+    dq = DevArray(shape=(1,), dtype=np.float64)
+    rc = L.yb_kmeans_accumulate(d, n, k, dv.ptr, da.ptr, dd.ptr, ds.ptr, dn.ptr, dq.ptr, 0, None)
+    assert rc == 0, L.yb_last_error()
+    L.yb_sync(None)
+    got, cnt = ds.get(), dn.get()
+    want = np.zeros((k, d), np.float32)
+    np.add.at(want, assign, v)
+    assert np.array_equal(cnt, np.bincount(assign, minlength=k))
+    small = cnt <= 2048
+    assert np.array_equal(got[small], want[small])
+    if skew:
+        assert (~small).sum() == 1 and cnt[7] > 2048
+        exact = v[assign == 7].astype(np.float64).sum(0)
+        # strict-order FP32 and pieced FP32 both sit within the accumulation error of the exact sums
+        tol = cnt[7] * 2.0 ** -24 * np.abs(exact) * 4
+        assert (np.abs(got[7] - exact) <= tol).all()
+        assert (np.abs(want[7] - exact) <= tol).all()
+    for a in (dv, da, dd, ds, dn, dq):
+        a.free()
